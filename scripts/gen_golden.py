@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""Generate the committed parity fixtures under tests/golden/ by running the UNMODIFIED
+reference (imported read-only from /root/reference with stubbed I/O deps, see
+oracle/refimport.py) on seeded inputs.  Runs only in the build container.
+
+    python scripts/gen_golden.py
+
+Fixtures
+  ckpt_att2s_v3.npz    the shipped v3 checkpoint's 30 tensors (the model the path is defined on)
+  ckpt_aggr_v2p.npz    the shipped aggregate checkpoint's 13 tensors ("module." prefix kept)
+  att2s_synth.npz      256 synthetic sites (config-2 generator) + explicit h0 -> logits, probs
+  att2s_edge.npz       edge cases: n=1, n=3 (ragged tail), all-'N' kmers, huge kinetics, npass 0/200,
+                       zero h0; each case -> logits, probs
+  att2s_seeded.npz     reference default behaviour: torch.manual_seed(1234) then forward (h0 drawn by
+                       the reference itself, strand 1 then strand 2) -> the h0 stream + outputs
+  att2s_batchloop.npz  reference _call_mods2s over 1100 sites with batch_size=512 (3 batches incl. a
+                       ragged tail), torch.manual_seed(1234): per-site (holeid, loc, prob_1_norm)
+  aggr_synth.npz       1500 synthetic pileup sites -> windows, h0, raw outputs, clipped+rounded probs
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import refimport  # noqa: E402
+from ccsmeth_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save_ckpts():
+    sd = torch.load(refimport.V3_CKPT, map_location="cpu")
+    np.savez_compressed(os.path.join(OUT, "ckpt_att2s_v3.npz"), **{k: v.numpy() for k, v in sd.items()})
+    sd = torch.load(refimport.AGGR_CKPT, map_location="cpu")
+    np.savez_compressed(os.path.join(OUT, "ckpt_aggr_v2p.npz"), **{k: v.numpy() for k, v in sd.items()})
+
+
+def run_ref(model, b, h0_f, h0_r):
+    args = synth.to_forward_args(b)
+    with refimport.fixed_h0(model, [h0_f.clone().requires_grad_(True), h0_r.clone().requires_grad_(True)]):
+        logits, probs = model(*args)
+    return logits.detach().numpy(), probs.detach().numpy()
+
+
+def gen_att2s():
+    torch.set_num_threads(8)
+    m = refimport.load_ref_att2s()
+
+    # --- synthetic, explicit h0
+    b = synth.make_batch(256, seed=synth.SEED)
+    logits, probs = run_ref(m, b, b["h0_f"], b["h0_r"])
+    np.savez_compressed(os.path.join(OUT, "att2s_synth.npz"),
+                        **{k: v.numpy() for k, v in b.items()}, logits=logits, probs=probs)
+    print("att2s_synth: prob1 mean %.4f" % probs[:, 1].mean())
+
+    # --- edge cases
+    edge = {}
+    cases = {}
+    b1 = synth.make_batch(1, seed=7)
+    cases["n1"] = b1
+    b3 = synth.make_batch(3, seed=8)
+    cases["n3"] = b3
+    bn = synth.make_batch(5, seed=9)
+    bn["kmer"][:] = 4.0
+    bn["kmer2"][:] = 4.0
+    cases["allN"] = bn
+    bk = synth.make_batch(6, seed=10)
+    bk["ipd"][:, ::3] = 21.89
+    bk["pw"][:, 1::4] = 17.33
+    bk["ipd2"][:, 5] = -1.67
+    bk["kpass"][:] = 0.0
+    bk["kpass2"][:] = 200.0
+    cases["extreme"] = bk
+    bz = synth.make_batch(4, seed=11)
+    bz["h0_f"].zero_()
+    bz["h0_r"].zero_()
+    cases["zeroh0"] = bz
+    bf = synth.make_batch(2, seed=12)
+    bf["kmer"] = bf["kmer"] + 0.7  # float codes are truncated by .int() (models.py:91)
+    cases["fraccode"] = bf
+    for name, bb in cases.items():
+        logits, probs = run_ref(m, bb, bb["h0_f"], bb["h0_r"])
+        for k, v in bb.items():
+            edge[f"{name}.{k}"] = v.numpy()
+        edge[f"{name}.logits"] = logits
+        edge[f"{name}.probs"] = probs
+    np.savez_compressed(os.path.join(OUT, "att2s_edge.npz"), **edge)
+
+    # --- reference default: seeded randn h0 drawn by the reference itself
+    b = synth.make_batch(64, seed=21, with_h0=False)
+    torch.manual_seed(1234)
+    logits, probs = m(*synth.to_forward_args(b))
+    torch.manual_seed(1234)
+    h0_f = torch.randn(6, 64, 256)
+    h0_r = torch.randn(6, 64, 256)
+    np.savez_compressed(os.path.join(OUT, "att2s_seeded.npz"),
+                        **{k: v.numpy() for k, v in b.items()},
+                        h0_f=h0_f.numpy(), h0_r=h0_r.numpy(),
+                        logits=logits.detach().numpy(), probs=probs.detach().numpy(), tseed=1234)
+
+    # --- the batch loop: reference _call_mods2s with batch_size 512 over 1100 sites
+    ref = refimport.import_reference()
+    import ccsmeth.call_modifications as rcm
+    n = 1100
+    b = synth.make_batch(n, seed=33, with_h0=False)
+    code2base = "ACGTN"
+    feature_list = []
+    for i in range(n):
+        fk = "".join(code2base[int(c)] for c in b["kmer"][i])
+        rk = "".join(code2base[int(c)] for c in b["kmer2"][i])
+        feature_list.append((".", -1, ".", "hole%d" % (i // 100), i * 7 + 3,
+                             fk, int(b["kpass"][i, 0]), b["ipd"][i].double().numpy(), ".",
+                             b["pw"][i].double().numpy(), ".", ".", ".",
+                             rk, int(b["kpass2"][i, 0]), b["ipd2"][i].double().numpy(), ".",
+                             b["pw2"][i].double().numpy(), ".", ".", ".", 1))
+    fb = rcm._batch_feature_list2s(feature_list)
+    torch.manual_seed(1234)
+    pred, nb = rcm._call_mods2s(fb, m, 512, 0)
+    np.savez_compressed(os.path.join(OUT, "att2s_batchloop.npz"),
+                        **{k: v.numpy() for k, v in b.items()},
+                        holeids=np.array([p[0] for p in pred]), locs=np.array([p[1] for p in pred]),
+                        prob1=np.array([p[2] for p in pred], dtype=np.float32),
+                        batch_num=nb, batch_size=512, tseed=1234)
+    print("att2s_batchloop: %d preds in %d batches" % (len(pred), nb))
+
+
+def gen_aggr():
+    m = refimport.load_ref_aggr()
+    import ccsmeth.call_mods_freq_bam as rfb
+    n = 1500
+    pos, histos, h0 = synth.make_aggr_batch(n, seed=synth.SEED)
+    # direct forward with explicit h0 on materialised windows
+    from oracle import aggr_numpy
+    pm, hm = aggr_numpy.build_windows(pos, list(histos))
+    with refimport.fixed_h0(m, [h0.clone().requires_grad_(True)]):
+        raw = m(torch.tensor(pm, dtype=torch.float), torch.tensor(np.array(hm), dtype=torch.float))
+    # the reference loop itself (batches of 1024, seeded randn h0)
+    torch.manual_seed(1234)
+    probs = rfb._cal_modfreq_in_aggregate_mode(pos, list(histos), m, 11, False)
+    torch.manual_seed(1234)
+    h0_b0 = torch.randn(2, 1024, 32)
+    h0_b1 = torch.randn(2, n - 1024, 32)
+    np.savez_compressed(os.path.join(OUT, "aggr_synth.npz"), pos=pos, histos=histos, h0=h0.numpy(),
+                        pos_mat=pm, raw=raw.detach().numpy(),
+                        loop_probs=np.array(probs, dtype=np.float32),
+                        loop_h0_b0=h0_b0.numpy(), loop_h0_b1=h0_b1.numpy(), tseed=1234)
+    print("aggr_synth: raw mean %.4f" % raw.mean().item())
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    save_ckpts()
+    gen_att2s()
+    gen_aggr()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,96 @@
+"""The oracle (numpy restatement + torch port) pinned against fixtures generated from the
+UNMODIFIED reference (scripts/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import att2s_numpy, aggr_numpy, torch_port
+
+FEATS = ("kmer", "kpass", "ipd", "pw", "kmer2", "kpass2", "ipd2", "pw2")
+EDGE_CASES = ("n1", "n3", "allN", "extreme", "zeroh0", "fraccode")
+
+
+def _np_forward(ckpt, g, pfx="", dtype=np.float64):
+    return att2s_numpy.forward(ckpt, *[g[pfx + k] for k in FEATS], g[pfx + "h0_f"], g[pfx + "h0_r"], dtype=dtype)
+
+
+def test_numpy_oracle_matches_reference_synth(ckpt_att2s, golden_synth):
+    logits, probs = _np_forward(ckpt_att2s, golden_synth)
+    assert np.abs(logits - golden_synth["logits"]).max() < 2e-5
+    assert np.abs(probs - golden_synth["probs"]).max() < 5e-6
+
+
+def test_numpy_oracle_fp32_matches_reference_synth(ckpt_att2s, golden_synth):
+    _, probs = _np_forward(ckpt_att2s, golden_synth, dtype=np.float32)
+    assert np.abs(probs - golden_synth["probs"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("case", EDGE_CASES)
+def test_numpy_oracle_edge_cases(ckpt_att2s, golden_edge, case):
+    logits, probs = _np_forward(ckpt_att2s, golden_edge, pfx=case + ".")
+    assert logits.shape == golden_edge[case + ".logits"].shape
+    assert np.abs(probs - golden_edge[case + ".probs"]).max() < 5e-6
+
+
+def test_numpy_oracle_seeded_h0_stream(ckpt_att2s, golden_seeded):
+    # the reference draws h0 itself: strand 1 then strand 2 from torch's CPU generator
+    torch.manual_seed(int(golden_seeded["tseed"]))
+    h0_f = torch.randn(6, 64, 256).numpy()
+    h0_r = torch.randn(6, 64, 256).numpy()
+    assert np.array_equal(h0_f, golden_seeded["h0_f"]) and np.array_equal(h0_r, golden_seeded["h0_r"])
+    g = dict(golden_seeded)
+    _, probs = _np_forward(ckpt_att2s, g)
+    assert np.abs(probs - golden_seeded["probs"]).max() < 5e-6
+
+
+def test_torch_port_matches_reference(ckpt_att2s, golden_synth):
+    m = torch_port.load_numpy_state(torch_port.Att2sPort(), ckpt_att2s)
+    t = {k: torch.from_numpy(golden_synth[k]) for k in FEATS + ("h0_f", "h0_r")}
+    logits, probs = m(*[t[k] for k in FEATS], t["h0_f"], t["h0_r"])
+    # same ATen kernels as the reference -> (near) bit-identical
+    assert np.abs(probs.detach().numpy() - golden_synth["probs"]).max() < 1e-6
+
+
+def test_batchloop_golden_is_reproducible_from_h0_stream(ckpt_att2s, golden_batchloop):
+    """Reference _call_mods2s semantics: for each 512-slice in order draw h0_f then h0_r; output
+    round(p1/(p0+p1), 6)  (reference call_modifications.py:177-224)."""
+    g = golden_batchloop
+    n, bs = g["kmer"].shape[0], int(g["batch_size"])
+    torch.manual_seed(int(g["tseed"]))
+    out = []
+    for s in range(0, n, bs):
+        e = min(n, s + bs)
+        h0_f = torch.randn(6, e - s, 256).numpy()
+        h0_r = torch.randn(6, e - s, 256).numpy()
+        _, probs = att2s_numpy.forward(ckpt_att2s, *[g[k][s:e] for k in FEATS], h0_f, h0_r, dtype=np.float32)
+        out.append(att2s_numpy.prob1_norm(probs))
+    out = np.concatenate(out)
+    assert int(g["batch_num"]) == 3 and len(out) == n
+    assert np.abs(out - g["prob1"]).max() < 2e-5
+
+
+def test_aggr_numpy_oracle(ckpt_aggr, golden_aggr):
+    g = golden_aggr
+    pm, hm = aggr_numpy.build_windows(g["pos"], list(g["histos"]))
+    assert np.array_equal(pm, g["pos_mat"])
+    raw = aggr_numpy.forward(ckpt_aggr, pm.astype(np.float32), hm.astype(np.float32), g["h0"])
+    assert np.abs(raw - g["raw"]).max() < 1e-5
+
+
+def test_aggr_loop_golden(ckpt_aggr, golden_aggr):
+    g = golden_aggr
+    pm, hm = aggr_numpy.build_windows(g["pos"], list(g["histos"]))
+    outs = []
+    for s, h0 in ((0, g["loop_h0_b0"]), (1024, g["loop_h0_b1"])):
+        e = s + h0.shape[1]
+        outs.append(aggr_numpy.postprocess(aggr_numpy.forward(ckpt_aggr, pm[s:e].astype(np.float32),
+                                                              hm[s:e].astype(np.float32), h0))[:, 0])
+    assert np.abs(np.concatenate(outs) - g["loop_probs"]).max() < 2e-6
+
+
+def test_aggr_torch_port(ckpt_aggr, golden_aggr):
+    g = golden_aggr
+    m = torch_port.load_numpy_state(torch_port.AggrPort(), ckpt_aggr)
+    pm, hm = aggr_numpy.build_windows(g["pos"], list(g["histos"]))
+    raw = m(torch.tensor(pm, dtype=torch.float), torch.tensor(np.array(hm), dtype=torch.float), torch.from_numpy(g["h0"]))
+    assert np.abs(raw.detach().numpy() - g["raw"]).max() < 1e-6
