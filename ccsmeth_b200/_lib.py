@@ -1,0 +1,123 @@
+"""ctypes binding of libccsm.so (C ABI declared in include/ccsm.h).
+
+The shared library is built in-tree (``ccsmeth_b200/libccsm.so``) by ``build()`` with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.  There is deliberately no CPU fallback: if the
+library is missing or fails to load, every product entry point raises.
+"""
+import ctypes
+import glob
+import os
+import shutil
+import subprocess
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libccsm.so")
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# error codes / enums (mirror include/ccsm.h)
+OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED, EKEY = 0, -1, -2, -3, -4, -5, -6
+KIND_ATT2S, KIND_AGGR = 0, 1
+PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x3": 3, "fp16": 4}
+FEAT_NPASS, FEAT_STDS, FEAT_SN, FEAT_MAP = 1, 2, 4, 8
+
+EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_create", "ccsm_destroy",
+           "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",
+           "ccsm_forward_att2s_host", "ccsm_forward_aggr", "ccsm_debug_last_rnn_out"]
+
+
+class CcsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libccsm error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("kind", "seq_len", "num_layers", "hidden", "num_classes", "n_vocab", "n_embed",
+                 "feat_flags", "precision", "device")]
+
+
+class Strand(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("kmer", "kpass", "ipd_means", "ipd_stds", "pw_means", "pw_stds", "sns", "maps")]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(INCLUDE, "*.h"))
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into ccsmeth_b200/libccsm.so for sm_100a (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", tmp] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
+    os.replace(tmp, LIB_PATH)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Returns the loaded library; raises if it is not built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a). ccsmeth_b200 has no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        lib.ccsm_abi_version.restype = ctypes.c_int
+        lib.ccsm_last_error.restype = ctypes.c_char_p
+        lib.ccsm_kernel_launches.restype = i64
+        lib.ccsm_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(Config)]
+        lib.ccsm_destroy.argtypes = [vp]
+        lib.ccsm_destroy.restype = None
+        lib.ccsm_set_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32]
+        lib.ccsm_finalize.argtypes = [vp]
+        lib.ccsm_set_precision.argtypes = [vp, i32]
+        lib.ccsm_forward_att2s.argtypes = [vp, i64, ctypes.POINTER(Strand), ctypes.POINTER(Strand), vp, vp, vp, vp, vp]
+        lib.ccsm_forward_att2s_host.argtypes = [vp, i64, ctypes.POINTER(Strand), ctypes.POINTER(Strand), vp, vp, vp, vp]
+        lib.ccsm_forward_aggr.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        lib.ccsm_debug_last_rnn_out.argtypes = [vp, vp, i64]
+        lib.ccsm_debug_last_rnn_out.restype = i64
+        for fn in ("ccsm_create", "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",
+                   "ccsm_forward_att2s_host", "ccsm_forward_aggr"):
+            getattr(lib, fn).restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise CcsmError(rc, load().ccsm_last_error().decode("utf-8", "replace"))
+
+
+def kernel_launches():
+    return int(load().ccsm_kernel_launches())

@@ -1,0 +1,394 @@
+// C-ABI layer of libccsm.so (declared in include/ccsm.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ccsm_internal.h"
+
+namespace ccsm {
+
+static thread_local char g_err[1024] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return CCSM_OK;
+  if (p) {
+    cudaError_t e = cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (e != cudaSuccess) {
+      set_error("cudaFree failed: %s", cudaGetErrorString(e));
+      return CCSM_ECUDA;
+    }
+  }
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? CCSM_ENOMEM : CCSM_ECUDA;
+  }
+  cap = bytes;
+  return CCSM_OK;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+static bool is_tc(int prec) { return prec != CCSM_PREC_FP32; }
+
+}  // namespace ccsm
+
+using namespace ccsm;
+
+extern "C" {
+
+int ccsm_abi_version(void) { return CCSM_ABI_VERSION; }
+const char* ccsm_last_error(void) { return g_err; }
+int64_t ccsm_kernel_launches(void) { return g_launches.load(); }
+
+int ccsm_create(ccsm_model** out, const ccsm_config* cfg) {
+  if (!out || !cfg) {
+    set_error("ccsm_create: null argument");
+    return CCSM_EINVAL;
+  }
+  *out = nullptr;
+  if (cfg->kind != CCSM_KIND_ATT2S && cfg->kind != CCSM_KIND_AGGR) {
+    set_error("ccsm_create: unknown kind %d", cfg->kind);
+    return CCSM_EINVAL;
+  }
+  if (cfg->seq_len < 1 || cfg->seq_len > 32 || (cfg->kind == CCSM_KIND_ATT2S && cfg->seq_len % 2 == 0)) {
+    // the reference requires an odd --seq_len (call_modifications.py:500-501)
+    set_error("ccsm_create: seq_len %d unsupported (odd, <= 32)", cfg->seq_len);
+    return CCSM_EINVAL;
+  }
+  if (cfg->num_layers < 1 || cfg->hidden < 1 || cfg->hidden % 16 != 0 || cfg->num_classes < 1 || cfg->num_classes > 4) {
+    set_error("ccsm_create: layers=%d hidden=%d classes=%d unsupported", cfg->num_layers, cfg->hidden, cfg->num_classes);
+    return CCSM_EINVAL;
+  }
+  if (cfg->precision < CCSM_PREC_FP32 || cfg->precision > CCSM_PREC_FP16) {
+    set_error("ccsm_create: unknown precision %d", cfg->precision);
+    return CCSM_EINVAL;
+  }
+  int ndev = 0;
+  CCSM_CUDA(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    set_error("ccsm_create: device %d not present (%d visible)", cfg->device, ndev);
+    return CCSM_EINVAL;
+  }
+  cudaDeviceProp prop;
+  CCSM_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error("ccsm_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
+              prop.major, prop.minor);
+    return CCSM_EUNSUPPORTED;
+  }
+  ccsm_model* m = new (std::nothrow) ccsm_model();
+  if (!m) return CCSM_ENOMEM;
+  m->cfg = *cfg;
+  if (cfg->kind == CCSM_KIND_ATT2S) {
+    m->strands = 2;
+    int feas = 2;  // ipd, pw  (reference models.py:39-47)
+    if (cfg->feat_flags & CCSM_FEAT_STDS) feas += 2;
+    if (cfg->feat_flags & CCSM_FEAT_NPASS) feas += 1;
+    if (cfg->feat_flags & CCSM_FEAT_SN) feas += 4;
+    if (cfg->feat_flags & CCSM_FEAT_MAP) feas += 1;
+    m->in_feat = cfg->n_embed + feas;
+  } else {
+    m->strands = 1;
+    m->in_feat = cfg->feat_flags + 1;  // bins + offset (reference models.py:639)
+    if (is_tc(cfg->precision)) {
+      // the aggregate model's K=21/32 contractions are not tensor-core shaped: fp32 FFMA only
+      m->cfg.precision = CCSM_PREC_FP32;
+    }
+  }
+  *out = m;
+  return CCSM_OK;
+}
+
+void ccsm_destroy(ccsm_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->cfg.device);
+  tc_release(m);
+  for (auto& l : m->fp32.layers) {
+    l.w_ih.release(); l.b_ih.release(); l.w_hh.release(); l.b_hh.release();
+  }
+  m->fp32.embed.release(); m->fp32.Wa.release(); m->fp32.Ua.release(); m->fp32.va.release();
+  m->fp32.fc_w.release(); m->fp32.fc_b.release();
+  Fp32Workspace& ws = m->ws32;
+  ws.x0.release(); ws.gi.release(); ws.gh.release(); ws.h.release(); ws.outA.release(); ws.outB.release(); ws.qa.release();
+  for (int i = 0; i < 2; ++i) {
+    m->stage_in[i].release();
+    m->stage_out[i].release();
+    if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
+    if (m->events[i]) cudaEventDestroy(m->events[i]);
+  }
+  delete m;
+}
+
+// expected shape of every state_dict key (reference models.py:33,52-64,644-654)
+static bool expected_shape(const ccsm_model* m, const std::string& key, std::vector<int64_t>& shp) {
+  const int64_t H = m->cfg.hidden, C = m->cfg.num_classes;
+  if (key == "embed.weight" && m->cfg.kind == CCSM_KIND_ATT2S) { shp = {m->cfg.n_vocab, m->cfg.n_embed}; return true; }
+  if (key == "_att3.Wa.weight" || key == "_att3.Ua.weight") { shp = {H, 2 * H}; return true; }
+  if (key == "_att3.va.weight") { shp = {1, H}; return true; }
+  if (key == "fc1.weight") { shp = {C, 2 * H * m->strands}; return true; }
+  if (key == "fc1.bias") { shp = {C}; return true; }
+  for (int l = 0; l < m->cfg.num_layers; ++l)
+    for (int d = 0; d < 2; ++d) {
+      std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+      int64_t K = l == 0 ? m->in_feat : 2 * H;
+      if (key == "rnn.weight_ih" + sfx) { shp = {3 * H, K}; return true; }
+      if (key == "rnn.weight_hh" + sfx) { shp = {3 * H, H}; return true; }
+      if (key == "rnn.bias_ih" + sfx || key == "rnn.bias_hh" + sfx) { shp = {3 * H}; return true; }
+    }
+  return false;
+}
+
+int ccsm_set_weight(ccsm_model* m, const char* key_c, const float* host, const int64_t* shape, int32_t ndim) {
+  if (!m || !key_c || !host || !shape || ndim < 1 || ndim > 4) {
+    set_error("ccsm_set_weight: bad argument");
+    return CCSM_EINVAL;
+  }
+  std::string key(key_c);
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);  // DDP prefix (reference call_modifications.py:350-358)
+  std::vector<int64_t> want;
+  if (!expected_shape(m, key, want)) {
+    set_error("ccsm_set_weight: unexpected key '%s' for this model", key.c_str());
+    return CCSM_EKEY;
+  }
+  std::vector<int64_t> got(shape, shape + ndim);
+  if (got != want) {
+    std::string a, b;
+    for (auto v : got) a += std::to_string(v) + ",";
+    for (auto v : want) b += std::to_string(v) + ",";
+    set_error("ccsm_set_weight: size mismatch for %s: got (%s) expected (%s)", key.c_str(), a.c_str(), b.c_str());
+    return CCSM_EKEY;
+  }
+  int64_t numel = 1;
+  for (auto v : got) numel *= v;
+  HostTensor t;
+  t.shape = got;
+  t.data.assign(host, host + numel);
+  m->w[key] = std::move(t);
+  m->finalized = false;
+  return CCSM_OK;
+}
+
+static int check_complete(ccsm_model* m) {
+  std::vector<std::string> keys = {"_att3.Wa.weight", "_att3.Ua.weight", "_att3.va.weight", "fc1.weight", "fc1.bias"};
+  if (m->cfg.kind == CCSM_KIND_ATT2S) keys.push_back("embed.weight");
+  for (int l = 0; l < m->cfg.num_layers; ++l)
+    for (int d = 0; d < 2; ++d) {
+      std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+      for (const char* p : {"rnn.weight_ih", "rnn.weight_hh", "rnn.bias_ih", "rnn.bias_hh"}) keys.push_back(p + sfx);
+    }
+  for (auto& k : keys)
+    if (!m->w.count(k)) {
+      set_error("ccsm_finalize: missing key '%s'", k.c_str());
+      return CCSM_EKEY;
+    }
+  return CCSM_OK;
+}
+
+int ccsm_finalize(ccsm_model* m) {
+  if (!m) {
+    set_error("ccsm_finalize: null model");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  CCSM_TRY(check_complete(m));
+  CCSM_TRY(fp32_upload_weights(m));  // always kept: cross-check path + attention/head fallback
+  if (is_tc(m->cfg.precision)) CCSM_TRY(tc_upload_weights(m));
+  m->finalized = true;
+  return CCSM_OK;
+}
+
+int ccsm_set_precision(ccsm_model* m, int32_t precision) {
+  if (!m || precision < CCSM_PREC_FP32 || precision > CCSM_PREC_FP16) {
+    set_error("ccsm_set_precision: bad argument");
+    return CCSM_EINVAL;
+  }
+  if (m->cfg.kind == CCSM_KIND_AGGR) precision = CCSM_PREC_FP32;
+  if (precision == m->cfg.precision) return CCSM_OK;
+  m->cfg.precision = precision;
+  if (m->finalized && is_tc(precision)) {
+    CCSM_CUDA(cudaSetDevice(m->cfg.device));
+    CCSM_TRY(tc_upload_weights(m));
+  }
+  return CCSM_OK;
+}
+
+static int check_strand(const ccsm_model* m, const ccsm_strand* s, const char* which) {
+  const int f = m->cfg.feat_flags;
+  if (!s || !s->kmer || !s->ipd_means || !s->pw_means || ((f & CCSM_FEAT_NPASS) && !s->kpass) ||
+      ((f & CCSM_FEAT_STDS) && (!s->ipd_stds || !s->pw_stds)) || ((f & CCSM_FEAT_SN) && !s->sns) ||
+      ((f & CCSM_FEAT_MAP) && !s->maps)) {
+    set_error("forward: %s strand is missing a tensor required by feat_flags=%d", which, f);
+    return CCSM_EINVAL;
+  }
+  return CCSM_OK;
+}
+
+int ccsm_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, const float* h0_fwd,
+                       const float* h0_rev, float* logits, float* probs, void* stream) {
+  if (!m || m->cfg.kind != CCSM_KIND_ATT2S) {
+    set_error("ccsm_forward_att2s: not an att2s model");
+    return CCSM_EINVAL;
+  }
+  if (!m->finalized) {
+    set_error("ccsm_forward_att2s: model not finalized");
+    return CCSM_ESTATE;
+  }
+  if (n < 0) {
+    set_error("ccsm_forward_att2s: n < 0");
+    return CCSM_EINVAL;
+  }
+  if (n == 0) return CCSM_OK;  // empty batch: nothing to do (the reference skips it, call_modifications.py:200)
+  CCSM_TRY(check_strand(m, fwd, "forward"));
+  CCSM_TRY(check_strand(m, rev, "reverse"));
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (is_tc(m->cfg.precision)) return tc_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
+  return fp32_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
+}
+
+int ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
+                      void* stream) {
+  if (!m || m->cfg.kind != CCSM_KIND_AGGR) {
+    set_error("ccsm_forward_aggr: not an aggregate model");
+    return CCSM_EINVAL;
+  }
+  if (!m->finalized) {
+    set_error("ccsm_forward_aggr: model not finalized");
+    return CCSM_ESTATE;
+  }
+  if (n < 0 || (n > 0 && (!offsets || !histos || !out))) {
+    set_error("ccsm_forward_aggr: bad argument");
+    return CCSM_EINVAL;
+  }
+  if (n == 0) return CCSM_OK;
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  return fp32_forward_aggr(m, n, offsets, histos, h0, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer entry: H2D staging -> forward -> D2H, pipelined over chunks with two staging buffers.
+// streams[0] copies in, streams[1] computes and copies the (tiny) results out.
+int ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
+                            const float* h0_fwd, const float* h0_rev, float* logits, float* probs) {
+  if (!m || m->cfg.kind != CCSM_KIND_ATT2S) {
+    set_error("ccsm_forward_att2s_host: not an att2s model");
+    return CCSM_EINVAL;
+  }
+  if (!m->finalized) {
+    set_error("ccsm_forward_att2s_host: model not finalized");
+    return CCSM_ESTATE;
+  }
+  if (n < 0) {
+    set_error("ccsm_forward_att2s_host: n < 0");
+    return CCSM_EINVAL;
+  }
+  if (n == 0) return CCSM_OK;
+  CCSM_TRY(check_strand(m, fwd, "forward"));
+  CCSM_TRY(check_strand(m, rev, "reverse"));
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  for (int i = 0; i < 2; ++i) {
+    if (!m->streams[i]) CCSM_CUDA(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
+    if (!m->events[i]) CCSM_CUDA(cudaEventCreateWithFlags(&m->events[i], cudaEventDisableTiming));
+  }
+  const int L = m->cfg.seq_len, H = m->cfg.hidden, NL = m->cfg.num_layers, C = m->cfg.num_classes;
+  const int64_t chunk = n < 32768 ? n : 32768;
+  // staging layout per buffer (floats): 2 strands x [kmer,kpass,ipd,ipd_sd,pw,pw_sd,maps](L each) + sns(4) + h0 x2
+  const int64_t per_strand = (int64_t)7 * L + 4;
+  const int64_t h0_floats = (int64_t)2 * NL * H;
+  const size_t in_bytes = (size_t)chunk * (2 * per_strand + 2 * h0_floats) * sizeof(float);
+  const size_t out_bytes = (size_t)chunk * 2 * C * sizeof(float);
+  cudaEvent_t done[2];
+  for (int i = 0; i < 2; ++i) {
+    CCSM_TRY(m->stage_in[i].reserve(in_bytes));
+    CCSM_TRY(m->stage_out[i].reserve(out_bytes));
+    CCSM_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
+  cudaStream_t s_in = m->streams[0], s_cmp = m->streams[1];
+  int rc = CCSM_OK;
+  int64_t ci = 0;
+  for (int64_t s0 = 0; s0 < n && rc == CCSM_OK; s0 += chunk, ++ci) {
+    const int b = (int)(ci & 1);
+    const int64_t cn = (n - s0) < chunk ? (n - s0) : chunk;
+    float* base = m->stage_in[b].as<float>();
+    if (ci >= 2) cudaStreamWaitEvent(s_in, done[b], 0);  // buffer b is free once chunk ci-2 finished
+    ccsm_strand dev[2];
+    const ccsm_strand* src[2] = {fwd, rev};
+    float* cur = base;
+    auto stage = [&](const float* hp, int64_t per) -> const float* {
+      if (!hp) return nullptr;
+      float* d = cur;
+      cur += cn * per;
+      cudaMemcpyAsync(d, hp + s0 * per, (size_t)cn * per * sizeof(float), cudaMemcpyHostToDevice, s_in);
+      return d;
+    };
+    for (int s = 0; s < 2; ++s) {
+      dev[s].kmer = stage(src[s]->kmer, L);
+      dev[s].kpass = stage(src[s]->kpass, L);
+      dev[s].ipd_means = stage(src[s]->ipd_means, L);
+      dev[s].ipd_stds = (m->cfg.feat_flags & CCSM_FEAT_STDS) ? stage(src[s]->ipd_stds, L) : nullptr;
+      dev[s].pw_means = stage(src[s]->pw_means, L);
+      dev[s].pw_stds = (m->cfg.feat_flags & CCSM_FEAT_STDS) ? stage(src[s]->pw_stds, L) : nullptr;
+      dev[s].sns = (m->cfg.feat_flags & CCSM_FEAT_SN) ? stage(src[s]->sns, 4) : nullptr;
+      dev[s].maps = (m->cfg.feat_flags & CCSM_FEAT_MAP) ? stage(src[s]->maps, L) : nullptr;
+    }
+    const float* h0s[2] = {h0_fwd, h0_rev};
+    const float* dh0[2] = {nullptr, nullptr};
+    for (int s = 0; s < 2; ++s) {
+      if (!h0s[s]) continue;
+      float* d = cur;
+      cur += cn * h0_floats;
+      // (2*layers, n, H) -> (2*layers, cn, H): one strided copy
+      cudaMemcpy2DAsync(d, (size_t)cn * H * sizeof(float), h0s[s] + s0 * H, (size_t)n * H * sizeof(float),
+                        (size_t)cn * H * sizeof(float), 2 * NL, cudaMemcpyHostToDevice, s_in);
+      dh0[s] = d;
+    }
+    cudaEventRecord(m->events[b], s_in);
+    cudaStreamWaitEvent(s_cmp, m->events[b], 0);
+    float* dl = m->stage_out[b].as<float>();
+    float* dp = dl + cn * C;
+    rc = ccsm_forward_att2s(m, cn, &dev[0], &dev[1], dh0[0], dh0[1], dl, dp, s_cmp);
+    if (rc != CCSM_OK) break;
+    if (logits) cudaMemcpyAsync(logits + s0 * C, dl, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, s_cmp);
+    if (probs) cudaMemcpyAsync(probs + s0 * C, dp, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, s_cmp);
+    cudaEventRecord(done[b], s_cmp);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(s_in);
+  cudaError_t e2 = cudaStreamSynchronize(s_cmp);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
+  if (rc != CCSM_OK) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("ccsm_forward_att2s_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return CCSM_ECUDA;
+  }
+  return CCSM_OK;
+}
+
+int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap) {
+  if (!m || !host || !m->dbg_rnn_out) {
+    set_error("ccsm_debug_last_rnn_out: nothing recorded");
+    return CCSM_ESTATE;
+  }
+  int64_t nfl = m->dbg_rnn_out_floats < cap ? m->dbg_rnn_out_floats : cap;
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  CCSM_CUDA(cudaDeviceSynchronize());
+  CCSM_CUDA(cudaMemcpy(host, m->dbg_rnn_out, (size_t)nfl * sizeof(float), cudaMemcpyDeviceToHost));
+  return nfl;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Internal declarations shared by the C-ABI layer and the kernel files of libccsm.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ccsm.h"
+
+namespace ccsm {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define CCSM_CUDA(expr)                                                                        \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ccsm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CCSM_ECUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+#define CCSM_TRY(expr)          \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != CCSM_OK) return _r; \
+  } while (0)
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+// A device allocation that grows on demand (workspace sized lazily on larger n).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// fp32 (FFMA) path: weights in PyTorch (N, K) row-major layout, K zero-padded to a multiple of 16,
+// both directions of a layer stacked along N for the input projection.
+struct Fp32Layer {
+  int K = 0, Kpad = 0;
+  DevBuf w_ih;  // (2*3H, Kpad)
+  DevBuf b_ih;  // (2*3H)
+  DevBuf w_hh;  // (2, 3H, H)
+  DevBuf b_hh;  // (2, 3H)
+};
+
+struct Fp32Weights {
+  std::vector<Fp32Layer> layers;
+  DevBuf embed;        // (n_vocab, n_embed)
+  DevBuf Wa, Ua, va;   // (H, 2H), (H, 2H), (H)
+  DevBuf fc_w, fc_b;   // (classes, strands*2H), (classes)
+  bool ready = false;
+};
+
+struct Fp32Workspace {
+  int64_t rows_cap = 0;
+  DevBuf x0, gi, gh, h, outA, outB, qa;
+};
+
+struct TcState;  // tensor-core (tcgen05) path state, defined in tc_path.cu
+
+}  // namespace ccsm
+
+struct ccsm_model {
+  ccsm_config cfg{};
+  int strands = 2;    // 2 for att2s, 1 for aggr
+  int in_feat = 0;    // GRU layer-0 input width (att2s: n_embed + feas_ccs; aggr: bins + 1)
+  std::map<std::string, ccsm::HostTensor> w;
+  bool finalized = false;
+  ccsm::Fp32Weights fp32;
+  ccsm::Fp32Workspace ws32;
+  ccsm::TcState* tc = nullptr;
+  // host-entry staging
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t events[2] = {nullptr, nullptr};
+  ccsm::DevBuf stage_in[2], stage_out[2];
+  // debug: where the last layer-stack output of the most recent fp32 chunk lives
+  const float* dbg_rnn_out = nullptr;
+  int64_t dbg_rnn_out_floats = 0;
+};
+
+namespace ccsm {
+
+// ---- fp32 path (fp32_path.cu)
+int fp32_upload_weights(ccsm_model* m);
+int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
+                       const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st);
+int fp32_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
+                      float* out, cudaStream_t st);
+
+// ---- tensor-core path (tc_path.cu)
+int tc_upload_weights(ccsm_model* m);
+void tc_release(ccsm_model* m);
+int tc_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
+                     const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st);
+
+}  // namespace ccsm

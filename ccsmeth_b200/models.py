@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference model interface for the call_mods inference path.
+
+``ModelAttRNN`` / ``AggrAttRNN`` keep the reference's constructor arguments, ``state_dict`` keys and
+shapes, ``.cuda(device)`` / ``.eval()`` / ``get_model_type()`` and the 16-tensor ``forward`` ->
+``(logits, probs)`` contract (reference ccsmeth/models.py:17-150, 625-694), so the reference's call
+sites (call_modifications.py:316-369, 201-214; call_mods_freq_bam.py:317-342, 301) work unchanged.
+The arithmetic is NOT torch: ``forward`` hands raw device pointers to libccsm.so (include/ccsm.h),
+which launches the sm_100a kernels.  torch is used for parameter storage, device memory and streams.
+
+Extension over the reference: ``forward(..., h0=(h0_strand1, h0_strand2))``.  The reference draws the
+GRU initial state with ``torch.randn`` on every call (models.py:77-87), so parity is only defined
+with h0 as a shared explicit input.  ``h0=None`` reproduces the reference exactly: two
+``torch.randn(2*layers, n, hidden)`` draws from the CPU default generator, strand 1 then strand 2.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .utils.process_utils import N_VOCAB, NEMBED_BASE
+
+DEFAULT_PRECISION = os.environ.get("CCSMETH_B200_PRECISION", "fp32")
+
+
+class Attention(nn.Module):
+    """Parameter container with the reference's names (utils/attention.py:39-46); all bias-free."""
+
+    def __init__(self, query_size, key_size, hidden_size=128):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.Wa = nn.Linear(query_size, hidden_size, bias=False)
+        self.Ua = nn.Linear(key_size, hidden_size, bias=False)
+        self.va = nn.Linear(hidden_size, 1, bias=False)
+
+
+class _NativeModule(nn.Module):
+    """Owns the libccsm handle; re-packs weights whenever parameters or the device change."""
+
+    _kind = None
+
+    def _native_init(self, precision):
+        if precision not in _lib.PREC:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PREC))
+        self._precision = precision
+        self._handle = None
+        self._handle_key = None
+        self._dirty = True
+
+    # -- parameter / device changes invalidate the packed weights
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        # accept the DDP/DataParallel "module." prefix the reference strips on RuntimeError
+        # (call_modifications.py:350-358)
+        if state_dict and all(k.startswith("module.") for k in state_dict.keys()):
+            state_dict = type(state_dict)((k[7:], v) for k, v in state_dict.items())
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._dirty = True
+        return r
+
+    def _apply(self, fn, *a, **kw):
+        r = super()._apply(fn, *a, **kw)
+        self._dirty = True
+        return r
+
+    def set_precision(self, precision):
+        if precision not in _lib.PREC:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PREC))
+        if precision != self._precision:
+            self._precision = precision
+            if self._handle is not None and not self._dirty:
+                _lib.check(_lib.load().ccsm_set_precision(self._handle, _lib.PREC[precision]))
+        return self
+
+    def get_precision(self):
+        return self._precision
+
+    def _device_index(self):
+        p = next(self.parameters())
+        if p.is_cuda:
+            return p.device.index if p.device.index is not None else torch.cuda.current_device()
+        if not torch.cuda.is_available():
+            raise RuntimeError("ccsmeth_b200 needs a CUDA device (sm_100a): there is no CPU fallback path")
+        d = self.device if isinstance(self.device, int) else 0
+        return d
+
+    def _config(self, dev):
+        raise NotImplementedError
+
+    def _ensure_handle(self):
+        lib = _lib.load()
+        dev = self._device_index()
+        key = (dev,)
+        if self._handle is not None and (key != self._handle_key):
+            lib.ccsm_destroy(self._handle)
+            self._handle = None
+        if self._handle is None:
+            cfg = self._config(dev)
+            h = ctypes.c_void_p()
+            _lib.check(lib.ccsm_create(ctypes.byref(h), ctypes.byref(cfg)))
+            self._handle, self._handle_key, self._dirty = h, key, True
+        if self._dirty:
+            _lib.check(lib.ccsm_set_precision(self._handle, _lib.PREC[self._precision]))
+            for k, v in self.state_dict().items():
+                a = np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy())
+                shp = (ctypes.c_int64 * a.ndim)(*a.shape)
+                _lib.check(lib.ccsm_set_weight(self._handle, k.encode(), a.ctypes.data_as(ctypes.c_void_p), shp, a.ndim))
+            _lib.check(lib.ccsm_finalize(self._handle))
+            self._dirty = False
+        return self._handle, dev
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.load().ccsm_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def get_model_type(self):
+        return self.model_type
+
+
+def _dev_f32(t, device, shape=None):
+    t = torch.as_tensor(t)
+    if t.dtype != torch.float32 or t.device != device:
+        t = t.to(device=device, dtype=torch.float32)
+    if shape is not None:
+        t = t.reshape(shape)
+    return t.contiguous()
+
+
+class ModelAttRNN(_NativeModule):
+    """Drop-in for the reference ``ModelAttRNN`` with ``model_type="attbigru2s"`` (models.py:17-150)."""
+
+    def __init__(self, seq_len=21, num_layers=3, num_classes=2, dropout_rate=0.5, hidden_size=256,
+                 is_npass=True, is_sn=False, is_map=False, is_stds=False, model_type="attbigru2s", device=0,
+                 precision=None):
+        super().__init__()
+        if model_type != "attbigru2s":
+            # the reference also builds an LSTM variant (models.py:48-51); no checkpoint ships for it and
+            # it is outside this path's scope
+            raise ValueError("--model_type not set right! (ccsmeth_b200 implements attbigru2s)")
+        self.model_type = model_type
+        self.device = device
+        self.seq_len, self.num_layers, self.num_classes, self.hidden_size = seq_len, num_layers, num_classes, hidden_size
+        self.n_embed = NEMBED_BASE
+        self.is_stds, self.is_npass, self.is_sn, self.is_map = is_stds, is_npass, is_sn, is_map
+        self.feas_ccs = 2 + (2 if is_stds else 0) + (1 if is_npass else 0) + (4 if is_sn else 0) + (1 if is_map else 0)
+        self.rnn_cell = "gru"
+        # parameter containers, never called: same names/shapes as the reference state_dict
+        self.embed = nn.Embedding(N_VOCAB, self.n_embed)
+        self.rnn = nn.GRU(self.n_embed + self.feas_ccs, hidden_size, num_layers, dropout=dropout_rate,
+                          batch_first=True, bidirectional=True)
+        self._att3 = Attention(hidden_size * 2, hidden_size * 2, hidden_size)
+        self.dropout1 = nn.Dropout(p=dropout_rate)  # identity at inference; kept for interface parity
+        self.fc1 = nn.Linear(hidden_size * 2 * 2, num_classes)
+        self.init_weights()
+        self.requires_grad_(False)
+        self._native_init(precision or DEFAULT_PRECISION)
+
+    def init_weights(self):  # reference models.py:71-75
+        nn.init.uniform_(self.embed.weight, -0.1, 0.1)
+        nn.init.zeros_(self.fc1.bias)
+        nn.init.uniform_(self.fc1.weight, -0.1, 0.1)
+
+    def init_hidden(self, batch_size, num_layers, hidden_size):
+        """Same draw as the reference (models.py:77-87): CPU default generator, then moved to the device."""
+        return torch.randn(num_layers * 2, batch_size, hidden_size)
+
+    def _config(self, dev):
+        flags = (_lib.FEAT_NPASS if self.is_npass else 0) | (_lib.FEAT_STDS if self.is_stds else 0) | \
+                (_lib.FEAT_SN if self.is_sn else 0) | (_lib.FEAT_MAP if self.is_map else 0)
+        return _lib.Config(_lib.KIND_ATT2S, self.seq_len, self.num_layers, self.hidden_size, self.num_classes,
+                           N_VOCAB, self.n_embed, flags, _lib.PREC[self._precision], dev)
+
+    def _strand(self, device, n, kmer, kpass, ipd_means, ipd_stds, pw_means, pw_stds, sns, maps, keep):
+        L = self.seq_len
+        s = _lib.Strand()
+
+        def put(name, t, shape):
+            t = _dev_f32(t, device, shape)
+            keep.append(t)
+            setattr(s, name, t.data_ptr())
+
+        put("kmer", kmer, (n, L))
+        put("ipd_means", ipd_means, (n, L))
+        put("pw_means", pw_means, (n, L))
+        if self.is_npass:
+            put("kpass", kpass, (n, L))
+        if self.is_stds:
+            put("ipd_stds", ipd_stds, (n, L))
+            put("pw_stds", pw_stds, (n, L))
+        if self.is_sn:
+            put("sns", sns, (n, 4))
+        if self.is_map:
+            put("maps", maps, (n, L))
+        return s
+
+    def forward(self, kmer, kpass, ipd_means, ipd_stds, pw_means, pw_stds, sns, maps,
+                kmer2, kpass2, ipd_means2, ipd_stds2, pw_means2, pw_stds2, sns2, maps2, h0=None):
+        handle, dev = self._ensure_handle()
+        device = torch.device("cuda", dev)
+        n = int(torch.as_tensor(kmer).reshape(-1, self.seq_len).shape[0])
+        if h0 is None:
+            h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
+                  self.init_hidden(n, self.num_layers, self.hidden_size))
+        keep = []
+        fwd = self._strand(device, n, kmer, kpass, ipd_means, ipd_stds, pw_means, pw_stds, sns, maps, keep)
+        rev = self._strand(device, n, kmer2, kpass2, ipd_means2, ipd_stds2, pw_means2, pw_stds2, sns2, maps2, keep)
+        hshape = (2 * self.num_layers, n, self.hidden_size)
+        h0a, h0b = _dev_f32(h0[0], device, hshape), _dev_f32(h0[1], device, hshape)
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        probs = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        if n > 0:
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(_lib.load().ccsm_forward_att2s(handle, n, ctypes.byref(fwd), ctypes.byref(rev),
+                                                      h0a.data_ptr(), h0b.data_ptr(), logits.data_ptr(),
+                                                      probs.data_ptr(), ctypes.c_void_p(stream)))
+        return logits, probs
+
+    def forward_host(self, feats, h0=None):
+        """Host-buffer entry (include/ccsm.h ccsm_forward_att2s_host): `feats` maps the live tensor names
+        (kmer, kpass, ipd, pw and the same with a '2' suffix) to float32 CPU tensors / numpy arrays of shape
+        (n, seq_len).  Copies, forward and result read-back are pipelined inside the library.  Returns
+        CPU tensors (logits, probs)."""
+        handle, dev = self._ensure_handle()
+        L = self.seq_len
+        cpu = torch.device("cpu")
+        n = int(torch.as_tensor(feats["kmer"]).reshape(-1, L).shape[0])
+        keep = []
+        strands = []
+        for sfx in ("", "2"):
+            s = _lib.Strand()
+            for name, key in (("kmer", "kmer"), ("kpass", "kpass"), ("ipd_means", "ipd"), ("pw_means", "pw"),
+                              ("ipd_stds", "ipd_sd"), ("pw_stds", "pw_sd"), ("sns", "sns"), ("maps", "maps")):
+                if key + sfx in feats and feats[key + sfx] is not None:
+                    t = _dev_f32(feats[key + sfx], cpu)
+                    keep.append(t)
+                    setattr(s, name, t.data_ptr())
+            strands.append(s)
+        if h0 is None:
+            h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
+                  self.init_hidden(n, self.num_layers, self.hidden_size))
+        hshape = (2 * self.num_layers, n, self.hidden_size)
+        h0a, h0b = _dev_f32(h0[0], cpu, hshape), _dev_f32(h0[1], cpu, hshape)
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32)
+        probs = torch.empty((n, self.num_classes), dtype=torch.float32)
+        if n > 0:
+            _lib.check(_lib.load().ccsm_forward_att2s_host(handle, n, ctypes.byref(strands[0]), ctypes.byref(strands[1]),
+                                                           h0a.data_ptr(), h0b.data_ptr(), logits.data_ptr(),
+                                                           probs.data_ptr()))
+        return logits, probs
+
+
+class AggrAttRNN(_NativeModule):
+    """Drop-in for the reference ``AggrAttRNN`` with ``model_type="attbigru"`` (models.py:625-694):
+    regression over 11 neighbouring CpG sites, raw fc1 output (no softmax)."""
+
+    def __init__(self, seq_len=11, num_layers=1, num_classes=1, dropout_rate=0.5, hidden_size=32, binsize=20,
+                 model_type="attbigru", device=0, precision=None):
+        super().__init__()
+        if model_type != "attbigru":
+            raise ValueError("--model_type not set right! (ccsmeth_b200 implements attbigru)")
+        self.model_type = model_type
+        self.device = device
+        self.seq_len, self.num_layers, self.num_classes, self.hidden_size = seq_len, num_layers, num_classes, hidden_size
+        self.binsize = binsize
+        self.feas_ccs = binsize + 1
+        self.rnn_cell = "gru"
+        self.rnn = nn.GRU(self.feas_ccs, hidden_size, num_layers, dropout=0, batch_first=True, bidirectional=True)
+        self._att3 = Attention(hidden_size * 2, hidden_size * 2, hidden_size)
+        self.dropout1 = nn.Dropout(p=dropout_rate)
+        self.fc1 = nn.Linear(hidden_size * 2, num_classes)
+        self.requires_grad_(False)
+        self._native_init("fp32")  # K=21/32 contractions are not tensor-core shaped
+
+    def init_hidden(self, batch_size, num_layers, hidden_size):  # reference models.py:661-671
+        return torch.randn(num_layers * 2, batch_size, hidden_size)
+
+    def _config(self, dev):
+        return _lib.Config(_lib.KIND_AGGR, self.seq_len, self.num_layers, self.hidden_size, self.num_classes,
+                           0, 0, self.binsize, _lib.PREC["fp32"], dev)
+
+    def forward(self, offsets, histos, h0=None):
+        handle, dev = self._ensure_handle()
+        device = torch.device("cuda", dev)
+        L = self.seq_len
+        offsets = _dev_f32(offsets, device, (-1, L))
+        n = int(offsets.shape[0])
+        histos = _dev_f32(histos, device, (n, L, self.binsize))
+        if h0 is None:
+            h0 = self.init_hidden(n, self.num_layers, self.hidden_size)
+        h0 = _dev_f32(h0, device, (2 * self.num_layers, n, self.hidden_size))
+        out = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        if n > 0:
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(_lib.load().ccsm_forward_aggr(handle, n, offsets.data_ptr(), histos.data_ptr(), h0.data_ptr(),
+                                                     out.data_ptr(), ctypes.c_void_p(stream)))
+        return out

@@ -1,0 +1,144 @@
+/* ccsm.h -- C ABI of libccsm.so, the B200 (sm_100a) implementation of ccsmeth's per-site
+ * methylation-call inference path.
+ *
+ * The reference (PengNi/ccsmeth, pure Python) has no FFI layer: the boundary this library replaces
+ * is the nn.Module protocol used at three call sites --
+ *     ccsmeth/call_modifications.py:315-369   model construction + checkpoint load (_call_mods_q)
+ *     ccsmeth/call_modifications.py:201-214   model(16 tensors) -> (logits, probs)  (_call_mods2s)
+ *     ccsmeth/call_mods_freq_bam.py:317-342, 301-302   AggrAttRNN load + model(offsets, histos)
+ * and the forwards behind them --
+ *     ccsmeth/models.py:89-150    ModelAttRNN.forward   (attbigru2s)
+ *     ccsmeth/models.py:673-694   AggrAttRNN.forward
+ *     ccsmeth/utils/attention.py:48-70   Attention.forward
+ * Each entry point below names the reference lines it stands in for.  The Python classes in
+ * ccsmeth_b200/models.py bind these symbols with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; tensors cross as raw pointers + sizes (torch tensors: data_ptr()).
+ *   - every function returns 0 on success or a negative CCSM_E* code; the message is available
+ *     from ccsm_last_error() (thread-local, never NULL).  No exceptions / exit() cross the ABI.
+ *   - "device" pointers are CUDA device pointers on the model's device; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Device entry points are asynchronous on
+ *     that stream and never call cudaDeviceSynchronize.
+ *   - a handle is bound to one device and is not thread-safe (the reference runs one model per
+ *     process per GPU, call_modifications.py:572-578).
+ *   - the caller owns all I/O buffers; the library owns packed weights and workspace.
+ */
+#ifndef CCSM_H_
+#define CCSM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCSM_ABI_VERSION 1
+
+/* error codes */
+#define CCSM_OK            0
+#define CCSM_EINVAL       -1   /* bad argument / unsupported configuration */
+#define CCSM_ESTATE       -2   /* call order violated (e.g. forward before finalize) */
+#define CCSM_ECUDA        -3   /* a CUDA runtime call failed (message has the CUDA error string) */
+#define CCSM_ENOMEM       -4
+#define CCSM_EUNSUPPORTED -5   /* device is not sm_100 / feature not built */
+#define CCSM_EKEY         -6   /* unknown state_dict key or wrong shape */
+
+/* model kinds */
+#define CCSM_KIND_ATT2S 0      /* ModelAttRNN(model_type="attbigru2s"), models.py:17-150 */
+#define CCSM_KIND_AGGR  1      /* AggrAttRNN(model_type="attbigru"),    models.py:625-694 */
+
+/* arithmetic of the GEMM-shaped work (gate/softmax math is always fp32) */
+#define CCSM_PREC_FP32    0    /* fp32 FFMA kernels: reference-exact to ~1e-6 */
+#define CCSM_PREC_BF16X3  1    /* tcgen05, bf16 hi/lo split, 3 passes, fp32 accumulate (parity mode) */
+#define CCSM_PREC_BF16    2    /* tcgen05, single-pass bf16 in / fp32 accumulate (throughput mode) */
+#define CCSM_PREC_FP16X3  3    /* tcgen05, fp16 hi/lo split, 3 passes (parity mode, ~fp32-exact) */
+#define CCSM_PREC_FP16    4    /* tcgen05, single-pass fp16 in / fp32 accumulate */
+
+/* feature flags (reference models.py:35-47, CLI --is_npass/--is_stds/--is_sn/--is_map) */
+#define CCSM_FEAT_NPASS 1
+#define CCSM_FEAT_STDS  2
+#define CCSM_FEAT_SN    4
+#define CCSM_FEAT_MAP   8
+
+typedef struct ccsm_model ccsm_model;
+
+typedef struct ccsm_config {
+  int32_t kind;         /* CCSM_KIND_* */
+  int32_t seq_len;      /* 21 (att2s) / 11 (aggr) */
+  int32_t num_layers;   /* 3 / 1 */
+  int32_t hidden;       /* 256 / 32 */
+  int32_t num_classes;  /* 2 / 1 */
+  int32_t n_vocab;      /* 5 (att2s); ignored for aggr */
+  int32_t n_embed;      /* 8 (att2s); ignored for aggr */
+  int32_t feat_flags;   /* CCSM_FEAT_* (att2s); for aggr: bin count (20) */
+  int32_t precision;    /* CCSM_PREC_* */
+  int32_t device;       /* CUDA device ordinal */
+} ccsm_config;
+
+/* One strand's 8 forward tensors, in the reference's positional order
+ * (models.py:89-90; call_modifications.py:201-208).  float32, row-major.  Dead slots may be NULL. */
+typedef struct ccsm_strand {
+  const float* kmer;       /* (n, L) base codes 0..4 stored as floats; truncated like .int() */
+  const float* kpass;      /* (n, L)   used iff CCSM_FEAT_NPASS */
+  const float* ipd_means;  /* (n, L) */
+  const float* ipd_stds;   /* (n, L)   used iff CCSM_FEAT_STDS */
+  const float* pw_means;   /* (n, L) */
+  const float* pw_stds;    /* (n, L)   used iff CCSM_FEAT_STDS */
+  const float* sns;        /* (n, 4)   used iff CCSM_FEAT_SN */
+  const float* maps;       /* (n, L)   used iff CCSM_FEAT_MAP */
+} ccsm_strand;
+
+int         ccsm_abi_version(void);
+const char* ccsm_last_error(void);
+
+/* Number of CUDA kernels this library has launched in the calling process (for bench accounting). */
+int64_t     ccsm_kernel_launches(void);
+
+/* Replaces model construction, reference call_modifications.py:316-323 / call_mods_freq_bam.py:317-321. */
+int  ccsm_create(ccsm_model** out, const ccsm_config* cfg);
+void ccsm_destroy(ccsm_model* m);
+
+/* Replaces load_state_dict, reference call_modifications.py:343-358.  `key` is a reference state_dict
+ * key ("embed.weight", "rnn.weight_ih_l0_reverse", "_att3.Ua.weight", "fc1.bias", ...); a leading
+ * "module." (DDP/DataParallel prefix) is stripped as the reference does (:350-358).
+ * `host` is float32 host memory of `shape[0..ndim)`; it is copied. */
+int  ccsm_set_weight(ccsm_model* m, const char* key, const float* host, const int64_t* shape, int32_t ndim);
+
+/* Replaces `.cuda(device)` + `.eval()`, reference call_modifications.py:367-369: validates that every
+ * tensor was provided, packs (transposes / splits hi-lo / tiles) the weights and uploads them.
+ * May be called again after further ccsm_set_weight calls. */
+int  ccsm_finalize(ccsm_model* m);
+
+/* Change the arithmetic mode of a finalized model (re-packs weights if needed). */
+int  ccsm_set_precision(ccsm_model* m, int32_t precision);
+
+/* Replaces ModelAttRNN.forward, reference models.py:89-150 (call site call_modifications.py:201-208).
+ * fwd/rev: device pointers.  h0_fwd/h0_rev: (2*layers, n, hidden) float32 device, the initial hidden
+ * states the reference draws with torch.randn (models.py:77-87); NULL means zeros.
+ * logits/probs: (n, num_classes) float32 device (either may be NULL). */
+int  ccsm_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
+                        const float* h0_fwd, const float* h0_rev, float* logits, float* probs, void* stream);
+
+/* Same computation with HOST buffers (pageable or pinned): the library stages host->device copies,
+ * the forward and the device->host copy of the results in double-buffered chunks on its own streams,
+ * and returns when `logits`/`probs` are complete.  This is the call the batch loop
+ * (reference call_modifications.py:170-227) makes once per hole-batch instead of once per 512 sites. */
+int  ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
+                             const float* h0_fwd, const float* h0_rev, float* logits, float* probs);
+
+/* Replaces AggrAttRNN.forward, reference models.py:673-694 (call site call_mods_freq_bam.py:301).
+ * offsets (n, L), histos (n, L, bins), h0 (2*layers, n, hidden) or NULL, out (n, num_classes); device. */
+int  ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos,
+                       const float* h0, float* out, void* stream);
+
+/* Introspection used by tests: copies the last layer-stack output of the most recent forward chunk.
+ * Returns the number of floats written (<= cap) or a negative error. */
+int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCSM_H_ */

@@ -1,0 +1,128 @@
+"""Parity of the CUDA path (through the C ABI) against the reference fixtures and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import att2s_numpy, aggr_numpy
+
+pytestmark = pytest.mark.gpu
+
+FEATS = ("kmer", "kpass", "ipd", "pw", "kmer2", "kpass2", "ipd2", "pw2")
+EDGE_CASES = ("n1", "n3", "allN", "extreme", "zeroh0", "fraccode")
+TOL = 1e-4  # BASELINE.json north_star: max |dprob| <= 1e-4 vs the reference fp32 CPU path
+
+
+def args16(g, pfx=""):
+    n = g[pfx + "kmer"].shape[0]
+    z = torch.zeros(n)
+    t = lambda k: torch.from_numpy(g[pfx + k])
+    return (t("kmer"), t("kpass"), t("ipd"), z, t("pw"), z, z, z, t("kmer2"), t("kpass2"), t("ipd2"), z, t("pw2"), z, z, z)
+
+
+@pytest.fixture(scope="module")
+def model(ckpt_att2s):
+    from ccsmeth_b200.models import ModelAttRNN
+    m = ModelAttRNN(21, 3, 2, 0, 256, is_npass=True, model_type="attbigru2s", device=0, precision="fp32")
+    d = m.state_dict()
+    d.update({k: torch.from_numpy(v) for k, v in ckpt_att2s.items()})
+    m.load_state_dict(d)
+    m = m.cuda(0)
+    m.eval()
+    return m
+
+
+def run(model, g, pfx=""):
+    h0 = (torch.from_numpy(g[pfx + "h0_f"]), torch.from_numpy(g[pfx + "h0_r"]))
+    logits, probs = model(*[a.cuda() for a in args16(g, pfx)], h0=h0)
+    assert logits.is_cuda and probs.is_cuda
+    return logits.cpu().numpy(), probs.cpu().numpy()
+
+
+def test_fp32_matches_reference_synth(model, golden_synth):
+    model.set_precision("fp32")
+    logits, probs = run(model, golden_synth)
+    assert np.abs(probs - golden_synth["probs"]).max() <= 2e-5
+    assert np.abs(logits - golden_synth["logits"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("case", EDGE_CASES)
+def test_fp32_edge_cases(model, golden_edge, case):
+    model.set_precision("fp32")
+    logits, probs = run(model, golden_edge, case + ".")
+    assert probs.shape == golden_edge[case + ".probs"].shape
+    assert np.abs(probs - golden_edge[case + ".probs"]).max() <= 2e-5
+
+
+def test_empty_batch(model):
+    z = torch.zeros(0, 21).cuda()
+    e = torch.zeros(0).cuda()
+    logits, probs = model(z, z, z, e, z, e, e, e, z, z, z, e, z, e, e, e)
+    assert logits.shape == (0, 2) and probs.shape == (0, 2)
+
+
+def test_default_h0_stream_matches_reference(model, golden_seeded):
+    """h0=None must reproduce the reference: torch.randn on the CPU generator, strand 1 then strand 2."""
+    model.set_precision("fp32")
+    g = golden_seeded
+    torch.manual_seed(int(g["tseed"]))
+    _, probs = model(*[a.cuda() for a in args16(g)])
+    assert np.abs(probs.cpu().numpy() - g["probs"]).max() <= 2e-5
+
+
+def test_rnn_stack_matches_oracle_internals(model, ckpt_att2s, golden_synth):
+    """Layer-stack output (n, 21, 512) of both strands vs the numpy oracle's intermediate."""
+    import ctypes
+    from ccsmeth_b200 import _lib
+    model.set_precision("fp32")
+    g = {k: (v[:, :32] if k.startswith("h0") else v[:32]) for k, v in golden_synth.items()}
+    run(model, g)
+    buf = np.empty(32 * 2 * 21 * 512, dtype=np.float32)
+    got = _lib.load().ccsm_debug_last_rnn_out(model._handle, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
+    assert got == buf.size
+    out = buf.reshape(32, 2, 21, 512)
+    _, _, it = att2s_numpy.forward(ckpt_att2s, *[g[k] for k in FEATS], g["h0_f"], g["h0_r"], return_internals=True)
+    assert np.abs(out[:, 0] - it["layers0"][-1]).max() <= 1e-4
+    assert np.abs(out[:, 1] - it["layers1"][-1]).max() <= 1e-4
+
+
+def test_host_entry_matches_device_entry(model, golden_synth):
+    model.set_precision("fp32")
+    g = golden_synth
+    feats = {k: g[k] for k in FEATS}
+    logits, probs = model.forward_host(feats, h0=(g["h0_f"], g["h0_r"]))
+    assert np.abs(probs.numpy() - g["probs"]).max() <= 2e-5
+
+
+def test_large_batch_chunking_is_consistent(model, golden_synth):
+    """n > the library's internal chunk (8192 sites): tile the 256 golden sites 40x, every copy must agree."""
+    model.set_precision("fp32")
+    g = golden_synth
+    rep = 40
+    big = {k: np.concatenate([g[k]] * rep, axis=1 if k.startswith("h0") else 0) for k in FEATS + ("h0_f", "h0_r")}
+    _, probs = run(model, big)
+    probs = probs.reshape(rep, 256, 2)
+    assert np.abs(probs - g["probs"][None]).max() <= 2e-5
+
+
+def test_aggr_matches_reference(ckpt_aggr, golden_aggr):
+    from ccsmeth_b200.models import AggrAttRNN
+    g = golden_aggr
+    m = AggrAttRNN(11, 1, 1, 0, 32, binsize=20, model_type="attbigru", device=0)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ckpt_aggr.items()})
+    m = m.cuda(0).eval()
+    pm, hm = aggr_numpy.build_windows(g["pos"], list(g["histos"]))
+    out = m(torch.tensor(pm, dtype=torch.float).cuda(), torch.tensor(np.array(hm), dtype=torch.float).cuda(),
+            h0=torch.from_numpy(g["h0"]))
+    assert np.abs(out.cpu().numpy() - g["raw"]).max() <= 1e-5
+
+
+def test_set_weight_rejects_wrong_shape(model):
+    import ctypes
+    from ccsmeth_b200 import _lib
+    lib = _lib.load()
+    a = np.zeros((3, 3), dtype=np.float32)
+    shp = (ctypes.c_int64 * 2)(3, 3)
+    rc = lib.ccsm_set_weight(model._handle, b"fc1.weight", a.ctypes.data_as(ctypes.c_void_p), shp, 2)
+    assert rc == _lib.EKEY and b"size mismatch" in lib.ccsm_last_error()
+    rc = lib.ccsm_set_weight(model._handle, b"nonexistent.weight", a.ctypes.data_as(ctypes.c_void_p), shp, 2)
+    assert rc == _lib.EKEY
