@@ -19,7 +19,7 @@ WORKER = textwrap.dedent("""
     assert tot == [1001, 7, 1, 2], tot
     assert mx == 11.0, mx
     parallel.finalize()
-    sys.stdout.write("rank" + str(rank) + "-ok\n")
+    print("rank" + str(rank) + "-ok", flush=True)
 """) % ROOT
 
 
