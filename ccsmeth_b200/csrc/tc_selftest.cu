@@ -1,0 +1,136 @@
+// Single-CTA tcgen05 GEMM used by tests to pin the UMMA descriptor conventions (LBO/SBO meaning,
+// instruction descriptor bits, TMEM lane/column mapping of tcgen05.ld) that tc_path.cu relies on.
+#include <vector>
+
+#include "ccsm_internal.h"
+#include "tc_common.cuh"
+
+namespace ccsm {
+using namespace tc;
+
+// A image: K/8 slabs of (128 rows x 16 B); B image: K/8 slabs of (N rows x 16 B).
+template <bool F16>
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __restrict__ a_img,
+                                                               const uint8_t* __restrict__ b_img, float* __restrict__ D,
+                                                               int N, int K, int swap_lbo_sbo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = (uint32_t)(K / 8) * 2048u, b_bytes = (uint32_t)(K / 8) * (uint32_t)N * 16u;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + a_bytes;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[1]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_base_s), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_full, a_bytes + b_bytes);
+      bulk_g2s(smem_u32(sA), a_img, a_bytes, bar_full);
+      bulk_g2s(smem_u32(sB), b_img, b_bytes, bar_full);
+      mbar_wait(bar_full, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(128, N, F16);
+      const uint32_t a_lbo = 2048, b_lbo = (uint32_t)N * 16u, sbo = 128;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        uint64_t ad, bd;
+        if (!swap_lbo_sbo) {
+          ad = make_smem_desc(smem_u32(sA) + ks * 2 * a_lbo, a_lbo, sbo);
+          bd = make_smem_desc(smem_u32(sB) + ks * 2 * b_lbo, b_lbo, sbo);
+        } else {
+          ad = make_smem_desc(smem_u32(sA) + ks * 2 * a_lbo, sbo, a_lbo);
+          bd = make_smem_desc(smem_u32(sB) + ks * 2 * b_lbo, sbo, b_lbo);
+        }
+        umma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_done);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)row * N + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static void pack_rows(const float* src, int rows, int K, bool f16, std::vector<uint16_t>& img) {
+  img.assign((size_t)rows * K, 0);
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < K; ++k) {
+      size_t off = (size_t)(k / 8) * rows * 8 + (size_t)r * 8 + (k % 8);
+      float v = src[(size_t)r * K + k];
+      uint16_t bits;
+      if (f16) {
+        __half h = __float2half_rn(v);
+        bits = *reinterpret_cast<uint16_t*>(&h);
+      } else {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        bits = *reinterpret_cast<uint16_t*>(&h);
+      }
+      img[off] = bits;
+    }
+}
+
+}  // namespace ccsm
+
+using namespace ccsm;
+
+extern "C" int ccsm_debug_umma_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, int32_t swap_lbo_sbo,
+                                    const float* A, const float* B, float* D) {
+  if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || !A || !B || !D) {
+    set_error("ccsm_debug_umma_gemm: bad shape N=%d K=%d", N, K);
+    return CCSM_EINVAL;
+  }
+  size_t smem = (size_t)(K / 8) * (2048 + (size_t)N * 16);
+  if (smem > 200 * 1024) {
+    set_error("ccsm_debug_umma_gemm: K too large for one stage");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(device));
+  std::vector<uint16_t> ai, bi;
+  pack_rows(A, 128, K, is_f16 != 0, ai);
+  pack_rows(B, N, K, is_f16 != 0, bi);
+  DevBuf da, db, dd;
+  CCSM_TRY(da.reserve(ai.size() * 2));
+  CCSM_TRY(db.reserve(bi.size() * 2));
+  CCSM_TRY(dd.reserve((size_t)128 * N * 4));
+  CCSM_CUDA(cudaMemcpy(da.p, ai.data(), ai.size() * 2, cudaMemcpyHostToDevice));
+  CCSM_CUDA(cudaMemcpy(db.p, bi.data(), bi.size() * 2, cudaMemcpyHostToDevice));
+  if (is_f16) {
+    CCSM_CUDA(cudaFuncSetAttribute(umma_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<true><<<1, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), N, K, swap_lbo_sbo);
+  } else {
+    CCSM_CUDA(cudaFuncSetAttribute(umma_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<false><<<1, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), N, K, swap_lbo_sbo);
+  }
+  count_launch();
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("umma selftest kernel failed: %s", cudaGetErrorString(e));
+    da.release(); db.release(); dd.release();
+    return CCSM_ECUDA;
+  }
+  CCSM_CUDA(cudaMemcpy(D, dd.p, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
+  da.release(); db.release(); dd.release();
+  return CCSM_OK;
+}
