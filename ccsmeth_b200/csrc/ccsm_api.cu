@@ -391,4 +391,15 @@ int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap) {
   return nfl;
 }
 
+int64_t ccsm_debug_tc_layer_out(ccsm_model* m, int32_t layer, float* host, int64_t cap) {
+  if (!m || !host || layer < 0 || layer >= m->cfg.num_layers) {
+    set_error("ccsm_debug_tc_layer_out: bad argument");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  int64_t written = 0;
+  int rc = tc_debug_layer_out(m, layer, host, cap, &written);
+  return rc != CCSM_OK ? rc : written;
+}
+
 }  // extern "C"

@@ -107,5 +107,6 @@ int tc_upload_weights(ccsm_model* m);
 void tc_release(ccsm_model* m);
 int tc_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
                      const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st);
+int tc_debug_layer_out(ccsm_model* m, int layer, float* host, int64_t cap, int64_t* written);
 
 }  // namespace ccsm

@@ -1,16 +1,952 @@
-// tcgen05 tensor-core path (placeholder until the kernels land).
+// Tensor-core (tcgen05 / TMEM / TMA bulk-copy) implementation of the attbigru2s forward for sm_100a.
+//
+// Replaces: reference ccsmeth/models.py:89-150 (ModelAttRNN.forward) + utils/attention.py:48-70.
+//
+// Data model (everything a kernel streams is a pre-tiled "image" so that one 1-D bulk copy lands an
+// MMA-ready operand in shared memory; see DESIGN.md "HBM layout"):
+//   row tile  = 128 strand-rows (row R = 2*site + strand) = 64 CpG sites; UMMA M = 128 (TMEM lane = row)
+//   slab      = 8 consecutive K elements of all rows of a tile, rows 16 B apart: (rows x 16 B) contiguous.
+//               This is the UMMA K-major SWIZZLE_NONE canonical layout with SBO = 128 B, LBO = slab bytes.
+//   x0 image  [tile][t][part][2 slabs x 2048 B]                     layer-0 input, K = 11 padded to 16
+//   act image [tile][t][chunk c = dir*4 + j][part][8 slabs x 2048]  layer output h_t, 64 hidden units per chunk
+//   h0 image  [layer][tile][dir][kc][part][8 slabs x 2048]          initial hidden state
+//   weights   [dir][j] { X: [part][KX/8 slabs x 3072 B], H: [part][32 slabs x 3072 B] }
+//             192 gate rows per unit-chunk j: X part rows = (n_i, r, z), H part rows = (r, z, n_h)
+//   part      = 0 (hi) or 1 (lo): P = 1 single pass; P = 2 -> x ~= hi + lo and three MMA passes
+//               hi*hi + hi*lo + lo*hi (error-compensated split, fp32 accumulate in TMEM).
+//
+// GRU layer kernel (persistent, one CTA per SM, 384 threads):
+//   warp 0      TMA producer: bulk copies weights + activation K-slabs into a 3-stage ring
+//   warp 1      MMA issuer (one elected thread): D[tmem] += A[smem] . B[smem]^T, N = 192 per instruction
+//   warps 4-11  gate epilogue: tcgen05.ld accumulators -> sigmoid/tanh/blend -> h_t written to the act image
+//   Two row tiles ("slots") share every weight stage; TMEM holds [n_i | r | z | n_h] x 64 units per slot.
+//   h_t goes back to the next step's A operand through the (L2-resident) act image.
+#include <stdio.h>
+
+#include <vector>
+
 #include "ccsm_internal.h"
+#include "tc_common.cuh"
 
 namespace ccsm {
-struct TcState {};
-int tc_upload_weights(ccsm_model*) {
-  set_error("tensor-core path not built yet");
-  return CCSM_EUNSUPPORTED;
+using namespace tc;
+
+constexpr int TILE_ROWS = 128;
+constexpr uint32_t A_SLAB = 2048;     // 128 rows x 16 B
+constexpr uint32_t G_SLAB = 3072;     // 192 gate rows x 16 B
+constexpr uint32_t T_SLAB = 4096;     // 256 attention rows x 16 B
+constexpr uint32_t CHUNK_BYTES = 8 * A_SLAB;  // 64 K elements of a 128-row tile, one part
+
+struct TcState {
+  int P = 0;          // parts of the currently packed weights (0 = none)
+  bool f16 = false;
+  std::vector<DevBuf> wimg;   // per layer
+  std::vector<size_t> kx_slabs;
+  DevBuf bias;                // [layer][dir][4][H]
+  DevBuf wa_img, ua_img;      // [part][64 slabs x 4096]
+  DevBuf va, fc_w, fc_b, embed;
+  // workspace
+  int64_t tiles_cap = 0;
+  int ws_P = 0;
+  DevBuf x0img, h0img, act[3];
+  int sm_count = 0;
+  // debug bookkeeping
+  int64_t last_tiles = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// math
+// ------------------------------------------------------------------------------------------------
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_(float x) {
+  if constexpr (FAST) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(t, 0.5f, 0.5f);
+  } else {
+    return __fdividef(1.f, 1.f + __expf(-x));
+  }
 }
-void tc_release(ccsm_model*) {}
-int tc_forward_att2s(ccsm_model*, int64_t, const ccsm_strand*, const ccsm_strand*, const float*, const float*, float*,
-                     float*, cudaStream_t) {
-  set_error("tensor-core path not built yet");
-  return CCSM_EUNSUPPORTED;
+template <bool FAST>
+__device__ __forceinline__ float tanh_(float x) {
+  if constexpr (FAST) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+  } else {
+    return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f);
+  }
 }
+
+// 8 fp32 -> one 16-byte vector of packed elements (hi) and optionally the residual (lo)
+template <int P, bool F16>
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
+    if constexpr (P == 2) {
+      float2 b = unpack2<F16>(h[i]);
+      l[i] = pack2<F16>(v[2 * i] - b.x, v[2 * i + 1] - b.y);
+    } else {
+      l[i] = 0;
+    }
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+template <int P, bool F16>
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&v)[8]) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+  const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 a = unpack2<F16>(h[i]);
+    if constexpr (P == 2) {
+      float2 b = unpack2<F16>(l[i]);
+      a.x += b.x;
+      a.y += b.y;
+    }
+    v[2 * i] = a.x;
+    v[2 * i + 1] = a.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: features -> x0 image (embedding lookup + kinetics concat, reference models.py:91-106),
+//       h0 (2*layers, n, H) fp32 -> h0 images.  One thread per strand-row.
+// ------------------------------------------------------------------------------------------------
+struct TcStrand {
+  const float *kmer, *kpass, *ipd, *pw;
+};
+
+template <int P, bool F16>
+__global__ void tc_prep_kernel(int64_t n_tiles, int64_t sites, int64_t site0, int64_t n_total, int L, int NL,
+                               int n_vocab, int has_npass, TcStrand s0, TcStrand s1,
+                               const float* __restrict__ embed, const float* __restrict__ h0_a,
+                               const float* __restrict__ h0_b, uint8_t* __restrict__ x0img,
+                               uint8_t* __restrict__ h0img) {
+  const int64_t gr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // global row in chunk
+  if (gr >= n_tiles * TILE_ROWS) return;
+  const int64_t tile = gr / TILE_ROWS;
+  const int r = (int)(gr % TILE_ROWS);
+  const int strand = (int)(gr & 1);
+  const int64_t site = gr >> 1;  // site within chunk
+  const bool valid = site < sites;
+  const TcStrand& s = strand ? s1 : s0;
+  for (int t = 0; t < L; ++t) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    if (valid) {
+      const int64_t o = (site0 + site) * L + t;
+      int code = (int)s.kmer[o];
+      code = code < 0 ? 0 : (code >= n_vocab ? n_vocab - 1 : code);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = embed[code * 8 + i];
+      v[8] = s.ipd[o];
+      v[9] = s.pw[o];
+      if (has_npass) v[10] = s.kpass[o];
+    }
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = v[sl * 8 + i];
+      uint4 hi, lo;
+      split8<P, F16>(w, hi, lo);
+      uint8_t* base = x0img + ((tile * L + t) * P) * (2 * (size_t)A_SLAB) + sl * A_SLAB + r * 16;
+      *reinterpret_cast<uint4*>(base) = hi;
+      if constexpr (P == 2) *reinterpret_cast<uint4*>(base + 2 * A_SLAB) = lo;
+    }
+  }
+  const float* h0 = strand ? h0_b : h0_a;
+  for (int l = 0; l < NL; ++l)
+    for (int d = 0; d < 2; ++d) {
+      const float* src = (valid && h0) ? h0 + ((int64_t)(2 * l + d) * n_total + site0 + site) * 256 : nullptr;
+      for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) {
+          float w[8];
+          if (src) {
+            float4 a = *reinterpret_cast<const float4*>(src + kc * 64 + sl * 8);
+            float4 b = *reinterpret_cast<const float4*>(src + kc * 64 + sl * 8 + 4);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = 0.f;
+          }
+          uint4 hi, lo;
+          split8<P, F16>(w, hi, lo);
+          uint8_t* base = h0img + ((((int64_t)l * n_tiles + tile) * 2 + d) * 4 + kc) * (size_t)(P * CHUNK_BYTES) +
+                          sl * A_SLAB + r * 16;
+          *reinterpret_cast<uint4*>(base) = hi;
+          if constexpr (P == 2) *reinterpret_cast<uint4*>(base + CHUNK_BYTES) = lo;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRU layer kernel
+// ------------------------------------------------------------------------------------------------
+struct GruParams {
+  const uint8_t* xin;    // layer 0: x0 image; else act image of the previous layer
+  const uint8_t* h0img;  // this layer's h0 images [tile][dir][kc][part][CHUNK]
+  uint8_t* out;          // this layer's act image
+  const uint8_t* wimg;   // this layer's weight images
+  const float* bias;     // [dir][4][256]: b_r(=b_ir+b_hr), b_z, b_in, b_hn
+  int n_tiles;           // even
+  int L;
+  int kx_slabs;          // 2 (layer 0) or 64
+};
+
+constexpr int GRU_STAGES = 3;
+constexpr int GRU_THREADS = 384;
+
+template <int P>
+struct GruCfg {
+  static constexpr int KS = 8 / P;  // slabs per stage per part
+  static constexpr uint32_t B_PART = KS * G_SLAB;
+  static constexpr uint32_t A_PART = KS * A_SLAB;
+  static constexpr uint32_t STAGE = P * (B_PART + 2 * A_PART);  // 57344 for both P
+  static constexpr uint32_t SMEM = GRU_STAGES * STAGE + 2 * 4 * 256 * 4;
+};
+
+template <int P, bool F16>
+__global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruParams p) {
+  using C = GruCfg<P>;
+  constexpr int KS = C::KS;
+  constexpr bool FAST = (P == 1);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * GRU_STAGES + 3];
+  __shared__ uint32_t tmem_base_s;
+  float* bias_s = reinterpret_cast<float*>(smem + GRU_STAGES * C::STAGE);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[GRU_STAGES]);
+  const uint32_t tmem_full = smem_u32(&bars[2 * GRU_STAGES]), tmem_empty = smem_u32(&bars[2 * GRU_STAGES + 1]),
+                 h_ready = smem_u32(&bars[2 * GRU_STAGES + 2]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GRU_STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 256);
+    mbar_init(h_ready, 256);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * 4 * 256; i += GRU_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const int L = p.L;
+  const int n_items = p.n_tiles;  // (n_tiles / 2 pairs) x 2 directions
+  const size_t xbytes = (size_t)P * p.kx_slabs * G_SLAB, hbytes = (size_t)P * 32 * G_SLAB;
+  const size_t wj_bytes = xbytes + hbytes;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t stage = 0, use = 0;  // use = how many times the ring wrapped
+      uint32_t gstep = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int pair = item >> 1, d = item & 1;
+        const int64_t tile0 = 2 * (int64_t)pair;
+        for (int s = 0; s < L; ++s, ++gstep) {
+          const int t = d ? (L - 1 - s) : s;
+          const int tprev = d ? t + 1 : t - 1;
+          for (int j = 0; j < 4; ++j) {
+            const uint8_t* wj = p.wimg + (size_t)(d * 4 + j) * wj_bytes;
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? p.kx_slabs : 32;
+              for (int so = 0; so < total; so += KS) {
+                const int ns = (total - so) < KS ? (total - so) : KS;
+                if (part == 1 && so == 0 && j == 0 && gstep > 0) {
+                  mbar_wait(h_ready, (gstep - 1) & 1);  // h_{t_prev} of both slots is in the act image
+                  fence_proxy_async_all();
+                }
+                mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+                const uint32_t fb = full0 + 8 * stage;
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + 2 * A_SLAB));
+                // weights
+                const uint8_t* wsrc = wj + (part ? xbytes : 0);
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp)
+                  bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb);
+                // activations of both slots
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                  const int64_t tile = tile0 + sl;
+                  const uint8_t* asrc;
+                  size_t part_stride;
+                  if (part == 0) {
+                    if (p.kx_slabs == 2) {
+                      asrc = p.xin + ((tile * L + t) * P) * (2 * (size_t)A_SLAB);
+                      part_stride = 2 * A_SLAB;
+                    } else {
+                      asrc = p.xin + (((tile * L + t) * 8 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                      part_stride = CHUNK_BYTES;
+                    }
+                  } else {
+                    if (s == 0)
+                      asrc = p.h0img + (((tile * 2 + d) * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                    else
+                      asrc = p.out + (((tile * L + tprev) * 8 + d * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES +
+                             (so & 7) * A_SLAB;
+                    part_stride = CHUNK_BYTES;
+                  }
+#pragma unroll
+                  for (int pp = 0; pp < P; ++pp)
+                    bulk_g2s(sb + P * C::B_PART + (sl * P + pp) * C::A_PART, asrc + pp * part_stride, ns * A_SLAB, fb);
+                }
+                if (++stage == GRU_STAGES) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc192 = make_idesc(128, 192, F16), idesc128 = make_idesc(128, 128, F16),
+                         idesc64 = make_idesc(128, 64, F16);
+      uint32_t stage = 0, use = 0, chunk = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int s = 0; s < L; ++s) {
+          for (int j = 0; j < 4; ++j, ++chunk) {
+            mbar_wait(tmem_empty, (chunk & 1) ^ 1);  // both slots' accumulators drained by the epilogue
+            tc_fence_after();
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? p.kx_slabs : 32;
+              for (int so = 0; so < total; so += KS) {
+                const int ns = (total - so) < KS ? (total - so) : KS;
+                mbar_wait(full0 + 8 * stage, use & 1);
+                tc_fence_after();
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                for (int ks = 0; ks < ns / 2; ++ks) {
+                  const bool first = (so == 0 && ks == 0);
+#pragma unroll
+                  for (int sl = 0; sl < 2; ++sl) {
+                    const uint32_t dcol = tmem + sl * 256;
+#pragma unroll
+                    for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
+                      const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                      const uint32_t a_addr = sb + P * C::B_PART + (sl * P + pa) * C::A_PART + ks * 2 * A_SLAB;
+                      const uint32_t b_addr = sb + pb * C::B_PART + ks * 2 * G_SLAB;
+                      const uint64_t ad = make_smem_desc(a_addr, A_SLAB, 128);
+                      if (part == 0) {
+                        // X part -> columns [0,192) = (n_i, r, z); the very first MMA zero-initialises them
+                        umma_f16(dcol, ad, make_smem_desc(b_addr, G_SLAB, 128), idesc192, (first && pass == 0) ? 0u : 1u);
+                      } else if (first && pass == 0) {
+                        // H part -> columns [64,256) = (r, z, n_h): r,z accumulate on top of the X part, n_h starts at 0
+                        umma_f16(dcol + 64, ad, make_smem_desc(b_addr, G_SLAB, 128), idesc128, 1u);
+                        umma_f16(dcol + 192, ad, make_smem_desc(b_addr + 128 * 16, G_SLAB, 128), idesc64, 0u);
+                      } else {
+                        umma_f16(dcol + 64, ad, make_smem_desc(b_addr, G_SLAB, 128), idesc192, 1u);
+                      }
+                    }
+                  }
+                }
+                umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
+                if (++stage == GRU_STAGES) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+            umma_commit(tmem_full);  // accumulators of both slots complete
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== gate epilogue =====================
+    const int ew = warp - 4;
+    const int slot = ew >> 2, quad = ew & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
+    uint32_t chunk = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int pair = item >> 1, d = item & 1;
+      const int64_t tile = 2 * (int64_t)pair + slot;
+      const float* bz = bias_s + d * 4 * 256;
+      for (int s = 0; s < L; ++s) {
+        const int t = d ? (L - 1 - s) : s;
+        const int tprev = d ? t + 1 : t - 1;
+        for (int j = 0; j < 4; ++j, ++chunk) {
+          const uint8_t* hp_base =
+              (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
+                       : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          mbar_wait(tmem_full, chunk & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int ub = 0; ub < 4; ++ub) {
+            uint4 hph[2], hpl[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (ub * 2 + q) * A_SLAB + row * 16));
+              if constexpr (P == 2)
+                hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + (ub * 2 + q) * A_SLAB + row * 16));
+              else
+                hpl[q] = make_uint4(0, 0, 0, 0);
+            }
+            uint32_t ani[16], ar[16], az[16], anh[16];
+            tmem_ld16(trow + 0 + ub * 16, ani);
+            tmem_ld16(trow + 64 + ub * 16, ar);
+            tmem_ld16(trow + 128 + ub * 16, az);
+            tmem_ld16(trow + 192 + ub * 16, anh);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              float hp[8], hn[8];
+              join8<P, F16>(hph[q], hpl[q], hp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int u = j * 64 + ub * 16 + q * 8 + i;
+                const int c = q * 8 + i;
+                const float r = sigmoid_<FAST>(__uint_as_float(ar[c]) + bz[u]);
+                const float z = sigmoid_<FAST>(__uint_as_float(az[c]) + bz[256 + u]);
+                const float n = tanh_<FAST>(__uint_as_float(ani[c]) + bz[512 + u] +
+                                            r * (__uint_as_float(anh[c]) + bz[768 + u]));
+                hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
+              }
+              uint4 hi, lo;
+              split8<P, F16>(hn, hi, lo);
+              *reinterpret_cast<uint4*>(out_base + (ub * 2 + q) * A_SLAB + row * 16) = hi;
+              if constexpr (P == 2)
+                *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + (ub * 2 + q) * A_SLAB + row * 16) = lo;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(tmem_empty);
+          if (j == 3) {
+            fence_proxy_async_all();  // generic-proxy global writes -> visible to the producer's bulk copies
+            mbar_arrive(h_ready);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention + head kernel (reference utils/attention.py:48-70, models.py:135-150)
+//   Qa = q . Wa^T -> TMEM cols [0,256);  per t: D_t = out_t . Ua^T -> TMEM cols [256,512)
+//   e_t = va . tanh(Qa + D_t) (thread-local: TMEM lane = row), softmax over t, ctx = sum_t w_t out_t,
+//   partial logits = fc1[:, strand*512 : +512] . ctx, two strands combined with a warp shuffle.
+// ------------------------------------------------------------------------------------------------
+struct AttParams {
+  const uint8_t* act;   // last layer's act image
+  const uint8_t* wa_img;
+  const uint8_t* ua_img;
+  const float* va;      // [256]
+  const float* fc_w;    // [2][1024]
+  const float* fc_b;    // [2]
+  float* logits;        // (n, 2) or null, already offset to the chunk's first site
+  float* probs;
+  int n_tiles;
+  int L;
+  int64_t sites;        // valid sites in this chunk
+};
+
+constexpr int ATT_STAGES = 4;
+constexpr int ATT_THREADS = 256;
+
+template <int P>
+struct AttCfg {
+  static constexpr int KS = 8 / P;
+  static constexpr uint32_t B_PART = KS * T_SLAB;
+  static constexpr uint32_t A_PART = KS * A_SLAB;
+  static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 49152
+  static constexpr uint32_t SMEM = ATT_STAGES * STAGE + (256 + 2048 + 128 * 22) * 4;
+};
+
+template <int P, bool F16>
+__global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttParams p) {
+  using C = AttCfg<P>;
+  constexpr int KS = C::KS;
+  constexpr bool FAST = (P == 1);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * ATT_STAGES + 2];
+  __shared__ uint32_t tmem_base_s;
+  float* va_s = reinterpret_cast<float*>(smem + ATT_STAGES * C::STAGE);
+  float* fc_s = va_s + 256;
+  float* e_s = fc_s + 2048;  // [128][22]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[ATT_STAGES]);
+  const uint32_t d_full = smem_u32(&bars[2 * ATT_STAGES]), d_empty = smem_u32(&bars[2 * ATT_STAGES + 1]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ATT_STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(d_full, 1);
+    mbar_init(d_empty, 128);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 256; i += ATT_THREADS) va_s[i] = p.va[i];
+  for (int i = threadIdx.x; i < 2048; i += ATT_THREADS) fc_s[i] = p.fc_w[i];
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const int L = p.L;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t stage = 0, use = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int g = 0; g <= L; ++g) {  // g == 0: Qa; g >= 1: D_{t = g-1}
+          const uint8_t* wimg = g == 0 ? p.wa_img : p.ua_img;
+          for (int so = 0; so < 64; so += KS) {
+            const int c = so >> 3;
+            const int t = g == 0 ? (c < 4 ? L - 1 : 0) : g - 1;  // q = [h_n fwd (t = L-1) | h_n rev (t = 0)]
+            mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t sb = smem_base + stage * C::STAGE;
+            mbar_expect_tx(fb, (uint32_t)(P * KS) * (T_SLAB + A_SLAB));
+            const uint8_t* asrc = p.act + ((((int64_t)tile * L + t) * 8 + c) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp) {
+              bulk_g2s(sb + pp * C::B_PART, wimg + ((size_t)pp * 64 + so) * T_SLAB, KS * T_SLAB, fb);
+              bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, asrc + (size_t)pp * CHUNK_BYTES, KS * A_SLAB, fb);
+            }
+            if (++stage == ATT_STAGES) {
+              stage = 0;
+              ++use;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc256 = make_idesc(128, 256, F16);
+      uint32_t stage = 0, use = 0, dcount = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int g = 0; g <= L; ++g) {
+          if (g != 1) {
+            // g == 0 overwrites Qa (previous tile fully drained), g >= 2 overwrites D: wait for the epilogue
+            mbar_wait(d_empty, (dcount & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t dcol = tmem + (g == 0 ? 0 : 256);
+          for (int so = 0; so < 64; so += KS) {
+            mbar_wait(full0 + 8 * stage, use & 1);
+            tc_fence_after();
+            const uint32_t sb = smem_base + stage * C::STAGE;
+            for (int ks = 0; ks < KS / 2; ++ks) {
+#pragma unroll
+              for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
+                const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                const uint64_t ad = make_smem_desc(sb + P * C::B_PART + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128);
+                const uint64_t bd = make_smem_desc(sb + pb * C::B_PART + ks * 2 * T_SLAB, T_SLAB, 128);
+                umma_f16(dcol, ad, bd, idesc256, (so == 0 && ks == 0 && pass == 0) ? 0u : 1u);
+              }
+            }
+            umma_commit(empty0 + 8 * stage);
+            if (++stage == ATT_STAGES) {
+              stage = 0;
+              ++use;
+            }
+          }
+          if (g >= 1) {
+            umma_commit(d_full);
+            ++dcount;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int quad = warp - 4;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    float* my_e = e_s + row * 22;
+    uint32_t dcount = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int t = 0; t < L; ++t, ++dcount) {
+        mbar_wait(d_full, dcount & 1);
+        tc_fence_after();
+        float e = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < 16; ++cb) {
+          uint32_t q[16], dd[16];
+          tmem_ld16(trow + cb * 16, q);
+          tmem_ld16(trow + 256 + cb * 16, dd);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            e = fmaf(va_s[cb * 16 + i], tanh_<FAST>(__uint_as_float(q[i]) + __uint_as_float(dd[i])), e);
+        }
+        my_e[t] = e;
+        tc_fence_before();
+        mbar_arrive(d_empty);
+      }
+      // softmax over t (thread-local)
+      float mx = -INFINITY;
+      for (int t = 0; t < L; ++t) mx = fmaxf(mx, my_e[t]);
+      float sum = 0.f;
+      for (int t = 0; t < L; ++t) {
+        float w = __expf(my_e[t] - mx);
+        my_e[t] = w;
+        sum += w;
+      }
+      const float inv = 1.f / sum;
+      // context + fc1 partial (this row's strand half of fc1)
+      const int strand = row & 1;
+      float lg0 = 0.f, lg1 = 0.f;
+#pragma unroll 1
+      for (int sl = 0; sl < 64; ++sl) {  // 64 slabs of 8 columns = 512 context features
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int t = 0; t < L; ++t) {
+          const uint8_t* src = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES +
+                               (sl & 7) * A_SLAB + row * 16;
+          uint4 hi = __ldcg(reinterpret_cast<const uint4*>(src));
+          uint4 lo = make_uint4(0, 0, 0, 0);
+          if constexpr (P == 2) lo = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
+          float v[8];
+          join8<P, F16>(hi, lo, v);
+          const float w = my_e[t];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+        }
+        const float* f0 = fc_s + strand * 512 + sl * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          lg0 = fmaf(acc[i], f0[i], lg0);
+          lg1 = fmaf(acc[i], f0[1024 + i], lg1);
+        }
+      }
+      lg0 *= inv;
+      lg1 *= inv;
+      lg0 += __shfl_xor_sync(0xffffffffu, lg0, 1);  // strand 1 + strand 2 of the same site (adjacent rows)
+      lg1 += __shfl_xor_sync(0xffffffffu, lg1, 1);
+      const int64_t site = ((int64_t)tile * TILE_ROWS + row) >> 1;
+      if (strand == 0 && site < p.sites) {
+        lg0 += p.fc_b[0];
+        lg1 += p.fc_b[1];
+        const float m2 = fmaxf(lg0, lg1);
+        const float e0 = __expf(lg0 - m2), e1 = __expf(lg1 - m2);
+        const float is = 1.f / (e0 + e1);
+        if (p.logits) {
+          p.logits[site * 2] = lg0;
+          p.logits[site * 2 + 1] = lg1;
+        }
+        if (p.probs) {
+          p.probs[site * 2] = e0 * is;
+          p.probs[site * 2 + 1] = e1 * is;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// act image (one layer) -> (rows, L, 512) fp32, for tests
+template <int P, bool F16>
+__global__ void tc_unpack_act_kernel(const uint8_t* __restrict__ act, float* __restrict__ out, int64_t rows, int L) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (row, t, slab 0..63)
+  if (idx >= rows * L * 64) return;
+  const int sl = (int)(idx % 64);
+  const int t = (int)((idx / 64) % L);
+  const int64_t R = idx / (64 * L);
+  const int64_t tile = R / TILE_ROWS;
+  const int r = (int)(R % TILE_ROWS);
+  const uint8_t* src = act + (((tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES + (sl & 7) * A_SLAB + r * 16;
+  uint4 hi = *reinterpret_cast<const uint4*>(src);
+  uint4 lo = make_uint4(0, 0, 0, 0);
+  if constexpr (P == 2) lo = *reinterpret_cast<const uint4*>(src + CHUNK_BYTES);
+  float v[8];
+  join8<P, F16>(hi, lo, v);
+  float* o = out + (R * L + t) * 512 + sl * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = v[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static uint16_t to_elem(float v, bool f16) {
+  if (f16) {
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+static float from_elem(uint16_t b, bool f16) {
+  if (f16) return __half2float(*reinterpret_cast<__half*>(&b));
+  return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&b));
+}
+
+// Packs `rows` weight rows (given by row_of(n) -> pointer to K floats, K_src valid entries) into
+// [part][kslabs][rows x 8 elems] at dst (uint16 elements).
+template <class RowFn>
+static void pack_image(uint16_t* dst, int rows, int kslabs, int K_src, int P, bool f16, RowFn row_of) {
+  const size_t part_elems = (size_t)kslabs * rows * 8;
+  for (int n = 0; n < rows; ++n) {
+    const float* w = row_of(n);
+    for (int k = 0; k < kslabs * 8; ++k) {
+      const float v = k < K_src ? w[k] : 0.f;
+      const size_t off = (size_t)(k / 8) * rows * 8 + (size_t)n * 8 + (k % 8);
+      const uint16_t hi = to_elem(v, f16);
+      dst[off] = hi;
+      if (P == 2) dst[part_elems + off] = to_elem(v - from_elem(hi, f16), f16);
+    }
+  }
+}
+
+static const HostTensor* findw(ccsm_model* m, const std::string& k) {
+  auto it = m->w.find(k);
+  return it == m->w.end() ? nullptr : &it->second;
+}
+
+int tc_upload_weights(ccsm_model* m) {
+  const int H = m->cfg.hidden, NL = m->cfg.num_layers;
+  if (m->cfg.kind != CCSM_KIND_ATT2S || H != 256 || m->cfg.num_classes != 2 || m->cfg.n_embed != 8 ||
+      m->in_feat > 16 || (m->cfg.feat_flags & ~CCSM_FEAT_NPASS) != 0) {
+    set_error("tensor-core path supports the shipped attbigru2s configuration (hidden 256, 2 classes, "
+              "embed 8, kmer+ipd+pw[+npass]); use precision fp32 for other configurations");
+    return CCSM_EUNSUPPORTED;
+  }
+  if (!m->tc) m->tc = new TcState();
+  TcState& T = *m->tc;
+  const int prec = m->cfg.precision;
+  const int P = (prec == CCSM_PREC_BF16X3 || prec == CCSM_PREC_FP16X3) ? 2 : 1;
+  const bool f16 = (prec == CCSM_PREC_FP16X3 || prec == CCSM_PREC_FP16);
+  cudaDeviceProp prop;
+  CCSM_CUDA(cudaGetDeviceProperties(&prop, m->cfg.device));
+  T.sm_count = prop.multiProcessorCount;
+  static const char* sfx[2] = {"", "_reverse"};
+  T.wimg.resize(NL);
+  T.kx_slabs.resize(NL);
+  std::vector<float> bias((size_t)NL * 2 * 4 * H);
+  for (int l = 0; l < NL; ++l) {
+    const int K = l == 0 ? m->in_feat : 2 * H;
+    const int kxs = l == 0 ? 2 : (2 * H) / 8;
+    T.kx_slabs[l] = kxs;
+    const size_t x_elems = (size_t)P * kxs * 192 * 8, h_elems = (size_t)P * 32 * 192 * 8;
+    std::vector<uint16_t> img((x_elems + h_elems) * 8);
+    for (int d = 0; d < 2; ++d) {
+      const HostTensor* wih = findw(m, "rnn.weight_ih_l" + std::to_string(l) + sfx[d]);
+      const HostTensor* whh = findw(m, "rnn.weight_hh_l" + std::to_string(l) + sfx[d]);
+      const HostTensor* bih = findw(m, "rnn.bias_ih_l" + std::to_string(l) + sfx[d]);
+      const HostTensor* bhh = findw(m, "rnn.bias_hh_l" + std::to_string(l) + sfx[d]);
+      if (!wih || !whh || !bih || !bhh) {
+        set_error("tc finalize: missing GRU tensors for layer %d", l);
+        return CCSM_EKEY;
+      }
+      for (int j = 0; j < 4; ++j) {
+        uint16_t* base = img.data() + (size_t)(d * 4 + j) * (x_elems + h_elems);
+        // X part rows: n_i, r, z   (PyTorch gate row order in weight_ih: r [0,H), z [H,2H), n [2H,3H))
+        pack_image(base, 192, kxs, K, P, f16, [&](int n) {
+          const int g = n / 64, u = j * 64 + n % 64;
+          const int row = (g == 0 ? 2 * H : (g == 1 ? 0 : H)) + u;
+          return wih->data.data() + (size_t)row * K;
+        });
+        // H part rows: r, z, n_h
+        pack_image(base + x_elems, 192, 32, H, P, f16, [&](int n) {
+          const int g = n / 64, u = j * 64 + n % 64;
+          const int row = (g == 0 ? 0 : (g == 1 ? H : 2 * H)) + u;
+          return whh->data.data() + (size_t)row * H;
+        });
+      }
+      float* b = bias.data() + ((size_t)l * 2 + d) * 4 * H;
+      for (int u = 0; u < H; ++u) {
+        b[u] = bih->data[u] + bhh->data[u];                  // b_r
+        b[H + u] = bih->data[H + u] + bhh->data[H + u];      // b_z
+        b[2 * H + u] = bih->data[2 * H + u];                 // b_in
+        b[3 * H + u] = bhh->data[2 * H + u];                 // b_hn (inside r * (.))
+      }
+    }
+    CCSM_TRY(T.wimg[l].reserve(img.size() * 2));
+    CCSM_CUDA(cudaMemcpy(T.wimg[l].p, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  }
+  CCSM_TRY(T.bias.reserve(bias.size() * 4));
+  CCSM_CUDA(cudaMemcpy(T.bias.p, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  for (int which = 0; which < 2; ++which) {
+    const HostTensor* w = findw(m, which == 0 ? "_att3.Wa.weight" : "_att3.Ua.weight");
+    std::vector<uint16_t> img((size_t)P * 64 * 256 * 8);
+    pack_image(img.data(), 256, 64, 2 * H, P, f16, [&](int n) { return w->data.data() + (size_t)n * 2 * H; });
+    DevBuf& dst = which == 0 ? T.wa_img : T.ua_img;
+    CCSM_TRY(dst.reserve(img.size() * 2));
+    CCSM_CUDA(cudaMemcpy(dst.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  }
+  auto up = [&](DevBuf& b, const char* key) -> int {
+    const HostTensor* w = findw(m, key);
+    CCSM_TRY(b.reserve(w->data.size() * 4));
+    CCSM_CUDA(cudaMemcpy(b.p, w->data.data(), w->data.size() * 4, cudaMemcpyHostToDevice));
+    return CCSM_OK;
+  };
+  CCSM_TRY(up(T.va, "_att3.va.weight"));
+  CCSM_TRY(up(T.fc_w, "fc1.weight"));
+  CCSM_TRY(up(T.fc_b, "fc1.bias"));
+  CCSM_TRY(up(T.embed, "embed.weight"));
+  T.P = P;
+  T.f16 = f16;
+  return CCSM_OK;
+}
+
+void tc_release(ccsm_model* m) {
+  if (!m->tc) return;
+  TcState& T = *m->tc;
+  for (auto& b : T.wimg) b.release();
+  T.bias.release(); T.wa_img.release(); T.ua_img.release(); T.va.release(); T.fc_w.release(); T.fc_b.release();
+  T.embed.release(); T.x0img.release(); T.h0img.release();
+  for (auto& b : T.act) b.release();
+  delete m->tc;
+  m->tc = nullptr;
+}
+
+static int tc_reserve(ccsm_model* m, int64_t tiles) {
+  TcState& T = *m->tc;
+  if (tiles <= T.tiles_cap && T.ws_P == T.P) return CCSM_OK;
+  const int L = m->cfg.seq_len, NL = m->cfg.num_layers, P = T.P;
+  CCSM_TRY(T.x0img.reserve((size_t)tiles * L * P * 2 * A_SLAB));
+  CCSM_TRY(T.h0img.reserve((size_t)NL * tiles * 2 * 4 * P * CHUNK_BYTES));
+  for (int i = 0; i < 3; ++i) CCSM_TRY(T.act[i].reserve((size_t)tiles * L * 8 * P * CHUNK_BYTES));
+  T.tiles_cap = tiles;
+  T.ws_P = P;
+  return CCSM_OK;
+}
+
+template <int P, bool F16>
+static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_total, const ccsm_strand* fwd,
+                        const ccsm_strand* rev, const float* h0_f, const float* h0_r, float* logits, float* probs,
+                        cudaStream_t st) {
+  TcState& T = *m->tc;
+  const int L = m->cfg.seq_len, NL = m->cfg.num_layers;
+  int64_t tiles = (sites * 2 + TILE_ROWS - 1) / TILE_ROWS;
+  tiles += tiles & 1;
+  T.last_tiles = tiles;
+  TcStrand s0{fwd->kmer, fwd->kpass, fwd->ipd_means, fwd->pw_means}, s1{rev->kmer, rev->kpass, rev->ipd_means, rev->pw_means};
+  const int64_t rows = tiles * TILE_ROWS;
+  tc_prep_kernel<P, F16><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(
+      tiles, sites, site0, n_total, L, NL, m->cfg.n_vocab, (m->cfg.feat_flags & CCSM_FEAT_NPASS) ? 1 : 0, s0, s1,
+      T.embed.as<float>(), h0_f, h0_r, T.x0img.as<uint8_t>(), T.h0img.as<uint8_t>());
+  count_launch();
+  static bool attr_set[2][2] = {{false, false}, {false, false}};
+  if (!attr_set[P - 1][F16]) {
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)GruCfg<P>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_att_head_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)AttCfg<P>::SMEM));
+    attr_set[P - 1][F16] = true;
+  }
+  for (int l = 0; l < NL; ++l) {
+    GruParams gp;
+    gp.xin = l == 0 ? T.x0img.as<uint8_t>() : T.act[(l - 1) % 3].as<uint8_t>();
+    gp.h0img = T.h0img.as<uint8_t>() + (size_t)l * tiles * 2 * 4 * P * CHUNK_BYTES;
+    gp.out = T.act[l % 3].as<uint8_t>();
+    gp.wimg = T.wimg[l].as<uint8_t>();
+    gp.bias = T.bias.as<float>() + (size_t)l * 2 * 4 * 256;
+    gp.n_tiles = (int)tiles;
+    gp.L = L;
+    gp.kx_slabs = (int)T.kx_slabs[l];
+    const int grid = (int)(tiles < T.sm_count ? tiles : T.sm_count);
+    tc_gru_layer_kernel<P, F16><<<grid, GRU_THREADS, GruCfg<P>::SMEM, st>>>(gp);
+    count_launch();
+  }
+  AttParams ap;
+  ap.act = T.act[(NL - 1) % 3].as<uint8_t>();
+  ap.wa_img = T.wa_img.as<uint8_t>();
+  ap.ua_img = T.ua_img.as<uint8_t>();
+  ap.va = T.va.as<float>();
+  ap.fc_w = T.fc_w.as<float>();
+  ap.fc_b = T.fc_b.as<float>();
+  ap.logits = logits ? logits + site0 * 2 : nullptr;
+  ap.probs = probs ? probs + site0 * 2 : nullptr;
+  ap.n_tiles = (int)tiles;
+  ap.L = L;
+  ap.sites = sites;
+  const int grid = (int)(tiles < T.sm_count ? tiles : T.sm_count);
+  tc_att_head_kernel<P, F16><<<grid, ATT_THREADS, AttCfg<P>::SMEM, st>>>(ap);
+  count_launch();
+  CCSM_CUDA(cudaGetLastError());
+  return CCSM_OK;
+}
+
+int tc_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, const float* h0_f,
+                     const float* h0_r, float* logits, float* probs, cudaStream_t st) {
+  if (!m->tc || m->tc->P == 0) {
+    set_error("tensor-core weights not packed");
+    return CCSM_ESTATE;
+  }
+  TcState& T = *m->tc;
+  // chunk = 8 items per SM: 2 slots x 148 SMs x 4 rounds of row tiles
+  const int64_t max_tiles = (int64_t)T.sm_count * 8;
+  const int64_t chunk_sites = max_tiles * (TILE_ROWS / 2);
+  int64_t need_tiles = ((n < chunk_sites ? n : chunk_sites) * 2 + TILE_ROWS - 1) / TILE_ROWS;
+  need_tiles += need_tiles & 1;
+  CCSM_TRY(tc_reserve(m, need_tiles));
+  for (int64_t s0 = 0; s0 < n; s0 += chunk_sites) {
+    const int64_t sites = (n - s0) < chunk_sites ? (n - s0) : chunk_sites;
+    int rc;
+    if (T.P == 1 && !T.f16) rc = tc_run_chunk<1, false>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
+    else if (T.P == 1 && T.f16) rc = tc_run_chunk<1, true>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
+    else if (T.P == 2 && !T.f16) rc = tc_run_chunk<2, false>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
+    else rc = tc_run_chunk<2, true>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
+    CCSM_TRY(rc);
+  }
+  return CCSM_OK;
+}
+
+int tc_debug_layer_out(ccsm_model* m, int layer, float* host, int64_t cap, int64_t* written) {
+  if (!m->tc || m->tc->last_tiles == 0) {
+    set_error("tc debug: no forward recorded");
+    return CCSM_ESTATE;
+  }
+  TcState& T = *m->tc;
+  const int L = m->cfg.seq_len;
+  const int64_t rows = T.last_tiles * TILE_ROWS;
+  int64_t nfl = rows * L * 512;
+  DevBuf tmp;
+  CCSM_TRY(tmp.reserve((size_t)nfl * 4));
+  const int64_t total = rows * L * 64;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const uint8_t* act = T.act[layer % 3].as<uint8_t>();
+  CCSM_CUDA(cudaDeviceSynchronize());
+  if (T.P == 1 && !T.f16) tc_unpack_act_kernel<1, false><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
+  else if (T.P == 1 && T.f16) tc_unpack_act_kernel<1, true><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
+  else if (T.P == 2 && !T.f16) tc_unpack_act_kernel<2, false><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
+  else tc_unpack_act_kernel<2, true><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
+  count_launch();
+  CCSM_CUDA(cudaDeviceSynchronize());
+  if (nfl > cap) nfl = cap;
+  CCSM_CUDA(cudaMemcpy(host, tmp.p, (size_t)nfl * 4, cudaMemcpyDeviceToHost));
+  tmp.release();
+  *written = nfl;
+  return CCSM_OK;
+}
+
 }  // namespace ccsm

@@ -138,6 +138,10 @@ int  ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const flo
  * Returns the number of floats written (<= cap) or a negative error. */
 int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap);
 
+/* Test hook (tensor-core path): unpacks layer `layer`'s output image of the most recent forward chunk into
+ * (tiles*128 rows, L, 512) float32 host memory; row R = 2*site + strand.  Returns floats written. */
+int64_t ccsm_debug_tc_layer_out(ccsm_model* m, int32_t layer, float* host, int64_t cap);
+
 /* Test hook: one-CTA tcgen05 GEMM  D(128,N) = A(128,K) . B(N,K)^T  with operands rounded to bf16 (or fp16),
  * fp32 accumulate; pins the UMMA descriptor conventions the tensor-core path relies on.  Host pointers. */
 int  ccsm_debug_umma_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, int32_t swap_lbo_sbo,

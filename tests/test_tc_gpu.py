@@ -1,0 +1,89 @@
+"""Tensor-core (tcgen05) path vs the reference fixtures / numpy oracle, through the C ABI."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import att2s_numpy
+from tests.test_parity_gpu import args16, FEATS, EDGE_CASES
+
+pytestmark = pytest.mark.gpu
+
+# parity modes must meet the north-star tolerance; single-pass modes are reported and only
+# sanity-bounded here
+TOL = {"fp16x3": 1e-4, "bf16x3": 1e-4, "fp16": 5e-3, "bf16": 3e-2}
+
+
+@pytest.fixture(scope="module")
+def model(ckpt_att2s):
+    from ccsmeth_b200.models import ModelAttRNN
+    m = ModelAttRNN(21, 3, 2, 0, 256, is_npass=True, model_type="attbigru2s", device=0, precision="fp16x3")
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ckpt_att2s.items()})
+    return m.cuda(0).eval()
+
+
+def run(model, g, pfx=""):
+    h0 = (torch.from_numpy(g[pfx + "h0_f"]), torch.from_numpy(g[pfx + "h0_r"]))
+    logits, probs = model(*[a.cuda() for a in args16(g, pfx)], h0=h0)
+    return logits.cpu().numpy(), probs.cpu().numpy()
+
+
+def layer_out(model, layer, n):
+    from ccsmeth_b200 import _lib
+    tiles = (2 * n + 127) // 128
+    tiles += tiles & 1
+    buf = np.empty(tiles * 128 * 21 * 512, dtype=np.float32)
+    got = _lib.load().ccsm_debug_tc_layer_out(model._handle, layer, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
+    assert got == buf.size, got
+    return buf.reshape(tiles * 128, 21, 512)[:2 * n].reshape(n, 2, 21, 512)
+
+
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3", "fp16", "bf16"])
+def test_tc_matches_reference_synth(model, golden_synth, prec):
+    model.set_precision(prec)
+    _, probs = run(model, golden_synth)
+    err = np.abs(probs - golden_synth["probs"]).max()
+    print("tc %s max|dprob| = %.3e" % (prec, err))
+    assert err <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3"])
+def test_tc_layers_match_oracle(model, ckpt_att2s, golden_synth, prec):
+    model.set_precision(prec)
+    n = 64
+    g = {k: (v[:, :n] if k.startswith("h0") else v[:n]) for k, v in golden_synth.items()}
+    run(model, g)
+    _, _, it = att2s_numpy.forward(ckpt_att2s, *[g[k] for k in FEATS], g["h0_f"], g["h0_r"], return_internals=True)
+    for l in range(3):
+        out = layer_out(model, l, n)
+        for s in range(2):
+            err = np.abs(out[:, s] - it["layers%d" % s][l]).max()
+            assert err <= 2e-4, (l, s, err)
+
+
+@pytest.mark.parametrize("case", EDGE_CASES)
+def test_tc_edge_cases(model, golden_edge, case):
+    model.set_precision("fp16x3")
+    _, probs = run(model, golden_edge, case + ".")
+    assert probs.shape == golden_edge[case + ".probs"].shape
+    assert np.abs(probs - golden_edge[case + ".probs"]).max() <= 1e-4
+
+
+def test_tc_multi_tile_and_chunks(model, golden_synth):
+    """More sites than one pair of row tiles and than one library chunk (148*8*64 sites): every replica of the
+    256 golden sites must reproduce the reference."""
+    model.set_precision("fp16x3")
+    g = golden_synth
+    rep = 300  # 76,800 sites > 75,776 per chunk
+    big = {k: np.concatenate([g[k]] * rep, axis=1 if k.startswith("h0") else 0) for k in FEATS + ("h0_f", "h0_r")}
+    _, probs = run(model, big)
+    probs = probs.reshape(rep, 256, 2)
+    assert np.abs(probs - g["probs"][None]).max() <= 1e-4
+
+
+def test_tc_host_entry(model, golden_synth):
+    model.set_precision("bf16x3")
+    g = golden_synth
+    _, probs = model.forward_host({k: g[k] for k in FEATS}, h0=(g["h0_f"], g["h0_r"]))
+    assert np.abs(probs.numpy() - g["probs"]).max() <= 1e-4
