@@ -1,0 +1,66 @@
+"""Aggregate-mode frequency model, host side (the reference's ccsmeth/call_mods_freq_bam.py, hot part only).
+
+Mirrors ``_cal_modfreq_in_aggregate_mode`` (reference call_mods_freq_bam.py:265-305): zero-pad 5 sites each
+side, sliding windows of 11 neighbouring CpG sites -> (n, 11, 20) histograms and (n, 11) |position offsets|,
+model forward, ``np.round(np.clip(out, 0, 1), 6)``.  The reference runs the model in batches of 1024 on the
+CPU and rebuilds + reloads it for every region (:308-342); here the model is resident on the GPU, the whole
+region goes through in one call, and the h0 stream is still drawn per 1024-slice in the reference's order.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from numpy.lib.stride_tricks import sliding_window_view
+
+from .models import AggrAttRNN
+
+AGGR_BATCH = 1024  # reference call_mods_freq_bam.py:295
+
+
+def _cal_modfreq_in_aggregate_mode(refposes, refposes_histos, model, seq_len=11, only_close=False, h0=None):
+    if len(refposes) == 0:
+        return None
+    pad_len = seq_len // 2
+    histos_mat = np.pad(np.stack(refposes_histos), pad_width=((pad_len, pad_len), (0, 0)),
+                        mode='constant', constant_values=0)
+    histos_mat = np.swapaxes(sliding_window_view(histos_mat, seq_len, axis=0), 1, 2)
+    if not only_close:
+        pos_mat = np.pad(refposes, pad_width=(pad_len, pad_len), mode='constant',
+                         constant_values=(refposes[0] - 1000, refposes[-1] + 1000))
+        pos_mat = sliding_window_view(pos_mat, seq_len)
+        pos_mat_center = np.repeat(refposes, seq_len).reshape((-1, seq_len))
+        pos_mat = np.absolute(np.subtract(pos_mat, pos_mat_center))
+    else:
+        pos_mat = np.pad(refposes, pad_width=(pad_len + 1, pad_len), mode='constant',
+                         constant_values=(refposes[0] - 1000, refposes[-1] + 1000))
+        pos_mat = np.diff(pos_mat)
+        pos_mat = (pos_mat == 2).astype(int)
+        pos_mat = sliding_window_view(pos_mat, seq_len)
+    n = len(histos_mat)
+    if h0 is None:
+        h0 = torch.empty(2 * model.num_layers, n, model.hidden_size)
+        for s in range(0, n, AGGR_BATCH):  # the reference draws one randn per 1024-slice (models.py:661-671)
+            e = min(n, s + AGGR_BATCH)
+            h0[:, s:e] = torch.randn(2 * model.num_layers, e - s, model.hidden_size)
+    out = model(torch.from_numpy(np.ascontiguousarray(pos_mat, dtype=np.float32)),
+                torch.from_numpy(np.ascontiguousarray(histos_mat, dtype=np.float32)), h0=h0)
+    logits = np.round(np.clip(out.cpu().numpy(), 0, 1), 6)
+    return [logits[idx][0] for idx in range(n)]
+
+
+def load_aggr_model(model_path, args, device=0):
+    """Model lifecycle of the reference's per-region loader (call_mods_freq_bam.py:317-342), done once."""
+    if args.model_type not in {"attbigru"}:
+        raise ValueError("--model_type not right!")
+    model = AggrAttRNN(args.seq_len, args.layer_rnn, args.class_num, 0, args.hid_rnn, binsize=args.bin_size,
+                       model_type=args.model_type, device=device)
+    para_dict = torch.load(model_path, map_location=torch.device('cpu'))
+    try:
+        model_dict = model.state_dict()
+        model_dict.update(para_dict)
+        model.load_state_dict(model_dict)
+    except RuntimeError:
+        model.load_state_dict(OrderedDict((k[7:], v) for k, v in para_dict.items()))
+    model = model.cuda(device)
+    model.eval()
+    return model

@@ -391,6 +391,40 @@ int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap) {
   return nfl;
 }
 
+int ccsm_profile_enable(ccsm_model* m, int32_t on) {
+  if (!m) {
+    set_error("ccsm_profile_enable: null model");
+    return CCSM_EINVAL;
+  }
+  m->prof.on = on != 0;
+  return CCSM_OK;
+}
+
+int ccsm_profile_read(ccsm_model* m, double* ms, double* units, int64_t* launches, int32_t nclass) {
+  if (!m || !ms || !units || !launches || nclass < PROF_NCLASS) {
+    set_error("ccsm_profile_read: bad argument");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  for (int i = 0; i < nclass; ++i) {
+    ms[i] = 0;
+    units[i] = 0;
+    launches[i] = 0;
+  }
+  for (auto& r : m->prof.recs) {
+    CCSM_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CCSM_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t;
+    units[r.cls] += r.units;
+    launches[r.cls] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  m->prof.recs.clear();
+  return CCSM_OK;
+}
+
 int64_t ccsm_debug_tc_layer_out(ccsm_model* m, int32_t layer, float* host, int64_t cap) {
   if (!m || !host || layer < 0 || layer >= m->cfg.num_layers) {
     set_error("ccsm_debug_tc_layer_out: bad argument");

@@ -73,6 +73,31 @@ struct Fp32Workspace {
 
 struct TcState;  // tensor-core (tcgen05) path state, defined in tc_path.cu
 
+// Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).
+enum ProfClass { PROF_PREP = 0, PROF_GRU_L0 = 1, PROF_GRU_LN = 2, PROF_ATT = 3, PROF_NCLASS = 4 };
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+  double units;  // sites processed by this launch
+};
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  int begin(int cls, double units, cudaStream_t st) {
+    if (!on) return -1;
+    ProfRec r;
+    r.cls = cls;
+    r.units = units;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+    return (int)recs.size() - 1;
+  }
+  void end(int id, cudaStream_t st) {
+    if (id >= 0) cudaEventRecord(recs[id].b, st);
+  }
+};
+
 }  // namespace ccsm
 
 struct ccsm_model {
@@ -84,6 +109,7 @@ struct ccsm_model {
   ccsm::Fp32Weights fp32;
   ccsm::Fp32Workspace ws32;
   ccsm::TcState* tc = nullptr;
+  ccsm::Profiler prof;
   // host-entry staging
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaEvent_t events[2] = {nullptr, nullptr};

@@ -22,6 +22,7 @@
 //   Two row tiles ("slots") share every weight stage; TMEM holds [n_i | r | z | n_h] x 64 units per slot.
 //   h_t goes back to the next step's A operand through the (L2-resident) act image.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -200,21 +201,30 @@ struct GruParams {
   int kx_slabs;          // 2 (layer 0) or 64
 };
 
-constexpr int GRU_STAGES = 3;
-constexpr int GRU_THREADS = 384;
-
-template <int P>
+// NSLOT = row tiles processed together by one CTA (sharing every weight stage).
+//   NSLOT = 2: one CTA per SM, 384 threads, 3 stages of 56 KB, TMEM 2 x 256 columns (one buffer per slot).
+//   NSLOT = 1: two CTAs per SM, 192 threads each, 4 stages of 20 KB, TMEM 256 columns per CTA: the two
+//              co-resident CTAs overlap one's gate epilogue with the other's MMAs.
+template <int P, int NSLOT>
 struct GruCfg {
-  static constexpr int KS = 8 / P;  // slabs per stage per part
+  static constexpr int KS = NSLOT == 2 ? 8 / P : 4 / P;  // slabs per stage per part
+  static constexpr int STAGES = NSLOT == 2 ? 3 : 4;
+  static constexpr int THREADS = NSLOT == 2 ? 384 : 192;
+  static constexpr int CTAS_PER_SM = NSLOT == 2 ? 1 : 2;
+  static constexpr int EPI_WARP0 = NSLOT == 2 ? 4 : 2;
+  static constexpr uint32_t TMEM_COLS = NSLOT * 256;
   static constexpr uint32_t B_PART = KS * G_SLAB;
   static constexpr uint32_t A_PART = KS * A_SLAB;
-  static constexpr uint32_t STAGE = P * (B_PART + 2 * A_PART);  // 57344 for both P
-  static constexpr uint32_t SMEM = GRU_STAGES * STAGE + 2 * 4 * 256 * 4;
+  static constexpr uint32_t STAGE = P * (B_PART + NSLOT * A_PART);
+  static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
 };
 
-template <int P, bool F16>
-__global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruParams p) {
-  using C = GruCfg<P>;
+template <int P, bool F16, int NSLOT>
+__global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::CTAS_PER_SM)
+    tc_gru_layer_kernel(const GruParams p) {
+  using C = GruCfg<P, NSLOT>;
+  constexpr int GRU_STAGES = C::STAGES;
+  constexpr int GRU_THREADS = C::THREADS;
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -232,13 +242,13 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
       mbar_init(empty0 + 8 * i, 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 256);
-    mbar_init(h_ready, 256);
+    mbar_init(tmem_empty, NSLOT * 128);
+    mbar_init(h_ready, NSLOT * 128);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * 4 * 256; i += GRU_THREADS) bias_s[i] = p.bias[i];
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
   const uint32_t tmem = tmem_base_s;
   const uint32_t smem_base = smem_u32(smem);
   const int L = p.L;
-  const int n_items = p.n_tiles;  // (n_tiles / 2 pairs) x 2 directions
+  const int n_items = (p.n_tiles / NSLOT) * 2;  // groups of NSLOT row tiles x 2 directions
   const size_t xbytes = (size_t)P * p.kx_slabs * G_SLAB, hbytes = (size_t)P * 32 * G_SLAB;
   const size_t wj_bytes = xbytes + hbytes;
 
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
       uint32_t gstep = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int pair = item >> 1, d = item & 1;
-        const int64_t tile0 = 2 * (int64_t)pair;
+        const int64_t tile0 = NSLOT * (int64_t)pair;
         for (int s = 0; s < L; ++s, ++gstep) {
           const int t = d ? (L - 1 - s) : s;
           const int tprev = d ? t + 1 : t - 1;
@@ -275,15 +285,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
                 mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
                 const uint32_t fb = full0 + 8 * stage;
                 const uint32_t sb = smem_base + stage * C::STAGE;
-                mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + 2 * A_SLAB));
+                mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + NSLOT * A_SLAB));
                 // weights
                 const uint8_t* wsrc = wj + (part ? xbytes : 0);
 #pragma unroll
                 for (int pp = 0; pp < P; ++pp)
                   bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb);
-                // activations of both slots
+                // activations of every slot
 #pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {
+                for (int sl = 0; sl < NSLOT; ++sl) {
                   const int64_t tile = tile0 + sl;
                   const uint8_t* asrc;
                   size_t part_stride;
@@ -339,7 +349,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
                 for (int ks = 0; ks < ns / 2; ++ks) {
                   const bool first = (so == 0 && ks == 0);
 #pragma unroll
-                  for (int sl = 0; sl < 2; ++sl) {
+                  for (int sl = 0; sl < NSLOT; ++sl) {
                     const uint32_t dcol = tmem + sl * 256;
 #pragma unroll
                     for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
@@ -373,16 +383,16 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= C::EPI_WARP0) {
     // ===================== gate epilogue =====================
-    const int ew = warp - 4;
-    const int slot = ew >> 2, quad = ew & 3;
+    // tcgen05.ld lane rule: a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int slot = (warp - C::EPI_WARP0) >> 2, quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
     uint32_t chunk = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int pair = item >> 1, d = item & 1;
-      const int64_t tile = 2 * (int64_t)pair + slot;
+      const int64_t tile = NSLOT * (int64_t)pair + slot;
       const float* bz = bias_s + d * 4 * 256;
       for (int s = 0; s < L; ++s) {
         const int t = d ? (L - 1 - s) : s;
@@ -392,19 +402,20 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
               (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
                        : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
           uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          // prefetch h_{t_prev} for this row's 64 units (L2 latency overlaps the MMAs of this chunk)
+          uint4 hph[8], hpl[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + q * A_SLAB + row * 16));
+            if constexpr (P == 2)
+              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + q * A_SLAB + row * 16));
+            else
+              hpl[q] = make_uint4(0, 0, 0, 0);
+          }
           mbar_wait(tmem_full, chunk & 1);
           tc_fence_after();
-#pragma unroll 1
-          for (int ub = 0; ub < 4; ++ub) {
-            uint4 hph[2], hpl[2];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (ub * 2 + q) * A_SLAB + row * 16));
-              if constexpr (P == 2)
-                hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + (ub * 2 + q) * A_SLAB + row * 16));
-              else
-                hpl[q] = make_uint4(0, 0, 0, 0);
-            }
+          for (int ub = 0; ub < 4; ++ub) {
             uint32_t ani[16], ar[16], az[16], anh[16];
             tmem_ld16(trow + 0 + ub * 16, ani);
             tmem_ld16(trow + 64 + ub * 16, ar);
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float hp[8], hn[8];
-              join8<P, F16>(hph[q], hpl[q], hp);
+              join8<P, F16>(hph[ub * 2 + q], hpl[ub * 2 + q], hp);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int u = j * 64 + ub * 16 + q * 8 + i;
@@ -444,7 +455,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) tc_gru_layer_kernel(const GruP
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -626,17 +637,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int t = 0; t < L; ++t) {
-          const uint8_t* src = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES +
-                               (sl & 7) * A_SLAB + row * 16;
-          uint4 hi = __ldcg(reinterpret_cast<const uint4*>(src));
-          uint4 lo = make_uint4(0, 0, 0, 0);
-          if constexpr (P == 2) lo = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
-          float v[8];
-          join8<P, F16>(hi, lo, v);
-          const float w = my_e[t];
+        constexpr int TB = 7;  // loads in flight per thread (L = 21 -> 3 batches)
+        for (int t0 = 0; t0 < L; t0 += TB) {
+          uint4 hi[TB], lo[TB];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+          for (int k = 0; k < TB; ++k) {
+            const int t = (t0 + k) < L ? (t0 + k) : (L - 1);
+            const uint8_t* src = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES +
+                                 (sl & 7) * A_SLAB + row * 16;
+            hi[k] = __ldcg(reinterpret_cast<const uint4*>(src));
+            if constexpr (P == 2) lo[k] = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
+            else lo[k] = make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int k = 0; k < TB; ++k) {
+            float v[8];
+            join8<P, F16>(hi[k], lo[k], v);
+            const float w = (t0 + k) < L ? my_e[t0 + k] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+          }
         }
         const float* f0 = fc_s + strand * 512 + sl * 8;
 #pragma unroll
@@ -840,6 +860,15 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
   return CCSM_OK;
 }
 
+static int gru_nslot() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CCSM_TC_NSLOT");
+    v = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  return v;
+}
+
 template <int P, bool F16>
 static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_total, const ccsm_strand* fwd,
                         const ccsm_strand* rev, const float* h0_f, const float* h0_r, float* logits, float* probs,
@@ -851,14 +880,18 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
   T.last_tiles = tiles;
   TcStrand s0{fwd->kmer, fwd->kpass, fwd->ipd_means, fwd->pw_means}, s1{rev->kmer, rev->kpass, rev->ipd_means, rev->pw_means};
   const int64_t rows = tiles * TILE_ROWS;
+  int pid = m->prof.begin(PROF_PREP, (double)sites, st);
   tc_prep_kernel<P, F16><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(
       tiles, sites, site0, n_total, L, NL, m->cfg.n_vocab, (m->cfg.feat_flags & CCSM_FEAT_NPASS) ? 1 : 0, s0, s1,
       T.embed.as<float>(), h0_f, h0_r, T.x0img.as<uint8_t>(), T.h0img.as<uint8_t>());
+  m->prof.end(pid, st);
   count_launch();
   static bool attr_set[2][2] = {{false, false}, {false, false}};
   if (!attr_set[P - 1][F16]) {
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)GruCfg<P>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)GruCfg<P, 1>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)GruCfg<P, 2>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_att_head_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)AttCfg<P>::SMEM));
     attr_set[P - 1][F16] = true;
@@ -873,8 +906,18 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
     gp.n_tiles = (int)tiles;
     gp.L = L;
     gp.kx_slabs = (int)T.kx_slabs[l];
-    const int grid = (int)(tiles < T.sm_count ? tiles : T.sm_count);
-    tc_gru_layer_kernel<P, F16><<<grid, GRU_THREADS, GruCfg<P>::SMEM, st>>>(gp);
+    pid = m->prof.begin(l == 0 ? PROF_GRU_L0 : PROF_GRU_LN, (double)sites, st);
+    if (gru_nslot() == 2) {
+      const int64_t items = tiles;  // (tiles / 2) x 2 directions
+      const int grid = (int)(items < T.sm_count ? items : T.sm_count);
+      tc_gru_layer_kernel<P, F16, 2><<<grid, GruCfg<P, 2>::THREADS, GruCfg<P, 2>::SMEM, st>>>(gp);
+    } else {
+      const int64_t items = tiles * 2;
+      const int64_t slots = (int64_t)T.sm_count * 2;
+      const int grid = (int)(items < slots ? items : slots);
+      tc_gru_layer_kernel<P, F16, 1><<<grid, GruCfg<P, 1>::THREADS, GruCfg<P, 1>::SMEM, st>>>(gp);
+    }
+    m->prof.end(pid, st);
     count_launch();
   }
   AttParams ap;
@@ -890,7 +933,9 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
   ap.L = L;
   ap.sites = sites;
   const int grid = (int)(tiles < T.sm_count ? tiles : T.sm_count);
+  pid = m->prof.begin(PROF_ATT, (double)sites, st);
   tc_att_head_kernel<P, F16><<<grid, ATT_THREADS, AttCfg<P>::SMEM, st>>>(ap);
+  m->prof.end(pid, st);
   count_launch();
   CCSM_CUDA(cudaGetLastError());
   return CCSM_OK;

@@ -220,6 +220,21 @@ class ModelAttRNN(_NativeModule):
                                                       probs.data_ptr(), ctypes.c_void_p(stream)))
         return logits, probs
 
+    def profile(self, on=True):
+        """Enable/disable per-kernel CUDA-event timing inside the library (include/ccsm.h ccsm_profile_*)."""
+        handle, _ = self._ensure_handle()
+        _lib.check(_lib.load().ccsm_profile_enable(handle, 1 if on else 0))
+
+    def profile_read(self):
+        """Returns {class: (ms, sites, launches)} accumulated since the last read."""
+        handle, _ = self._ensure_handle()
+        ms = (ctypes.c_double * 4)()
+        units = (ctypes.c_double * 4)()
+        launches = (ctypes.c_int64 * 4)()
+        _lib.check(_lib.load().ccsm_profile_read(handle, ms, units, launches, 4))
+        names = ("prep", "gru_l0", "gru_ln", "att_head")
+        return {n: (ms[i], units[i], int(launches[i])) for i, n in enumerate(names)}
+
     def forward_host(self, feats, h0=None):
         """Host-buffer entry (include/ccsm.h ccsm_forward_att2s_host): `feats` maps the live tensor names
         (kmer, kpass, ipd, pw and the same with a '2' suffix) to float32 CPU tensors / numpy arrays of shape

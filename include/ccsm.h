@@ -138,6 +138,13 @@ int  ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const flo
  * Returns the number of floats written (<= cap) or a negative error. */
 int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap);
 
+/* Per-kernel-class device timing for bench.py's roofline: while enabled, every tensor-core kernel launch is
+ * bracketed by CUDA events recorded on the launching stream.  ccsm_profile_read waits for them and returns,
+ * per class {0: feature/h0 packing, 1: GRU layer 0, 2: GRU layers >= 1, 3: attention + head}, the summed
+ * milliseconds, the summed sites processed and the launch count (arrays of >= 4 entries), then resets. */
+int  ccsm_profile_enable(ccsm_model* m, int32_t on);
+int  ccsm_profile_read(ccsm_model* m, double* ms, double* units, int64_t* launches, int32_t nclass);
+
 /* Test hook (tensor-core path): unpacks layer `layer`'s output image of the most recent forward chunk into
  * (tiles*128 rows, L, 512) float32 host memory; row R = 2*site + strand.  Returns floats written. */
 int64_t ccsm_debug_tc_layer_out(ccsm_model* m, int32_t layer, float* host, int64_t cap);

@@ -126,3 +126,17 @@ def test_set_weight_rejects_wrong_shape(model):
     assert rc == _lib.EKEY and b"size mismatch" in lib.ccsm_last_error()
     rc = lib.ccsm_set_weight(model._handle, b"nonexistent.weight", a.ctypes.data_as(ctypes.c_void_p), shp, 2)
     assert rc == _lib.EKEY
+
+
+def test_aggr_loop_matches_reference_loop(ckpt_aggr, golden_aggr):
+    """_cal_modfreq_in_aggregate_mode vs the reference's own loop output (seeded randn h0 per 1024-slice)."""
+    from ccsmeth_b200.models import AggrAttRNN
+    from ccsmeth_b200.call_mods_freq_bam import _cal_modfreq_in_aggregate_mode
+    g = golden_aggr
+    m = AggrAttRNN(11, 1, 1, 0, 32, binsize=20, model_type="attbigru", device=0)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ckpt_aggr.items()})
+    m = m.cuda(0).eval()
+    torch.manual_seed(int(g["tseed"]))
+    probs = _cal_modfreq_in_aggregate_mode(g["pos"], list(g["histos"]), m, 11, False)
+    assert len(probs) == len(g["loop_probs"])
+    assert np.abs(np.array(probs) - g["loop_probs"]).max() <= 2e-6
