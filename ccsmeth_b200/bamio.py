@@ -1,0 +1,303 @@
+"""Minimal BAM reader/writer (BGZF via zlib) for the call_mods path -- no pysam/htslib dependency.
+
+The reference does all BAM I/O through pysam (reader ccsmeth/extract_features.py:129-177, writer
+ccsmeth/call_modifications.py:410-462).  pysam is not part of this environment, and the path only
+needs: iterate records of a (possibly unaligned) HiFi BAM, read the kinetics tags, and write the same
+records back with MM/ML tags added.  Records are kept as raw bytes; only the fields the path uses are
+decoded, and untouched aux tags are copied byte-for-byte on output (types preserved exactly).
+
+SAM/BAM spec section 4 (BGZF: 4.1; alignment record layout: 4.2; aux types: 4.2.4).
+"""
+import struct
+import zlib
+
+import numpy as np
+
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+_SEQ_DECODE = "=ACMGRSVTWYHKDBN"
+_SEQ_LUT = np.array([ord(_SEQ_DECODE[i >> 4]) for i in range(256)], dtype=np.uint8), \
+    np.array([ord(_SEQ_DECODE[i & 15]) for i in range(256)], dtype=np.uint8)
+_AUX_FIXED = {ord('A'): 1, ord('c'): 1, ord('C'): 1, ord('s'): 2, ord('S'): 2, ord('i'): 4, ord('I'): 4, ord('f'): 4}
+_AUX_FMT = {ord('c'): '<b', ord('C'): '<B', ord('s'): '<h', ord('S'): '<H', ord('i'): '<i', ord('I'): '<I', ord('f'): '<f'}
+_ARR_DTYPE = {ord('c'): np.int8, ord('C'): np.uint8, ord('s'): np.int16, ord('S'): np.uint16, ord('i'): np.int32,
+              ord('I'): np.uint32, ord('f'): np.float32}
+
+
+class BgzfReader:
+    """Sequential reader over concatenated BGZF blocks."""
+
+    def __init__(self, path):
+        self.f = open(path, "rb")
+        self.buf = b""
+        self.pos = 0
+
+    def _fill(self):
+        hdr = self.f.read(18)
+        if len(hdr) < 18:
+            return False
+        if hdr[:4] != b"\x1f\x8b\x08\x04":
+            raise ValueError("not a BGZF block")
+        xlen = struct.unpack_from("<H", hdr, 10)[0]
+        extra = hdr[12:18] + self.f.read(xlen - 6)
+        bsize = None
+        i = 0
+        while i + 4 <= len(extra):
+            si1, si2, slen = extra[i], extra[i + 1], struct.unpack_from("<H", extra, i + 2)[0]
+            if si1 == 66 and si2 == 67:
+                bsize = struct.unpack_from("<H", extra, i + 4)[0]
+            i += 4 + slen
+        if bsize is None:
+            raise ValueError("BGZF block without BC subfield")
+        cdata = self.f.read(bsize - xlen - 19)
+        self.f.read(8)  # crc32 + isize
+        data = zlib.decompress(cdata, -15) if cdata else b""
+        self.buf = self.buf[self.pos:] + data
+        self.pos = 0
+        return True
+
+    def read(self, n):
+        while len(self.buf) - self.pos < n:
+            if not self._fill():
+                break
+        out = self.buf[self.pos:self.pos + n]
+        self.pos += len(out)
+        return out
+
+    def close(self):
+        self.f.close()
+
+
+class BgzfWriter:
+    def __init__(self, path, level=6):
+        self.f = open(path, "wb")
+        self.level = level
+        self.buf = bytearray()
+
+    def write(self, data):
+        self.buf += data
+        while len(self.buf) >= 65280:
+            self._flush_block(bytes(self.buf[:65280]))
+            del self.buf[:65280]
+
+    def _flush_block(self, data):
+        c = zlib.compressobj(self.level, zlib.DEFLATED, -15)
+        cdata = c.compress(data) + c.flush()
+        bsize = len(cdata) + 25
+        self.f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + cdata +
+                     struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+    def close(self):
+        if self.buf:
+            self._flush_block(bytes(self.buf))
+            self.buf = bytearray()
+        self.f.write(_BGZF_EOF)
+        self.f.close()
+
+
+class BamRecord:
+    """One alignment record; `raw` excludes the leading block_size field."""
+    __slots__ = ("raw", "ref_id", "pos", "l_read_name", "mapq", "n_cigar", "flag", "l_seq", "_aux_off", "_tags",
+                 "reference_name")
+
+    def __init__(self, raw):
+        self.raw = raw
+        (self.ref_id, self.pos, self.l_read_name, self.mapq, _bin, self.n_cigar, self.flag, self.l_seq,
+         _nref, _npos, _tlen) = struct.unpack_from("<iiBBHHHiiii", raw, 0)
+        self._aux_off = 32 + self.l_read_name + 4 * self.n_cigar + (self.l_seq + 1) // 2 + self.l_seq
+        self._tags = None
+        self.reference_name = None  # filled in by BamReader for mapped records
+
+    # ---- the attributes the extractor reads (reference extract_features.py:88-126)
+    @property
+    def query_name(self):
+        return self.raw[32:32 + self.l_read_name - 1].decode("ascii")
+
+    @property
+    def is_unmapped(self):
+        return bool(self.flag & 0x4)
+
+    @property
+    def is_reverse(self):
+        return bool(self.flag & 0x10)
+
+    @property
+    def is_secondary(self):
+        return bool(self.flag & 0x100)
+
+    @property
+    def is_duplicate(self):
+        return bool(self.flag & 0x400)
+
+    @property
+    def is_supplementary(self):
+        return bool(self.flag & 0x800)
+
+    @property
+    def cigartuples(self):
+        off = 32 + self.l_read_name
+        ops = np.frombuffer(self.raw, dtype="<u4", count=self.n_cigar, offset=off)
+        return [(int(v & 0xf), int(v >> 4)) for v in ops]
+
+    @property
+    def query_sequence(self):
+        off = 32 + self.l_read_name + 4 * self.n_cigar
+        packed = np.frombuffer(self.raw, dtype=np.uint8, count=(self.l_seq + 1) // 2, offset=off)
+        out = np.empty(2 * len(packed), dtype=np.uint8)
+        out[0::2] = _SEQ_LUT[0][packed]
+        out[1::2] = _SEQ_LUT[1][packed]
+        return out[:self.l_seq].tobytes().decode("ascii")
+
+    def get_forward_sequence(self):
+        s = self.query_sequence
+        if self.is_reverse:
+            from .utils.process_utils import complement_seq
+            return complement_seq(s)
+        return s
+
+    @property
+    def query_alignment_start(self):
+        ct = self.cigartuples
+        return ct[0][1] if ct and ct[0][0] == 4 else 0
+
+    @property
+    def query_alignment_end(self):
+        ct = self.cigartuples
+        end = self.l_seq
+        if ct and ct[-1][0] == 4:
+            end -= ct[-1][1]
+        return end
+
+    # ---- pysam-compatible names the reference's extractor touches in align mode
+    @property
+    def mapping_quality(self):
+        return self.mapq
+
+    @property
+    def reference_start(self):
+        return self.pos
+
+    @property
+    def reference_end(self):
+        if self.is_unmapped or self.n_cigar == 0:
+            return None
+        return self.pos + sum(l for op, l in self.cigartuples if op in (0, 2, 3, 7, 8))
+
+    def get_cigar_stats(self):
+        base = [0] * 11
+        blocks = [0] * 11
+        for op, l in self.cigartuples:
+            base[op] += l
+            blocks[op] += 1
+        try:
+            base[10] = int(self.get_tag("NM"))
+        except KeyError:
+            pass
+        return base, blocks
+
+    # ---- aux tags
+    def _parse_tags(self):
+        tags = {}
+        raw, i, n = self.raw, self._aux_off, len(self.raw)
+        while i + 3 <= n:
+            tag = raw[i:i + 2].decode("ascii")
+            ty = raw[i + 2]
+            start = i
+            i += 3
+            if ty in _AUX_FIXED:
+                ln = _AUX_FIXED[ty]
+                val = raw[i:i + 1].decode("ascii") if ty == ord('A') else struct.unpack_from(_AUX_FMT[ty], raw, i)[0]
+                i += ln
+            elif ty in (ord('Z'), ord('H')):
+                j = raw.index(b"\x00", i)
+                val = raw[i:j].decode("ascii")
+                i = j + 1
+            elif ty == ord('B'):
+                sub = raw[i]
+                cnt = struct.unpack_from("<I", raw, i + 1)[0]
+                dt = np.dtype(_ARR_DTYPE[sub]).newbyteorder("<")
+                val = np.frombuffer(raw, dtype=dt, count=cnt, offset=i + 5)
+                i += 5 + cnt * dt.itemsize
+            else:
+                raise ValueError("bad aux type %r in read %s" % (chr(ty), self.query_name))
+            tags[tag] = (val, start, i)
+        self._tags = tags
+
+    def get_tag(self, name):
+        if self._tags is None:
+            self._parse_tags()
+        if name not in self._tags:
+            raise KeyError(name)
+        return self._tags[name][0]
+
+    def has_tag(self, name):
+        if self._tags is None:
+            self._parse_tags()
+        return name in self._tags
+
+    def with_tags(self, drop, mm=None, ml=None):
+        """Record bytes (without block_size) with tags in `drop` removed and MM:Z / ML:B:C appended
+        (reference _bam2modbam.py:211-226 `_refill_tags`)."""
+        if self._tags is None:
+            self._parse_tags()
+        out = bytearray(self.raw[:self._aux_off])
+        for tag, (_, s, e) in self._tags.items():
+            if tag in drop:
+                continue
+            out += self.raw[s:e]
+        if mm is not None:
+            out += b"MMZ" + mm.encode("ascii") + b"\x00"
+            out += b"MLBC" + struct.pack("<I", len(ml)) + bytes(bytearray(ml))
+        return bytes(out)
+
+
+class BamReader:
+    def __init__(self, path):
+        self.bg = BgzfReader(path)
+        if self.bg.read(4) != b"BAM\x01":
+            raise ValueError("%s is not a BAM file" % path)
+        l_text = struct.unpack("<i", self.bg.read(4))[0]
+        self.header_text = self.bg.read(l_text).rstrip(b"\x00").decode("utf-8", "replace")
+        n_ref = struct.unpack("<i", self.bg.read(4))[0]
+        self.references = []
+        for _ in range(n_ref):
+            l_name = struct.unpack("<i", self.bg.read(4))[0]
+            name = self.bg.read(l_name)[:-1].decode("ascii")
+            l_ref = struct.unpack("<i", self.bg.read(4))[0]
+            self.references.append((name, l_ref))
+
+    def __iter__(self):
+        while True:
+            b = self.bg.read(4)
+            if len(b) < 4:
+                return
+            n = struct.unpack("<i", b)[0]
+            rec = BamRecord(self.bg.read(n))
+            if 0 <= rec.ref_id < len(self.references):
+                rec.reference_name = self.references[rec.ref_id][0]
+            yield rec
+
+    def close(self):
+        self.bg.close()
+
+
+class BamWriter:
+    def __init__(self, path, header_text, references, level=6):
+        self.bg = BgzfWriter(path, level)
+        text = header_text.encode("utf-8")
+        self.bg.write(b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(references)))
+        for name, l_ref in references:
+            nm = name.encode("ascii") + b"\x00"
+            self.bg.write(struct.pack("<i", len(nm)) + nm + struct.pack("<i", l_ref))
+
+    def write_raw(self, raw):
+        self.bg.write(struct.pack("<i", len(raw)) + raw)
+
+    def close(self):
+        self.bg.close()
+
+
+def add_pg_line(header_text, version, cmdline):
+    """Input header + @PG ID:ccsmeth (reference call_modifications.py:445)."""
+    if header_text and not header_text.endswith("\n"):
+        header_text += "\n"
+    return header_text + "@PG\tPN:ccsmeth\tID:ccsmeth\tVN:%s\tCL:%s\n" % (version, cmdline)

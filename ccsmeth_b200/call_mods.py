@@ -1,0 +1,252 @@
+"""`call_mods` for BAM input on one process per GPU: BAM -> features -> model -> MM/ML tags -> modbam.
+
+Keeps the reference's `ccsmeth call_mods` flag surface (ccsmeth/ccsmeth.py:196-326 ==
+ccsmeth/call_modifications.py:616-752) and its output rules:
+  * per read: predictions sorted by loc; ``MM:Z:C+m?,d0,d1,...;`` deltas = skipped C's of the FORWARD read
+    sequence between called C's (_bam2modbam.py:187-203); ``ML:B:C`` = floor(p*256), 255 if p >= 1 (:206-208)
+  * existing MM/ML dropped, fi/fp/ri/rp dropped unless --keep_pulse (:215-218)
+  * reads without predictions are still written (call_modifications.py:239-242)
+  * header gets an ``@PG ID:ccsmeth`` line (:445)
+The reference wires reader / extractors / model workers / writer with multiprocessing queues
+(call_modifications.py:520-590); here each rank runs a reader+extractor thread feeding the GPU call, takes the
+hole-batches with ``batch_idx % world == rank`` and writes its own BAM shard.  Sorting/indexing
+(call_modifications.py:592-607) needs samtools and is left to the caller: the output is always unsorted.
+
+    python -m ccsmeth_b200.call_mods -i in.hifi.bam -m model.ckpt -o out_prefix [--mode denovo] ...
+"""
+import argparse
+import os
+import queue
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+from . import VERSION, parallel
+from .bamio import BamReader, BamWriter, add_pg_line
+from .call_modifications import draw_h0_stream, load_model
+from .extract_features import batch_read_features, extract_read
+from .utils.process_utils import str2bool
+
+IUPAC = {'A': 'A', 'C': 'C', 'G': 'G', 'T': 'T', 'R': 'AG', 'M': 'AC', 'S': 'CG', 'Y': 'CT', 'K': 'GT', 'W': 'AT',
+         'B': 'CGT', 'D': 'AGT', 'H': 'ACT', 'V': 'ACG', 'N': 'ACGT'}
+
+
+def get_motif_seqs(motifs):
+    """IUPAC motif expansion (reference process_utils.py:140-170)."""
+    out = []
+    for m in motifs.strip().split(","):
+        seqs = [""]
+        for b in m.strip().upper():
+            seqs = [s + x for s in seqs for x in IUPAC[b]]
+        out += seqs
+    return out
+
+
+def convert_locs_to_mmtag(locs, fwd_seq_bytes, base=ord('C')):
+    """MM deltas (reference _bam2modbam.py:187-203): order of each called loc among the read's C's, then
+    first order followed by gaps - 1.  Raises AssertionError like the reference when a loc is not a C."""
+    assert len(locs) > 0
+    base_all = np.nonzero(fwd_seq_bytes == base)[0]
+    orders = np.searchsorted(base_all, locs)
+    assert orders[-1] < len(base_all) and np.array_equal(base_all[np.minimum(orders, len(base_all) - 1)], locs)
+    mm = np.empty(len(orders), dtype=np.int64)
+    mm[0] = orders[0]
+    mm[1:] = np.diff(orders) - 1
+    return mm
+
+
+def convert_probs_to_mltag(probs):
+    """floor(p * 256), 255 if p >= 1, in float32 like the reference's np.float32 scalars (_bam2modbam.py:206-208)."""
+    p = np.asarray(probs, dtype=np.float32)
+    return np.where(p < 1, np.floor(p * np.float32(256)), 255).astype(np.uint8)
+
+
+def call_holebatch(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=None):
+    """One hole-batch (list of BamRecord) -> (per-read list of (locs, prob_1_norm) or None, n_sites, n_model_batches).
+    Equivalent of process_one_holebatch + _batch_feature_list2s + _call_mods2s (reference
+    extract_features.py:409-431, call_modifications.py:73-123,170-227)."""
+    feats = []
+    for i, r in enumerate(reads):
+        try:
+            rf = extract_read(r, motifs, args, holeids_e, holeids_ne)
+        except Exception:  # the reference counts such reads as failed and goes on (extract_features.py:416-429)
+            rf = None
+        if rf is not None and len(rf):
+            feats.append((i, rf))
+    arrays, holeidx, locs = batch_read_features(feats, args.seq_len)
+    per_read = [None] * len(reads)
+    if arrays is None:
+        return per_read, 0, 0
+    n = len(locs)
+    if h0 is None:
+        h0 = draw_h0_stream(n, args.batch_size, model.num_layers, model.hidden_size)
+    _, probs = model.forward_host(arrays, h0=h0)
+    p = probs.numpy()
+    prob1 = np.round(p[:, 1] / (p[:, 0] + p[:, 1]), 6)  # reference call_modifications.py:223 (float32)
+    bounds = np.nonzero(np.diff(holeidx))[0] + 1
+    starts = np.concatenate(([0], bounds))
+    ends = np.concatenate((bounds, [n]))
+    for s, e in zip(starts, ends):
+        per_read[int(holeidx[s])] = (locs[s:e], prob1[s:e])
+    return per_read, n, (n + args.batch_size - 1) // args.batch_size
+
+
+def tag_read(rec, pred, rm_pulse):
+    """BamRecord + (locs, probs) -> (record bytes with MM/ML, mm_flag)  (reference call_modifications.py:230-266)."""
+    drop = {"MM", "ML"} | ({"fi", "fp", "ri", "rp"} if rm_pulse else set())
+    if pred is None or len(pred[0]) == 0:
+        return rec.with_tags(drop), 0
+    locs, probs = pred
+    order = np.argsort(locs, kind="stable")
+    locs, probs = locs[order], probs[order]
+    fwd = np.frombuffer(rec.get_forward_sequence().encode("ascii"), dtype=np.uint8)
+    try:
+        mm = convert_locs_to_mmtag(locs, fwd)
+    except AssertionError:
+        return rec.with_tags(drop), 0  # reference writes the read without tags (:260-263)
+    ml = convert_probs_to_mltag(probs)
+    return rec.with_tags(drop, "C+m?," + ",".join(map(str, mm.tolist())) + ";", ml.tolist()), 1
+
+
+def _reader_thread(path, args, rank, world, q):
+    try:
+        rd = BamReader(path)
+        q.put(("header", rd.header_text, rd.references))
+        batch, bidx = [], 0
+        for rec in rd:
+            batch.append(rec)
+            if len(batch) == args.holes_batch:
+                if parallel.owns_holebatch(bidx, rank, world):
+                    q.put(("batch", bidx, batch))
+                batch, bidx = [], bidx + 1
+        if batch and parallel.owns_holebatch(bidx, rank, world):
+            q.put(("batch", bidx, batch))
+        rd.close()
+        q.put(("done",))
+    except Exception as e:  # surface reader failures to the main thread
+        q.put(("error", e))
+
+
+def call_mods(args):
+    """Runs the whole path; returns the summed run counters
+    {sites, model_batches, reads_written, reads_with_mm} (all ranks)."""
+    t0 = time.time()
+    if args.seq_len % 2 == 0:
+        raise ValueError("--seq_len must be odd")
+    if not os.path.exists(args.model_file):
+        raise ValueError("--model_file is not set right!")
+    if not os.path.exists(args.input):
+        raise ValueError("--input_file does not exist!")
+    if not (args.input.endswith(".bam")):
+        raise ValueError("ccsmeth_b200 call_mods takes BAM input (features.tsv input is out of scope)")
+    if str2bool(args.is_map) or str2bool(args.is_stds):
+        raise ValueError("--is_map/--is_stds features are not extracted by ccsmeth_b200 (SURVEY.md section 8f)")
+    rank, world, local = parallel.init_from_env()
+    out_dir = os.path.dirname(os.path.abspath(args.output))
+    os.makedirs(out_dir, exist_ok=True)
+    out_modbam = args.output + (".modbam.bam" if world == 1 else ".rank%d.modbam.bam" % rank)
+    torch.manual_seed(args.tseed)  # seeds the process that draws h0 (the reference seeds only its parent, :479-481)
+    model = load_model(args.model_file, args, device=local, precision=getattr(args, "precision", None))
+    motifs = get_motif_seqs(args.motifs)
+    holeids_e = _get_holes(args.holeids_e) if args.holeids_e else None
+    holeids_ne = _get_holes(args.holeids_ne) if args.holeids_ne else None
+
+    q = queue.Queue(maxsize=8)
+    th = threading.Thread(target=_reader_thread, args=(args.input, args, rank, world, q), daemon=True)
+    th.start()
+    msg = q.get()
+    if msg[0] == "error":
+        raise msg[1]
+    _, header_text, references = msg
+    wr = BamWriter(out_modbam, add_pg_line(header_text, VERSION, " ".join(sys.argv)), references)
+    counts = [0, 0, 0, 0]
+    rm_pulse = not args.keep_pulse
+    while True:
+        msg = q.get()
+        if msg[0] == "done":
+            break
+        if msg[0] == "error":
+            raise msg[1]
+        _, bidx, reads = msg
+        per_read, n_sites, n_batches = call_holebatch(model, reads, motifs, args, holeids_e, holeids_ne)
+        counts[0] += n_sites
+        counts[1] += n_batches
+        for rec, pred in zip(reads, per_read):
+            raw, mm_flag = tag_read(rec, pred, rm_pulse)
+            wr.write_raw(raw)
+            counts[2] += 1
+            counts[3] += mm_flag
+    wr.close()
+    total = parallel.allreduce_counts(counts)
+    if rank == 0:
+        dt = time.time() - t0
+        sys.stderr.write("[call_mods] %d sites in %d model batches(%d), wrote %d reads, in which %d were added mm "
+                         "tags; %.1f s, %d rank(s)\n" % (total[0], total[1], args.batch_size, total[2], total[3], dt, world))
+    return dict(zip(("sites", "model_batches", "reads_written", "reads_with_mm"), total)), out_modbam
+
+
+def _get_holes(path):
+    with open(path) as f:
+        return {ln.strip().split("\t")[0] for ln in f if ln.strip()}
+
+
+def build_parser():
+    """The reference's call_mods flags with the same defaults (call_modifications.py:616-752)."""
+    p = argparse.ArgumentParser("ccsmeth_b200 call_mods", description="call modifications with the B200-native path")
+    p.add_argument("--input", "-i", type=str, required=True)
+    p.add_argument("--holes_batch", type=int, default=50)
+    p.add_argument("--output", "-o", type=str, required=True)
+    p.add_argument("--gzip", action="store_true", default=False)
+    p.add_argument("--keep_pulse", action="store_true", default=False)
+    p.add_argument("--no_sort", action="store_true", default=False)
+    p.add_argument("--model_file", "-m", type=str, required=True)
+    p.add_argument("--model_type", type=str, default="attbigru2s",
+                   choices=["attbilstm2s", "attbigru2s", "transencoder2s", "attbilstm2s2", "attbigru2s2"])
+    p.add_argument("--seq_len", type=int, default=21)
+    p.add_argument("--is_npass", type=str, default="yes")
+    p.add_argument("--is_stds", type=str, default="no")
+    p.add_argument("--is_sn", type=str, default="no")
+    p.add_argument("--is_map", type=str, default="no")
+    p.add_argument("--class_num", type=int, default=2)
+    p.add_argument("--dropout_rate", type=float, default=0)
+    p.add_argument("--batch_size", "-b", type=int, default=512)
+    p.add_argument("--layer_rnn", type=int, default=3)
+    p.add_argument("--hid_rnn", type=int, default=256)
+    p.add_argument("--layer_trans", type=int, default=6)
+    p.add_argument("--nhead", type=int, default=4)
+    p.add_argument("--d_model", type=int, default=256)
+    p.add_argument("--dim_ff", type=int, default=512)
+    p.add_argument("--mode", type=str, default="denovo", choices=["denovo", "align"])
+    p.add_argument("--holeids_e", type=str, default=None)
+    p.add_argument("--holeids_ne", type=str, default=None)
+    p.add_argument("--motifs", type=str, default="CG")
+    p.add_argument("--mod_loc", type=int, default=0)
+    p.add_argument("--methy_label", type=int, default=1, choices=[1, 0])
+    p.add_argument("--norm", type=str, default="zscore", choices=["zscore", "min-mean", "min-max", "mad", "none"])
+    p.add_argument("--no_decode", action="store_true", default=False)
+    p.add_argument("--ref", type=str, default=None)
+    p.add_argument("--mapq", type=int, default=1)
+    p.add_argument("--identity", type=float, default=0.0)
+    p.add_argument("--no_supplementary", action="store_true", default=False)
+    p.add_argument("--skip_unmapped", type=str, default="yes")
+    p.add_argument("--threads", "-p", type=int, default=10)
+    p.add_argument("--threads_call", type=int, default=3)
+    p.add_argument("--tseed", type=int, default=1234)
+    p.add_argument("--use_compile", type=str, default="no")
+    p.add_argument("--precision", type=str, default=None, choices=["fp32", "fp16x3", "bf16x3", "fp16", "bf16"],
+                   help="ccsmeth_b200 only: arithmetic mode (default fp16x3, <= 1e-4 vs the fp32 reference)")
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    counts, out = call_mods(args)
+    parallel.finalize()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -205,44 +205,51 @@ struct GruParams {
 //   NSLOT = 2: one CTA per SM, 384 threads, 3 stages of 56 KB, TMEM 2 x 256 columns (one buffer per slot).
 //   NSLOT = 1: two CTAs per SM, 192 threads each, 4 stages of 20 KB, TMEM 256 columns per CTA: the two
 //              co-resident CTAs overlap one's gate epilogue with the other's MMAs.
-template <int P, int NSLOT>
+//   NBUF  = accumulator buffers per slot in TMEM (2: the MMAs of unit-chunk j+1 overlap the epilogue of j).
+//   (NSLOT, NBUF) = (1, 2): one CTA per SM, 192 threads, 10 stages of 20 KB, TMEM 2 x 256 columns; half the
+//              row tiles in flight of the other variants, so the activation re-reads stay in L2.
+template <int P, int NSLOT, int NBUF>
 struct GruCfg {
-  static constexpr int KS = NSLOT == 2 ? 8 / P : 4 / P;  // slabs per stage per part
-  static constexpr int STAGES = NSLOT == 2 ? 3 : 4;
+  static constexpr int KS = (NSLOT == 2) ? 8 / P : 4 / P;  // slabs per stage per part
+  static constexpr int STAGES = NSLOT == 2 ? 3 : (NBUF == 2 ? 10 : 4);
   static constexpr int THREADS = NSLOT == 2 ? 384 : 192;
-  static constexpr int CTAS_PER_SM = NSLOT == 2 ? 1 : 2;
+  static constexpr int CTAS_PER_SM = (NSLOT == 1 && NBUF == 1) ? 2 : 1;
   static constexpr int EPI_WARP0 = NSLOT == 2 ? 4 : 2;
-  static constexpr uint32_t TMEM_COLS = NSLOT * 256;
+  static constexpr uint32_t TMEM_COLS = NSLOT * NBUF * 256;
   static constexpr uint32_t B_PART = KS * G_SLAB;
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + NSLOT * A_PART);
   static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
 };
 
-template <int P, bool F16, int NSLOT>
-__global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::CTAS_PER_SM)
+template <int P, bool F16, int NSLOT, int NBUF>
+__global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSLOT, NBUF>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
-  using C = GruCfg<P, NSLOT>;
+  static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
+  using C = GruCfg<P, NSLOT, NBUF>;
   constexpr int GRU_STAGES = C::STAGES;
   constexpr int GRU_THREADS = C::THREADS;
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * GRU_STAGES + 3];
+  __shared__ __align__(8) uint64_t bars[2 * GRU_STAGES + 5];
   __shared__ uint32_t tmem_base_s;
   float* bias_s = reinterpret_cast<float*>(smem + GRU_STAGES * C::STAGE);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[GRU_STAGES]);
-  const uint32_t tmem_full = smem_u32(&bars[2 * GRU_STAGES]), tmem_empty = smem_u32(&bars[2 * GRU_STAGES + 1]),
-                 h_ready = smem_u32(&bars[2 * GRU_STAGES + 2]);
+  // tmem_full/empty: one barrier pair per accumulator buffer (8 bytes apart)
+  const uint32_t tmem_full = smem_u32(&bars[2 * GRU_STAGES]), tmem_empty = smem_u32(&bars[2 * GRU_STAGES + 2]),
+                 h_ready = smem_u32(&bars[2 * GRU_STAGES + 4]);
   if (threadIdx.x == 0) {
     for (int i = 0; i < GRU_STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, NSLOT * 128);
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, NSLOT * 128);
+    }
     mbar_init(h_ready, NSLOT * 128);
     fence_barrier_init();
   }
@@ -337,7 +344,8 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::C
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         for (int s = 0; s < L; ++s) {
           for (int j = 0; j < 4; ++j, ++chunk) {
-            mbar_wait(tmem_empty, (chunk & 1) ^ 1);  // both slots' accumulators drained by the epilogue
+            const uint32_t buf = chunk % NBUF, bphase = (chunk / NBUF) & 1;
+            mbar_wait(tmem_empty + 8 * buf, bphase ^ 1);  // this buffer's accumulators drained by the epilogue
             tc_fence_after();
             for (int part = 0; part < 2; ++part) {
               const int total = part == 0 ? p.kx_slabs : 32;
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::C
                   const bool first = (so == 0 && ks == 0);
 #pragma unroll
                   for (int sl = 0; sl < NSLOT; ++sl) {
-                    const uint32_t dcol = tmem + sl * 256;
+                    const uint32_t dcol = tmem + (NBUF == 2 ? buf : sl) * 256;
 #pragma unroll
                     for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
                       const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::C
                 }
               }
             }
-            umma_commit(tmem_full);  // accumulators of both slots complete
+            umma_commit(tmem_full + 8 * buf);  // accumulators of this unit-chunk complete
           }
         }
       }
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::C
     // tcgen05.ld lane rule: a warp may only touch TMEM lanes [32 * (warp % 4), +32)
     const int slot = (warp - C::EPI_WARP0) >> 2, quad = warp & 3;
     const int row = quad * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
+    const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
     uint32_t chunk = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int pair = item >> 1, d = item & 1;
@@ -412,7 +420,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::C
             else
               hpl[q] = make_uint4(0, 0, 0, 0);
           }
-          mbar_wait(tmem_full, chunk & 1);
+          const uint32_t buf = chunk % NBUF, bphase = (chunk / NBUF) & 1;
+          const uint32_t trow = trow0 + (NBUF == 2 ? buf * 256 : 0);
+          mbar_wait(tmem_full + 8 * buf, bphase);
           tc_fence_after();
 #pragma unroll
           for (int ub = 0; ub < 4; ++ub) {
@@ -444,7 +454,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT>::THREADS, GruCfg<P, NSLOT>::C
             }
           }
           tc_fence_before();
-          mbar_arrive(tmem_empty);
+          mbar_arrive(tmem_empty + 8 * buf);
           if (j == 3) {
             fence_proxy_async_all();  // generic-proxy global writes -> visible to the producer's bulk copies
             mbar_arrive(h_ready);
@@ -860,13 +870,21 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
   return CCSM_OK;
 }
 
-static int gru_nslot() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CCSM_TC_NSLOT");
-    v = (e && atoi(e) == 2) ? 2 : 1;
+// GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2).
+// Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
+// Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0; layers >= 1 -> 0 for the
+// single-pass modes and 2 for the x3 modes (hi+lo images double the L2 working set; fewer tiles in flight keeps the
+// 4x-per-step activation re-reads out of HBM).
+static int gru_variant(int layer, int P) {
+  static int v[2] = {-2, -2};
+  if (v[0] == -2) {
+    const char* e = getenv("CCSM_TC_VARIANT");
+    v[0] = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
+    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '2') ? e[1] - '0' : v[0];
   }
-  return v;
+  const int forced = v[layer == 0 ? 0 : 1];
+  if (forced >= 0) return forced;
+  return (layer > 0 && P == 2) ? 2 : 0;
 }
 
 template <int P, bool F16>
@@ -888,10 +906,12 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
   count_launch();
   static bool attr_set[2][2] = {{false, false}, {false, false}};
   if (!attr_set[P - 1][F16]) {
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)GruCfg<P, 1>::SMEM));
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)GruCfg<P, 2>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)GruCfg<P, 1, 1>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)GruCfg<P, 2, 1>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)GruCfg<P, 1, 2>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_att_head_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)AttCfg<P>::SMEM));
     attr_set[P - 1][F16] = true;
@@ -907,15 +927,20 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
     gp.L = L;
     gp.kx_slabs = (int)T.kx_slabs[l];
     pid = m->prof.begin(l == 0 ? PROF_GRU_L0 : PROF_GRU_LN, (double)sites, st);
-    if (gru_nslot() == 2) {
+    const int variant = gru_variant(l, P);
+    if (variant == 1) {
       const int64_t items = tiles;  // (tiles / 2) x 2 directions
       const int grid = (int)(items < T.sm_count ? items : T.sm_count);
-      tc_gru_layer_kernel<P, F16, 2><<<grid, GruCfg<P, 2>::THREADS, GruCfg<P, 2>::SMEM, st>>>(gp);
+      tc_gru_layer_kernel<P, F16, 2, 1><<<grid, GruCfg<P, 2, 1>::THREADS, GruCfg<P, 2, 1>::SMEM, st>>>(gp);
+    } else if (variant == 2) {
+      const int64_t items = tiles * 2;
+      const int grid = (int)(items < T.sm_count ? items : T.sm_count);
+      tc_gru_layer_kernel<P, F16, 1, 2><<<grid, GruCfg<P, 1, 2>::THREADS, GruCfg<P, 1, 2>::SMEM, st>>>(gp);
     } else {
       const int64_t items = tiles * 2;
       const int64_t slots = (int64_t)T.sm_count * 2;
       const int grid = (int)(items < slots ? items : slots);
-      tc_gru_layer_kernel<P, F16, 1><<<grid, GruCfg<P, 1>::THREADS, GruCfg<P, 1>::SMEM, st>>>(gp);
+      tc_gru_layer_kernel<P, F16, 1, 1><<<grid, GruCfg<P, 1, 1>::THREADS, GruCfg<P, 1, 1>::SMEM, st>>>(gp);
     }
     m->prof.end(pid, st);
     count_launch();

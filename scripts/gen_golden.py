@@ -151,10 +151,95 @@ def gen_aggr():
     print("aggr_synth: raw mean %.4f" % raw.mean().item())
 
 
+def demo_args():
+    import argparse
+    return argparse.Namespace(mode="denovo", seq_len=21, motifs="CG", mod_loc=0, methy_label=1, norm="zscore",
+                              no_decode=False, is_sn="no", is_map="no", is_stds="no", is_npass="yes", mapq=1,
+                              identity=0.0, no_supplementary=False, skip_unmapped="yes", holes_batch=50,
+                              batch_size=512, keep_pulse=False)
+
+
+def gen_demo():
+    """Config 1/3 golden: the reference chain  extract_features_from_double_strand_read ->
+    _batch_feature_list2s -> _call_mods2s(batch 512)  over demo/hg002.chr20_demo.hifi.bam (--mode denovo),
+    hole-batches of 50 reads, torch.manual_seed(1234) in-process; MM/ML through the reference's own
+    _convert_locs_to_mmtag / _convert_probs_to_mltag.  Reads come from ccsmeth_b200.bamio (pysam is absent);
+    the reference extractor only touches the duck-typed attributes listed in extract_features.py:88-126."""
+    import shutil
+    import time
+    from ccsmeth_b200.bamio import BamReader
+    ref = refimport.import_reference()
+    import ccsmeth.extract_features as ref_ef
+    import ccsmeth.call_modifications as rcm
+    import ccsmeth._bam2modbam as rmb
+    os.makedirs(os.path.join(OUT, "demo"), exist_ok=True)
+    dst = os.path.join(OUT, "demo", "hg002.chr20_demo.hifi.bam")
+    if not os.path.exists(dst):
+        shutil.copyfile(refimport.DEMO_BAM, dst)
+        os.chmod(dst, 0o644)
+    m = refimport.load_ref_att2s()
+    args = demo_args()
+    reads = list(BamReader(dst))
+    t0 = time.time()
+    torch.manual_seed(1234)
+    out = {"names": [], "n_sites_per_read": [], "locs": [], "prob1": [], "mm": [], "ml": [], "site_counts_per_batch": []}
+    feat0 = None
+    t_extract = t_model = 0.0
+    for b0 in range(0, len(reads), args.holes_batch):
+        hb = reads[b0:b0 + args.holes_batch]
+        ta = time.time()
+        feature_list, holeidx = [], []
+        for i, r in enumerate(hb):
+            f = ref_ef.extract_features_from_double_strand_read(r, ["CG"], None, None, None, args)
+            feature_list += f
+            holeidx += [i] * len(f)
+        fb = rcm._batch_feature_list2s(feature_list)
+        tb = time.time()
+        pred, nb = rcm._call_mods2s(fb, m, 512, 0)
+        tc = time.time()
+        t_extract += tb - ta
+        t_model += tc - tb
+        out["site_counts_per_batch"].append(len(pred))
+        if feat0 is None:  # feature-level golden for the first 3 reads
+            k = sum(1 for h in holeidx if h < 3)
+            feat0 = {"fkmer": np.array(fb[1][:k]), "fpass": np.array(fb[2][:k]), "fipd": np.array(fb[3][:k]),
+                     "fpw": np.array(fb[5][:k]), "rkmer": np.array(fb[9][:k]), "rpass": np.array(fb[10][:k]),
+                     "ripd": np.array(fb[11][:k]), "rpw": np.array(fb[13][:k]),
+                     "locs": np.array([f[4] for f in feature_list[:k]]), "holeidx": np.array(holeidx[:k])}
+        # per read MM/ML with the reference's converters
+        for i, r in enumerate(hb):
+            lp = sorted([(p[1], p[2]) for p, h in zip(pred, holeidx) if h == i], key=lambda x: x[0])
+            out["names"].append(r.query_name)
+            out["n_sites_per_read"].append(len(lp))
+            if lp:
+                locs, probs = zip(*lp)
+                mm = rmb._convert_locs_to_mmtag(locs, r.get_forward_sequence())
+                ml = rmb._convert_probs_to_mltag(probs)
+                out["locs"] += list(locs)
+                out["prob1"] += list(probs)
+                out["mm"] += mm
+                out["ml"] += ml
+    dt = time.time() - t0
+    n = len(out["prob1"])
+    print("demo: %d reads, %d sites, batches %s; %.2f s total (extract+batch %.2f s, model %.2f s) -> %.0f sites/s"
+          % (len(reads), n, out["site_counts_per_batch"], dt, t_extract, t_model, n / dt))
+    np.savez_compressed(os.path.join(OUT, "demo_callmods.npz"), names=np.array(out["names"]),
+                        n_sites_per_read=np.array(out["n_sites_per_read"]), locs=np.array(out["locs"]),
+                        prob1=np.array(out["prob1"], dtype=np.float32), mm=np.array(out["mm"]),
+                        ml=np.array(out["ml"], dtype=np.uint8),
+                        site_counts_per_batch=np.array(out["site_counts_per_batch"]), tseed=1234,
+                        ref_cpu_seconds=dt, ref_cpu_threads=torch.get_num_threads(),
+                        **{"feat0." + k: v for k, v in feat0.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "demo":
+        gen_demo()
+        sys.exit(0)
     save_ckpts()
     gen_att2s()
     gen_aggr()
+    gen_demo()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

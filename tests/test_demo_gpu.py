@@ -1,0 +1,67 @@
+"""Config 3: demo BAM end to end on one B200 (BAM -> features -> kernels -> MM/ML -> modbam) against the
+reference chain's per-site probabilities and MM/ML tags (fixture demo_callmods.npz, same tseed => same h0)."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from ccsmeth_b200 import call_mods as cm
+from ccsmeth_b200.bamio import BamReader
+from tests.conftest import GOLDEN, load_npz
+
+pytestmark = pytest.mark.gpu
+DEMO = os.path.join(GOLDEN, "demo", "hg002.chr20_demo.hifi.bam")
+
+
+@pytest.fixture(scope="module")
+def ckpt_file(tmp_path_factory, ckpt_att2s):
+    p = str(tmp_path_factory.mktemp("ckpt") / "model_v3.ckpt")
+    torch.save(OrderedDict((k, torch.from_numpy(v)) for k, v in ckpt_att2s.items()), p)
+    return p
+
+
+@pytest.mark.parametrize("prec,max_ml_flips", [("fp16x3", 12), ("fp32", 12), ("bf16x3", 20)])
+def test_call_mods_demo_matches_reference_chain(tmp_path, ckpt_file, prec, max_ml_flips):
+    g = load_npz("demo_callmods.npz")
+    out = str(tmp_path / ("demo_" + prec))
+    args = cm.build_parser().parse_args(["-i", DEMO, "-m", ckpt_file, "-o", out, "--mode", "denovo",
+                                         "--tseed", str(int(g["tseed"])), "--precision", prec])
+    counts, path = cm.call_mods(args)
+    assert counts == {"sites": 12691, "model_batches": 26, "reads_written": 116,
+                      "reads_with_mm": int((g["n_sites_per_read"] > 0).sum())}
+    recs = list(BamReader(path))
+    assert [r.query_name for r in recs] == list(g["names"])
+    off, flips, n_tot = 0, 0, 0
+    for r, n in zip(recs, g["n_sites_per_read"]):
+        if n == 0:
+            assert not r.has_tag("MM")
+            continue
+        mm = r.get_tag("MM")
+        assert [int(x) for x in mm[5:-1].split(",")] == list(g["mm"][off:off + n])  # same sites called
+        ml = r.get_tag("ML")
+        flips += int((ml != g["ml"][off:off + n]).sum())
+        # an ML byte may differ only where a <=1e-4 probability difference straddles a k/256 edge
+        assert np.abs(ml.astype(int) - g["ml"][off:off + n].astype(int)).max() <= 1
+        n_tot += n
+        off += n
+    assert n_tot == 12691 and flips <= max_ml_flips, flips
+
+
+def test_call_holebatch_probabilities(ckpt_file):
+    g = load_npz("demo_callmods.npz")
+    args = cm.build_parser().parse_args(["-i", DEMO, "-m", ckpt_file, "-o", "x", "--precision", "fp16x3"])
+    model = cm.load_model(ckpt_file, args, device=0, precision="fp16x3")
+    reads = list(BamReader(DEMO))
+    torch.manual_seed(int(g["tseed"]))
+    probs = []
+    for b0 in range(0, len(reads), 50):
+        per_read, n, nb = cm.call_holebatch(model, reads[b0:b0 + 50], ["CG"], args)
+        for pr in per_read:
+            if pr is not None:
+                order = np.argsort(pr[0], kind="stable")
+                probs.append(pr[1][order])
+    probs = np.concatenate(probs)
+    assert probs.shape == g["prob1"].shape
+    assert np.abs(probs - g["prob1"]).max() <= 1e-4  # north-star tolerance, whole demo, reference h0 stream
