@@ -148,8 +148,10 @@ def call_mods(args):
     out_dir = os.path.dirname(os.path.abspath(args.output))
     os.makedirs(out_dir, exist_ok=True)
     out_modbam = args.output + (".modbam.bam" if world == 1 else ".rank%d.modbam.bam" % rank)
-    torch.manual_seed(args.tseed)  # seeds the process that draws h0 (the reference seeds only its parent, :479-481)
     model = load_model(args.model_file, args, device=local, precision=getattr(args, "precision", None))
+    # seed the process that draws h0, after model construction (which itself consumes the generator); the
+    # reference seeds only its parent process (:479-481), so its workers' h0 streams are not reproducible
+    torch.manual_seed(args.tseed + rank)
     motifs = get_motif_seqs(args.motifs)
     holeids_e = _get_holes(args.holeids_e) if args.holeids_e else None
     holeids_ne = _get_holes(args.holeids_ne) if args.holeids_ne else None
