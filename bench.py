@@ -231,22 +231,36 @@ def main():
     prof = m.profile_read()
     m.profile(False)
 
-    # ---- e2e: host buffers through the C-ABI host entry
+    # ---- e2e: host buffers through the C-ABI host entry (ccsm_forward_att2s_host).
+    # Like the reference's forward, the model draws h0 itself (models.py:77-87,125-130) -- here on the device
+    # (Philox, CCSM_H0_DEVICE_RANDOM) -- so the caller hands over only the 8 feature tensors and reads back probs.
     E = min(args.e2e_sites, S)
     hb = synth.make_batch(E, seed=synth.SEED + 77 + rank, with_h0=False)
     hfeats = {k: hb[k].pin_memory() for k in FEATS}
-    hh0 = (torch.randn(6, E, 256).pin_memory(), torch.randn(6, E, 256).pin_memory())
+    m.set_h0_mode("device", seed=synth.SEED + rank)
     for _ in range(max(1, args.warmup - 1)):
-        m.forward_host(hfeats, h0=hh0)
+        m.forward_host(hfeats)
     parallel.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, p_host = m.forward_host(hfeats, h0=hh0)
+        _, p_host = m.forward_host(hfeats)
     e2e_s = time.perf_counter() - t0
     e2e_s = parallel.allreduce_max(e2e_s)
     e2e_val = world * E * args.steps / e2e_s
-    h2d = E * (8 * 21 * 4 + 2 * 6 * 256 * 4)
+    h2d = E * (8 * 21 * 4)
     d2h = E * 2 * 2 * 4
+    # same call with an explicit host-resident h0 (parity-style use): +12,288 B/site over PCIe
+    m.set_h0_mode("reference")
+    E2 = min(E, 1 << 17)
+    hh0 = (torch.randn(6, E2, 256).pin_memory(), torch.randn(6, E2, 256).pin_memory())
+    hf2 = {k: v[:E2] for k, v in hfeats.items()}
+    m.forward_host(hf2, h0=hh0)
+    parallel.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.forward_host(hf2, h0=hh0)
+    e2e2_s = parallel.allreduce_max(time.perf_counter() - t0)
+    e2e_host_h0 = world * E2 * args.steps / e2e2_s
 
     # ---- end-of-run count all-reduce (the path's only collective: SURVEY.md section 8e)
     counts = parallel.allreduce_counts([S * args.steps, -(-S // 512) * args.steps, 0, 0])
@@ -301,7 +315,10 @@ def main():
                       "parallelism": "dp%d (reads sharded per rank, no data-path collective)" % world},
            "max_abs_dprob_vs_cpu_port": dprob, "parity_sites": P,
            "e2e": {"value": e2e_val, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "sites_per_step": E, "timer": "host wall clock around ccsm_forward_att2s_host, max over ranks"},
+                   "sites_per_step": E, "timer": "host wall clock around ccsm_forward_att2s_host, max over ranks",
+                   "h0": "drawn on device by the library (the reference's forward also draws h0 internally)",
+                   "with_explicit_host_h0": {"value": e2e_host_h0, "sites_per_step": E2,
+                                             "h2d_bytes_per_step": E2 * (8 * 21 * 4 + 2 * 6 * 256 * 4)}},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
            "allreduce_counts": {"sites": counts[0], "model_batches": counts[1]}}
     if not args.no_cpu_baseline:

@@ -81,7 +81,7 @@ def call_holebatch(model, reads, motifs, args, holeids_e=None, holeids_ne=None, 
     if arrays is None:
         return per_read, 0, 0
     n = len(locs)
-    if h0 is None:
+    if h0 is None and getattr(args, "h0", "reference") == "reference":
         h0 = draw_h0_stream(n, args.batch_size, model.num_layers, model.hidden_size)
     _, probs = model.forward_host(arrays, h0=h0)
     p = probs.numpy()
@@ -152,6 +152,7 @@ def call_mods(args):
     # seed the process that draws h0, after model construction (which itself consumes the generator); the
     # reference seeds only its parent process (:479-481), so its workers' h0 streams are not reproducible
     torch.manual_seed(args.tseed + rank)
+    model.set_h0_mode(getattr(args, "h0", "reference"), seed=args.tseed + rank)
     motifs = get_motif_seqs(args.motifs)
     holeids_e = _get_holes(args.holeids_e) if args.holeids_e else None
     holeids_ne = _get_holes(args.holeids_ne) if args.holeids_ne else None
@@ -238,6 +239,9 @@ def build_parser():
     p.add_argument("--threads_call", type=int, default=3)
     p.add_argument("--tseed", type=int, default=1234)
     p.add_argument("--use_compile", type=str, default="no")
+    p.add_argument("--h0", type=str, default="reference", choices=["reference", "device", "zeros"],
+                   help="ccsmeth_b200 only: GRU initial state: the reference's torch.randn stream on the CPU "
+                        "(default), N(0,1) drawn on the device (no 12 KB/site transfer), or zeros")
     p.add_argument("--precision", type=str, default=None, choices=["fp32", "fp16x3", "bf16x3", "fp16", "bf16"],
                    help="ccsmeth_b200 only: arithmetic mode (default fp16x3, <= 1e-4 vs the fp32 reference)")
     return p

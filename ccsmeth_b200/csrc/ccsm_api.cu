@@ -214,6 +214,17 @@ int ccsm_finalize(ccsm_model* m) {
   return CCSM_OK;
 }
 
+int ccsm_set_h0_mode(ccsm_model* m, int32_t mode, uint64_t seed) {
+  if (!m || (mode != CCSM_H0_ZEROS && mode != CCSM_H0_DEVICE_RANDOM)) {
+    set_error("ccsm_set_h0_mode: bad argument");
+    return CCSM_EINVAL;
+  }
+  m->h0_mode = mode;
+  m->h0_seed = seed;
+  m->h0_calls = 0;
+  return CCSM_OK;
+}
+
 int ccsm_set_precision(ccsm_model* m, int32_t precision) {
   if (!m || precision < CCSM_PREC_FP32 || precision > CCSM_PREC_FP16) {
     set_error("ccsm_set_precision: bad argument");
@@ -259,8 +270,10 @@ int ccsm_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
   CCSM_TRY(check_strand(m, rev, "reverse"));
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (is_tc(m->cfg.precision)) return tc_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
-  return fp32_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
+  const int rc = is_tc(m->cfg.precision) ? tc_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st)
+                                         : fp32_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
+  m->h0_calls += 1;
+  return rc;
 }
 
 int ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
@@ -307,7 +320,9 @@ int ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, co
     if (!m->events[i]) CCSM_CUDA(cudaEventCreateWithFlags(&m->events[i], cudaEventDisableTiming));
   }
   const int L = m->cfg.seq_len, H = m->cfg.hidden, NL = m->cfg.num_layers, C = m->cfg.num_classes;
-  const int64_t chunk = n < 32768 ? n : 32768;
+  // one tensor-core library chunk (8 row-tile items per SM) per staging buffer
+  const int64_t kHostChunk = 75776;
+  const int64_t chunk = n < kHostChunk ? n : kHostChunk;
   // staging layout per buffer (floats): 2 strands x [kmer,kpass,ipd,ipd_sd,pw,pw_sd,maps](L each) + sns(4) + h0 x2
   const int64_t per_strand = (int64_t)7 * L + 4;
   const int64_t h0_floats = (int64_t)2 * NL * H;

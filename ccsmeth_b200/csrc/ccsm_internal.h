@@ -110,6 +110,9 @@ struct ccsm_model {
   ccsm::Fp32Workspace ws32;
   ccsm::TcState* tc = nullptr;
   ccsm::Profiler prof;
+  int h0_mode = 0;            // CCSM_H0_*
+  uint64_t h0_seed = 0;
+  uint64_t h0_calls = 0;      // forward calls so far (Philox offset = 256 * call)
   // host-entry staging
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaEvent_t events[2] = {nullptr, nullptr};

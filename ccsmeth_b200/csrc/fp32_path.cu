@@ -11,6 +11,7 @@
 //                 gate math     r,z,n,h' (PyTorch GRU cell, gate order r,z,n)   reference models.py:125-130
 //   attention     e = out . Ua^T, qa = q . Wa^T, softmax_t(va . tanh(qa + e_t)) reference utils/attention.py:48-70
 //   head          ctx -> fc1 -> softmax                                          reference models.py:145-150
+#include <curand_kernel.h>
 #include <math.h>
 #include <stdio.h>
 
@@ -186,9 +187,9 @@ __global__ void pack_x_aggr_kernel(int64_t sites, int L, int Bn, int Kpad, const
 }
 
 // h[R][d][u] = h0_strand(R)[(2*layer + d)][site][u]   (h0 index 2*layer+direction, torch nn.GRU)
-__global__ void load_h0_kernel(int64_t rows, int strands, int H, int layer, int64_t n_total, int64_t site0,
-                               const float* __restrict__ h0_a, const float* __restrict__ h0_b,
-                               float* __restrict__ h) {
+__global__ void load_h0_kernel(int64_t rows, int strands, int H, int layer, int NL, int64_t n_total, int64_t site0,
+                               const float* __restrict__ h0_a, const float* __restrict__ h0_b, int h0_random,
+                               unsigned long long h0_seed, unsigned long long h0_offset, float* __restrict__ h) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (R, d, u)
   if (idx >= rows * 2 * H) return;
   int u = (int)(idx % H);
@@ -197,6 +198,15 @@ __global__ void load_h0_kernel(int64_t rows, int strands, int H, int layer, int6
   int strand = (int)(R % strands);
   int64_t site = site0 + R / strands;
   const float* h0 = strand ? h0_b : h0_a;
+  if (!h0 && h0_random) {
+    // same stream as tc_prep_kernel: output u of subsequence (row*2*layers + 2*layer+dir), see include/ccsm.h
+    curandStatePhilox4_32_10_t rng;
+    curand_init(h0_seed, (unsigned long long)((site * strands + strand) * 2 * NL + 2 * layer + d),
+                h0_offset + (unsigned long long)(u & ~3), &rng);
+    const float4 v = curand_normal4(&rng);
+    h[idx] = (u & 3) == 0 ? v.x : ((u & 3) == 1 ? v.y : ((u & 3) == 2 ? v.z : v.w));
+    return;
+  }
   h[idx] = h0 ? h0[((int64_t)(2 * layer + d) * n_total + site) * H + u] : 0.f;
 }
 
@@ -372,8 +382,9 @@ static int run_stack(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_tota
     // input projection for all time steps and both directions: gi[R][t][d][3H]
     CCSM_TRY(sgemm_nt((int)(rows * L), 6 * H, Lw.Kpad, xin, Lw.Kpad, 0, Lw.w_ih.as<float>(), Lw.Kpad, 0,
                       Lw.b_ih.as<float>(), 0, ws.gi.as<float>(), 6 * H, 0, 1, st));
-    load_h0_kernel<<<nblk(rows * 2 * H, 256), 256, 0, st>>>(rows, S, H, l, n_total, site0, h0_a, h0_b,
-                                                            ws.h.as<float>());
+    load_h0_kernel<<<nblk(rows * 2 * H, 256), 256, 0, st>>>(
+        rows, S, H, l, NL, n_total, site0, h0_a, h0_b, m->h0_mode == CCSM_H0_DEVICE_RANDOM ? 1 : 0,
+        (unsigned long long)m->h0_seed, (unsigned long long)(m->h0_calls * 256), ws.h.as<float>());
     count_launch();
     for (int s = 0; s < L; ++s) {
       // gh[R][d][3H] = h[R][d][:] . W_hh[d]^T + b_hh[d]

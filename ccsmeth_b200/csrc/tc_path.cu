@@ -21,6 +21,7 @@
 //   warps 4-11  gate epilogue: tcgen05.ld accumulators -> sigmoid/tanh/blend -> h_t written to the act image
 //   Two row tiles ("slots") share every weight stage; TMEM holds [n_i | r | z | n_h] x 64 units per slot.
 //   h_t goes back to the next step's A operand through the (L2-resident) act image.
+#include <curand_kernel.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -125,7 +126,8 @@ template <int P, bool F16>
 __global__ void tc_prep_kernel(int64_t n_tiles, int64_t sites, int64_t site0, int64_t n_total, int L, int NL,
                                int n_vocab, int has_npass, TcStrand s0, TcStrand s1,
                                const float* __restrict__ embed, const float* __restrict__ h0_a,
-                               const float* __restrict__ h0_b, uint8_t* __restrict__ x0img,
+                               const float* __restrict__ h0_b, int h0_random, unsigned long long h0_seed,
+                               unsigned long long h0_offset, uint8_t* __restrict__ x0img,
                                uint8_t* __restrict__ h0img) {
   const int64_t gr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // global row in chunk
   if (gr >= n_tiles * TILE_ROWS) return;
@@ -165,11 +167,18 @@ __global__ void tc_prep_kernel(int64_t n_tiles, int64_t sites, int64_t site0, in
   for (int l = 0; l < NL; ++l)
     for (int d = 0; d < 2; ++d) {
       const float* src = (valid && h0) ? h0 + ((int64_t)(2 * l + d) * n_total + site0 + site) * 256 : nullptr;
+      const bool rnd = valid && !h0 && h0_random;
+      curandStatePhilox4_32_10_t rng;
+      if (rnd)
+        curand_init(h0_seed, (unsigned long long)(((site0 + site) * 2 + strand) * 2 * NL + 2 * l + d), h0_offset, &rng);
       for (int kc = 0; kc < 4; ++kc)
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl) {
           float w[8];
-          if (src) {
+          if (rnd) {
+            const float4 a = curand_normal4(&rng), b = curand_normal4(&rng);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+          } else if (src) {
             float4 a = *reinterpret_cast<const float4*>(src + kc * 64 + sl * 8);
             float4 b = *reinterpret_cast<const float4*>(src + kc * 64 + sl * 8 + 4);
             w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
@@ -901,7 +910,9 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
   int pid = m->prof.begin(PROF_PREP, (double)sites, st);
   tc_prep_kernel<P, F16><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(
       tiles, sites, site0, n_total, L, NL, m->cfg.n_vocab, (m->cfg.feat_flags & CCSM_FEAT_NPASS) ? 1 : 0, s0, s1,
-      T.embed.as<float>(), h0_f, h0_r, T.x0img.as<uint8_t>(), T.h0img.as<uint8_t>());
+      T.embed.as<float>(), h0_f, h0_r, m->h0_mode == CCSM_H0_DEVICE_RANDOM ? 1 : 0,
+      (unsigned long long)m->h0_seed, (unsigned long long)(m->h0_calls * 256), T.x0img.as<uint8_t>(),
+      T.h0img.as<uint8_t>());
   m->prof.end(pid, st);
   count_launch();
   static bool attr_set[2][2] = {{false, false}, {false, false}};

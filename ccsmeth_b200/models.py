@@ -48,6 +48,9 @@ class _NativeModule(nn.Module):
         self._handle = None
         self._handle_key = None
         self._dirty = True
+        self._h0_mode = "reference"
+        self._h0_seed = 1234
+        self._h0_mode_dirty = False
 
     # -- parameter / device changes invalidate the packed weights
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -76,6 +79,26 @@ class _NativeModule(nn.Module):
     def get_precision(self):
         return self._precision
 
+    def set_h0_mode(self, mode, seed=1234):
+        """How ``forward(..., h0=None)`` obtains the GRU initial state:
+        "reference" (default) -- torch.randn on the CPU default generator, exactly the reference's stream
+                                 (models.py:77-87), copied to the device (12 KB/site);
+        "device"              -- N(0,1) drawn inside the feature-packing kernel (Philox, include/ccsm.h
+                                 CCSM_H0_DEVICE_RANDOM): same distribution, nothing materialised or transferred;
+        "zeros"               -- zero state."""
+        if mode not in ("reference", "device", "zeros"):
+            raise ValueError("h0 mode must be reference, device or zeros")
+        self._h0_mode = mode
+        self._h0_seed = int(seed)
+        self._h0_mode_dirty = True
+        return self
+
+    def _apply_h0_mode(self, handle):
+        if getattr(self, "_h0_mode_dirty", False):
+            mode = 1 if self._h0_mode == "device" else 0
+            _lib.check(_lib.load().ccsm_set_h0_mode(handle, mode, ctypes.c_uint64(self._h0_seed)))
+            self._h0_mode_dirty = False
+
     def _device_index(self):
         p = next(self.parameters())
         if p.is_cuda:
@@ -100,6 +123,7 @@ class _NativeModule(nn.Module):
             h = ctypes.c_void_p()
             _lib.check(lib.ccsm_create(ctypes.byref(h), ctypes.byref(cfg)))
             self._handle, self._handle_key, self._dirty = h, key, True
+            self._h0_mode_dirty = self._h0_mode != "reference"
         if self._dirty:
             _lib.check(lib.ccsm_set_precision(self._handle, _lib.PREC[self._precision]))
             for k, v in self.state_dict().items():
@@ -203,20 +227,25 @@ class ModelAttRNN(_NativeModule):
         handle, dev = self._ensure_handle()
         device = torch.device("cuda", dev)
         n = int(torch.as_tensor(kmer).reshape(-1, self.seq_len).shape[0])
-        if h0 is None:
+        self._apply_h0_mode(handle)
+        if h0 is None and self._h0_mode == "reference":
             h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
                   self.init_hidden(n, self.num_layers, self.hidden_size))
         keep = []
         fwd = self._strand(device, n, kmer, kpass, ipd_means, ipd_stds, pw_means, pw_stds, sns, maps, keep)
         rev = self._strand(device, n, kmer2, kpass2, ipd_means2, ipd_stds2, pw_means2, pw_stds2, sns2, maps2, keep)
         hshape = (2 * self.num_layers, n, self.hidden_size)
-        h0a, h0b = _dev_f32(h0[0], device, hshape), _dev_f32(h0[1], device, hshape)
+        if h0 is not None:
+            h0a, h0b = _dev_f32(h0[0], device, hshape), _dev_f32(h0[1], device, hshape)
+            pa, pb = h0a.data_ptr(), h0b.data_ptr()
+        else:
+            pa = pb = None  # library draws (device mode) or uses zeros
         logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
         probs = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
         if n > 0:
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(_lib.load().ccsm_forward_att2s(handle, n, ctypes.byref(fwd), ctypes.byref(rev),
-                                                      h0a.data_ptr(), h0b.data_ptr(), logits.data_ptr(),
+                                                      pa, pb, logits.data_ptr(),
                                                       probs.data_ptr(), ctypes.c_void_p(stream)))
         return logits, probs
 
@@ -255,17 +284,21 @@ class ModelAttRNN(_NativeModule):
                     keep.append(t)
                     setattr(s, name, t.data_ptr())
             strands.append(s)
-        if h0 is None:
+        self._apply_h0_mode(handle)
+        if h0 is None and self._h0_mode == "reference":
             h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
                   self.init_hidden(n, self.num_layers, self.hidden_size))
         hshape = (2 * self.num_layers, n, self.hidden_size)
-        h0a, h0b = _dev_f32(h0[0], cpu, hshape), _dev_f32(h0[1], cpu, hshape)
+        if h0 is not None:
+            h0a, h0b = _dev_f32(h0[0], cpu, hshape), _dev_f32(h0[1], cpu, hshape)
+            pa, pb = h0a.data_ptr(), h0b.data_ptr()
+        else:
+            pa = pb = None
         logits = torch.empty((n, self.num_classes), dtype=torch.float32)
         probs = torch.empty((n, self.num_classes), dtype=torch.float32)
         if n > 0:
             _lib.check(_lib.load().ccsm_forward_att2s_host(handle, n, ctypes.byref(strands[0]), ctypes.byref(strands[1]),
-                                                           h0a.data_ptr(), h0b.data_ptr(), logits.data_ptr(),
-                                                           probs.data_ptr()))
+                                                           pa, pb, logits.data_ptr(), probs.data_ptr()))
         return logits, probs
 
 

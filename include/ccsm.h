@@ -112,6 +112,17 @@ int  ccsm_set_weight(ccsm_model* m, const char* key, const float* host, const in
  * May be called again after further ccsm_set_weight calls. */
 int  ccsm_finalize(ccsm_model* m);
 
+/* What a NULL h0 pointer means in the forward calls.
+ *   CCSM_H0_ZEROS (default): zero initial state.
+ *   CCSM_H0_DEVICE_RANDOM:   N(0,1) drawn on the device (Philox4x32-10, Box-Muller) inside the feature-packing
+ *     kernel -- the reference draws torch.randn inside forward (models.py:77-87,125-130); this is the same
+ *     distribution without materialising or transferring 12 KB/site of noise.  Value u of (site, strand, layer,
+ *     direction) is output u of Philox subsequence ((site*2+strand)*2*layers + 2*layer+direction) at offset
+ *     256*call, so every forward call sees fresh noise and all arithmetic modes see the same noise. */
+#define CCSM_H0_ZEROS 0
+#define CCSM_H0_DEVICE_RANDOM 1
+int  ccsm_set_h0_mode(ccsm_model* m, int32_t mode, uint64_t seed);
+
 /* Change the arithmetic mode of a finalized model (re-packs weights if needed). */
 int  ccsm_set_precision(ccsm_model* m, int32_t precision);
 
