@@ -28,7 +28,8 @@ FEAT_NPASS, FEAT_STDS, FEAT_SN, FEAT_MAP = 1, 2, 4, 8
 EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_create", "ccsm_destroy",
            "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",
            "ccsm_forward_att2s_host", "ccsm_forward_aggr", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
-           "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode"]
+           "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
+           "ccsm_debug_umma_pair_gemm"]
 
 
 class CcsmError(RuntimeError):
@@ -110,6 +111,8 @@ def load():
         lib.ccsm_debug_last_rnn_out.restype = i64
         lib.ccsm_debug_tc_layer_out.argtypes = [vp, i32, vp, i64]
         lib.ccsm_debug_tc_layer_out.restype = i64
+        lib.ccsm_debug_umma_pair_gemm.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
+        lib.ccsm_debug_umma_pair_gemm.restype = ctypes.c_int
         lib.ccsm_set_h0_mode.argtypes = [vp, i32, ctypes.c_uint64]
         lib.ccsm_set_h0_mode.restype = ctypes.c_int
         lib.ccsm_profile_enable.argtypes = [vp, i32]

@@ -73,6 +73,90 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// CTA-pair variant: D(256, N) = A(256, K) . B(N, K)^T with tcgen05.mma.cta_group::2.  CTA c holds A rows
+// [128c, 128c+128) and B rows [c*N/2, (c+1)*N/2).  Also exercises tcgen05.st (zeroing columns) -> Z.
+template <bool F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    umma_pair_selftest_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img,
+                              float* __restrict__ D, float* __restrict__ Z, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[3];  // full (local), peer_full (used in CTA 0), done
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int NH = N / 2;
+  const uint32_t a_bytes = (uint32_t)(K / 8) * 2048u, b_bytes = (uint32_t)(K / 8) * (uint32_t)NH * 16u;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + a_bytes;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_peer = smem_u32(&bars[1]), bar_done = smem_u32(&bars[2]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_peer, 1);
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 256);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_full, a_bytes + b_bytes);
+      bulk_g2s(smem_u32(sA), a_img + (size_t)rank * a_bytes, a_bytes, bar_full);
+      bulk_g2s(smem_u32(sB), b_img + (size_t)rank * b_bytes, b_bytes, bar_full);
+      mbar_wait(bar_full, 0);
+      if (rank == 1) {
+        mbar_arrive_remote(mapa_u32(bar_peer, 0));  // tell the leader our half of the operands has landed
+      } else {
+        mbar_wait(bar_peer, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(256, N, F16);
+        const uint32_t a_lbo = 2048, b_lbo = (uint32_t)NH * 16u, sbo = 128;
+        for (int ks = 0; ks < K / 16; ++ks) {
+          const uint64_t ad = make_smem_desc(smem_u32(sA) + ks * 2 * a_lbo, a_lbo, sbo);
+          const uint64_t bd = make_smem_desc(smem_u32(sB) + ks * 2 * b_lbo, b_lbo, sbo);
+          umma_f16_pair(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit_pair(bar_done, 0x3);
+      }
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  const int row = (int)rank * 128 + warp * 32 + lane;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(trow + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)row * N + c0 + i] = __uint_as_float(v[i]);
+  }
+  {
+    uint32_t z[16], v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+    tmem_st16(trow + 16, z);  // zero columns [16, 32)
+    tmem_st_wait();
+    tmem_ld16(trow + 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Z[(size_t)row * 32 + i] = __uint_as_float(v[i]);
+    tmem_ld16(trow + 0, v);  // neighbours must be untouched
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Z[(size_t)row * 32 + 16 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem, 256);
+}
+
 static void pack_rows(const float* src, int rows, int K, bool f16, std::vector<uint16_t>& img) {
   img.assign((size_t)rows * K, 0);
   for (int r = 0; r < rows; ++r)
@@ -94,6 +178,52 @@ static void pack_rows(const float* src, int rows, int K, bool f16, std::vector<u
 }  // namespace ccsm
 
 using namespace ccsm;
+
+extern "C" int ccsm_debug_umma_pair_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, const float* A,
+                                         const float* B, float* D, float* Z) {
+  if (N < 32 || N > 256 || N % 32 || K < 16 || K % 16 || !A || !B || !D || !Z) {
+    set_error("ccsm_debug_umma_pair_gemm: bad shape N=%d K=%d", N, K);
+    return CCSM_EINVAL;
+  }
+  const int NH = N / 2;
+  size_t smem = (size_t)(K / 8) * (2048 + (size_t)NH * 16);
+  if (smem > 200 * 1024) {
+    set_error("ccsm_debug_umma_pair_gemm: K too large");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(device));
+  std::vector<uint16_t> ai, a0, a1, b0, b1;
+  pack_rows(A, 128, K, is_f16 != 0, a0);
+  pack_rows(A + (size_t)128 * K, 128, K, is_f16 != 0, a1);
+  pack_rows(B, NH, K, is_f16 != 0, b0);
+  pack_rows(B + (size_t)NH * K, NH, K, is_f16 != 0, b1);
+  ai = a0; ai.insert(ai.end(), a1.begin(), a1.end());
+  std::vector<uint16_t> bi = b0; bi.insert(bi.end(), b1.begin(), b1.end());
+  DevBuf da, db, dd, dz;
+  CCSM_TRY(da.reserve(ai.size() * 2));
+  CCSM_TRY(db.reserve(bi.size() * 2));
+  CCSM_TRY(dd.reserve((size_t)256 * N * 4));
+  CCSM_TRY(dz.reserve((size_t)256 * 32 * 4));
+  CCSM_CUDA(cudaMemcpy(da.p, ai.data(), ai.size() * 2, cudaMemcpyHostToDevice));
+  CCSM_CUDA(cudaMemcpy(db.p, bi.data(), bi.size() * 2, cudaMemcpyHostToDevice));
+  if (is_f16) {
+    CCSM_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_pair_selftest_kernel<true><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K);
+  } else {
+    CCSM_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_pair_selftest_kernel<false><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K);
+  }
+  count_launch();
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("umma pair selftest kernel failed: %s", cudaGetErrorString(e));
+    return CCSM_ECUDA;
+  }
+  CCSM_CUDA(cudaMemcpy(D, dd.p, (size_t)256 * N * 4, cudaMemcpyDeviceToHost));
+  CCSM_CUDA(cudaMemcpy(Z, dz.p, (size_t)256 * 32 * 4, cudaMemcpyDeviceToHost));
+  da.release(); db.release(); dd.release(); dz.release();
+  return CCSM_OK;
+}
 
 extern "C" int ccsm_debug_umma_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, int32_t swap_lbo_sbo,
                                     const float* A, const float* B, float* D) {

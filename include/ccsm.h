@@ -165,6 +165,11 @@ int64_t ccsm_debug_tc_layer_out(ccsm_model* m, int32_t layer, float* host, int64
 int  ccsm_debug_umma_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, int32_t swap_lbo_sbo,
                           const float* A, const float* B, float* D);
 
+/* Test hook: CTA-pair tcgen05 GEMM (cta_group::2)  D(256,N) = A(256,K) . B(N,K)^T, plus a tcgen05.st check:
+ * Z(256,32) = [columns 16..31 after zeroing | columns 0..15 untouched].  Host pointers. */
+int  ccsm_debug_umma_pair_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, const float* A,
+                               const float* B, float* D, float* Z);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,3 +30,25 @@ def test_umma_gemm_matches_numpy(N, K, f16):
     D, ref = _run(N, K, f16, swap=False)
     err = np.abs(D - ref).max()
     assert err < 1e-3 * max(1.0, np.abs(ref).max()), err
+
+
+@pytest.mark.parametrize("N,K", [(192, 64), (64, 16), (256, 128)])
+@pytest.mark.parametrize("f16", [False, True])
+def test_umma_pair_gemm_matches_numpy(N, K, f16):
+    """cta_group::2: M = 256 across a CTA pair, B rows split half/half, multicast commit, remote mbarrier arrive,
+    tcgen05.st zeroing."""
+    from ccsmeth_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(N * 7 + K)
+    A = rng.standard_normal((256, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    D = np.zeros((256, N), dtype=np.float32)
+    Z = np.ones((256, 32), dtype=np.float32)
+    vp = ctypes.c_void_p
+    _lib.check(lib.ccsm_debug_umma_pair_gemm(0, N, K, int(f16), A.ctypes.data_as(vp), B.ctypes.data_as(vp),
+                                             D.ctypes.data_as(vp), Z.ctypes.data_as(vp)))
+    dt = torch.float16 if f16 else torch.bfloat16
+    ref = torch.from_numpy(A).to(dt).double().numpy() @ torch.from_numpy(B).to(dt).double().numpy().T
+    assert np.abs(D - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
+    assert np.all(Z[:, :16] == 0.0)                      # tcgen05.st zeroed columns 16..31
+    assert np.abs(Z[:, 16:] - ref[:, :16]).max() < 1e-3 * max(1.0, np.abs(ref).max())  # neighbours untouched
