@@ -43,6 +43,7 @@ struct TcState {
   int P = 0;          // parts of the currently packed weights (0 = none)
   bool f16 = false;
   std::vector<DevBuf> wimg;   // per layer
+  std::vector<DevBuf> wpair;  // per layer, CTA-pair layout (each CTA's 96-row half contiguous)
   std::vector<size_t> kx_slabs;
   DevBuf bias;                // [layer][dir][4][H]
   DevBuf wa_img, ua_img;      // [part][64 slabs x 4096]
@@ -478,6 +479,294 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair GRU layer kernel (tcgen05.mma.cta_group::2): a cluster of two CTAs (one TPC) runs M = 256:
+// CTA c owns row tile 2*pair + c (its 128 rows of A in its own shared memory, its 128 TMEM lanes) and
+// HALF of every weight tile (96 of the 192 gate rows), so each weight byte is fetched from L2 and read
+// from shared memory once per 256 rows.  TMEM holds two accumulator buffers per CTA: the MMAs of
+// unit-chunk j+1 overlap the gate epilogue of j.
+//   warp 0      producer (both CTAs): own A K-slabs + own half of the weights -> 7-stage ring
+//   warp 1      rank 0: MMA issuer for the pair; rank 1: relay (local full barrier -> leader's peer_full)
+//   warps 2-5   gate epilogue of the CTA's own row tile; zero the n_h columns with tcgen05.st after
+//               draining a buffer so that every H-part MMA can accumulate
+// Weight image: [dir][j]{X: [half][part][K_in/8 slabs x 1536 B], H: [half][part][32 slabs x 1536 B]}.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t GH_SLAB = 1536;  // 96 gate rows x 16 B
+constexpr int PAIR_STAGES = 7;
+constexpr int PAIR_THREADS = 192;
+
+template <int P>
+struct PairCfg {
+  static constexpr int KS = 8 / P;
+  static constexpr uint32_t B_PART = KS * GH_SLAB;
+  static constexpr uint32_t A_PART = KS * A_SLAB;
+  static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 28672
+  static constexpr uint32_t SMEM = PAIR_STAGES * STAGE + 2 * 4 * 256 * 4;
+};
+
+template <int P, bool F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_gru_pair_kernel(const GruParams p) {
+  using C = PairCfg<P>;
+  constexpr int KS = C::KS;
+  constexpr bool FAST = (P == 1);
+  constexpr int S = PAIR_STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[3 * S + 5];
+  __shared__ uint32_t tmem_base_s;
+  float* bias_s = reinterpret_cast<float*>(smem + S * C::STAGE);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), peer0 = smem_u32(&bars[2 * S]);
+  const uint32_t tmem_full = smem_u32(&bars[3 * S]), tmem_empty = smem_u32(&bars[3 * S + 2]),
+                 h_ready = smem_u32(&bars[3 * S + 4]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(peer0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, 8);  // one arrival per epilogue warp of both CTAs
+    }
+    mbar_init(h_ready, 4);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * 4 * 256; i += PAIR_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const int L = p.L;
+  const int n_items = (p.n_tiles / 2) * 2;  // pairs of row tiles x 2 directions
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const size_t xbytes = (size_t)2 * P * p.kx_slabs * GH_SLAB, hbytes = (size_t)2 * P * 32 * GH_SLAB;
+  const size_t wj_bytes = xbytes + hbytes;
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA: own A tile, own half of B) =====================
+    if (elect_one()) {
+      uint32_t stage = 0, use = 0, gstep = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int pair = item >> 1, d = item & 1;
+        const int64_t tile = 2 * (int64_t)pair + rank;
+        for (int s = 0; s < L; ++s, ++gstep) {
+          const int t = d ? (L - 1 - s) : s;
+          const int tprev = d ? t + 1 : t - 1;
+          for (int j = 0; j < 4; ++j) {
+            const uint8_t* wj = p.wimg + (size_t)(d * 4 + j) * wj_bytes;
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? p.kx_slabs : 32;
+              const uint8_t* wsrc = wj + (part ? xbytes : 0) + (size_t)rank * P * total * GH_SLAB;
+              for (int so = 0; so < total; so += KS) {
+                const int ns = (total - so) < KS ? (total - so) : KS;
+                if (part == 1 && so == 0 && j == 0 && gstep > 0) {
+                  mbar_wait(h_ready, (gstep - 1) & 1);
+                  fence_proxy_async_all();
+                }
+                mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+                const uint32_t fb = full0 + 8 * stage;
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                mbar_expect_tx(fb, (uint32_t)(P * ns) * (GH_SLAB + A_SLAB));
+                const uint8_t* asrc;
+                size_t part_stride;
+                if (part == 0) {
+                  if (p.kx_slabs == 2) {
+                    asrc = p.xin + ((tile * L + t) * P) * (2 * (size_t)A_SLAB);
+                    part_stride = 2 * A_SLAB;
+                  } else {
+                    asrc = p.xin + (((tile * L + t) * 8 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                    part_stride = CHUNK_BYTES;
+                  }
+                } else {
+                  if (s == 0)
+                    asrc = p.h0img + (((tile * 2 + d) * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                  else
+                    asrc = p.out + (((tile * L + tprev) * 8 + d * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES +
+                           (so & 7) * A_SLAB;
+                  part_stride = CHUNK_BYTES;
+                }
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp) {
+                  bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * GH_SLAB, ns * GH_SLAB, fb);
+                  bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, asrc + pp * part_stride, ns * A_SLAB, fb);
+                }
+                if (++stage == S) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      if (rank == 1) {
+        // ===================== relay: my operands landed -> tell the leader =====================
+        uint32_t stage = 0, use = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters)
+          for (int s = 0; s < L; ++s)
+            for (int j = 0; j < 4; ++j)
+              for (int part = 0; part < 2; ++part) {
+                const int total = part == 0 ? p.kx_slabs : 32;
+                for (int so = 0; so < total; so += KS) {
+                  mbar_wait(full0 + 8 * stage, use & 1);
+                  mbar_arrive_remote(mapa_u32(peer0 + 8 * stage, 0));
+                  if (++stage == S) {
+                    stage = 0;
+                    ++use;
+                  }
+                }
+              }
+      } else {
+        // ===================== MMA issuer for the pair =====================
+        constexpr uint32_t idesc = make_idesc(256, 192, F16);
+        uint32_t stage = 0, use = 0, chunk = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+          for (int s = 0; s < L; ++s) {
+            for (int j = 0; j < 4; ++j, ++chunk) {
+              const uint32_t buf = chunk & 1, u = chunk >> 1;
+              mbar_wait(tmem_empty + 8 * buf, u & 1);  // completion #u: #0 = initial zeroing, #k = drain of use k-1
+              tc_fence_after();
+              const uint32_t dcol = tmem + buf * 256;
+              for (int part = 0; part < 2; ++part) {
+                const int total = part == 0 ? p.kx_slabs : 32;
+                for (int so = 0; so < total; so += KS) {
+                  const int ns = (total - so) < KS ? (total - so) : KS;
+                  mbar_wait(full0 + 8 * stage, use & 1);
+                  mbar_wait(peer0 + 8 * stage, use & 1);
+                  tc_fence_after();
+                  const uint32_t sb = smem_base + stage * C::STAGE;
+                  for (int ks = 0; ks < ns / 2; ++ks) {
+#pragma unroll
+                    for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
+                      const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                      const uint64_t ad = make_smem_desc(sb + P * C::B_PART + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128);
+                      const uint64_t bd = make_smem_desc(sb + pb * C::B_PART + ks * 2 * GH_SLAB, GH_SLAB, 128);
+                      if (part == 0)
+                        umma_f16_pair(dcol, ad, bd, idesc, (so == 0 && ks == 0 && pass == 0) ? 0u : 1u);
+                      else
+                        umma_f16_pair(dcol + 64, ad, bd, idesc, 1u);  // n_h columns were zeroed by the epilogue
+                    }
+                  }
+                  umma_commit_pair(empty0 + 8 * stage, 0x3);
+                  if (++stage == S) {
+                    stage = 0;
+                    ++use;
+                  }
+                }
+              }
+              umma_commit_pair(tmem_full + 8 * buf, 0x3);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== gate epilogue (warps 2-5) of this CTA's row tile =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t remote_empty = mapa_u32(tmem_empty, 0);
+    uint32_t zeros[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) zeros[i] = 0u;
+    // initial state: n_h columns of both buffers are zero, both buffers are free
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st16(trow0 + b * 256 + 192 + c * 16, zeros);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive_remote(remote_empty);
+      mbar_arrive_remote(remote_empty + 8);
+    }
+    uint32_t chunk = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int pair = item >> 1, d = item & 1;
+      const int64_t tile = 2 * (int64_t)pair + rank;
+      const float* bz = bias_s + d * 4 * 256;
+      for (int s = 0; s < L; ++s) {
+        const int t = d ? (L - 1 - s) : s;
+        const int tprev = d ? t + 1 : t - 1;
+        for (int j = 0; j < 4; ++j, ++chunk) {
+          const uint8_t* hp_base =
+              (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
+                       : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint4 hph[8], hpl[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + q * A_SLAB + row * 16));
+            if constexpr (P == 2)
+              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + q * A_SLAB + row * 16));
+            else
+              hpl[q] = make_uint4(0, 0, 0, 0);
+          }
+          const uint32_t buf = chunk & 1, u = chunk >> 1;
+          const uint32_t trow = trow0 + buf * 256;
+          mbar_wait(tmem_full + 8 * buf, u & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ub = 0; ub < 4; ++ub) {
+            uint32_t ani[16], ar[16], az[16], anh[16];
+            tmem_ld16(trow + 0 + ub * 16, ani);
+            tmem_ld16(trow + 64 + ub * 16, ar);
+            tmem_ld16(trow + 128 + ub * 16, az);
+            tmem_ld16(trow + 192 + ub * 16, anh);
+            tmem_ld_wait();
+            tmem_st16(trow + 192 + ub * 16, zeros);  // re-arm n_h for the next use of this buffer
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              float hp[8], hn[8];
+              join8<P, F16>(hph[ub * 2 + q], hpl[ub * 2 + q], hp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int uu = j * 64 + ub * 16 + q * 8 + i;
+                const int c = q * 8 + i;
+                const float r = sigmoid_<FAST>(__uint_as_float(ar[c]) + bz[uu]);
+                const float z = sigmoid_<FAST>(__uint_as_float(az[c]) + bz[256 + uu]);
+                const float n = tanh_<FAST>(__uint_as_float(ani[c]) + bz[512 + uu] +
+                                            r * (__uint_as_float(anh[c]) + bz[768 + uu]));
+                hn[i] = fmaf(z, hp[i] - n, n);
+              }
+              uint4 hi, lo;
+              split8<P, F16>(hn, hi, lo);
+              *reinterpret_cast<uint4*>(out_base + (ub * 2 + q) * A_SLAB + row * 16) = hi;
+              if constexpr (P == 2)
+                *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + (ub * 2 + q) * A_SLAB + row * 16) = lo;
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          if (j == 3) fence_proxy_async_all();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_remote(remote_empty + 8 * buf);
+            if (j == 3) mbar_arrive(h_ready);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention + head kernel (reference utils/attention.py:48-70, models.py:135-150)
 //   Qa = q . Wa^T -> TMEM cols [0,256);  per t: D_t = out_t . Ua^T -> TMEM cols [256,512)
 //   e_t = va . tanh(Qa + D_t) (thread-local: TMEM lane = row), softmax over t, ctx = sum_t w_t out_t,
@@ -656,7 +945,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        constexpr int TB = 7;  // loads in flight per thread (L = 21 -> 3 batches)
+        constexpr int TB = (P == 1) ? 21 : 11;  // 16-byte loads in flight per thread and part
         for (int t0 = 0; t0 < L; t0 += TB) {
           uint4 hi[TB], lo[TB];
 #pragma unroll
@@ -788,6 +1077,7 @@ int tc_upload_weights(ccsm_model* m) {
   T.sm_count = prop.multiProcessorCount;
   static const char* sfx[2] = {"", "_reverse"};
   T.wimg.resize(NL);
+  T.wpair.resize(NL);
   T.kx_slabs.resize(NL);
   std::vector<float> bias((size_t)NL * 2 * 4 * H);
   for (int l = 0; l < NL; ++l) {
@@ -830,6 +1120,26 @@ int tc_upload_weights(ccsm_model* m) {
     }
     CCSM_TRY(T.wimg[l].reserve(img.size() * 2));
     CCSM_CUDA(cudaMemcpy(T.wimg[l].p, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    {
+      // CTA-pair layout: same rows, split into halves of 96: [half][part][slab][96 rows x 8]
+      std::vector<uint16_t> pimg(img.size());
+      for (int dj = 0; dj < 8; ++dj)
+        for (int part = 0; part < 2; ++part) {
+          const int ks = part == 0 ? kxs : 32;
+          const uint16_t* src = img.data() + (size_t)dj * (x_elems + h_elems) + (part ? x_elems : 0);
+          uint16_t* dst = pimg.data() + (size_t)dj * (x_elems + h_elems) + (part ? x_elems : 0);
+          for (int pp = 0; pp < P; ++pp)
+            for (int sl = 0; sl < ks; ++sl)
+              for (int n = 0; n < 192; ++n) {
+                const int c = n / 96, nn = n % 96;
+                const uint16_t* a = src + ((size_t)pp * ks + sl) * 192 * 8 + (size_t)n * 8;
+                uint16_t* b = dst + (((size_t)c * P + pp) * ks + sl) * 96 * 8 + (size_t)nn * 8;
+                for (int e = 0; e < 8; ++e) b[e] = a[e];
+              }
+        }
+      CCSM_TRY(T.wpair[l].reserve(pimg.size() * 2));
+      CCSM_CUDA(cudaMemcpy(T.wpair[l].p, pimg.data(), pimg.size() * 2, cudaMemcpyHostToDevice));
+    }
   }
   CCSM_TRY(T.bias.reserve(bias.size() * 4));
   CCSM_CUDA(cudaMemcpy(T.bias.p, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
@@ -860,6 +1170,7 @@ void tc_release(ccsm_model* m) {
   if (!m->tc) return;
   TcState& T = *m->tc;
   for (auto& b : T.wimg) b.release();
+  for (auto& b : T.wpair) b.release();
   T.bias.release(); T.wa_img.release(); T.ua_img.release(); T.va.release(); T.fc_w.release(); T.fc_b.release();
   T.embed.release(); T.x0img.release(); T.h0img.release();
   for (auto& b : T.act) b.release();
@@ -879,7 +1190,8 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
   return CCSM_OK;
 }
 
-// GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2).
+// GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2),
+// 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
 // Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0; layers >= 1 -> 0 for the
 // single-pass modes and 2 for the x3 modes (hi+lo images double the L2 working set; fewer tiles in flight keeps the
@@ -888,8 +1200,8 @@ static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    v[0] = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
-    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '2') ? e[1] - '0' : v[0];
+    v[0] = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : -1;
+    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '3') ? e[1] - '0' : v[0];
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
@@ -923,6 +1235,8 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
                                    (int)GruCfg<P, 2, 1>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)GruCfg<P, 1, 2>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)PairCfg<P>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_att_head_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)AttCfg<P>::SMEM));
     attr_set[P - 1][F16] = true;
@@ -939,7 +1253,13 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
     gp.kx_slabs = (int)T.kx_slabs[l];
     pid = m->prof.begin(l == 0 ? PROF_GRU_L0 : PROF_GRU_LN, (double)sites, st);
     const int variant = gru_variant(l, P);
-    if (variant == 1) {
+    if (variant == 3) {
+      gp.wimg = T.wpair[l].as<uint8_t>();
+      const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
+      const int64_t max_clusters = T.sm_count / 2;
+      const int clusters = (int)(items < max_clusters ? items : max_clusters);
+      tc_gru_pair_kernel<P, F16><<<2 * clusters, PAIR_THREADS, PairCfg<P>::SMEM, st>>>(gp);
+    } else if (variant == 1) {
       const int64_t items = tiles;  // (tiles / 2) x 2 directions
       const int grid = (int)(items < T.sm_count ? items : T.sm_count);
       tc_gru_layer_kernel<P, F16, 2, 1><<<grid, GruCfg<P, 2, 1>::THREADS, GruCfg<P, 2, 1>::SMEM, st>>>(gp);
