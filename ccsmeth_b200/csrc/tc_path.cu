@@ -60,11 +60,13 @@ struct TcState {
 // ------------------------------------------------------------------------------------------------
 // math
 // ------------------------------------------------------------------------------------------------
+// FAST: the argument arrives pre-halved (the r/z gate rows and biases are scaled by 0.5 when the weight images
+// are packed -- exact in bf16/fp16), so sigmoid(2x') = 0.5 * tanh(x') + 0.5 is one MUFU + one FFMA.
 template <bool FAST>
 __device__ __forceinline__ float sigmoid_(float x) {
   if constexpr (FAST) {
     float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
     return fmaf(t, 0.5f, 0.5f);
   } else {
     return __fdividef(1.f, 1.f + __expf(-x));
@@ -112,6 +114,28 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&
     }
     v[2 * i] = a.x;
     v[2 * i + 1] = a.y;
+  }
+}
+
+// Writes the gate biases of hidden units [u0, u0+16) into the four accumulator column groups of a buffer
+// (tcgen05.st), so that every MMA of the next unit-chunk simply accumulates on top of them:
+//   [0,64) n_i <- b_in, [64,128) r <- b_ir+b_hr, [128,192) z <- b_iz+b_hz, [192,256) n_h <- b_hn.
+// bias_d: this CTA's direction, [4][256] floats in shared memory (gate order r, z, in, hn).
+__device__ __forceinline__ void arm_bias16(uint32_t trow, int ub, const float* bias_d, int u0) {
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {  // not unrolled: keeps only 16 staging registers live
+    uint32_t v[16];
+    const int goff = g == 0 ? 512 : (g == 1 ? 0 : (g == 2 ? 256 : 768));  // column group -> bias row: n_i, r, z, n_h
+    const float4* src = reinterpret_cast<const float4*>(bias_d + goff + u0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = src[q];
+      v[4 * q + 0] = __float_as_uint(b.x);
+      v[4 * q + 1] = __float_as_uint(b.y);
+      v[4 * q + 2] = __float_as_uint(b.z);
+      v[4 * q + 3] = __float_as_uint(b.w);
+    }
+    tmem_st16(trow + g * 64 + ub * 16, v);
   }
 }
 
@@ -221,7 +245,7 @@ struct GruParams {
 template <int P, int NSLOT, int NBUF>
 struct GruCfg {
   static constexpr int KS = (NSLOT == 2) ? 8 / P : 4 / P;  // slabs per stage per part
-  static constexpr int STAGES = NSLOT == 2 ? 3 : (NBUF == 2 ? 10 : 4);
+  static constexpr int STAGES = NSLOT == 2 ? 3 : (NBUF == 2 ? 10 : 5);
   static constexpr int THREADS = NSLOT == 2 ? 384 : 192;
   static constexpr int CTAS_PER_SM = (NSLOT == 1 && NBUF == 1) ? 2 : 1;
   static constexpr int EPI_WARP0 = NSLOT == 2 ? 4 : 2;
@@ -348,14 +372,14 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc192 = make_idesc(128, 192, F16), idesc128 = make_idesc(128, 128, F16),
-                         idesc64 = make_idesc(128, 64, F16);
+      constexpr uint32_t idesc192 = make_idesc(128, 192, F16);
       uint32_t stage = 0, use = 0, chunk = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         for (int s = 0; s < L; ++s) {
           for (int j = 0; j < 4; ++j, ++chunk) {
             const uint32_t buf = chunk % NBUF, bphase = (chunk / NBUF) & 1;
-            mbar_wait(tmem_empty + 8 * buf, bphase ^ 1);  // this buffer's accumulators drained by the epilogue
+            // completion #u of tmem_empty[buf]: #0 = initial bias arming, #k = drain + re-arm after use k-1
+            mbar_wait(tmem_empty + 8 * buf, bphase);
             tc_fence_after();
             for (int part = 0; part < 2; ++part) {
               const int total = part == 0 ? p.kx_slabs : 32;
@@ -365,7 +389,6 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
                 tc_fence_after();
                 const uint32_t sb = smem_base + stage * C::STAGE;
                 for (int ks = 0; ks < ns / 2; ++ks) {
-                  const bool first = (so == 0 && ks == 0);
 #pragma unroll
                   for (int sl = 0; sl < NSLOT; ++sl) {
                     const uint32_t dcol = tmem + (NBUF == 2 ? buf : sl) * 256;
@@ -375,16 +398,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
                       const uint32_t a_addr = sb + P * C::B_PART + (sl * P + pa) * C::A_PART + ks * 2 * A_SLAB;
                       const uint32_t b_addr = sb + pb * C::B_PART + ks * 2 * G_SLAB;
                       const uint64_t ad = make_smem_desc(a_addr, A_SLAB, 128);
-                      if (part == 0) {
-                        // X part -> columns [0,192) = (n_i, r, z); the very first MMA zero-initialises them
-                        umma_f16(dcol, ad, make_smem_desc(b_addr, G_SLAB, 128), idesc192, (first && pass == 0) ? 0u : 1u);
-                      } else if (first && pass == 0) {
-                        // H part -> columns [64,256) = (r, z, n_h): r,z accumulate on top of the X part, n_h starts at 0
-                        umma_f16(dcol + 64, ad, make_smem_desc(b_addr, G_SLAB, 128), idesc128, 1u);
-                        umma_f16(dcol + 192, ad, make_smem_desc(b_addr + 128 * 16, G_SLAB, 128), idesc64, 0u);
-                      } else {
-                        umma_f16(dcol + 64, ad, make_smem_desc(b_addr, G_SLAB, 128), idesc192, 1u);
-                      }
+                      // X part -> columns [0,192) = (n_i, r, z); H part -> columns [64,256) = (r, z, n_h).
+                      // The epilogue pre-loaded every column with its gate bias, so all MMAs accumulate.
+                      umma_f16(dcol + (part == 0 ? 0 : 64), ad, make_smem_desc(b_addr, G_SLAB, 128), idesc192, 1u);
                     }
                   }
                 }
@@ -408,10 +424,18 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
     const int row = quad * 32 + lane;
     const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
     uint32_t chunk = 0;
+    // gridDim.x is even (host), so every item of this CTA has the same direction: the biases to arm are fixed
+    const float* bz = bias_s + (blockIdx.x & 1) * 4 * 256;
+    for (int b = 0; b < NBUF; ++b) {  // arm the first NBUF unit-chunks (j = b)
+#pragma unroll
+      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + (NBUF == 2 ? b * 256 : 0), ub, bz, b * 64 + ub * 16);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(tmem_empty + 8 * b);
+    }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int pair = item >> 1, d = item & 1;
       const int64_t tile = NSLOT * (int64_t)pair + slot;
-      const float* bz = bias_s + d * 4 * 256;
       for (int s = 0; s < L; ++s) {
         const int t = d ? (L - 1 - s) : s;
         const int tprev = d ? t + 1 : t - 1;
@@ -442,18 +466,18 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
             tmem_ld16(trow + 128 + ub * 16, az);
             tmem_ld16(trow + 192 + ub * 16, anh);
             tmem_ld_wait();
+            // re-arm these columns with the biases of the unit-chunk that uses this buffer next
+            arm_bias16(trow, ub, bz, ((j + NBUF) & 3) * 64 + ub * 16);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float hp[8], hn[8];
               join8<P, F16>(hph[ub * 2 + q], hpl[ub * 2 + q], hp);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int u = j * 64 + ub * 16 + q * 8 + i;
                 const int c = q * 8 + i;
-                const float r = sigmoid_<FAST>(__uint_as_float(ar[c]) + bz[u]);
-                const float z = sigmoid_<FAST>(__uint_as_float(az[c]) + bz[256 + u]);
-                const float n = tanh_<FAST>(__uint_as_float(ani[c]) + bz[512 + u] +
-                                            r * (__uint_as_float(anh[c]) + bz[768 + u]));
+                const float r = sigmoid_<FAST>(__uint_as_float(ar[c]));
+                const float z = sigmoid_<FAST>(__uint_as_float(az[c]));
+                const float n = tanh_<FAST>(fmaf(r, __uint_as_float(anh[c]), __uint_as_float(ani[c])));
                 hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
               }
               uint4 hi, lo;
@@ -463,6 +487,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
                 *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + (ub * 2 + q) * A_SLAB + row * 16) = lo;
             }
           }
+          tmem_st_wait();
           tc_fence_before();
           mbar_arrive(tmem_empty + 8 * buf);
           if (j == 3) {
@@ -651,10 +676,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
                       const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
                       const uint64_t ad = make_smem_desc(sb + P * C::B_PART + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128);
                       const uint64_t bd = make_smem_desc(sb + pb * C::B_PART + ks * 2 * GH_SLAB, GH_SLAB, 128);
-                      if (part == 0)
-                        umma_f16_pair(dcol, ad, bd, idesc, (so == 0 && ks == 0 && pass == 0) ? 0u : 1u);
-                      else
-                        umma_f16_pair(dcol + 64, ad, bd, idesc, 1u);  // n_h columns were zeroed by the epilogue
+                      umma_f16_pair(dcol + (part == 0 ? 0 : 64), ad, bd, idesc, 1u);  // columns pre-loaded with biases
                     }
                   }
                   umma_commit_pair(empty0 + 8 * stage, 0x3);
@@ -677,14 +699,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
     const int row = quad * 32 + lane;
     const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t remote_empty = mapa_u32(tmem_empty, 0);
-    uint32_t zeros[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) zeros[i] = 0u;
-    // initial state: n_h columns of both buffers are zero, both buffers are free
+    // every item of this cluster has the same direction (the cluster count is even)
+    const float* bz = bias_s + (cluster_id & 1) * 4 * 256;
+    // initial state: both buffers armed with the biases of unit-chunks 0 and 1
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st16(trow0 + b * 256 + 192 + c * 16, zeros);
+      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + b * 256, ub, bz, b * 64 + ub * 16);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -697,7 +718,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int pair = item >> 1, d = item & 1;
       const int64_t tile = 2 * (int64_t)pair + rank;
-      const float* bz = bias_s + d * 4 * 256;
       for (int s = 0; s < L; ++s) {
         const int t = d ? (L - 1 - s) : s;
         const int tprev = d ? t + 1 : t - 1;
@@ -727,19 +747,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
             tmem_ld16(trow + 128 + ub * 16, az);
             tmem_ld16(trow + 192 + ub * 16, anh);
             tmem_ld_wait();
-            tmem_st16(trow + 192 + ub * 16, zeros);  // re-arm n_h for the next use of this buffer
+            arm_bias16(trow, ub, bz, ((j + 2) & 3) * 64 + ub * 16);  // biases of the next user of this buffer
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float hp[8], hn[8];
               join8<P, F16>(hph[ub * 2 + q], hpl[ub * 2 + q], hp);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int uu = j * 64 + ub * 16 + q * 8 + i;
                 const int c = q * 8 + i;
-                const float r = sigmoid_<FAST>(__uint_as_float(ar[c]) + bz[uu]);
-                const float z = sigmoid_<FAST>(__uint_as_float(az[c]) + bz[256 + uu]);
-                const float n = tanh_<FAST>(__uint_as_float(ani[c]) + bz[512 + uu] +
-                                            r * (__uint_as_float(anh[c]) + bz[768 + uu]));
+                const float r = sigmoid_<FAST>(__uint_as_float(ar[c]));
+                const float z = sigmoid_<FAST>(__uint_as_float(az[c]));
+                const float n = tanh_<FAST>(fmaf(r, __uint_as_float(anh[c]), __uint_as_float(ani[c])));
                 hn[i] = fmaf(z, hp[i] - n, n);
               }
               uint4 hi, lo;
@@ -1098,22 +1116,31 @@ int tc_upload_weights(ccsm_model* m) {
       for (int j = 0; j < 4; ++j) {
         uint16_t* base = img.data() + (size_t)(d * 4 + j) * (x_elems + h_elems);
         // X part rows: n_i, r, z   (PyTorch gate row order in weight_ih: r [0,H), z [H,2H), n [2H,3H))
+        // single-pass modes: r/z rows pre-scaled by 0.5 (exact) for the one-MUFU sigmoid, see sigmoid_<FAST>
+        std::vector<float> tmp((size_t)(K > H ? K : H));
         pack_image(base, 192, kxs, K, P, f16, [&](int n) {
           const int g = n / 64, u = j * 64 + n % 64;
           const int row = (g == 0 ? 2 * H : (g == 1 ? 0 : H)) + u;
-          return wih->data.data() + (size_t)row * K;
+          const float* w = wih->data.data() + (size_t)row * K;
+          if (P == 2 || g == 0) return w;
+          for (int k = 0; k < K; ++k) tmp[k] = 0.5f * w[k];
+          return (const float*)tmp.data();
         });
         // H part rows: r, z, n_h
         pack_image(base + x_elems, 192, 32, H, P, f16, [&](int n) {
           const int g = n / 64, u = j * 64 + n % 64;
           const int row = (g == 0 ? 0 : (g == 1 ? H : 2 * H)) + u;
-          return whh->data.data() + (size_t)row * H;
+          const float* w = whh->data.data() + (size_t)row * H;
+          if (P == 2 || g == 2) return w;
+          for (int k = 0; k < H; ++k) tmp[k] = 0.5f * w[k];
+          return (const float*)tmp.data();
         });
       }
       float* b = bias.data() + ((size_t)l * 2 + d) * 4 * H;
       for (int u = 0; u < H; ++u) {
-        b[u] = bih->data[u] + bhh->data[u];                  // b_r
-        b[H + u] = bih->data[H + u] + bhh->data[H + u];      // b_z
+        const float gs = P == 1 ? 0.5f : 1.f;                // matches the r/z row scaling above
+        b[u] = gs * (bih->data[u] + bhh->data[u]);                  // b_r
+        b[H + u] = gs * (bih->data[H + u] + bhh->data[H + u]);      // b_z
         b[2 * H + u] = bih->data[2 * H + u];                 // b_in
         b[3 * H + u] = bhh->data[2 * H + u];                 // b_hn (inside r * (.))
       }
@@ -1193,9 +1220,9 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
 // GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2),
 // 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
-// Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0; layers >= 1 -> 0 for the
-// single-pass modes and 2 for the x3 modes (hi+lo images double the L2 working set; fewer tiles in flight keeps the
-// 4x-per-step activation re-reads out of HBM).
+// Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound, little weight traffic) -> 3, the
+// CTA-pair kernel; layers >= 1 -> 0 for the single-pass modes and 2 for the x3 modes (hi+lo images double the L2
+// working set; fewer tiles in flight keeps the 4x-per-step activation re-reads out of HBM).
 static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
@@ -1205,7 +1232,8 @@ static int gru_variant(int layer, int P) {
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
-  return (layer > 0 && P == 2) ? 2 : 0;
+  if (layer == 0) return 3;
+  return P == 2 ? 2 : 0;
 }
 
 template <int P, bool F16>
@@ -1257,20 +1285,20 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
       gp.wimg = T.wpair[l].as<uint8_t>();
       const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
       const int64_t max_clusters = T.sm_count / 2;
-      const int clusters = (int)(items < max_clusters ? items : max_clusters);
+      const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;  // even: fixed direction per cluster
       tc_gru_pair_kernel<P, F16><<<2 * clusters, PAIR_THREADS, PairCfg<P>::SMEM, st>>>(gp);
     } else if (variant == 1) {
       const int64_t items = tiles;  // (tiles / 2) x 2 directions
-      const int grid = (int)(items < T.sm_count ? items : T.sm_count);
+      const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;  // even: fixed direction per CTA
       tc_gru_layer_kernel<P, F16, 2, 1><<<grid, GruCfg<P, 2, 1>::THREADS, GruCfg<P, 2, 1>::SMEM, st>>>(gp);
     } else if (variant == 2) {
       const int64_t items = tiles * 2;
-      const int grid = (int)(items < T.sm_count ? items : T.sm_count);
+      const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;
       tc_gru_layer_kernel<P, F16, 1, 2><<<grid, GruCfg<P, 1, 2>::THREADS, GruCfg<P, 1, 2>::SMEM, st>>>(gp);
     } else {
       const int64_t items = tiles * 2;
       const int64_t slots = (int64_t)T.sm_count * 2;
-      const int grid = (int)(items < slots ? items : slots);
+      const int grid = (int)(items < slots ? items : slots) & ~1;
       tc_gru_layer_kernel<P, F16, 1, 1><<<grid, GruCfg<P, 1, 1>::THREADS, GruCfg<P, 1, 1>::SMEM, st>>>(gp);
     }
     m->prof.end(pid, st);
