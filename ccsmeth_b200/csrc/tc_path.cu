@@ -1220,9 +1220,9 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
 // GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2),
 // 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
-// Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound, little weight traffic) -> 3, the
-// CTA-pair kernel; layers >= 1 -> 0 for the single-pass modes and 2 for the x3 modes (hi+lo images double the L2
-// working set; fewer tiles in flight keeps the 4x-per-step activation re-reads out of HBM).
+// Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0; layers >= 1 -> 0 for the
+// single-pass modes and 2 for the x3 modes (hi+lo images double the L2 working set; fewer tiles in flight keeps the
+// 4x-per-step activation re-reads out of HBM).  The CTA-pair kernel (3) is correct but slower in round 1.
 static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
@@ -1232,8 +1232,7 @@ static int gru_variant(int layer, int P) {
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
-  if (layer == 0) return 3;
-  return P == 2 ? 2 : 0;
+  return (layer > 0 && P == 2) ? 2 : 0;
 }
 
 template <int P, bool F16>
