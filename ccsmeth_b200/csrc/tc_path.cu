@@ -233,6 +233,7 @@ struct GruParams {
   int n_tiles;           // even
   int L;
   int kx_slabs;          // 2 (layer 0) or 64
+  int l2_hint;           // 1: bulk loads carry an L2 evict_last hint (experiment, CCSM_TC_L2HINT)
 };
 
 // NSLOT = row tiles processed together by one CTA (sharing every weight stage).
@@ -307,6 +308,8 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
     if (elect_one()) {
       uint32_t stage = 0, use = 0;  // use = how many times the ring wrapped
       uint32_t gstep = 0;
+      const uint64_t pol = make_policy_evict_last();
+      const bool hint = p.l2_hint != 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int pair = item >> 1, d = item & 1;
         const int64_t tile0 = NSLOT * (int64_t)pair;
@@ -330,8 +333,10 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
                 // weights
                 const uint8_t* wsrc = wj + (part ? xbytes : 0);
 #pragma unroll
-                for (int pp = 0; pp < P; ++pp)
-                  bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb);
+                for (int pp = 0; pp < P; ++pp) {
+                  if (hint) bulk_g2s_hint(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb, pol);
+                  else bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb);
+                }
                 // activations of every slot
 #pragma unroll
                 for (int sl = 0; sl < NSLOT; ++sl) {
@@ -355,8 +360,11 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
                     part_stride = CHUNK_BYTES;
                   }
 #pragma unroll
-                  for (int pp = 0; pp < P; ++pp)
-                    bulk_g2s(sb + P * C::B_PART + (sl * P + pp) * C::A_PART, asrc + pp * part_stride, ns * A_SLAB, fb);
+                  for (int pp = 0; pp < P; ++pp) {
+                    const uint32_t dsta = sb + P * C::B_PART + (sl * P + pp) * C::A_PART;
+                    if (hint) bulk_g2s_hint(dsta, asrc + pp * part_stride, ns * A_SLAB, fb, pol);
+                    else bulk_g2s(dsta, asrc + pp * part_stride, ns * A_SLAB, fb);
+                  }
                 }
                 if (++stage == GRU_STAGES) {
                   stage = 0;
@@ -516,24 +524,30 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
 // Weight image: [dir][j]{X: [half][part][K_in/8 slabs x 1536 B], H: [half][part][32 slabs x 1536 B]}.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t GH_SLAB = 1536;  // 96 gate rows x 16 B
-constexpr int PAIR_STAGES = 7;
 constexpr int PAIR_THREADS = 192;
 
-template <int P>
+// NBUF = 2: one cluster per TPC, TMEM double-buffered, 7 stages.
+// NBUF = 1: two clusters per TPC (two CTAs per SM, 256 TMEM columns each), 3 stages each: one cluster's gate
+//           epilogue and step-boundary latency overlap the other cluster's MMAs.
+template <int P, int NBUF>
 struct PairCfg {
   static constexpr int KS = 8 / P;
+  static constexpr int STAGES = NBUF == 2 ? 7 : 3;
+  static constexpr int CTAS_PER_SM = NBUF == 2 ? 1 : 2;
+  static constexpr uint32_t TMEM_COLS = NBUF * 256;
   static constexpr uint32_t B_PART = KS * GH_SLAB;
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 28672
-  static constexpr uint32_t SMEM = PAIR_STAGES * STAGE + 2 * 4 * 256 * 4;
+  static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
 };
 
-template <int P, bool F16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_gru_pair_kernel(const GruParams p) {
-  using C = PairCfg<P>;
+template <int P, bool F16, int NBUF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, PairCfg<P, NBUF>::CTAS_PER_SM)
+    tc_gru_pair_kernel(const GruParams p) {
+  using C = PairCfg<P, NBUF>;
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
-  constexpr int S = PAIR_STAGES;
+  constexpr int S = C::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[3 * S + 5];
   __shared__ uint32_t tmem_base_s;
@@ -550,7 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
       mbar_init(empty0 + 8 * i, 1);
       mbar_init(peer0 + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NBUF; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
       mbar_init(tmem_empty + 8 * i, 8);  // one arrival per epilogue warp of both CTAs
     }
@@ -559,7 +573,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
   }
   for (int i = threadIdx.x; i < 2 * 4 * 256; i += PAIR_THREADS) bias_s[i] = p.bias[i];
   if (warp == 1) {
-    tmem_alloc2(smem_u32(&tmem_base_s), 512);
+    tmem_alloc2(smem_u32(&tmem_base_s), C::TMEM_COLS);
     tmem_relinquish2();
   }
   tc_fence_before();
@@ -658,8 +672,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
         for (int item = cluster_id; item < n_items; item += n_clusters) {
           for (int s = 0; s < L; ++s) {
             for (int j = 0; j < 4; ++j, ++chunk) {
-              const uint32_t buf = chunk & 1, u = chunk >> 1;
-              mbar_wait(tmem_empty + 8 * buf, u & 1);  // completion #u: #0 = initial zeroing, #k = drain of use k-1
+              const uint32_t buf = chunk % NBUF, u = chunk / NBUF;
+              mbar_wait(tmem_empty + 8 * buf, u & 1);  // completion #u: #0 = initial arming, #k = drain of use k-1
               tc_fence_after();
               const uint32_t dcol = tmem + buf * 256;
               for (int part = 0; part < 2; ++part) {
@@ -701,9 +715,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
     const uint32_t remote_empty = mapa_u32(tmem_empty, 0);
     // every item of this cluster has the same direction (the cluster count is even)
     const float* bz = bias_s + (cluster_id & 1) * 4 * 256;
-    // initial state: both buffers armed with the biases of unit-chunks 0 and 1
+    // initial state: every buffer armed with the biases of its first unit-chunk
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
 #pragma unroll
       for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + b * 256, ub, bz, b * 64 + ub * 16);
     }
@@ -711,8 +725,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive_remote(remote_empty);
-      mbar_arrive_remote(remote_empty + 8);
+#pragma unroll
+      for (int b = 0; b < NBUF; ++b) mbar_arrive_remote(remote_empty + 8 * b);
     }
     uint32_t chunk = 0;
     for (int item = cluster_id; item < n_items; item += n_clusters) {
@@ -735,7 +749,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
             else
               hpl[q] = make_uint4(0, 0, 0, 0);
           }
-          const uint32_t buf = chunk & 1, u = chunk >> 1;
+          const uint32_t buf = chunk % NBUF, u = chunk / NBUF;
           const uint32_t trow = trow0 + buf * 256;
           mbar_wait(tmem_full + 8 * buf, u & 1);
           tc_fence_after();
@@ -747,7 +761,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
             tmem_ld16(trow + 128 + ub * 16, az);
             tmem_ld16(trow + 192 + ub * 16, anh);
             tmem_ld_wait();
-            arm_bias16(trow, ub, bz, ((j + 2) & 3) * 64 + ub * 16);  // biases of the next user of this buffer
+            arm_bias16(trow, ub, bz, ((j + NBUF) & 3) * 64 + ub * 16);  // biases of the next user of this buffer
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float hp[8], hn[8];
@@ -781,7 +795,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) tc_
   }
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc2(tmem, 512);
+  if (warp == 1) tmem_dealloc2(tmem, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1218,7 +1232,7 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
 }
 
 // GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2),
-// 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered).
+// 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered), 4 = CTA pair, two clusters per TPC (NBUF 1).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
 // Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0; layers >= 1 -> 0 for the
 // single-pass modes and 2 for the x3 modes (hi+lo images double the L2 working set; fewer tiles in flight keeps the
@@ -1227,8 +1241,8 @@ static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    v[0] = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : -1;
-    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '3') ? e[1] - '0' : v[0];
+    v[0] = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : -1;
+    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '4') ? e[1] - '0' : v[0];
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
@@ -1262,8 +1276,10 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
                                    (int)GruCfg<P, 2, 1>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)GruCfg<P, 1, 2>::SMEM));
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)PairCfg<P>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)PairCfg<P, 2>::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)PairCfg<P, 1>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_att_head_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)AttCfg<P>::SMEM));
     attr_set[P - 1][F16] = true;
@@ -1278,14 +1294,25 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
     gp.n_tiles = (int)tiles;
     gp.L = L;
     gp.kx_slabs = (int)T.kx_slabs[l];
+    {
+      static int hint = -1;
+      if (hint < 0) {
+        const char* e = getenv("CCSM_TC_L2HINT");
+        hint = (e && atoi(e) != 0) ? 1 : 0;
+      }
+      gp.l2_hint = hint;
+    }
     pid = m->prof.begin(l == 0 ? PROF_GRU_L0 : PROF_GRU_LN, (double)sites, st);
     const int variant = gru_variant(l, P);
-    if (variant == 3) {
+    if (variant == 3 || variant == 4) {
       gp.wimg = T.wpair[l].as<uint8_t>();
       const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
-      const int64_t max_clusters = T.sm_count / 2;
+      const int64_t max_clusters = (variant == 3 ? 1 : 2) * (T.sm_count / 2);
       const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;  // even: fixed direction per cluster
-      tc_gru_pair_kernel<P, F16><<<2 * clusters, PAIR_THREADS, PairCfg<P>::SMEM, st>>>(gp);
+      if (variant == 3)
+        tc_gru_pair_kernel<P, F16, 2><<<2 * clusters, PAIR_THREADS, PairCfg<P, 2>::SMEM, st>>>(gp);
+      else
+        tc_gru_pair_kernel<P, F16, 1><<<2 * clusters, PAIR_THREADS, PairCfg<P, 1>::SMEM, st>>>(gp);
     } else if (variant == 1) {
       const int64_t items = tiles;  // (tiles / 2) x 2 directions
       const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;  // even: fixed direction per CTA
