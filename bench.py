@@ -143,7 +143,7 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "synthetic (batch,21,feat) attbigru2s forward, bounded sample: %d batches x %d sites "
-                                  "per step on host cores" % (per_step, bs), "seq_len": 21, "hidden": 256, "layers": 3},
+                                  "per step on host cores" % (per_step, bs), "kmer_len": 21},
            "cpu_baseline": {"value": val, "unit": "sites/s", "cores": cores, "kind": "port",
                             "sample": "%d steps x %d batches x %d sites, torch %s CPU, %d threads" %
                                       (args.steps, per_step, bs, torch.__version__, cores)},
@@ -310,7 +310,7 @@ def main():
                                           "fp32": "f32"}[prec],
            "data": "synthetic",
            "config": {"workload": "synthetic %dx21xfeat per GPU, attbigru2s forward (v3 checkpoint weights), %s" % (S, prec),
-                      "sites_per_gpu_per_step": S, "seq_len": 21, "hidden": 256, "layers": 3, "precision": prec,
+                      "sites_per_gpu_per_step": S, "kmer_len": 21, "precision": prec,
                       "l2": "inputs (%.1f GB/step) larger than L2" % (S * ALG_BYTES_PER_SITE / 1e9),
                       "parallelism": "dp%d (reads sharded per rank, no data-path collective)" % world},
            "max_abs_dprob_vs_cpu_port": dprob, "parity_sites": P,
@@ -321,7 +321,7 @@ def main():
                                              "h2d_bytes_per_step": E2 * (8 * 21 * 4 + 2 * 6 * 256 * 4)}},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
            "allreduce_counts": {"sites": counts[0], "model_batches": counts[1]}}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count()
         v, dt, th = cpu_port_throughput(ck, 24, 512, warmup=2)
         out["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": th, "kind": "port",
