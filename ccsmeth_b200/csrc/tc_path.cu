@@ -819,7 +819,7 @@ struct AttParams {
 };
 
 constexpr int ATT_STAGES = 4;
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 384;  // warp 0 producer, 1 MMA, 4-7 score warps, 8-11 context/head warps
 
 template <int P>
 struct AttCfg {
@@ -827,7 +827,7 @@ struct AttCfg {
   static constexpr uint32_t B_PART = KS * T_SLAB;
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 49152
-  static constexpr uint32_t SMEM = ATT_STAGES * STAGE + (256 + 2048 + 128 * 22) * 4;
+  static constexpr uint32_t SMEM = ATT_STAGES * STAGE + (256 + 2048 + 2 * 128 * 22) * 4;
 };
 
 template <int P, bool F16>
@@ -836,15 +836,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * ATT_STAGES + 2];
+  __shared__ __align__(8) uint64_t bars[2 * ATT_STAGES + 6];
   __shared__ uint32_t tmem_base_s;
   float* va_s = reinterpret_cast<float*>(smem + ATT_STAGES * C::STAGE);
   float* fc_s = va_s + 256;
-  float* e_s = fc_s + 2048;  // [128][22]
+  float* e_s = fc_s + 2048;  // [2][128][22]: softmax weights of a tile, double-buffered between the warp groups
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[ATT_STAGES]);
   const uint32_t d_full = smem_u32(&bars[2 * ATT_STAGES]), d_empty = smem_u32(&bars[2 * ATT_STAGES + 1]);
+  const uint32_t w_full = smem_u32(&bars[2 * ATT_STAGES + 2]), w_empty = smem_u32(&bars[2 * ATT_STAGES + 4]);
   if (threadIdx.x == 0) {
     for (int i = 0; i < ATT_STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
@@ -852,6 +853,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
     }
     mbar_init(d_full, 1);
     mbar_init(d_empty, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(w_full + 8 * i, 128);   // score warps -> context warps: weights of a tile are in e_s[i]
+      mbar_init(w_empty + 8 * i, 128);  // context warps -> score warps: e_s[i] may be overwritten
+    }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 256; i += ATT_THREADS) va_s[i] = p.va[i];
@@ -934,13 +939,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== score warps: e_t = va . tanh(Qa + D_t), softmax over t =====================
     const int quad = warp - 4;
     const int row = quad * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-    float* my_e = e_s + row * 22;
-    uint32_t dcount = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    uint32_t dcount = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t wb = it & 1;
+      float* my_e = e_s + (wb * 128 + row) * 22;
+      mbar_wait(w_empty + 8 * wb, ((it >> 1) & 1) ^ 1);  // context warps are done with this buffer
       for (int t = 0; t < L; ++t, ++dcount) {
         mbar_wait(d_full, dcount & 1);
         tc_fence_after();
@@ -959,7 +967,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
         tc_fence_before();
         mbar_arrive(d_empty);
       }
-      // softmax over t (thread-local)
+      // softmax over t (thread-local), normalised weights handed to the context warps
       float mx = -INFINITY;
       for (int t = 0; t < L; ++t) mx = fmaxf(mx, my_e[t]);
       float sum = 0.f;
@@ -969,6 +977,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
         sum += w;
       }
       const float inv = 1.f / sum;
+      for (int t = 0; t < L; ++t) my_e[t] *= inv;
+      mbar_arrive(w_full + 8 * wb);
+    }
+  } else if (warp >= 8) {
+    // ===================== context + head warps (overlap the next tile's MMAs and scores) =====================
+    const int row = (warp - 8) * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t wb = it & 1;
+      const float* my_e = e_s + (wb * 128 + row) * 22;
+      mbar_wait(w_full + 8 * wb, (it >> 1) & 1);
+      float wt[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) wt[t] = t < L ? my_e[t] : 0.f;
+      mbar_arrive(w_empty + 8 * wb);  // weights are in registers
       // context + fc1 partial (this row's strand half of fc1)
       const int strand = row & 1;
       float lg0 = 0.f, lg1 = 0.f;
@@ -978,24 +1001,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
         constexpr int TB = (P == 1) ? 21 : 11;  // 16-byte loads in flight per thread and part
-        for (int t0 = 0; t0 < L; t0 += TB) {
-          uint4 hi[TB], lo[TB];
 #pragma unroll
-          for (int k = 0; k < TB; ++k) {
-            const int t = (t0 + k) < L ? (t0 + k) : (L - 1);
-            const uint8_t* src = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES +
-                                 (sl & 7) * A_SLAB + row * 16;
-            hi[k] = __ldcg(reinterpret_cast<const uint4*>(src));
-            if constexpr (P == 2) lo[k] = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
-            else lo[k] = make_uint4(0, 0, 0, 0);
-          }
+        for (int t0 = 0; t0 < 32; t0 += TB) {  // seq_len <= 32 (ccsm_create)
+          if (t0 < L) {
+            uint4 hi[TB], lo[TB];
 #pragma unroll
-          for (int k = 0; k < TB; ++k) {
-            float v[8];
-            join8<P, F16>(hi[k], lo[k], v);
-            const float w = (t0 + k) < L ? my_e[t0 + k] : 0.f;
+            for (int k = 0; k < TB; ++k) {
+              const int t = (t0 + k) < L ? (t0 + k) : (L - 1);
+              const uint8_t* src = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES +
+                                   (sl & 7) * A_SLAB + row * 16;
+              hi[k] = __ldcg(reinterpret_cast<const uint4*>(src));
+              if constexpr (P == 2) lo[k] = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
+              else lo[k] = make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+            for (int k = 0; k < TB; ++k) {
+              float v[8];
+              join8<P, F16>(hi[k], lo[k], v);
+              const float w = (t0 + k) < 32 ? wt[(t0 + k) & 31] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+            }
           }
         }
         const float* f0 = fc_s + strand * 512 + sl * 8;
@@ -1005,8 +1031,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
           lg1 = fmaf(acc[i], f0[1024 + i], lg1);
         }
       }
-      lg0 *= inv;
-      lg1 *= inv;
       lg0 += __shfl_xor_sync(0xffffffffu, lg0, 1);  // strand 1 + strand 2 of the same site (adjacent rows)
       lg1 += __shfl_xor_sync(0xffffffffu, lg1, 1);
       const int64_t site = ((int64_t)tile * TILE_ROWS + row) >> 1;
