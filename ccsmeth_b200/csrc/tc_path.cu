@@ -241,27 +241,36 @@ struct GruParams {
 //   NSLOT = 1: two CTAs per SM, 192 threads each, 4 stages of 20 KB, TMEM 256 columns per CTA: the two
 //              co-resident CTAs overlap one's gate epilogue with the other's MMAs.
 //   NBUF  = accumulator buffers per slot in TMEM (2: the MMAs of unit-chunk j+1 overlap the epilogue of j).
-//   (NSLOT, NBUF) = (1, 2): one CTA per SM, 192 threads, 10 stages of 20 KB, TMEM 2 x 256 columns; half the
-//              row tiles in flight of the other variants, so the activation re-reads stay in L2.
-template <int P, int NSLOT, int NBUF>
+//   KSB   = K-slabs (of 8 elements) per stage and part in the single-pass modes (x3 modes: KSB / 2, same bytes).
+//           Bigger stages = more MMAs per full-barrier wait + commit of the single issuing thread (measured:
+//           the issue loop, not the tensor pipe, bounds the kernel at 2 MMAs per stage).
+//   (NSLOT, NBUF) = (1, 2): one CTA per SM, 192 threads, TMEM 2 x 256 columns; half the row tiles in flight of the
+//           other variants, so the activation re-reads stay in L2.
+//   EPIW  = epilogue warps per TMEM lane quadrant (2: two warps share a row, each takes two of the four 16-unit
+//           blocks of a unit-chunk -- halves the epilogue latency when one CTA owns the SM).
+template <int P, int NSLOT, int NBUF, int KSB, int EPIW = 1>
 struct GruCfg {
-  static constexpr int KS = (NSLOT == 2) ? 8 / P : 4 / P;  // slabs per stage per part
-  static constexpr int STAGES = NSLOT == 2 ? 3 : (NBUF == 2 ? 10 : 5);
-  static constexpr int THREADS = NSLOT == 2 ? 384 : 192;
+  static_assert(P == 1 || 8 % (KSB / P) == 0, "a stage must not straddle two 64-K chunks of a hi/lo image");
+  static_assert(EPIW == 1 || NSLOT == 1, "EPIW = 2 only with one row tile per CTA");
+  static constexpr int KS = KSB / P;  // slabs per stage per part
+  static constexpr int THREADS = NSLOT == 2 ? 384 : 64 + 128 * EPIW;
   static constexpr int CTAS_PER_SM = (NSLOT == 1 && NBUF == 1) ? 2 : 1;
   static constexpr int EPI_WARP0 = NSLOT == 2 ? 4 : 2;
   static constexpr uint32_t TMEM_COLS = NSLOT * NBUF * 256;
   static constexpr uint32_t B_PART = KS * G_SLAB;
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + NSLOT * A_PART);
+  static constexpr uint32_t BUDGET = CTAS_PER_SM == 2 ? 102400 : 208896;  // ring bytes per CTA
+  static constexpr int STAGES = (int)(BUDGET / STAGE);
+  static_assert(STAGES >= 2, "ring too shallow");
   static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
 };
 
-template <int P, bool F16, int NSLOT, int NBUF>
-__global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSLOT, NBUF>::CTAS_PER_SM)
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW>
+__global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, GruCfg<P, NSLOT, NBUF, KSB, EPIW>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
   static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
-  using C = GruCfg<P, NSLOT, NBUF>;
+  using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW>;
   constexpr int GRU_STAGES = C::STAGES;
   constexpr int GRU_THREADS = C::THREADS;
   constexpr int KS = C::KS;
@@ -283,9 +292,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
     }
     for (int i = 0; i < NBUF; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, NSLOT * 128);
+      mbar_init(tmem_empty + 8 * i, NSLOT * EPIW * 128);
     }
-    mbar_init(h_ready, NSLOT * 128);
+    mbar_init(h_ready, NSLOT * EPIW * 128);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * 4 * 256; i += GRU_THREADS) bias_s[i] = p.bias[i];
@@ -428,7 +437,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
   } else if (warp >= C::EPI_WARP0) {
     // ===================== gate epilogue =====================
     // tcgen05.ld lane rule: a warp may only touch TMEM lanes [32 * (warp % 4), +32)
-    const int slot = (warp - C::EPI_WARP0) >> 2, quad = warp & 3;
+    const int slot = EPIW == 2 ? 0 : (warp - C::EPI_WARP0) >> 2, quad = warp & 3;
+    const int ub0 = EPIW == 2 ? 2 * ((warp - C::EPI_WARP0) >> 2) : 0;  // first 16-unit block of this warp
+    constexpr int NUB = 4 / EPIW;                                       // blocks per warp
     const int row = quad * 32 + lane;
     const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
     uint32_t chunk = 0;
@@ -436,7 +447,8 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
     const float* bz = bias_s + (blockIdx.x & 1) * 4 * 256;
     for (int b = 0; b < NBUF; ++b) {  // arm the first NBUF unit-chunks (j = b)
 #pragma unroll
-      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + (NBUF == 2 ? b * 256 : 0), ub, bz, b * 64 + ub * 16);
+      for (int k = 0; k < NUB; ++k)
+        arm_bias16(trow0 + (NBUF == 2 ? b * 256 : 0), ub0 + k, bz, b * 64 + (ub0 + k) * 16);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(tmem_empty + 8 * b);
@@ -453,12 +465,12 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
                        : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
           uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
           // prefetch h_{t_prev} for this row's 64 units (L2 latency overlaps the MMAs of this chunk)
-          uint4 hph[8], hpl[8];
+          uint4 hph[2 * NUB], hpl[2 * NUB];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + q * A_SLAB + row * 16));
+          for (int q = 0; q < 2 * NUB; ++q) {
+            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (2 * ub0 + q) * A_SLAB + row * 16));
             if constexpr (P == 2)
-              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + q * A_SLAB + row * 16));
+              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + (2 * ub0 + q) * A_SLAB + row * 16));
             else
               hpl[q] = make_uint4(0, 0, 0, 0);
           }
@@ -467,7 +479,8 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
           mbar_wait(tmem_full + 8 * buf, bphase);
           tc_fence_after();
 #pragma unroll
-          for (int ub = 0; ub < 4; ++ub) {
+          for (int k = 0; k < NUB; ++k) {
+            const int ub = ub0 + k;
             uint32_t ani[16], ar[16], az[16], anh[16];
             tmem_ld16(trow + 0 + ub * 16, ani);
             tmem_ld16(trow + 64 + ub * 16, ar);
@@ -479,7 +492,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF>::THREADS, GruCfg<P, NSL
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float hp[8], hn[8];
-              join8<P, F16>(hph[ub * 2 + q], hpl[ub * 2 + q], hp);
+              join8<P, F16>(hph[k * 2 + q], hpl[k * 2 + q], hp);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int c = q * 8 + i;
@@ -1256,21 +1269,54 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
 }
 
 // GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2),
+// 5 = variant 0 with 40 KB stages, 6 = variant 2 with two epilogue warps per quadrant,
 // 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered), 4 = CTA pair, two clusters per TPC (NBUF 1).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
-// Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0; layers >= 1 -> 0 for the
-// single-pass modes and 2 for the x3 modes (hi+lo images double the L2 working set; fewer tiles in flight keeps the
-// 4x-per-step activation re-reads out of HBM).  The CTA-pair kernel (3) is correct but slower in round 1.
+// Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0 (two CTAs per SM);
+// layers >= 1 -> 2 (one CTA per SM, TMEM double-buffered, 40 KB stages = 4-6 MMAs per barrier round trip of the
+// issuing thread, half the row tiles in flight so the activation re-reads stay in L2).
+// The CTA-pair kernels (3, 4) are correct but slower in round 1.
 static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    v[0] = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : -1;
-    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '4') ? e[1] - '0' : v[0];
+    v[0] = (e && e[0] >= '0' && e[0] <= '6') ? e[0] - '0' : -1;
+    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '6') ? e[1] - '0' : v[0];
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
-  return (layer > 0 && P == 2) ? 2 : 0;
+  return layer > 0 ? 2 : 0;
+}
+
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1>
+static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
+  using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW>;
+  static bool attr = false;
+  if (!attr) {
+    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr = true;
+  }
+  const int64_t items = (tiles / NSLOT) * 2;  // groups of NSLOT row tiles x 2 directions
+  const int64_t slots = (int64_t)sm_count * C::CTAS_PER_SM;
+  const int grid = (int)(items < slots ? items : slots) & ~1;  // even: fixed direction per CTA
+  tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW><<<grid, C::THREADS, C::SMEM, st>>>(gp);
+  return CCSM_OK;
+}
+
+// variant -> (NSLOT, NBUF, KSB); 3 and 4 are the CTA-pair kernels
+template <int P, bool F16>
+static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
+  switch (variant) {
+    case 0: return launch_gru<P, F16, 1, 1, 4>(gp, tiles, sm_count, st);
+    case 1: return launch_gru<P, F16, 2, 1, 8>(gp, tiles, sm_count, st);
+    case 2: return launch_gru<P, F16, 1, 2, 8>(gp, tiles, sm_count, st);
+    case 5: return launch_gru<P, F16, 1, 1, 8>(gp, tiles, sm_count, st);
+    case 6: return launch_gru<P, F16, 1, 2, 8, 2>(gp, tiles, sm_count, st);  // 2 + 8 epilogue warps
+    default:
+      set_error("unknown GRU kernel variant %d", variant);
+      return CCSM_EINVAL;
+  }
 }
 
 template <int P, bool F16>
@@ -1294,12 +1340,6 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
   count_launch();
   static bool attr_set[2][2] = {{false, false}, {false, false}};
   if (!attr_set[P - 1][F16]) {
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)GruCfg<P, 1, 1>::SMEM));
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)GruCfg<P, 2, 1>::SMEM));
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)GruCfg<P, 1, 2>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)PairCfg<P, 2>::SMEM));
     CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1337,19 +1377,8 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
         tc_gru_pair_kernel<P, F16, 2><<<2 * clusters, PAIR_THREADS, PairCfg<P, 2>::SMEM, st>>>(gp);
       else
         tc_gru_pair_kernel<P, F16, 1><<<2 * clusters, PAIR_THREADS, PairCfg<P, 1>::SMEM, st>>>(gp);
-    } else if (variant == 1) {
-      const int64_t items = tiles;  // (tiles / 2) x 2 directions
-      const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;  // even: fixed direction per CTA
-      tc_gru_layer_kernel<P, F16, 2, 1><<<grid, GruCfg<P, 2, 1>::THREADS, GruCfg<P, 2, 1>::SMEM, st>>>(gp);
-    } else if (variant == 2) {
-      const int64_t items = tiles * 2;
-      const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;
-      tc_gru_layer_kernel<P, F16, 1, 2><<<grid, GruCfg<P, 1, 2>::THREADS, GruCfg<P, 1, 2>::SMEM, st>>>(gp);
     } else {
-      const int64_t items = tiles * 2;
-      const int64_t slots = (int64_t)T.sm_count * 2;
-      const int grid = (int)(items < slots ? items : slots) & ~1;
-      tc_gru_layer_kernel<P, F16, 1, 1><<<grid, GruCfg<P, 1, 1>::THREADS, GruCfg<P, 1, 1>::SMEM, st>>>(gp);
+      CCSM_TRY((launch_gru_variant<P, F16>(variant, gp, tiles, T.sm_count, st)));
     }
     m->prof.end(pid, st);
     count_launch();
