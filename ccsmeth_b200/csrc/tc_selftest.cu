@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
 template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     umma_pair_selftest_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img,
-                              float* __restrict__ D, float* __restrict__ Z, int N, int K) {
+                              float* __restrict__ D, float* __restrict__ Z, int N, int K, int direct_signal) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[3];  // full (local), peer_full (used in CTA 0), done
   __shared__ uint32_t tmem_base_s;
@@ -105,14 +105,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
   const uint32_t tmem = tmem_base_s;
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(bar_full, a_bytes + b_bytes);
-      bulk_g2s(smem_u32(sA), a_img + (size_t)rank * a_bytes, a_bytes, bar_full);
-      bulk_g2s(smem_u32(sB), b_img + (size_t)rank * b_bytes, b_bytes, bar_full);
-      mbar_wait(bar_full, 0);
-      if (rank == 1) {
-        mbar_arrive_remote(mapa_u32(bar_peer, 0));  // tell the leader our half of the operands has landed
+      if (direct_signal) {
+        // experiment: the peer's bulk copies complete_tx directly on the LEADER's mbarrier (no relay hop)
+        if (rank == 0) mbar_expect_tx(bar_full, 2 * (a_bytes + b_bytes));
+        const uint32_t bar = rank == 0 ? bar_full : mapa_u32(bar_full, 0);
+        bulk_g2s(smem_u32(sA), a_img + (size_t)rank * a_bytes, a_bytes, bar);
+        bulk_g2s(smem_u32(sB), b_img + (size_t)rank * b_bytes, b_bytes, bar);
+        if (rank == 0) mbar_wait(bar_full, 0);
       } else {
-        mbar_wait(bar_peer, 0);
+        mbar_expect_tx(bar_full, a_bytes + b_bytes);
+        bulk_g2s(smem_u32(sA), a_img + (size_t)rank * a_bytes, a_bytes, bar_full);
+        bulk_g2s(smem_u32(sB), b_img + (size_t)rank * b_bytes, b_bytes, bar_full);
+        mbar_wait(bar_full, 0);
+      }
+      if (rank == 1) {
+        if (!direct_signal) mbar_arrive_remote(mapa_u32(bar_peer, 0));  // tell the leader our half has landed
+      } else {
+        if (!direct_signal) mbar_wait(bar_peer, 0);
         tc_fence_after();
         const uint32_t idesc = make_idesc(256, N, F16);
         const uint32_t a_lbo = 2048, b_lbo = (uint32_t)NH * 16u, sbo = 128;
@@ -181,6 +190,9 @@ using namespace ccsm;
 
 extern "C" int ccsm_debug_umma_pair_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, const float* A,
                                          const float* B, float* D, float* Z) {
+  // is_f16 bit 1 selects the "peer signals the leader's mbarrier directly" experiment
+  const int direct_signal = (is_f16 >> 1) & 1;
+  is_f16 &= 1;
   if (N < 32 || N > 256 || N % 32 || K < 16 || K % 16 || !A || !B || !D || !Z) {
     set_error("ccsm_debug_umma_pair_gemm: bad shape N=%d K=%d", N, K);
     return CCSM_EINVAL;
@@ -208,10 +220,10 @@ extern "C" int ccsm_debug_umma_pair_gemm(int32_t device, int32_t N, int32_t K, i
   CCSM_CUDA(cudaMemcpy(db.p, bi.data(), bi.size() * 2, cudaMemcpyHostToDevice));
   if (is_f16) {
     CCSM_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_pair_selftest_kernel<true><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K);
+    umma_pair_selftest_kernel<true><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K, direct_signal);
   } else {
     CCSM_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_pair_selftest_kernel<false><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K);
+    umma_pair_selftest_kernel<false><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K, direct_signal);
   }
   count_launch();
   cudaError_t e = cudaDeviceSynchronize();
