@@ -18,6 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
+LINK_LIBS = ["-lz", "-lpthread"]
 
 # error codes / enums (mirror include/ccsm.h)
 OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED, EKEY = 0, -1, -2, -3, -4, -5, -6
@@ -29,7 +30,9 @@ EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_
            "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",
            "ccsm_forward_att2s_host", "ccsm_forward_aggr", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
-           "ccsm_debug_umma_pair_gemm"]
+           "ccsm_debug_umma_pair_gemm", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
+           "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound",
+           "ccsm_bgzf_deflate"]
 
 
 class CcsmError(RuntimeError):
@@ -49,6 +52,11 @@ class Strand(ctypes.Structure):
                 ("kmer", "kpass", "ipd_means", "ipd_stds", "pw_means", "pw_stds", "sns", "maps")]
 
 
+class ExtractOpts(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("mod_loc", "norm", "decode", "n_motifs", "motif_len")] + \
+               [("motifs", ctypes.c_char * 64)]
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -63,18 +71,39 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu into ccsmeth_b200/libccsm.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu into ccsmeth_b200/libccsm.so for sm_100a (cross-compiles without a GPU).
+    One nvcc -c per source file (in parallel, objects cached under csrc/build/), then one link."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(INCLUDE, "*.h"))
+    hdr_t = max(os.path.getmtime(p) for p in hdrs)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        done = list(ex.map(compile_one, sources()))
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", tmp] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [o for o, _ in done] + LINK_LIBS
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
+        raise RuntimeError("nvcc link failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
     os.replace(tmp, LIB_PATH)
     if verbose:
-        print(res.stderr)
+        print("".join(e for _, e in done))
     return LIB_PATH
 
 
@@ -121,6 +150,18 @@ def load():
         lib.ccsm_profile_read.restype = ctypes.c_int
         lib.ccsm_debug_umma_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
         lib.ccsm_debug_umma_gemm.restype = ctypes.c_int
+        lib.ccsm_reads_extract_host.argtypes = [vp, ctypes.POINTER(ExtractOpts), vp, i64, vp, i32, ctypes.POINTER(i64)]
+        lib.ccsm_reads_sites.argtypes = [vp, vp, vp]
+        lib.ccsm_reads_features.argtypes = [vp, i64, i64, ctypes.POINTER(Strand), ctypes.POINTER(Strand), vp]
+        lib.ccsm_reads_forward_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.ccsm_bgzf_inflated_size.argtypes = [vp, i64, ctypes.POINTER(i64)]
+        lib.ccsm_bgzf_inflate.argtypes = [vp, i64, vp, i64, i32, ctypes.POINTER(i64)]
+        lib.ccsm_bgzf_deflate_bound.argtypes = [i64]
+        lib.ccsm_bgzf_deflate.argtypes = [vp, i64, vp, i64, i32, i32]
+        for fn in ("ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound", "ccsm_bgzf_deflate"):
+            getattr(lib, fn).restype = i64
+        for fn in ("ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features", "ccsm_reads_forward_host"):
+            getattr(lib, fn).restype = ctypes.c_int
         for fn in ("ccsm_create", "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",
                    "ccsm_forward_att2s_host", "ccsm_forward_aggr"):
             getattr(lib, fn).restype = ctypes.c_int

@@ -24,17 +24,26 @@ _ARR_DTYPE = {ord('c'): np.int8, ord('C'): np.uint8, ord('s'): np.int16, ord('S'
 
 
 class BgzfReader:
-    """Sequential reader over concatenated BGZF blocks."""
+    """Sequential reader over concatenated BGZF blocks.  ``threads > 1``: the file is read in large pieces and all
+    complete blocks of a piece are inflated at once by libccsm's thread team (include/ccsm.h ccsm_bgzf_inflate;
+    Python's own zlib holds the GIL in this interpreter, so Python threads do not scale)."""
 
-    def __init__(self, path):
+    PIECE = 16 << 20
+
+    def __init__(self, path, threads=1):
         self.f = open(path, "rb")
         self.buf = b""
         self.pos = 0
+        self.threads = threads
+        self.tail = b""
+        if threads > 1:
+            from . import _lib
+            self.lib = _lib.load()
 
-    def _fill(self):
+    def _fill_python(self):
         hdr = self.f.read(18)
         if len(hdr) < 18:
-            return False
+            return None
         if hdr[:4] != b"\x1f\x8b\x08\x04":
             raise ValueError("not a BGZF block")
         xlen = struct.unpack_from("<H", hdr, 10)[0]
@@ -50,7 +59,35 @@ class BgzfReader:
             raise ValueError("BGZF block without BC subfield")
         cdata = self.f.read(bsize - xlen - 19)
         self.f.read(8)  # crc32 + isize
-        data = zlib.decompress(cdata, -15) if cdata else b""
+        return zlib.decompress(cdata, -15) if cdata else b""
+
+    def _fill_native(self):
+        import ctypes
+        from . import _lib
+        piece = self.f.read(self.PIECE)
+        if not piece and not self.tail:
+            return None
+        src = self.tail + piece
+        consumed = ctypes.c_int64(0)
+        total = self.lib.ccsm_bgzf_inflated_size(src, len(src), ctypes.byref(consumed))
+        if total < 0:
+            _lib.check(int(total))
+        if consumed.value == 0:
+            if not piece:
+                raise ValueError("truncated BGZF block at end of file")
+            self.tail = src
+            return b""
+        dst = ctypes.create_string_buffer(int(total)) if total else None
+        got = self.lib.ccsm_bgzf_inflate(src, len(src), dst, int(total), self.threads, ctypes.byref(consumed))
+        if got < 0:
+            _lib.check(int(got))
+        self.tail = src[consumed.value:]
+        return dst.raw if total else b""
+
+    def _fill(self):
+        data = self._fill_native() if self.threads > 1 else self._fill_python()
+        if data is None:
+            return False
         self.buf = self.buf[self.pos:] + data
         self.pos = 0
         return True
@@ -67,29 +104,55 @@ class BgzfReader:
         self.f.close()
 
 
+def _deflate_block(data, level):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    cdata = c.compress(data) + c.flush()
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cdata) + 25) + cdata +
+            struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+
 class BgzfWriter:
-    def __init__(self, path, level=6):
+    """BGZF writer; ``threads > 1``: blocks are deflated by libccsm's thread team (ccsm_bgzf_deflate)."""
+
+    BLOCK = 65280
+
+    def __init__(self, path, level=6, threads=1):
         self.f = open(path, "wb")
         self.level = level
         self.buf = bytearray()
+        self.threads = threads
+        self.batch = 1
+        if threads > 1:
+            from . import _lib
+            self.lib = _lib.load()
+            self.batch = 16 * threads
 
     def write(self, data):
         self.buf += data
-        while len(self.buf) >= 65280:
-            self._flush_block(bytes(self.buf[:65280]))
-            del self.buf[:65280]
+        if len(self.buf) >= self.batch * self.BLOCK:
+            self._flush(final=False)
 
-    def _flush_block(self, data):
-        c = zlib.compressobj(self.level, zlib.DEFLATED, -15)
-        cdata = c.compress(data) + c.flush()
-        bsize = len(cdata) + 25
-        self.f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + cdata +
-                     struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+    def _flush(self, final):
+        n_full = len(self.buf) // self.BLOCK
+        end = len(self.buf) if final else n_full * self.BLOCK
+        view = bytes(self.buf[:end])
+        del self.buf[:end]
+        if self.threads > 1:
+            import ctypes
+            from . import _lib
+            cap = int(self.lib.ccsm_bgzf_deflate_bound(len(view)))
+            dst = ctypes.create_string_buffer(cap)
+            got = self.lib.ccsm_bgzf_deflate(view, len(view), dst, cap, self.level, self.threads)
+            if got < 0:
+                _lib.check(int(got))
+            self.f.write(memoryview(dst)[:int(got)])
+        else:
+            for i in range(0, len(view), self.BLOCK):
+                self.f.write(_deflate_block(view[i:i + self.BLOCK], self.level))
 
     def close(self):
         if self.buf:
-            self._flush_block(bytes(self.buf))
-            self.buf = bytearray()
+            self._flush(final=True)
         self.f.write(_BGZF_EOF)
         self.f.close()
 
@@ -246,13 +309,13 @@ class BamRecord:
             out += self.raw[s:e]
         if mm is not None:
             out += b"MMZ" + mm.encode("ascii") + b"\x00"
-            out += b"MLBC" + struct.pack("<I", len(ml)) + bytes(bytearray(ml))
+            out += b"MLBC" + struct.pack("<I", len(ml)) + (ml if isinstance(ml, bytes) else bytes(bytearray(ml)))
         return bytes(out)
 
 
 class BamReader:
-    def __init__(self, path):
-        self.bg = BgzfReader(path)
+    def __init__(self, path, threads=1):
+        self.bg = BgzfReader(path, threads)
         if self.bg.read(4) != b"BAM\x01":
             raise ValueError("%s is not a BAM file" % path)
         l_text = struct.unpack("<i", self.bg.read(4))[0]
@@ -281,8 +344,8 @@ class BamReader:
 
 
 class BamWriter:
-    def __init__(self, path, header_text, references, level=6):
-        self.bg = BgzfWriter(path, level)
+    def __init__(self, path, header_text, references, level=6, threads=1):
+        self.bg = BgzfWriter(path, level, threads)
         text = header_text.encode("utf-8")
         self.bg.write(b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(references)))
         for name, l_ref in references:

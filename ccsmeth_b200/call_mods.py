@@ -8,8 +8,10 @@ ccsmeth/call_modifications.py:616-752) and its output rules (SURVEY.md appendix 
   * reads without predictions are still written (call_modifications.py:239-242)
   * header gets an ``@PG ID:ccsmeth`` line (:445)
 The reference wires reader / extractors / model workers / writer with multiprocessing queues
-(call_modifications.py:520-590); here each rank runs a reader+extractor thread feeding the GPU call, takes the
-hole-batches with ``batch_idx % world == rank`` and writes its own BAM shard.  Sorting/indexing
+(call_modifications.py:520-590); here each rank runs a reader thread (BGZF inflate on a native thread team), the
+GPU calls (feature extraction + forward + MM/ML values on the device, csrc/extract.cu) and a writer thread
+(tagging + BGZF deflate on the thread team), takes the hole-batches with ``batch_idx % world == rank`` and writes
+its own BAM shard.  Sorting/indexing
 (call_modifications.py:592-607) needs samtools and is left to the caller: the output is always unsorted.
 
     python -m ccsmeth_b200.call_mods -i in.hifi.bam -m model.ckpt -o out_prefix [--mode denovo] ...
@@ -27,7 +29,7 @@ import torch
 from . import VERSION, parallel
 from .bamio import BamReader, BamWriter, add_pg_line
 from .call_modifications import draw_h0_stream, load_model
-from .extract_features import batch_read_features, extract_read
+from .extract_features import extract_opts, pack_reads
 from .utils.process_utils import str2bool
 
 IUPAC = {'A': 'A', 'C': 'C', 'G': 'G', 'T': 'T', 'R': 'AG', 'M': 'AC', 'S': 'CG', 'Y': 'CT', 'K': 'GT', 'W': 'AT',
@@ -64,41 +66,57 @@ def convert_probs_to_mltag(probs):
     return np.where(p < 1, np.floor(p * np.float32(256)), 255).astype(np.uint8)
 
 
-def call_holebatch(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=None):
-    """One hole-batch (list of BamRecord) -> (per-read list of (locs, prob_1_norm) or None, n_sites, n_model_batches).
-    Equivalent of process_one_holebatch + _batch_feature_list2s + _call_mods2s (reference
-    extract_features.py:409-431, call_modifications.py:73-123,170-227)."""
-    feats = []
-    for i, r in enumerate(reads):
-        try:
-            rf = extract_read(r, motifs, args, holeids_e, holeids_ne)
-        except Exception:  # the reference counts such reads as failed and goes on (extract_features.py:416-429)
-            rf = None
-        if rf is not None and len(rf):
-            feats.append((i, rf))
-    arrays, holeidx, locs = batch_read_features(feats, args.seq_len)
+def call_reads(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=None, holes_batch=None):
+    """A run of consecutive hole-batches (list of BamRecord) -> (per-read list of (locs, prob_1_norm, mm, ml) or None,
+    n_sites, n_model_batches).  Equivalent of process_one_holebatch + _batch_feature_list2s + _call_mods2s + the
+    MM/ML conversion (reference extract_features.py:409-431, call_modifications.py:73-123,170-227,
+    _bam2modbam.py:187-208) with the per-read work done on the device (csrc/extract.cu).
+
+    ``holes_batch``: reads per hole-batch inside `reads` (default: all of `reads` is one hole-batch).  It only
+    matters for the reference's h0 stream and batch counter, which restart their 512-slicing at every hole-batch."""
     per_read = [None] * len(reads)
-    if arrays is None:
+    batch = pack_reads(reads, args, holeids_e, holeids_ne)
+    if len(batch) == 0:
         return per_read, 0, 0
-    n = len(locs)
+    n = model.extract_reads(batch, extract_opts(args, motifs))
+    if n == 0:
+        return per_read, 0, 0
+    site_read, site_loc = model.reads_sites()
+    hb = holes_batch or len(reads)
+    rec_idx = np.asarray(batch.index, dtype=np.int64)[site_read]       # site -> position in `reads`
+    per_hb = np.bincount(rec_idx // hb, minlength=(len(reads) + hb - 1) // hb)
+    n_batches = int(sum((c + args.batch_size - 1) // args.batch_size for c in per_hb))
     if h0 is None and getattr(args, "h0", "reference") == "reference":
-        h0 = draw_h0_stream(n, args.batch_size, model.num_layers, model.hidden_size)
-    _, probs = model.forward_host(arrays, h0=h0)
-    p = probs.numpy()
-    prob1 = np.round(p[:, 1] / (p[:, 0] + p[:, 1]), 6)  # reference call_modifications.py:223 (float32)
-    bounds = np.nonzero(np.diff(holeidx))[0] + 1
+        parts = [draw_h0_stream(int(c), args.batch_size, model.num_layers, model.hidden_size) for c in per_hb if c]
+        h0 = (torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1)) if len(parts) > 1 \
+            else parts[0]
+    res = model.reads_forward(h0=h0, want_probs=False)
+    bounds = np.nonzero(np.diff(site_read))[0] + 1
     starts = np.concatenate(([0], bounds))
     ends = np.concatenate((bounds, [n]))
     for s, e in zip(starts, ends):
-        per_read[int(holeidx[s])] = (locs[s:e], prob1[s:e])
-    return per_read, n, (n + args.batch_size - 1) // args.batch_size
+        per_read[batch.index[int(site_read[s])]] = (site_loc[s:e], res["prob1"][s:e], res["mm"][s:e], res["ml"][s:e])
+    return per_read, n, n_batches
 
 
-def tag_read(rec, pred, rm_pulse):
-    """BamRecord + (locs, probs) -> (record bytes with MM/ML, mm_flag)  (reference call_modifications.py:230-266)."""
+def call_holebatch(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=None):
+    """One hole-batch; returns (per-read list of (locs, prob_1_norm) or None, n_sites, n_model_batches)."""
+    per_read, n, nb = call_reads(model, reads, motifs, args, holeids_e, holeids_ne, h0)
+    return [None if p is None else (p[0], p[1]) for p in per_read], n, nb
+
+
+def tag_read(rec, pred, rm_pulse, mod_base_is_c=True):
+    """BamRecord + (locs, probs[, mm, ml]) -> (record bytes with MM/ML, mm_flag)
+    (reference call_modifications.py:230-266).  With the device outputs (mm, ml) present nothing is recomputed;
+    the 2-tuple form converts on the host like the reference does."""
     drop = {"MM", "ML"} | ({"fi", "fp", "ri", "rp"} if rm_pulse else set())
     if pred is None or len(pred[0]) == 0:
         return rec.with_tags(drop), 0
+    if len(pred) == 4:
+        if not mod_base_is_c:  # the reference counts C's only (_bam2modbam.py:187-199): assertion -> no tags
+            return rec.with_tags(drop), 0
+        mm, ml = pred[2], pred[3]
+        return rec.with_tags(drop, "C+m?," + ",".join(map(str, mm.tolist())) + ";", ml.tobytes()), 1
     locs, probs = pred
     order = np.argsort(locs, kind="stable")
     locs, probs = locs[order], probs[order]
@@ -111,23 +129,50 @@ def tag_read(rec, pred, rm_pulse):
     return rec.with_tags(drop, "C+m?," + ",".join(map(str, mm.tolist())) + ";", ml.tolist()), 1
 
 
-def _reader_thread(path, args, rank, world, q):
+def _reader_thread(path, args, rank, world, q, group):
+    """Reads the BAM, keeps the hole-batches this rank owns (batch_idx % world == rank) and hands them over in
+    groups of `group` hole-batches (one device call each)."""
     try:
-        rd = BamReader(path)
+        rd = BamReader(path, threads=max(1, args.threads))
         q.put(("header", rd.header_text, rd.references))
-        batch, bidx = [], 0
+        batch, bidx, run = [], 0, []
         for rec in rd:
             batch.append(rec)
             if len(batch) == args.holes_batch:
                 if parallel.owns_holebatch(bidx, rank, world):
-                    q.put(("batch", bidx, batch))
+                    run.append(batch)
+                    if len(run) == group:
+                        q.put(("reads", [r for b in run for r in b]))
+                        run = []
                 batch, bidx = [], bidx + 1
         if batch and parallel.owns_holebatch(bidx, rank, world):
-            q.put(("batch", bidx, batch))
+            run.append(batch)
+        if run:
+            q.put(("reads", [r for b in run for r in b]))
         rd.close()
         q.put(("done",))
     except Exception as e:  # surface reader failures to the main thread
         q.put(("error", e))
+
+
+def _writer_thread(wr, q, rm_pulse, mod_base_is_c, counts, err):
+    """Tags and writes the reads of finished device calls (reference _worker_write_modbam,
+    call_modifications.py:410-462)."""
+    try:
+        while True:
+            msg = q.get()
+            if msg is None:
+                return
+            reads, per_read = msg
+            for rec, pred in zip(reads, per_read):
+                raw, mm_flag = tag_read(rec, pred, rm_pulse, mod_base_is_c)
+                wr.write_raw(raw)
+                counts[2] += 1
+                counts[3] += mm_flag
+    except Exception as e:
+        err.append(e)
+        while q.get() is not None:  # keep draining so the producer never blocks
+            pass
 
 
 def call_mods(args):
@@ -154,34 +199,45 @@ def call_mods(args):
     torch.manual_seed(args.tseed + rank)
     model.set_h0_mode(getattr(args, "h0", "reference"), seed=args.tseed + rank)
     motifs = get_motif_seqs(args.motifs)
+    mod_base_is_c = all(m[args.mod_loc] == "C" for m in motifs)
     holeids_e = _get_holes(args.holeids_e) if args.holeids_e else None
     holeids_ne = _get_holes(args.holeids_ne) if args.holeids_ne else None
 
-    q = queue.Queue(maxsize=8)
-    th = threading.Thread(target=_reader_thread, args=(args.input, args, rank, world, q), daemon=True)
+    group = max(1, getattr(args, "device_batch", 16))
+    q = queue.Queue(maxsize=3)
+    th = threading.Thread(target=_reader_thread, args=(args.input, args, rank, world, q, group), daemon=True)
     th.start()
     msg = q.get()
     if msg[0] == "error":
         raise msg[1]
     _, header_text, references = msg
-    wr = BamWriter(out_modbam, add_pg_line(header_text, VERSION, " ".join(sys.argv)), references)
+    wr = BamWriter(out_modbam, add_pg_line(header_text, VERSION, " ".join(sys.argv)), references,
+                   threads=max(1, args.threads))
     counts = [0, 0, 0, 0]
-    rm_pulse = not args.keep_pulse
-    while True:
-        msg = q.get()
-        if msg[0] == "done":
-            break
-        if msg[0] == "error":
-            raise msg[1]
-        _, bidx, reads = msg
-        per_read, n_sites, n_batches = call_holebatch(model, reads, motifs, args, holeids_e, holeids_ne)
-        counts[0] += n_sites
-        counts[1] += n_batches
-        for rec, pred in zip(reads, per_read):
-            raw, mm_flag = tag_read(rec, pred, rm_pulse)
-            wr.write_raw(raw)
-            counts[2] += 1
-            counts[3] += mm_flag
+    wq, werr = queue.Queue(maxsize=3), []
+    wth = threading.Thread(target=_writer_thread, args=(wr, wq, not args.keep_pulse, mod_base_is_c, counts, werr),
+                           daemon=True)
+    wth.start()
+    try:
+        while True:
+            msg = q.get()
+            if msg[0] == "done":
+                break
+            if msg[0] == "error":
+                raise msg[1]
+            reads = msg[1]
+            per_read, n_sites, n_batches = call_reads(model, reads, motifs, args, holeids_e, holeids_ne,
+                                                      holes_batch=args.holes_batch)
+            counts[0] += n_sites
+            counts[1] += n_batches
+            wq.put((reads, per_read))
+            if werr:
+                raise werr[0]
+    finally:
+        wq.put(None)
+        wth.join()
+    if werr:
+        raise werr[0]
     wr.close()
     total = parallel.allreduce_counts(counts)
     if rank == 0:
@@ -242,6 +298,9 @@ def build_parser():
     p.add_argument("--h0", type=str, default="reference", choices=["reference", "device", "zeros"],
                    help="ccsmeth_b200 only: GRU initial state: the reference's torch.randn stream on the CPU "
                         "(default), N(0,1) drawn on the device (no 12 KB/site transfer), or zeros")
+    p.add_argument("--device_batch", type=int, default=16,
+                   help="ccsmeth_b200 only: hole-batches per device call (features are extracted on the GPU for "
+                        "this many x --holes_batch reads at once)")
     p.add_argument("--precision", type=str, default=None, choices=["fp32", "fp16x3", "bf16x3", "fp16", "bf16"],
                    help="ccsmeth_b200 only: arithmetic mode (default fp16x3, <= 1e-4 vs the fp32 reference)")
     return p

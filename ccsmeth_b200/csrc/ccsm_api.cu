@@ -120,6 +120,7 @@ void ccsm_destroy(ccsm_model* m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
   tc_release(m);
+  ex_release(m);
   for (auto& l : m->fp32.layers) {
     l.w_ih.release(); l.b_ih.release(); l.w_hh.release(); l.b_hh.release();
   }

@@ -72,6 +72,7 @@ struct Fp32Workspace {
 };
 
 struct TcState;  // tensor-core (tcgen05) path state, defined in tc_path.cu
+struct ExState;  // device feature extraction state (resident read batch), defined in extract.cu
 
 // Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).
 enum ProfClass { PROF_PREP = 0, PROF_GRU_L0 = 1, PROF_GRU_LN = 2, PROF_ATT = 3, PROF_NCLASS = 4 };
@@ -109,6 +110,7 @@ struct ccsm_model {
   ccsm::Fp32Weights fp32;
   ccsm::Fp32Workspace ws32;
   ccsm::TcState* tc = nullptr;
+  ccsm::ExState* ex = nullptr;
   ccsm::Profiler prof;
   int h0_mode = 0;            // CCSM_H0_*
   uint64_t h0_seed = 0;
@@ -137,5 +139,8 @@ void tc_release(ccsm_model* m);
 int tc_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
                      const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st);
 int tc_debug_layer_out(ccsm_model* m, int layer, float* host, int64_t cap, int64_t* written);
+
+// ---- device feature extraction (extract.cu)
+void ex_release(ccsm_model* m);
 
 }  // namespace ccsm

@@ -1,0 +1,621 @@
+// Device feature extraction for call_mods: reads (raw bytes + descriptors) -> site list -> the reference's
+// 16-tensor feature layout -> forward -> per-site MM/ML values.  HBM-bound byte/integer kernels.
+//
+// Reference behaviour restated here (all under /root/reference/ccsmeth/):
+//   extract_features.py:261-406   extract_features_from_double_strand_read (site selection and windows)
+//   extract_features.py:181-199   _normalize_signals (np.mean / population np.std / np.around(6), float64)
+//   utils/process_utils.py:426-449 CodecV1 code -> frames
+//   utils/process_utils.py:122-137 get_refloc_of_methysite_in_motif
+//   call_modifications.py:73-123  _batch_feature_list2s (base codes, npass broadcast over the window)
+//   call_modifications.py:222-224 prob_1_norm;  _bam2modbam.py:187-208 MM deltas / ML bytes
+//
+// Arithmetic notes.  The kinetics are small integers (<= 952), so sum and sum of squares of a read are exact in
+// int64: mean = S/n and var = (n*Q - S*S)/n^2 are each one IEEE division away from the exact rational, where
+// numpy's pairwise float64 sums may differ from it in the last ulps.  Every later step ((x-mean)/std, *1e6, rint,
+// /1e6, cast to float32) is the same sequence of IEEE double operations numpy performs (no FMA contraction).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "ccsm_internal.h"
+
+namespace ccsm {
+
+struct ExState {
+  DevBuf blob, reads, stats, site_cnt, site_off, site_read, site_loc, site_cord;
+  DevBuf feat, h0, out, tags;   // per-chunk staging: 16-tensor features, h0, logits/probs, prob1/mm/ml
+  ccsm_extract_opts opts{};
+  int32_t n_reads = 0;
+  int64_t n_sites = -1;
+  int64_t blob_bytes = 0;
+  cudaStream_t st = nullptr, st_copy = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+};
+
+struct ExParams {
+  const uint8_t* blob;
+  const ccsm_read* reads;
+  int n_reads;
+  int seq_len, nb, mod_loc, rev_offset, norm, decode, n_motifs, motif_len;
+  uint32_t motif_code[8];  // motif k packed 4 bits per base code (A0 C1 G2 T3)
+};
+
+__device__ __forceinline__ int nib_to_code(int nib) {
+  return nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : 4;
+}
+__device__ __forceinline__ int ascii_to_code(int c) {
+  return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+}
+__host__ __device__ __forceinline__ int code_to_frames(int c) {
+  // CodecV1 (process_utils.py:426-449): 64 codes each at strides 1, 2, 4, 8
+  return c < 64 ? c : c < 128 ? 64 + ((c - 64) << 1) : c < 192 ? 192 + ((c - 128) << 2) : 448 + ((c - 192) << 3);
+}
+
+// base code (0..4) of base i of the FORWARD read
+__device__ __forceinline__ int fwd_code(const uint8_t* blob, const ccsm_read& r, int i) {
+  const int j = (r.flags & CCSM_READ_REVERSE) ? r.len - 1 - i : i;
+  int c;
+  if (r.flags & CCSM_READ_SEQ_4BIT) {
+    const int b = blob[r.seq_off + (j >> 1)];
+    c = nib_to_code((j & 1) ? (b & 15) : (b >> 4));
+  } else {
+    c = ascii_to_code(blob[r.seq_off + j]);
+  }
+  if ((r.flags & CCSM_READ_REVERSE) && c < 4) c = 3 - c;
+  return c;
+}
+
+// is position p the start of a motif whose modified base is a callable site?  (extract_features.py:336-343)
+__device__ __forceinline__ bool site_at(const ExParams& P, const ccsm_read& r, int p) {
+  if (p + P.motif_len > r.len) return false;
+  uint32_t w = 0;
+  for (int k = 0; k < P.motif_len; ++k) {
+    const int c = fwd_code(P.blob, r, p + k);
+    if (c > 3) return false;
+    w |= (uint32_t)c << (4 * k);
+  }
+  bool hit = false;
+  for (int k = 0; k < P.n_motifs; ++k) hit |= (w == P.motif_code[k]);
+  if (!hit) return false;
+  const int loc = p + P.mod_loc;
+  const int rl = r.len - 1 - (loc + P.rev_offset);
+  return loc >= P.nb && loc < r.len - P.nb && rl >= P.nb && rl < r.len - P.nb && loc >= r.win_lo && loc < r.win_hi;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- kernel 1: one CTA per read -- normalisation statistics of the four kinetics arrays + site count
+struct SigStat { double shift, scale; };
+
+__global__ void __launch_bounds__(256) read_scan_kernel(ExParams P, SigStat* __restrict__ stats,
+                                                        int* __restrict__ site_cnt) {
+  const int r_idx = blockIdx.x;
+  const ccsm_read r = P.reads[r_idx];
+  __shared__ long long s_sum[8], s_sq[8];
+  __shared__ int s_min[8], s_max[8], s_cnt[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t offs[4] = {r.fi_off, r.ri_off, r.fp_off, r.rp_off};  // order: ipd fwd, ipd rev, pw fwd, pw rev
+  for (int sig = 0; sig < 4; ++sig) {
+    const uint8_t* a = P.blob + offs[sig];
+    long long S = 0, Q = 0;
+    int mn = 1 << 30, mx = -1;
+    if (P.norm != CCSM_NORM_NONE) {
+      for (int i = threadIdx.x; i < r.len; i += blockDim.x) {
+        const int c = a[i];
+        const int v = P.decode ? code_to_frames(c) : c;
+        S += v;
+        Q += v * v;
+        mn = min(mn, v);
+        mx = max(mx, v);
+      }
+    }
+    S = warp_sum_ll(S);
+    Q = warp_sum_ll(Q);
+    for (int o = 16; o; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_sum[warp] = S; s_sq[warp] = Q; s_min[warp] = mn; s_max[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long St = 0, Qt = 0;
+      int mnt = 1 << 30, mxt = -1;
+      for (int w = 0; w < 8; ++w) { St += s_sum[w]; Qt += s_sq[w]; mnt = min(mnt, s_min[w]); mxt = max(mxt, s_max[w]); }
+      SigStat st;
+      const double n = (double)r.len;
+      if (P.norm == CCSM_NORM_ZSCORE) {
+        st.shift = __ddiv_rn((double)St, n);
+        const long long num = (long long)r.len * Qt - St * St;  // exact: n^2 * variance
+        st.scale = __dsqrt_rn(__ddiv_rn((double)num, __dmul_rn(n, n)));
+      } else if (P.norm == CCSM_NORM_MINMEAN) {
+        st.shift = (double)mnt;
+        st.scale = __ddiv_rn((double)St, n);
+      } else if (P.norm == CCSM_NORM_MINMAX) {
+        st.shift = (double)mnt;
+        st.scale = (double)(mxt - mnt);
+      } else {
+        st.shift = 0.0;
+        st.scale = 1.0;
+      }
+      if (r.len == 0) { st.shift = 0.0; st.scale = 0.0; }
+      stats[(size_t)r_idx * 4 + sig] = st;
+    }
+    __syncthreads();
+  }
+  int cnt = 0;
+  for (int p = threadIdx.x; p < r.len; p += blockDim.x) cnt += site_at(P, r, p) ? 1 : 0;
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += s_cnt[w];
+    site_cnt[r_idx] = t;
+  }
+}
+
+// ---- kernel 2: exclusive scan of the per-read site counts (one CTA; n_reads is small)
+__global__ void __launch_bounds__(1024) site_offsets_kernel(const int* __restrict__ cnt, long long* __restrict__ off,
+                                                            int n) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const long long v = i < n ? cnt[i] : 0;
+    long long x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const long long before = s_carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+    if (i < n) off[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[n] = s_carry;
+}
+
+// ---- kernel 3: one CTA per read -- ordered emission of (read, loc, order of the C among the read's C's)
+__global__ void __launch_bounds__(256) site_emit_kernel(ExParams P, const long long* __restrict__ site_off,
+                                                        int* __restrict__ site_read, int* __restrict__ site_loc,
+                                                        int* __restrict__ site_cord) {
+  const int r_idx = blockIdx.x;
+  const ccsm_read r = P.reads[r_idx];
+  const long long o0 = site_off[r_idx];
+  if (site_off[r_idx + 1] == o0) return;
+  __shared__ int s_ws[8], s_wc[8];
+  __shared__ int s_cs, s_cc;  // running carries: sites, C's
+  if (threadIdx.x == 0) {
+    s_cs = 0;
+    int c0 = 0;  // C's in front of the first position the loop below looks at
+    for (int q = 0; q < P.mod_loc && q < r.len; ++q) c0 += fwd_code(P.blob, r, q) == 1;
+    s_cc = c0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < r.len; base += 256) {
+    const int p = base + threadIdx.x;
+    const bool in = p < r.len;
+    const bool is_site = in && site_at(P, r, p);
+    // MM deltas count C's of the forward read (_bam2modbam.py:187-203); the called base sits at p + mod_loc, so
+    // count C's at position q = p + mod_loc for q's own p (shift the C flag by mod_loc to stay thread-local)
+    const int q = p + P.mod_loc;
+    const bool is_c = in && q < r.len && fwd_code(P.blob, r, q) == 1;
+    const unsigned ms = __ballot_sync(0xffffffffu, is_site), mc = __ballot_sync(0xffffffffu, is_c);
+    const unsigned below = (1u << lane) - 1u;
+    if (lane == 0) { s_ws[warp] = __popc(ms); s_wc[warp] = __popc(mc); }
+    __syncthreads();
+    int ps = s_cs, pc = s_cc;
+    for (int w = 0; w < warp; ++w) { ps += s_ws[w]; pc += s_wc[w]; }
+    ps += __popc(ms & below);
+    pc += __popc(mc & below);
+    if (is_site) {
+      site_read[o0 + ps] = r_idx;
+      site_loc[o0 + ps] = q;
+      site_cord[o0 + ps] = pc;  // C's strictly before q (positions q' = p' + mod_loc with p' < p)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ts = 0, tc = 0;
+      for (int w = 0; w < 8; ++w) { ts += s_ws[w]; tc += s_wc[w]; }
+      s_cs += ts;
+      s_cc += tc;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- kernel 4: the 16-tensor layout of sites [s0, s0+cn)
+struct FeatOut {
+  float *kmer, *kpass, *ipd, *pw, *sns;
+};
+
+__device__ __forceinline__ float norm_value(int v, const SigStat& st, int norm) {
+  if (norm == CCSM_NORM_NONE) return (float)v;
+  if (st.scale == 0.0) return 0.f;
+  const double x = __ddiv_rn(__dsub_rn((double)v, st.shift), st.scale);
+  return (float)__ddiv_rn(rint(__dmul_rn(x, 1e6)), 1e6);  // np.around(x, 6): multiply, rint, divide
+}
+
+__global__ void __launch_bounds__(256) window_gather_kernel(ExParams P, const SigStat* __restrict__ stats,
+                                                            const int* __restrict__ site_read,
+                                                            const int* __restrict__ site_loc, long long s0, long long cn,
+                                                            FeatOut f, FeatOut rv) {
+  const int L = P.seq_len;
+  const long long total = cn * 2 * L;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int strand = (int)(idx / (cn * L));
+    const long long rem = idx - (long long)strand * cn * L;
+    const long long i = rem / L;
+    const int t = (int)(rem - i * L);
+    const int r_idx = site_read[s0 + i];
+    const int loc = site_loc[s0 + i];
+    const ccsm_read r = P.reads[r_idx];
+    const SigStat* st = stats + (size_t)r_idx * 4;
+    const FeatOut& o = strand ? rv : f;
+    int pos, code, ipd_c, pw_c;
+    if (strand == 0) {
+      pos = loc - P.nb + t;
+      code = fwd_code(P.blob, r, pos);
+      ipd_c = P.blob[r.fi_off + pos];
+      pw_c = P.blob[r.fp_off + pos];
+    } else {
+      // window on the reverse complement around len-1-(loc+rev_offset); kinetics of the reverse strand are
+      // indexed in that same coordinate, unflipped (extract_features.py:316,319,355-360)
+      pos = r.len - 1 - (loc + P.rev_offset) - P.nb + t;
+      const int c = fwd_code(P.blob, r, r.len - 1 - pos);
+      code = c < 4 ? 3 - c : 4;
+      ipd_c = P.blob[r.ri_off + pos];
+      pw_c = P.blob[r.rp_off + pos];
+    }
+    const int ipd_v = P.decode ? code_to_frames(ipd_c) : ipd_c;
+    const int pw_v = P.decode ? code_to_frames(pw_c) : pw_c;
+    const long long w = i * L + t;
+    o.kmer[w] = (float)code;
+    if (o.kpass) o.kpass[w] = (float)(strand ? r.rn : r.fn);
+    o.ipd[w] = norm_value(ipd_v, st[strand ? 1 : 0], P.norm);
+    o.pw[w] = norm_value(pw_v, st[strand ? 3 : 2], P.norm);
+    if (o.sns && t < 4) {
+      // np.around(np.array(tag_sn, dtype=float), 6) (extract_features.py:328)
+      o.sns[i * 4 + t] = (float)__ddiv_rn(rint(__dmul_rn((double)r.sn[t], 1e6)), 1e6);
+    }
+  }
+}
+
+// ---- kernel 5: per-site outputs for the modbam writer
+__global__ void __launch_bounds__(256) site_tags_kernel(const float* __restrict__ probs, int classes,
+                                                        const int* __restrict__ site_read,
+                                                        const int* __restrict__ site_cord, long long s0, long long cn,
+                                                        float* __restrict__ prob1, int* __restrict__ mm,
+                                                        uint8_t* __restrict__ ml) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cn) return;
+  const float p0 = probs[i * classes], p1 = probs[i * classes + 1];
+  // round(prob_1 / (prob_0 + prob_1), 6) on float32 scalars (call_modifications.py:222-223)
+  const float p = __fdiv_rn(rintf(__fmul_rn(__fdiv_rn(p1, __fadd_rn(p0, p1)), 1e6f)), 1e6f);
+  prob1[i] = p;
+  ml[i] = p < 1.f ? (uint8_t)floorf(__fmul_rn(p, 256.f)) : (uint8_t)255;  // _bam2modbam.py:206-208
+  const long long g = s0 + i;
+  const bool first = g == 0 || site_read[g - 1] != site_read[g];
+  mm[i] = first ? site_cord[g] : site_cord[g] - site_cord[g - 1] - 1;    // _bam2modbam.py:200-203
+}
+
+// ------------------------------------------------------------------------------------------------------------
+static int ensure_streams(ExState* ex) {
+  if (!ex->st) CCSM_CUDA(cudaStreamCreateWithFlags(&ex->st, cudaStreamNonBlocking));
+  if (!ex->st_copy) CCSM_CUDA(cudaStreamCreateWithFlags(&ex->st_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    if (!ex->ev[i]) CCSM_CUDA(cudaEventCreateWithFlags(&ex->ev[i], cudaEventDisableTiming));
+    if (!ex->done[i]) CCSM_CUDA(cudaEventCreateWithFlags(&ex->done[i], cudaEventDisableTiming));
+  }
+  return CCSM_OK;
+}
+
+static int make_params(const ccsm_model* m, const ExState* ex, ExParams& P) {
+  const ccsm_extract_opts& o = ex->opts;
+  P.blob = ex->blob.as<uint8_t>();
+  P.reads = ex->reads.as<ccsm_read>();
+  P.n_reads = ex->n_reads;
+  P.seq_len = m->cfg.seq_len;
+  P.nb = (m->cfg.seq_len - 1) / 2;
+  P.mod_loc = o.mod_loc;
+  P.rev_offset = (o.motif_len - 1 - o.mod_loc) - o.mod_loc;  // extract_features.py:333
+  P.norm = o.norm;
+  P.decode = o.decode;
+  P.n_motifs = o.n_motifs;
+  P.motif_len = o.motif_len;
+  for (int k = 0; k < 8; ++k) P.motif_code[k] = 0xffffffffu;
+  for (int k = 0; k < o.n_motifs; ++k) {
+    uint32_t w = 0;
+    for (int j = 0; j < o.motif_len; ++j) {
+      const char c = o.motifs[k * o.motif_len + j];
+      const int code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+      if (code < 0) {
+        set_error("ccsm_reads_extract_host: motif character '%c' is not one of ACGT (expand IUPAC codes first)", c);
+        return CCSM_EINVAL;
+      }
+      w |= (uint32_t)code << (4 * j);
+    }
+    P.motif_code[k] = w;
+  }
+  return CCSM_OK;
+}
+
+void ex_release(ccsm_model* m) {
+  ExState* ex = m->ex;
+  if (!ex) return;
+  for (DevBuf* b : {&ex->blob, &ex->reads, &ex->stats, &ex->site_cnt, &ex->site_off, &ex->site_read, &ex->site_loc,
+                    &ex->site_cord, &ex->feat, &ex->h0, &ex->out, &ex->tags})
+    b->release();
+  if (ex->st) cudaStreamDestroy(ex->st);
+  if (ex->st_copy) cudaStreamDestroy(ex->st_copy);
+  for (int i = 0; i < 2; ++i) {
+    if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
+    if (ex->done[i]) cudaEventDestroy(ex->done[i]);
+  }
+  delete ex;
+  m->ex = nullptr;
+}
+
+static int check_model(ccsm_model* m, const char* fn) {
+  if (!m || m->cfg.kind != CCSM_KIND_ATT2S) {
+    set_error("%s: not an att2s model", fn);
+    return CCSM_EINVAL;
+  }
+  if (m->cfg.feat_flags & (CCSM_FEAT_STDS | CCSM_FEAT_MAP)) {
+    set_error("%s: --is_stds / --is_map features are not produced by the device extractor", fn);
+    return CCSM_EUNSUPPORTED;
+  }
+  return CCSM_OK;
+}
+
+static int launch_features(ccsm_model* m, int64_t s0, int64_t cn, const ccsm_strand* fo, const ccsm_strand* ro,
+                           cudaStream_t st) {
+  ExState* ex = m->ex;
+  ExParams P;
+  CCSM_TRY(make_params(m, ex, P));
+  FeatOut f{const_cast<float*>(fo->kmer), const_cast<float*>(fo->kpass), const_cast<float*>(fo->ipd_means),
+            const_cast<float*>(fo->pw_means), const_cast<float*>(fo->sns)};
+  FeatOut r{const_cast<float*>(ro->kmer), const_cast<float*>(ro->kpass), const_cast<float*>(ro->ipd_means),
+            const_cast<float*>(ro->pw_means), const_cast<float*>(ro->sns)};
+  if (!f.kmer || !f.ipd || !f.pw || !r.kmer || !r.ipd || !r.pw) {
+    set_error("ccsm_reads_features: kmer / ipd_means / pw_means outputs are required");
+    return CCSM_EINVAL;
+  }
+  const long long total = cn * 2 * P.seq_len;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  window_gather_kernel<<<grid, 256, 0, st>>>(P, ex->stats.as<SigStat>(), ex->site_read.as<int>(),
+                                             ex->site_loc.as<int>(), s0, cn, f, r);
+  count_launch();
+  CCSM_CUDA(cudaGetLastError());
+  return CCSM_OK;
+}
+
+}  // namespace ccsm
+
+using namespace ccsm;
+
+extern "C" {
+
+int ccsm_reads_extract_host(ccsm_model* m, const ccsm_extract_opts* o, const uint8_t* blob, int64_t blob_bytes,
+                            const ccsm_read* reads, int32_t n_reads, int64_t* n_sites) {
+  CCSM_TRY(check_model(m, "ccsm_reads_extract_host"));
+  if (!o || !n_sites || n_reads < 0 || blob_bytes < 0 || (n_reads > 0 && (!blob || !reads))) {
+    set_error("ccsm_reads_extract_host: bad argument");
+    return CCSM_EINVAL;
+  }
+  if (o->n_motifs < 1 || o->n_motifs > 8 || o->motif_len < 1 || o->motif_len > 8 || o->mod_loc < 0 ||
+      o->mod_loc >= o->motif_len || o->norm < CCSM_NORM_ZSCORE || o->norm > CCSM_NORM_NONE) {
+    set_error("ccsm_reads_extract_host: unsupported options (motifs=%d x %d, mod_loc=%d, norm=%d)", o->n_motifs,
+              o->motif_len, o->mod_loc, o->norm);
+    return CCSM_EINVAL;
+  }
+  for (int i = 0; i < n_reads; ++i) {
+    const ccsm_read& r = reads[i];
+    const int64_t seq_bytes = (r.flags & CCSM_READ_SEQ_4BIT) ? (r.len + 1) / 2 : r.len;
+    if (r.len < 0 || r.seq_off < 0 || r.seq_off + seq_bytes > blob_bytes || r.fi_off < 0 || r.ri_off < 0 ||
+        r.fp_off < 0 || r.rp_off < 0 || r.fi_off + r.len > blob_bytes || r.ri_off + r.len > blob_bytes ||
+        r.fp_off + r.len > blob_bytes || r.rp_off + r.len > blob_bytes) {
+      set_error("ccsm_reads_extract_host: read %d points outside the blob", i);
+      return CCSM_EINVAL;
+    }
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  if (!m->ex) m->ex = new (std::nothrow) ExState();
+  ExState* ex = m->ex;
+  if (!ex) return CCSM_ENOMEM;
+  CCSM_TRY(ensure_streams(ex));
+  ex->opts = *o;
+  ex->n_reads = n_reads;
+  ex->n_sites = 0;
+  ex->blob_bytes = blob_bytes;
+  *n_sites = 0;
+  if (n_reads == 0) return CCSM_OK;
+  cudaStream_t st = ex->st;
+  CCSM_TRY(ex->blob.reserve((size_t)blob_bytes + 16));
+  CCSM_TRY(ex->reads.reserve((size_t)n_reads * sizeof(ccsm_read)));
+  CCSM_TRY(ex->stats.reserve((size_t)n_reads * 4 * sizeof(SigStat)));
+  CCSM_TRY(ex->site_cnt.reserve((size_t)n_reads * sizeof(int)));
+  CCSM_TRY(ex->site_off.reserve((size_t)(n_reads + 1) * sizeof(long long)));
+  CCSM_CUDA(cudaMemcpyAsync(ex->blob.p, blob, (size_t)blob_bytes, cudaMemcpyHostToDevice, st));
+  CCSM_CUDA(cudaMemcpyAsync(ex->reads.p, reads, (size_t)n_reads * sizeof(ccsm_read), cudaMemcpyHostToDevice, st));
+  ExParams P;
+  CCSM_TRY(make_params(m, ex, P));
+  read_scan_kernel<<<n_reads, 256, 0, st>>>(P, ex->stats.as<SigStat>(), ex->site_cnt.as<int>());
+  site_offsets_kernel<<<1, 1024, 0, st>>>(ex->site_cnt.as<int>(), ex->site_off.as<long long>(), n_reads);
+  count_launch(2);
+  CCSM_CUDA(cudaGetLastError());
+  long long total = 0;
+  CCSM_CUDA(cudaMemcpyAsync(&total, ex->site_off.as<long long>() + n_reads, sizeof(long long), cudaMemcpyDeviceToHost,
+                            st));
+  CCSM_CUDA(cudaStreamSynchronize(st));
+  if (total > 0) {
+    CCSM_TRY(ex->site_read.reserve((size_t)total * sizeof(int)));
+    CCSM_TRY(ex->site_loc.reserve((size_t)total * sizeof(int)));
+    CCSM_TRY(ex->site_cord.reserve((size_t)total * sizeof(int)));
+    site_emit_kernel<<<n_reads, 256, 0, st>>>(P, ex->site_off.as<long long>(), ex->site_read.as<int>(),
+                                              ex->site_loc.as<int>(), ex->site_cord.as<int>());
+    count_launch();
+    CCSM_CUDA(cudaGetLastError());
+  }
+  ex->n_sites = total;
+  *n_sites = total;
+  return CCSM_OK;
+}
+
+int ccsm_reads_sites(ccsm_model* m, int32_t* site_read, int32_t* site_loc) {
+  CCSM_TRY(check_model(m, "ccsm_reads_sites"));
+  if (!m->ex || m->ex->n_sites < 0) {
+    set_error("ccsm_reads_sites: no resident read batch (call ccsm_reads_extract_host first)");
+    return CCSM_ESTATE;
+  }
+  ExState* ex = m->ex;
+  if (ex->n_sites == 0) return CCSM_OK;
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  const size_t bytes = (size_t)ex->n_sites * sizeof(int);
+  if (site_read) CCSM_CUDA(cudaMemcpyAsync(site_read, ex->site_read.p, bytes, cudaMemcpyDeviceToHost, ex->st));
+  if (site_loc) CCSM_CUDA(cudaMemcpyAsync(site_loc, ex->site_loc.p, bytes, cudaMemcpyDeviceToHost, ex->st));
+  CCSM_CUDA(cudaStreamSynchronize(ex->st));
+  return CCSM_OK;
+}
+
+int ccsm_reads_features(ccsm_model* m, int64_t s0, int64_t cn, const ccsm_strand* fwd_out, const ccsm_strand* rev_out,
+                        void* stream) {
+  CCSM_TRY(check_model(m, "ccsm_reads_features"));
+  if (!m->ex || m->ex->n_sites < 0) {
+    set_error("ccsm_reads_features: no resident read batch (call ccsm_reads_extract_host first)");
+    return CCSM_ESTATE;
+  }
+  if (!fwd_out || !rev_out || s0 < 0 || cn < 0 || s0 + cn > m->ex->n_sites) {
+    set_error("ccsm_reads_features: bad site range [%lld, %lld) of %lld", (long long)s0, (long long)(s0 + cn),
+              (long long)m->ex->n_sites);
+    return CCSM_EINVAL;
+  }
+  if (cn == 0) return CCSM_OK;
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // the site list was produced on the extractor's stream
+  CCSM_CUDA(cudaEventRecord(m->ex->ev[0], m->ex->st));
+  CCSM_CUDA(cudaStreamWaitEvent(st, m->ex->ev[0], 0));
+  return launch_features(m, s0, cn, fwd_out, rev_out, st);
+}
+
+int ccsm_reads_forward_host(ccsm_model* m, const float* h0_fwd, const float* h0_rev, float* logits, float* probs,
+                            float* prob1, int32_t* mm_delta, uint8_t* ml) {
+  CCSM_TRY(check_model(m, "ccsm_reads_forward_host"));
+  if (!m->finalized) {
+    set_error("ccsm_reads_forward_host: model not finalized");
+    return CCSM_ESTATE;
+  }
+  if (!m->ex || m->ex->n_sites < 0) {
+    set_error("ccsm_reads_forward_host: no resident read batch (call ccsm_reads_extract_host first)");
+    return CCSM_ESTATE;
+  }
+  if (m->cfg.num_classes != 2 && (prob1 || mm_delta || ml)) {
+    set_error("ccsm_reads_forward_host: prob1/mm/ml need a 2-class model");
+    return CCSM_EINVAL;
+  }
+  ExState* ex = m->ex;
+  const int64_t n = ex->n_sites;
+  if (n == 0) return CCSM_OK;
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  const int L = m->cfg.seq_len, H = m->cfg.hidden, NL = m->cfg.num_layers, C = m->cfg.num_classes;
+  const bool has_np = m->cfg.feat_flags & CCSM_FEAT_NPASS, has_sn = m->cfg.feat_flags & CCSM_FEAT_SN;
+  const int64_t kChunk = 75776;  // one tensor-core library chunk
+  const int64_t chunk = n < kChunk ? n : kChunk;
+  const int64_t per_strand = (int64_t)4 * L + 4;
+  const int64_t h0_floats = (int64_t)2 * NL * H;
+  const bool has_h0 = h0_fwd && h0_rev;
+  // two of everything: chunk c+1's h0 upload overlaps chunk c's kernels
+  const size_t feat_bytes = (size_t)chunk * 2 * per_strand * sizeof(float);
+  const size_t h0_bytes = has_h0 ? (size_t)chunk * 2 * h0_floats * sizeof(float) : 0;
+  const size_t out_bytes = (size_t)chunk * 2 * C * sizeof(float);
+  const size_t tag_bytes = (size_t)chunk * (sizeof(float) + sizeof(int) + 4);
+  CCSM_TRY(ex->feat.reserve(2 * feat_bytes));
+  CCSM_TRY(ex->h0.reserve(2 * h0_bytes + 16));
+  CCSM_TRY(ex->out.reserve(2 * out_bytes));
+  CCSM_TRY(ex->tags.reserve(2 * tag_bytes));
+  cudaStream_t st = ex->st, sc = ex->st_copy;
+  int rc = CCSM_OK;
+  int64_t ci = 0;
+  for (int64_t s0 = 0; s0 < n && rc == CCSM_OK; s0 += chunk, ++ci) {
+    const int b = (int)(ci & 1);
+    const int64_t cn = (n - s0) < chunk ? (n - s0) : chunk;
+    float* fb = reinterpret_cast<float*>(ex->feat.as<char>() + b * feat_bytes);
+    ccsm_strand dev[2];
+    float* cur = fb;
+    for (int s = 0; s < 2; ++s) {
+      memset(&dev[s], 0, sizeof(ccsm_strand));
+      dev[s].kmer = cur; cur += cn * L;
+      if (has_np) { dev[s].kpass = cur; cur += cn * L; }
+      dev[s].ipd_means = cur; cur += cn * L;
+      dev[s].pw_means = cur; cur += cn * L;
+      if (has_sn) { dev[s].sns = cur; cur += cn * 4; }
+    }
+    const float* dh0[2] = {nullptr, nullptr};
+    if (has_h0) {
+      if (ci >= 2) cudaStreamWaitEvent(sc, ex->done[b], 0);
+      float* hb = reinterpret_cast<float*>(ex->h0.as<char>() + b * h0_bytes);
+      const float* src[2] = {h0_fwd, h0_rev};
+      for (int s = 0; s < 2; ++s) {
+        float* d = hb + (int64_t)s * cn * h0_floats;
+        cudaMemcpy2DAsync(d, (size_t)cn * H * sizeof(float), src[s] + s0 * H, (size_t)n * H * sizeof(float),
+                          (size_t)cn * H * sizeof(float), 2 * NL, cudaMemcpyHostToDevice, sc);
+        dh0[s] = d;
+      }
+      cudaEventRecord(ex->ev[b], sc);
+      cudaStreamWaitEvent(st, ex->ev[b], 0);
+    }
+    rc = launch_features(m, s0, cn, &dev[0], &dev[1], st);
+    if (rc != CCSM_OK) break;
+    float* dl = reinterpret_cast<float*>(ex->out.as<char>() + b * out_bytes);
+    float* dp = dl + cn * C;
+    rc = ccsm_forward_att2s(m, cn, &dev[0], &dev[1], dh0[0], dh0[1], dl, dp, st);
+    if (rc != CCSM_OK) break;
+    char* tb = ex->tags.as<char>() + b * tag_bytes;
+    float* d_p1 = reinterpret_cast<float*>(tb);
+    int* d_mm = reinterpret_cast<int*>(tb + (size_t)chunk * sizeof(float));
+    uint8_t* d_ml = reinterpret_cast<uint8_t*>(tb + (size_t)chunk * (sizeof(float) + sizeof(int)));
+    if (prob1 || mm_delta || ml) {
+      site_tags_kernel<<<(unsigned)((cn + 255) / 256), 256, 0, st>>>(dp, C, ex->site_read.as<int>(),
+                                                                     ex->site_cord.as<int>(), s0, cn, d_p1, d_mm, d_ml);
+      count_launch();
+    }
+    if (logits) cudaMemcpyAsync(logits + s0 * C, dl, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (probs) cudaMemcpyAsync(probs + s0 * C, dp, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (prob1) cudaMemcpyAsync(prob1 + s0, d_p1, (size_t)cn * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (mm_delta) cudaMemcpyAsync(mm_delta + s0, d_mm, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ml) cudaMemcpyAsync(ml + s0, d_ml, (size_t)cn, cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(ex->done[b], st);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(sc);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (rc != CCSM_OK) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("ccsm_reads_forward_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return CCSM_ECUDA;
+  }
+  return CCSM_OK;
+}
+
+}  // extern "C"

@@ -145,6 +145,85 @@ int  ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, c
 int  ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos,
                        const float* h0, float* out, void* stream);
 
+/* ---- reads in, calls out: feature extraction on the device -----------------------
+ * Replaces, for one batch of reads, the per-read host work of
+ *     ccsmeth/extract_features.py:261-406   extract_features_from_double_strand_read
+ *         (CodecV1 decode process_utils.py:426-449, per-read normalisation :181-199, motif scan
+ *          process_utils.py:122-137, forward / reverse-complement windows :343-363)
+ *     ccsmeth/call_modifications.py:73-123  _batch_feature_list2s (the 16-tensor layout)
+ *     ccsmeth/call_modifications.py:222-224 prob_1_norm = round(p1 / (p0 + p1), 6)
+ *     ccsmeth/_bam2modbam.py:187-208        _convert_locs_to_mmtag / _convert_probs_to_mltag
+ * The caller hands over the reads as raw bytes (e.g. the inflated BAM records themselves) plus one
+ * descriptor per read that says where the read's sequence and kinetics arrays start inside that blob. */
+#define CCSM_READ_REVERSE   1   /* stored sequence is the reverse complement of the forward read (BAM flag 0x10):
+                                   forward base i = complement(stored[len-1-i]); kinetics arrays are used as stored
+                                   (extract_features.py:313-319 does not flip them) */
+#define CCSM_READ_SEQ_4BIT  2   /* sequence is BAM 4-bit packed ("=ACMGRSVTWYHKDBN", high nibble first); else ASCII */
+
+typedef struct ccsm_read {
+  int64_t seq_off;            /* byte offsets into the blob */
+  int64_t fi_off, ri_off;     /* IPD codes, forward / reverse strand, `len` bytes each (tags fi, ri) */
+  int64_t fp_off, rp_off;     /* PW codes (tags fp, rp) */
+  int32_t len;                /* read length in bases */
+  int32_t fn, rn;             /* number of passes per strand (tags fn, rn) */
+  int32_t flags;              /* CCSM_READ_* */
+  int32_t win_lo, win_hi;     /* keep only sites with win_lo <= loc < win_hi (align mode + --skip_unmapped yes:
+                                 the aligned part of the query, extract_features.py:374,388-390; else 0, len) */
+  float   sn[4];              /* tag sn (used iff CCSM_FEAT_SN) */
+} ccsm_read;
+
+#define CCSM_NORM_ZSCORE  0    /* --norm, extract_features.py:181-199 ("mad" needs statsmodels: not offered) */
+#define CCSM_NORM_MINMEAN 1
+#define CCSM_NORM_MINMAX  2
+#define CCSM_NORM_NONE    3
+
+typedef struct ccsm_extract_opts {
+  int32_t mod_loc;            /* --mod_loc */
+  int32_t norm;               /* CCSM_NORM_* */
+  int32_t decode;             /* 1: CodecV1 codes -> frames (default), 0: --no_decode */
+  int32_t n_motifs;           /* expanded (ACGT-only) motifs, all of length motif_len, e.g. 1 x "CG" */
+  int32_t motif_len;          /* <= 8 */
+  char    motifs[64];         /* n_motifs * motif_len characters, concatenated */
+} ccsm_extract_opts;
+
+/* Step 1 (host buffers): upload the batch, compute the per-read normalisation statistics, scan the motif and
+ * build the site list (ordered by read, then by position -- the reference's order).  Synchronous; *n_sites is
+ * the number of candidate sites.  The batch stays resident in the handle until the next call. */
+int  ccsm_reads_extract_host(ccsm_model* m, const ccsm_extract_opts* opts, const uint8_t* blob, int64_t blob_bytes,
+                             const ccsm_read* reads, int32_t n_reads, int64_t* n_sites);
+
+/* The site list of the resident batch: index of the read in the batch and 0-based position `loc` in the forward
+ * read (host int32[n_sites] each; either may be NULL). */
+int  ccsm_reads_sites(ccsm_model* m, int32_t* site_read, int32_t* site_loc);
+
+/* Materialises sites [s0, s0+cn) of the resident batch in the reference's 16-tensor layout (device pointers,
+ * written; dead slots may be NULL) -- what _batch_feature_list2s + the FloatTensor stacking produce. */
+int  ccsm_reads_features(ccsm_model* m, int64_t s0, int64_t cn, const ccsm_strand* fwd_out,
+                         const ccsm_strand* rev_out, void* stream);
+
+/* Step 2 (host buffers): features -> forward -> per-site outputs for every site of the resident batch.
+ * h0_fwd/h0_rev: host (2*layers, n_sites, hidden) or NULL (h0 mode of the handle).  Outputs are host arrays of
+ * n_sites entries (any may be NULL): logits/probs (n, classes); prob1 = round(p1/(p0+p1), 6) in float32;
+ * mm_delta = the MM-tag number of the site (count of uncalled C's of the forward read since the previous
+ * called site of the read); ml = floor(prob1 * 256), 255 if prob1 >= 1. */
+int  ccsm_reads_forward_host(ccsm_model* m, const float* h0_fwd, const float* h0_rev, float* logits, float* probs,
+                             float* prob1, int32_t* mm_delta, uint8_t* ml);
+
+/* ---- host I/O helpers: BGZF block codec on a thread team (SAM/BAM spec 4.1) --------------------------------
+ * The reference reads and writes BAM through pysam/htslib with `threads=` (extract_features.py:60-73,
+ * call_modifications.py:410-462).  Pure host code; buffers are host memory.
+ * ccsm_bgzf_inflated_size: sum of the inflated sizes of the COMPLETE blocks found in src; *consumed = their bytes.
+ * ccsm_bgzf_inflate:       inflates those blocks into dst (CRC32 checked); returns bytes written.
+ * ccsm_bgzf_deflate:       cuts src into 65280-byte blocks, deflates them in parallel, writes the concatenated
+ *                          BGZF blocks (no EOF marker) into dst (capacity >= ccsm_bgzf_deflate_bound(src_bytes));
+ *                          returns bytes written.  Negative return = CCSM_E* code. */
+int64_t ccsm_bgzf_inflated_size(const uint8_t* src, int64_t src_bytes, int64_t* consumed);
+int64_t ccsm_bgzf_inflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, int64_t dst_cap, int32_t threads,
+                          int64_t* consumed);
+int64_t ccsm_bgzf_deflate_bound(int64_t src_bytes);
+int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, int64_t dst_cap, int32_t level,
+                          int32_t threads);
+
 /* Introspection used by tests: copies the last layer-stack output of the most recent forward chunk.
  * Returns the number of floats written (<= cap) or a negative error. */
 int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap);

@@ -15,6 +15,9 @@ Contents
                         (``aten::gru`` etc., which is where the reference's own
                         arithmetic lives); this is the "port" that the CPU
                         baseline times on the host cores.
+  * ``extract_numpy`` -- numpy restatement of the per-read feature extraction
+                        (reference ``ccsmeth/extract_features.py:181-199,261-406``), the checker
+                        for the device extractor (``ccsm_reads_*``).
   * ``refimport``    -- imports the *unmodified* reference from /root/reference
                         with stub modules for its absent I/O deps; used only by
                         ``scripts/gen_golden.py`` in the build container.

@@ -8,7 +8,8 @@ import pytest
 
 from ccsmeth_b200 import call_mods as cm
 from ccsmeth_b200.bamio import BamReader, BamWriter, add_pg_line
-from ccsmeth_b200.extract_features import CODE2FRAMES, batch_read_features, extract_read, to_feature_rows
+from ccsmeth_b200.extract_features import READ_SEQ_4BIT, pack_reads
+from oracle.extract_numpy import CODE2FRAMES, batch_read_features, extract_read, to_feature_rows
 from tests.conftest import GOLDEN, load_npz
 
 DEMO = os.path.join(GOLDEN, "demo", "hg002.chr20_demo.hifi.bam")
@@ -129,6 +130,50 @@ def test_modbam_write_read_roundtrip(tmp_path, reads, golden):
         else:
             assert not b.has_tag("MM")
         off += n
+
+
+def test_pack_reads_points_at_the_right_bytes(reads):
+    """The descriptors handed to the device extractor must address each read's packed sequence and kinetics
+    arrays inside the blob of raw records."""
+    args = _args()
+    batch = pack_reads(reads[:7], args)
+    assert len(batch) == 7 and batch.index == list(range(7)) and batch.descs.dtype.itemsize == 80
+    nib = "=ACMGRSVTWYHKDBN"
+    for d, r in zip(batch.descs, reads[:7]):
+        n = int(d["len"])
+        assert n == r.l_seq and d["flags"] == READ_SEQ_4BIT and (d["win_lo"], d["win_hi"]) == (0, n)
+        assert (d["fn"], d["rn"]) == (r.get_tag("fn"), r.get_tag("rn"))
+        for key, tag in (("fi_off", "fi"), ("ri_off", "ri"), ("fp_off", "fp"), ("rp_off", "rp")):
+            assert np.array_equal(batch.blob[d[key]:d[key] + n], r.get_tag(tag))
+        packed = batch.blob[d["seq_off"]:d["seq_off"] + (n + 1) // 2]
+        seq = "".join(nib[b >> 4] + nib[b & 15] for b in packed[:16])
+        assert seq[:32] == r.query_sequence[:32]
+
+
+def test_pack_reads_skips_reads_without_kinetics(reads):
+    args = _args()
+    r = reads[0]
+    stripped = type(r)(r.with_tags({"fi"}))
+    batch = pack_reads([stripped, reads[1]], args)
+    assert batch.index == [1]
+
+
+def test_native_bgzf_codec_roundtrip(tmp_path):
+    """libccsm's BGZF thread team (include/ccsm.h ccsm_bgzf_*) against Python's zlib path, both directions."""
+    a = list(BamReader(DEMO, threads=1))
+    b = list(BamReader(DEMO, threads=4))
+    assert [r.raw for r in a] == [r.raw for r in b]
+    rd = BamReader(DEMO)
+    outs = []
+    for th in (1, 4):
+        out = str(tmp_path / ("t%d.bam" % th))
+        wr = BamWriter(out, rd.header_text, rd.references, threads=th)
+        for r in a[:40]:
+            wr.write_raw(r.raw)
+        wr.close()
+        outs.append(out)
+    assert open(outs[0], "rb").read() == open(outs[1], "rb").read()  # same zlib, same level: identical bytes
+    assert [r.raw for r in BamReader(outs[1], threads=4)] == [r.raw for r in a[:40]]
 
 
 def test_motif_expansion():
