@@ -24,10 +24,10 @@ rep = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 demo = os.path.join(ROOT, "tests", "golden", "demo", "hg002.chr20_demo.hifi.bam")
 
 
-def run(inp, extra, reps):
+def run(inp, extra, reps, out_prefix=None):
     times = []
     for _ in range(reps):
-        args = cm.build_parser().parse_args(["-i", inp, "-m", ckpt, "-o", os.path.join(out_dir, "demo_out"),
+        args = cm.build_parser().parse_args(["-i", inp, "-m", ckpt, "-o", out_prefix or os.path.join(out_dir, "demo_out"),
                                              "--precision", prec, "--threads", str(os.cpu_count())] + extra)
         t0 = time.perf_counter()
         counts, path = cm.call_mods(args)
@@ -45,7 +45,9 @@ res = {"workload": "demo/hg002.chr20_demo.hifi.bam call_mods end to end (BAM in 
        "speedup_vs_reference_chain": float(g["ref_cpu_seconds"]) / best, "host_cores": os.cpu_count()}
 
 if rep > 0:
-    big = os.path.join(out_dir, "demo_x%d.bam" % rep)
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="ccsm_demo_")  # not under gpurun_out/: only small files travel back
+    big = os.path.join(tmp, "demo_x%d.bam" % rep)
     rd = BamReader(demo)
     recs = list(rd)
     wr = BamWriter(big, rd.header_text, rd.references, threads=os.cpu_count())
@@ -58,6 +60,6 @@ if rep > 0:
     wr.close()
     res["big"] = {"workload": "demo reads x%d (%d reads, %.1f MB BAM)" % (rep, rep * len(recs), os.path.getsize(big) / 1e6)}
     for mode in ("device", "reference"):
-        c, t = run(big, ["--h0", mode], 2)
+        c, t = run(big, ["--h0", mode], 2, os.path.join(tmp, "out"))
         res["big"]["h0_" + mode] = {"sites": c["sites"], "seconds_runs": t, "sites_per_s": c["sites"] / min(t)}
 print(json.dumps(res))

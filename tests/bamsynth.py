@@ -34,7 +34,7 @@ def make_record(name, seq, fi, ri, fp, rp, fn=5, rn=6, flag=4, cigar=(), sn=None
     return BamRecord(raw)
 
 
-def random_read(rng, name, n, p_cg=0.08, p_n=0.002, reverse=False, const_sig=None, **kw):
+def random_read(rng, name, n, p_cg=0.08, p_n=0.002, reverse=False, const_sig=None, no_cg=False, **kw):
     """A random forward read of n bases with CpGs sprinkled in; returns the BamRecord (stored orientation
     follows `reverse`) and the forward sequence string."""
     bases = np.array(list("ACGT"))
@@ -42,6 +42,10 @@ def random_read(rng, name, n, p_cg=0.08, p_n=0.002, reverse=False, const_sig=Non
     for i in np.nonzero(rng.random(max(n - 1, 0)) < p_cg)[0]:
         s[i], s[i + 1] = "C", "G"
     s[rng.random(n) < p_n] = "N"
+    if no_cg:
+        for i in range(n - 1):
+            if s[i] == "C" and s[i + 1] == "G":
+                s[i + 1] = "A"
     fwd = "".join(s)
     comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
     stored = "".join(comp[c] for c in reversed(fwd)) if reverse else fwd

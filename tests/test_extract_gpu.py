@@ -128,7 +128,7 @@ def test_synthetic_edge_cases(model):
         random_read(rng, "short20", 20)[0],                      # shorter than one window: no sites
         random_read(rng, "short21", 21, p_cg=1.0)[0],            # exactly one window long
         random_read(rng, "len22", 22, p_cg=1.0)[0],
-        random_read(rng, "nocg", 500, p_cg=0.0)[0],
+        random_read(rng, "nocg", 500, no_cg=True)[0],
         random_read(rng, "manyN", 800, p_n=0.2)[0],
         random_read(rng, "const_ipd", 600, const_sig=0)[0],      # zero variance -> all-zero feature
         random_read(rng, "const_rpw", 600, const_sig=3)[0],
@@ -217,7 +217,7 @@ def test_mm_counts_reverse_strand_records(model):
 def test_empty_and_bad_batches(model):
     args = _args()
     rng = np.random.default_rng(23)
-    none = pack_reads([random_read(rng, "x", 300, p_cg=0.0)[0]], args)
+    none = pack_reads([random_read(rng, "x", 300, no_cg=True)[0]], args)
     assert model.extract_reads(none, extract_opts(args, ["CG"])) == 0
     assert model.reads_forward()["prob1"].shape == (0,)
     batch = pack_reads([random_read(rng, "y", 300)[0]], args)
