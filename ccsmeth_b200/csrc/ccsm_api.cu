@@ -417,7 +417,7 @@ int ccsm_profile_enable(ccsm_model* m, int32_t on) {
 }
 
 int ccsm_profile_read(ccsm_model* m, double* ms, double* units, int64_t* launches, int32_t nclass) {
-  if (!m || !ms || !units || !launches || nclass < PROF_NCLASS) {
+  if (!m || !ms || !units || !launches || nclass < 4) {
     set_error("ccsm_profile_read: bad argument");
     return CCSM_EINVAL;
   }
@@ -431,9 +431,11 @@ int ccsm_profile_read(ccsm_model* m, double* ms, double* units, int64_t* launche
     CCSM_CUDA(cudaEventSynchronize(r.b));
     float t = 0.f;
     CCSM_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
-    ms[r.cls] += t;
-    units[r.cls] += r.units;
-    launches[r.cls] += 1;
+    if (r.cls < nclass) {
+      ms[r.cls] += t;
+      units[r.cls] += r.units;
+      launches[r.cls] += 1;
+    }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }

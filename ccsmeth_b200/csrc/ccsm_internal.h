@@ -75,7 +75,8 @@ struct TcState;  // tensor-core (tcgen05) path state, defined in tc_path.cu
 struct ExState;  // device feature extraction state (resident read batch), defined in extract.cu
 
 // Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).
-enum ProfClass { PROF_PREP = 0, PROF_GRU_L0 = 1, PROF_GRU_LN = 2, PROF_ATT = 3, PROF_NCLASS = 4 };
+enum ProfClass { PROF_PREP = 0, PROF_GRU_L0 = 1, PROF_GRU_LN = 2, PROF_ATT = 3, PROF_EX_SCAN = 4, PROF_EX_GATHER = 5,
+                 PROF_NCLASS = 6 };
 struct ProfRec {
   cudaEvent_t a, b;
   int cls;

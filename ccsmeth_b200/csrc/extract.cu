@@ -404,8 +404,10 @@ static int launch_features(ccsm_model* m, int64_t s0, int64_t cn, const ccsm_str
   }
   const long long total = cn * 2 * P.seq_len;
   const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const int pid = m->prof.begin(PROF_EX_GATHER, (double)cn, st);
   window_gather_kernel<<<grid, 256, 0, st>>>(P, ex->stats.as<SigStat>(), ex->site_read.as<int>(),
                                              ex->site_loc.as<int>(), s0, cn, f, r);
+  m->prof.end(pid, st);
   count_launch();
   CCSM_CUDA(cudaGetLastError());
   return CCSM_OK;
@@ -461,8 +463,12 @@ int ccsm_reads_extract_host(ccsm_model* m, const ccsm_extract_opts* o, const uin
   CCSM_CUDA(cudaMemcpyAsync(ex->reads.p, reads, (size_t)n_reads * sizeof(ccsm_read), cudaMemcpyHostToDevice, st));
   ExParams P;
   CCSM_TRY(make_params(m, ex, P));
+  double n_bases = 0;
+  for (int i = 0; i < n_reads; ++i) n_bases += reads[i].len;
+  int pid = m->prof.begin(PROF_EX_SCAN, n_bases, st);
   read_scan_kernel<<<n_reads, 256, 0, st>>>(P, ex->stats.as<SigStat>(), ex->site_cnt.as<int>());
   site_offsets_kernel<<<1, 1024, 0, st>>>(ex->site_cnt.as<int>(), ex->site_off.as<long long>(), n_reads);
+  m->prof.end(pid, st);
   count_launch(2);
   CCSM_CUDA(cudaGetLastError());
   long long total = 0;
@@ -473,8 +479,10 @@ int ccsm_reads_extract_host(ccsm_model* m, const ccsm_extract_opts* o, const uin
     CCSM_TRY(ex->site_read.reserve((size_t)total * sizeof(int)));
     CCSM_TRY(ex->site_loc.reserve((size_t)total * sizeof(int)));
     CCSM_TRY(ex->site_cord.reserve((size_t)total * sizeof(int)));
+    pid = m->prof.begin(PROF_EX_SCAN, 0, st);
     site_emit_kernel<<<n_reads, 256, 0, st>>>(P, ex->site_off.as<long long>(), ex->site_read.as<int>(),
                                               ex->site_loc.as<int>(), ex->site_cord.as<int>());
+    m->prof.end(pid, st);
     count_launch();
     CCSM_CUDA(cudaGetLastError());
   }

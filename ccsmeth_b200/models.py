@@ -257,11 +257,11 @@ class ModelAttRNN(_NativeModule):
     def profile_read(self):
         """Returns {class: (ms, sites, launches)} accumulated since the last read."""
         handle, _ = self._ensure_handle()
-        ms = (ctypes.c_double * 4)()
-        units = (ctypes.c_double * 4)()
-        launches = (ctypes.c_int64 * 4)()
-        _lib.check(_lib.load().ccsm_profile_read(handle, ms, units, launches, 4))
-        names = ("prep", "gru_l0", "gru_ln", "att_head")
+        ms = (ctypes.c_double * 6)()
+        units = (ctypes.c_double * 6)()
+        launches = (ctypes.c_int64 * 6)()
+        _lib.check(_lib.load().ccsm_profile_read(handle, ms, units, launches, 6))
+        names = ("prep", "gru_l0", "gru_ln", "att_head", "read_scan", "window_gather")
         return {n: (ms[i], units[i], int(launches[i])) for i, n in enumerate(names)}
 
     def forward_host(self, feats, h0=None):

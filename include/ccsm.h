@@ -230,8 +230,10 @@ int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap);
 
 /* Per-kernel-class device timing for bench.py's roofline: while enabled, every tensor-core kernel launch is
  * bracketed by CUDA events recorded on the launching stream.  ccsm_profile_read waits for them and returns,
- * per class {0: feature/h0 packing, 1: GRU layer 0, 2: GRU layers >= 1, 3: attention + head}, the summed
- * milliseconds, the summed sites processed and the launch count (arrays of >= 4 entries), then resets. */
+ * per class {0: feature/h0 packing, 1: GRU layer 0, 2: GRU layers >= 1, 3: attention + head, 4: read scan (per-read
+ * statistics + motif scan + site list; units = bases), 5: window gather (units = sites)}, the summed milliseconds,
+ * the summed units processed and the launch count (arrays of nclass >= 4 entries; classes >= nclass are dropped),
+ * then resets. */
 int  ccsm_profile_enable(ccsm_model* m, int32_t on);
 int  ccsm_profile_read(ccsm_model* m, double* ms, double* units, int64_t* launches, int32_t nclass);
 
