@@ -266,10 +266,16 @@ struct GruCfg {
   static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
 };
 
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW>
+//   MC    = launched as clusters of two CTAs (same direction, neighbouring row tiles) that share every weight
+//           stage: each CTA fetches HALF of the stage's weight bytes and multicasts them into both CTAs' shared
+//           memory (cp.async.bulk ... .multicast::cluster), halving the L2 -> SM weight traffic (weights are
+//           6/7 of what this kernel pulls through the crossbar).  A stage is refilled only when BOTH CTAs'
+//           MMAs have retired it (multicast tcgen05.commit onto both empty barriers, count 2).
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC>
 __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, GruCfg<P, NSLOT, NBUF, KSB, EPIW>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
   static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
+  static_assert(!MC || NSLOT == 1, "multicast variant: one row tile per CTA");
   using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW>;
   constexpr int GRU_STAGES = C::STAGES;
   constexpr int GRU_THREADS = C::THREADS;
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
   if (threadIdx.x == 0) {
     for (int i = 0; i < GRU_STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, MC ? 2 : 1);
     }
     for (int i = 0; i < NBUF; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
@@ -304,11 +310,18 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t smem_base = smem_u32(smem);
   const int L = p.L;
-  const int n_items = (p.n_tiles / NSLOT) * 2;  // groups of NSLOT row tiles x 2 directions
+  // work items = (group of row tiles, direction).  Plain: one item per CTA at a time, NSLOT tiles each.
+  // MC: one item per CLUSTER at a time = two neighbouring row tiles, one per CTA (rank), same direction.
+  const uint32_t crank = MC ? cluster_ctarank() : 0;
+  const int n_items = MC ? (p.n_tiles / 2) * 2 : (p.n_tiles / NSLOT) * 2;
+  const int item0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILES_PER_ITEM = MC ? 2 : NSLOT;
   const size_t xbytes = (size_t)P * p.kx_slabs * G_SLAB, hbytes = (size_t)P * 32 * G_SLAB;
   const size_t wj_bytes = xbytes + hbytes;
 
@@ -319,9 +332,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
       uint32_t gstep = 0;
       const uint64_t pol = make_policy_evict_last();
       const bool hint = p.l2_hint != 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = item0; item < n_items; item += item_step) {
         const int pair = item >> 1, d = item & 1;
-        const int64_t tile0 = NSLOT * (int64_t)pair;
+        const int64_t tile0 = TILES_PER_ITEM * (int64_t)pair + crank;
         for (int s = 0; s < L; ++s, ++gstep) {
           const int t = d ? (L - 1 - s) : s;
           const int tprev = d ? t + 1 : t - 1;
@@ -343,8 +356,16 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
                 const uint8_t* wsrc = wj + (part ? xbytes : 0);
 #pragma unroll
                 for (int pp = 0; pp < P; ++pp) {
-                  if (hint) bulk_g2s_hint(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb, pol);
-                  else bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb);
+                  if constexpr (MC) {
+                    // this CTA's half of the stage's weight slabs, delivered to both CTAs of the cluster
+                    const uint32_t half = (uint32_t)(ns / 2) * G_SLAB;
+                    bulk_g2s_mc(sb + pp * C::B_PART + crank * half,
+                                wsrc + ((size_t)pp * total + so) * G_SLAB + crank * half, half, fb, (uint16_t)3);
+                  } else if (hint) {
+                    bulk_g2s_hint(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb, pol);
+                  } else {
+                    bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb);
+                  }
                 }
                 // activations of every slot
 #pragma unroll
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
     if (elect_one()) {
       constexpr uint32_t idesc192 = make_idesc(128, 192, F16);
       uint32_t stage = 0, use = 0, chunk = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = item0; item < n_items; item += item_step) {
         for (int s = 0; s < L; ++s) {
           for (int j = 0; j < 4; ++j, ++chunk) {
             const uint32_t buf = chunk % NBUF, bphase = (chunk / NBUF) & 1;
@@ -421,7 +442,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
                     }
                   }
                 }
-                umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
+                // frees the smem stage when these MMAs retire (MC: in both CTAs -- the peer refills half of it)
+                if constexpr (MC) umma_commit_mc(empty0 + 8 * stage, (uint16_t)3);
+                else umma_commit(empty0 + 8 * stage);
                 if (++stage == GRU_STAGES) {
                   stage = 0;
                   ++use;
@@ -444,7 +467,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
     const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
     uint32_t chunk = 0;
     // gridDim.x is even (host), so every item of this CTA has the same direction: the biases to arm are fixed
-    const float* bz = bias_s + (blockIdx.x & 1) * 4 * 256;
+    const float* bz = bias_s + (item0 & 1) * 4 * 256;
     for (int b = 0; b < NBUF; ++b) {  // arm the first NBUF unit-chunks (j = b)
 #pragma unroll
       for (int k = 0; k < NUB; ++k)
@@ -453,9 +476,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
       tc_fence_before();
       mbar_arrive(tmem_empty + 8 * b);
     }
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
       const int pair = item >> 1, d = item & 1;
-      const int64_t tile = NSLOT * (int64_t)pair + slot;
+      const int64_t tile = TILES_PER_ITEM * (int64_t)pair + crank + slot;
       for (int s = 0; s < L; ++s) {
         const int t = d ? (L - 1 - s) : s;
         const int tprev = d ? t + 1 : t - 1;
@@ -521,6 +544,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peer may still be arriving on this CTA's empty barriers
   if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
@@ -1270,6 +1294,7 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
 
 // GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2),
 // 5 = variant 0 with 40 KB stages, 6 = variant 2 with two epilogue warps per quadrant,
+// 7 / 8 / 9 = variants 2 / 0 / 5 as clusters of two CTAs sharing every weight stage by TMA multicast,
 // 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered), 4 = CTA pair, two clusters per TPC (NBUF 1).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
 // Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0 (two CTAs per SM);
@@ -1280,27 +1305,47 @@ static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    v[0] = (e && e[0] >= '0' && e[0] <= '6') ? e[0] - '0' : -1;
-    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '6') ? e[1] - '0' : v[0];
+    v[0] = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1;
+    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '9') ? e[1] - '0' : v[0];
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
   return layer > 0 ? 2 : 0;
 }
 
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1>
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false>
 static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
   using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW>;
   static bool attr = false;
+  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC>;
   if (!attr) {
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CCSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr = true;
   }
-  const int64_t items = (tiles / NSLOT) * 2;  // groups of NSLOT row tiles x 2 directions
   const int64_t slots = (int64_t)sm_count * C::CTAS_PER_SM;
+  if constexpr (MC) {
+    // clusters of two CTAs; an even number of clusters so that every cluster keeps one direction
+    const int64_t items = (tiles / 2) * 2;  // pairs of row tiles x 2 directions
+    const int64_t max_clusters = slots / 2;
+    const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CCSM_CUDA(cudaLaunchKernelEx(&cfg, kern, gp));
+    return CCSM_OK;
+  }
+  const int64_t items = (tiles / NSLOT) * 2;  // groups of NSLOT row tiles x 2 directions
   const int grid = (int)(items < slots ? items : slots) & ~1;  // even: fixed direction per CTA
-  tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW><<<grid, C::THREADS, C::SMEM, st>>>(gp);
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(gp);
   return CCSM_OK;
 }
 
@@ -1313,6 +1358,9 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
     case 2: return launch_gru<P, F16, 1, 2, 8>(gp, tiles, sm_count, st);
     case 5: return launch_gru<P, F16, 1, 1, 8>(gp, tiles, sm_count, st);
     case 6: return launch_gru<P, F16, 1, 2, 8, 2>(gp, tiles, sm_count, st);  // 2 + 8 epilogue warps
+    case 7: return launch_gru<P, F16, 1, 2, 8, 1, true>(gp, tiles, sm_count, st);  // 2 + weight multicast
+    case 8: return launch_gru<P, F16, 1, 1, 4, 1, true>(gp, tiles, sm_count, st);  // 0 + weight multicast
+    case 9: return launch_gru<P, F16, 1, 1, 8, 1, true>(gp, tiles, sm_count, st);  // 5 + weight multicast
     default:
       set_error("unknown GRU kernel variant %d", variant);
       return CCSM_EINVAL;
