@@ -1,6 +1,7 @@
 // C-ABI layer of libccsm.so (declared in include/ccsm.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ccsm_internal.h"
@@ -121,6 +122,8 @@ void ccsm_destroy(ccsm_model* m) {
   cudaSetDevice(m->cfg.device);
   tc_release(m);
   ex_release(m);
+  m->aggr_packed.release();
+  m->aggr_scratch.release();
   for (auto& l : m->fp32.layers) {
     l.w_ih.release(); l.b_ih.release(); l.w_hh.release(); l.b_hh.release();
   }
@@ -211,6 +214,7 @@ int ccsm_finalize(ccsm_model* m) {
   CCSM_TRY(check_complete(m));
   CCSM_TRY(fp32_upload_weights(m));  // always kept: cross-check path + attention/head fallback
   if (is_tc(m->cfg.precision)) CCSM_TRY(tc_upload_weights(m));
+  if (m->cfg.kind == CCSM_KIND_AGGR) CCSM_TRY(aggr_fused_upload(m));
   m->finalized = true;
   return CCSM_OK;
 }
@@ -293,6 +297,12 @@ int ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const floa
   }
   if (n == 0) return CCSM_OK;
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  // one fused kernel for the shipped configuration (H = 32, 21 inputs, one layer); CCSM_AGGR_UNFUSED=1 keeps the
+  // layer-by-layer fp32 kernels (the path other shapes take) for cross-checks
+  const char* env = getenv("CCSM_AGGR_UNFUSED");
+  const bool unfused = env && atoi(env) != 0;
+  if (!unfused && aggr_fused_supported(m))
+    return aggr_fused_forward(m, n, offsets, histos, h0, out, reinterpret_cast<cudaStream_t>(stream));
   return fp32_forward_aggr(m, n, offsets, histos, h0, out, reinterpret_cast<cudaStream_t>(stream));
 }
 

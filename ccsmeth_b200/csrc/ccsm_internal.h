@@ -112,6 +112,7 @@ struct ccsm_model {
   ccsm::Fp32Workspace ws32;
   ccsm::TcState* tc = nullptr;
   ccsm::ExState* ex = nullptr;
+  ccsm::DevBuf aggr_packed, aggr_scratch;  // fused aggregate kernel (aggr_fused.cu)
   ccsm::Profiler prof;
   int h0_mode = 0;            // CCSM_H0_*
   uint64_t h0_seed = 0;
@@ -140,6 +141,12 @@ void tc_release(ccsm_model* m);
 int tc_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
                      const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st);
 int tc_debug_layer_out(ccsm_model* m, int layer, float* host, int64_t cap, int64_t* written);
+
+// ---- fused aggregate model (aggr_fused.cu)
+bool aggr_fused_supported(const ccsm_model* m);
+int aggr_fused_upload(ccsm_model* m);
+int aggr_fused_forward(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
+                       cudaStream_t st);
 
 // ---- device feature extraction (extract.cu)
 void ex_release(ccsm_model* m);

@@ -116,6 +116,29 @@ def test_aggr_matches_reference(ckpt_aggr, golden_aggr):
     assert np.abs(out.cpu().numpy() - g["raw"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("n", [1, 255, 257, 1000, 70001])
+def test_aggr_fused_kernel_vs_oracle_and_layerwise_path(ckpt_aggr, n, monkeypatch):
+    """The one-kernel aggregate forward (csrc/aggr_fused.cu) against the numpy oracle on random windows of ragged
+    sizes, and against the layer-by-layer fp32 kernels (CCSM_AGGR_UNFUSED=1)."""
+    from ccsmeth_b200.models import AggrAttRNN
+    rng = np.random.default_rng(n)
+    histos = rng.random((n, 11, 20)).astype(np.float32)
+    histos = np.round(histos / np.linalg.norm(histos, axis=2, keepdims=True), 6).astype(np.float32)
+    offsets = rng.integers(0, 1500, (n, 11)).astype(np.float32)
+    h0 = rng.standard_normal((2, n, 32)).astype(np.float32)
+    m = AggrAttRNN(11, 1, 1, 0, 32, binsize=20, model_type="attbigru", device=0)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ckpt_aggr.items()})
+    m = m.cuda(0).eval()
+    fused = m(torch.from_numpy(offsets), torch.from_numpy(histos), h0=torch.from_numpy(h0)).cpu().numpy()
+    monkeypatch.setenv("CCSM_AGGR_UNFUSED", "1")
+    layerwise = m(torch.from_numpy(offsets), torch.from_numpy(histos), h0=torch.from_numpy(h0)).cpu().numpy()
+    monkeypatch.delenv("CCSM_AGGR_UNFUSED")
+    assert np.abs(fused - layerwise).max() <= 1e-5
+    k = min(n, 2000)
+    ref = aggr_numpy.forward(ckpt_aggr, offsets[:k], histos[:k], h0[:, :k], dtype=np.float64)
+    assert np.abs(fused[:k] - ref).max() <= 1e-5
+
+
 def test_set_weight_rejects_wrong_shape(model):
     import ctypes
     from ccsmeth_b200 import _lib
