@@ -32,7 +32,7 @@ EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
            "ccsm_debug_umma_pair_gemm", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
            "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound",
-           "ccsm_bgzf_deflate"]
+           "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records"]
 
 
 class CcsmError(RuntimeError):
@@ -55,6 +55,10 @@ class Strand(ctypes.Structure):
 class ExtractOpts(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("mod_loc", "norm", "decode", "n_motifs", "motif_len")] + \
                [("motifs", ctypes.c_char * 64)]
+
+
+class BamFilter(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("mode_align", "mapq", "no_supplementary", "skip_unmapped", "want_sn")]
 
 
 def sources():
@@ -160,6 +164,11 @@ def load():
         lib.ccsm_bgzf_deflate.argtypes = [vp, i64, vp, i64, i32, i32]
         for fn in ("ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound", "ccsm_bgzf_deflate"):
             getattr(lib, fn).restype = i64
+        lib.ccsm_bam_index.argtypes = [vp, i64, ctypes.POINTER(BamFilter), vp, i32, vp, ctypes.POINTER(i32),
+                                       ctypes.POINTER(i32), ctypes.POINTER(i64)]
+        lib.ccsm_bam_index.restype = ctypes.c_int
+        lib.ccsm_bam_tag_records.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i64, ctypes.POINTER(i32)]
+        lib.ccsm_bam_tag_records.restype = i64
         for fn in ("ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features", "ccsm_reads_forward_host"):
             getattr(lib, fn).restype = ctypes.c_int
         for fn in ("ccsm_create", "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",

@@ -219,15 +219,27 @@ class BamRecord:
 
     @property
     def query_alignment_start(self):
-        ct = self.cigartuples
-        return ct[0][1] if ct and ct[0][0] == 4 else 0
+        """Leading soft clips (hard clips are not part of the stored sequence), like pysam."""
+        start = 0
+        for op, ln in self.cigartuples:
+            if op == 5:
+                continue
+            if op == 4:
+                start += ln
+            else:
+                break
+        return start
 
     @property
     def query_alignment_end(self):
-        ct = self.cigartuples
         end = self.l_seq
-        if ct and ct[-1][0] == 4:
-            end -= ct[-1][1]
+        for op, ln in reversed(self.cigartuples):
+            if op == 5:
+                continue
+            if op == 4:
+                end -= ln
+            else:
+                break
         return end
 
     # ---- pysam-compatible names the reference's extractor touches in align mode

@@ -8,10 +8,11 @@ ccsmeth/call_modifications.py:616-752) and its output rules (SURVEY.md appendix 
   * reads without predictions are still written (call_modifications.py:239-242)
   * header gets an ``@PG ID:ccsmeth`` line (:445)
 The reference wires reader / extractors / model workers / writer with multiprocessing queues
-(call_modifications.py:520-590); here each rank runs a reader thread (BGZF inflate on a native thread team), the
-GPU calls (feature extraction + forward + MM/ML values on the device, csrc/extract.cu) and a writer thread
-(tagging + BGZF deflate on the thread team), takes the hole-batches with ``batch_idx % world == rank`` and writes
-its own BAM shard.  Sorting/indexing
+(call_modifications.py:520-590); here each rank runs a reader thread (BGZF inflate on a native thread team +
+native record indexing, bamstream.py), the GPU calls (feature extraction + forward + MM/ML values on the device,
+csrc/extract.cu) and a writer thread (native re-tagging + BGZF deflate on the thread team), takes the hole-batches
+with ``batch_idx % world == rank`` and writes its own BAM shard.  No per-read Python objects on this path;
+``call_reads`` / ``tag_read`` are the record-level equivalents kept for callers that hold BamRecords.  Sorting/indexing
 (call_modifications.py:592-607) needs samtools and is left to the caller: the output is always unsorted.
 
     python -m ccsmeth_b200.call_mods -i in.hifi.bam -m model.ckpt -o out_prefix [--mode denovo] ...
@@ -26,11 +27,19 @@ import time
 import numpy as np
 import torch
 
-from . import VERSION, parallel
-from .bamio import BamReader, BamWriter, add_pg_line
+from . import VERSION, _lib, parallel
+from .bamio import BamWriter, add_pg_line
+from .bamstream import BamPieceReader, tag_records
 from .call_modifications import draw_h0_stream, load_model
-from .extract_features import extract_opts, pack_reads
+from .extract_features import ReadBatch, extract_opts, pack_reads
 from .utils.process_utils import str2bool
+
+TIMING = {}  # stage -> seconds, filled when CCSM_TIMING=1 (reader / pack / extract / forward / tag / write)
+
+
+def _tic(key, t0):
+    TIMING[key] = TIMING.get(key, 0.0) + (time.perf_counter() - t0)
+
 
 IUPAC = {'A': 'A', 'C': 'C', 'G': 'G', 'T': 'T', 'R': 'AG', 'M': 'AC', 'S': 'CG', 'Y': 'CT', 'K': 'GT', 'W': 'AT',
          'B': 'CGT', 'D': 'AGT', 'H': 'ACT', 'V': 'ACG', 'N': 'ACGT'}
@@ -75,10 +84,14 @@ def call_reads(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=N
     ``holes_batch``: reads per hole-batch inside `reads` (default: all of `reads` is one hole-batch).  It only
     matters for the reference's h0 stream and batch counter, which restart their 512-slicing at every hole-batch."""
     per_read = [None] * len(reads)
+    t0 = time.perf_counter()
     batch = pack_reads(reads, args, holeids_e, holeids_ne)
+    _tic("pack", t0)
     if len(batch) == 0:
         return per_read, 0, 0
+    t0 = time.perf_counter()
     n = model.extract_reads(batch, extract_opts(args, motifs))
+    _tic("extract", t0)
     if n == 0:
         return per_read, 0, 0
     site_read, site_loc = model.reads_sites()
@@ -90,7 +103,9 @@ def call_reads(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=N
         parts = [draw_h0_stream(int(c), args.batch_size, model.num_layers, model.hidden_size) for c in per_hb if c]
         h0 = (torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1)) if len(parts) > 1 \
             else parts[0]
+    t0 = time.perf_counter()
     res = model.reads_forward(h0=h0, want_probs=False)
+    _tic("forward", t0)
     bounds = np.nonzero(np.diff(site_read))[0] + 1
     starts = np.concatenate(([0], bounds))
     ends = np.concatenate((bounds, [n]))
@@ -129,46 +144,81 @@ def tag_read(rec, pred, rm_pulse, mod_base_is_c=True):
     return rec.with_tags(drop, "C+m?," + ",".join(map(str, mm.tolist())) + ";", ml.tolist()), 1
 
 
-def _reader_thread(path, args, rank, world, q, group):
-    """Reads the BAM, keeps the hole-batches this rank owns (batch_idx % world == rank) and hands them over in
-    groups of `group` hole-batches (one device call each)."""
+def call_piece(model, piece, motifs, args, rank=0, world=1, holeids_e=None, holeids_ne=None):
+    """One bamstream.Piece -> (recs of this rank, site_begin per read, mm, ml, n_sites, n_model_batches).
+    Same work as ``call_reads`` without per-read Python objects: the piece's buffer is the device blob."""
+    recs = piece.recs
+    descs = piece.descs
+    hb = args.holes_batch
+    gidx = piece.first + np.arange(len(recs), dtype=np.int64)
+    own = np.ones(len(recs), dtype=bool) if world == 1 else ((gidx // hb) % world) == rank
+    use = own & (recs["read_idx"] >= 0)
+    if holeids_e is not None or holeids_ne is not None:
+        for i, nm in enumerate(piece.names()):
+            nm = nm.decode("ascii", "replace")
+            if (holeids_e is not None and nm not in holeids_e) or (holeids_ne is not None and nm in holeids_ne):
+                use[i] = False
+    recs = recs[own].copy()
+    sel = piece.recs["read_idx"][use]                 # descs that take part, in record order
+    remap = np.full(len(descs) + 1, -1, dtype=np.int32)
+    remap[sel] = np.arange(len(sel), dtype=np.int32)
+    recs["read_idx"] = np.where(use[own], remap[recs["read_idx"]], -1)
+    site_begin = np.zeros(len(sel) + 1, dtype=np.int64)
+    if len(sel) == 0:
+        return recs, site_begin, None, None, 0, 0
+    t0 = time.perf_counter()
+    batch = ReadBatch(piece.buf, np.ascontiguousarray(descs[sel]), None)
+    n = model.extract_reads(batch, extract_opts(args, motifs))
+    _tic("extract", t0)
+    if n == 0:
+        return recs, site_begin, None, None, 0, 0
+    site_read, _ = model.reads_sites()
+    np.cumsum(np.bincount(site_read, minlength=len(sel)), out=site_begin[1:])
+    # the reference's bookkeeping restarts at every hole-batch: batch counter and, in --h0 reference, the randn stream
+    site_hb = (gidx[use] // hb)[site_read]
+    per_hb = np.diff(np.concatenate(([0], np.nonzero(np.diff(site_hb))[0] + 1, [n])))
+    n_batches = int(((per_hb + args.batch_size - 1) // args.batch_size).sum())
+    h0 = None
+    if getattr(args, "h0", "reference") == "reference":
+        parts = [draw_h0_stream(int(c), args.batch_size, model.num_layers, model.hidden_size) for c in per_hb]
+        h0 = (torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1)) if len(parts) > 1 \
+            else parts[0]
+    t0 = time.perf_counter()
+    res = model.reads_forward(h0=h0, want_probs=False)
+    _tic("forward", t0)
+    return recs, site_begin, res["mm"], res["ml"], n, n_batches
+
+
+def _reader_thread(rd, q):
+    """Inflates and indexes the next pieces while the GPU works on the current one."""
     try:
-        rd = BamReader(path, threads=max(1, args.threads))
-        q.put(("header", rd.header_text, rd.references))
-        batch, bidx, run = [], 0, []
-        for rec in rd:
-            batch.append(rec)
-            if len(batch) == args.holes_batch:
-                if parallel.owns_holebatch(bidx, rank, world):
-                    run.append(batch)
-                    if len(run) == group:
-                        q.put(("reads", [r for b in run for r in b]))
-                        run = []
-                batch, bidx = [], bidx + 1
-        if batch and parallel.owns_holebatch(bidx, rank, world):
-            run.append(batch)
-        if run:
-            q.put(("reads", [r for b in run for r in b]))
-        rd.close()
+        t0 = time.perf_counter()
+        for piece in rd:
+            _tic("reader", t0)
+            q.put(("piece", piece))
+            t0 = time.perf_counter()
         q.put(("done",))
     except Exception as e:  # surface reader failures to the main thread
         q.put(("error", e))
 
 
-def _writer_thread(wr, q, rm_pulse, mod_base_is_c, counts, err):
-    """Tags and writes the reads of finished device calls (reference _worker_write_modbam,
+def _writer_thread(wr, q, keep_pulse, mod_base_is_c, counts, err):
+    """Re-tags and writes the records of finished pieces (reference _worker_write_modbam,
     call_modifications.py:410-462)."""
     try:
         while True:
             msg = q.get()
             if msg is None:
                 return
-            reads, per_read = msg
-            for rec, pred in zip(reads, per_read):
-                raw, mm_flag = tag_read(rec, pred, rm_pulse, mod_base_is_c)
-                wr.write_raw(raw)
-                counts[2] += 1
-                counts[3] += mm_flag
+            piece, recs, site_begin, mm, ml = msg
+            t0 = time.perf_counter()
+            if not mod_base_is_c:  # the reference counts C's only (_bam2modbam.py:187-199): assertion -> no tags
+                mm = ml = None
+            data, with_mm = tag_records(piece, recs, keep_pulse, site_begin, mm, ml)
+            wr.bg.write(data)
+            counts[2] += len(recs)
+            counts[3] += with_mm
+            _tic("tag+write", t0)
     except Exception as e:
         err.append(e)
         while q.get() is not None:  # keep draining so the producer never blocks
@@ -190,10 +240,14 @@ def call_mods(args):
     if str2bool(args.is_map) or str2bool(args.is_stds):
         raise ValueError("--is_map/--is_stds features are not extracted by ccsmeth_b200 (SURVEY.md section 8f)")
     rank, world, local = parallel.init_from_env()
+    TIMING.clear()
     out_dir = os.path.dirname(os.path.abspath(args.output))
     os.makedirs(out_dir, exist_ok=True)
     out_modbam = args.output + (".modbam.bam" if world == 1 else ".rank%d.modbam.bam" % rank)
+    t_load = time.perf_counter()
     model = load_model(args.model_file, args, device=local, precision=getattr(args, "precision", None))
+    model._ensure_handle()
+    _tic("model_load", t_load)
     # seed the process that draws h0, after model construction (which itself consumes the generator); the
     # reference seeds only its parent process (:479-481), so its workers' h0 streams are not reproducible
     torch.manual_seed(args.tseed + rank)
@@ -203,19 +257,20 @@ def call_mods(args):
     holeids_e = _get_holes(args.holeids_e) if args.holeids_e else None
     holeids_ne = _get_holes(args.holeids_ne) if args.holeids_ne else None
 
-    group = max(1, getattr(args, "device_batch", 16))
-    q = queue.Queue(maxsize=3)
-    th = threading.Thread(target=_reader_thread, args=(args.input, args, rank, world, q, group), daemon=True)
+    threads = max(1, args.threads)
+    flt = _lib.BamFilter(1 if args.mode == "align" else 0, args.mapq, 1 if args.no_supplementary else 0,
+                         1 if str2bool(args.skip_unmapped) else 0, 1 if str2bool(args.is_sn) else 0)
+    # a piece = `device_batch` hole-batches' worth of compressed bytes (about 3 MB per 50 HiFi reads)
+    rd = BamPieceReader(args.input, flt, threads=threads,
+                        piece_bytes=max(1, getattr(args, "device_batch", 16)) * args.holes_batch * 65536,
+                        align_to=args.holes_batch)
+    wr = BamWriter(out_modbam, add_pg_line(rd.header_text, VERSION, " ".join(sys.argv)), rd.references, threads=threads)
+    q = queue.Queue(maxsize=2)
+    th = threading.Thread(target=_reader_thread, args=(rd, q), daemon=True)
     th.start()
-    msg = q.get()
-    if msg[0] == "error":
-        raise msg[1]
-    _, header_text, references = msg
-    wr = BamWriter(out_modbam, add_pg_line(header_text, VERSION, " ".join(sys.argv)), references,
-                   threads=max(1, args.threads))
     counts = [0, 0, 0, 0]
-    wq, werr = queue.Queue(maxsize=3), []
-    wth = threading.Thread(target=_writer_thread, args=(wr, wq, not args.keep_pulse, mod_base_is_c, counts, werr),
+    wq, werr = queue.Queue(maxsize=2), []
+    wth = threading.Thread(target=_writer_thread, args=(wr, wq, args.keep_pulse, mod_base_is_c, counts, werr),
                            daemon=True)
     wth.start()
     try:
@@ -225,12 +280,12 @@ def call_mods(args):
                 break
             if msg[0] == "error":
                 raise msg[1]
-            reads = msg[1]
-            per_read, n_sites, n_batches = call_reads(model, reads, motifs, args, holeids_e, holeids_ne,
-                                                      holes_batch=args.holes_batch)
+            piece = msg[1]
+            recs, site_begin, mm, ml, n_sites, n_batches = call_piece(model, piece, motifs, args, rank, world,
+                                                                      holeids_e, holeids_ne)
             counts[0] += n_sites
             counts[1] += n_batches
-            wq.put((reads, per_read))
+            wq.put((piece, recs, site_begin, mm, ml))
             if werr:
                 raise werr[0]
     finally:
@@ -239,11 +294,15 @@ def call_mods(args):
     if werr:
         raise werr[0]
     wr.close()
+    rd.close()
     total = parallel.allreduce_counts(counts)
     if rank == 0:
         dt = time.time() - t0
         sys.stderr.write("[call_mods] %d sites in %d model batches(%d), wrote %d reads, in which %d were added mm "
                          "tags; %.1f s, %d rank(s)\n" % (total[0], total[1], args.batch_size, total[2], total[3], dt, world))
+        if os.environ.get("CCSM_TIMING"):
+            sys.stderr.write("[call_mods] stage seconds (threads overlap): %s\n" %
+                             ", ".join("%s %.3f" % kv for kv in sorted(TIMING.items())))
     return dict(zip(("sites", "model_batches", "reads_written", "reads_with_mm"), total)), out_modbam
 
 

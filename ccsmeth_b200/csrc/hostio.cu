@@ -188,3 +188,251 @@ int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// BAM record indexing and re-tagging (SAM/BAM spec 4.2): the per-read host work of the call_mods pipeline that
+// remains once feature extraction runs on the device -- finding each read's sequence / kinetics arrays inside the
+// inflated records (reference extract_features.py:88-126 through pysam) and writing the records back with MM/ML
+// (reference call_modifications.py:230-266, _bam2modbam.py:211-226).
+// ------------------------------------------------------------------------------------------------------------
+namespace ccsm {
+
+static inline int32_t rd_i32(const uint8_t* p) {
+  return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+}
+static inline uint32_t rd_u16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+// size in bytes of the aux field starting at p (p[0..1] = tag, p[2] = type), or -1 if malformed / beyond end
+static int64_t aux_size(const uint8_t* p, const uint8_t* end) {
+  if (p + 3 > end) return -1;
+  const uint8_t ty = p[2];
+  int64_t sz;
+  switch (ty) {
+    case 'A': case 'c': case 'C': sz = 3 + 1; break;
+    case 's': case 'S': sz = 3 + 2; break;
+    case 'i': case 'I': case 'f': sz = 3 + 4; break;
+    case 'Z': case 'H': {
+      const uint8_t* q = p + 3;
+      while (q < end && *q) ++q;
+      if (q >= end) return -1;
+      sz = (q - p) + 1;
+      break;
+    }
+    case 'B': {
+      if (p + 8 > end) return -1;
+      const uint8_t sub = p[3];
+      const int64_t cnt = (uint32_t)rd_i32(p + 4);
+      const int w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+      if (!w) return -1;
+      sz = 8 + cnt * w;
+      break;
+    }
+    default: return -1;
+  }
+  return (p + sz <= end) ? sz : -1;
+}
+
+static bool aux_int(const uint8_t* p, int32_t* v) {
+  switch (p[2]) {
+    case 'c': *v = (int8_t)p[3]; return true;
+    case 'C': *v = p[3]; return true;
+    case 's': *v = (int16_t)rd_u16(p + 3); return true;
+    case 'S': *v = (int32_t)rd_u16(p + 3); return true;
+    case 'i': case 'I': *v = rd_i32(p + 3); return true;
+    default: return false;
+  }
+}
+
+}  // namespace ccsm
+
+extern "C" {
+
+int ccsm_bam_index(const uint8_t* buf, int64_t n_bytes, const ccsm_bam_filter* f, ccsm_bam_rec* recs, int32_t max_recs,
+                   ccsm_read* descs, int32_t* n_recs, int32_t* n_descs, int64_t* consumed) {
+  if (!buf || n_bytes < 0 || !f || !recs || !descs || !n_recs || !n_descs || !consumed || max_recs < 0) {
+    set_error("ccsm_bam_index: bad argument");
+    return CCSM_EINVAL;
+  }
+  int64_t p = 0;
+  int32_t nr = 0, nd = 0;
+  while (p + 4 <= n_bytes && nr < max_recs) {
+    const int64_t len = rd_i32(buf + p);
+    if (len < 32) {
+      set_error("ccsm_bam_index: malformed record (block_size %lld) at offset %lld", (long long)len, (long long)p);
+      return CCSM_EINVAL;
+    }
+    if (p + 4 + len > n_bytes) break;  // incomplete: the caller carries the tail over
+    const uint8_t* r = buf + p + 4;
+    const uint8_t* end = r + len;
+    ccsm_bam_rec& rec = recs[nr];
+    rec.off = p;
+    rec.len = (int32_t)len;
+    const int l_name = r[8];
+    rec.mapq = r[9];
+    rec.n_cigar = (int32_t)rd_u16(r + 12);
+    rec.flag = (int32_t)rd_u16(r + 14);
+    rec.l_seq = rd_i32(r + 16);
+    const int64_t seq_off = 32 + l_name + 4LL * rec.n_cigar;
+    const int64_t aux_off = seq_off + (rec.l_seq + 1) / 2 + rec.l_seq;
+    if (rec.l_seq < 0 || aux_off > len) {
+      set_error("ccsm_bam_index: record at offset %lld is inconsistent", (long long)p);
+      return CCSM_EINVAL;
+    }
+    rec.aux_off = (int32_t)aux_off;
+    rec.read_idx = -1;
+    // read-level filters of the reference extractor (extract_features.py:269-288)
+    bool use = true;
+    if (f->mode_align) {
+      if (rec.flag & (0x4 | 0x100 | 0x400)) use = false;
+      if (f->no_supplementary && (rec.flag & 0x800)) use = false;
+      if (rec.mapq < f->mapq) use = false;
+    }
+    // aux scan: kinetics arrays (B:C of l_seq entries), pass counts, sn
+    const uint8_t* a = r + aux_off;
+    int64_t koff[4] = {-1, -1, -1, -1};
+    int32_t fn = 0, rn = 0;
+    bool has_fn = false, has_rn = false;
+    float sn[4] = {0.f, 0.f, 0.f, 0.f};
+    bool bad_kin = false;
+    while (a < end) {
+      const int64_t sz = aux_size(a, end);
+      if (sz < 0) {
+        set_error("ccsm_bam_index: bad aux field in the record at offset %lld", (long long)p);
+        return CCSM_EINVAL;
+      }
+      const char t0 = (char)a[0], t1 = (char)a[1];
+      int k = -1;
+      if (t0 == 'f' && t1 == 'i') k = 0;
+      else if (t0 == 'r' && t1 == 'i') k = 1;
+      else if (t0 == 'f' && t1 == 'p') k = 2;
+      else if (t0 == 'r' && t1 == 'p') k = 3;
+      if (k >= 0) {
+        if (a[2] == 'B' && a[3] == 'C') {
+          if (rd_i32(a + 4) == rec.l_seq) koff[k] = (a + 8) - buf;
+          else bad_kin = true;  // incomplete kinetics: the reference skips the read (extract_features.py:321-326)
+        } else {
+          set_error("ccsm_bam_index: tag %c%c is not a B:C (uint8) array; ccsmeth_b200 reads CodecV1 kinetics", t0, t1);
+          return CCSM_EUNSUPPORTED;
+        }
+      } else if (t0 == 'f' && t1 == 'n') {
+        has_fn = aux_int(a, &fn);
+      } else if (t0 == 'r' && t1 == 'n') {
+        has_rn = aux_int(a, &rn);
+      } else if (t0 == 's' && t1 == 'n' && a[2] == 'B' && a[3] == 'f') {
+        const int cnt = rd_i32(a + 4);
+        for (int q = 0; q < 4 && q < cnt; ++q) memcpy(&sn[q], a + 8 + 4 * q, 4);
+      }
+      a += sz;
+    }
+    if (use && !bad_kin && rec.l_seq > 0 && koff[0] >= 0 && koff[1] >= 0 && koff[2] >= 0 && koff[3] >= 0) {
+      ccsm_read& d = descs[nd];
+      memset(&d, 0, sizeof(d));
+      d.seq_off = (r + seq_off) - buf;
+      d.fi_off = koff[0]; d.ri_off = koff[1]; d.fp_off = koff[2]; d.rp_off = koff[3];
+      d.len = rec.l_seq;
+      if (has_fn && has_rn) { d.fn = fn; d.rn = rn; }  // both or neither (extract_features.py:113-117)
+      const bool reverse = rec.flag & 0x10;
+      d.flags = CCSM_READ_SEQ_4BIT | (reverse ? CCSM_READ_REVERSE : 0);
+      int32_t lo = 0, hi = rec.l_seq;
+      if (f->mode_align && f->skip_unmapped && rec.n_cigar > 0) {
+        // aligned part of the query = sequence minus the soft clips (pysam query_alignment_start / _end)
+        const uint8_t* c = r + 32 + l_name;
+        int32_t qs = 0, qe = rec.l_seq;
+        for (int i = 0; i < rec.n_cigar; ++i) {
+          const uint32_t v = (uint32_t)rd_i32(c + 4 * i);
+          if ((v & 15) == 5) continue;
+          if ((v & 15) == 4) qs += (int32_t)(v >> 4);
+          else break;
+        }
+        for (int i = rec.n_cigar - 1; i >= 0; --i) {
+          const uint32_t v = (uint32_t)rd_i32(c + 4 * i);
+          if ((v & 15) == 5) continue;
+          if ((v & 15) == 4) qe -= (int32_t)(v >> 4);
+          else break;
+        }
+        if (reverse) { lo = rec.l_seq - qe; hi = rec.l_seq - qs; }  // extract_features.py:296-301
+        else { lo = qs; hi = qe; }
+      }
+      d.win_lo = lo;
+      d.win_hi = hi;
+      if (f->want_sn) memcpy(d.sn, sn, sizeof(sn));
+      rec.read_idx = nd++;
+    }
+    p += 4 + len;
+    ++nr;
+  }
+  *n_recs = nr;
+  *n_descs = nd;
+  *consumed = p;
+  return CCSM_OK;
+}
+
+int64_t ccsm_bam_tag_records(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t n_recs, int32_t keep_pulse,
+                             const int64_t* site_begin, const int32_t* mm, const uint8_t* ml, uint8_t* out,
+                             int64_t out_cap, int32_t* n_with_mm) {
+  if (!buf || !recs || n_recs < 0 || !site_begin || !out || !n_with_mm) {
+    set_error("ccsm_bam_tag_records: bad argument");
+    return CCSM_EINVAL;
+  }
+  int64_t o = 0;
+  int32_t with_mm = 0;
+  for (int32_t i = 0; i < n_recs; ++i) {
+    const ccsm_bam_rec& rec = recs[i];
+    const uint8_t* r = buf + rec.off + 4;
+    const uint8_t* end = r + rec.len;
+    const int64_t ns = rec.read_idx >= 0 ? site_begin[rec.read_idx + 1] - site_begin[rec.read_idx] : 0;
+    // worst case: the record itself + "MMZC+m?," + 11 chars per delta + ";\0" + "MLBC" + count + bytes
+    if (o + 4 + rec.len + 32 + ns * 13 > out_cap) {
+      set_error("ccsm_bam_tag_records: output buffer too small");
+      return CCSM_EINVAL;
+    }
+    uint8_t* w0 = out + o;
+    uint8_t* w = w0 + 4;
+    memcpy(w, r, (size_t)rec.aux_off);
+    w += rec.aux_off;
+    const uint8_t* a = r + rec.aux_off;
+    while (a < end) {
+      const int64_t sz = aux_size(a, end);
+      if (sz < 0) {
+        set_error("ccsm_bam_tag_records: bad aux field in record %d", i);
+        return CCSM_EINVAL;
+      }
+      const char t0 = (char)a[0], t1 = (char)a[1];
+      const bool is_mod = t0 == 'M' && (t1 == 'M' || t1 == 'L');                       // _bam2modbam.py:215-216
+      const bool is_pulse = (t0 == 'f' || t0 == 'r') && (t1 == 'i' || t1 == 'p');      // :217-218
+      if (!(is_mod || (is_pulse && !keep_pulse))) {
+        memcpy(w, a, (size_t)sz);
+        w += sz;
+      }
+      a += sz;
+    }
+    if (ns > 0 && mm && ml) {
+      const int64_t b = site_begin[rec.read_idx];
+      memcpy(w, "MMZC+m?,", 8);
+      w += 8;
+      for (int64_t k = 0; k < ns; ++k) {
+        char tmp[12];
+        int len = 0;
+        uint32_t v = (uint32_t)mm[b + k];
+        do { tmp[len++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (len) *w++ = (uint8_t)tmp[--len];
+        *w++ = (k + 1 < ns) ? ',' : ';';
+      }
+      *w++ = 0;
+      memcpy(w, "MLBC", 4);
+      w += 4;
+      const uint32_t cnt = (uint32_t)ns;
+      for (int k = 0; k < 4; ++k) *w++ = (uint8_t)(cnt >> (8 * k));
+      memcpy(w, ml + b, (size_t)ns);
+      w += ns;
+      ++with_mm;
+    }
+    const uint32_t blen = (uint32_t)(w - w0 - 4);
+    for (int k = 0; k < 4; ++k) w0[k] = (uint8_t)(blen >> (8 * k));
+    o += 4 + blen;
+  }
+  *n_with_mm = with_mm;
+  return o;
+}
+
+}  // extern "C"

@@ -224,6 +224,39 @@ int64_t ccsm_bgzf_deflate_bound(int64_t src_bytes);
 int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, int64_t dst_cap, int32_t level,
                           int32_t threads);
 
+/* ---- host I/O helpers: BAM record indexing and re-tagging (SAM/BAM spec 4.2) -------------------------------
+ * ccsm_bam_index walks the complete alignment records in an inflated BAM byte stream `buf` (positioned at a
+ * record boundary) and fills, per record, a ccsm_bam_rec, and per read that takes part in calling, a ccsm_read
+ * whose offsets address `buf` itself -- so `buf` is the blob ccsm_reads_extract_host takes, with no copy.  It stands
+ * in for the pysam accessors of reference extract_features.py:88-126 and the read-level filters of :269-288,321-326.
+ * *consumed = bytes of complete records seen (the caller carries the tail over to the next piece).
+ * ccsm_bam_tag_records writes the records back (each with its 4-byte block_size) without MM/ML -- and without
+ * fi/fp/ri/rp unless keep_pulse -- and, for read r with sites [site_begin[r], site_begin[r+1]), appends
+ * "MM:Z:C+m?,<mm...>;" and "ML:B:C,<ml...>" (reference _bam2modbam.py:211-226, call_modifications.py:230-266);
+ * pass mm = ml = NULL to write no tags at all.  Returns bytes written (or a negative CCSM_E* code). */
+typedef struct ccsm_bam_rec {
+  int64_t off;        /* offset of the record's block_size field in buf */
+  int32_t len;        /* block_size */
+  int32_t aux_off;    /* offset of the first aux field, from the start of the record body (off + 4) */
+  int32_t flag, mapq, l_seq, n_cigar;
+  int32_t read_idx;   /* index into the ccsm_read array, or -1: the read takes no part (filtered / no kinetics) */
+  int32_t pad_;
+} ccsm_bam_rec;
+
+typedef struct ccsm_bam_filter {
+  int32_t mode_align;        /* --mode align: drop unmapped / secondary / duplicate reads, apply mapq */
+  int32_t mapq;              /* --mapq */
+  int32_t no_supplementary;  /* --no_supplementary */
+  int32_t skip_unmapped;     /* --skip_unmapped yes: only sites inside the aligned part of the query */
+  int32_t want_sn;           /* --is_sn yes: copy the sn tag */
+} ccsm_bam_filter;
+
+int     ccsm_bam_index(const uint8_t* buf, int64_t n_bytes, const ccsm_bam_filter* f, ccsm_bam_rec* recs,
+                       int32_t max_recs, ccsm_read* descs, int32_t* n_recs, int32_t* n_descs, int64_t* consumed);
+int64_t ccsm_bam_tag_records(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t n_recs, int32_t keep_pulse,
+                             const int64_t* site_begin, const int32_t* mm, const uint8_t* ml, uint8_t* out,
+                             int64_t out_cap, int32_t* n_with_mm);
+
 /* Introspection used by tests: copies the last layer-stack output of the most recent forward chunk.
  * Returns the number of floats written (<= cap) or a negative error. */
 int64_t ccsm_debug_last_rnn_out(ccsm_model* m, float* host, int64_t cap);

@@ -1,0 +1,116 @@
+"""Native piece-wise BAM streaming (ccsmeth_b200/bamstream.py over ccsm_bgzf_* / ccsm_bam_* in libccsm) against the
+record-level Python implementation (bamio.BamRecord, extract_features.pack_reads, call_mods.tag_read), which is itself
+pinned on the reference's fixtures in tests/test_demo_cpu.py.  No GPU needed: these are host helpers."""
+import os
+
+import numpy as np
+import pytest
+
+from ccsmeth_b200 import _lib, call_mods as cm
+from ccsmeth_b200.bamio import BamReader, BamWriter
+from ccsmeth_b200.bamstream import BamPieceReader, tag_records
+from ccsmeth_b200.extract_features import pack_reads
+from tests.bamsynth import random_read
+from tests.conftest import GOLDEN, load_npz
+
+DEMO = os.path.join(GOLDEN, "demo", "hg002.chr20_demo.hifi.bam")
+
+
+def _args(**kw):
+    a = cm.build_parser().parse_args(["-i", DEMO, "-m", "x.ckpt", "-o", "out"])
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def _filter(args):
+    return _lib.BamFilter(1 if args.mode == "align" else 0, args.mapq, 1 if args.no_supplementary else 0,
+                          1 if args.skip_unmapped == "yes" else 0, 0)
+
+
+def _check_pieces(path, args, piece_bytes, align_to):
+    recs_py = list(BamReader(path))
+    rd = BamPieceReader(path, _filter(args), threads=3, piece_bytes=piece_bytes, align_to=align_to)
+    k = 0
+    pieces = list(rd)
+    for pi, p in enumerate(pieces):
+        n = len(p.recs)
+        assert p.first == k
+        if pi + 1 < len(pieces):
+            assert n % align_to == 0
+        b = pack_reads(recs_py[k:k + n], args)
+        assert len(b) == len(p.descs)
+        assert list(np.nonzero(p.recs["read_idx"] >= 0)[0]) == b.index
+        for name in ("len", "fn", "rn", "flags", "win_lo", "win_hi"):
+            assert np.array_equal(b.descs[name], p.descs[name]), name
+        for name in ("seq_off", "fi_off", "ri_off", "fp_off", "rp_off"):
+            for i in range(len(b)):
+                L = int(b.descs["len"][i])
+                w = (L + 1) // 2 if name == "seq_off" else L
+                assert np.array_equal(b.blob[b.descs[name][i]:b.descs[name][i] + w],
+                                      p.buf[p.descs[name][i]:p.descs[name][i] + w])
+        k += n
+    assert k == len(recs_py)
+    return pieces, recs_py
+
+
+@pytest.mark.parametrize("piece_bytes,align_to", [(48 << 20, 50), (1 << 20, 50), (300000, 7), (70000, 1)])
+def test_pieces_cover_the_demo_like_the_record_reader(piece_bytes, align_to):
+    _check_pieces(DEMO, _args(), piece_bytes, align_to)
+
+
+def test_retagging_matches_the_record_level_writer():
+    g = load_npz("demo_callmods.npz")
+    pieces, recs_py = _check_pieces(DEMO, _args(), 1 << 20, 50)
+    off = 0
+    k = 0
+    for p in pieces:
+        n = len(p.recs)
+        counts = g["n_sites_per_read"][k:k + n]
+        site_begin = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+        ns = int(site_begin[-1])
+        mm = g["mm"][off:off + ns].astype(np.int32)
+        ml = g["ml"][off:off + ns].astype(np.uint8)
+        for keep in (False, True):
+            out, with_mm = tag_records(p, p.recs, keep, site_begin, mm, ml)
+            exp = []
+            for j, r in enumerate(recs_py[k:k + n]):
+                s, e = site_begin[j], site_begin[j + 1]
+                pred = (np.zeros(e - s, dtype=np.int64), np.zeros(e - s, dtype=np.float32), mm[s:e], ml[s:e]) if e > s else None
+                raw, _ = cm.tag_read(r, pred, rm_pulse=not keep)
+                exp.append(len(raw).to_bytes(4, "little") + raw)
+            assert bytes(out) == b"".join(exp)
+            assert with_mm == int((counts > 0).sum())
+        off += ns
+        k += n
+
+
+def test_index_applies_align_mode_filters_and_softclip_windows(tmp_path):
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(9):
+        n = int(rng.integers(100, 900))
+        lc, rc = int(rng.integers(0, 30)), int(rng.integers(0, 30))
+        rev = bool(i % 2)
+        recs.append(random_read(rng, "a%d" % i, n, reverse=rev, flag=16 if rev else 0,
+                                cigar=((5, 3), (4, lc), (0, n - lc - rc), (4, rc)), mapq=60)[0])
+    recs.append(random_read(rng, "unmapped", 300, flag=4)[0])
+    recs.append(random_read(rng, "lowq", 300, flag=0, cigar=((0, 300),), mapq=0)[0])
+    recs.append(random_read(rng, "dup", 300, flag=1024, cigar=((0, 300),), mapq=60)[0])
+    path = str(tmp_path / "syn.bam")
+    wr = BamWriter(path, "@HD\tVN:1.6\n@SQ\tSN:chr1\tLN:100000\n", [("chr1", 100000)])
+    for r in recs:
+        wr.write_raw(r.raw)
+    wr.close()
+    for kw in ({"mode": "align"}, {"mode": "align", "skip_unmapped": "no"}, {"mode": "denovo"}):
+        pieces, _ = _check_pieces(path, _args(**kw), 1 << 20, 5)
+        kept = sum(len(p.descs) for p in pieces)
+        assert kept == (9 if kw["mode"] == "align" else 12)
+
+
+def test_truncated_file_is_an_error(tmp_path):
+    raw = open(DEMO, "rb").read()
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(Exception):
+        list(BamPieceReader(cut, _filter(_args()), threads=2, piece_bytes=1 << 20, align_to=1))

@@ -65,3 +65,36 @@ def test_call_holebatch_probabilities(ckpt_file):
     probs = np.concatenate(probs)
     assert probs.shape == g["prob1"].shape
     assert np.abs(probs - g["prob1"]).max() <= 1e-4  # north-star tolerance, whole demo, reference h0 stream
+
+
+def _tags_by_name(path):
+    out = {}
+    for r in BamReader(path):
+        out[r.query_name] = (r.get_tag("MM"), r.get_tag("ML").tobytes()) if r.has_tag("MM") else None
+    return out
+
+
+def test_pieces_and_rank_shards_give_the_same_modbam(tmp_path, ckpt_file, monkeypatch):
+    """The native piece pipeline must not depend on where the file is cut (--device_batch) nor on how hole-batches
+    are dealt to ranks: same MM/ML per read.  h0 = zeros so that every configuration sees the same initial state."""
+    base = ["-i", DEMO, "-m", ckpt_file, "--precision", "fp16x3", "--h0", "zeros", "--holes_batch", "10"]
+    one = cm.build_parser().parse_args(base + ["-o", str(tmp_path / "one")])
+    counts1, p1 = cm.call_mods(one)
+    ref = _tags_by_name(p1)
+    assert counts1["sites"] == 12691 and counts1["reads_written"] == 116
+    many = cm.build_parser().parse_args(base + ["-o", str(tmp_path / "many"), "--device_batch", "1"])
+    counts2, p2 = cm.call_mods(many)  # 10 reads x 64 KiB per piece -> several pieces
+    assert counts2 == counts1
+    assert _tags_by_name(p2) == ref
+    # two "ranks" run one after the other in this process (no process group: counts are per rank)
+    from ccsmeth_b200 import parallel
+    merged, sites = {}, 0
+    for rank in (0, 1):
+        monkeypatch.setattr(parallel, "init_from_env", lambda r=rank: (r, 2, 0))
+        monkeypatch.setattr(parallel, "allreduce_counts", lambda c: list(c))
+        a = cm.build_parser().parse_args(base + ["-o", str(tmp_path / "shard"), "--device_batch", "2"])
+        c, p = cm.call_mods(a)
+        assert p.endswith(".rank%d.modbam.bam" % rank)
+        merged.update(_tags_by_name(p))
+        sites += c["sites"]
+    assert sites == 12691 and merged == ref
