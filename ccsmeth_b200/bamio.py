@@ -128,7 +128,7 @@ class BgzfWriter:
             self.batch = 16 * threads
 
     def write(self, data):
-        self.buf += data
+        self.buf += memoryview(data)  # bytes, bytearray or a uint8 numpy array
         if len(self.buf) >= self.batch * self.BLOCK:
             self._flush(final=False)
 

@@ -85,6 +85,34 @@ def test_retagging_matches_the_record_level_writer():
         k += n
 
 
+def test_retagged_pieces_written_through_the_bgzf_writer_read_back(tmp_path):
+    g = load_npz("demo_callmods.npz")
+    rd = BamPieceReader(DEMO, _filter(_args()), threads=3, piece_bytes=1 << 20, align_to=50)
+    out = str(tmp_path / "o.bam")
+    wr = BamWriter(out, rd.header_text, rd.references, threads=3)
+    off = k = 0
+    for p in rd:
+        counts = g["n_sites_per_read"][k:k + len(p.recs)]
+        sb = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+        ns = int(sb[-1])
+        data, _ = tag_records(p, p.recs, False, sb, g["mm"][off:off + ns].astype(np.int32), g["ml"][off:off + ns])
+        wr.bg.write(data)  # a uint8 numpy array, as the call_mods writer thread passes it
+        off += ns
+        k += len(p.recs)
+    wr.close()
+    back = list(BamReader(out, threads=2))
+    assert [r.query_name for r in back] == list(g["names"])
+    off = 0
+    for r, n in zip(back, g["n_sites_per_read"]):
+        if n:
+            assert [int(x) for x in r.get_tag("MM")[5:-1].split(",")] == list(g["mm"][off:off + n])
+            assert np.array_equal(r.get_tag("ML"), g["ml"][off:off + n])
+        else:
+            assert not r.has_tag("MM")
+        assert not r.has_tag("fi")
+        off += n
+
+
 def test_index_applies_align_mode_filters_and_softclip_windows(tmp_path):
     rng = np.random.default_rng(3)
     recs = []
