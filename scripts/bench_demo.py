@@ -15,8 +15,8 @@ from ccsmeth_b200.bamio import BamReader, BamWriter
 
 g = dict(np.load(os.path.join(ROOT, "tests", "golden", "demo_callmods.npz")))
 ck = dict(np.load(os.path.join(ROOT, "tests", "golden", "ckpt_att2s_v3.npz")))
-out_dir = os.path.join(ROOT, "gpurun_out")
-os.makedirs(out_dir, exist_ok=True)
+import tempfile
+out_dir = tempfile.mkdtemp(prefix="ccsm_demo_")  # nothing large goes under gpurun_out/ (it travels back)
 ckpt = os.path.join(out_dir, "model_v3.ckpt")
 torch.save(OrderedDict((k, torch.from_numpy(v)) for k, v in ck.items()), ckpt)
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
@@ -45,8 +45,7 @@ res = {"workload": "demo/hg002.chr20_demo.hifi.bam call_mods end to end (BAM in 
        "speedup_vs_reference_chain": float(g["ref_cpu_seconds"]) / best, "host_cores": os.cpu_count()}
 
 if rep > 0:
-    import tempfile
-    tmp = tempfile.mkdtemp(prefix="ccsm_demo_")  # not under gpurun_out/: only small files travel back
+    tmp = out_dir
     big = os.path.join(tmp, "demo_x%d.bam" % rep)
     rd = BamReader(demo)
     recs = list(rd)
