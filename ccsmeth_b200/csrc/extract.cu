@@ -66,14 +66,44 @@ __device__ __forceinline__ int fwd_code(const uint8_t* blob, const ccsm_read& r,
   return c;
 }
 
-// is position p the start of a motif whose modified base is a callable site?  (extract_features.py:336-343)
-__device__ __forceinline__ bool site_at(const ExParams& P, const ccsm_read& r, int p) {
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- sequence tiles in shared memory -----------------------------------------------------------------------
+// Both per-read kernels walk the read in tiles of SEQ_TILE forward positions.  A tile (plus a halo long enough for
+// the longest motif and mod_loc) is first expanded into one base code per byte in shared memory -- the only place
+// that knows about 4-bit packing and reverse-strand storage -- and sites / C's are then flagged from there.
+constexpr int SEQ_TILE = 4096;
+constexpr int SEQ_HALO = 16;
+
+__device__ __forceinline__ void stage_codes(const ExParams& P, const ccsm_read& r, int t0, uint8_t* s_codes) {
+  const int n = min(SEQ_TILE + SEQ_HALO, r.len - t0);
+  if ((r.flags & CCSM_READ_SEQ_4BIT) && !(r.flags & CCSM_READ_REVERSE)) {
+    // forward 4-bit: t0 is even, so stored byte (t0 >> 1) + i holds positions t0 + 2i, t0 + 2i + 1
+    const uint8_t* src = P.blob + r.seq_off + (t0 >> 1);
+    const int nb = (n + 1) >> 1;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      const int b = src[i];
+      s_codes[2 * i] = (uint8_t)nib_to_code(b >> 4);
+      s_codes[2 * i + 1] = (uint8_t)nib_to_code(b & 15);  // position t0 + n may get a pad nibble: never read
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_codes[i] = (uint8_t)fwd_code(P.blob, r, t0 + i);
+  }
+}
+
+// is tile-relative position q (forward position t0 + q) the start of a motif whose modified base is a callable site?
+// (extract_features.py:336-343; needs codes up to q + motif_len - 1 < SEQ_TILE + SEQ_HALO)
+__device__ __forceinline__ bool site_in_tile(const ExParams& P, const ccsm_read& r, int t0, int q, const uint8_t* s_codes) {
+  const int p = t0 + q;
   if (p + P.motif_len > r.len) return false;
   uint32_t w = 0;
   for (int k = 0; k < P.motif_len; ++k) {
-    const int c = fwd_code(P.blob, r, p + k);
+    const uint32_t c = s_codes[q + k];
     if (c > 3) return false;
-    w |= (uint32_t)c << (4 * k);
+    w |= c << (4 * k);
   }
   bool hit = false;
   for (int k = 0; k < P.n_motifs; ++k) hit |= (w == P.motif_code[k]);
@@ -83,13 +113,16 @@ __device__ __forceinline__ bool site_at(const ExParams& P, const ccsm_read& r, i
   return loc >= P.nb && loc < r.len - P.nb && rl >= P.nb && rl < r.len - P.nb && loc >= r.win_lo && loc < r.win_hi;
 }
 
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // ---- kernel 1: one CTA per read -- normalisation statistics of the four kinetics arrays + site count
 struct SigStat { double shift, scale; };
+
+__device__ __forceinline__ void acc_code(int c, int decode, long long& S, long long& Q, int& mn, int& mx) {
+  const int v = decode ? code_to_frames(c) : c;
+  S += v;
+  Q += v * v;
+  mn = min(mn, v);
+  mx = max(mx, v);
+}
 
 __global__ void __launch_bounds__(256) read_scan_kernel(ExParams P, SigStat* __restrict__ stats,
                                                         int* __restrict__ site_cnt) {
@@ -97,20 +130,33 @@ __global__ void __launch_bounds__(256) read_scan_kernel(ExParams P, SigStat* __r
   const ccsm_read r = P.reads[r_idx];
   __shared__ long long s_sum[8], s_sq[8];
   __shared__ int s_min[8], s_max[8], s_cnt[8];
+  __shared__ __align__(16) uint8_t s_codes[SEQ_TILE + SEQ_HALO + 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t offs[4] = {r.fi_off, r.ri_off, r.fp_off, r.rp_off};  // order: ipd fwd, ipd rev, pw fwd, pw rev
   for (int sig = 0; sig < 4; ++sig) {
-    const uint8_t* a = P.blob + offs[sig];
+    // order: ipd fwd, ipd rev, pw fwd, pw rev
+    const int64_t off = sig == 0 ? r.fi_off : sig == 1 ? r.ri_off : sig == 2 ? r.fp_off : r.rp_off;
     long long S = 0, Q = 0;
     int mn = 1 << 30, mx = -1;
     if (P.norm != CCSM_NORM_NONE) {
-      for (int i = threadIdx.x; i < r.len; i += blockDim.x) {
-        const int c = a[i];
-        const int v = P.decode ? code_to_frames(c) : c;
-        S += v;
-        Q += v * v;
-        mn = min(mn, v);
-        mx = max(mx, v);
+      // 16-byte loads over the aligned span covering [off, off + len); only the two end chunks are masked
+      // (the blob allocation is 16-byte aligned and padded by 16 bytes)
+      const uint8_t* a = P.blob + off;
+      const int mis = (int)(reinterpret_cast<uintptr_t>(a) & 15);
+      const uint4* A = reinterpret_cast<const uint4*>(a - mis);
+      const int nchunk = (r.len + mis + 15) >> 4;
+      for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
+        const uint4 v = __ldg(A + c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if (c > 0 && c < nchunk - 1) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) acc_code((w[k >> 2] >> (8 * (k & 3))) & 255, P.decode, S, Q, mn, mx);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int i = c * 16 + k - mis;
+            if (i >= 0 && i < r.len) acc_code((w[k >> 2] >> (8 * (k & 3))) & 255, P.decode, S, Q, mn, mx);
+          }
+        }
       }
     }
     S = warp_sum_ll(S);
@@ -147,7 +193,13 @@ __global__ void __launch_bounds__(256) read_scan_kernel(ExParams P, SigStat* __r
     __syncthreads();
   }
   int cnt = 0;
-  for (int p = threadIdx.x; p < r.len; p += blockDim.x) cnt += site_at(P, r, p) ? 1 : 0;
+  for (int t0 = 0; t0 < r.len; t0 += SEQ_TILE) {
+    stage_codes(P, r, t0, s_codes);
+    __syncthreads();
+    const int nq = min(SEQ_TILE, r.len - t0);
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) cnt += site_in_tile(P, r, t0, q, s_codes) ? 1 : 0;
+    __syncthreads();
+  }
   for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) s_cnt[warp] = cnt;
   __syncthreads();
@@ -204,6 +256,7 @@ __global__ void __launch_bounds__(256) site_emit_kernel(ExParams P, const long l
   if (site_off[r_idx + 1] == o0) return;
   __shared__ int s_ws[8], s_wc[8];
   __shared__ int s_cs, s_cc;  // running carries: sites, C's
+  __shared__ __align__(16) uint8_t s_codes[SEQ_TILE + SEQ_HALO + 16];
   if (threadIdx.x == 0) {
     s_cs = 0;
     int c0 = 0;  // C's in front of the first position the loop below looks at
@@ -212,35 +265,40 @@ __global__ void __launch_bounds__(256) site_emit_kernel(ExParams P, const long l
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < r.len; base += 256) {
-    const int p = base + threadIdx.x;
-    const bool in = p < r.len;
-    const bool is_site = in && site_at(P, r, p);
-    // MM deltas count C's of the forward read (_bam2modbam.py:187-203); the called base sits at p + mod_loc, so
-    // count C's at position q = p + mod_loc for q's own p (shift the C flag by mod_loc to stay thread-local)
-    const int q = p + P.mod_loc;
-    const bool is_c = in && q < r.len && fwd_code(P.blob, r, q) == 1;
-    const unsigned ms = __ballot_sync(0xffffffffu, is_site), mc = __ballot_sync(0xffffffffu, is_c);
-    const unsigned below = (1u << lane) - 1u;
-    if (lane == 0) { s_ws[warp] = __popc(ms); s_wc[warp] = __popc(mc); }
+  for (int t0 = 0; t0 < r.len; t0 += SEQ_TILE) {
+    stage_codes(P, r, t0, s_codes);
     __syncthreads();
-    int ps = s_cs, pc = s_cc;
-    for (int w = 0; w < warp; ++w) { ps += s_ws[w]; pc += s_wc[w]; }
-    ps += __popc(ms & below);
-    pc += __popc(mc & below);
-    if (is_site) {
-      site_read[o0 + ps] = r_idx;
-      site_loc[o0 + ps] = q;
-      site_cord[o0 + ps] = pc;  // C's strictly before q (positions q' = p' + mod_loc with p' < p)
+    const int nq = min(SEQ_TILE, r.len - t0);
+    for (int base = 0; base < nq; base += 256) {
+      const int q = base + threadIdx.x;
+      const bool in = q < nq;
+      const bool is_site = in && site_in_tile(P, r, t0, q, s_codes);
+      // MM deltas count C's of the forward read (_bam2modbam.py:187-203); the called base sits at p + mod_loc, so
+      // flag the C at position p + mod_loc in p's own thread (mod_loc < motif_len <= 8 stays inside the halo)
+      const int pc_pos = t0 + q + P.mod_loc;
+      const bool is_c = in && pc_pos < r.len && s_codes[q + P.mod_loc] == 1;
+      const unsigned ms = __ballot_sync(0xffffffffu, is_site), mc = __ballot_sync(0xffffffffu, is_c);
+      const unsigned below = (1u << lane) - 1u;
+      if (lane == 0) { s_ws[warp] = __popc(ms); s_wc[warp] = __popc(mc); }
+      __syncthreads();
+      int ps = s_cs, pc = s_cc;
+      for (int w = 0; w < warp; ++w) { ps += s_ws[w]; pc += s_wc[w]; }
+      ps += __popc(ms & below);
+      pc += __popc(mc & below);
+      if (is_site) {
+        site_read[o0 + ps] = r_idx;
+        site_loc[o0 + ps] = pc_pos;
+        site_cord[o0 + ps] = pc;  // C's strictly before the called base
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int ts = 0, tc = 0;
+        for (int w = 0; w < 8; ++w) { ts += s_ws[w]; tc += s_wc[w]; }
+        s_cs += ts;
+        s_cc += tc;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int ts = 0, tc = 0;
-      for (int w = 0; w < 8; ++w) { ts += s_ws[w]; tc += s_wc[w]; }
-      s_cs += ts;
-      s_cc += tc;
-    }
-    __syncthreads();
   }
 }
 
@@ -256,49 +314,86 @@ __device__ __forceinline__ float norm_value(int v, const SigStat& st, int norm) 
   return (float)__ddiv_rn(rint(__dmul_rn(x, 1e6)), 1e6);  // np.around(x, 6): multiply, rint, divide
 }
 
-__global__ void __launch_bounds__(256) window_gather_kernel(ExParams P, const SigStat* __restrict__ stats,
-                                                            const int* __restrict__ site_read,
-                                                            const int* __restrict__ site_loc, long long s0, long long cn,
-                                                            FeatOut f, FeatOut rv) {
+// One thread per (site, strand) computes the 21-position window into shared memory; the CTA then writes each output
+// array as one contiguous, coalesced run (rows of GATHER_SITES consecutive sites).
+constexpr int GATHER_SITES = 64;
+
+__global__ void __launch_bounds__(2 * GATHER_SITES) window_gather_kernel(ExParams P, const SigStat* __restrict__ stats,
+                                                                         const int* __restrict__ site_read,
+                                                                         const int* __restrict__ site_loc, long long s0,
+                                                                         long long cn, FeatOut f, FeatOut rv) {
+  extern __shared__ float s_out[];  // [strand][array kmer, kpass, ipd, pw][site][L]
+  __shared__ float s_sn[GATHER_SITES][4];
   const int L = P.seq_len;
-  const long long total = cn * 2 * L;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int strand = (int)(idx / (cn * L));
-    const long long rem = idx - (long long)strand * cn * L;
-    const long long i = rem / L;
-    const int t = (int)(rem - i * L);
-    const int r_idx = site_read[s0 + i];
-    const int loc = site_loc[s0 + i];
-    const ccsm_read r = P.reads[r_idx];
-    const SigStat* st = stats + (size_t)r_idx * 4;
-    const FeatOut& o = strand ? rv : f;
-    int pos, code, ipd_c, pw_c;
-    if (strand == 0) {
-      pos = loc - P.nb + t;
-      code = fwd_code(P.blob, r, pos);
-      ipd_c = P.blob[r.fi_off + pos];
-      pw_c = P.blob[r.fp_off + pos];
-    } else {
-      // window on the reverse complement around len-1-(loc+rev_offset); kinetics of the reverse strand are
-      // indexed in that same coordinate, unflipped (extract_features.py:316,319,355-360)
-      pos = r.len - 1 - (loc + P.rev_offset) - P.nb + t;
-      const int c = fwd_code(P.blob, r, r.len - 1 - pos);
-      code = c < 4 ? 3 - c : 4;
-      ipd_c = P.blob[r.ri_off + pos];
-      pw_c = P.blob[r.rp_off + pos];
+  const int strand = threadIdx.x / GATHER_SITES, ls = threadIdx.x % GATHER_SITES;
+  const int per_arr = GATHER_SITES * L;
+  for (long long g0 = (long long)blockIdx.x * GATHER_SITES; g0 < cn; g0 += (long long)gridDim.x * GATHER_SITES) {
+    const long long i = g0 + ls;
+    if (i < cn) {
+      const int r_idx = site_read[s0 + i];
+      const int loc = site_loc[s0 + i];
+      const ccsm_read* rp = P.reads + r_idx;
+      const int len = rp->len, flags = rp->flags;
+      const SigStat st_ipd = stats[(size_t)r_idx * 4 + (strand ? 1 : 0)];
+      const SigStat st_pw = stats[(size_t)r_idx * 4 + (strand ? 3 : 2)];
+      const float npass = (float)(strand ? rp->rn : rp->fn);
+      // forward strand: window [loc - nb, loc + nb].  reverse strand: window on the reverse complement around
+      // len-1-(loc+rev_offset); its kinetics are indexed in that same coordinate, unflipped
+      // (extract_features.py:316,319,355-360)
+      const int w0 = strand ? len - 1 - (loc + P.rev_offset) - P.nb : loc - P.nb;
+      const uint8_t* ipd_a = P.blob + (strand ? rp->ri_off : rp->fi_off) + w0;
+      const uint8_t* pw_a = P.blob + (strand ? rp->rp_off : rp->fp_off) + w0;
+      const int64_t seq_off = rp->seq_off;
+      float* o_kmer = s_out + (strand * 4 + 0) * per_arr + ls * L;
+      float* o_kpass = s_out + (strand * 4 + 1) * per_arr + ls * L;
+      float* o_ipd = s_out + (strand * 4 + 2) * per_arr + ls * L;
+      float* o_pw = s_out + (strand * 4 + 3) * per_arr + ls * L;
+      for (int t = 0; t < L; ++t) {
+        // forward-read position whose base this window slot shows
+        const int fpos = strand ? len - 1 - (w0 + t) : w0 + t;
+        const int j = (flags & CCSM_READ_REVERSE) ? len - 1 - fpos : fpos;
+        int c;
+        if (flags & CCSM_READ_SEQ_4BIT) {
+          const int b = P.blob[seq_off + (j >> 1)];
+          c = nib_to_code((j & 1) ? (b & 15) : (b >> 4));
+        } else {
+          c = ascii_to_code(P.blob[seq_off + j]);
+        }
+        // complement once per strand flip: stored-reverse and reverse-strand window cancel each other
+        const bool comp = ((flags & CCSM_READ_REVERSE) != 0) != (strand != 0);
+        if (comp && c < 4) c = 3 - c;
+        const int ic = ipd_a[t], pc = pw_a[t];
+        o_kmer[t] = (float)c;
+        o_kpass[t] = npass;
+        o_ipd[t] = norm_value(P.decode ? code_to_frames(ic) : ic, st_ipd, P.norm);
+        o_pw[t] = norm_value(P.decode ? code_to_frames(pc) : pc, st_pw, P.norm);
+      }
+      if (strand == 0 && f.sns) {
+        // np.around(np.array(tag_sn, dtype=float), 6) (extract_features.py:328)
+        for (int k = 0; k < 4; ++k) s_sn[ls][k] = (float)__ddiv_rn(rint(__dmul_rn((double)rp->sn[k], 1e6)), 1e6);
+      }
     }
-    const int ipd_v = P.decode ? code_to_frames(ipd_c) : ipd_c;
-    const int pw_v = P.decode ? code_to_frames(pw_c) : pw_c;
-    const long long w = i * L + t;
-    o.kmer[w] = (float)code;
-    if (o.kpass) o.kpass[w] = (float)(strand ? r.rn : r.fn);
-    o.ipd[w] = norm_value(ipd_v, st[strand ? 1 : 0], P.norm);
-    o.pw[w] = norm_value(pw_v, st[strand ? 3 : 2], P.norm);
-    if (o.sns && t < 4) {
-      // np.around(np.array(tag_sn, dtype=float), 6) (extract_features.py:328)
-      o.sns[i * 4 + t] = (float)__ddiv_rn(rint(__dmul_rn((double)r.sn[t], 1e6)), 1e6);
+    __syncthreads();
+    const int rows = (int)min((long long)GATHER_SITES, cn - g0);
+    const int nval = rows * L;
+    const long long obase = g0 * L;
+    for (int k = threadIdx.x; k < nval; k += blockDim.x) {
+      f.kmer[obase + k] = s_out[0 * per_arr + k];
+      if (f.kpass) f.kpass[obase + k] = s_out[1 * per_arr + k];
+      f.ipd[obase + k] = s_out[2 * per_arr + k];
+      f.pw[obase + k] = s_out[3 * per_arr + k];
+      rv.kmer[obase + k] = s_out[4 * per_arr + k];
+      if (rv.kpass) rv.kpass[obase + k] = s_out[5 * per_arr + k];
+      rv.ipd[obase + k] = s_out[6 * per_arr + k];
+      rv.pw[obase + k] = s_out[7 * per_arr + k];
     }
+    if (f.sns)
+      for (int k = threadIdx.x; k < rows * 4; k += blockDim.x) {
+        const float v = s_sn[k >> 2][k & 3];
+        f.sns[g0 * 4 + k] = v;
+        if (rv.sns) rv.sns[g0 * 4 + k] = v;
+      }
+    __syncthreads();
   }
 }
 
@@ -402,11 +497,16 @@ static int launch_features(ccsm_model* m, int64_t s0, int64_t cn, const ccsm_str
     set_error("ccsm_reads_features: kmer / ipd_means / pw_means outputs are required");
     return CCSM_EINVAL;
   }
-  const long long total = cn * 2 * P.seq_len;
-  const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const size_t smem = (size_t)8 * GATHER_SITES * P.seq_len * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    CCSM_CUDA(cudaFuncSetAttribute(window_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GATHER_SITES * 32 * 4));
+    attr = true;
+  }
+  const int grid = (int)std::min<long long>((cn + GATHER_SITES - 1) / GATHER_SITES, 148LL * 8);
   const int pid = m->prof.begin(PROF_EX_GATHER, (double)cn, st);
-  window_gather_kernel<<<grid, 256, 0, st>>>(P, ex->stats.as<SigStat>(), ex->site_read.as<int>(),
-                                             ex->site_loc.as<int>(), s0, cn, f, r);
+  window_gather_kernel<<<grid, 2 * GATHER_SITES, smem, st>>>(P, ex->stats.as<SigStat>(), ex->site_read.as<int>(),
+                                                             ex->site_loc.as<int>(), s0, cn, f, r);
   m->prof.end(pid, st);
   count_launch();
   CCSM_CUDA(cudaGetLastError());
