@@ -64,3 +64,42 @@ def load_aggr_model(model_path, args, device=0):
     model = model.cuda(device)
     model.eval()
     return model
+
+
+def _call_modfreq_of_one_region(refpos2modinfo, args, model, h0=None):
+    """Drop-in for the reference's ``_call_modfreq_of_one_region`` (call_mods_freq_bam.py:423-442 and, in aggregate
+    mode, :308-420) with the pileup statistics, histograms, window building and the model on the device.
+
+    refpos2modinfo: {refpos: [(ML byte or probability, hap), ...]} as ``_readmods_to_bed_of_one_region`` builds it
+    (:457-540); probabilities are mapped back to their ML byte (``_cal_mod_prob`` is a bijection on 0..255).
+    Unlike the reference, the model is not rebuilt per region: pass the resident ``AggrAttRNN``.
+    Returns the reference's list of ``(refpos, info_all, info_hp1, info_hp2)`` with ``info = (cov, cnt_mod, freq)``
+    or None.  h0: optional per-group initial states; default = the reference's stream (one ``torch.randn`` per
+    1024-site slice, groups in the order all / hp1 / hp2)."""
+    refposes = np.array(sorted(refpos2modinfo.keys()), dtype=np.int64)
+    counts = np.array([len(refpos2modinfo[p]) for p in refposes], dtype=np.int64)
+    ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+    ml = np.empty(int(ptr[-1]), dtype=np.uint8)
+    hap = np.empty(int(ptr[-1]), dtype=np.uint8)
+    k = 0
+    for p in refposes:
+        for v, h in refpos2modinfo[p]:
+            ml[k] = v if isinstance(v, (int, np.integer)) else (0 if v <= 0 else int(round((v - 0.000001) * 256)))
+            hap[k] = h if 0 <= h <= 255 else 0
+            k += 1
+    n_high = model.pileup_begin(refposes, ptr, ml, hap, call_mode=args.call_mode, cov_cf=args.cov_cf,
+                                prob_cf=args.prob_cf, no_amb_cov=args.no_amb_cov, no_hap=args.no_hap)
+    if h0 is None and args.call_mode == "aggregate":
+        h0 = []
+        for nh in n_high:
+            t = torch.empty(2 * model.num_layers, nh, model.hidden_size)
+            for s in range(0, nh, AGGR_BATCH):
+                e = min(nh, s + AGGR_BATCH)
+                t[:, s:e] = torch.randn(2 * model.num_layers, e - s, model.hidden_size)
+            h0.append(t if nh else None)
+    cov, cnt, freq = model.pileup_finish(h0 if h0 is not None else (None, None, None))
+    out = []
+    for i, p in enumerate(refposes):
+        infos = [None if cov[g, i] == 0 else (int(cov[g, i]), float(cnt[g, i]), float(freq[g, i])) for g in range(3)]
+        out.append((int(p), infos[0], infos[1], infos[2]))
+    return out

@@ -122,6 +122,7 @@ void ccsm_destroy(ccsm_model* m) {
   cudaSetDevice(m->cfg.device);
   tc_release(m);
   ex_release(m);
+  pu_release(m);
   m->aggr_packed.release();
   m->aggr_scratch.release();
   for (auto& l : m->fp32.layers) {

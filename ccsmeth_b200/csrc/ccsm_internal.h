@@ -72,6 +72,7 @@ struct Fp32Workspace {
 };
 
 struct TcState;  // tensor-core (tcgen05) path state, defined in tc_path.cu
+struct PuState;  // resident region pileup (pileup.cu)
 struct ExState;  // device feature extraction state (resident read batch), defined in extract.cu
 
 // Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).
@@ -112,6 +113,7 @@ struct ccsm_model {
   ccsm::Fp32Workspace ws32;
   ccsm::TcState* tc = nullptr;
   ccsm::ExState* ex = nullptr;
+  ccsm::PuState* pu = nullptr;
   ccsm::DevBuf aggr_packed, aggr_scratch;  // fused aggregate kernel (aggr_fused.cu)
   ccsm::Profiler prof;
   int h0_mode = 0;            // CCSM_H0_*
@@ -147,6 +149,9 @@ bool aggr_fused_supported(const ccsm_model* m);
 int aggr_fused_upload(ccsm_model* m);
 int aggr_fused_forward(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
                        cudaStream_t st);
+int aggr_fused_forward_sites(ccsm_model* m, int64_t n, const long long* site_pos, const float* site_histo, const float* h0,
+                             float* out, cudaStream_t st);
+void pu_release(ccsm_model* m);
 
 // ---- device feature extraction (extract.cu)
 void ex_release(ccsm_model* m);

@@ -1310,7 +1310,8 @@ static int gru_variant(int layer, int P) {
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
-  return layer > 0 ? 2 : 0;
+  // x3 modes: layer 0 on variant 6 (8 epilogue warps: 395 vs 484 ms per 3 steps; single-pass modes see no difference)
+  return layer > 0 ? 2 : (P == 2 ? 6 : 0);
 }
 
 template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false>

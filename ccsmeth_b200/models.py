@@ -424,3 +424,35 @@ class AggrAttRNN(_NativeModule):
             _lib.check(_lib.load().ccsm_forward_aggr(handle, n, offsets.data_ptr(), histos.data_ptr(), h0.data_ptr(),
                                                      out.data_ptr(), ctypes.c_void_p(stream)))
         return out
+
+    # ---- call_freqb on the device: one region's pileup -> per-site frequencies (include/ccsm.h ccsm_pileup_*)
+    def pileup_begin(self, refpos, ptr, ml, hap=None, call_mode="aggregate", cov_cf=4, prob_cf=0.0, no_amb_cov=False,
+                     no_hap=False):
+        """Uploads a region's pileup in CSR form (site i at reference position refpos[i] is covered by entries
+        ptr[i]:ptr[i+1] of `ml` / `hap`) and returns n_high = (all, hp1, hp2): how many sites of each read group
+        go through the aggregate model -- the n of the h0 tensors ``pileup_finish`` takes."""
+        handle, _ = self._ensure_handle()
+        self._pu = (np.ascontiguousarray(refpos, dtype=np.int64), np.ascontiguousarray(ptr, dtype=np.int64),
+                    np.ascontiguousarray(ml, dtype=np.uint8),
+                    None if hap is None else np.ascontiguousarray(hap, dtype=np.uint8))
+        pos, ptr, ml, hap = self._pu
+        o = _lib.PileupOpts({"count": 0, "aggregate": 1}[call_mode], int(cov_cf), float(prob_cf), int(bool(no_amb_cov)),
+                            int(bool(no_hap)), 0, 0)
+        n_high = (ctypes.c_int64 * 3)()
+        _lib.check(_lib.load().ccsm_pileup_begin_host(handle, ctypes.byref(o), len(pos), pos.ctypes.data, ptr.ctypes.data,
+                                                      ml.ctypes.data, hap.ctypes.data if hap is not None else None, n_high))
+        self._pu_n = len(pos)
+        return tuple(int(v) for v in n_high)
+
+    def pileup_finish(self, h0=(None, None, None)):
+        """-> (cov (3, n) int32, cnt_mod (3, n) float64, freq (3, n) float64), rows = all reads / haplotype 1 / 2;
+        cov == 0 marks "no call of this group at this site" (the reference's None)."""
+        handle, _ = self._ensure_handle()
+        n = self._pu_n
+        cov = np.zeros((3, n), dtype=np.int32)
+        cnt = np.zeros((3, n), dtype=np.float64)
+        freq = np.zeros((3, n), dtype=np.float64)
+        hs = [None if h is None else _dev_f32(h, torch.device("cpu")) for h in h0]
+        _lib.check(_lib.load().ccsm_pileup_finish_host(handle, *[None if h is None else h.data_ptr() for h in hs],
+                                                       cov.ctypes.data, cnt.ctypes.data, freq.ctypes.data))
+        return cov, cnt, freq

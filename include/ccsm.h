@@ -209,6 +209,39 @@ int  ccsm_reads_features(ccsm_model* m, int64_t s0, int64_t cn, const ccsm_stran
 int  ccsm_reads_forward_host(ccsm_model* m, const float* h0_fwd, const float* h0_rev, float* logits, float* probs,
                              float* prob1, int32_t* mm_delta, uint8_t* ml);
 
+/* ---- call_freqb on the device: one region's pileup -> per-site modification frequencies -------
+ * Replaces _call_modfreq_of_one_region / _call_modfreq_of_one_region_aggregate_mode and their helpers
+ * _cal_mod_prob, _cal_modfreq_in_count_mode, _get_normalized_histo, _cal_modfreq_in_aggregate_mode
+ * (reference call_mods_freq_bam.py:102-107, 200-237, 265-305, 308-442).  The caller supplies the pileup of a region
+ * in CSR form: site i (reference position refpos[i], ascending) is covered by entries [ptr[i], ptr[i+1]) of `ml`
+ * (the ML byte of each read's call at that position) and `hap` (the read's haplotype tag value: 0 none, 1, 2; NULL =
+ * all 0).  Building that pileup from an aligned modbam (region fetch, CIGAR walk, MM/ML parsing,
+ * call_mods_freq_bam.py:457-594) is host work outside this library. */
+typedef struct ccsm_pileup_opts {
+  int32_t call_mode;    /* --call_mode: 0 count, 1 aggregate */
+  int32_t cov_cf;       /* --cov_cf: sites with fewer calls than this are counted, not modelled (aggregate mode) */
+  double  prob_cf;      /* --prob_cf */
+  int32_t no_amb_cov;   /* --no_amb_cov */
+  int32_t no_hap;       /* --no_hap: only the "all reads" group */
+  int32_t discrete;     /* --discrete: not implemented (CCSM_EUNSUPPORTED) */
+  int32_t only_close;   /* --only_close: not implemented */
+} ccsm_pileup_opts;
+
+/* The two tables the kernels use: prob[v] = _cal_mod_prob(v) and bin[v] = np.histogram bin of prob[v] (v = ML byte). */
+int  ccsm_pileup_luts(const ccsm_pileup_opts* opts, int32_t bins, double* prob, int32_t* bin);
+
+/* Step 1 (host buffers): upload the pileup, compute per-group coverage and the count-mode results, and find the
+ * sites the aggregate model will see.  n_high[g] = their number for group g (0 all reads, 1 haplotype 1, 2 haplotype 2),
+ * which is the n of the h0 tensors step 2 takes.  `m` is an aggregate (CCSM_KIND_AGGR) model. */
+int  ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* opts, int64_t n_sites, const int64_t* refpos,
+                            const int64_t* ptr, const uint8_t* ml, const uint8_t* hap, int64_t* n_high);
+
+/* Step 2 (host buffers): histograms -> fused aggregate model (windows formed in the kernel) -> results.
+ * h0_*: host (2, n_high[g], hidden) float32 or NULL (zeros).  Outputs are (3, n_sites) arrays, group-major:
+ * cov = coverage reported for the site (0 = the group has no call there: the reference's None), cnt_mod, freq. */
+int  ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_hp1, const float* h0_hp2,
+                             int32_t* cov, double* cnt_mod, double* freq);
+
 /* ---- host I/O helpers: BGZF block codec on a thread team (SAM/BAM spec 4.1) --------------------------------
  * The reference reads and writes BAM through pysam/htslib with `threads=` (extract_features.py:60-73,
  * call_modifications.py:410-462).  Pure host code; buffers are host memory.

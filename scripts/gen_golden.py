@@ -232,14 +232,84 @@ def gen_demo():
                         **{"feat0." + k: v for k, v in feat0.items()})
 
 
+def gen_pileup():
+    """Config 5 / section 8f-3 golden: the reference's own region caller ``_call_modfreq_of_one_region``
+    (call_mods_freq_bam.py:423-442 -> :308-420 in aggregate mode) on a synthetic region pileup, in aggregate and in
+    count mode.  The model is built inside the reference function; its ``init_hidden`` draws are recorded so that the
+    device path can be given the same h0 (groups in the order all reads / haplotype 1 / haplotype 2, one draw per
+    1024 sites).  Also pins the two 256-entry tables (_cal_mod_prob, np.histogram bin)."""
+    import argparse
+    ref = refimport.import_reference()
+    import ccsmeth.call_mods_freq_bam as rfb
+    import ccsmeth.models as rmodels
+    rng = np.random.default_rng(20261017)
+    n = 2600
+    pos = np.cumsum(rng.integers(2, 201, size=n)).astype(np.int64)
+    cov = rng.integers(1, 41, size=n)
+    cov[:5] = [1, 2, 3, 4, 5]
+    ptr = np.concatenate(([0], np.cumsum(cov))).astype(np.int64)
+    ml = np.floor(256 * rng.beta(0.3, 0.3, size=int(ptr[-1]))).clip(0, 255).astype(np.uint8)
+    ml[:3] = [0, 128, 255]
+    hap = rng.choice([0, 1, 2], size=int(ptr[-1]), p=[0.4, 0.3, 0.3]).astype(np.uint8)
+    info = {int(pos[i]): [(rfb._cal_mod_prob(int(ml[k])), int(hap[k])) for k in range(ptr[i], ptr[i + 1])] for i in range(n)}
+
+    def ns(**kw):
+        a = argparse.Namespace(call_mode="aggregate", cov_cf=4, bin_size=20, prob_cf=0.0, no_amb_cov=False, no_hap=False,
+                               seq_len=11, layer_rnn=1, class_num=1, hid_rnn=32, model_type="attbigru",
+                               aggre_model=refimport.AGGR_CKPT, only_close=False, discrete=False, tseed=1234)
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return a
+
+    def pack(res):
+        out = np.full((3, n, 3), np.nan)
+        assert [r[0] for r in res] == [int(p) for p in pos]
+        for i, r in enumerate(res):
+            for g in range(3):
+                if r[1 + g] is not None:
+                    out[g, i] = [float(x) for x in r[1 + g]]
+        return out
+
+    drawn = []
+    orig = rmodels.AggrAttRNN.init_hidden
+
+    def recording(self, *a, **k):
+        h = orig(self, *a, **k)
+        drawn.append(h.detach().clone())
+        return h
+
+    save = {"pos": pos, "ptr": ptr, "ml": ml, "hap": hap,
+            "lut_prob": np.array([rfb._cal_mod_prob(v) for v in range(256)], dtype=np.float64),
+            "lut_bin": np.array([int(np.argmax(np.histogram([rfb._cal_mod_prob(v)], bins=20, range=[0, 1])[0]))
+                                 for v in range(256)], dtype=np.int32)}
+    rmodels.AggrAttRNN.init_hidden = recording
+    try:
+        for tag, kw in (("aggr", {}), ("aggr_cf3", {"prob_cf": 0.3}), ("aggr_nohap", {"no_hap": True})):
+            drawn.clear()
+            res = rfb._call_modfreq_of_one_region(info, ns(**kw))
+            save[tag] = pack(res)
+            save[tag + "_h0"] = torch.cat(drawn, dim=1).numpy()   # (2, sum of high-coverage sites over groups, 32)
+            save[tag + "_h0_sizes"] = np.array([h.shape[1] for h in drawn], dtype=np.int64)
+    finally:
+        rmodels.AggrAttRNN.init_hidden = orig
+    for tag, kw in (("count", {}), ("count_cf3", {"prob_cf": 0.3}), ("count_cf3_noamb", {"prob_cf": 0.3, "no_amb_cov": True})):
+        save[tag] = pack(rfb._call_modfreq_of_one_region(info, ns(call_mode="count", **kw)))
+    np.savez_compressed(os.path.join(OUT, "pileup_region.npz"), **save)
+    print("pileup_region: %d sites, %d calls, aggregate mean freq %.4f" % (n, len(ml), np.nanmean(save["aggr"][0, :, 2])))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "demo":
         gen_demo()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pileup":
+        gen_pileup()
+        sys.exit(0)
     save_ckpts()
     gen_att2s()
     gen_aggr()
+    gen_pileup()
     gen_demo()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
