@@ -100,6 +100,6 @@ def _call_modfreq_of_one_region(refpos2modinfo, args, model, h0=None):
     cov, cnt, freq = model.pileup_finish(h0 if h0 is not None else (None, None, None))
     out = []
     for i, p in enumerate(refposes):
-        infos = [None if cov[g, i] == 0 else (int(cov[g, i]), float(cnt[g, i]), float(freq[g, i])) for g in range(3)]
+        infos = [None if cov[g, i] < 0 else (int(cov[g, i]), float(cnt[g, i]), float(freq[g, i])) for g in range(3)]
         out.append((int(p), infos[0], infos[1], infos[2]))
     return out

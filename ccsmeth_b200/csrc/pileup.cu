@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) pileup_count_kernel(int64_t n, const long
   const bool high = o.call_mode == 1 && cov >= o.cov_cf && cov > 0;
   flag[idx] = high ? 1 : 0;
   if (cov == 0) {
-    r_cov[idx] = 0;  // "None" for this group
+    r_cov[idx] = -1;  // "None" for this group (a coverage of 0 is a legitimate --no_amb_cov result)
     r_cnt[idx] = 0.0;
     r_freq[idx] = 0.0;
   } else if (!high) {

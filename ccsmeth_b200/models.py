@@ -446,10 +446,10 @@ class AggrAttRNN(_NativeModule):
 
     def pileup_finish(self, h0=(None, None, None)):
         """-> (cov (3, n) int32, cnt_mod (3, n) float64, freq (3, n) float64), rows = all reads / haplotype 1 / 2;
-        cov == 0 marks "no call of this group at this site" (the reference's None)."""
+        cov == -1 marks "no call of this group at this site" (the reference's None)."""
         handle, _ = self._ensure_handle()
         n = self._pu_n
-        cov = np.zeros((3, n), dtype=np.int32)
+        cov = np.full((3, n), -1, dtype=np.int32)
         cnt = np.zeros((3, n), dtype=np.float64)
         freq = np.zeros((3, n), dtype=np.float64)
         hs = [None if h is None else _dev_f32(h, torch.device("cpu")) for h in h0]

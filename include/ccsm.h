@@ -238,7 +238,7 @@ int  ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* opts, int64_t
 
 /* Step 2 (host buffers): histograms -> fused aggregate model (windows formed in the kernel) -> results.
  * h0_*: host (2, n_high[g], hidden) float32 or NULL (zeros).  Outputs are (3, n_sites) arrays, group-major:
- * cov = coverage reported for the site (0 = the group has no call there: the reference's None), cnt_mod, freq. */
+ * cov = coverage reported for the site (-1 = the group has no call there: the reference's None), cnt_mod, freq. */
 int  ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_hp1, const float* h0_hp2,
                              int32_t* cov, double* cnt_mod, double* freq);
 
