@@ -248,8 +248,15 @@ struct GruParams {
 //           other variants, so the activation re-reads stay in L2.
 //   EPIW  = epilogue warps per TMEM lane quadrant (2: two warps share a row, each takes two of the four 16-unit
 //           blocks of a unit-chunk -- halves the epilogue latency when one CTA owns the SM).
-template <int P, int NSLOT, int NBUF, int KSB, int EPIW = 1>
+//   HS    = the recurrent operand stays on chip: the gate epilogue writes h_t straight into a shared-memory buffer in
+//           the UMMA A layout (two 64 KB buffers, ping-pong) and the H-part MMAs of the next step read it from
+//           there, instead of h_t -> global -> fence -> TMA -> shared.  The act image is still written (it is the
+//           layer's output) but is off the step-to-step critical path.  Single-pass modes only (hi+lo would need
+//           2 x 128 KB); meant for layer 0, whose K_in = 16 leaves no input-projection MMAs to hide that round trip.
+template <int P, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool HS = false>
 struct GruCfg {
+  static_assert(!HS || (P == 1 && NSLOT == 1 && NBUF == 2), "HS: single pass, one row tile per CTA, TMEM double-buffered");
+  static constexpr uint32_t HBUF = HS ? 4 * CHUNK_BYTES : 0;  // one h_t: 128 rows x 256 units
   static_assert(P == 1 || 8 % (KSB / P) == 0, "a stage must not straddle two 64-K chunks of a hi/lo image");
   static_assert(EPIW == 1 || NSLOT == 1, "EPIW = 2 only with one row tile per CTA");
   static constexpr int KS = KSB / P;  // slabs per stage per part
@@ -260,10 +267,11 @@ struct GruCfg {
   static constexpr uint32_t B_PART = KS * G_SLAB;
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + NSLOT * A_PART);
-  static constexpr uint32_t BUDGET = CTAS_PER_SM == 2 ? 102400 : 208896;  // ring bytes per CTA
+  static constexpr uint32_t BUDGET = (CTAS_PER_SM == 2 ? 102400 : 208896) - (HS ? 2 * HBUF - 14336 : 0);  // ring bytes per CTA
   static constexpr int STAGES = (int)(BUDGET / STAGE);
   static_assert(STAGES >= 2, "ring too shallow");
-  static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
+  static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4 + 2 * HBUF;
+  static_assert(SMEM <= 231424, "shared memory per CTA");
 };
 
 //   MC    = launched as clusters of two CTAs (same direction, neighbouring row tiles) that share every weight
@@ -271,12 +279,13 @@ struct GruCfg {
 //           memory (cp.async.bulk ... .multicast::cluster), halving the L2 -> SM weight traffic (weights are
 //           6/7 of what this kernel pulls through the crossbar).  A stage is refilled only when BOTH CTAs'
 //           MMAs have retired it (multicast tcgen05.commit onto both empty barriers, count 2).
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC>
-__global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, GruCfg<P, NSLOT, NBUF, KSB, EPIW>::CTAS_PER_SM)
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false>
+__global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS, GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
   static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
   static_assert(!MC || NSLOT == 1, "multicast variant: one row tile per CTA");
-  using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW>;
+  static_assert(!(MC && HS), "HS and MC are separate experiments");
+  using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>;
   constexpr int GRU_STAGES = C::STAGES;
   constexpr int GRU_THREADS = C::THREADS;
   constexpr int KS = C::KS;
@@ -285,6 +294,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
   __shared__ __align__(8) uint64_t bars[2 * GRU_STAGES + 5];
   __shared__ uint32_t tmem_base_s;
   float* bias_s = reinterpret_cast<float*>(smem + GRU_STAGES * C::STAGE);
+  // HS: two h_t buffers [kc 0..3][8 slabs x 2048 B] right after the biases (1024-byte aligned: STAGE and 8 KB are)
+  const uint32_t hbuf0 = smem_u32(smem) + GRU_STAGES * C::STAGE + 2 * 4 * 256 * 4;
+  uint8_t* hbuf_g = smem + GRU_STAGES * C::STAGE + 2 * 4 * 256 * 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[GRU_STAGES]);
@@ -344,14 +356,15 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
               const int total = part == 0 ? p.kx_slabs : 32;
               for (int so = 0; so < total; so += KS) {
                 const int ns = (total - so) < KS ? (total - so) : KS;
-                if (part == 1 && so == 0 && j == 0 && gstep > 0) {
+                if (!HS && part == 1 && so == 0 && j == 0 && gstep > 0) {
                   mbar_wait(h_ready, (gstep - 1) & 1);  // h_{t_prev} of both slots is in the act image
                   fence_proxy_async_all();
                 }
                 mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
                 const uint32_t fb = full0 + 8 * stage;
                 const uint32_t sb = smem_base + stage * C::STAGE;
-                mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + NSLOT * A_SLAB));
+                const bool load_a = !(HS && part == 1);  // HS: the recurrent operand is already in shared memory
+                mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + (load_a ? NSLOT * A_SLAB : 0)));
                 // weights
                 const uint8_t* wsrc = wj + (part ? xbytes : 0);
 #pragma unroll
@@ -370,6 +383,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
                 // activations of every slot
 #pragma unroll
                 for (int sl = 0; sl < NSLOT; ++sl) {
+                  if (!load_a) break;
                   const int64_t tile = tile0 + sl;
                   const uint8_t* asrc;
                   size_t part_stride;
@@ -412,8 +426,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
     if (elect_one()) {
       constexpr uint32_t idesc192 = make_idesc(128, 192, F16);
       uint32_t stage = 0, use = 0, chunk = 0;
+      uint32_t hcount = 0;  // HS: completions of h_ready consumed so far (one per step: item start, then every step)
       for (int item = item0; item < n_items; item += item_step) {
-        for (int s = 0; s < L; ++s) {
+        for (int s = 0; s < L; ++s, ++hcount) {
           for (int j = 0; j < 4; ++j, ++chunk) {
             const uint32_t buf = chunk % NBUF, bphase = (chunk / NBUF) & 1;
             // completion #u of tmem_empty[buf]: #0 = initial bias arming, #k = drain + re-arm after use k-1
@@ -423,6 +438,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
               const int total = part == 0 ? p.kx_slabs : 32;
               for (int so = 0; so < total; so += KS) {
                 const int ns = (total - so) < KS ? (total - so) : KS;
+                if (HS && part == 1 && so == 0 && j == 0) mbar_wait(h_ready, hcount & 1);  // h_{t_prev} is in hbuf
                 mbar_wait(full0 + 8 * stage, use & 1);
                 tc_fence_after();
                 const uint32_t sb = smem_base + stage * C::STAGE;
@@ -433,7 +449,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
 #pragma unroll
                     for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
                       const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
-                      const uint32_t a_addr = sb + P * C::B_PART + (sl * P + pa) * C::A_PART + ks * 2 * A_SLAB;
+                      const uint32_t a_addr = (HS && part == 1)
+                                                  ? hbuf0 + (hcount & 1) * C::HBUF + (so + ks * 2) * A_SLAB
+                                                  : sb + P * C::B_PART + (sl * P + pa) * C::A_PART + ks * 2 * A_SLAB;
                       const uint32_t b_addr = sb + pb * C::B_PART + ks * 2 * G_SLAB;
                       const uint64_t ad = make_smem_desc(a_addr, A_SLAB, 128);
                       // X part -> columns [0,192) = (n_i, r, z); H part -> columns [64,256) = (r, z, n_h).
@@ -476,22 +494,41 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
       tc_fence_before();
       mbar_arrive(tmem_empty + 8 * b);
     }
+    uint32_t hcnt = 0;  // HS: steps started so far (selects the h buffer: read (hcnt & 1), write the other one)
     for (int item = item0; item < n_items; item += item_step) {
       const int pair = item >> 1, d = item & 1;
       const int64_t tile = TILES_PER_ITEM * (int64_t)pair + crank + slot;
-      for (int s = 0; s < L; ++s) {
+      if constexpr (HS) {
+        // h0 of this row -> the buffer step 0 reads.  Safe to overwrite: every MMA that read this buffer (step L-2 of
+        // the previous item) retired before the tmem_full of the previous item's last step, which this thread passed.
+        const uint8_t* src = p.h0img + ((tile * 2 + d) * 4) * (size_t)CHUNK_BYTES + row * 16;
+        uint8_t* dst = hbuf_g + (hcnt & 1) * C::HBUF + row * 16;
+        constexpr int NSL = 32 / EPIW;  // K-slabs this warp copies
+        const int sl0 = EPIW == 2 ? ((warp - C::EPI_WARP0) >> 2) * NSL : 0;
+#pragma unroll 8
+        for (int sl = sl0; sl < sl0 + NSL; ++sl)
+          *reinterpret_cast<uint4*>(dst + sl * A_SLAB) = __ldcg(reinterpret_cast<const uint4*>(src + sl * A_SLAB));
+        fence_proxy_async_smem();
+        mbar_arrive(h_ready);
+      }
+      for (int s = 0; s < L; ++s, ++hcnt) {
         const int t = d ? (L - 1 - s) : s;
         const int tprev = d ? t + 1 : t - 1;
         for (int j = 0; j < 4; ++j, ++chunk) {
           const uint8_t* hp_base =
-              (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
-                       : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+              HS ? hbuf_g + (hcnt & 1) * C::HBUF + j * (size_t)CHUNK_BYTES
+                 : ((s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
+                             : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES);
           uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint8_t* hnext = hbuf_g + ((hcnt + 1) & 1) * C::HBUF + j * (size_t)CHUNK_BYTES;
           // prefetch h_{t_prev} for this row's 64 units (L2 latency overlaps the MMAs of this chunk)
           uint4 hph[2 * NUB], hpl[2 * NUB];
 #pragma unroll
           for (int q = 0; q < 2 * NUB; ++q) {
-            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (2 * ub0 + q) * A_SLAB + row * 16));
+            if constexpr (HS)
+              hph[q] = *reinterpret_cast<const uint4*>(hp_base + (2 * ub0 + q) * A_SLAB + row * 16);
+            else
+              hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (2 * ub0 + q) * A_SLAB + row * 16));
             if constexpr (P == 2)
               hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + (2 * ub0 + q) * A_SLAB + row * 16));
             else
@@ -526,6 +563,10 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
               }
               uint4 hi, lo;
               split8<P, F16>(hn, hi, lo);
+              if constexpr (HS) {
+                // next step's A operand, written in place in the UMMA layout (the last step's output feeds nobody)
+                if (s + 1 < L) *reinterpret_cast<uint4*>(hnext + (ub * 2 + q) * A_SLAB + row * 16) = hi;
+              }
               *reinterpret_cast<uint4*>(out_base + (ub * 2 + q) * A_SLAB + row * 16) = hi;
               if constexpr (P == 2)
                 *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + (ub * 2 + q) * A_SLAB + row * 16) = lo;
@@ -535,8 +576,15 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW>::THREADS, Gr
           tc_fence_before();
           mbar_arrive(tmem_empty + 8 * buf);
           if (j == 3) {
-            fence_proxy_async_all();  // generic-proxy global writes -> visible to the producer's bulk copies
-            mbar_arrive(h_ready);
+            if constexpr (HS) {
+              if (s + 1 < L) {
+                fence_proxy_async_smem();  // generic-proxy shared-memory writes -> visible to the MMA's operand reads
+                mbar_arrive(h_ready);
+              }
+            } else {
+              fence_proxy_async_all();  // generic-proxy global writes -> visible to the producer's bulk copies
+              mbar_arrive(h_ready);
+            }
           }
         }
       }
@@ -1295,6 +1343,7 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
 // GRU kernel variant: 0 = (NSLOT 1, NBUF 1, two CTAs per SM), 1 = (NSLOT 2, NBUF 1), 2 = (NSLOT 1, NBUF 2),
 // 5 = variant 0 with 40 KB stages, 6 = variant 2 with two epilogue warps per quadrant,
 // 7 / 8 / 9 = variants 2 / 0 / 5 as clusters of two CTAs sharing every weight stage by TMA multicast,
+// a / b (10 / 11) = h_t kept in shared memory between steps (HS), 8 / 4 epilogue warps,
 // 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered), 4 = CTA pair, two clusters per TPC (NBUF 1).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
 // Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0 (two CTAs per SM);
@@ -1305,8 +1354,9 @@ static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    v[0] = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1;
-    v[1] = (e && e[0] && e[1] >= '0' && e[1] <= '9') ? e[1] - '0' : v[0];
+    auto dig = [](char c) { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'b') ? 10 + (c - 'a') : -1; };
+    v[0] = e ? dig(e[0]) : -1;
+    v[1] = (e && e[0] && dig(e[1]) >= 0) ? dig(e[1]) : v[0];
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
@@ -1314,11 +1364,11 @@ static int gru_variant(int layer, int P) {
   return layer > 0 ? 2 : (P == 2 ? 6 : 0);
 }
 
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false>
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false, bool HS = false>
 static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
-  using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW>;
+  using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>;
   static bool attr = false;
-  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC>;
+  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC, HS>;
   if (!attr) {
     CCSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr = true;
@@ -1362,6 +1412,12 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
     case 7: return launch_gru<P, F16, 1, 2, 8, 1, true>(gp, tiles, sm_count, st);  // 2 + weight multicast
     case 8: return launch_gru<P, F16, 1, 1, 4, 1, true>(gp, tiles, sm_count, st);  // 0 + weight multicast
     case 9: return launch_gru<P, F16, 1, 1, 8, 1, true>(gp, tiles, sm_count, st);  // 5 + weight multicast
+    case 10:  // h_t kept in shared memory (single-pass modes; x3 falls back to variant 6)
+      if constexpr (P == 1) return launch_gru<P, F16, 1, 2, 4, 2, false, true>(gp, tiles, sm_count, st);
+      else return launch_gru<P, F16, 1, 2, 8, 2>(gp, tiles, sm_count, st);
+    case 11:
+      if constexpr (P == 1) return launch_gru<P, F16, 1, 2, 4, 1, false, true>(gp, tiles, sm_count, st);
+      else return launch_gru<P, F16, 1, 2, 8, 2>(gp, tiles, sm_count, st);
     default:
       set_error("unknown GRU kernel variant %d", variant);
       return CCSM_EINVAL;
