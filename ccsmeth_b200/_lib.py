@@ -32,7 +32,7 @@ EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
            "ccsm_debug_umma_pair_gemm", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
            "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound",
-           "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records", "ccsm_pileup_luts",
+           "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records", "ccsm_bam_modcalls", "ccsm_pileup_luts",
            "ccsm_pileup_begin_host", "ccsm_pileup_finish_host"]
 
 
@@ -62,6 +62,11 @@ class PileupOpts(ctypes.Structure):
     _fields_ = [("call_mode", ctypes.c_int32), ("cov_cf", ctypes.c_int32), ("prob_cf", ctypes.c_double),
                 ("no_amb_cov", ctypes.c_int32), ("no_hap", ctypes.c_int32), ("discrete", ctypes.c_int32),
                 ("only_close", ctypes.c_int32)]
+
+
+class ModcallOpts(ctypes.Structure):
+    _fields_ = [("mapq", ctypes.c_int32), ("no_supplementary", ctypes.c_int32), ("base_clip", ctypes.c_int32),
+                ("hap_tag", ctypes.c_char * 4), ("identity", ctypes.c_double)]
 
 
 class BamFilter(ctypes.Structure):
@@ -173,9 +178,11 @@ def load():
             getattr(lib, fn).restype = i64
         lib.ccsm_pileup_luts.argtypes = [ctypes.POINTER(PileupOpts), i32, vp, vp]
         lib.ccsm_pileup_begin_host.argtypes = [vp, ctypes.POINTER(PileupOpts), i64, vp, vp, vp, vp, vp]
-        lib.ccsm_pileup_finish_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        lib.ccsm_pileup_finish_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         for fn in ("ccsm_pileup_luts", "ccsm_pileup_begin_host", "ccsm_pileup_finish_host"):
             getattr(lib, fn).restype = ctypes.c_int
+        lib.ccsm_bam_modcalls.argtypes = [vp, vp, i32, ctypes.POINTER(ModcallOpts), vp, vp, vp, vp, vp, i64, ctypes.POINTER(i32)]
+        lib.ccsm_bam_modcalls.restype = i64
         lib.ccsm_bam_index.argtypes = [vp, i64, ctypes.POINTER(BamFilter), vp, i32, vp, ctypes.POINTER(i32),
                                        ctypes.POINTER(i32), ctypes.POINTER(i64)]
         lib.ccsm_bam_index.restype = ctypes.c_int

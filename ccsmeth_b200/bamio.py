@@ -257,6 +257,32 @@ class BamRecord:
             return None
         return self.pos + sum(l for op, l in self.cigartuples if op in (0, 2, 3, 7, 8))
 
+    def get_aligned_pairs(self, matches_only=False):
+        """(query_pos, ref_pos) pairs like pysam: M/=/X pair up; with matches_only insertions, soft clips,
+        deletions and skips produce no pair (otherwise the missing side is None)."""
+        out = []
+        q, r = 0, self.pos
+        for op, ln in self.cigartuples:
+            if op in (0, 7, 8):
+                out.extend(zip(range(q, q + ln), range(r, r + ln)))
+                q += ln
+                r += ln
+            elif op in (1, 4):
+                if not matches_only:
+                    out.extend((i, None) for i in range(q, q + ln))
+                q += ln
+            elif op in (2, 3):
+                if not matches_only:
+                    out.extend((None, i) for i in range(r, r + ln))
+                r += ln
+        return out
+
+    @property
+    def modified_bases(self):
+        """pysam >= 0.19 parses MM/ML itself; None makes the reference fall back to its own tag parser
+        (call_mods_freq_bam.py:172-197)."""
+        return None
+
     def get_cigar_stats(self):
         base = [0] * 11
         blocks = [0] * 11

@@ -1,0 +1,329 @@
+"""`call_freqb`: modification frequencies at genome level from an aligned, sorted modbam -- one process per GPU.
+
+Keeps the reference's flag surface and output format (ccsmeth/call_mods_freq_bam.py:741-845, `_write_one_line`
+:626-634, file names :639-642) for the default path: symmetric ``--motifs CG``-style sites, count or aggregate mode,
+haplotype split by ``--hap_tag``, ``--refsites_only`` motif filter, ``--base_clip``.  Not offered: ``--refsites_all``
+(zero-probability entries for uncalled reference sites), ``--discrete``, ``--only_close``, bed sorting / tabix.
+
+Where the reference forks region workers that each ``fetch`` their reads through pysam and pile calls up in Python
+dictionaries (:457-540), this streams the sorted BAM once: native BGZF inflate + record index (bamstream.py), native
+MM/ML-to-reference projection (``ccsm_bam_modcalls``), then per reference chunk (`_get_reference_chunks`, same
+boundaries incl. the CG adjustment :62-82) one device call that turns the chunk's pileup into per-site results
+(``ccsm_pileup_*``: count statistics, histograms, in-kernel windows, fused aggregate model).
+
+    python -m ccsmeth_b200.call_freqb --input_bam aln.modbam.bam --ref genome.fa -o out --call_mode aggregate -m aggr.ckpt
+"""
+import argparse
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .bamstream import BamPieceReader
+from .call_mods import get_motif_seqs
+from .call_mods_freq_bam import AGGR_BATCH, load_aggr_model
+from .models import AggrAttRNN
+from .utils.process_utils import complement_seq
+
+
+def read_fasta(path):
+    """{contig: upper-case sequence} like the reference's DNAReference (utils/ref_reader.py:33-53)."""
+    contigs, name, parts = {}, "", []
+    with open(path) as f:
+        for line in f:
+            if line.startswith(">"):
+                if name != "" and parts:
+                    contigs[name] = "".join(parts)
+                name = line.strip()[1:].split(" ")[0]
+                parts = []
+            else:
+                parts.append(line.strip().upper())
+    contigs[name] = "".join(parts)
+    return contigs
+
+
+def get_reference_chunks(dnacontigs, contig_str, chunk_len=500000, motifs="CG"):
+    """Reference regions (call_mods_freq_bam.py:48-83): chunks of chunk_len per contig, boundaries moved by one base
+    where they would split a CG."""
+    if contig_str is not None:
+        if os.path.isfile(contig_str):
+            with open(contig_str) as f:
+                contigs = sorted(set(f.read().splitlines()))
+        else:
+            contigs = sorted(set(contig_str.strip().split(",")))
+    else:
+        contigs = sorted(dnacontigs.keys())
+    chunks = []
+    for contig in contigs:
+        n = len(dnacontigs[contig])
+        for i in range(0, n, chunk_len):
+            chunks.append((contig, i, i + chunk_len if i + chunk_len < n else n))
+    if motifs == "CG":
+        for idx in range(1, len(chunks)):
+            pre_ref, pre_s, pre_e = chunks[idx - 1]
+            cur_ref, cur_s, cur_e = chunks[idx]
+            if pre_ref != cur_ref:
+                continue
+            if dnacontigs[pre_ref][(pre_e - 1):(pre_e + 1)] == "CG":
+                chunks[idx - 1] = (pre_ref, pre_s, pre_e + 1)
+                chunks[idx] = (cur_ref, cur_s + 1, cur_e)
+    return chunks
+
+
+class ModCalls:
+    """All modification calls of the reads seen so far, as flat arrays (ref_id, ref_pos, ml, hap, strand)."""
+
+    def __init__(self):
+        self.parts = []
+
+    def add_piece(self, piece, opts):
+        lib = _lib.load()
+        cap = int(piece.recs["l_seq"].sum()) // 8 + 1024
+        used = ctypes.c_int32(0)
+        while True:
+            rid = np.empty(cap, dtype=np.int32)
+            pos = np.empty(cap, dtype=np.int32)
+            ml = np.empty(cap, dtype=np.uint8)
+            hap = np.empty(cap, dtype=np.uint8)
+            strand = np.empty(cap, dtype=np.uint8)
+            recs = np.ascontiguousarray(piece.recs)
+            n = lib.ccsm_bam_modcalls(piece.buf.ctypes.data, recs.ctypes.data, len(recs), ctypes.byref(opts),
+                                      rid.ctypes.data, pos.ctypes.data, ml.ctypes.data, hap.ctypes.data,
+                                      strand.ctypes.data, cap, ctypes.byref(used))
+            if n < 0:
+                _lib.check(int(n))
+            if n <= cap:
+                break
+            cap = int(n)
+        n = int(n)
+        self.parts.append((rid[:n], pos[:n], ml[:n], hap[:n], strand[:n]))
+        return used.value
+
+    def arrays(self):
+        if not self.parts:
+            z = np.zeros(0, dtype=np.int32)
+            return z, z, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.uint8)
+        return tuple(np.concatenate([p[k] for p in self.parts]) for k in range(5))
+
+
+def region_pileups(pos, ml, hap, strand, ref_start, ref_end, comb):
+    """Calls of one contig -> the region's CSR pileups.  Returns a list of (strand_char, refpos, ptr, ml, hap):
+    one "+" pileup with the reverse-strand CpG calls folded onto the C of the forward strand (pos - 1) when `comb`
+    (call_mods_freq_bam.py:542-551), else a "+" and a "-" pileup."""
+    sel = (pos >= ref_start) & (pos < ref_end)
+    p, m, h, s = pos[sel].astype(np.int64), ml[sel], hap[sel], strand[sel]
+    out = []
+    if comb:
+        keep = ~((s == 1) & (p == 0))          # a reverse call at position 0 has no forward partner (:544-545)
+        p, m, h, s = p[keep], m[keep], h[keep], s[keep]
+        groups = (("+", p - (s == 1), m, h),)
+    else:
+        groups = (("+", p[s == 0], m[s == 0], h[s == 0]), ("-", p[s == 1], m[s == 1], h[s == 1]))
+    for ch, gp, gm, gh in groups:
+        if len(gp) == 0:
+            continue
+        order = np.argsort(gp, kind="stable")
+        gp, gm, gh = gp[order], gm[order], gh[order]
+        refpos, first = np.unique(gp, return_index=True)
+        ptr = np.concatenate((first, [len(gp)])).astype(np.int64)
+        out.append((ch, refpos.astype(np.int64), ptr, gm, gh))
+    return out
+
+
+def draw_region_h0(args, n_high):
+    """The h0 the reference's region caller would draw: it seeds torch with --tseed, BUILDS the model (parameter
+    initialisation consumes the generator) and then draws one randn per 1024-site slice, group after group
+    (call_mods_freq_bam.py:310-321, 295-301; models.py:661-671)."""
+    torch.manual_seed(args.tseed)
+    AggrAttRNN(args.seq_len, args.layer_rnn, args.class_num, 0, args.hid_rnn, binsize=args.bin_size,
+               model_type=args.model_type, device="cpu")  # same constructor calls, same generator consumption
+    out = []
+    for nh in n_high:
+        if nh == 0:
+            out.append(None)
+            continue
+        t = torch.empty(2 * args.layer_rnn, nh, args.hid_rnn)
+        for s in range(0, nh, AGGR_BATCH):
+            e = min(nh, s + AGGR_BATCH)
+            t[:, s:e] = torch.randn(2 * args.layer_rnn, e - s, args.hid_rnn)
+        out.append(t)
+    return out
+
+
+def call_region(model, args, contig_seq, ref_name, pileups, motifs_filter):
+    """One region's pileups -> (bed_all, bed_hp1, bed_hp2) lists of (ref_name, refpos, strand, cov, cnt, freq), the
+    reference's `_readmods_to_bed_of_one_region` return value (:553-594)."""
+    beds = ([], [], [])
+    if motifs_filter is not None:
+        mlen = len(motifs_filter[0])
+        fwd_s, fwd_e = -args.mod_loc, mlen - args.mod_loc
+        rev_s, rev_e = -(mlen - 1 - args.mod_loc), args.mod_loc + 1
+        mset = set(motifs_filter)
+    for ch, refpos, ptr, ml, hap in pileups:
+        n_high = model.pileup_begin(refpos, ptr, ml, hap, call_mode=args.call_mode, cov_cf=args.cov_cf,
+                                    prob_cf=args.prob_cf, no_amb_cov=args.no_amb_cov, no_hap=args.no_hap)
+        h0 = (None, None, None)
+        if args.call_mode == "aggregate" and getattr(args, "h0", "reference") == "reference":
+            h0 = draw_region_h0(args, n_high)
+        cov, cnt, freq, kind = model.pileup_finish(h0, with_kind=True)
+        for i, p in enumerate(refpos):
+            p = int(p)
+            if motifs_filter is not None:
+                if ch == "+":
+                    if contig_seq[p + fwd_s:p + fwd_e] not in mset:
+                        continue
+                elif complement_seq(contig_seq[p + rev_s:p + rev_e]) not in mset:
+                    continue
+            for g in range(3):
+                k = kind[g, i]
+                if k == 0:
+                    continue
+                # the value types the reference holds (they decide how str() prints them in the output files)
+                if k == 1:
+                    c, fr = int(cnt[g, i]), float(freq[g, i])
+                elif k == 2:
+                    c, fr = np.float64(cnt[g, i]), float(freq[g, i])
+                else:
+                    c, fr = np.float32(cnt[g, i]), np.float32(freq[g, i])
+                beds[g].append((ref_name, p, ch, int(cov[g, i]), c, fr))
+    return beds
+
+
+def write_one_line(beditem, wf, is_bed):
+    """reference `_write_one_line` (:626-634)."""
+    ref_name, refpos, strand, cov, met, metprob = beditem
+    if is_bed:
+        wf.write("\t".join([ref_name, str(refpos), str(refpos + 1), ".", str(cov), strand, str(refpos), str(refpos + 1),
+                            "0,0,0", str(cov), str(int(round(metprob * 100 + 0.001, 0)))]) + "\n")
+    else:
+        wf.write("\t".join([ref_name, str(refpos), str(refpos + 1), strand, ".", ".", str(met), str(cov - met),
+                            str(cov), str(round(metprob + 0.000001, 4)), "."]) + "\n")
+
+
+def iter_region_results(args, model, dnacontigs, bam_path):
+    """Streams the sorted BAM and yields (region, bed_all, bed_hp1, bed_hp2) for every reference chunk that has calls."""
+    motifs = get_motif_seqs(args.motifs)
+    motifs_filter = motifs if (args.refsites_only or args.refsites_all) else None
+    comb = args.motifs == "CG" and not args.no_comb
+    chunks = get_reference_chunks(dnacontigs, args.contigs, args.chunk_len, args.motifs)
+    by_contig = {}
+    for c in chunks:
+        by_contig.setdefault(c[0], []).append(c)
+    flt = _lib.BamFilter(0, 0, 0, 0, 0)
+    rd = BamPieceReader(bam_path, flt, threads=max(1, args.threads), align_to=1)
+    ref_names = [r[0] for r in rd.references]
+    opts = _lib.ModcallOpts(args.mapq, 1 if args.no_supplementary else 0, args.base_clip,
+                            args.hap_tag.encode("ascii")[:2], float(args.identity))
+    calls = ModCalls()
+    for piece in rd:
+        calls.add_piece(piece, opts)
+    rd.close()
+    rid, pos, ml, hap, strand = calls.arrays()
+    for ref_id, name in enumerate(ref_names):
+        if name not in by_contig:
+            continue
+        sel = rid == ref_id
+        if not sel.any():
+            continue
+        cpos, cml, chap, cstrand = pos[sel], ml[sel], hap[sel], strand[sel]
+        for region in by_contig[name]:
+            _, s, e = region
+            pile = region_pileups(cpos, cml, chap, cstrand, s, e, comb)
+            if not pile:
+                continue
+            beds = call_region(model, args, dnacontigs[name], name, pile, motifs_filter)
+            if beds[0]:
+                yield (region,) + beds
+
+
+def call_freqb(args):
+    t0 = time.time()
+    if args.call_mode == "aggregate" and not (args.aggre_model and os.path.exists(args.aggre_model)):
+        raise ValueError("--aggre_model is not set right!")
+    if not args.input_bam.endswith(".bam"):
+        raise ValueError("--input_bam not a bam file!")
+    if not os.path.exists(args.input_bam):
+        raise ValueError("--input_bam does not exist!")
+    if not os.path.exists(args.ref):
+        raise ValueError("--ref does not exist!")
+    if args.refsites_all or args.discrete or args.only_close:
+        raise ValueError("--refsites_all / --discrete / --only_close are not implemented by ccsmeth_b200")
+    os.makedirs(os.path.dirname(os.path.abspath(args.output)), exist_ok=True)
+    dnacontigs = read_fasta(args.ref)
+    if args.call_mode == "aggregate":
+        model = load_aggr_model(args.aggre_model, args, device=int(os.environ.get("LOCAL_RANK", 0)))
+    else:
+        model = AggrAttRNN(args.seq_len, args.layer_rnn, args.class_num, 0, args.hid_rnn, binsize=args.bin_size,
+                           model_type=args.model_type, device=int(os.environ.get("LOCAL_RANK", 0))).cuda().eval()
+    fext = "bed" if args.bed else "freq.txt"
+    paths = [args.output + ".%s.%s.%s" % (args.call_mode, g, fext) for g in ("all", "hp1", "hp2")]
+    files = [open(p, "w") for p in paths]
+    n_lines = [0, 0, 0]
+    for _, *beds in iter_region_results(args, model, dnacontigs, args.input_bam):
+        for g in range(3):
+            for item in beds[g]:
+                write_one_line(item, files[g], args.bed)
+            n_lines[g] += len(beds[g])
+    for f, p, n in zip(files, paths, n_lines):
+        f.close()
+        if n == 0:
+            os.remove(p)  # the reference removes empty outputs (:663-666)
+    sys.stderr.write("[call_freqb] %d / %d / %d sites (all / hp1 / hp2) in %.1f s\n" % (*n_lines, time.time() - t0))
+    return dict(zip(("all", "hp1", "hp2"), n_lines)), paths
+
+
+def build_parser():
+    """The reference's call_freqb flags with the same defaults (call_mods_freq_bam.py:741-840)."""
+    p = argparse.ArgumentParser("ccsmeth_b200 call_freqb")
+    p.add_argument("--threads", type=int, default=5)
+    p.add_argument("--input_bam", type=str, required=True)
+    p.add_argument("--ref", type=str, required=True)
+    p.add_argument("--contigs", type=str, default=None)
+    p.add_argument("--chunk_len", type=int, default=500000)
+    p.add_argument("--output", "-o", type=str, required=True)
+    p.add_argument("--bed", action="store_true", default=False)
+    p.add_argument("--sort", action="store_true", default=False)
+    p.add_argument("--gzip", action="store_true", default=False)
+    p.add_argument("--modtype", type=str, default="5mC", choices=["5mC"])
+    p.add_argument("--call_mode", type=str, default="count", choices=["count", "aggregate"])
+    p.add_argument("--prob_cf", type=float, default=0.0)
+    p.add_argument("--no_amb_cov", action="store_true", default=False)
+    p.add_argument("--hap_tag", type=str, default="HP")
+    p.add_argument("--mapq", type=int, default=1)
+    p.add_argument("--identity", type=float, default=0.0)
+    p.add_argument("--no_supplementary", action="store_true", default=False)
+    p.add_argument("--motifs", type=str, default="CG")
+    p.add_argument("--mod_loc", type=int, default=0)
+    p.add_argument("--no_comb", action="store_true", default=False)
+    p.add_argument("--refsites_only", action="store_true", default=False)
+    p.add_argument("--refsites_all", action="store_true", default=False)
+    p.add_argument("--no_hap", action="store_true", default=False)
+    p.add_argument("--base_clip", type=int, default=0)
+    p.add_argument("--aggre_model", "-m", type=str, default=None)
+    p.add_argument("--model_type", type=str, default="attbigru", choices=["attbilstm", "attbigru"])
+    p.add_argument("--seq_len", type=int, default=11)
+    p.add_argument("--class_num", type=int, default=1)
+    p.add_argument("--layer_rnn", type=int, default=1)
+    p.add_argument("--hid_rnn", type=int, default=32)
+    p.add_argument("--bin_size", type=int, default=20)
+    p.add_argument("--cov_cf", type=int, default=4)
+    p.add_argument("--only_close", action="store_true", default=False)
+    p.add_argument("--discrete", action="store_true", default=False)
+    p.add_argument("--tseed", type=int, default=1234)
+    p.add_argument("--h0", type=str, default="reference", choices=["reference", "zeros"],
+                   help="ccsmeth_b200 only: GRU initial state of the aggregate model: the reference's per-region "
+                        "seeded torch.randn stream (default) or zeros")
+    return p
+
+
+def main(argv=None):
+    call_freqb(build_parser().parse_args(argv))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -436,3 +436,157 @@ int64_t ccsm_bam_tag_records(const uint8_t* buf, const ccsm_bam_rec* recs, int32
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// call_freqb, host half: per aligned read, the modification calls carried by its MM/ML tags projected onto the
+// reference through the CIGAR (reference call_mods_freq_bam.py:118-168 _get_moddict_in_tags, :457-540 the read
+// loop of _readmods_to_bed_of_one_region).  Output: one tuple per call that lands on an aligned reference base.
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int64_t ccsm_bam_modcalls(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t n_recs, const ccsm_modcall_opts* o,
+                          int32_t* ref_id, int32_t* ref_pos, uint8_t* ml, uint8_t* hap, uint8_t* strand, int64_t cap,
+                          int32_t* n_reads_used) {
+  if (!buf || !recs || n_recs < 0 || !o || !n_reads_used || cap < 0 ||
+      (cap > 0 && (!ref_id || !ref_pos || !ml || !hap || !strand))) {
+    set_error("ccsm_bam_modcalls: bad argument");
+    return CCSM_EINVAL;
+  }
+  int64_t n_out = 0;
+  int32_t used = 0;
+  std::vector<int32_t> cpos;       // positions of 'C' in the forward (original) read
+  std::vector<int32_t> q_ml;       // query position (alignment orientation) -> ML value, -1 = no call
+  for (int32_t i = 0; i < n_recs; ++i) {
+    const ccsm_bam_rec& rec = recs[i];
+    // read filters (:470-480)
+    if (rec.flag & (0x4 | 0x100 | 0x400)) continue;
+    if (o->no_supplementary && (rec.flag & 0x800)) continue;
+    if (rec.mapq < o->mapq) continue;
+    const uint8_t* r = buf + rec.off + 4;
+    const uint8_t* end = r + rec.len;
+    const int l_name = r[8];
+    const int32_t rid = rd_i32(r + 0), pos0 = rd_i32(r + 4);
+    const uint8_t* cig = r + 32 + l_name;
+    const uint8_t* seq = cig + 4LL * rec.n_cigar;
+    const bool reverse = rec.flag & 0x10;
+    // aux scan: MM:Z, ML:B:C, hap tag, NM
+    const uint8_t* a = r + rec.aux_off;
+    const char* mm = nullptr;
+    const uint8_t* mlp = nullptr;
+    int64_t ml_n = -1;
+    int32_t hp = 0, nm = 0;
+    bool ok = true;
+    while (a < end) {
+      const int64_t sz = aux_size(a, end);
+      if (sz < 0) { ok = false; break; }
+      const char t0 = (char)a[0], t1 = (char)a[1];
+      if (t0 == 'M' && t1 == 'M' && a[2] == 'Z') mm = (const char*)a + 3;
+      else if (t0 == 'M' && t1 == 'L' && a[2] == 'B' && (a[3] == 'C' || a[3] == 'c')) { mlp = a + 8; ml_n = (uint32_t)rd_i32(a + 4); }
+      else if (t0 == o->hap_tag[0] && t1 == o->hap_tag[1]) { int32_t v; if (aux_int(a, &v)) hp = v; }
+      else if (t0 == 'N' && t1 == 'M') { int32_t v; if (aux_int(a, &v)) nm = v; }
+      a += sz;
+    }
+    if (!ok) {
+      set_error("ccsm_bam_modcalls: bad aux field in record %d", i);
+      return CCSM_EINVAL;
+    }
+    (void)nm;
+    if (o->identity > 0.0) {
+      // compute_pct_identity (process_utils.py:174-186): matches (M, =) over all aligned ops but clips
+      double nalign = 0, nmatch = 0;
+      for (int c = 0; c < rec.n_cigar; ++c) {
+        const uint32_t v = (uint32_t)rd_i32(cig + 4 * c);
+        const int op = v & 15;
+        if (op != 4 && op != 5 && op <= 9) nalign += v >> 4;
+        if (op == 0 || op == 7) nmatch += v >> 4;
+      }
+      const double ident = nalign > 0 ? nmatch / nalign : 0.0;
+      if (ident < o->identity) continue;
+    }
+    ++used;
+    if (!mm || !mlp) continue;  // no MM/ML: the read counts as used but carries no calls
+    // the first MM entry for C+m (optionally followed by '?' or '.'), :131-141
+    const char* x = mm;
+    const char* hit = nullptr;
+    while (*x) {
+      const char* e = x;
+      while (*e && *e != ';') ++e;
+      if (e - x >= 3 && x[0] == 'C' && x[1] == '+' && x[2] == 'm') { hit = x; break; }
+      x = *e ? e + 1 : e;
+    }
+    if (!hit) continue;
+    const char* q = hit + 3;
+    if (*q == '?' || *q == '.') ++q;
+    if (*q != ',') continue;  // no positions listed
+    ++q;
+    // C positions of the forward read
+    const int32_t L = rec.l_seq;
+    cpos.clear();
+    for (int32_t f = 0; f < L; ++f) {
+      const int32_t j = reverse ? L - 1 - f : f;
+      const int nib = (j & 1) ? (seq[j >> 1] & 15) : (seq[j >> 1] >> 4);
+      // forward base is C  <=>  stored base is C (forward strand) or G (reverse strand)
+      if (nib == (reverse ? 4 : 2)) cpos.push_back(f);
+    }
+    q_ml.assign((size_t)L, -1);
+    int64_t base_count = 0, n_mod = 0;
+    bool bad = false;
+    while (true) {
+      char* endp = nullptr;
+      const long d = strtol(q, &endp, 10);
+      if (endp == q) { bad = true; break; }
+      base_count += d + 1;  // _get_mm_position_iters (:110-116)
+      if (base_count - 1 >= (int64_t)cpos.size() || base_count < 1) { bad = true; break; }  // IndexError -> {}
+      if (n_mod >= ml_n) { bad = true; break; }                                             // MM longer than ML
+      const int32_t fpos = cpos[(size_t)(base_count - 1)];
+      const int32_t qpos = reverse ? L - 1 - fpos : fpos;
+      q_ml[(size_t)qpos] = mlp[n_mod];
+      ++n_mod;
+      q = endp;
+      if (*q == ',') { ++q; continue; }
+      break;
+    }
+    if (bad || n_mod != ml_n) continue;  // assertion len(modbases) == len(mltag) (:147)
+    const int hv = (hp == 1 || hp == 2) ? hp : 0;
+    // aligned pairs, matches only (M, =, X), then the optional clip of the PAIR list (:489-491)
+    int64_t n_pairs = 0;
+    for (int c = 0; c < rec.n_cigar; ++c) {
+      const uint32_t v = (uint32_t)rd_i32(cig + 4 * c);
+      const int op = v & 15;
+      if (op == 0 || op == 7 || op == 8) n_pairs += v >> 4;
+    }
+    const int64_t p_lo = o->base_clip > 0 ? o->base_clip : 0;
+    const int64_t p_hi = o->base_clip > 0 ? n_pairs - o->base_clip : n_pairs;
+    int64_t pi = 0;
+    int32_t qp = 0, rp = pos0;
+    for (int c = 0; c < rec.n_cigar; ++c) {
+      const uint32_t v = (uint32_t)rd_i32(cig + 4 * c);
+      const int op = v & 15;
+      const int32_t ln = (int32_t)(v >> 4);
+      if (op == 0 || op == 7 || op == 8) {
+        for (int32_t k = 0; k < ln; ++k, ++pi) {
+          if (pi >= p_lo && pi < p_hi && qp + k < L && q_ml[(size_t)(qp + k)] >= 0) {
+            if (n_out < cap) {
+              ref_id[n_out] = rid;
+              ref_pos[n_out] = rp + k;
+              ml[n_out] = (uint8_t)q_ml[(size_t)(qp + k)];
+              hap[n_out] = (uint8_t)hv;
+              strand[n_out] = reverse ? 1 : 0;
+            }
+            ++n_out;
+          }
+        }
+        qp += ln;
+        rp += ln;
+      } else if (op == 1 || op == 4) {
+        qp += ln;
+      } else if (op == 2 || op == 3) {
+        rp += ln;
+      }  // H, P: neither
+    }
+  }
+  *n_reads_used = used;
+  return n_out;  // > cap: the caller retries with a larger buffer
+}
+
+}  // extern "C"

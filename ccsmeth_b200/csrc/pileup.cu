@@ -30,7 +30,7 @@ struct PuState {
   DevBuf pos, ptr, ml, hap, lut;
   DevBuf cov, filt, nmod, flag, cidx, blocksum;          // per (group, site)
   DevBuf c_pos, c_histo, c_site, c_out;                  // compact high-coverage lists of the three groups
-  DevBuf r_cov, r_cnt, r_freq, h0;
+  DevBuf r_cov, r_cnt, r_freq, r_kind, h0;
   ccsm_pileup_opts opts{};
   int64_t n = -1;
   int64_t n_high[3] = {0, 0, 0};
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256) pileup_count_kernel(int64_t n, const long
                                                            const uint8_t* __restrict__ ml, const uint8_t* __restrict__ hap,
                                                            const PileupLut* __restrict__ lut, ccsm_pileup_opts o,
                                                            int* __restrict__ flag, int* __restrict__ r_cov,
-                                                           double* __restrict__ r_cnt, double* __restrict__ r_freq) {
+                                                           double* __restrict__ r_cnt, double* __restrict__ r_freq,
+                                                           uint8_t* __restrict__ r_kind) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 3 * n) return;
   const int g = (int)(idx / n);
@@ -91,6 +92,9 @@ __global__ void __launch_bounds__(256) pileup_count_kernel(int64_t n, const long
   }
   const bool high = o.call_mode == 1 && cov >= o.cov_cf && cov > 0;
   flag[idx] = high ? 1 : 0;
+  // which of the reference's value types the result has: 0 None, 1 count path with an integer count, 2 count path
+  // with np.round(len * freq, 2), 3 model path (float32 values)
+  r_kind[idx] = cov == 0 ? 0 : high ? 3 : (o.no_amb_cov || filt == cov) ? 1 : 2;
   if (cov == 0) {
     r_cov[idx] = -1;  // "None" for this group (a coverage of 0 is a legitimate --no_amb_cov result)
     r_cnt[idx] = 0.0;
@@ -227,7 +231,7 @@ void pu_release(ccsm_model* m) {
   PuState* s = m->pu;
   if (!s) return;
   for (DevBuf* b : {&s->pos, &s->ptr, &s->ml, &s->hap, &s->lut, &s->cov, &s->filt, &s->nmod, &s->flag, &s->cidx,
-                    &s->blocksum, &s->c_pos, &s->c_histo, &s->c_site, &s->c_out, &s->r_cov, &s->r_cnt, &s->r_freq, &s->h0})
+                    &s->blocksum, &s->c_pos, &s->c_histo, &s->c_site, &s->c_out, &s->r_cov, &s->r_cnt, &s->r_freq, &s->r_kind, &s->h0})
     b->release();
   delete s;
   m->pu = nullptr;
@@ -302,6 +306,7 @@ int ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* o, int64_t n, 
   CCSM_TRY(s->r_cov.reserve((size_t)3 * n * 4));
   CCSM_TRY(s->r_cnt.reserve((size_t)3 * n * 8));
   CCSM_TRY(s->r_freq.reserve((size_t)3 * n * 8));
+  CCSM_TRY(s->r_kind.reserve((size_t)3 * n + 16));
   const int nb = (int)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
   CCSM_TRY(s->blocksum.reserve((size_t)(nb + 4) * 8));
   CCSM_CUDA(cudaMemcpyAsync(s->lut.p, &L, sizeof(L), cudaMemcpyHostToDevice, st));
@@ -311,7 +316,7 @@ int ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* o, int64_t n, 
   if (hap) CCSM_CUDA(cudaMemcpyAsync(s->hap.p, hap, (size_t)total, cudaMemcpyHostToDevice, st));
   pileup_count_kernel<<<(unsigned)((3 * n + 255) / 256), 256, 0, st>>>(
       n, s->ptr.as<long long>(), s->ml.as<uint8_t>(), hap ? s->hap.as<uint8_t>() : nullptr, s->lut.as<PileupLut>(), *o,
-      s->flag.as<int>(), s->r_cov.as<int>(), s->r_cnt.as<double>(), s->r_freq.as<double>());
+      s->flag.as<int>(), s->r_cov.as<int>(), s->r_cnt.as<double>(), s->r_freq.as<double>(), s->r_kind.as<uint8_t>());
   count_launch();
   long long totals[3] = {0, 0, 0};
   if (o->call_mode == 1) {
@@ -333,7 +338,7 @@ int ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* o, int64_t n, 
 }
 
 int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_hp1, const float* h0_hp2, int32_t* cov,
-                            double* cnt_mod, double* freq) {
+                            double* cnt_mod, double* freq, uint8_t* kind) {
   if (!m || !m->pu || m->pu->n < 0) {
     set_error("ccsm_pileup_finish_host: no resident pileup (call ccsm_pileup_begin_host first)");
     return CCSM_ESTATE;
@@ -377,6 +382,7 @@ int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_
   CCSM_CUDA(cudaMemcpyAsync(cov, s->r_cov.p, (size_t)3 * n * 4, cudaMemcpyDeviceToHost, st));
   CCSM_CUDA(cudaMemcpyAsync(cnt_mod, s->r_cnt.p, (size_t)3 * n * 8, cudaMemcpyDeviceToHost, st));
   CCSM_CUDA(cudaMemcpyAsync(freq, s->r_freq.p, (size_t)3 * n * 8, cudaMemcpyDeviceToHost, st));
+  if (kind) CCSM_CUDA(cudaMemcpyAsync(kind, s->r_kind.p, (size_t)3 * n, cudaMemcpyDeviceToHost, st));
   CCSM_CUDA(cudaStreamSynchronize(st));
   CCSM_CUDA(cudaGetLastError());
   return CCSM_OK;

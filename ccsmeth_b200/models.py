@@ -444,15 +444,18 @@ class AggrAttRNN(_NativeModule):
         self._pu_n = len(pos)
         return tuple(int(v) for v in n_high)
 
-    def pileup_finish(self, h0=(None, None, None)):
-        """-> (cov (3, n) int32, cnt_mod (3, n) float64, freq (3, n) float64), rows = all reads / haplotype 1 / 2;
-        cov == -1 marks "no call of this group at this site" (the reference's None)."""
+    def pileup_finish(self, h0=(None, None, None), with_kind=False):
+        """-> (cov (3, n) int32, cnt_mod (3, n) float64, freq (3, n) float64[, kind (3, n) uint8]), rows = all reads /
+        haplotype 1 / 2; cov == -1 marks "no call of this group at this site" (the reference's None); kind: see
+        include/ccsm.h (which Python / NumPy value types the reference would hold)."""
         handle, _ = self._ensure_handle()
         n = self._pu_n
         cov = np.full((3, n), -1, dtype=np.int32)
         cnt = np.zeros((3, n), dtype=np.float64)
         freq = np.zeros((3, n), dtype=np.float64)
         hs = [None if h is None else _dev_f32(h, torch.device("cpu")) for h in h0]
+        kind = np.zeros((3, n), dtype=np.uint8)
         _lib.check(_lib.load().ccsm_pileup_finish_host(handle, *[None if h is None else h.data_ptr() for h in hs],
-                                                       cov.ctypes.data, cnt.ctypes.data, freq.ctypes.data))
-        return cov, cnt, freq
+                                                       cov.ctypes.data, cnt.ctypes.data, freq.ctypes.data,
+                                                       kind.ctypes.data))
+        return (cov, cnt, freq, kind) if with_kind else (cov, cnt, freq)

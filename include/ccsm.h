@@ -238,9 +238,11 @@ int  ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* opts, int64_t
 
 /* Step 2 (host buffers): histograms -> fused aggregate model (windows formed in the kernel) -> results.
  * h0_*: host (2, n_high[g], hidden) float32 or NULL (zeros).  Outputs are (3, n_sites) arrays, group-major:
- * cov = coverage reported for the site (-1 = the group has no call there: the reference's None), cnt_mod, freq. */
+ * cov = coverage reported for the site (-1 = the group has no call there: the reference's None), cnt_mod, freq, and
+ * (optional) kind = which value types the reference would hold: 0 None, 1 count path with an integer count, 2 count
+ * path with np.round(len * freq, 2) (float64), 3 model path (cnt_mod and freq are float32 values). */
 int  ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_hp1, const float* h0_hp2,
-                             int32_t* cov, double* cnt_mod, double* freq);
+                             int32_t* cov, double* cnt_mod, double* freq, uint8_t* kind);
 
 /* ---- host I/O helpers: BGZF block codec on a thread team (SAM/BAM spec 4.1) --------------------------------
  * The reference reads and writes BAM through pysam/htslib with `threads=` (extract_features.py:60-73,
@@ -289,6 +291,23 @@ int     ccsm_bam_index(const uint8_t* buf, int64_t n_bytes, const ccsm_bam_filte
 int64_t ccsm_bam_tag_records(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t n_recs, int32_t keep_pulse,
                              const int64_t* site_begin, const int32_t* mm, const uint8_t* ml, uint8_t* out,
                              int64_t out_cap, int32_t* n_with_mm);
+
+/* call_freqb, host half: walks aligned records (as indexed by ccsm_bam_index) and emits one tuple per modification
+ * call of the read's MM/ML tags ("C+m", first entry) that sits on an aligned reference base -- the work of
+ * _get_moddict_in_tags (reference call_mods_freq_bam.py:118-168) and of the read loop of
+ * _readmods_to_bed_of_one_region (:466-520, matches-only aligned pairs, --base_clip on the pair list).  Arrays have
+ * `cap` entries; the return value is the number of calls found (if > cap nothing beyond cap was written: retry), or a
+ * negative CCSM_E* code.  strand: 0 forward, 1 reverse; hap: the --hap_tag value if 1 or 2, else 0. */
+typedef struct ccsm_modcall_opts {
+  int32_t mapq;              /* --mapq */
+  int32_t no_supplementary;  /* --no_supplementary */
+  int32_t base_clip;         /* --base_clip */
+  char    hap_tag[4];        /* --hap_tag, two characters (default "HP") */
+  double  identity;          /* --identity */
+} ccsm_modcall_opts;
+int64_t ccsm_bam_modcalls(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t n_recs, const ccsm_modcall_opts* opts,
+                          int32_t* ref_id, int32_t* ref_pos, uint8_t* ml, uint8_t* hap, uint8_t* strand, int64_t cap,
+                          int32_t* n_reads_used);
 
 /* Introspection used by tests: copies the last layer-stack output of the most recent forward chunk.
  * Returns the number of floats written (<= cap) or a negative error. */

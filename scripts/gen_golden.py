@@ -298,8 +298,87 @@ def gen_pileup():
     print("pileup_region: %d sites, %d calls, aggregate mean freq %.4f" % (n, len(ml), np.nanmean(save["aggr"][0, :, 2])))
 
 
+class DuckBam:
+    """What the reference's region worker needs from pysam.AlignmentFile: fetch(contig, start, stop) over records that
+    overlap the interval, in file order (records are ccsmeth_b200.bamio.BamRecord)."""
+
+    def __init__(self, path):
+        from ccsmeth_b200.bamio import BamReader
+        self.recs = list(BamReader(path))
+
+    def fetch(self, contig=None, start=None, stop=None):
+        for r in self.recs:
+            if r.is_unmapped or r.reference_name != contig:
+                continue
+            if r.pos < stop and r.reference_end > start:
+                yield r
+
+
+def freqb_args(**kw):
+    import argparse
+    a = argparse.Namespace(call_mode="count", cov_cf=4, bin_size=20, prob_cf=0.0, no_amb_cov=False, no_hap=False, seq_len=11,
+                           layer_rnn=1, class_num=1, hid_rnn=32, model_type="attbigru", aggre_model=refimport.AGGR_CKPT,
+                           only_close=False, discrete=False, tseed=1234, modtype="5mC", mod_loc=0, motifs="CG",
+                           no_comb=False, refsites_only=False, refsites_all=False, no_supplementary=False, mapq=1,
+                           identity=0.0, hap_tag="HP", base_clip=0, contigs=None, chunk_len=10000, bed=False)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+FREQB_CASES = (("count", {}), ("count_cf3", {"prob_cf": 0.3}), ("count_cf3_noamb", {"prob_cf": 0.3, "no_amb_cov": True}),
+               ("count_nocomb", {"no_comb": True}), ("count_refsites", {"refsites_only": True}),
+               ("count_clip_nosupp_ident", {"base_clip": 15, "no_supplementary": True, "identity": 0.995, "mapq": 20}),
+               ("aggregate", {"call_mode": "aggregate"}), ("aggregate_nohap", {"call_mode": "aggregate", "no_hap": True}))
+
+
+def gen_freqb():
+    """Section 8f-3 host half: the reference's region worker `_readmods_to_bed_of_one_region` + `_write_one_line`
+    (call_mods_freq_bam.py:457-594, 626-634) over a synthetic aligned modbam (tests/bamsynth.make_aligned_modbam),
+    one text file per flag combination and output group, in both output formats."""
+    sys.path.insert(0, ROOT)
+    from tests.bamsynth import make_aligned_modbam
+    ref = refimport.import_reference()
+    import ccsmeth.call_mods_freq_bam as rfb
+    from ccsmeth.utils.ref_reader import DNAReference
+    from ccsmeth.utils.process_utils import get_motif_seqs
+    d = os.path.join(OUT, "freqb")
+    os.makedirs(d, exist_ok=True)
+    bam, fa = os.path.join(d, "synth.aligned.modbam.bam"), os.path.join(d, "synth.fa")
+    make_aligned_modbam(bam, fa)
+    dnacontigs = DNAReference(fa).getcontigs()
+    reader = DuckBam(bam)
+    import io
+    texts = {}
+    for tag, kw in FREQB_CASES:
+        args = freqb_args(**kw)
+        motifs = get_motif_seqs(args.motifs)
+        mf = motifs if (args.refsites_only or args.refsites_all) else None
+        chunks = rfb._get_reference_chunks(dnacontigs, args.contigs, args.chunk_len, args.motifs)
+        outs = {(g, fmt): io.StringIO() for g in ("all", "hp1", "hp2") for fmt in ("bed", "freq.txt")}
+        for region in chunks:
+            beds = rfb._readmods_to_bed_of_one_region(reader, region, dnacontigs, mf, args)
+            if len(beds[0]) == 0:
+                continue
+            for g, items in zip(("all", "hp1", "hp2"), beds):
+                for it in items:
+                    rfb._write_one_line(it, outs[(g, "bed")], True)
+                    rfb._write_one_line(it, outs[(g, "freq.txt")], False)
+        for (g, fmt), f in outs.items():
+            if fmt == "bed" and not (g == "all" and tag in ("count", "aggregate")):
+                continue  # the bed format of the same tuples: two samples are enough
+            texts["%s.%s.%s" % (tag, g, fmt)] = np.frombuffer(f.getvalue().encode("ascii"), dtype=np.uint8)
+        print("freqb", tag, {g: outs[(g, "bed")].getvalue().count("\n") for g in ("all", "hp1", "hp2")})
+    texts["chunks"] = np.frombuffer("".join("%s\t%d\t%d\n" % c for c in
+                                            rfb._get_reference_chunks(dnacontigs, None, 10000, "CG")).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(d, "reference_outputs.npz"), **texts)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "freqb":
+        gen_freqb()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "demo":
         gen_demo()
         sys.exit(0)
@@ -310,6 +389,7 @@ if __name__ == "__main__":
     gen_att2s()
     gen_aggr()
     gen_pileup()
+    gen_freqb()
     gen_demo()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

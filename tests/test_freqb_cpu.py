@@ -1,0 +1,146 @@
+"""call_freqb host half without a GPU: reference chunks, FASTA reader, the native MM/ML -> reference projection
+(ccsm_bam_modcalls) against the oracle restatement, and the region pileup builder + numpy pileup oracle against the
+output of the reference's own region worker (tests/golden/freqb/reference_outputs.npz)."""
+import argparse
+import io
+import os
+
+import numpy as np
+import pytest
+
+from ccsmeth_b200 import _lib, call_freqb as cf
+from ccsmeth_b200.bamio import BamReader
+from ccsmeth_b200.bamstream import BamPieceReader
+from oracle import freqb_numpy, pileup_numpy
+from tests.conftest import GOLDEN
+
+D = os.path.join(GOLDEN, "freqb")
+BAM, FA = os.path.join(D, "synth.aligned.modbam.bam"), os.path.join(D, "synth.fa")
+
+
+@pytest.fixture(scope="module")
+def ref_out():
+    with np.load(os.path.join(D, "reference_outputs.npz")) as z:
+        return {k: z[k].tobytes().decode("ascii") for k in z.files}
+
+
+def _args(**kw):
+    a = cf.build_parser().parse_args(["--input_bam", BAM, "--ref", FA, "-o", "out", "--chunk_len", "10000"])
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def test_fasta_and_chunks_match_the_reference(ref_out):
+    contigs = cf.read_fasta(FA)
+    assert sorted(contigs) == ["chrA", "chrB"] and contigs["chrA"] == contigs["chrA"].upper()
+    chunks = cf.get_reference_chunks(contigs, None, 10000, "CG")
+    assert "".join("%s\t%d\t%d\n" % c for c in chunks) == ref_out["chunks"]
+    assert ("chrA", 0, 10001) in chunks and ("chrA", 10001, 20000) in chunks  # the CG on the boundary moved it
+
+
+def _native_calls(**kw):
+    o = _lib.ModcallOpts(kw.get("mapq", 1), int(kw.get("no_supplementary", False)), kw.get("base_clip", 0),
+                         kw.get("hap_tag", "HP").encode(), kw.get("identity", 0.0))
+    rd = BamPieceReader(BAM, _lib.BamFilter(0, 0, 0, 0, 0), threads=2, piece_bytes=40000, align_to=1)
+    calls = cf.ModCalls()
+    used = 0
+    n_pieces = 0
+    for piece in rd:
+        used += calls.add_piece(piece, o)
+        n_pieces += 1
+    assert n_pieces > 1
+    return calls.arrays(), used
+
+
+@pytest.mark.parametrize("kw", [{}, {"base_clip": 15, "no_supplementary": True, "identity": 0.995, "mapq": 20},
+                                {"hap_tag": "XX"}])
+def test_native_modcalls_match_the_oracle(kw):
+    (rid, pos, ml, hap, strand), used = _native_calls(**kw)
+    exp, n_used = [], 0
+    for rec in BamReader(BAM):
+        c = freqb_numpy.read_calls(rec, **kw)
+        if c is not None:
+            n_used += 1
+            exp += c
+    assert used == n_used and len(exp) == len(rid) > 1000
+    got = list(zip(rid.tolist(), pos.tolist(), ml.tolist(), hap.tolist(), strand.tolist()))
+    assert got == exp  # same calls in the same order (file order, then along the read)
+    if kw.get("hap_tag") == "XX":
+        assert not hap.any()
+    else:
+        assert set(np.unique(hap)) == {0, 1, 2}
+
+
+def test_malformed_mm_tags_yield_no_calls():
+    from tests.bamsynth import make_record
+    import struct
+    seq = "ACGTCGCGTTCGAACCGG" * 3
+    def rec(mm, ml):
+        tags = b"MMZ" + mm.encode() + b"\x00" + b"MLBC" + struct.pack("<I", len(ml)) + bytes(ml)
+        return make_record("r", seq, None, None, None, None, fn=None, flag=0, cigar=((0, len(seq)),), extra_tags=tags,
+                           mapq=60, ref_id=0, pos=10)
+    good = rec("C+m?,0,1;", [10, 200])
+    assert [c[1:3] for c in freqb_numpy.read_calls(good)] == [(11, 10), (16, 200)]
+    for bad in (rec("C+m?,0,1;", [10]), rec("C+m?,0,400;", [1, 2]), rec("C+h?,0,1;", [1, 2]), rec("C+m?;", [])):
+        assert freqb_numpy.read_calls(bad) == []
+    # the native walker agrees on each of them
+    import ctypes
+    from ccsmeth_b200.bamstream import REC_DTYPE
+    from ccsmeth_b200.extract_features import READ_DTYPE
+    lib = _lib.load()
+    for r in (good, rec("C+m?,0,1;", [10]), rec("C+m?,0,400;", [1, 2]), rec("C+h?,0,1;", [1, 2]), rec("C+m?;", [])):
+        buf = np.frombuffer(struct.pack("<i", len(r.raw)) + r.raw, dtype=np.uint8)
+        recs, descs = np.zeros(4, REC_DTYPE), np.zeros(4, READ_DTYPE)
+        nr, nd, cons = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int64(0)
+        f = _lib.BamFilter(0, 0, 0, 0, 0)
+        _lib.check(lib.ccsm_bam_index(buf.ctypes.data, len(buf), ctypes.byref(f), recs.ctypes.data, 4, descs.ctypes.data,
+                                      ctypes.byref(nr), ctypes.byref(nd), ctypes.byref(cons)))
+        o = _lib.ModcallOpts(1, 0, 0, b"HP", 0.0)
+        out = [np.zeros(64, dt) for dt in (np.int32, np.int32, np.uint8, np.uint8, np.uint8)]
+        used = ctypes.c_int32(0)
+        n = lib.ccsm_bam_modcalls(buf.ctypes.data, recs.ctypes.data, 1, ctypes.byref(o), *[a.ctypes.data for a in out], 64,
+                                  ctypes.byref(used))
+        exp = freqb_numpy.read_calls(r)
+        assert n == len(exp) and [(int(out[1][k]), int(out[2][k])) for k in range(n)] == [c[1:3] for c in exp]
+
+
+@pytest.mark.parametrize("tag,kw", [("count", {}), ("count_cf3", {"prob_cf": 0.3}),
+                                    ("count_cf3_noamb", {"prob_cf": 0.3, "no_amb_cov": True}),
+                                    ("count_nocomb", {"no_comb": True}), ("count_refsites", {"refsites_only": True}),
+                                    ("count_clip_nosupp_ident", {"base_clip": 15, "no_supplementary": True,
+                                                                 "identity": 0.995, "mapq": 20})])
+def test_host_chain_with_the_pileup_oracle_reproduces_the_reference_files(ref_out, tag, kw):
+    """Native projection -> region pileups -> (numpy pileup oracle instead of the device) -> text lines ==
+    the reference region worker's output, byte for byte, in count mode."""
+    args = _args(**kw)
+
+    class OracleModel:  # stands in for AggrAttRNN.pileup_begin / pileup_finish
+        def pileup_begin(self, refpos, ptr, ml, hap, **k):
+            self.a = (refpos, ptr, ml, hap, k)
+            return (0, 0, 0)
+
+        def pileup_finish(self, h0, with_kind=False):
+            refpos, ptr, ml, hap, k = self.a
+            out = pileup_numpy.call_region(refpos, ptr, ml, hap, None, call_mode="count", cov_cf=k["cov_cf"],
+                                           prob_cf=k["prob_cf"], no_amb_cov=k["no_amb_cov"], no_hap=k["no_hap"])
+            n = len(refpos)
+            cov = np.where(np.isnan(out[..., 0]), -1, out[..., 0]).astype(np.int32)
+            kind = np.zeros((3, n), np.uint8)
+            for g in range(3):
+                for i in range(n):
+                    if cov[g, i] >= 0:
+                        sel = slice(ptr[i], ptr[i + 1])
+                        probs = [pileup_numpy.cal_mod_prob(int(v)) for v, h in zip(ml[sel], hap[sel]) if g == 0 or h == g]
+                        filt = sum(1 for p in probs if not abs(p - (1 - p)) < k["prob_cf"])
+                        kind[g, i] = 1 if (k["no_amb_cov"] or filt == len(probs)) else 2
+            return cov, np.nan_to_num(out[..., 1]), np.nan_to_num(out[..., 2]), kind
+
+    contigs = cf.read_fasta(FA)
+    bufs = [io.StringIO() for _ in range(3)]
+    for _, *beds in cf.iter_region_results(args, OracleModel(), contigs, BAM):
+        for g in range(3):
+            for item in beds[g]:
+                cf.write_one_line(item, bufs[g], False)
+    for g, name in enumerate(("all", "hp1", "hp2")):
+        assert bufs[g].getvalue() == ref_out["%s.%s.freq.txt" % (tag, name)], (tag, name)
