@@ -2,8 +2,8 @@
 
 Keeps the reference's flag surface and output format (ccsmeth/call_mods_freq_bam.py:741-845, `_write_one_line`
 :626-634, file names :639-642) for the default path: symmetric ``--motifs CG``-style sites, count or aggregate mode,
-haplotype split by ``--hap_tag``, ``--refsites_only`` motif filter, ``--base_clip``.  Not offered: ``--refsites_all``
-(zero-probability entries for uncalled reference sites), ``--discrete``, ``--only_close``, bed sorting / tabix.
+haplotype split by ``--hap_tag``, ``--refsites_only`` motif filter, ``--base_clip``, ``--discrete``, ``--only_close``.
+Not offered: ``--refsites_all`` (zero-probability entries for uncalled reference sites), bed sorting / tabix.
 
 Where the reference forks region workers that each ``fetch`` their reads through pysam and pile calls up in Python
 dictionaries (:457-540), this streams the sorted BAM once: native BGZF inflate + record index (bamstream.py), native
@@ -154,6 +154,20 @@ def draw_region_h0(args, n_high):
     return out
 
 
+def discretize_score(modprob, coverage):
+    """--discrete (reference call_mods_freq_bam.py:240-262): push the model frequency of a site towards whole read
+    counts.  Scalar post-processing of the float32 model output, same expressions as the reference."""
+    if modprob > 0.66:
+        mod_reads = int(np.ceil(modprob * float(coverage)))
+    elif modprob <= 0.33:
+        mod_reads = int(np.floor(modprob * float(coverage)))
+    else:
+        mod_reads = round(coverage * modprob, 2)
+    unmod_reads = int(coverage) - mod_reads
+    adjusted_score = 0.0 if mod_reads == 0 else float(mod_reads) / (mod_reads + unmod_reads)
+    return mod_reads, unmod_reads, adjusted_score
+
+
 def call_region(model, args, contig_seq, ref_name, pileups, motifs_filter):
     """One region's pileups -> (bed_all, bed_hp1, bed_hp2) lists of (ref_name, refpos, strand, cov, cnt, freq), the
     reference's `_readmods_to_bed_of_one_region` return value (:553-594)."""
@@ -165,7 +179,8 @@ def call_region(model, args, contig_seq, ref_name, pileups, motifs_filter):
         mset = set(motifs_filter)
     for ch, refpos, ptr, ml, hap in pileups:
         n_high = model.pileup_begin(refpos, ptr, ml, hap, call_mode=args.call_mode, cov_cf=args.cov_cf,
-                                    prob_cf=args.prob_cf, no_amb_cov=args.no_amb_cov, no_hap=args.no_hap)
+                                    prob_cf=args.prob_cf, no_amb_cov=args.no_amb_cov, no_hap=args.no_hap,
+                                    only_close=args.only_close)
         h0 = (None, None, None)
         if args.call_mode == "aggregate" and getattr(args, "h0", "reference") == "reference":
             h0 = draw_region_h0(args, n_high)
@@ -189,6 +204,8 @@ def call_region(model, args, contig_seq, ref_name, pileups, motifs_filter):
                     c, fr = np.float64(cnt[g, i]), float(freq[g, i])
                 else:
                     c, fr = np.float32(cnt[g, i]), np.float32(freq[g, i])
+                    if args.discrete:
+                        c, _, fr = discretize_score(fr, int(cov[g, i]))
                 beds[g].append((ref_name, p, ch, int(cov[g, i]), c, fr))
     return beds
 
@@ -250,8 +267,8 @@ def call_freqb(args):
         raise ValueError("--input_bam does not exist!")
     if not os.path.exists(args.ref):
         raise ValueError("--ref does not exist!")
-    if args.refsites_all or args.discrete or args.only_close:
-        raise ValueError("--refsites_all / --discrete / --only_close are not implemented by ccsmeth_b200")
+    if args.refsites_all:
+        raise ValueError("--refsites_all is not implemented by ccsmeth_b200")
     os.makedirs(os.path.dirname(os.path.abspath(args.output)), exist_ok=True)
     dnacontigs = read_fasta(args.ref)
     if args.call_mode == "aggregate":

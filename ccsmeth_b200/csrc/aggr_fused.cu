@@ -54,7 +54,7 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf
 template <int IN, int S>
 __global__ void __launch_bounds__(AG_THREADS, 2)
     aggr_fused_kernel(const float* __restrict__ packed, int64_t n, int L, int C, const float* __restrict__ offsets,
-                      const float* __restrict__ histos, const long long* __restrict__ site_pos,
+                      const float* __restrict__ histos, const long long* __restrict__ site_pos, int only_close,
                       const float* __restrict__ h0, float* scratch, float* __restrict__ out) {
   extern __shared__ __align__(16) float sm[];
   const AggrPacked lay = aggr_layout(IN, C);
@@ -98,15 +98,23 @@ __global__ void __launch_bounds__(AG_THREADS, 2)
             // zero histogram and a position 1000 bp beyond the ends outside the region
             const int64_t j = sidx[q] + t - L / 2;
             const long long centre = site_pos[sidx[q]];
+            // padded position of neighbour j (:279-280, 285-286)
+            const long long pj = j < 0 ? site_pos[0] - 1000 : j >= n ? site_pos[n - 1] + 1000 : site_pos[j];
+            float off;
+            if (only_close) {
+                // --only_close: 1 where the neighbour directly follows its predecessor as the next CpG (distance 2)
+                const long long pjm = j - 1 < 0 ? site_pos[0] - 1000 : j - 1 >= n ? site_pos[n - 1] + 1000 : site_pos[j - 1];
+                off = (pj - pjm == 2) ? 1.f : 0.f;
+            } else {
+                off = (float)llabs(pj - centre);
+            }
+            x[q][BINS] = off;
             if (j < 0 || j >= n) {
 #pragma unroll
               for (int k = 0; k < BINS; ++k) x[q][k] = 0.f;
-              const long long pp = j < 0 ? site_pos[0] - 1000 : site_pos[n - 1] + 1000;
-              x[q][BINS] = (float)llabs(pp - centre);
               continue;
             }
             hp = histos + (size_t)j * BINS;
-            x[q][BINS] = (float)llabs(site_pos[j] - centre);
           }
           if constexpr (BINS % 4 == 0) {
 #pragma unroll
@@ -320,22 +328,22 @@ int aggr_fused_upload(ccsm_model* m) {
 }
 
 static int aggr_launch(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const long long* site_pos,
-                       const float* h0, float* out, cudaStream_t st);
+                       int only_close, const float* h0, float* out, cudaStream_t st);
 
 int aggr_fused_forward(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
                        cudaStream_t st) {
-  return aggr_launch(m, n, offsets, histos, nullptr, h0, out, st);
+  return aggr_launch(m, n, offsets, histos, nullptr, 0, h0, out, st);
 }
 
 // Same model over per-site rows: site_histo (n, bins) and site_pos (n) of consecutive sites; the 11-site windows and
 // their |position offsets| are formed inside the kernel (84 B read per site instead of 924 B).
-int aggr_fused_forward_sites(ccsm_model* m, int64_t n, const long long* site_pos, const float* site_histo, const float* h0,
-                             float* out, cudaStream_t st) {
-  return aggr_launch(m, n, nullptr, site_histo, site_pos, h0, out, st);
+int aggr_fused_forward_sites(ccsm_model* m, int64_t n, const long long* site_pos, const float* site_histo, int only_close,
+                             const float* h0, float* out, cudaStream_t st) {
+  return aggr_launch(m, n, nullptr, site_histo, site_pos, only_close, h0, out, st);
 }
 
 static int aggr_launch(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const long long* site_pos,
-                       const float* h0, float* out, cudaStream_t st) {
+                       int only_close, const float* h0, float* out, cudaStream_t st) {
   const int IN = m->in_feat, C = m->cfg.num_classes;
   const AggrPacked lay = aggr_layout(IN, C);
   constexpr int COLS = AG_S * AG_THREADS;
@@ -351,7 +359,7 @@ static int aggr_launch(ccsm_model* m, int64_t n, const float* offsets, const flo
   const int grid = (int)(tiles < 2LL * sms ? tiles : 2LL * sms);
   CCSM_TRY(m->aggr_scratch.reserve((size_t)grid * m->cfg.seq_len * 2 * AG_H * COLS * sizeof(float)));
   aggr_fused_kernel<21, AG_S><<<grid, AG_THREADS, smem, st>>>(m->aggr_packed.as<float>(), n, m->cfg.seq_len, C, offsets, histos,
-                                                              site_pos, h0, m->aggr_scratch.as<float>(), out);
+                                                              site_pos, only_close, h0, m->aggr_scratch.as<float>(), out);
   count_launch();
   CCSM_CUDA(cudaGetLastError());
   return CCSM_OK;

@@ -149,8 +149,8 @@ bool aggr_fused_supported(const ccsm_model* m);
 int aggr_fused_upload(ccsm_model* m);
 int aggr_fused_forward(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
                        cudaStream_t st);
-int aggr_fused_forward_sites(ccsm_model* m, int64_t n, const long long* site_pos, const float* site_histo, const float* h0,
-                             float* out, cudaStream_t st);
+int aggr_fused_forward_sites(ccsm_model* m, int64_t n, const long long* site_pos, const float* site_histo, int only_close,
+                             const float* h0, float* out, cudaStream_t st);
 void pu_release(ccsm_model* m);
 
 // ---- device feature extraction (extract.cu)

@@ -271,10 +271,6 @@ int ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* o, int64_t n, 
     set_error("ccsm_pileup_begin_host: call_mode must be 0 (count) or 1 (aggregate)");
     return CCSM_EINVAL;
   }
-  if (o->discrete || o->only_close) {
-    set_error("ccsm_pileup_begin_host: --discrete / --only_close are not implemented");
-    return CCSM_EUNSUPPORTED;
-  }
   if (o->call_mode == 1 && (!m->finalized || !aggr_fused_supported(m))) {
     set_error("ccsm_pileup_begin_host: aggregate mode needs a finalized attbigru model (H = 32, 20 bins, one layer)");
     return CCSM_ESTATE;
@@ -372,7 +368,8 @@ int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_
       CCSM_CUDA(cudaMemcpyAsync(s->h0.p, h0s[g], (size_t)2 * nc * H * 4, cudaMemcpyHostToDevice, st));
       dh0 = s->h0.as<float>();
     }
-    CCSM_TRY(aggr_fused_forward_sites(m, nc, s->c_pos.as<long long>(), s->c_histo.as<float>(), dh0, s->c_out.as<float>(), st));
+    CCSM_TRY(aggr_fused_forward_sites(m, nc, s->c_pos.as<long long>(), s->c_histo.as<float>(), s->opts.only_close ? 1 : 0, dh0,
+                                      s->c_out.as<float>(), st));
     pileup_finish_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(nc, n, g, s->c_out.as<float>(), s->c_site.as<int>(),
                                                                         s->r_cov.as<int>(), s->r_cnt.as<double>(),
                                                                         s->r_freq.as<double>());

@@ -427,7 +427,7 @@ class AggrAttRNN(_NativeModule):
 
     # ---- call_freqb on the device: one region's pileup -> per-site frequencies (include/ccsm.h ccsm_pileup_*)
     def pileup_begin(self, refpos, ptr, ml, hap=None, call_mode="aggregate", cov_cf=4, prob_cf=0.0, no_amb_cov=False,
-                     no_hap=False):
+                     no_hap=False, only_close=False):
         """Uploads a region's pileup in CSR form (site i at reference position refpos[i] is covered by entries
         ptr[i]:ptr[i+1] of `ml` / `hap`) and returns n_high = (all, hp1, hp2): how many sites of each read group
         go through the aggregate model -- the n of the h0 tensors ``pileup_finish`` takes."""
@@ -437,7 +437,7 @@ class AggrAttRNN(_NativeModule):
                     None if hap is None else np.ascontiguousarray(hap, dtype=np.uint8))
         pos, ptr, ml, hap = self._pu
         o = _lib.PileupOpts({"count": 0, "aggregate": 1}[call_mode], int(cov_cf), float(prob_cf), int(bool(no_amb_cov)),
-                            int(bool(no_hap)), 0, 0)
+                            int(bool(no_hap)), 0, int(bool(only_close)))
         n_high = (ctypes.c_int64 * 3)()
         _lib.check(_lib.load().ccsm_pileup_begin_host(handle, ctypes.byref(o), len(pos), pos.ctypes.data, ptr.ctypes.data,
                                                       ml.ctypes.data, hap.ctypes.data if hap is not None else None, n_high))

@@ -223,8 +223,10 @@ typedef struct ccsm_pileup_opts {
   double  prob_cf;      /* --prob_cf */
   int32_t no_amb_cov;   /* --no_amb_cov */
   int32_t no_hap;       /* --no_hap: only the "all reads" group */
-  int32_t discrete;     /* --discrete: not implemented (CCSM_EUNSUPPORTED) */
-  int32_t only_close;   /* --only_close: not implemented */
+  int32_t discrete;     /* --discrete: ignored here -- discretize_score (:240-262) is scalar post-processing the caller
+                           applies to the returned model frequencies */
+  int32_t only_close;   /* --only_close: the 21st model input is "this neighbour is the CpG right after its predecessor"
+                           (position distance 2) instead of the distance to the centre site (:285-290) */
 } ccsm_pileup_opts;
 
 /* The two tables the kernels use: prob[v] = _cal_mod_prob(v) and bin[v] = np.histogram bin of prob[v] (v = ML byte). */

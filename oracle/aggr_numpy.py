@@ -25,8 +25,8 @@ def forward(sd, offsets, histos, h0, num_layers=1, dtype=np.float64):
     return ctx @ sd["fc1.weight"].T + sd["fc1.bias"]
 
 
-def build_windows(refposes, refposes_histos, seq_len=11):
-    """Sliding windows over neighbouring CpG sites (call_mods_freq_bam.py:272-283, only_close=False).
+def build_windows(refposes, refposes_histos, seq_len=11, only_close=False):
+    """Sliding windows over neighbouring CpG sites (call_mods_freq_bam.py:272-290).
 
     Returns pos_mat (n, seq_len) |pos_j - pos_center| and histos_mat (n, seq_len, B).
     """
@@ -35,6 +35,11 @@ def build_windows(refposes, refposes_histos, seq_len=11):
     pad = seq_len // 2
     hm = np.pad(np.stack(refposes_histos), pad_width=((pad, pad), (0, 0)), mode="constant", constant_values=0)
     hm = np.swapaxes(sliding_window_view(hm, seq_len, axis=0), 1, 2)
+    if only_close:
+        pm = np.pad(refposes, pad_width=(pad + 1, pad), mode="constant",
+                    constant_values=(refposes[0] - 1000, refposes[-1] + 1000))
+        pm = (np.diff(pm) == 2).astype(int)
+        return sliding_window_view(pm, seq_len), hm
     pm = np.pad(refposes, pad_width=(pad, pad), mode="constant",
                 constant_values=(refposes[0] - 1000, refposes[-1] + 1000))
     pm = sliding_window_view(pm, seq_len)

@@ -40,7 +40,7 @@ def normalized_histo(probs, binsize=20):
 
 
 def call_region(pos, ptr, ml, hap, sd, call_mode="aggregate", cov_cf=4, prob_cf=0.0, no_amb_cov=False, no_hap=False,
-                h0=(None, None, None), seq_len=11):
+                h0=(None, None, None), seq_len=11, only_close=False):
     """-> (3, n, 3) array of (cov, cnt_mod, freq) per group (all, hp1, hp2), NaN where the reference returns None.
     h0[g]: (2, n_high_g, 32) initial states of group g's high-coverage sites (zeros if None)."""
     n = len(pos)
@@ -61,7 +61,7 @@ def call_region(pos, ptr, ml, hap, sd, call_mode="aggregate", cov_cf=4, prob_cf=
             else:
                 out[g, i] = count_mode(probs, prob_cf, no_amb_cov)
         if hi_idx:
-            pm, hm = aggr_numpy.build_windows(pos[hi_idx], hi_hist, seq_len)
+            pm, hm = aggr_numpy.build_windows(pos[hi_idx], hi_hist, seq_len, only_close)
             hh = h0[g] if h0[g] is not None else np.zeros((2, len(hi_idx), 32), dtype=np.float32)
             raw = aggr_numpy.forward(sd, pm.astype(np.float32), hm.astype(np.float32), hh, dtype=np.float32)
             p = aggr_numpy.postprocess(raw)[:, 0]

@@ -329,7 +329,9 @@ def freqb_args(**kw):
 FREQB_CASES = (("count", {}), ("count_cf3", {"prob_cf": 0.3}), ("count_cf3_noamb", {"prob_cf": 0.3, "no_amb_cov": True}),
                ("count_nocomb", {"no_comb": True}), ("count_refsites", {"refsites_only": True}),
                ("count_clip_nosupp_ident", {"base_clip": 15, "no_supplementary": True, "identity": 0.995, "mapq": 20}),
-               ("aggregate", {"call_mode": "aggregate"}), ("aggregate_nohap", {"call_mode": "aggregate", "no_hap": True}))
+               ("aggregate", {"call_mode": "aggregate"}), ("aggregate_nohap", {"call_mode": "aggregate", "no_hap": True}),
+               ("aggregate_discrete", {"call_mode": "aggregate", "discrete": True, "no_hap": True}),
+               ("aggregate_onlyclose", {"call_mode": "aggregate", "only_close": True, "no_hap": True}))
 
 
 def gen_freqb():

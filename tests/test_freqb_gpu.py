@@ -55,13 +55,15 @@ def test_count_mode_files_are_identical_to_the_reference(tmp_path, ref_out, aggr
         assert _read(bed_paths[0]) == ref_out["count.all.bed"]
 
 
-@pytest.mark.parametrize("tag,extra", [("aggregate", []), ("aggregate_nohap", ["--no_hap"])])
+@pytest.mark.parametrize("tag,extra", [("aggregate", []), ("aggregate_nohap", ["--no_hap"]),
+                                       ("aggregate_discrete", ["--no_hap", "--discrete"]),
+                                       ("aggregate_onlyclose", ["--no_hap", "--only_close"])])
 def test_aggregate_mode_files_match_the_reference(tmp_path, ref_out, aggr_ckpt, tag, extra):
     counts, paths = _run(tmp_path, tag, ["--call_mode", "aggregate"] + extra, aggr_ckpt)
     for name, p in zip(("all", "hp1", "hp2"), paths):
         mine, ref = _read(p).splitlines(), ref_out["%s.%s.freq.txt" % (tag, name)].splitlines()
         assert len(mine) == len(ref), (tag, name)
-        n_model = 0
+        n_model = n_same = 0
         for a, b in zip(mine, ref):
             fa, fb = a.split("\t"), b.split("\t")
             assert fa[:6] == fb[:6] and fa[8] == fb[8]  # contig, position, strand, coverage
@@ -69,9 +71,16 @@ def test_aggregate_mode_files_match_the_reference(tmp_path, ref_out, aggr_ckpt, 
                 assert a == b  # count path
             else:
                 n_model += 1
+                if tag == "aggregate_discrete":
+                    # discretize_score snaps to whole reads: a 1e-6 difference can move the count by one read at most
+                    assert abs(float(fa[6]) - float(fb[6])) <= 1.0 and abs(float(fa[9]) - float(fb[9])) <= 1.0 / int(fb[8]) + 1e-4
+                    n_same += a == b
+                    continue
                 assert abs(float(fa[9]) - float(fb[9])) <= 1.01e-4  # printed with 4 decimals
                 assert abs(float(fa[6]) - float(fb[6])) <= 0.0101   # round(cov * freq, 2)
         assert n_model > 100 or not ref
+        if tag == "aggregate_discrete" and ref:
+            assert n_same >= 0.99 * n_model
     if tag == "aggregate":
         _, bed_paths = _run(tmp_path, tag + "_bed", ["--call_mode", "aggregate", "--bed"], aggr_ckpt)
         mine, ref = _read(bed_paths[0]).splitlines(), ref_out["aggregate.all.bed"].splitlines()

@@ -109,6 +109,19 @@ def test_edge_regions_against_the_oracle(model, ckpt_aggr):
             assert np.array_equal(cov_d[m], ref[..., 0][m].astype(np.int32)), (name, mode)
             assert np.abs(freq_d[m] - ref[..., 2][m]).max() <= 2e-6, (name, mode)
             assert np.abs(cnt_d[m] - ref[..., 1][m]).max() <= 0.0101, (name, mode)
+    # --only_close: the 21st input becomes the "directly follows its predecessor" flag
+    pos = np.cumsum(rng.choice([2, 2, 3, 40, 700], size=900)).astype(np.int64)
+    cov = rng.integers(4, 40, 900)
+    ptr = np.concatenate(([0], np.cumsum(cov))).astype(np.int64)
+    ml = rng.integers(0, 256, int(ptr[-1])).astype(np.uint8)
+    n_high = model.pileup_begin(pos, ptr, ml, None, call_mode="aggregate", only_close=True)
+    h0 = rng.standard_normal((2, n_high[0], 32)).astype(np.float32)
+    _, _, freq_d = model.pileup_finish([torch.from_numpy(h0), None, None])
+    ref = pileup_numpy.call_region(pos, ptr, ml, np.zeros(len(ml), np.uint8), ckpt_aggr, h0=(h0, None, None), only_close=True)
+    assert np.abs(freq_d[0] - ref[0][:, 2]).max() <= 2e-6
+    n_high = model.pileup_begin(pos, ptr, ml, None, call_mode="aggregate", only_close=False)
+    _, _, freq_far = model.pileup_finish([torch.from_numpy(h0), None, None])
+    assert np.abs(freq_far[0] - freq_d[0]).max() > 1e-3  # the flag really changes the model input
     assert model.pileup_begin(np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.uint8)) == (0, 0, 0)
     assert model.pileup_finish()[0].shape == (3, 0)
     # hap = None: everything is haplotype 0, the hp groups are empty
