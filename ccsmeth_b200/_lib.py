@@ -66,7 +66,9 @@ class PileupOpts(ctypes.Structure):
 
 class ModcallOpts(ctypes.Structure):
     _fields_ = [("mapq", ctypes.c_int32), ("no_supplementary", ctypes.c_int32), ("base_clip", ctypes.c_int32),
-                ("hap_tag", ctypes.c_char * 4), ("identity", ctypes.c_double)]
+                ("hap_tag", ctypes.c_char * 4), ("identity", ctypes.c_double), ("refsites_all", ctypes.c_int32),
+                ("n_refs", ctypes.c_int32), ("ref_off", ctypes.c_void_p), ("sites_fwd", ctypes.c_void_p),
+                ("sites_rev", ctypes.c_void_p)]
 
 
 class BamFilter(ctypes.Structure):

@@ -2,8 +2,8 @@
 
 Keeps the reference's flag surface and output format (ccsmeth/call_mods_freq_bam.py:741-845, `_write_one_line`
 :626-634, file names :639-642) for the default path: symmetric ``--motifs CG``-style sites, count or aggregate mode,
-haplotype split by ``--hap_tag``, ``--refsites_only`` motif filter, ``--base_clip``, ``--discrete``, ``--only_close``.
-Not offered: ``--refsites_all`` (zero-probability entries for uncalled reference sites), bed sorting / tabix.
+haplotype split by ``--hap_tag``, ``--refsites_only`` / ``--refsites_all``, ``--base_clip``, ``--discrete``,
+``--only_close``.  Not offered: bed sorting / tabix (``--sort``, ``--gzip`` need bedtools / tabix).
 
 Where the reference forks region workers that each ``fetch`` their reads through pysam and pile calls up in Python
 dictionaries (:457-540), this streams the sorted BAM once: native BGZF inflate + record index (bamstream.py), native
@@ -110,12 +110,47 @@ class ModCalls:
         return tuple(np.concatenate([p[k] for p in self.parts]) for k in range(5))
 
 
-def region_pileups(pos, ml, hap, strand, ref_start, ref_end, comb):
+def motif_site_masks(seq, motifs, mod_loc):
+    """One byte per reference base: is it the modified base of a motif occurrence on the forward / on the reverse
+    strand (what get_refloc_of_methysite_in_motif finds on the sequence and on its reverse complement,
+    call_mods_freq_bam.py:448-455)."""
+    b = np.frombuffer(seq.encode("ascii"), dtype=np.uint8)
+    n, mlen = len(b), len(motifs[0])
+    comp = np.full(256, ord("N"), dtype=np.uint8)
+    for x, y in zip("ACGTNWSMKRYBVDHZ", "TGCANWSKMYRVBHDZ"):
+        comp[ord(x)] = ord(y)
+    rc = comp[b[::-1]]
+    masks = []
+    for arr in (b, rc):
+        hit = np.zeros(max(n - mlen + 1, 0), dtype=bool)
+        for m in set(motifs):
+            mb = np.frombuffer(m.encode("ascii"), dtype=np.uint8)
+            h = np.ones(len(hit), dtype=bool)
+            for k in range(mlen):
+                h &= arr[k:k + len(hit)] == mb[k]
+            hit |= h
+        mask = np.zeros(n, dtype=np.uint8)
+        mask[np.nonzero(hit)[0] + mod_loc] = 1
+        masks.append(mask)
+    return masks[0], np.ascontiguousarray(masks[1][::-1])
+
+
+def region_pileups(pos, ml, hap, strand, ref_start, ref_end, comb, zero_rule=None):
     """Calls of one contig -> the region's CSR pileups.  Returns a list of (strand_char, refpos, ptr, ml, hap):
     one "+" pileup with the reverse-strand CpG calls folded onto the C of the forward strand (pos - 1) when `comb`
-    (call_mods_freq_bam.py:542-551), else a "+" and a "-" pileup."""
+    (call_mods_freq_bam.py:542-551), else a "+" and a "-" pileup.  `strand` bit 1 marks --refsites_all zero calls;
+    zero_rule = (motif_len, mod_loc): such a call only counts where its motif occurrence lies inside the region, because
+    the reference searches the motif in the region's slice of the contig (:448-455)."""
     sel = (pos >= ref_start) & (pos < ref_end)
     p, m, h, s = pos[sel].astype(np.int64), ml[sel], hap[sel], strand[sel]
+    if zero_rule is not None and len(p):
+        mlen, mod_loc = zero_rule
+        zero, rev = s >= 2, (s & 1) == 1
+        lo = np.where(rev, p + mod_loc - (mlen - 1), p - mod_loc)
+        hi = np.where(rev, p + mod_loc, p - mod_loc + mlen - 1)
+        keep = ~zero | ((lo >= ref_start) & (hi <= ref_end - 1))
+        p, m, h, s = p[keep], m[keep], h[keep], s[keep]
+    s = s & 1
     out = []
     if comb:
         keep = ~((s == 1) & (p == 0))          # a reverse call at position 0 has no forward partner (:544-545)
@@ -234,7 +269,22 @@ def iter_region_results(args, model, dnacontigs, bam_path):
     rd = BamPieceReader(bam_path, flt, threads=max(1, args.threads), align_to=1)
     ref_names = [r[0] for r in rd.references]
     opts = _lib.ModcallOpts(args.mapq, 1 if args.no_supplementary else 0, args.base_clip,
-                            args.hap_tag.encode("ascii")[:2], float(args.identity))
+                            args.hap_tag.encode("ascii")[:2], float(args.identity), 0, 0, None, None, None)
+    zero_rule = None
+    if args.refsites_all:
+        # reference motif sites of both strands, all references of the BAM header concatenated
+        lens = [len(dnacontigs.get(nm, "")) for nm in ref_names]
+        ref_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        sites_fwd = np.zeros(int(ref_off[-1]) + 1, dtype=np.uint8)
+        sites_rev = np.zeros(int(ref_off[-1]) + 1, dtype=np.uint8)
+        for i, nm in enumerate(ref_names):
+            if nm in by_contig and lens[i]:
+                f, r = motif_site_masks(dnacontigs[nm], motifs, args.mod_loc)
+                sites_fwd[ref_off[i]:ref_off[i + 1]] = f
+                sites_rev[ref_off[i]:ref_off[i + 1]] = r
+        opts.refsites_all, opts.n_refs = 1, len(ref_names)
+        opts.ref_off, opts.sites_fwd, opts.sites_rev = ref_off.ctypes.data, sites_fwd.ctypes.data, sites_rev.ctypes.data
+        zero_rule = (len(motifs[0]), args.mod_loc)
     calls = ModCalls()
     for piece in rd:
         calls.add_piece(piece, opts)
@@ -249,7 +299,7 @@ def iter_region_results(args, model, dnacontigs, bam_path):
         cpos, cml, chap, cstrand = pos[sel], ml[sel], hap[sel], strand[sel]
         for region in by_contig[name]:
             _, s, e = region
-            pile = region_pileups(cpos, cml, chap, cstrand, s, e, comb)
+            pile = region_pileups(cpos, cml, chap, cstrand, s, e, comb, zero_rule)
             if not pile:
                 continue
             beds = call_region(model, args, dnacontigs[name], name, pile, motifs_filter)
@@ -267,8 +317,6 @@ def call_freqb(args):
         raise ValueError("--input_bam does not exist!")
     if not os.path.exists(args.ref):
         raise ValueError("--ref does not exist!")
-    if args.refsites_all:
-        raise ValueError("--refsites_all is not implemented by ccsmeth_b200")
     os.makedirs(os.path.dirname(os.path.abspath(args.output)), exist_ok=True)
     dnacontigs = read_fasta(args.ref)
     if args.call_mode == "aggregate":

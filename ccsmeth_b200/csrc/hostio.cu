@@ -504,59 +504,88 @@ int64_t ccsm_bam_modcalls(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t 
       if (ident < o->identity) continue;
     }
     ++used;
-    if (!mm || !mlp) continue;  // no MM/ML: the read counts as used but carries no calls
-    // the first MM entry for C+m (optionally followed by '?' or '.'), :131-141
-    const char* x = mm;
-    const char* hit = nullptr;
-    while (*x) {
-      const char* e = x;
-      while (*e && *e != ';') ++e;
-      if (e - x >= 3 && x[0] == 'C' && x[1] == '+' && x[2] == 'm') { hit = x; break; }
-      x = *e ? e + 1 : e;
-    }
-    if (!hit) continue;
-    const char* q = hit + 3;
-    if (*q == '?' || *q == '.') ++q;
-    if (*q != ',') continue;  // no positions listed
-    ++q;
-    // C positions of the forward read
+    // The read's calls: query position (alignment orientation) -> ML byte; any defect of the tags leaves the read
+    // without calls (the reference's {} results, :127-168) -- with --refsites_all it still spans reference sites.
     const int32_t L = rec.l_seq;
-    cpos.clear();
-    for (int32_t f = 0; f < L; ++f) {
-      const int32_t j = reverse ? L - 1 - f : f;
-      const int nib = (j & 1) ? (seq[j >> 1] & 15) : (seq[j >> 1] >> 4);
-      // forward base is C  <=>  stored base is C (forward strand) or G (reverse strand)
-      if (nib == (reverse ? 4 : 2)) cpos.push_back(f);
-    }
     q_ml.assign((size_t)L, -1);
-    int64_t base_count = 0, n_mod = 0;
-    bool bad = false;
-    while (true) {
-      char* endp = nullptr;
-      const long d = strtol(q, &endp, 10);
-      if (endp == q) { bad = true; break; }
-      base_count += d + 1;  // _get_mm_position_iters (:110-116)
-      if (base_count - 1 >= (int64_t)cpos.size() || base_count < 1) { bad = true; break; }  // IndexError -> {}
-      if (n_mod >= ml_n) { bad = true; break; }                                             // MM longer than ML
-      const int32_t fpos = cpos[(size_t)(base_count - 1)];
-      const int32_t qpos = reverse ? L - 1 - fpos : fpos;
-      q_ml[(size_t)qpos] = mlp[n_mod];
-      ++n_mod;
-      q = endp;
-      if (*q == ',') { ++q; continue; }
-      break;
-    }
-    if (bad || n_mod != ml_n) continue;  // assertion len(modbases) == len(mltag) (:147)
+    bool have_calls = false;
+    do {
+      if (!mm || !mlp) break;
+      // the first MM entry for C+m (optionally followed by '?' or '.'), :131-141
+      const char* x = mm;
+      const char* hit = nullptr;
+      while (*x) {
+        const char* e = x;
+        while (*e && *e != ';') ++e;
+        if (e - x >= 3 && x[0] == 'C' && x[1] == '+' && x[2] == 'm') { hit = x; break; }
+        x = *e ? e + 1 : e;
+      }
+      if (!hit) break;
+      const char* q = hit + 3;
+      if (*q == '?' || *q == '.') ++q;
+      if (*q != ',') break;  // no positions listed
+      ++q;
+      // C positions of the forward read
+      cpos.clear();
+      for (int32_t f = 0; f < L; ++f) {
+        const int32_t j = reverse ? L - 1 - f : f;
+        const int nib = (j & 1) ? (seq[j >> 1] & 15) : (seq[j >> 1] >> 4);
+        // forward base is C  <=>  stored base is C (forward strand) or G (reverse strand)
+        if (nib == (reverse ? 4 : 2)) cpos.push_back(f);
+      }
+      int64_t base_count = 0, n_mod = 0;
+      bool bad = false;
+      while (true) {
+        char* endp = nullptr;
+        const long d = strtol(q, &endp, 10);
+        if (endp == q) { bad = true; break; }
+        base_count += d + 1;  // _get_mm_position_iters (:110-116)
+        if (base_count - 1 >= (int64_t)cpos.size() || base_count < 1) { bad = true; break; }  // IndexError -> {}
+        if (n_mod >= ml_n) { bad = true; break; }                                             // MM longer than ML
+        const int32_t fpos = cpos[(size_t)(base_count - 1)];
+        const int32_t qpos = reverse ? L - 1 - fpos : fpos;
+        q_ml[(size_t)qpos] = mlp[n_mod];
+        ++n_mod;
+        q = endp;
+        if (*q == ',') { ++q; continue; }
+        break;
+      }
+      if (bad || n_mod != ml_n) {  // assertion len(modbases) == len(mltag) (:147)
+        q_ml.assign((size_t)L, -1);
+        break;
+      }
+      have_calls = true;
+    } while (false);
+    if (!have_calls && !o->refsites_all) continue;
     const int hv = (hp == 1 || hp == 2) ? hp : 0;
-    // aligned pairs, matches only (M, =, X), then the optional clip of the PAIR list (:489-491)
+    // aligned pairs -- matches only (M, =, X), or with --refsites_all every pair pysam lists (soft clips and
+    // insertions pair with no reference base, deletions / skips with no query base) -- then the optional clip of
+    // the PAIR list (:487-491)
+    const bool all_pairs = o->refsites_all != 0;
     int64_t n_pairs = 0;
     for (int c = 0; c < rec.n_cigar; ++c) {
       const uint32_t v = (uint32_t)rd_i32(cig + 4 * c);
       const int op = v & 15;
-      if (op == 0 || op == 7 || op == 8) n_pairs += v >> 4;
+      if (op == 0 || op == 7 || op == 8 || (all_pairs && (op == 1 || op == 2 || op == 3 || op == 4))) n_pairs += v >> 4;
     }
     const int64_t p_lo = o->base_clip > 0 ? o->base_clip : 0;
     const int64_t p_hi = o->base_clip > 0 ? n_pairs - o->base_clip : n_pairs;
+    const uint8_t* site_mask = nullptr;  // reference motif sites of this read's strand (--refsites_all)
+    int64_t mask_len = 0;
+    if (all_pairs && rid >= 0 && rid < o->n_refs) {
+      site_mask = (reverse ? o->sites_rev : o->sites_fwd) + o->ref_off[rid];
+      mask_len = o->ref_off[rid + 1] - o->ref_off[rid];
+    }
+    auto emit = [&](int32_t rpos, int mlv, int zero_call) {
+      if (n_out < cap) {
+        ref_id[n_out] = rid;
+        ref_pos[n_out] = rpos;
+        ml[n_out] = (uint8_t)mlv;
+        hap[n_out] = (uint8_t)hv;
+        strand[n_out] = (uint8_t)((reverse ? 1 : 0) | (zero_call ? 2 : 0));
+      }
+      ++n_out;
+    };
     int64_t pi = 0;
     int32_t qp = 0, rp = pos0;
     for (int c = 0; c < rec.n_cigar; ++c) {
@@ -565,22 +594,19 @@ int64_t ccsm_bam_modcalls(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t 
       const int32_t ln = (int32_t)(v >> 4);
       if (op == 0 || op == 7 || op == 8) {
         for (int32_t k = 0; k < ln; ++k, ++pi) {
-          if (pi >= p_lo && pi < p_hi && qp + k < L && q_ml[(size_t)(qp + k)] >= 0) {
-            if (n_out < cap) {
-              ref_id[n_out] = rid;
-              ref_pos[n_out] = rp + k;
-              ml[n_out] = (uint8_t)q_ml[(size_t)(qp + k)];
-              hap[n_out] = (uint8_t)hv;
-              strand[n_out] = reverse ? 1 : 0;
-            }
-            ++n_out;
-          }
+          if (pi < p_lo || pi >= p_hi) continue;
+          if (qp + k < L && q_ml[(size_t)(qp + k)] >= 0) emit(rp + k, q_ml[(size_t)(qp + k)], 0);
+          else if (site_mask && rp + k >= 0 && rp + k < mask_len && site_mask[rp + k]) emit(rp + k, 0, 1);  // (0.0, hap) :505-509
         }
         qp += ln;
         rp += ln;
       } else if (op == 1 || op == 4) {
+        if (all_pairs) pi += ln;  // (q, None): never lands on the reference
         qp += ln;
       } else if (op == 2 || op == 3) {
+        if (all_pairs)
+          for (int32_t k = 0; k < ln; ++k, ++pi)
+            if (pi >= p_lo && pi < p_hi && site_mask && rp + k >= 0 && rp + k < mask_len && site_mask[rp + k]) emit(rp + k, 0, 1);
         rp += ln;
       }  // H, P: neither
     }

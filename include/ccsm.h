@@ -299,13 +299,23 @@ int64_t ccsm_bam_tag_records(const uint8_t* buf, const ccsm_bam_rec* recs, int32
  * _get_moddict_in_tags (reference call_mods_freq_bam.py:118-168) and of the read loop of
  * _readmods_to_bed_of_one_region (:466-520, matches-only aligned pairs, --base_clip on the pair list).  Arrays have
  * `cap` entries; the return value is the number of calls found (if > cap nothing beyond cap was written: retry), or a
- * negative CCSM_E* code.  strand: 0 forward, 1 reverse; hap: the --hap_tag value if 1 or 2, else 0. */
+ * negative CCSM_E* code.  strand: 0 forward, 1 reverse (+2 for --refsites_all zero calls); hap: the --hap_tag value if
+ * 1 or 2, else 0. */
 typedef struct ccsm_modcall_opts {
   int32_t mapq;              /* --mapq */
   int32_t no_supplementary;  /* --no_supplementary */
   int32_t base_clip;         /* --base_clip */
   char    hap_tag[4];        /* --hap_tag, two characters (default "HP") */
   double  identity;          /* --identity */
+  /* --refsites_all (:497-520): every reference motif site a read spans without calling it counts as an unmodified
+   * call (ML 0).  sites_fwd / sites_rev: one byte per reference base, all references concatenated, reference i at
+   * [ref_off[i], ref_off[i+1]); non-zero = a motif site of that strand.  Such calls come back with bit 1 set in
+   * `strand` (2 = forward, 3 = reverse) so that the caller can apply region-local rules. */
+  int32_t refsites_all;
+  int32_t n_refs;
+  const int64_t* ref_off;
+  const uint8_t* sites_fwd;
+  const uint8_t* sites_rev;
 } ccsm_modcall_opts;
 int64_t ccsm_bam_modcalls(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t n_recs, const ccsm_modcall_opts* opts,
                           int32_t* ref_id, int32_t* ref_pos, uint8_t* ml, uint8_t* hap, uint8_t* strand, int64_t cap,

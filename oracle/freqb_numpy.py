@@ -42,8 +42,10 @@ def moddict_from_tags(rec, modbase="C", modification="m"):
     return out
 
 
-def read_calls(rec, mapq=1, no_supplementary=False, base_clip=0, hap_tag="HP", identity=0.0):
-    """-> list of (ref_id, ref_pos, ml, hap, strand) or None if the read is filtered out."""
+def read_calls(rec, mapq=1, no_supplementary=False, base_clip=0, hap_tag="HP", identity=0.0, refsites=None):
+    """-> list of (ref_id, ref_pos, ml, hap, strand) or None if the read is filtered out.  refsites = (fwd set, rev set) of
+    reference motif positions switches to --refsites_all: all aligned pairs, uncalled reference sites give (ml 0,
+    strand + 2)."""
     if rec.is_unmapped or rec.is_secondary or rec.is_duplicate:
         return None
     if no_supplementary and rec.is_supplementary:
@@ -60,7 +62,16 @@ def read_calls(rec, mapq=1, no_supplementary=False, base_clip=0, hap_tag="HP", i
     except (KeyError, ValueError):
         hap = 0
     md = moddict_from_tags(rec)
-    pairs = rec.get_aligned_pairs(matches_only=True)
+    pairs = rec.get_aligned_pairs(matches_only=refsites is None)
     if base_clip > 0:
         pairs = pairs[base_clip:(-base_clip)]
-    return [(rec.ref_id, r, md[q], hap if hap in (1, 2) else 0, 1 if rec.is_reverse else 0) for q, r in pairs if q in md]
+    hv, st = hap if hap in (1, 2) else 0, 1 if rec.is_reverse else 0
+    out = []
+    for q, r in pairs:
+        if r is None:
+            continue
+        if q is not None and q in md:
+            out.append((rec.ref_id, r, md[q], hv, st))
+        elif refsites is not None and r in refsites[st]:
+            out.append((rec.ref_id, r, 0, hv, st + 2))
+    return out

@@ -331,7 +331,10 @@ FREQB_CASES = (("count", {}), ("count_cf3", {"prob_cf": 0.3}), ("count_cf3_noamb
                ("count_clip_nosupp_ident", {"base_clip": 15, "no_supplementary": True, "identity": 0.995, "mapq": 20}),
                ("aggregate", {"call_mode": "aggregate"}), ("aggregate_nohap", {"call_mode": "aggregate", "no_hap": True}),
                ("aggregate_discrete", {"call_mode": "aggregate", "discrete": True, "no_hap": True}),
-               ("aggregate_onlyclose", {"call_mode": "aggregate", "only_close": True, "no_hap": True}))
+               ("aggregate_onlyclose", {"call_mode": "aggregate", "only_close": True, "no_hap": True}),
+               ("count_refsites_all", {"refsites_all": True}),
+               ("count_refsites_all_clip_nocomb", {"refsites_all": True, "base_clip": 40, "no_comb": True}),
+               ("aggregate_refsites_all", {"call_mode": "aggregate", "refsites_all": True, "no_hap": True}))
 
 
 def gen_freqb():

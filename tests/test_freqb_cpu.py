@@ -41,7 +41,7 @@ def test_fasta_and_chunks_match_the_reference(ref_out):
 
 def _native_calls(**kw):
     o = _lib.ModcallOpts(kw.get("mapq", 1), int(kw.get("no_supplementary", False)), kw.get("base_clip", 0),
-                         kw.get("hap_tag", "HP").encode(), kw.get("identity", 0.0))
+                         kw.get("hap_tag", "HP").encode(), kw.get("identity", 0.0), 0, 0, None, None, None)
     rd = BamPieceReader(BAM, _lib.BamFilter(0, 0, 0, 0, 0), threads=2, piece_bytes=40000, align_to=1)
     calls = cf.ModCalls()
     used = 0
@@ -72,6 +72,41 @@ def test_native_modcalls_match_the_oracle(kw):
         assert set(np.unique(hap)) == {0, 1, 2}
 
 
+def test_native_refsites_all_matches_the_oracle():
+    """--refsites_all: every aligned pair (insertions, soft clips, deletions included in the clip arithmetic), zero
+    calls at uncalled reference motif sites, reads without MM/ML still counted."""
+    import ctypes
+    contigs = cf.read_fasta(FA)
+    names = ["chrA", "chrB"]
+    masks = [cf.motif_site_masks(contigs[n], ["CG"], 0) for n in names]
+    # the masks themselves against a plain scan
+    for n, (f, r) in zip(names, masks):
+        seq = contigs[n]
+        assert list(np.nonzero(f)[0]) == [i for i in range(len(seq) - 1) if seq[i:i + 2] == "CG"]
+        assert list(np.nonzero(r)[0]) == [i + 1 for i in range(len(seq) - 1) if seq[i:i + 2] == "CG"]
+    lens = [len(contigs[n]) for n in names]
+    ref_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    sf = np.concatenate([m[0] for m in masks] + [np.zeros(1, np.uint8)])
+    sr = np.concatenate([m[1] for m in masks] + [np.zeros(1, np.uint8)])
+    for clip in (0, 40):
+        o = _lib.ModcallOpts(1, 0, clip, b"HP", 0.0, 1, 2, ref_off.ctypes.data, sf.ctypes.data, sr.ctypes.data)
+        rd = BamPieceReader(BAM, _lib.BamFilter(0, 0, 0, 0, 0), threads=2, piece_bytes=40000, align_to=1)
+        calls = cf.ModCalls()
+        for piece in rd:
+            calls.add_piece(piece, o)
+        rid, pos, ml, hap, strand = calls.arrays()
+        exp = []
+        for rec in BamReader(BAM):
+            if rec.is_unmapped:
+                continue
+            sets = (set(np.nonzero(masks[rec.ref_id][0])[0].tolist()), set(np.nonzero(masks[rec.ref_id][1])[0].tolist()))
+            c = freqb_numpy.read_calls(rec, base_clip=clip, refsites=sets)
+            if c is not None:
+                exp += c
+        got = list(zip(rid.tolist(), pos.tolist(), ml.tolist(), hap.tolist(), strand.tolist()))
+        assert got == exp and (strand >= 2).sum() > 100
+
+
 def test_malformed_mm_tags_yield_no_calls():
     from tests.bamsynth import make_record
     import struct
@@ -96,7 +131,7 @@ def test_malformed_mm_tags_yield_no_calls():
         f = _lib.BamFilter(0, 0, 0, 0, 0)
         _lib.check(lib.ccsm_bam_index(buf.ctypes.data, len(buf), ctypes.byref(f), recs.ctypes.data, 4, descs.ctypes.data,
                                       ctypes.byref(nr), ctypes.byref(nd), ctypes.byref(cons)))
-        o = _lib.ModcallOpts(1, 0, 0, b"HP", 0.0)
+        o = _lib.ModcallOpts(1, 0, 0, b"HP", 0.0, 0, 0, None, None, None)
         out = [np.zeros(64, dt) for dt in (np.int32, np.int32, np.uint8, np.uint8, np.uint8)]
         used = ctypes.c_int32(0)
         n = lib.ccsm_bam_modcalls(buf.ctypes.data, recs.ctypes.data, 1, ctypes.byref(o), *[a.ctypes.data for a in out], 64,
@@ -109,7 +144,10 @@ def test_malformed_mm_tags_yield_no_calls():
                                     ("count_cf3_noamb", {"prob_cf": 0.3, "no_amb_cov": True}),
                                     ("count_nocomb", {"no_comb": True}), ("count_refsites", {"refsites_only": True}),
                                     ("count_clip_nosupp_ident", {"base_clip": 15, "no_supplementary": True,
-                                                                 "identity": 0.995, "mapq": 20})])
+                                                                 "identity": 0.995, "mapq": 20}),
+                                    ("count_refsites_all", {"refsites_all": True}),
+                                    ("count_refsites_all_clip_nocomb", {"refsites_all": True, "base_clip": 40,
+                                                                        "no_comb": True})])
 def test_host_chain_with_the_pileup_oracle_reproduces_the_reference_files(ref_out, tag, kw):
     """Native projection -> region pileups -> (numpy pileup oracle instead of the device) -> text lines ==
     the reference region worker's output, byte for byte, in count mode."""

@@ -44,7 +44,9 @@ def _read(path):
 @pytest.mark.parametrize("tag,extra", [
     ("count", []), ("count_cf3", ["--prob_cf", "0.3"]), ("count_cf3_noamb", ["--prob_cf", "0.3", "--no_amb_cov"]),
     ("count_nocomb", ["--no_comb"]), ("count_refsites", ["--refsites_only"]),
-    ("count_clip_nosupp_ident", ["--base_clip", "15", "--no_supplementary", "--identity", "0.995", "--mapq", "20"])])
+    ("count_clip_nosupp_ident", ["--base_clip", "15", "--no_supplementary", "--identity", "0.995", "--mapq", "20"]),
+    ("count_refsites_all", ["--refsites_all"]),
+    ("count_refsites_all_clip_nocomb", ["--refsites_all", "--base_clip", "40", "--no_comb"])])
 def test_count_mode_files_are_identical_to_the_reference(tmp_path, ref_out, aggr_ckpt, tag, extra):
     counts, paths = _run(tmp_path, tag, extra, aggr_ckpt)
     for name, p in zip(("all", "hp1", "hp2"), paths):
@@ -57,7 +59,8 @@ def test_count_mode_files_are_identical_to_the_reference(tmp_path, ref_out, aggr
 
 @pytest.mark.parametrize("tag,extra", [("aggregate", []), ("aggregate_nohap", ["--no_hap"]),
                                        ("aggregate_discrete", ["--no_hap", "--discrete"]),
-                                       ("aggregate_onlyclose", ["--no_hap", "--only_close"])])
+                                       ("aggregate_onlyclose", ["--no_hap", "--only_close"]),
+                                       ("aggregate_refsites_all", ["--no_hap", "--refsites_all"])])
 def test_aggregate_mode_files_match_the_reference(tmp_path, ref_out, aggr_ckpt, tag, extra):
     counts, paths = _run(tmp_path, tag, ["--call_mode", "aggregate"] + extra, aggr_ckpt)
     for name, p in zip(("all", "hp1", "hp2"), paths):
