@@ -237,6 +237,9 @@ def call_mods(args):
         raise ValueError("--input_file does not exist!")
     if not (args.input.endswith(".bam")):
         raise ValueError("ccsmeth_b200 call_mods takes BAM input (features.tsv input is out of scope)")
+    if args.model_type != "attbigru2s":
+        raise ValueError("the call_mods pipeline runs attbigru2s (the shipped model); attbilstm2s is available through "
+                         "ccsmeth_b200.models.ModelAttRNN.forward, other --model_type values are not implemented")
     if str2bool(args.is_map) or str2bool(args.is_stds):
         raise ValueError("--is_map/--is_stds features are not extracted by ccsmeth_b200 (SURVEY.md section 8f)")
     rank, world, local = parallel.init_from_env()

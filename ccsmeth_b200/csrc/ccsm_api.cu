@@ -105,6 +105,10 @@ int ccsm_create(ccsm_model** out, const ccsm_config* cfg) {
     if (cfg->feat_flags & CCSM_FEAT_SN) feas += 4;
     if (cfg->feat_flags & CCSM_FEAT_MAP) feas += 1;
     m->in_feat = cfg->n_embed + feas;
+    if (cfg->feat_flags & CCSM_CELL_LSTM) {
+      m->gates = 4;
+      m->cfg.precision = CCSM_PREC_FP32;  // the tensor-core kernels implement the GRU cell only
+    }
   } else {
     m->strands = 1;
     m->in_feat = cfg->feat_flags + 1;  // bins + offset (reference models.py:639)
@@ -131,7 +135,7 @@ void ccsm_destroy(ccsm_model* m) {
   m->fp32.embed.release(); m->fp32.Wa.release(); m->fp32.Ua.release(); m->fp32.va.release();
   m->fp32.fc_w.release(); m->fp32.fc_b.release();
   Fp32Workspace& ws = m->ws32;
-  ws.x0.release(); ws.gi.release(); ws.gh.release(); ws.h.release(); ws.outA.release(); ws.outB.release(); ws.qa.release();
+  ws.x0.release(); ws.gi.release(); ws.gh.release(); ws.h.release(); ws.c.release(); ws.outA.release(); ws.outB.release(); ws.qa.release();
   for (int i = 0; i < 2; ++i) {
     m->stage_in[i].release();
     m->stage_out[i].release();
@@ -153,9 +157,10 @@ static bool expected_shape(const ccsm_model* m, const std::string& key, std::vec
     for (int d = 0; d < 2; ++d) {
       std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
       int64_t K = l == 0 ? m->in_feat : 2 * H;
-      if (key == "rnn.weight_ih" + sfx) { shp = {3 * H, K}; return true; }
-      if (key == "rnn.weight_hh" + sfx) { shp = {3 * H, H}; return true; }
-      if (key == "rnn.bias_ih" + sfx || key == "rnn.bias_hh" + sfx) { shp = {3 * H}; return true; }
+      const int64_t G = m->gates;
+      if (key == "rnn.weight_ih" + sfx) { shp = {G * H, K}; return true; }
+      if (key == "rnn.weight_hh" + sfx) { shp = {G * H, H}; return true; }
+      if (key == "rnn.bias_ih" + sfx || key == "rnn.bias_hh" + sfx) { shp = {G * H}; return true; }
     }
   return false;
 }
@@ -236,7 +241,7 @@ int ccsm_set_precision(ccsm_model* m, int32_t precision) {
     set_error("ccsm_set_precision: bad argument");
     return CCSM_EINVAL;
   }
-  if (m->cfg.kind == CCSM_KIND_AGGR) precision = CCSM_PREC_FP32;
+  if (m->cfg.kind == CCSM_KIND_AGGR || m->gates == 4) precision = CCSM_PREC_FP32;
   if (precision == m->cfg.precision) return CCSM_OK;
   m->cfg.precision = precision;
   if (m->finalized && is_tc(precision)) {
@@ -278,6 +283,31 @@ int ccsm_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rc = is_tc(m->cfg.precision) ? tc_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st)
                                          : fp32_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
+  m->h0_calls += 1;
+  return rc;
+}
+
+int ccsm_forward_att2s_lstm(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, const float* h0_fwd,
+                            const float* c0_fwd, const float* h0_rev, const float* c0_rev, float* logits, float* probs,
+                            void* stream) {
+  if (!m || m->cfg.kind != CCSM_KIND_ATT2S || m->gates != 4) {
+    set_error("ccsm_forward_att2s_lstm: not an LSTM (CCSM_CELL_LSTM) att2s model");
+    return CCSM_EINVAL;
+  }
+  if (!m->finalized) {
+    set_error("ccsm_forward_att2s_lstm: model not finalized");
+    return CCSM_ESTATE;
+  }
+  if (n < 0) {
+    set_error("ccsm_forward_att2s_lstm: n < 0");
+    return CCSM_EINVAL;
+  }
+  if (n == 0) return CCSM_OK;
+  CCSM_TRY(check_strand(m, fwd, "forward"));
+  CCSM_TRY(check_strand(m, rev, "reverse"));
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  const int rc = fp32_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, reinterpret_cast<cudaStream_t>(stream),
+                                    c0_fwd, c0_rev);
   m->h0_calls += 1;
   return rc;
 }

@@ -68,7 +68,7 @@ struct Fp32Weights {
 
 struct Fp32Workspace {
   int64_t rows_cap = 0;
-  DevBuf x0, gi, gh, h, outA, outB, qa;
+  DevBuf x0, gi, gh, h, c, outA, outB, qa;
 };
 
 struct TcState;  // tensor-core (tcgen05) path state, defined in tc_path.cu
@@ -107,6 +107,7 @@ struct ccsm_model {
   ccsm_config cfg{};
   int strands = 2;    // 2 for att2s, 1 for aggr
   int in_feat = 0;    // GRU layer-0 input width (att2s: n_embed + feas_ccs; aggr: bins + 1)
+  int gates = 3;      // 3 GRU (r, z, n) / 4 LSTM (i, f, g, o): gate row blocks of the rnn weights
   std::map<std::string, ccsm::HostTensor> w;
   bool finalized = false;
   ccsm::Fp32Weights fp32;
@@ -133,7 +134,8 @@ namespace ccsm {
 // ---- fp32 path (fp32_path.cu)
 int fp32_upload_weights(ccsm_model* m);
 int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
-                       const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st);
+                       const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st,
+                       const float* c0_f = nullptr, const float* c0_r = nullptr);
 int fp32_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
                       float* out, cudaStream_t st);
 

@@ -231,6 +231,31 @@ __global__ void gru_step_kernel(int64_t rows, int L, int H, int step, const floa
   out[(R * L + t) * 2 * (int64_t)H + d * H + u] = hn;
 }
 
+// One LSTM time step for both directions (PyTorch cell, gate row blocks i, f, g, o; gi/gh contain the biases):
+//   i = sig(.), f = sig(.), g = tanh(.), o = sig(.);  c' = f * c + i * g;  h' = o * tanh(c')
+// reference models.py:48-51 (nn.LSTM in ModelAttRNN(model_type="attbilstm2s")).
+__global__ void lstm_step_kernel(int64_t rows, int L, int H, int step, const float* __restrict__ gi,
+                                 const float* __restrict__ gh, float* __restrict__ h, float* __restrict__ c,
+                                 float* __restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (R, d, u)
+  if (idx >= rows * 2 * H) return;
+  int u = (int)(idx % H);
+  int d = (int)((idx / H) & 1);
+  int64_t R = idx / (2 * H);
+  int t = d ? (L - 1 - step) : step;
+  const float* gip = gi + ((R * L + t) * 2 + d) * 4 * (int64_t)H;
+  const float* ghp = gh + (R * 2 + d) * 4 * (int64_t)H;
+  const float ig = 1.f / (1.f + expf(-(gip[u] + ghp[u])));
+  const float fg = 1.f / (1.f + expf(-(gip[H + u] + ghp[H + u])));
+  const float gg = tanhf(gip[2 * H + u] + ghp[2 * H + u]);
+  const float og = 1.f / (1.f + expf(-(gip[3 * H + u] + ghp[3 * H + u])));
+  const float cn = fg * c[idx] + ig * gg;
+  const float hn = og * tanhf(cn);
+  c[idx] = cn;
+  h[idx] = hn;
+  out[(R * L + t) * 2 * (int64_t)H + d * H + u] = hn;
+}
+
 // Attention reduction + head, one warp per site (both strands).
 //   e_t = va . tanh(qa + E_t);  w = softmax_t(e);  ctx = sum_t w_t out_t      (attention.py:55-70)
 //   logits = fc1 [ctx_strand1 | ctx_strand2] + b;  probs = softmax(logits)    (models.py:145-150)
@@ -315,8 +340,9 @@ int fp32_upload_weights(ccsm_model* m) {
     Fp32Layer& Lw = W.layers[l];
     Lw.K = l == 0 ? m->in_feat : 2 * H;
     Lw.Kpad = round_up(Lw.K, 16);
-    std::vector<float> wih((size_t)2 * 3 * H * Lw.Kpad, 0.f), bih((size_t)2 * 3 * H), whh((size_t)2 * 3 * H * H),
-        bhh((size_t)2 * 3 * H);
+    const int G = m->gates;
+    std::vector<float> wih((size_t)2 * G * H * Lw.Kpad, 0.f), bih((size_t)2 * G * H), whh((size_t)2 * G * H * H),
+        bhh((size_t)2 * G * H);
     for (int d = 0; d < 2; ++d) {
       std::string base = "rnn.";
       const HostTensor* a = find(m, base + "weight_ih_l" + std::to_string(l) + sfx[d]);
@@ -327,11 +353,11 @@ int fp32_upload_weights(ccsm_model* m) {
         set_error("finalize: missing GRU tensors for layer %d%s", l, sfx[d]);
         return CCSM_EKEY;
       }
-      for (int r = 0; r < 3 * H; ++r)
-        for (int k = 0; k < Lw.K; ++k) wih[((size_t)d * 3 * H + r) * Lw.Kpad + k] = a->data[(size_t)r * Lw.K + k];
-      std::copy(b->data.begin(), b->data.end(), whh.begin() + (size_t)d * 3 * H * H);
-      std::copy(c->data.begin(), c->data.end(), bih.begin() + (size_t)d * 3 * H);
-      std::copy(e->data.begin(), e->data.end(), bhh.begin() + (size_t)d * 3 * H);
+      for (int r = 0; r < G * H; ++r)
+        for (int k = 0; k < Lw.K; ++k) wih[((size_t)d * G * H + r) * Lw.Kpad + k] = a->data[(size_t)r * Lw.K + k];
+      std::copy(b->data.begin(), b->data.end(), whh.begin() + (size_t)d * G * H * H);
+      std::copy(c->data.begin(), c->data.end(), bih.begin() + (size_t)d * G * H);
+      std::copy(e->data.begin(), e->data.end(), bhh.begin() + (size_t)d * G * H);
     }
     CCSM_TRY(upload(Lw.w_ih, wih));
     CCSM_TRY(upload(Lw.b_ih, bih));
@@ -354,9 +380,11 @@ static int reserve_ws(ccsm_model* m, int64_t rows) {
   const int64_t H = m->cfg.hidden, L = m->cfg.seq_len;
   const int64_t K0 = m->fp32.layers[0].Kpad;
   CCSM_TRY(ws.x0.reserve(rows * L * K0 * 4));
-  CCSM_TRY(ws.gi.reserve(rows * L * 6 * H * 4));
-  CCSM_TRY(ws.gh.reserve(rows * 6 * H * 4));
+  const int64_t G = m->gates;
+  CCSM_TRY(ws.gi.reserve(rows * L * 2 * G * H * 4));
+  CCSM_TRY(ws.gh.reserve(rows * 2 * G * H * 4));
   CCSM_TRY(ws.h.reserve(rows * 2 * H * 4));
+  if (G == 4) CCSM_TRY(ws.c.reserve(rows * 2 * H * 4));
   CCSM_TRY(ws.outA.reserve(rows * L * 2 * H * 4));
   CCSM_TRY(ws.outB.reserve(rows * L * 2 * H * 4));
   CCSM_TRY(ws.qa.reserve(rows * H * 4));
@@ -368,8 +396,9 @@ static inline unsigned nblk(int64_t total, int threads) { return (unsigned)((tot
 
 // Runs layers + attention + head on x0 (already packed) for `sites` sites starting at site0.
 static int run_stack(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_total, const float* h0_a,
-                     const float* h0_b, float* logits, float* probs, cudaStream_t st) {
-  const int H = m->cfg.hidden, L = m->cfg.seq_len, NL = m->cfg.num_layers, S = m->strands;
+                     const float* h0_b, float* logits, float* probs, cudaStream_t st, const float* c0_a = nullptr,
+                     const float* c0_b = nullptr) {
+  const int H = m->cfg.hidden, L = m->cfg.seq_len, NL = m->cfg.num_layers, S = m->strands, G = m->gates;
   const int64_t rows = sites * S;
   Fp32Workspace& ws = m->ws32;
   Fp32Weights& W = m->fp32;
@@ -380,18 +409,28 @@ static int run_stack(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_tota
     Fp32Layer& Lw = W.layers[l];
     out = outs[l & 1];
     // input projection for all time steps and both directions: gi[R][t][d][3H]
-    CCSM_TRY(sgemm_nt((int)(rows * L), 6 * H, Lw.Kpad, xin, Lw.Kpad, 0, Lw.w_ih.as<float>(), Lw.Kpad, 0,
-                      Lw.b_ih.as<float>(), 0, ws.gi.as<float>(), 6 * H, 0, 1, st));
+    CCSM_TRY(sgemm_nt((int)(rows * L), 2 * G * H, Lw.Kpad, xin, Lw.Kpad, 0, Lw.w_ih.as<float>(), Lw.Kpad, 0,
+                      Lw.b_ih.as<float>(), 0, ws.gi.as<float>(), 2 * G * H, 0, 1, st));
     load_h0_kernel<<<nblk(rows * 2 * H, 256), 256, 0, st>>>(
         rows, S, H, l, NL, n_total, site0, h0_a, h0_b, m->h0_mode == CCSM_H0_DEVICE_RANDOM ? 1 : 0,
         (unsigned long long)m->h0_seed, (unsigned long long)(m->h0_calls * 256), ws.h.as<float>());
     count_launch();
+    if (G == 4) {  // c0: explicit, zeros, or (device-random mode) a second stream with its own seed
+      load_h0_kernel<<<nblk(rows * 2 * H, 256), 256, 0, st>>>(
+          rows, S, H, l, NL, n_total, site0, c0_a, c0_b, m->h0_mode == CCSM_H0_DEVICE_RANDOM ? 1 : 0,
+          (unsigned long long)(m->h0_seed ^ 0x9e3779b97f4a7c15ULL), (unsigned long long)(m->h0_calls * 256), ws.c.as<float>());
+      count_launch();
+    }
     for (int s = 0; s < L; ++s) {
-      // gh[R][d][3H] = h[R][d][:] . W_hh[d]^T + b_hh[d]
-      CCSM_TRY(sgemm_nt((int)rows, 3 * H, H, ws.h.as<float>(), 2 * H, H, Lw.w_hh.as<float>(), H, (long)3 * H * H,
-                        Lw.b_hh.as<float>(), 3 * H, ws.gh.as<float>(), 6 * H, 3 * H, 2, st));
-      gru_step_kernel<<<nblk(rows * 2 * H, 256), 256, 0, st>>>(rows, L, H, s, ws.gi.as<float>(), ws.gh.as<float>(),
-                                                                ws.h.as<float>(), out);
+      // gh[R][d][G*H] = h[R][d][:] . W_hh[d]^T + b_hh[d]
+      CCSM_TRY(sgemm_nt((int)rows, G * H, H, ws.h.as<float>(), 2 * H, H, Lw.w_hh.as<float>(), H, (long)G * H * H,
+                        Lw.b_hh.as<float>(), G * H, ws.gh.as<float>(), 2 * G * H, G * H, 2, st));
+      if (G == 4)
+        lstm_step_kernel<<<nblk(rows * 2 * H, 256), 256, 0, st>>>(rows, L, H, s, ws.gi.as<float>(), ws.gh.as<float>(),
+                                                                   ws.h.as<float>(), ws.c.as<float>(), out);
+      else
+        gru_step_kernel<<<nblk(rows * 2 * H, 256), 256, 0, st>>>(rows, L, H, s, ws.gi.as<float>(), ws.gh.as<float>(),
+                                                                  ws.h.as<float>(), out);
       count_launch();
     }
     xin = out;
@@ -435,7 +474,8 @@ static StrandPtrs offset_strand(const ccsm_strand* s, int64_t site0, int L) {
 }
 
 int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, const float* h0_f,
-                       const float* h0_r, float* logits, float* probs, cudaStream_t st) {
+                       const float* h0_r, float* logits, float* probs, cudaStream_t st, const float* c0_f,
+                       const float* c0_r) {
   const int L = m->cfg.seq_len;
   const int64_t chunk = n < kChunkSites ? n : kChunkSites;
   CCSM_TRY(reserve_ws(m, chunk * 2));
@@ -445,7 +485,7 @@ int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
         sites, L, m->cfg.n_embed, m->cfg.n_vocab, m->cfg.feat_flags, m->fp32.layers[0].Kpad,
         offset_strand(fwd, s0, L), offset_strand(rev, s0, L), m->fp32.embed.as<float>(), m->ws32.x0.as<float>());
     count_launch();
-    CCSM_TRY(run_stack(m, sites, s0, n, h0_f, h0_r, logits, probs, st));
+    CCSM_TRY(run_stack(m, sites, s0, n, h0_f, h0_r, logits, probs, st, c0_f, c0_r));
   }
   return CCSM_OK;
 }

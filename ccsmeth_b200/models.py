@@ -162,27 +162,27 @@ class ModelAttRNN(_NativeModule):
                  is_npass=True, is_sn=False, is_map=False, is_stds=False, model_type="attbigru2s", device=0,
                  precision=None):
         super().__init__()
-        if model_type != "attbigru2s":
-            # the reference also builds an LSTM variant (models.py:48-51); no checkpoint ships for it and
-            # it is outside this path's scope
-            raise ValueError("--model_type not set right! (ccsmeth_b200 implements attbigru2s)")
+        if model_type not in ("attbigru2s", "attbilstm2s"):
+            raise ValueError("--model_type not set right! (ccsmeth_b200 implements attbigru2s and attbilstm2s)")
         self.model_type = model_type
         self.device = device
         self.seq_len, self.num_layers, self.num_classes, self.hidden_size = seq_len, num_layers, num_classes, hidden_size
         self.n_embed = NEMBED_BASE
         self.is_stds, self.is_npass, self.is_sn, self.is_map = is_stds, is_npass, is_sn, is_map
         self.feas_ccs = 2 + (2 if is_stds else 0) + (1 if is_npass else 0) + (4 if is_sn else 0) + (1 if is_map else 0)
-        self.rnn_cell = "gru"
+        # the LSTM variant (reference models.py:48-51) has no shipped checkpoint; it runs on the fp32 kernels
+        self.rnn_cell = "lstm" if model_type == "attbilstm2s" else "gru"
         # parameter containers, never called: same names/shapes as the reference state_dict
         self.embed = nn.Embedding(N_VOCAB, self.n_embed)
-        self.rnn = nn.GRU(self.n_embed + self.feas_ccs, hidden_size, num_layers, dropout=dropout_rate,
-                          batch_first=True, bidirectional=True)
+        rnn_cls = nn.LSTM if self.rnn_cell == "lstm" else nn.GRU
+        self.rnn = rnn_cls(self.n_embed + self.feas_ccs, hidden_size, num_layers, dropout=dropout_rate,
+                           batch_first=True, bidirectional=True)
         self._att3 = Attention(hidden_size * 2, hidden_size * 2, hidden_size)
         self.dropout1 = nn.Dropout(p=dropout_rate)  # identity at inference; kept for interface parity
         self.fc1 = nn.Linear(hidden_size * 2 * 2, num_classes)
         self.init_weights()
         self.requires_grad_(False)
-        self._native_init(precision or DEFAULT_PRECISION)
+        self._native_init("fp32" if self.rnn_cell == "lstm" else (precision or DEFAULT_PRECISION))
 
     def init_weights(self):  # reference models.py:71-75
         nn.init.uniform_(self.embed.weight, -0.1, 0.1)
@@ -190,12 +190,17 @@ class ModelAttRNN(_NativeModule):
         nn.init.uniform_(self.fc1.weight, -0.1, 0.1)
 
     def init_hidden(self, batch_size, num_layers, hidden_size):
-        """Same draw as the reference (models.py:77-87): CPU default generator, then moved to the device."""
-        return torch.randn(num_layers * 2, batch_size, hidden_size)
+        """Same draw as the reference (models.py:77-87): CPU default generator, then moved to the device.
+        LSTM: (h0, c0), h0 drawn first."""
+        h0 = torch.randn(num_layers * 2, batch_size, hidden_size)
+        if self.rnn_cell == "lstm":
+            return h0, torch.randn(num_layers * 2, batch_size, hidden_size)
+        return h0
 
     def _config(self, dev):
         flags = (_lib.FEAT_NPASS if self.is_npass else 0) | (_lib.FEAT_STDS if self.is_stds else 0) | \
-                (_lib.FEAT_SN if self.is_sn else 0) | (_lib.FEAT_MAP if self.is_map else 0)
+                (_lib.FEAT_SN if self.is_sn else 0) | (_lib.FEAT_MAP if self.is_map else 0) | \
+                (_lib.CELL_LSTM if self.rnn_cell == "lstm" else 0)
         return _lib.Config(_lib.KIND_ATT2S, self.seq_len, self.num_layers, self.hidden_size, self.num_classes,
                            N_VOCAB, self.n_embed, flags, _lib.PREC[self._precision], dev)
 
@@ -235,13 +240,25 @@ class ModelAttRNN(_NativeModule):
         fwd = self._strand(device, n, kmer, kpass, ipd_means, ipd_stds, pw_means, pw_stds, sns, maps, keep)
         rev = self._strand(device, n, kmer2, kpass2, ipd_means2, ipd_stds2, pw_means2, pw_stds2, sns2, maps2, keep)
         hshape = (2 * self.num_layers, n, self.hidden_size)
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        probs = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        if self.rnn_cell == "lstm":
+            # h0 = ((h0, c0) of strand 1, (h0, c0) of strand 2), as init_hidden returns them
+            ptrs = [None] * 4
+            if h0 is not None:
+                ts = [_dev_f32(t, device, hshape) for pair in h0 for t in pair]
+                keep += ts
+                ptrs = [t.data_ptr() for t in ts]
+            if n > 0:
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _lib.check(_lib.load().ccsm_forward_att2s_lstm(handle, n, ctypes.byref(fwd), ctypes.byref(rev), *ptrs,
+                                                               logits.data_ptr(), probs.data_ptr(), ctypes.c_void_p(stream)))
+            return logits, probs
         if h0 is not None:
             h0a, h0b = _dev_f32(h0[0], device, hshape), _dev_f32(h0[1], device, hshape)
             pa, pb = h0a.data_ptr(), h0b.data_ptr()
         else:
             pa = pb = None  # library draws (device mode) or uses zeros
-        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
-        probs = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
         if n > 0:
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(_lib.load().ccsm_forward_att2s(handle, n, ctypes.byref(fwd), ctypes.byref(rev),
@@ -269,6 +286,8 @@ class ModelAttRNN(_NativeModule):
         (kmer, kpass, ipd, pw and the same with a '2' suffix) to float32 CPU tensors / numpy arrays of shape
         (n, seq_len).  Copies, forward and result read-back are pipelined inside the library.  Returns
         CPU tensors (logits, probs)."""
+        if self.rnn_cell == "lstm":
+            raise NotImplementedError("the host-buffer entry implements the GRU model; use forward() for attbilstm2s")
         handle, dev = self._ensure_handle()
         L = self.seq_len
         cpu = torch.device("cpu")

@@ -62,6 +62,10 @@ extern "C" {
 #define CCSM_FEAT_STDS  2
 #define CCSM_FEAT_SN    4
 #define CCSM_FEAT_MAP   8
+/* cell type, carried in feat_flags: ModelAttRNN(model_type="attbilstm2s") (models.py:48-51) -- nn.LSTM instead of
+ * nn.GRU: state_dict keys are the same with 4*hidden gate rows (i, f, g, o), the initial state is (h0, c0).  No
+ * checkpoint ships for it; it runs in CCSM_PREC_FP32 only and through ccsm_forward_att2s_lstm. */
+#define CCSM_CELL_LSTM  16
 
 typedef struct ccsm_model ccsm_model;
 
@@ -132,6 +136,13 @@ int  ccsm_set_precision(ccsm_model* m, int32_t precision);
  * logits/probs: (n, num_classes) float32 device (either may be NULL). */
 int  ccsm_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
                         const float* h0_fwd, const float* h0_rev, float* logits, float* probs, void* stream);
+
+/* ModelAttRNN.forward of the LSTM variant (models.py:89-150 with rnn_cell == "lstm"): as ccsm_forward_att2s plus the
+ * initial cell states c0_fwd / c0_rev, (2*layers, n, hidden) float32 device or NULL (zeros); the reference draws h0
+ * then c0 with torch.randn per strand (models.py:77-87).  Calling ccsm_forward_att2s on an LSTM model uses c0 = 0. */
+int  ccsm_forward_att2s_lstm(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev,
+                             const float* h0_fwd, const float* c0_fwd, const float* h0_rev, const float* c0_rev,
+                             float* logits, float* probs, void* stream);
 
 /* Same computation with HOST buffers (pageable or pinned): the library stages host->device copies,
  * the forward and the device->host copy of the results in double-buffered chunks on its own streams,

@@ -298,6 +298,38 @@ def gen_pileup():
     print("pileup_region: %d sites, %d calls, aggregate mean freq %.4f" % (n, len(ml), np.nanmean(save["aggr"][0, :, 2])))
 
 
+def gen_lstm():
+    """Section 8f-4: the reference's ModelAttRNN(model_type="attbilstm2s") -- no checkpoint ships, so a seeded random
+    initialisation of a small configuration (hidden 64, 2 layers) is the fixture -- with explicit (h0, c0)."""
+    ref = refimport.import_reference()
+    torch.manual_seed(4321)
+    m = ref.models.ModelAttRNN(21, 2, 2, 0, 64, is_npass=True, model_type="attbilstm2s", device="cpu")
+    m.eval()
+    n = 128
+    b = synth.make_batch(n, seed=synth.SEED + 5, with_h0=False)
+    g = torch.Generator().manual_seed(99)
+    hc = [(torch.randn(4, n, 64, generator=g), torch.randn(4, n, 64, generator=g)) for _ in range(2)]
+    z = torch.zeros(n)
+    args = (b["kmer"], b["kpass"], b["ipd"], z, b["pw"], z, z, z, b["kmer2"], b["kpass2"], b["ipd2"], z, b["pw2"], z, z, z)
+    import ccsmeth.models as rmodels
+    old = rmodels.use_cuda
+    rmodels.use_cuda = False
+    try:
+        with refimport.fixed_h0(m, [(h.clone(), c.clone()) for h, c in hc]):
+            logits, probs = m(*args)
+        torch.manual_seed(777)  # the reference's own draw order: h0, c0 of strand 1, then of strand 2
+        _, probs_seeded = m(*args)
+    finally:
+        rmodels.use_cuda = old
+    save = {"sd." + k: v.detach().numpy() for k, v in m.state_dict().items()}
+    save.update({k: b[k].numpy() for k in ("kmer", "kpass", "ipd", "pw", "kmer2", "kpass2", "ipd2", "pw2")})
+    save.update({"h0_f": hc[0][0].numpy(), "c0_f": hc[0][1].numpy(), "h0_r": hc[1][0].numpy(), "c0_r": hc[1][1].numpy(),
+                 "logits": logits.detach().numpy(), "probs": probs.detach().numpy(),
+                 "probs_seeded": probs_seeded.detach().numpy(), "seed": 777})
+    np.savez_compressed(os.path.join(OUT, "att2s_lstm.npz"), **save)
+    print("att2s_lstm: mean p1 %.4f" % probs[:, 1].mean().item())
+
+
 class DuckBam:
     """What the reference's region worker needs from pysam.AlignmentFile: fetch(contig, start, stop) over records that
     overlap the interval, in file order (records are ccsmeth_b200.bamio.BamRecord)."""
@@ -381,6 +413,9 @@ def gen_freqb():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "lstm":
+        gen_lstm()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "freqb":
         gen_freqb()
         sys.exit(0)
@@ -394,6 +429,7 @@ if __name__ == "__main__":
     gen_att2s()
     gen_aggr()
     gen_pileup()
+    gen_lstm()
     gen_freqb()
     gen_demo()
     for f in sorted(os.listdir(OUT)):

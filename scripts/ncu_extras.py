@@ -29,5 +29,16 @@ o = torch.randint(0, 1200, (N, 11), generator=g, device="cuda").float()
 h0 = torch.randn((2, N, 32), generator=g, device="cuda")
 for _ in range(2):
     a(o, h, h0=h0)
+# region pileup: 2^18 sites, coverage U{4..60}
+rng = np.random.default_rng(3)
+ns = 1 << 18
+cov = rng.integers(4, 61, size=ns)
+ptr = np.concatenate(([0], np.cumsum(cov))).astype(np.int64)
+ml = rng.integers(0, 256, int(ptr[-1])).astype(np.uint8)
+hap = rng.integers(0, 3, int(ptr[-1])).astype(np.uint8)
+pos = np.cumsum(rng.integers(2, 201, size=ns)).astype(np.int64)
+for _ in range(2):
+    a.pileup_begin(pos, ptr, ml, hap, call_mode="aggregate")
+    a.pileup_finish()
 torch.cuda.synchronize()
 print("done", n)

@@ -94,3 +94,15 @@ def test_aggr_torch_port(ckpt_aggr, golden_aggr):
     pm, hm = aggr_numpy.build_windows(g["pos"], list(g["histos"]))
     raw = m(torch.tensor(pm, dtype=torch.float), torch.tensor(np.array(hm), dtype=torch.float), torch.from_numpy(g["h0"]))
     assert np.abs(raw.detach().numpy() - g["raw"]).max() < 1e-6
+
+
+def test_lstm_numpy_oracle_matches_reference():
+    """attbilstm2s (reference models.py:48-51): numpy LSTM restatement vs the reference's own forward on a seeded
+    random initialisation (no checkpoint ships for this model type)."""
+    from tests.conftest import load_npz
+    g = load_npz("att2s_lstm.npz")
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    logits, probs = att2s_numpy.forward_lstm(sd, *[g[k] for k in ("kmer", "kpass", "ipd", "pw", "kmer2", "kpass2", "ipd2", "pw2")],
+                                             (g["h0_f"], g["c0_f"]), (g["h0_r"], g["c0_r"]), num_layers=2)
+    assert np.abs(probs - g["probs"]).max() <= 1e-6
+    assert np.abs(logits - g["logits"]).max() <= 1e-5

@@ -163,3 +163,27 @@ def test_aggr_loop_matches_reference_loop(ckpt_aggr, golden_aggr):
     probs = _cal_modfreq_in_aggregate_mode(g["pos"], list(g["histos"]), m, 11, False)
     assert len(probs) == len(g["loop_probs"])
     assert np.abs(np.array(probs) - g["loop_probs"]).max() <= 2e-6
+
+
+def test_lstm_variant_matches_reference():
+    """ModelAttRNN(model_type="attbilstm2s") on the fp32 kernels (ccsm_forward_att2s_lstm) vs the reference's own forward
+    (fixture att2s_lstm.npz: seeded random weights, hidden 64, 2 layers), with explicit (h0, c0) and with the
+    reference's seeded draw order."""
+    from ccsmeth_b200.models import ModelAttRNN
+    from tests.conftest import load_npz
+    g = load_npz("att2s_lstm.npz")
+    m = ModelAttRNN(21, 2, 2, 0, 64, is_npass=True, model_type="attbilstm2s", device=0)
+    m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})
+    m = m.cuda(0).eval()
+    assert m.get_precision() == "fp32" and m.rnn_cell == "lstm"
+    a = args16(g)
+    hc = ((torch.from_numpy(g["h0_f"]), torch.from_numpy(g["c0_f"])), (torch.from_numpy(g["h0_r"]), torch.from_numpy(g["c0_r"])))
+    logits, probs = m(*a, h0=hc)
+    assert np.abs(probs.cpu().numpy() - g["probs"]).max() <= 1e-5
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() <= 1e-4
+    torch.manual_seed(int(g["seed"]))
+    _, probs = m(*a)
+    assert np.abs(probs.cpu().numpy() - g["probs_seeded"]).max() <= 1e-5
+    m.set_precision("bf16")  # ignored: the tensor-core kernels implement the GRU cell
+    _, probs = m(*a, h0=hc)
+    assert np.abs(probs.cpu().numpy() - g["probs"]).max() <= 1e-5
