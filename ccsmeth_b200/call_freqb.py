@@ -22,7 +22,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, parallel
 from .bamstream import BamPieceReader
 from .call_mods import get_motif_seqs
 from .call_mods_freq_bam import AGGR_BATCH, load_aggr_model
@@ -256,15 +256,18 @@ def write_one_line(beditem, wf, is_bed):
                             str(cov), str(round(metprob + 0.000001, 4)), "."]) + "\n")
 
 
-def iter_region_results(args, model, dnacontigs, bam_path):
-    """Streams the sorted BAM and yields (region, bed_all, bed_hp1, bed_hp2) for every reference chunk that has calls."""
+def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1):
+    """Streams the sorted BAM and yields (region, bed_all, bed_hp1, bed_hp2) for every reference chunk that has calls.
+    With world > 1 the chunks are dealt round-robin to the ranks (chunk index % world == rank): regions are
+    independent, windows never cross a chunk boundary, so no data moves between ranks."""
     motifs = get_motif_seqs(args.motifs)
     motifs_filter = motifs if (args.refsites_only or args.refsites_all) else None
     comb = args.motifs == "CG" and not args.no_comb
     chunks = get_reference_chunks(dnacontigs, args.contigs, args.chunk_len, args.motifs)
     by_contig = {}
-    for c in chunks:
-        by_contig.setdefault(c[0], []).append(c)
+    for ci, c in enumerate(chunks):
+        if ci % world == rank:
+            by_contig.setdefault(c[0], []).append(c)
     flt = _lib.BamFilter(0, 0, 0, 0, 0)
     rd = BamPieceReader(bam_path, flt, threads=max(1, args.threads), align_to=1)
     ref_names = [r[0] for r in rd.references]
@@ -318,17 +321,19 @@ def call_freqb(args):
     if not os.path.exists(args.ref):
         raise ValueError("--ref does not exist!")
     os.makedirs(os.path.dirname(os.path.abspath(args.output)), exist_ok=True)
+    rank, world, local = parallel.init_from_env()
     dnacontigs = read_fasta(args.ref)
     if args.call_mode == "aggregate":
-        model = load_aggr_model(args.aggre_model, args, device=int(os.environ.get("LOCAL_RANK", 0)))
+        model = load_aggr_model(args.aggre_model, args, device=local)
     else:
         model = AggrAttRNN(args.seq_len, args.layer_rnn, args.class_num, 0, args.hid_rnn, binsize=args.bin_size,
-                           model_type=args.model_type, device=int(os.environ.get("LOCAL_RANK", 0))).cuda().eval()
+                           model_type=args.model_type, device=local).cuda(local).eval()
     fext = "bed" if args.bed else "freq.txt"
-    paths = [args.output + ".%s.%s.%s" % (args.call_mode, g, fext) for g in ("all", "hp1", "hp2")]
+    shard = "" if world == 1 else ".rank%d" % rank  # one file set per rank; concatenate (and sort) afterwards
+    paths = [args.output + "%s.%s.%s.%s" % (shard, args.call_mode, g, fext) for g in ("all", "hp1", "hp2")]
     files = [open(p, "w") for p in paths]
     n_lines = [0, 0, 0]
-    for _, *beds in iter_region_results(args, model, dnacontigs, args.input_bam):
+    for _, *beds in iter_region_results(args, model, dnacontigs, args.input_bam, rank, world):
         for g in range(3):
             for item in beds[g]:
                 write_one_line(item, files[g], args.bed)
@@ -337,8 +342,11 @@ def call_freqb(args):
         f.close()
         if n == 0:
             os.remove(p)  # the reference removes empty outputs (:663-666)
-    sys.stderr.write("[call_freqb] %d / %d / %d sites (all / hp1 / hp2) in %.1f s\n" % (*n_lines, time.time() - t0))
-    return dict(zip(("all", "hp1", "hp2"), n_lines)), paths
+    total = parallel.allreduce_counts(n_lines + [0])[:3]  # the run's only collective, like call_mods
+    if rank == 0:
+        sys.stderr.write("[call_freqb] %d / %d / %d sites (all / hp1 / hp2) in %.1f s, %d rank(s)\n"
+                         % (*total, time.time() - t0, world))
+    return dict(zip(("all", "hp1", "hp2"), total)), paths
 
 
 def build_parser():
@@ -387,6 +395,7 @@ def build_parser():
 
 def main(argv=None):
     call_freqb(build_parser().parse_args(argv))
+    parallel.finalize()
     return 0
 
 

@@ -182,3 +182,13 @@ def test_host_chain_with_the_pileup_oracle_reproduces_the_reference_files(ref_ou
                 cf.write_one_line(item, bufs[g], False)
     for g, name in enumerate(("all", "hp1", "hp2")):
         assert bufs[g].getvalue() == ref_out["%s.%s.freq.txt" % (tag, name)], (tag, name)
+    if tag == "count":
+        # reference chunks dealt round-robin to three ranks: disjoint, and together the one-rank result
+        parts = []
+        for rank in range(3):
+            b = io.StringIO()
+            for _, *beds in cf.iter_region_results(args, OracleModel(), contigs, BAM, rank, 3):
+                for item in beds[0]:
+                    cf.write_one_line(item, b, False)
+            parts.append(b.getvalue().splitlines())
+        assert all(parts) and sorted(sum(parts, [])) == sorted(ref_out["count.all.freq.txt"].splitlines())

@@ -99,3 +99,17 @@ def test_aggregate_identical_lines_when_h0_stream_is_reproduced(tmp_path, ref_ou
     mine, ref = _read(paths[0]).splitlines(), ref_out["aggregate.all.freq.txt"].splitlines()
     same = sum(a == b for a, b in zip(mine, ref))
     assert same >= 0.98 * len(ref), (same, len(ref))
+
+
+def test_region_shards_over_ranks_cover_the_single_rank_output(tmp_path, ref_out, aggr_ckpt, monkeypatch):
+    """Reference chunks dealt round-robin to two "ranks": the union of the rank files equals the one-rank file."""
+    from ccsmeth_b200 import parallel
+    lines = []
+    for rank in (0, 1):
+        monkeypatch.setattr(parallel, "init_from_env", lambda r=rank: (r, 2, 0))
+        monkeypatch.setattr(parallel, "allreduce_counts", lambda c: list(c))
+        _, paths = _run(tmp_path, "shard", [], aggr_ckpt)
+        assert ".rank%d.count.all." % rank in paths[0]
+        lines += _read(paths[0]).splitlines()
+    ref = ref_out["count.all.freq.txt"].splitlines()
+    assert len(lines) == len(ref) and sorted(lines) == sorted(ref)
