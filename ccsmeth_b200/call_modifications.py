@@ -17,7 +17,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from .models import ModelAttRNN
+from .models import ModelAttRNN, ModelAttRNN2
 from .utils.process_utils import base2code_dna, str2bool
 
 _CODE_LUT = np.full(256, 4, dtype=np.int64)
@@ -120,9 +120,10 @@ def load_model(model_path, args, device=0, precision=None):
     """Model lifecycle of the reference's model worker (call_modifications.py:313-369): construct from the
     CLI args, ``torch.load`` the checkpoint on CPU, ``state_dict().update(); load_state_dict``, with the
     ``module.``-prefix fallback, then ``.cuda(device)`` and ``.eval()``."""
-    if args.model_type not in {"attbigru2s", "attbilstm2s"}:
-        raise ValueError("--model_type not right! (ccsmeth_b200 implements attbigru2s and attbilstm2s)")
-    model = ModelAttRNN(args.seq_len, args.layer_rnn, args.class_num, args.dropout_rate, args.hid_rnn,
+    if args.model_type not in {"attbigru2s", "attbilstm2s", "attbigru2s2", "attbilstm2s2"}:
+        raise ValueError("--model_type not right! (ccsmeth_b200 does not implement transencoder2s)")
+    cls = ModelAttRNN2 if args.model_type.endswith("2s2") else ModelAttRNN
+    model = cls(args.seq_len, args.layer_rnn, args.class_num, args.dropout_rate, args.hid_rnn,
                         is_sn=str2bool(args.is_sn), is_map=str2bool(args.is_map), is_stds=str2bool(args.is_stds),
                         is_npass=str2bool(args.is_npass), model_type=args.model_type, device=device,
                         precision=precision)

@@ -109,6 +109,16 @@ int ccsm_create(ccsm_model** out, const ccsm_config* cfg) {
       m->gates = 4;
       m->cfg.precision = CCSM_PREC_FP32;  // the tensor-core kernels implement the GRU cell only
     }
+    if (cfg->feat_flags & CCSM_MODEL_2S2) {
+      if (cfg->feat_flags & (CCSM_FEAT_STDS | CCSM_FEAT_SN | CCSM_FEAT_MAP)) {
+        set_error("ccsm_create: ModelAttRNN2 with --is_stds / --is_sn / --is_map is not implemented");
+        delete m;
+        return CCSM_EUNSUPPORTED;
+      }
+      m->is_2s2 = true;
+      m->in_feat = cfg->n_embed + 2 * 8 + ((cfg->feat_flags & CCSM_FEAT_NPASS) ? 4 : 0);  // process_utils.py:68-70
+      m->cfg.precision = CCSM_PREC_FP32;
+    }
   } else {
     m->strands = 1;
     m->in_feat = cfg->feat_flags + 1;  // bins + offset (reference models.py:639)
@@ -132,6 +142,8 @@ void ccsm_destroy(ccsm_model* m) {
   for (auto& l : m->fp32.layers) {
     l.w_ih.release(); l.b_ih.release(); l.w_hh.release(); l.b_hh.release();
   }
+  m->fp32.ipd_embed.release(); m->fp32.pw_embed.release(); m->fp32.npass_embed.release();
+  m->fp32.cls0_w.release(); m->fp32.cls0_b.release();
   m->fp32.embed.release(); m->fp32.Wa.release(); m->fp32.Ua.release(); m->fp32.va.release();
   m->fp32.fc_w.release(); m->fp32.fc_b.release();
   Fp32Workspace& ws = m->ws32;
@@ -148,11 +160,21 @@ void ccsm_destroy(ccsm_model* m) {
 // expected shape of every state_dict key (reference models.py:33,52-64,644-654)
 static bool expected_shape(const ccsm_model* m, const std::string& key, std::vector<int64_t>& shp) {
   const int64_t H = m->cfg.hidden, C = m->cfg.num_classes;
-  if (key == "embed.weight" && m->cfg.kind == CCSM_KIND_ATT2S) { shp = {m->cfg.n_vocab, m->cfg.n_embed}; return true; }
+  if (m->is_2s2) {
+    if (key == "seq_embed.weight") { shp = {m->cfg.n_vocab, m->cfg.n_embed}; return true; }
+    if (key == "ipd_embed.weight" || key == "pw_embed.weight") { shp = {953, 8}; return true; }  // MAX_KINETICS + 1
+    if (key == "npass_embed.weight" && (m->cfg.feat_flags & CCSM_FEAT_NPASS)) { shp = {31, 4}; return true; }
+    if (key == "classifier.0.weight") { shp = {4 * H, 4 * H}; return true; }
+    if (key == "classifier.0.bias") { shp = {4 * H}; return true; }
+    if (key == "classifier.3.weight") { shp = {C, 4 * H}; return true; }
+    if (key == "classifier.3.bias") { shp = {C}; return true; }
+  } else {
+    if (key == "embed.weight" && m->cfg.kind == CCSM_KIND_ATT2S) { shp = {m->cfg.n_vocab, m->cfg.n_embed}; return true; }
+    if (key == "fc1.weight") { shp = {C, 2 * H * m->strands}; return true; }
+    if (key == "fc1.bias") { shp = {C}; return true; }
+  }
   if (key == "_att3.Wa.weight" || key == "_att3.Ua.weight") { shp = {H, 2 * H}; return true; }
   if (key == "_att3.va.weight") { shp = {1, H}; return true; }
-  if (key == "fc1.weight") { shp = {C, 2 * H * m->strands}; return true; }
-  if (key == "fc1.bias") { shp = {C}; return true; }
   for (int l = 0; l < m->cfg.num_layers; ++l)
     for (int d = 0; d < 2; ++d) {
       std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
@@ -196,8 +218,17 @@ int ccsm_set_weight(ccsm_model* m, const char* key_c, const float* host, const i
 }
 
 static int check_complete(ccsm_model* m) {
-  std::vector<std::string> keys = {"_att3.Wa.weight", "_att3.Ua.weight", "_att3.va.weight", "fc1.weight", "fc1.bias"};
-  if (m->cfg.kind == CCSM_KIND_ATT2S) keys.push_back("embed.weight");
+  std::vector<std::string> keys = {"_att3.Wa.weight", "_att3.Ua.weight", "_att3.va.weight"};
+  if (m->is_2s2) {
+    for (const char* k : {"seq_embed.weight", "ipd_embed.weight", "pw_embed.weight", "classifier.0.weight", "classifier.0.bias",
+                          "classifier.3.weight", "classifier.3.bias"})
+      keys.push_back(k);
+    if (m->cfg.feat_flags & CCSM_FEAT_NPASS) keys.push_back("npass_embed.weight");
+  } else {
+    keys.push_back("fc1.weight");
+    keys.push_back("fc1.bias");
+    if (m->cfg.kind == CCSM_KIND_ATT2S) keys.push_back("embed.weight");
+  }
   for (int l = 0; l < m->cfg.num_layers; ++l)
     for (int d = 0; d < 2; ++d) {
       std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
@@ -241,7 +272,7 @@ int ccsm_set_precision(ccsm_model* m, int32_t precision) {
     set_error("ccsm_set_precision: bad argument");
     return CCSM_EINVAL;
   }
-  if (m->cfg.kind == CCSM_KIND_AGGR || m->gates == 4) precision = CCSM_PREC_FP32;
+  if (m->cfg.kind == CCSM_KIND_AGGR || m->gates == 4 || m->is_2s2) precision = CCSM_PREC_FP32;
   if (precision == m->cfg.precision) return CCSM_OK;
   m->cfg.precision = precision;
   if (m->finalized && is_tc(precision)) {

@@ -61,6 +61,8 @@ struct Fp32Layer {
 struct Fp32Weights {
   std::vector<Fp32Layer> layers;
   DevBuf embed;        // (n_vocab, n_embed)
+  DevBuf ipd_embed, pw_embed, npass_embed;  // ModelAttRNN2: (953, 8), (953, 8), (31, 4)
+  DevBuf cls0_w, cls0_b;                    // ModelAttRNN2: classifier.0 (4H, 4H), (4H); classifier.3 lives in fc_w / fc_b
   DevBuf Wa, Ua, va;   // (H, 2H), (H, 2H), (H)
   DevBuf fc_w, fc_b;   // (classes, strands*2H), (classes)
   bool ready = false;
@@ -108,6 +110,7 @@ struct ccsm_model {
   int strands = 2;    // 2 for att2s, 1 for aggr
   int in_feat = 0;    // GRU layer-0 input width (att2s: n_embed + feas_ccs; aggr: bins + 1)
   int gates = 3;      // 3 GRU (r, z, n) / 4 LSTM (i, f, g, o): gate row blocks of the rnn weights
+  bool is_2s2 = false;  // ModelAttRNN2: integer kinetics embeddings + two-layer classifier (CCSM_MODEL_2S2)
   std::map<std::string, ccsm::HostTensor> w;
   bool finalized = false;
   ccsm::Fp32Weights fp32;

@@ -173,6 +173,70 @@ __global__ void pack_x_att2s_kernel(int64_t sites, int L, int E, int n_vocab, in
   for (; k < Kpad; ++k) x[k] = 0.f;
 }
 
+// ModelAttRNN2 (models.py:319-333): x = [seq_embed[kmer] (E) | ipd_embed[int(ipd)] (8) | pw_embed[int(pw)] (8) |
+// npass_embed[clamp(npass, 1, 30)] (4)?].  Indices outside a table (the reference would raise) are clamped.
+__global__ void pack_x_att2s2_kernel(int64_t sites, int L, int E, int n_vocab, int flags, int Kpad, StrandPtrs s0,
+                                     StrandPtrs s1, const float* __restrict__ seq_embed,
+                                     const float* __restrict__ ipd_embed, const float* __restrict__ pw_embed,
+                                     const float* __restrict__ npass_embed, float* __restrict__ x0) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (site, strand, t)
+  if (idx >= sites * 2 * L) return;
+  int t = (int)(idx % L);
+  int64_t R = idx / L;
+  const StrandPtrs& s = (R & 1) ? s1 : s0;
+  int64_t o = (R >> 1) * L + t;
+  float* x = x0 + idx * Kpad;
+  auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  const int code = clampi((int)s.kmer[o], 0, n_vocab - 1);
+  const int ic = clampi((int)s.ipd[o], 0, 952), pc = clampi((int)s.pw[o], 0, 952);
+  int k = 0;
+  for (int j = 0; j < E; ++j) x[k++] = seq_embed[code * E + j];
+  for (int j = 0; j < 8; ++j) x[k++] = ipd_embed[ic * 8 + j];
+  for (int j = 0; j < 8; ++j) x[k++] = pw_embed[pc * 8 + j];
+  if (flags & CCSM_FEAT_NPASS) {
+    // torch.clamp(kpass, 1, MAX_PASSES).int(): clamp the float, then truncate
+    const float kp = fminf(fmaxf(s.kpass[o], 1.f), 30.f);
+    const int np = (int)kp;
+    for (int j = 0; j < 4; ++j) x[k++] = npass_embed[np * 4 + j];
+  }
+  for (; k < Kpad; ++k) x[k] = 0.f;
+}
+
+// classifier tail of ModelAttRNN2 (models.py:275-278,378-380): hid already holds Linear(4H,4H)(ctx) + bias;
+// logits = Linear(4H, classes)(relu(hid)), probs = softmax(logits).  One warp per site.
+template <int MAXC>
+__global__ void cls_out_kernel(int64_t sites, int D, int classes, const float* __restrict__ hid,
+                               const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ logits,
+                               float* __restrict__ probs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t site = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (site >= sites) return;
+  float lg[MAXC];
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) lg[k] = 0.f;
+  for (int j = lane; j < D; j += 32) {
+    const float v = fmaxf(hid[site * D + j], 0.f);
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k)
+      if (k < classes) lg[k] += v * w[(int64_t)k * D + j];
+  }
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lg[k] += __shfl_xor_sync(0xffffffffu, lg[k], o);
+    if (k < classes) lg[k] += b[k];
+  }
+  if (lane == 0) {
+    float mx = -INFINITY, sum = 0.f;
+    for (int k = 0; k < classes; ++k) mx = fmaxf(mx, lg[k]);
+    for (int k = 0; k < classes; ++k) sum += expf(lg[k] - mx);
+    for (int k = 0; k < classes; ++k) {
+      if (logits) logits[site * classes + k] = lg[k];
+      if (probs) probs[site * classes + k] = expf(lg[k] - mx) / sum;
+    }
+  }
+}
+
 // aggregate model: x = cat(histos (n,L,B), offsets (n,L,1))   (reference models.py:675-677)
 __global__ void pack_x_aggr_kernel(int64_t sites, int L, int Bn, int Kpad, const float* __restrict__ offsets,
                                    const float* __restrict__ histos, float* __restrict__ x0) {
@@ -265,7 +329,8 @@ __global__ void att_head_kernel(int64_t sites, int strands, int L, int H, int cl
                                 const float* __restrict__ E, const float* __restrict__ qa,
                                 const float* __restrict__ out, const float* __restrict__ va,
                                 const float* __restrict__ fc_w, const float* __restrict__ fc_b,
-                                float* __restrict__ logits, float* __restrict__ probs) {
+                                float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ ctx_out) {
+  // ctx_out != nullptr: only write the context vectors [ctx_strand1 | ctx_strand2] (ModelAttRNN2's classifier follows)
   const int lane = threadIdx.x & 31;
   const int64_t site = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (site >= sites) return;
@@ -295,11 +360,16 @@ __global__ void att_head_kernel(int64_t sites, int strands, int L, int H, int cl
     for (int c = lane; c < C2; c += 32) {
       float ctx = 0.f;
       for (int t = 0; t < L; ++t) ctx += __shfl_sync(0xffffffffu, w, t) * out[(R * L + t) * (int64_t)C2 + c];
+      if (ctx_out) {
+        ctx_out[site * (int64_t)strands * C2 + s * C2 + c] = ctx;
+        continue;
+      }
 #pragma unroll
       for (int k = 0; k < MAXC; ++k)
         if (k < classes) lg[k] += ctx * fc_w[(int64_t)k * strands * C2 + s * C2 + c];
     }
   }
+  if (ctx_out) return;
 #pragma unroll
   for (int k = 0; k < MAXC; ++k) {
 #pragma unroll
@@ -364,12 +434,23 @@ int fp32_upload_weights(ccsm_model* m) {
     CCSM_TRY(upload(Lw.w_hh, whh));
     CCSM_TRY(upload(Lw.b_hh, bhh));
   }
-  if (m->cfg.kind == CCSM_KIND_ATT2S) CCSM_TRY(upload(W.embed, find(m, "embed.weight")->data));
   CCSM_TRY(upload(W.Wa, find(m, "_att3.Wa.weight")->data));
   CCSM_TRY(upload(W.Ua, find(m, "_att3.Ua.weight")->data));
   CCSM_TRY(upload(W.va, find(m, "_att3.va.weight")->data));
-  CCSM_TRY(upload(W.fc_w, find(m, "fc1.weight")->data));
-  CCSM_TRY(upload(W.fc_b, find(m, "fc1.bias")->data));
+  if (m->is_2s2) {
+    CCSM_TRY(upload(W.embed, find(m, "seq_embed.weight")->data));
+    CCSM_TRY(upload(W.ipd_embed, find(m, "ipd_embed.weight")->data));
+    CCSM_TRY(upload(W.pw_embed, find(m, "pw_embed.weight")->data));
+    if (m->cfg.feat_flags & CCSM_FEAT_NPASS) CCSM_TRY(upload(W.npass_embed, find(m, "npass_embed.weight")->data));
+    CCSM_TRY(upload(W.cls0_w, find(m, "classifier.0.weight")->data));
+    CCSM_TRY(upload(W.cls0_b, find(m, "classifier.0.bias")->data));
+    CCSM_TRY(upload(W.fc_w, find(m, "classifier.3.weight")->data));
+    CCSM_TRY(upload(W.fc_b, find(m, "classifier.3.bias")->data));
+  } else {
+    if (m->cfg.kind == CCSM_KIND_ATT2S) CCSM_TRY(upload(W.embed, find(m, "embed.weight")->data));
+    CCSM_TRY(upload(W.fc_w, find(m, "fc1.weight")->data));
+    CCSM_TRY(upload(W.fc_b, find(m, "fc1.bias")->data));
+  }
   W.ready = true;
   return CCSM_OK;
 }
@@ -448,10 +529,26 @@ static int run_stack(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_tota
     set_error("num_classes > 4 unsupported");
     return CCSM_EINVAL;
   }
+  float* lg = logits ? logits + site0 * m->cfg.num_classes : nullptr;
+  float* pr = probs ? probs + site0 * m->cfg.num_classes : nullptr;
+  if (m->is_2s2) {
+    // contexts -> classifier.0 (GEMM + bias) -> ReLU + classifier.3 + softmax; scratch lives in gi behind E
+    const int D = S * 2 * H;
+    float* ctx = E + rows * L * (int64_t)H;
+    float* hid = ctx + sites * (int64_t)D;
+    att_head_kernel<4><<<nblk(sites, warps), warps * 32, 0, st>>>(sites, S, L, H, 0, 0, E, ws.qa.as<float>(), out,
+                                                                  W.va.as<float>(), nullptr, nullptr, nullptr, nullptr, ctx);
+    count_launch();
+    CCSM_TRY(sgemm_nt((int)sites, D, D, ctx, D, 0, W.cls0_w.as<float>(), D, 0, W.cls0_b.as<float>(), 0, hid, D, 0, 1, st));
+    cls_out_kernel<4><<<nblk(sites, warps), warps * 32, 0, st>>>(sites, D, m->cfg.num_classes, hid, W.fc_w.as<float>(),
+                                                                 W.fc_b.as<float>(), lg, pr);
+    count_launch();
+    CCSM_CUDA(cudaGetLastError());
+    return CCSM_OK;
+  }
   att_head_kernel<4><<<nblk(sites, warps), warps * 32, 0, st>>>(
       sites, S, L, H, m->cfg.num_classes, m->cfg.kind == CCSM_KIND_ATT2S ? 1 : 0, E, ws.qa.as<float>(), out,
-      W.va.as<float>(), W.fc_w.as<float>(), W.fc_b.as<float>(),
-      logits ? logits + site0 * m->cfg.num_classes : nullptr, probs ? probs + site0 * m->cfg.num_classes : nullptr);
+      W.va.as<float>(), W.fc_w.as<float>(), W.fc_b.as<float>(), lg, pr, nullptr);
   count_launch();
   CCSM_CUDA(cudaGetLastError());
   return CCSM_OK;
@@ -481,9 +578,15 @@ int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
   CCSM_TRY(reserve_ws(m, chunk * 2));
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     int64_t sites = (n - s0) < chunk ? (n - s0) : chunk;
-    pack_x_att2s_kernel<<<nblk(sites * 2 * L, 256), 256, 0, st>>>(
-        sites, L, m->cfg.n_embed, m->cfg.n_vocab, m->cfg.feat_flags, m->fp32.layers[0].Kpad,
-        offset_strand(fwd, s0, L), offset_strand(rev, s0, L), m->fp32.embed.as<float>(), m->ws32.x0.as<float>());
+    if (m->is_2s2)
+      pack_x_att2s2_kernel<<<nblk(sites * 2 * L, 256), 256, 0, st>>>(
+          sites, L, m->cfg.n_embed, m->cfg.n_vocab, m->cfg.feat_flags, m->fp32.layers[0].Kpad, offset_strand(fwd, s0, L),
+          offset_strand(rev, s0, L), m->fp32.embed.as<float>(), m->fp32.ipd_embed.as<float>(), m->fp32.pw_embed.as<float>(),
+          m->fp32.npass_embed.as<float>(), m->ws32.x0.as<float>());
+    else
+      pack_x_att2s_kernel<<<nblk(sites * 2 * L, 256), 256, 0, st>>>(
+          sites, L, m->cfg.n_embed, m->cfg.n_vocab, m->cfg.feat_flags, m->fp32.layers[0].Kpad,
+          offset_strand(fwd, s0, L), offset_strand(rev, s0, L), m->fp32.embed.as<float>(), m->ws32.x0.as<float>());
     count_launch();
     CCSM_TRY(run_stack(m, sites, s0, n, h0_f, h0_r, logits, probs, st, c0_f, c0_r));
   }

@@ -398,6 +398,62 @@ class ModelAttRNN(_NativeModule):
         return res
 
 
+class ModelAttRNN2(ModelAttRNN):
+    """Drop-in for the reference ``ModelAttRNN2`` (``model_type`` "attbigru2s2" / "attbilstm2s2", models.py:221-382):
+    bases, kinetics (as integers: use ``--norm none``) and pass counts are embedded, the head is a two-layer
+    classifier.  No checkpoint ships for it; fp32 kernels; same 16-tensor ``forward`` as ``ModelAttRNN``."""
+
+    def __init__(self, seq_len=21, num_layers=3, num_classes=2, dropout_rate=0.5, hidden_size=256,
+                 is_npass=True, is_sn=False, is_map=False, is_stds=False, model_type="attbigru2s2", device=0,
+                 precision=None):
+        nn.Module.__init__(self)
+        if model_type not in ("attbigru2s2", "attbilstm2s2"):
+            raise ValueError("--model_type not set right!")
+        if is_sn or is_map or is_stds:
+            raise ValueError("ccsmeth_b200 implements ModelAttRNN2 with the kinetics and pass-count features only")
+        self.model_type = model_type
+        self.device = device
+        self.seq_len, self.num_layers, self.num_classes, self.hidden_size = seq_len, num_layers, num_classes, hidden_size
+        self.n_embed = NEMBED_BASE
+        self.is_stds, self.is_npass, self.is_sn, self.is_map = is_stds, is_npass, is_sn, is_map
+        self.rnn_cell = "lstm" if model_type == "attbilstm2s2" else "gru"
+        self.feas_ccs = 2 + (1 if is_npass else 0)
+        self.nembed_all = NEMBED_BASE + 2 * 8 + (4 if is_npass else 0)  # NEMBED_KINETICS = 8, NEMBED_PASSES = 4
+        # parameter containers in the reference's construction order (same state_dict keys, same generator draws)
+        self.seq_embed = nn.Embedding(N_VOCAB, NEMBED_BASE)
+        self.ipd_embed = nn.Embedding(952 + 1, 8)   # MAX_KINETICS + 1
+        self.pw_embed = nn.Embedding(952 + 1, 8)
+        if is_npass:
+            self.npass_embed = nn.Embedding(30 + 1, 4)  # MAX_PASSES + 1
+        rnn_cls = nn.LSTM if self.rnn_cell == "lstm" else nn.GRU
+        self.rnn = rnn_cls(self.nembed_all, hidden_size, num_layers, dropout=dropout_rate, batch_first=True,
+                           bidirectional=True)
+        self._att3 = Attention(hidden_size * 2, hidden_size * 2, hidden_size)
+        self.classifier = nn.Sequential(nn.Linear(hidden_size * 4, hidden_size * 4), nn.ReLU(), nn.Dropout(p=dropout_rate),
+                                        nn.Linear(hidden_size * 4, num_classes))
+        self.init_weights()
+        self.requires_grad_(False)
+        self._native_init("fp32")
+
+    def init_weights(self):  # reference models.py:285-303
+        for emb in (self.seq_embed, self.ipd_embed, self.pw_embed):
+            nn.init.uniform_(emb.weight, -0.1, 0.1)
+        if self.is_npass:
+            nn.init.uniform_(self.npass_embed.weight, -0.1, 0.1)
+        for m in self.classifier.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.uniform_(m.weight, -0.1, 0.1)
+                nn.init.zeros_(m.bias)
+
+    def _config(self, dev):
+        flags = _lib.MODEL_2S2 | (_lib.FEAT_NPASS if self.is_npass else 0) | (_lib.CELL_LSTM if self.rnn_cell == "lstm" else 0)
+        return _lib.Config(_lib.KIND_ATT2S, self.seq_len, self.num_layers, self.hidden_size, self.num_classes,
+                           N_VOCAB, self.n_embed, flags, _lib.PREC["fp32"], dev)
+
+    def set_precision(self, precision):  # fp32 kernels only
+        return self
+
+
 class AggrAttRNN(_NativeModule):
     """Drop-in for the reference ``AggrAttRNN`` with ``model_type="attbigru"`` (models.py:625-694):
     regression over 11 neighbouring CpG sites, raw fc1 output (no softmax)."""

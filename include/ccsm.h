@@ -66,6 +66,12 @@ extern "C" {
  * nn.GRU: state_dict keys are the same with 4*hidden gate rows (i, f, g, o), the initial state is (h0, c0).  No
  * checkpoint ships for it; it runs in CCSM_PREC_FP32 only and through ccsm_forward_att2s_lstm. */
 #define CCSM_CELL_LSTM  16
+/* model class, carried in feat_flags: ModelAttRNN2 (model_type "attbigru2s2" / "attbilstm2s2", models.py:221-382) --
+ * the kinetics are embedded as integers (ipd_embed / pw_embed: 953 x 8, npass_embed: 31 x 4 on clamp(npass, 1, 30))
+ * and the head is classifier = Linear(4H, 4H) + ReLU + Linear(4H, classes).  state_dict keys: seq_embed.weight,
+ * ipd_embed.weight, pw_embed.weight, npass_embed.weight, rnn.*, _att3.*, classifier.0.*, classifier.3.*.
+ * CCSM_PREC_FP32 only; --is_stds / --is_sn / --is_map are not implemented for it. */
+#define CCSM_MODEL_2S2  32
 
 typedef struct ccsm_model ccsm_model;
 

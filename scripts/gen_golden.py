@@ -330,6 +330,44 @@ def gen_lstm():
     print("att2s_lstm: mean p1 %.4f" % probs[:, 1].mean().item())
 
 
+def gen_2s2():
+    """Section 8f-4: the reference's ModelAttRNN2 ("attbigru2s2", "attbilstm2s2") on seeded random weights (hidden 64,
+    2 layers; no checkpoint ships), raw integer kinetics as input (the model embeds them), explicit initial states."""
+    ref = refimport.import_reference()
+    import ccsmeth.models as rmodels
+    rng = np.random.default_rng(12)
+    n, L = 96, 21
+    feats = {}
+    for sfx in ("", "2"):
+        feats["kmer" + sfx] = torch.from_numpy(rng.integers(0, 5, (n, L)).astype(np.float32))
+        feats["ipd" + sfx] = torch.from_numpy(rng.integers(0, 953, (n, L)).astype(np.float32))
+        feats["pw" + sfx] = torch.from_numpy(rng.integers(0, 953, (n, L)).astype(np.float32))
+        feats["kpass" + sfx] = torch.from_numpy(np.repeat(rng.integers(0, 45, (n, 1)), L, axis=1).astype(np.float32))
+    z = torch.zeros(n)
+    args = (feats["kmer"], feats["kpass"], feats["ipd"], z, feats["pw"], z, z, z,
+            feats["kmer2"], feats["kpass2"], feats["ipd2"], z, feats["pw2"], z, z, z)
+    save = {k: v.numpy() for k, v in feats.items()}
+    old = rmodels.use_cuda
+    rmodels.use_cuda = False
+    try:
+        for tag, mt in (("gru", "attbigru2s2"), ("lstm", "attbilstm2s2")):
+            torch.manual_seed(2468)
+            m = rmodels.ModelAttRNN2(21, 2, 2, 0, 32, is_npass=True, model_type=mt, device="cpu")
+            m.eval()
+            g = torch.Generator().manual_seed(7)
+            hs = [torch.randn(4, n, 32, generator=g) for _ in range(4)]
+            fixed = [hs[0], hs[1]] if tag == "gru" else [(hs[0], hs[1]), (hs[2], hs[3])]
+            with refimport.fixed_h0(m, [tuple(t.clone() for t in f) if isinstance(f, tuple) else f.clone() for f in fixed]):
+                logits, probs = m(*args)
+            save.update({"%s.sd.%s" % (tag, k): v.detach().numpy() for k, v in m.state_dict().items()})
+            save.update({"%s.h%d" % (tag, i): h.numpy() for i, h in enumerate(hs[:2 if tag == "gru" else 4])})
+            save["%s.logits" % tag], save["%s.probs" % tag] = logits.detach().numpy(), probs.detach().numpy()
+            print("2s2", tag, "mean p1 %.4f" % probs[:, 1].mean().item())
+    finally:
+        rmodels.use_cuda = old
+    np.savez_compressed(os.path.join(OUT, "att2s2.npz"), **save)
+
+
 class DuckBam:
     """What the reference's region worker needs from pysam.AlignmentFile: fetch(contig, start, stop) over records that
     overlap the interval, in file order (records are ccsmeth_b200.bamio.BamRecord)."""
@@ -413,6 +451,9 @@ def gen_freqb():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "2s2":
+        gen_2s2()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "lstm":
         gen_lstm()
         sys.exit(0)
@@ -430,6 +471,7 @@ if __name__ == "__main__":
     gen_aggr()
     gen_pileup()
     gen_lstm()
+    gen_2s2()
     gen_freqb()
     gen_demo()
     for f in sorted(os.listdir(OUT)):

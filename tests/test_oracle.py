@@ -106,3 +106,17 @@ def test_lstm_numpy_oracle_matches_reference():
                                              (g["h0_f"], g["c0_f"]), (g["h0_r"], g["c0_r"]), num_layers=2)
     assert np.abs(probs - g["probs"]).max() <= 1e-6
     assert np.abs(logits - g["logits"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("cell", ["gru", "lstm"])
+def test_2s2_numpy_oracle_matches_reference(cell):
+    """ModelAttRNN2 (attbigru2s2 / attbilstm2s2, reference models.py:221-382): numpy restatement vs the reference's own
+    forward on seeded random weights."""
+    from tests.conftest import load_npz
+    g = load_npz("att2s2.npz")
+    sd = {k[len(cell) + 4:]: v for k, v in g.items() if k.startswith(cell + ".sd.")}
+    h = (g[cell + ".h0"], g[cell + ".h1"]) if cell == "gru" else ((g[cell + ".h0"], g[cell + ".h1"]), (g[cell + ".h2"], g[cell + ".h3"]))
+    logits, probs = att2s_numpy.forward_2s2(sd, *[g[k] for k in ("kmer", "kpass", "ipd", "pw", "kmer2", "kpass2", "ipd2", "pw2")],
+                                            h[0], h[1], num_layers=2, cell=cell)
+    assert np.abs(probs - g[cell + ".probs"]).max() <= 1e-6
+    assert np.abs(logits - g[cell + ".logits"]).max() <= 1e-5

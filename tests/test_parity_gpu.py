@@ -187,3 +187,20 @@ def test_lstm_variant_matches_reference():
     m.set_precision("bf16")  # ignored: the tensor-core kernels implement the GRU cell
     _, probs = m(*a, h0=hc)
     assert np.abs(probs.cpu().numpy() - g["probs"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("cell,mt", [("gru", "attbigru2s2"), ("lstm", "attbilstm2s2")])
+def test_2s2_variants_match_reference(cell, mt):
+    """ModelAttRNN2 on the fp32 kernels (integer kinetics / pass-count embeddings, two-layer classifier) vs the
+    reference's own forward (fixture att2s2.npz: seeded random weights, hidden 32, 2 layers)."""
+    from ccsmeth_b200.models import ModelAttRNN2
+    from tests.conftest import load_npz
+    g = load_npz("att2s2.npz")
+    m = ModelAttRNN2(21, 2, 2, 0, 32, is_npass=True, model_type=mt, device=0)
+    m.load_state_dict({k[len(cell) + 4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith(cell + ".sd.")})
+    m = m.cuda(0).eval()
+    t = lambda k: torch.from_numpy(g[k])
+    h = (t(cell + ".h0"), t(cell + ".h1")) if cell == "gru" else ((t(cell + ".h0"), t(cell + ".h1")), (t(cell + ".h2"), t(cell + ".h3")))
+    logits, probs = m(*args16(g), h0=h)
+    assert np.abs(probs.cpu().numpy() - g[cell + ".probs"]).max() <= 1e-5
+    assert np.abs(logits.cpu().numpy() - g[cell + ".logits"]).max() <= 1e-4
