@@ -139,6 +139,20 @@ __device__ __forceinline__ void arm_bias16(uint32_t trow, int ub, const float* b
   }
 }
 
+// Same for 8 hidden units [u0, u0+8) at accumulator columns col0 + {0, 64, 128, 192} (pipelined epilogue).
+__device__ __forceinline__ void arm_bias8(uint32_t trow, int col0, const float* bias_d, int u0) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t v[8];
+    const int goff = g == 0 ? 512 : (g == 1 ? 0 : (g == 2 ? 256 : 768));
+    const float4* src = reinterpret_cast<const float4*>(bias_d + goff + u0);
+    const float4 b0 = src[0], b1 = src[1];
+    v[0] = __float_as_uint(b0.x); v[1] = __float_as_uint(b0.y); v[2] = __float_as_uint(b0.z); v[3] = __float_as_uint(b0.w);
+    v[4] = __float_as_uint(b1.x); v[5] = __float_as_uint(b1.y); v[6] = __float_as_uint(b1.z); v[7] = __float_as_uint(b1.w);
+    tmem_st8(trow + g * 64 + col0, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // prep: features -> x0 image (embedding lookup + kinetics concat, reference models.py:91-106),
 //       h0 (2*layers, n, H) fp32 -> h0 images.  One thread per strand-row.
@@ -279,7 +293,11 @@ struct GruCfg {
 //           memory (cp.async.bulk ... .multicast::cluster), halving the L2 -> SM weight traffic (weights are
 //           6/7 of what this kernel pulls through the crossbar).  A stage is refilled only when BOTH CTAs'
 //           MMAs have retired it (multicast tcgen05.commit onto both empty barriers, count 2).
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false>
+//   PIPE  = software-pipelined gate epilogue: the accumulators are read in 8-unit sub-blocks and the tcgen05.ld of
+//           sub-block i+1 is in flight while sub-block i goes through the MUFU / pack / store work (same register
+//           footprint as one 16-unit block).  Aimed at layer 0, whose epilogue (128 KB of TMEM reads per chunk at
+//           64 B/cycle) is longer than its 17 MMAs.
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false, bool PIPE = false>
 __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS, GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
   static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
@@ -538,6 +556,41 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
           const uint32_t trow = trow0 + (NBUF == 2 ? buf * 256 : 0);
           mbar_wait(tmem_full + 8 * buf, bphase);
           tc_fence_after();
+          if constexpr (PIPE) {
+            constexpr int NSB = 2 * NUB;  // 8-unit sub-blocks of this warp
+            uint32_t acc[2][4][8];        // [ping-pong][n_i, r, z, n_h][8 units]
+            const int c00 = ub0 * 16;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + c00, acc[0][g]);
+#pragma unroll
+            for (int sb = 0; sb < NSB; ++sb) {
+              const int col = c00 + sb * 8;
+              tmem_ld_wait();  // sub-block sb has landed (issued one iteration ago)
+              if (sb + 1 < NSB) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(sb + 1) & 1][g]);
+              }
+              // re-arm these columns with the biases of the unit-chunk that uses this buffer next
+              arm_bias8(trow, col, bz, ((j + NBUF) & 3) * 64 + col);
+              float hp[8], hn[8];
+              join8<P, F16>(hph[sb], hpl[sb], hp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float r = sigmoid_<FAST>(__uint_as_float(acc[sb & 1][1][i]));
+                const float z = sigmoid_<FAST>(__uint_as_float(acc[sb & 1][2][i]));
+                const float n = tanh_<FAST>(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
+                hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
+              }
+              uint4 hi, lo;
+              split8<P, F16>(hn, hi, lo);
+              const int slab = (col >> 3);  // K-slab of these 8 units inside the 64-unit chunk
+              if constexpr (HS) {
+                if (s + 1 < L) *reinterpret_cast<uint4*>(hnext + slab * A_SLAB + row * 16) = hi;
+              }
+              *reinterpret_cast<uint4*>(out_base + slab * A_SLAB + row * 16) = hi;
+              if constexpr (P == 2) *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + slab * A_SLAB + row * 16) = lo;
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < NUB; ++k) {
             const int ub = ub0 + k;
@@ -571,6 +624,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
               if constexpr (P == 2)
                 *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + (ub * 2 + q) * A_SLAB + row * 16) = lo;
             }
+          }
           }
           tmem_st_wait();
           tc_fence_before();
@@ -1344,6 +1398,7 @@ static int tc_reserve(ccsm_model* m, int64_t tiles) {
 // 5 = variant 0 with 40 KB stages, 6 = variant 2 with two epilogue warps per quadrant,
 // 7 / 8 / 9 = variants 2 / 0 / 5 as clusters of two CTAs sharing every weight stage by TMA multicast,
 // a / b (10 / 11) = h_t kept in shared memory between steps (HS), 8 / 4 epilogue warps,
+// c / d / e (12 / 13 / 14) = variants 0 / 2 / 6 with the software-pipelined gate epilogue (PIPE),
 // 3 = CTA pair (cta_group::2, M = 256, TMEM double-buffered), 4 = CTA pair, two clusters per TPC (NBUF 1).
 // Selectable per layer class for experiments: CCSM_TC_VARIANT="<layer0><layers>=1>", e.g. "02".
 // Measured defaults (profiles/r01_variants.md): layer 0 (K_in = 16, latency-bound) -> 0 (two CTAs per SM);
@@ -1354,21 +1409,22 @@ static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    auto dig = [](char c) { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'b') ? 10 + (c - 'a') : -1; };
+    auto dig = [](char c) { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'e') ? 10 + (c - 'a') : -1; };
     v[0] = e ? dig(e[0]) : -1;
     v[1] = (e && e[0] && dig(e[1]) >= 0) ? dig(e[1]) : v[0];
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
-  // x3 modes: layer 0 on variant 6 (8 epilogue warps: 395 vs 484 ms per 3 steps; single-pass modes see no difference)
-  return layer > 0 ? 2 : (P == 2 ? 6 : 0);
+  // Defaults = the pipelined-epilogue forms (profiles/r01_variants.md): layers >= 1 -> d (variant 2 + PIPE); layer 0 ->
+  // c (two CTAs per SM + PIPE) in the single-pass modes, e (8 epilogue warps + PIPE) in the x3 modes.
+  return layer > 0 ? 13 : (P == 2 ? 14 : 12);
 }
 
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false, bool HS = false>
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false, bool HS = false, bool PIPE = false>
 static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
   using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>;
   static bool attr = false;
-  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC, HS>;
+  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC, HS, PIPE>;
   if (!attr) {
     CCSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr = true;
@@ -1418,6 +1474,9 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
     case 11:
       if constexpr (P == 1) return launch_gru<P, F16, 1, 2, 4, 1, false, true>(gp, tiles, sm_count, st);
       else return launch_gru<P, F16, 1, 2, 8, 2>(gp, tiles, sm_count, st);
+    case 12: return launch_gru<P, F16, 1, 1, 4, 1, false, false, true>(gp, tiles, sm_count, st);  // 0 + pipelined epilogue
+    case 13: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 2 + pipelined epilogue
+    case 14: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true>(gp, tiles, sm_count, st);  // 6 + pipelined epilogue
     default:
       set_error("unknown GRU kernel variant %d", variant);
       return CCSM_EINVAL;
