@@ -1,0 +1,33 @@
+"""The driver-facing contract of bench.py that can be checked without a GPU: the reference arm prints ONE JSON line
+with the agreed keys, and non-zero ranks of a multi-rank reference launch stay silent."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra=None, gpus="1"):
+    env = dict(os.environ, **(env_extra or {}))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", gpus, "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+def test_reference_arm_prints_one_json_line():
+    out = _run().strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    assert d["impl"] == "reference" and d["unit"] == "sites/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("CpG sites/sec call_mods attbigru2s")
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert "workload" in d["config"] and d["gpu_launches"] == 0
+
+
+def test_reference_arm_non_zero_rank_is_silent():
+    assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, gpus="2").strip() == ""
