@@ -17,7 +17,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from .models import ModelAttRNN, ModelAttRNN2
+from .models import ModelAttRNN, ModelAttRNN2, ModelTransEnc
 from .utils.process_utils import base2code_dna, str2bool
 
 _CODE_LUT = np.full(256, 4, dtype=np.int64)
@@ -120,13 +120,23 @@ def load_model(model_path, args, device=0, precision=None):
     """Model lifecycle of the reference's model worker (call_modifications.py:313-369): construct from the
     CLI args, ``torch.load`` the checkpoint on CPU, ``state_dict().update(); load_state_dict``, with the
     ``module.``-prefix fallback, then ``.cuda(device)`` and ``.eval()``."""
-    if args.model_type not in {"attbigru2s", "attbilstm2s", "attbigru2s2", "attbilstm2s2"}:
-        raise ValueError("--model_type not right! (ccsmeth_b200 does not implement transencoder2s)")
+    if args.model_type not in {"attbigru2s", "attbilstm2s", "attbigru2s2", "attbilstm2s2", "transencoder2s"}:
+        raise ValueError("--model_type not right!")
+    if args.model_type == "transencoder2s":  # reference call_modifications.py:333-338
+        model = ModelTransEnc(args.seq_len, args.layer_trans, args.class_num, args.dropout_rate, args.d_model, args.nhead,
+                              args.dim_ff, is_npass=str2bool(args.is_npass), is_sn=str2bool(args.is_sn),
+                              is_map=str2bool(args.is_map), is_stds=str2bool(args.is_stds), model_type=args.model_type,
+                              device=device)
+        return _load_and_place(model, model_path, device)
     cls = ModelAttRNN2 if args.model_type.endswith("2s2") else ModelAttRNN
     model = cls(args.seq_len, args.layer_rnn, args.class_num, args.dropout_rate, args.hid_rnn,
                         is_sn=str2bool(args.is_sn), is_map=str2bool(args.is_map), is_stds=str2bool(args.is_stds),
                         is_npass=str2bool(args.is_npass), model_type=args.model_type, device=device,
                         precision=precision)
+    return _load_and_place(model, model_path, device)
+
+
+def _load_and_place(model, model_path, device):
     para_dict = torch.load(model_path, map_location=torch.device('cpu'))
     try:
         model_dict = model.state_dict()

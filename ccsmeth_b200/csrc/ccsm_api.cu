@@ -109,7 +109,19 @@ int ccsm_create(ccsm_model** out, const ccsm_config* cfg) {
       m->gates = 4;
       m->cfg.precision = CCSM_PREC_FP32;  // the tensor-core kernels implement the GRU cell only
     }
-    if (cfg->feat_flags & CCSM_MODEL_2S2) {
+    if (cfg->feat_flags & CCSM_MODEL_TRANSENC) {
+      const int nhead = (cfg->feat_flags >> 8) & 255;
+      if ((cfg->feat_flags & (CCSM_FEAT_STDS | CCSM_FEAT_SN | CCSM_FEAT_MAP)) || nhead < 1 || cfg->hidden % nhead != 0 ||
+          cfg->hidden % 32 != 0) {
+        set_error("ccsm_create: ModelTransEnc needs d_model %% 32 == 0, d_model %% nhead == 0 and only the kinetics / npass features");
+        delete m;
+        return CCSM_EUNSUPPORTED;
+      }
+      m->is_trans = true;
+      m->nhead = nhead;
+      m->in_feat = cfg->n_embed + 2 * 8 + ((cfg->feat_flags & CCSM_FEAT_NPASS) ? 4 : 0);
+      m->cfg.precision = CCSM_PREC_FP32;
+    } else if (cfg->feat_flags & CCSM_MODEL_2S2) {
       if (cfg->feat_flags & (CCSM_FEAT_STDS | CCSM_FEAT_SN | CCSM_FEAT_MAP)) {
         set_error("ccsm_create: ModelAttRNN2 with --is_stds / --is_sn / --is_map is not implemented");
         delete m;
@@ -137,6 +149,7 @@ void ccsm_destroy(ccsm_model* m) {
   tc_release(m);
   ex_release(m);
   pu_release(m);
+  trans_release(m);
   m->aggr_packed.release();
   m->aggr_scratch.release();
   for (auto& l : m->fp32.layers) {
@@ -160,6 +173,39 @@ void ccsm_destroy(ccsm_model* m) {
 // expected shape of every state_dict key (reference models.py:33,52-64,644-654)
 static bool expected_shape(const ccsm_model* m, const std::string& key, std::vector<int64_t>& shp) {
   const int64_t H = m->cfg.hidden, C = m->cfg.num_classes;
+  if (m->is_trans) {
+    const int64_t d = H, L = m->cfg.seq_len, ff = m->dim_ff;
+    if (key == "seq_embed.weight") { shp = {m->cfg.n_vocab, m->cfg.n_embed}; return true; }
+    if (key == "ipd_embed.weight" || key == "pw_embed.weight") { shp = {953, 8}; return true; }
+    if (key == "npass_embed.weight" && (m->cfg.feat_flags & CCSM_FEAT_NPASS)) { shp = {31, 4}; return true; }
+    if (key == "pos_encoder.pos_embed.weight") { shp = {L, d}; return true; }
+    if (key == "classifier.0.weight") { shp = {2 * d, 2 * d}; return true; }
+    if (key == "classifier.0.bias") { shp = {2 * d}; return true; }
+    if (key == "classifier.3.weight") { shp = {C, 2 * d}; return true; }
+    if (key == "classifier.3.bias") { shp = {C}; return true; }
+    static const char* convs[3] = {"trans_input.conv_embed.0", "trans_input.conv_embed.4", "trans_input.conv_embed_plus.0.conv_embed.0"};
+    static const char* bns[3] = {"trans_input.conv_embed.1", "trans_input.conv_embed.5", "trans_input.conv_embed_plus.0.conv_embed.1"};
+    const int64_t cin[3] = {m->in_feat, d / 2, d}, cout[3] = {d / 2, d, d};
+    for (int i = 0; i < 3; ++i) {
+      if (key == std::string(convs[i]) + ".weight") { shp = {cout[i], cin[i], 3}; return true; }
+      for (const char* t : {".weight", ".bias", ".running_mean", ".running_var"})
+        if (key == std::string(bns[i]) + t) { shp = {cout[i]}; return true; }
+    }
+    for (int l = 0; l < m->cfg.num_layers; ++l) {
+      const std::string pre = "transformer_encoder.layers." + std::to_string(l) + ".";
+      if (key == pre + "self_attn.in_proj_weight") { shp = {3 * d, d}; return true; }
+      if (key == pre + "self_attn.in_proj_bias") { shp = {3 * d}; return true; }
+      if (key == pre + "self_attn.out_proj.weight") { shp = {d, d}; return true; }
+      if (key == pre + "self_attn.out_proj.bias") { shp = {d}; return true; }
+      if (key == pre + "linear1.weight") { shp = {ff, d}; return true; }   // ff = 0 until known: see ccsm_set_weight
+      if (key == pre + "linear1.bias") { shp = {ff}; return true; }
+      if (key == pre + "linear2.weight") { shp = {d, ff}; return true; }
+      if (key == pre + "linear2.bias") { shp = {d}; return true; }
+      for (const char* t : {"norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"})
+        if (key == pre + t) { shp = {d}; return true; }
+    }
+    return false;
+  }
   if (m->is_2s2) {
     if (key == "seq_embed.weight") { shp = {m->cfg.n_vocab, m->cfg.n_embed}; return true; }
     if (key == "ipd_embed.weight" || key == "pw_embed.weight") { shp = {953, 8}; return true; }  // MAX_KINETICS + 1
@@ -194,6 +240,18 @@ int ccsm_set_weight(ccsm_model* m, const char* key_c, const float* host, const i
   }
   std::string key(key_c);
   if (key.rfind("module.", 0) == 0) key = key.substr(7);  // DDP prefix (reference call_modifications.py:350-358)
+  if (m->is_trans && m->dim_ff == 0) {
+    // dim_feedforward is not part of ccsm_config: take it from the first feed-forward tensor that arrives
+    const size_t n = key.size();
+    if (n > 14 && key.compare(n - 14, 14, "linear1.weight") == 0 && ndim == 2) m->dim_ff = (int)shape[0];
+    else if (n > 12 && key.compare(n - 12, 12, "linear1.bias") == 0 && ndim == 1) m->dim_ff = (int)shape[0];
+    else if (n > 14 && key.compare(n - 14, 14, "linear2.weight") == 0 && ndim == 2) m->dim_ff = (int)shape[1];
+    if (m->dim_ff % 16 != 0) {
+      set_error("ccsm_set_weight: dim_feedforward %d must be a multiple of 16", m->dim_ff);
+      m->dim_ff = 0;
+      return CCSM_EKEY;
+    }
+  }
   std::vector<int64_t> want;
   if (!expected_shape(m, key, want)) {
     set_error("ccsm_set_weight: unexpected key '%s' for this model", key.c_str());
@@ -218,6 +276,26 @@ int ccsm_set_weight(ccsm_model* m, const char* key_c, const float* host, const i
 }
 
 static int check_complete(ccsm_model* m) {
+  if (m->is_trans) {
+    std::vector<std::string> tk = {"seq_embed.weight", "ipd_embed.weight", "pw_embed.weight", "pos_encoder.pos_embed.weight",
+                                   "classifier.0.weight", "classifier.0.bias", "classifier.3.weight", "classifier.3.bias",
+                                   "trans_input.conv_embed.0.weight", "trans_input.conv_embed.4.weight",
+                                   "trans_input.conv_embed_plus.0.conv_embed.0.weight"};
+    if (m->cfg.feat_flags & CCSM_FEAT_NPASS) tk.push_back("npass_embed.weight");
+    for (const char* bn : {"trans_input.conv_embed.1", "trans_input.conv_embed.5", "trans_input.conv_embed_plus.0.conv_embed.1"})
+      for (const char* t : {".weight", ".bias", ".running_mean", ".running_var"}) tk.push_back(std::string(bn) + t);
+    for (int l = 0; l < m->cfg.num_layers; ++l)
+      for (const char* t : {"self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+                            "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias",
+                            "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"})
+        tk.push_back("transformer_encoder.layers." + std::to_string(l) + "." + t);
+    for (auto& k : tk)
+      if (!m->w.count(k)) {
+        set_error("ccsm_finalize: missing key '%s'", k.c_str());
+        return CCSM_EKEY;
+      }
+    return CCSM_OK;
+  }
   std::vector<std::string> keys = {"_att3.Wa.weight", "_att3.Ua.weight", "_att3.va.weight"};
   if (m->is_2s2) {
     for (const char* k : {"seq_embed.weight", "ipd_embed.weight", "pw_embed.weight", "classifier.0.weight", "classifier.0.bias",
@@ -249,6 +327,11 @@ int ccsm_finalize(ccsm_model* m) {
   }
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
   CCSM_TRY(check_complete(m));
+  if (m->is_trans) {
+    CCSM_TRY(trans_upload_weights(m));
+    m->finalized = true;
+    return CCSM_OK;
+  }
   CCSM_TRY(fp32_upload_weights(m));  // always kept: cross-check path + attention/head fallback
   if (is_tc(m->cfg.precision)) CCSM_TRY(tc_upload_weights(m));
   if (m->cfg.kind == CCSM_KIND_AGGR) CCSM_TRY(aggr_fused_upload(m));
@@ -272,7 +355,7 @@ int ccsm_set_precision(ccsm_model* m, int32_t precision) {
     set_error("ccsm_set_precision: bad argument");
     return CCSM_EINVAL;
   }
-  if (m->cfg.kind == CCSM_KIND_AGGR || m->gates == 4 || m->is_2s2) precision = CCSM_PREC_FP32;
+  if (m->cfg.kind == CCSM_KIND_AGGR || m->gates == 4 || m->is_2s2 || m->is_trans) precision = CCSM_PREC_FP32;
   if (precision == m->cfg.precision) return CCSM_OK;
   m->cfg.precision = precision;
   if (m->finalized && is_tc(precision)) {
@@ -312,6 +395,7 @@ int ccsm_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
   CCSM_TRY(check_strand(m, rev, "reverse"));
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (m->is_trans) return trans_forward(m, n, fwd, rev, logits, probs, st);  // no recurrent state: h0 is ignored
   const int rc = is_tc(m->cfg.precision) ? tc_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st)
                                          : fp32_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
   m->h0_calls += 1;

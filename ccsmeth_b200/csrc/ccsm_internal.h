@@ -68,6 +68,17 @@ struct Fp32Weights {
   bool ready = false;
 };
 
+// ModelTransEnc weights (fp32_path.cu, transformer section)
+struct TrConv { DevBuf w, scale, shift; int cin = 0, cout = 0, kpad = 0; };
+struct TrLayer { DevBuf in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b; };
+struct TrWeights {
+  TrConv conv[3];
+  DevBuf pos;
+  std::vector<TrLayer> layers;
+  DevBuf x0, col, a, b, qkv, ffh, ctx, hid;  // workspace
+  int64_t tokens_cap = 0;
+};
+
 struct Fp32Workspace {
   int64_t rows_cap = 0;
   DevBuf x0, gi, gh, h, c, outA, outB, qa;
@@ -111,6 +122,9 @@ struct ccsm_model {
   int in_feat = 0;    // GRU layer-0 input width (att2s: n_embed + feas_ccs; aggr: bins + 1)
   int gates = 3;      // 3 GRU (r, z, n) / 4 LSTM (i, f, g, o): gate row blocks of the rnn weights
   bool is_2s2 = false;  // ModelAttRNN2: integer kinetics embeddings + two-layer classifier (CCSM_MODEL_2S2)
+  bool is_trans = false;  // ModelTransEnc (CCSM_MODEL_TRANSENC)
+  int nhead = 0, dim_ff = 0;
+  ccsm::TrWeights tr;
   std::map<std::string, ccsm::HostTensor> w;
   bool finalized = false;
   ccsm::Fp32Weights fp32;
@@ -141,6 +155,10 @@ int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
                        const float* c0_f = nullptr, const float* c0_r = nullptr);
 int fp32_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
                       float* out, cudaStream_t st);
+int trans_upload_weights(ccsm_model* m);
+int trans_forward(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, float* logits, float* probs,
+                  cudaStream_t st);
+void trans_release(ccsm_model* m);
 
 // ---- tensor-core path (tc_path.cu)
 int tc_upload_weights(ccsm_model* m);

@@ -609,4 +609,268 @@ int fp32_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const floa
   return CCSM_OK;
 }
 
+
+// ================================================================================================
+// ModelTransEnc ("transencoder2s", reference models.py:451-620) on fp32 FFMA kernels.  No checkpoint ships for this
+// model type; it exists for `--model_type` completeness and reuses sgemm_nt for every
+// linear map.  Token order: row R = site * 2 + strand, token = R * L + t.
+//   embeddings (pack_x_att2s2_kernel) -> 3 x [Conv1d(k=3, p=1) as im2col + GEMM -> BatchNorm(eval) -> ReLU ->
+//   MaxPool1d(k=3, s=1, p=1)] -> + pos_embed -> num_layers x [QKV GEMM -> per-(row, head) softmax attention ->
+//   out-proj GEMM -> add + LayerNorm -> FFN GEMM + ReLU + GEMM -> add + LayerNorm] -> mean over t -> classifier.
+// ================================================================================================
+__global__ void tr_im2col_kernel(int64_t tokens, int L, int cin, int ldin, int kpad, const float* __restrict__ in,
+                                 float* __restrict__ col) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (token, k)
+  if (idx >= tokens * kpad) return;
+  const int k = (int)(idx % kpad);
+  const int64_t tok = idx / kpad;
+  float v = 0.f;
+  if (k < 3 * cin) {
+    const int dk = k / cin, ci = k - dk * cin;
+    const int t = (int)(tok % L) + dk - 1;
+    if (t >= 0 && t < L) v = in[(tok + dk - 1) * ldin + ci];
+  }
+  col[idx] = v;
+}
+
+// out[R, t, c] = max over the valid neighbours t-1, t, t+1 of relu(v * scale[c] + shift[c])  (+ pos[t][c])
+__global__ void tr_bn_relu_pool_kernel(int64_t tokens, int L, int C, const float* __restrict__ v,
+                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                       const float* __restrict__ pos, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (token, c)
+  if (idx >= tokens * C) return;
+  const int c = (int)(idx % C);
+  const int64_t tok = idx / C;
+  const int t = (int)(tok % L);
+  const float sc = scale[c], sh = shift[c];
+  float m = fmaxf(fmaf(v[idx], sc, sh), 0.f);
+  if (t > 0) m = fmaxf(m, fmaxf(fmaf(v[idx - C], sc, sh), 0.f));
+  if (t + 1 < L) m = fmaxf(m, fmaxf(fmaf(v[idx + C], sc, sh), 0.f));
+  out[idx] = pos ? m + pos[t * C + c] : m;
+}
+
+// softmax(q k^T / sqrt(dh)) v for one (row, head) per warp; lane = query position (L <= 32)
+__global__ void tr_attention_kernel(int64_t rows, int L, int d, int nhead, const float* __restrict__ qkv,
+                                    float* __restrict__ out) {
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= rows * nhead) return;
+  const int head = (int)(w % nhead);
+  const int64_t R = w / nhead;
+  const int dh = d / nhead;
+  const float* base = qkv + R * L * (int64_t)(3 * d) + head * dh;
+  if (lane >= L) return;
+  const float* q = base + (int64_t)lane * 3 * d;
+  const float inv = rsqrtf((float)dh);
+  float sc[32];
+  float mx = -INFINITY;
+  for (int j = 0; j < L; ++j) {
+    const float* k = base + (int64_t)j * 3 * d + d;
+    float a = 0.f;
+    for (int c = 0; c < dh; ++c) a = fmaf(q[c], k[c], a);
+    sc[j] = a * inv;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < L; ++j) {
+    sc[j] = expf(sc[j] - mx);
+    sum += sc[j];
+  }
+  float* o = out + (R * L + lane) * (int64_t)d + head * dh;
+  for (int c = 0; c < dh; ++c) {
+    float a = 0.f;
+    for (int j = 0; j < L; ++j) a = fmaf(sc[j], base[(int64_t)j * 3 * d + 2 * d + c], a);
+    o[c] = a / sum;
+  }
+}
+
+// x = LayerNorm(x + y) * w + b, one warp per token (biased variance, eps 1e-5)
+__global__ void tr_add_ln_kernel(int64_t tokens, int d, float* __restrict__ x, const float* __restrict__ y,
+                                 const float* __restrict__ w, const float* __restrict__ b) {
+  const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= tokens) return;
+  float* xp = x + tok * d;
+  const float* yp = y + tok * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s += xp[c] + yp[c];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s / d;
+  float q = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float t = xp[c] + yp[c] - mu;
+    q += t * t;
+  }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.f / sqrtf(q / d + 1e-5f);
+  for (int c = lane; c < d; c += 32) xp[c] = (xp[c] + yp[c] - mu) * rstd * w[c] + b[c];
+}
+
+__global__ void tr_relu_kernel(int64_t n, float* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = fmaxf(x[i], 0.f);
+}
+
+// ctx[site][strand * d + c] = mean_t x[(site * 2 + strand) * L + t][c]
+__global__ void tr_mean_pool_kernel(int64_t sites, int L, int d, const float* __restrict__ x, float* __restrict__ ctx) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (site, strand, c)
+  if (idx >= sites * 2 * d) return;
+  const int c = (int)(idx % d);
+  const int64_t R = idx / d;
+  float s = 0.f;
+  for (int t = 0; t < L; ++t) s += x[(R * L + t) * d + c];
+  ctx[idx] = s / L;
+}
+
+int trans_upload_weights(ccsm_model* m) {
+  const int d = m->cfg.hidden;
+  Fp32Weights& W = m->fp32;
+  TrWeights& T = m->tr;
+  if (m->dim_ff <= 0) {
+    set_error("finalize: feed-forward weights missing");
+    return CCSM_EKEY;
+  }
+  CCSM_TRY(upload(W.embed, find(m, "seq_embed.weight")->data));
+  CCSM_TRY(upload(W.ipd_embed, find(m, "ipd_embed.weight")->data));
+  CCSM_TRY(upload(W.pw_embed, find(m, "pw_embed.weight")->data));
+  if (m->cfg.feat_flags & CCSM_FEAT_NPASS) CCSM_TRY(upload(W.npass_embed, find(m, "npass_embed.weight")->data));
+  CCSM_TRY(upload(W.cls0_w, find(m, "classifier.0.weight")->data));
+  CCSM_TRY(upload(W.cls0_b, find(m, "classifier.0.bias")->data));
+  CCSM_TRY(upload(W.fc_w, find(m, "classifier.3.weight")->data));
+  CCSM_TRY(upload(W.fc_b, find(m, "classifier.3.bias")->data));
+  CCSM_TRY(upload(T.pos, find(m, "pos_encoder.pos_embed.weight")->data));
+  static const char* convs[3] = {"trans_input.conv_embed.0", "trans_input.conv_embed.4", "trans_input.conv_embed_plus.0.conv_embed.0"};
+  static const char* bns[3] = {"trans_input.conv_embed.1", "trans_input.conv_embed.5", "trans_input.conv_embed_plus.0.conv_embed.1"};
+  const int cin[3] = {m->in_feat, d / 2, d}, cout[3] = {d / 2, d, d};
+  for (int i = 0; i < 3; ++i) {
+    TrConv& c = T.conv[i];
+    c.cin = cin[i];
+    c.cout = cout[i];
+    c.kpad = round_up(3 * cin[i], 16);
+    const HostTensor* w = find(m, std::string(convs[i]) + ".weight");
+    std::vector<float> w2((size_t)cout[i] * c.kpad, 0.f), sc((size_t)cout[i]), sh((size_t)cout[i]);
+    for (int co = 0; co < cout[i]; ++co)
+      for (int ci = 0; ci < cin[i]; ++ci)
+        for (int dk = 0; dk < 3; ++dk) w2[(size_t)co * c.kpad + dk * cin[i] + ci] = w->data[((size_t)co * cin[i] + ci) * 3 + dk];
+    const HostTensor *g = find(m, std::string(bns[i]) + ".weight"), *b = find(m, std::string(bns[i]) + ".bias"),
+                     *mu = find(m, std::string(bns[i]) + ".running_mean"), *var = find(m, std::string(bns[i]) + ".running_var");
+    for (int co = 0; co < cout[i]; ++co) {  // eval-mode BatchNorm1d as one affine map (eps 1e-5)
+      const double s = (double)g->data[co] / sqrt((double)var->data[co] + 1e-5);
+      sc[co] = (float)s;
+      sh[co] = (float)((double)b->data[co] - (double)mu->data[co] * s);
+    }
+    CCSM_TRY(upload(c.w, w2));
+    CCSM_TRY(upload(c.scale, sc));
+    CCSM_TRY(upload(c.shift, sh));
+  }
+  T.layers.resize(m->cfg.num_layers);
+  for (int l = 0; l < m->cfg.num_layers; ++l) {
+    const std::string pre = "transformer_encoder.layers." + std::to_string(l) + ".";
+    TrLayer& Lw = T.layers[l];
+    CCSM_TRY(upload(Lw.in_w, find(m, pre + "self_attn.in_proj_weight")->data));
+    CCSM_TRY(upload(Lw.in_b, find(m, pre + "self_attn.in_proj_bias")->data));
+    CCSM_TRY(upload(Lw.out_w, find(m, pre + "self_attn.out_proj.weight")->data));
+    CCSM_TRY(upload(Lw.out_b, find(m, pre + "self_attn.out_proj.bias")->data));
+    CCSM_TRY(upload(Lw.l1_w, find(m, pre + "linear1.weight")->data));
+    CCSM_TRY(upload(Lw.l1_b, find(m, pre + "linear1.bias")->data));
+    CCSM_TRY(upload(Lw.l2_w, find(m, pre + "linear2.weight")->data));
+    CCSM_TRY(upload(Lw.l2_b, find(m, pre + "linear2.bias")->data));
+    CCSM_TRY(upload(Lw.n1_w, find(m, pre + "norm1.weight")->data));
+    CCSM_TRY(upload(Lw.n1_b, find(m, pre + "norm1.bias")->data));
+    CCSM_TRY(upload(Lw.n2_w, find(m, pre + "norm2.weight")->data));
+    CCSM_TRY(upload(Lw.n2_b, find(m, pre + "norm2.bias")->data));
+  }
+  return CCSM_OK;
+}
+
+void trans_release(ccsm_model* m) {
+  TrWeights& T = m->tr;
+  for (auto& c : T.conv) { c.w.release(); c.scale.release(); c.shift.release(); }
+  T.pos.release();
+  for (auto& l : T.layers)
+    for (DevBuf* b : {&l.in_w, &l.in_b, &l.out_w, &l.out_b, &l.l1_w, &l.l1_b, &l.l2_w, &l.l2_b, &l.n1_w, &l.n1_b, &l.n2_w, &l.n2_b})
+      b->release();
+  for (DevBuf* b : {&T.x0, &T.col, &T.a, &T.b, &T.qkv, &T.ffh, &T.ctx, &T.hid}) b->release();
+}
+
+int trans_forward(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, float* logits, float* probs,
+                  cudaStream_t st) {
+  const int L = m->cfg.seq_len, d = m->cfg.hidden, ff = m->dim_ff, C = m->cfg.num_classes, nhead = m->nhead;
+  Fp32Weights& W = m->fp32;
+  TrWeights& T = m->tr;
+  const int K0 = round_up(m->in_feat, 16);
+  const int64_t chunk = n < 4096 ? n : 4096;
+  const int64_t tok_cap = chunk * 2 * L;
+  if (tok_cap > T.tokens_cap) {
+    int colw = 0;
+    for (auto& c : T.conv) colw = c.kpad > colw ? c.kpad : colw;
+    CCSM_TRY(T.x0.reserve(tok_cap * K0 * 4));
+    CCSM_TRY(T.col.reserve(tok_cap * colw * 4));
+    CCSM_TRY(T.a.reserve(tok_cap * d * 4));
+    CCSM_TRY(T.b.reserve(tok_cap * d * 4));
+    CCSM_TRY(T.qkv.reserve(tok_cap * 3 * d * 4));
+    CCSM_TRY(T.ffh.reserve(tok_cap * (ff > d ? ff : d) * 4));
+    CCSM_TRY(T.ctx.reserve(chunk * 2 * d * 4));
+    CCSM_TRY(T.hid.reserve(chunk * 2 * d * 4));
+    T.tokens_cap = tok_cap;
+  }
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const int64_t sites = (n - s0) < chunk ? (n - s0) : chunk;
+    const int64_t rows = sites * 2, tokens = rows * L;
+    pack_x_att2s2_kernel<<<nblk(tokens, 256), 256, 0, st>>>(
+        sites, L, m->cfg.n_embed, m->cfg.n_vocab, m->cfg.feat_flags, K0, offset_strand(fwd, s0, L), offset_strand(rev, s0, L),
+        W.embed.as<float>(), W.ipd_embed.as<float>(), W.pw_embed.as<float>(), W.npass_embed.as<float>(), T.x0.as<float>());
+    count_launch();
+    // SrcEmbed: three conv stages; activations ping-pong between a and b
+    const float* in = T.x0.as<float>();
+    int ldin = K0;
+    float* bufs[2] = {T.a.as<float>(), T.b.as<float>()};
+    float* x = nullptr;
+    for (int i = 0; i < 3; ++i) {
+      TrConv& c = T.conv[i];
+      tr_im2col_kernel<<<nblk(tokens * c.kpad, 256), 256, 0, st>>>(tokens, L, c.cin, ldin, c.kpad, in, T.col.as<float>());
+      count_launch();
+      float* conv_out = T.qkv.as<float>();  // scratch: (tokens, cout)
+      CCSM_TRY(sgemm_nt((int)tokens, c.cout, c.kpad, T.col.as<float>(), c.kpad, 0, c.w.as<float>(), c.kpad, 0, nullptr, 0,
+                        conv_out, c.cout, 0, 1, st));
+      x = bufs[i & 1];
+      tr_bn_relu_pool_kernel<<<nblk(tokens * c.cout, 256), 256, 0, st>>>(tokens, L, c.cout, conv_out, c.scale.as<float>(),
+                                                                          c.shift.as<float>(),
+                                                                          i == 2 ? T.pos.as<float>() : nullptr, x);
+      count_launch();
+      in = x;
+      ldin = c.cout;
+    }
+    float* y = x == bufs[0] ? bufs[1] : bufs[0];
+    for (auto& Lw : T.layers) {
+      CCSM_TRY(sgemm_nt((int)tokens, 3 * d, d, x, d, 0, Lw.in_w.as<float>(), d, 0, Lw.in_b.as<float>(), 0, T.qkv.as<float>(),
+                        3 * d, 0, 1, st));
+      tr_attention_kernel<<<nblk(rows * nhead, 4), 128, 0, st>>>(rows, L, d, nhead, T.qkv.as<float>(), T.ffh.as<float>());
+      count_launch();
+      CCSM_TRY(sgemm_nt((int)tokens, d, d, T.ffh.as<float>(), d, 0, Lw.out_w.as<float>(), d, 0, Lw.out_b.as<float>(), 0, y, d, 0,
+                        1, st));
+      tr_add_ln_kernel<<<nblk(tokens, 8), 256, 0, st>>>(tokens, d, x, y, Lw.n1_w.as<float>(), Lw.n1_b.as<float>());
+      count_launch();
+      CCSM_TRY(sgemm_nt((int)tokens, ff, d, x, d, 0, Lw.l1_w.as<float>(), d, 0, Lw.l1_b.as<float>(), 0, T.ffh.as<float>(), ff, 0,
+                        1, st));
+      tr_relu_kernel<<<nblk(tokens * ff, 256), 256, 0, st>>>(tokens * ff, T.ffh.as<float>());
+      count_launch();
+      CCSM_TRY(sgemm_nt((int)tokens, d, ff, T.ffh.as<float>(), ff, 0, Lw.l2_w.as<float>(), ff, 0, Lw.l2_b.as<float>(), 0, y, d, 0,
+                        1, st));
+      tr_add_ln_kernel<<<nblk(tokens, 8), 256, 0, st>>>(tokens, d, x, y, Lw.n2_w.as<float>(), Lw.n2_b.as<float>());
+      count_launch();
+    }
+    tr_mean_pool_kernel<<<nblk(sites * 2 * d, 256), 256, 0, st>>>(sites, L, d, x, T.ctx.as<float>());
+    count_launch();
+    const int D = 2 * d;
+    CCSM_TRY(sgemm_nt((int)sites, D, D, T.ctx.as<float>(), D, 0, W.cls0_w.as<float>(), D, 0, W.cls0_b.as<float>(), 0,
+                      T.hid.as<float>(), D, 0, 1, st));
+    cls_out_kernel<4><<<nblk(sites, 4), 128, 0, st>>>(sites, D, C, T.hid.as<float>(), W.fc_w.as<float>(), W.fc_b.as<float>(),
+                                                      logits ? logits + s0 * C : nullptr, probs ? probs + s0 * C : nullptr);
+    count_launch();
+    CCSM_CUDA(cudaGetLastError());
+  }
+  return CCSM_OK;
+}
+
 }  // namespace ccsm

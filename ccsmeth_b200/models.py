@@ -127,6 +127,8 @@ class _NativeModule(nn.Module):
         if self._dirty:
             _lib.check(lib.ccsm_set_precision(self._handle, _lib.PREC[self._precision]))
             for k, v in self.state_dict().items():
+                if k.endswith("num_batches_tracked"):
+                    continue  # BatchNorm bookkeeping, not a weight
                 a = np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy())
                 shp = (ctypes.c_int64 * a.ndim)(*a.shape)
                 _lib.check(lib.ccsm_set_weight(self._handle, k.encode(), a.ctypes.data_as(ctypes.c_void_p), shp, a.ndim))
@@ -452,6 +454,88 @@ class ModelAttRNN2(ModelAttRNN):
 
     def set_precision(self, precision):  # fp32 kernels only
         return self
+
+
+class _EmbedBlockPlus(nn.Module):  # parameter container, reference models.py:153-170
+    def __init__(self, d_model):
+        super().__init__()
+        self.conv_embed = nn.Sequential(nn.Conv1d(d_model, d_model, 3, 1, 1, bias=False), nn.BatchNorm1d(d_model),
+                                        nn.ReLU(inplace=True), nn.MaxPool1d(3, 1, 1))
+
+
+class _SrcEmbed(nn.Module):  # parameter container, reference models.py:173-218
+    def __init__(self, input_dim, d_model, block_plus=1):
+        super().__init__()
+        self.conv_embed = nn.Sequential(nn.Conv1d(input_dim, d_model // 2, 3, 1, 1, bias=False), nn.BatchNorm1d(d_model // 2),
+                                        nn.ReLU(inplace=True), nn.MaxPool1d(3, 1, 1),
+                                        nn.Conv1d(d_model // 2, d_model, 3, 1, 1, bias=False), nn.BatchNorm1d(d_model),
+                                        nn.ReLU(inplace=True), nn.MaxPool1d(3, 1, 1))
+        self.conv_embed_plus = nn.Sequential(*[_EmbedBlockPlus(d_model) for _ in range(block_plus)])
+
+
+class _PositionalEmbedding(nn.Module):  # parameter container, reference models.py:437-448
+    def __init__(self, seq_len, d_model):
+        super().__init__()
+        self.pos_embed = nn.Embedding(seq_len, d_model)
+
+
+class ModelTransEnc(_NativeModule):
+    """Drop-in for the reference ``ModelTransEnc`` (``model_type="transencoder2s"``, models.py:451-620): integer
+    embeddings, SrcEmbed conv stack, learned positions, post-norm transformer encoder, mean pooling, classifier.
+    No checkpoint ships for it; fp32 kernels; same 16-tensor ``forward`` (there is no recurrent state, so no h0)."""
+
+    def __init__(self, seq_len=21, num_layers=6, num_classes=2, dropout_rate=0.5, d_model=256, nhead=4, dim_ff=512,
+                 is_npass=True, is_sn=False, is_map=False, is_stds=False, model_type="transencoder2s", device=0):
+        super().__init__()
+        if model_type != "transencoder2s":
+            raise ValueError("--model_type not set right!")
+        if is_sn or is_map or is_stds:
+            raise ValueError("ccsmeth_b200 implements ModelTransEnc with the kinetics and pass-count features only")
+        self.model_type, self.device = model_type, device
+        self.seq_len, self.num_layers, self.num_classes, self.d_model = seq_len, num_layers, num_classes, d_model
+        self.nhead, self.dim_ff = nhead, dim_ff
+        self.hidden_size = d_model
+        self.n_embed = NEMBED_BASE
+        self.is_stds, self.is_npass, self.is_sn, self.is_map = is_stds, is_npass, is_sn, is_map
+        self.nembed_all = NEMBED_BASE + 2 * 8 + (4 if is_npass else 0)
+        self.seq_embed = nn.Embedding(N_VOCAB, NEMBED_BASE)
+        self.ipd_embed = nn.Embedding(952 + 1, 8)
+        self.pw_embed = nn.Embedding(952 + 1, 8)
+        if is_npass:
+            self.npass_embed = nn.Embedding(30 + 1, 4)
+        self.trans_input = _SrcEmbed(self.nembed_all, d_model, block_plus=1)
+        self.pos_encoder = _PositionalEmbedding(seq_len, d_model)
+        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=nhead, dim_feedforward=dim_ff, dropout=dropout_rate,
+                                           batch_first=True)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers)
+        self.classifier = nn.Sequential(nn.Linear(d_model * 2, d_model * 2), nn.ReLU(), nn.Dropout(p=dropout_rate),
+                                        nn.Linear(d_model * 2, num_classes))
+        self.requires_grad_(False)
+        self._native_init("fp32")
+
+    def _config(self, dev):
+        flags = _lib.MODEL_TRANSENC | (_lib.FEAT_NPASS if self.is_npass else 0) | (self.nhead << 8)
+        return _lib.Config(_lib.KIND_ATT2S, self.seq_len, self.num_layers, self.d_model, self.num_classes,
+                           N_VOCAB, self.n_embed, flags, _lib.PREC["fp32"], dev)
+
+    def set_precision(self, precision):  # fp32 kernels only
+        return self
+
+    def forward(self, kmer, kpass, ipd_means, ipd_stds, pw_means, pw_stds, sns, maps,
+                kmer2, kpass2, ipd_means2, ipd_stds2, pw_means2, pw_stds2, sns2, maps2, has_mask=False):
+        handle, dev = self._ensure_handle()
+        device = torch.device("cuda", dev)
+        n = int(torch.as_tensor(kmer).reshape(-1, self.seq_len).shape[0])
+        keep = []
+        fwd = ModelAttRNN._strand(self, device, n, kmer, kpass, ipd_means, ipd_stds, pw_means, pw_stds, sns, maps, keep)
+        rev = ModelAttRNN._strand(self, device, n, kmer2, kpass2, ipd_means2, ipd_stds2, pw_means2, pw_stds2, sns2, maps2, keep)
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        probs = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        if n > 0:
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(_lib.load().ccsm_forward_att2s(handle, n, ctypes.byref(fwd), ctypes.byref(rev), None, None,
+                                                      logits.data_ptr(), probs.data_ptr(), ctypes.c_void_p(stream)))
+        return logits, probs
 
 
 class AggrAttRNN(_NativeModule):

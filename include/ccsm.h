@@ -72,6 +72,12 @@ extern "C" {
  * ipd_embed.weight, pw_embed.weight, npass_embed.weight, rnn.*, _att3.*, classifier.0.*, classifier.3.*.
  * CCSM_PREC_FP32 only; --is_stds / --is_sn / --is_map are not implemented for it. */
 #define CCSM_MODEL_2S2  32
+/* ModelTransEnc (model_type "transencoder2s", models.py:451-620): the ModelAttRNN2 embeddings, SrcEmbed (three
+ * Conv1d(k=3) + BatchNorm1d + ReLU + MaxPool1d(k=3) stages), a learned positional embedding, `num_layers` post-norm
+ * nn.TransformerEncoderLayer's (hidden = d_model, heads = (feat_flags >> 8) & 255, dim_feedforward taken from the
+ * linear1 weight), mean over positions, the two-layer classifier.  state_dict keys as in the reference (BatchNorm
+ * running_mean / running_var included; num_batches_tracked is not a float tensor and is not passed).  CCSM_PREC_FP32. */
+#define CCSM_MODEL_TRANSENC 64
 
 typedef struct ccsm_model ccsm_model;
 

@@ -368,6 +368,42 @@ def gen_2s2():
     np.savez_compressed(os.path.join(OUT, "att2s2.npz"), **save)
 
 
+def gen_transenc():
+    """Section 8f-4: the reference's ModelTransEnc ("transencoder2s") on seeded random weights (d_model 64, 4 heads,
+    dim_ff 128, 2 layers; BatchNorm running statistics randomised so that the eval-mode affine is exercised)."""
+    ref = refimport.import_reference()
+    import ccsmeth.models as rmodels
+    rng = np.random.default_rng(21)
+    n, L = 64, 21
+    feats = {}
+    for sfx in ("", "2"):
+        feats["kmer" + sfx] = torch.from_numpy(rng.integers(0, 5, (n, L)).astype(np.float32))
+        feats["ipd" + sfx] = torch.from_numpy(rng.integers(0, 953, (n, L)).astype(np.float32))
+        feats["pw" + sfx] = torch.from_numpy(rng.integers(0, 953, (n, L)).astype(np.float32))
+        feats["kpass" + sfx] = torch.from_numpy(np.repeat(rng.integers(0, 45, (n, 1)), L, axis=1).astype(np.float32))
+    z = torch.zeros(n)
+    args = (feats["kmer"], feats["kpass"], feats["ipd"], z, feats["pw"], z, z, z,
+            feats["kmer2"], feats["kpass2"], feats["ipd2"], z, feats["pw2"], z, z, z)
+    torch.manual_seed(1357)
+    m = rmodels.ModelTransEnc(21, 2, 2, 0, 64, 4, 128, is_npass=True, device="cpu")
+    with torch.no_grad():
+        for k, v in m.state_dict().items():
+            if k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape) * 0.05)
+            elif k.endswith("running_var"):
+                v.copy_(torch.rand(v.shape) * 0.5 + 0.05)
+            elif ".conv_embed." in k and k.endswith(("1.weight", "5.weight", "1.bias", "5.bias")) and v.dim() == 1:
+                v.copy_(torch.rand(v.shape) + 0.5 if k.endswith("weight") else torch.randn(v.shape) * 0.1)
+    m.eval()
+    with torch.no_grad():
+        logits, probs = m(*args)
+    save = {k: v.numpy() for k, v in feats.items()}
+    save.update({"sd." + k: v.detach().numpy() for k, v in m.state_dict().items() if "num_batches_tracked" not in k})
+    save["logits"], save["probs"] = logits.numpy(), probs.numpy()
+    np.savez_compressed(os.path.join(OUT, "transenc.npz"), **save)
+    print("transenc: mean p1 %.4f, logits spread %.4f" % (probs[:, 1].mean().item(), logits.std().item()))
+
+
 class DuckBam:
     """What the reference's region worker needs from pysam.AlignmentFile: fetch(contig, start, stop) over records that
     overlap the interval, in file order (records are ccsmeth_b200.bamio.BamRecord)."""
@@ -451,6 +487,9 @@ def gen_freqb():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "transenc":
+        gen_transenc()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "2s2":
         gen_2s2()
         sys.exit(0)
@@ -472,6 +511,7 @@ if __name__ == "__main__":
     gen_pileup()
     gen_lstm()
     gen_2s2()
+    gen_transenc()
     gen_freqb()
     gen_demo()
     for f in sorted(os.listdir(OUT)):

@@ -68,7 +68,7 @@ def test_state_dict_contract(ckpt_att2s, ckpt_aggr):
     a.load_state_dict({k: torch.from_numpy(v) for k, v in ckpt_aggr.items()})  # "module." prefix stripped
     assert a.get_model_type() == "attbigru" and m.get_model_type() == "attbigru2s"
     with pytest.raises(ValueError):
-        ModelAttRNN(model_type="transencoder2s")
+        ModelAttRNN(model_type="transencoder2s")  # that model type has its own class, like in the reference
     lstm = ModelAttRNN(21, 2, 2, 0, 64, model_type="attbilstm2s")  # reference models.py:48-51: nn.LSTM parameter shapes
     assert lstm.state_dict()["rnn.weight_ih_l0"].shape == (256, 11) and lstm.get_precision() == "fp32"
     h, c = lstm.init_hidden(5, 2, 64)

@@ -120,3 +120,15 @@ def test_2s2_numpy_oracle_matches_reference(cell):
                                             h[0], h[1], num_layers=2, cell=cell)
     assert np.abs(probs - g[cell + ".probs"]).max() <= 1e-6
     assert np.abs(logits - g[cell + ".logits"]).max() <= 1e-5
+
+
+def test_transenc_numpy_oracle_matches_reference():
+    """ModelTransEnc (transencoder2s, reference models.py:451-620): numpy restatement (conv stack, BatchNorm in eval
+    mode, post-norm encoder layers) vs the reference's own forward on seeded random weights."""
+    from tests.conftest import load_npz
+    g = load_npz("transenc.npz")
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    logits, probs = att2s_numpy.forward_transenc(sd, *[g[k] for k in ("kmer", "kpass", "ipd", "pw", "kmer2", "kpass2", "ipd2", "pw2")],
+                                                 num_layers=2, nhead=4)
+    assert np.abs(probs - g["probs"]).max() <= 1e-6
+    assert np.abs(logits - g["logits"]).max() <= 1e-5

@@ -204,3 +204,22 @@ def test_2s2_variants_match_reference(cell, mt):
     logits, probs = m(*args16(g), h0=h)
     assert np.abs(probs.cpu().numpy() - g[cell + ".probs"]).max() <= 1e-5
     assert np.abs(logits.cpu().numpy() - g[cell + ".logits"]).max() <= 1e-4
+
+
+def test_transencoder_matches_reference():
+    """ModelTransEnc on the fp32 kernels vs the reference's own forward (fixture transenc.npz: seeded random weights,
+    d_model 64, 4 heads, dim_ff 128, 2 layers, randomised BatchNorm statistics), incl. ragged sizes."""
+    from ccsmeth_b200.models import ModelTransEnc
+    from tests.conftest import load_npz
+    g = load_npz("transenc.npz")
+    m = ModelTransEnc(21, 2, 2, 0, 64, 4, 128, is_npass=True, device=0)
+    d = m.state_dict()
+    d.update({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})
+    m.load_state_dict(d)
+    m = m.cuda(0).eval()
+    logits, probs = m(*args16(g))
+    assert np.abs(probs.cpu().numpy() - g["probs"]).max() <= 1e-5
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() <= 1e-4
+    sub = {k: v[:5] for k, v in g.items() if not k.startswith("sd.") and k not in ("logits", "probs")}
+    _, p5 = m(*args16(sub))
+    assert np.abs(p5.cpu().numpy() - g["probs"][:5]).max() <= 1e-5
