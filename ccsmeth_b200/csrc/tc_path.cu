@@ -1409,7 +1409,7 @@ static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    auto dig = [](char c) { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'e') ? 10 + (c - 'a') : -1; };
+    auto dig = [](char c) { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? 10 + (c - 'a') : -1; };
     v[0] = e ? dig(e[0]) : -1;
     v[1] = (e && e[0] && dig(e[1]) >= 0) ? dig(e[1]) : v[0];
   }
@@ -1477,6 +1477,7 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
     case 12: return launch_gru<P, F16, 1, 1, 4, 1, false, false, true>(gp, tiles, sm_count, st);  // 0 + pipelined epilogue
     case 13: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 2 + pipelined epilogue
     case 14: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true>(gp, tiles, sm_count, st);  // 6 + pipelined epilogue
+    case 15: return launch_gru<P, F16, 2, 1, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 1 + pipelined epilogue
     default:
       set_error("unknown GRU kernel variant %d", variant);
       return CCSM_EINVAL;
