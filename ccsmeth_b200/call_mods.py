@@ -179,7 +179,7 @@ def call_piece(model, piece, motifs, args, rank=0, world=1, holeids_e=None, hole
     per_hb = np.diff(np.concatenate(([0], np.nonzero(np.diff(site_hb))[0] + 1, [n])))
     n_batches = int(((per_hb + args.batch_size - 1) // args.batch_size).sum())
     h0 = None
-    if getattr(args, "h0", "reference") == "reference":
+    if getattr(args, "h0", "reference") == "reference" and getattr(model, "rnn_cell", None) == "gru":
         parts = [draw_h0_stream(int(c), args.batch_size, model.num_layers, model.hidden_size) for c in per_hb]
         h0 = (torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1)) if len(parts) > 1 \
             else parts[0]
@@ -237,9 +237,11 @@ def call_mods(args):
         raise ValueError("--input_file does not exist!")
     if not (args.input.endswith(".bam")):
         raise ValueError("ccsmeth_b200 call_mods takes BAM input (features.tsv input is out of scope)")
-    if args.model_type != "attbigru2s":
-        raise ValueError("the call_mods pipeline runs attbigru2s (the shipped model); attbilstm2s is available through "
-                         "ccsmeth_b200.models.ModelAttRNN.forward, other --model_type values are not implemented")
+    if args.model_type in ("attbilstm2s", "attbilstm2s2") and getattr(args, "h0", "reference") == "reference":
+        raise ValueError("--model_type %s: the BAM pipeline takes the LSTM initial state from the library; "
+                         "pass --h0 device or --h0 zeros" % args.model_type)
+    if args.model_type in ("attbigru2s2", "attbilstm2s2", "transencoder2s") and args.norm != "none":
+        raise ValueError("--model_type %s embeds the kinetics as integers: run it with --norm none" % args.model_type)
     if str2bool(args.is_map) or str2bool(args.is_stds):
         raise ValueError("--is_map/--is_stds features are not extracted by ccsmeth_b200 (SURVEY.md section 8f)")
     rank, world, local = parallel.init_from_env()

@@ -157,7 +157,95 @@ def _dev_f32(t, device, shape=None):
     return t.contiguous()
 
 
-class ModelAttRNN(_NativeModule):
+class _ReadsMixin:
+    """reads in, calls out: the device feature extractor + forward + MM/ML values (include/ccsm.h ccsm_reads_*),
+    shared by every two-strand model class."""
+
+    # ---- reads in, calls out: device feature extraction (include/ccsm.h ccsm_reads_*)
+    def extract_reads(self, batch, opts):
+        """Uploads a ``extract_features.ReadBatch`` and builds its site list on the device
+        (replaces extract_features_from_double_strand_read, reference extract_features.py:261-406).
+        ``opts`` = ``extract_features.extract_opts(args, motifs)``.  Returns the number of candidate sites."""
+        handle, _ = self._ensure_handle()
+        motifs = opts["motifs"]
+        o = _lib.ExtractOpts(opts["mod_loc"], opts["norm"], opts["decode"], len(motifs), len(motifs[0]),
+                             "".join(motifs).encode("ascii"))
+        blob = np.ascontiguousarray(batch.blob, dtype=np.uint8)
+        descs = np.ascontiguousarray(batch.descs)
+        n_sites = ctypes.c_int64(0)
+        _lib.check(_lib.load().ccsm_reads_extract_host(handle, ctypes.byref(o), blob.ctypes.data, blob.size,
+                                                       descs.ctypes.data, len(descs), ctypes.byref(n_sites)))
+        self._n_sites = int(n_sites.value)
+        return self._n_sites
+
+    def reads_sites(self):
+        """(site_read, site_loc) int32 arrays of the resident batch: index into the batch's reads, and the 0-based
+        position of the called base in the forward read."""
+        handle, _ = self._ensure_handle()
+        sr = np.empty(self._n_sites, dtype=np.int32)
+        sl = np.empty(self._n_sites, dtype=np.int32)
+        _lib.check(_lib.load().ccsm_reads_sites(handle, sr.ctypes.data, sl.ctypes.data))
+        return sr, sl
+
+    def reads_features(self, s0=0, cn=None):
+        """The reference's feature tensors of sites [s0, s0+cn) of the resident batch, as device tensors
+        {kmer, kpass, ipd, pw, kmer2, kpass2, ipd2, pw2 (, sns, sns2)} -- what _batch_feature_list2s + the
+        FloatTensor stacking would hand to forward (reference call_modifications.py:73-123,201-208)."""
+        handle, dev = self._ensure_handle()
+        device = torch.device("cuda", dev)
+        cn = self._n_sites - s0 if cn is None else cn
+        out, strands = {}, []
+        for sfx in ("", "2"):
+            s = _lib.Strand()
+            for name, key, w in (("kmer", "kmer", self.seq_len), ("kpass", "kpass", self.seq_len),
+                                 ("ipd_means", "ipd", self.seq_len), ("pw_means", "pw", self.seq_len), ("sns", "sns", 4)):
+                if (key == "kpass" and not self.is_npass) or (key == "sns" and not self.is_sn):
+                    continue
+                t = torch.empty((cn, w), dtype=torch.float32, device=device)
+                out[key + sfx] = t
+                setattr(s, name, t.data_ptr())
+            strands.append(s)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(_lib.load().ccsm_reads_features(handle, s0, cn, ctypes.byref(strands[0]), ctypes.byref(strands[1]),
+                                                   ctypes.c_void_p(stream)))
+        return out
+
+    def reads_forward(self, h0=None, want_probs=True):
+        """Features -> forward -> per-site outputs for the resident batch (include/ccsm.h ccsm_reads_forward_host).
+        Returns a dict of numpy arrays: probs (n, 2) float32 [if want_probs], prob1 (n,) float32 =
+        round(p1/(p0+p1), 6), mm (n,) int32 MM-tag deltas, ml (n,) uint8 ML bytes."""
+        handle, _ = self._ensure_handle()
+        n = self._n_sites
+        self._apply_h0_mode(handle)
+        cell = getattr(self, "rnn_cell", None)
+        if cell is None:
+            h0 = None  # no recurrent state (transformer encoder)
+        elif cell == "lstm":
+            if h0 is not None or self._h0_mode == "reference":
+                raise ValueError("LSTM models in the reads pipeline take their initial state from the library: use "
+                                 "h0 mode 'device' or 'zeros' (the cell state is zero)")
+        elif h0 is None and self._h0_mode == "reference":
+            h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
+                  self.init_hidden(n, self.num_layers, self.hidden_size))
+        pa = pb = None
+        if h0 is not None:
+            hshape = (2 * self.num_layers, n, self.hidden_size)
+            h0a, h0b = _dev_f32(h0[0], torch.device("cpu"), hshape), _dev_f32(h0[1], torch.device("cpu"), hshape)
+            pa, pb = h0a.data_ptr(), h0b.data_ptr()
+        res = {"prob1": np.empty(n, dtype=np.float32), "mm": np.empty(n, dtype=np.int32),
+               "ml": np.empty(n, dtype=np.uint8)}
+        probs = np.empty((n, self.num_classes), dtype=np.float32) if want_probs else None
+        if n > 0:
+            _lib.check(_lib.load().ccsm_reads_forward_host(handle, pa, pb, None,
+                                                           probs.ctypes.data if want_probs else None,
+                                                           res["prob1"].ctypes.data, res["mm"].ctypes.data,
+                                                           res["ml"].ctypes.data))
+        if want_probs:
+            res["probs"] = probs
+        return res
+
+
+class ModelAttRNN(_ReadsMixin, _NativeModule):
     """Drop-in for the reference ``ModelAttRNN`` with ``model_type="attbigru2s"`` (models.py:17-150)."""
 
     def __init__(self, seq_len=21, num_layers=3, num_classes=2, dropout_rate=0.5, hidden_size=256,
@@ -323,82 +411,6 @@ class ModelAttRNN(_NativeModule):
         return logits, probs
 
 
-    # ---- reads in, calls out: device feature extraction (include/ccsm.h ccsm_reads_*)
-    def extract_reads(self, batch, opts):
-        """Uploads a ``extract_features.ReadBatch`` and builds its site list on the device
-        (replaces extract_features_from_double_strand_read, reference extract_features.py:261-406).
-        ``opts`` = ``extract_features.extract_opts(args, motifs)``.  Returns the number of candidate sites."""
-        handle, _ = self._ensure_handle()
-        motifs = opts["motifs"]
-        o = _lib.ExtractOpts(opts["mod_loc"], opts["norm"], opts["decode"], len(motifs), len(motifs[0]),
-                             "".join(motifs).encode("ascii"))
-        blob = np.ascontiguousarray(batch.blob, dtype=np.uint8)
-        descs = np.ascontiguousarray(batch.descs)
-        n_sites = ctypes.c_int64(0)
-        _lib.check(_lib.load().ccsm_reads_extract_host(handle, ctypes.byref(o), blob.ctypes.data, blob.size,
-                                                       descs.ctypes.data, len(descs), ctypes.byref(n_sites)))
-        self._n_sites = int(n_sites.value)
-        return self._n_sites
-
-    def reads_sites(self):
-        """(site_read, site_loc) int32 arrays of the resident batch: index into the batch's reads, and the 0-based
-        position of the called base in the forward read."""
-        handle, _ = self._ensure_handle()
-        sr = np.empty(self._n_sites, dtype=np.int32)
-        sl = np.empty(self._n_sites, dtype=np.int32)
-        _lib.check(_lib.load().ccsm_reads_sites(handle, sr.ctypes.data, sl.ctypes.data))
-        return sr, sl
-
-    def reads_features(self, s0=0, cn=None):
-        """The reference's feature tensors of sites [s0, s0+cn) of the resident batch, as device tensors
-        {kmer, kpass, ipd, pw, kmer2, kpass2, ipd2, pw2 (, sns, sns2)} -- what _batch_feature_list2s + the
-        FloatTensor stacking would hand to forward (reference call_modifications.py:73-123,201-208)."""
-        handle, dev = self._ensure_handle()
-        device = torch.device("cuda", dev)
-        cn = self._n_sites - s0 if cn is None else cn
-        out, strands = {}, []
-        for sfx in ("", "2"):
-            s = _lib.Strand()
-            for name, key, w in (("kmer", "kmer", self.seq_len), ("kpass", "kpass", self.seq_len),
-                                 ("ipd_means", "ipd", self.seq_len), ("pw_means", "pw", self.seq_len), ("sns", "sns", 4)):
-                if (key == "kpass" and not self.is_npass) or (key == "sns" and not self.is_sn):
-                    continue
-                t = torch.empty((cn, w), dtype=torch.float32, device=device)
-                out[key + sfx] = t
-                setattr(s, name, t.data_ptr())
-            strands.append(s)
-        stream = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(_lib.load().ccsm_reads_features(handle, s0, cn, ctypes.byref(strands[0]), ctypes.byref(strands[1]),
-                                                   ctypes.c_void_p(stream)))
-        return out
-
-    def reads_forward(self, h0=None, want_probs=True):
-        """Features -> forward -> per-site outputs for the resident batch (include/ccsm.h ccsm_reads_forward_host).
-        Returns a dict of numpy arrays: probs (n, 2) float32 [if want_probs], prob1 (n,) float32 =
-        round(p1/(p0+p1), 6), mm (n,) int32 MM-tag deltas, ml (n,) uint8 ML bytes."""
-        handle, _ = self._ensure_handle()
-        n = self._n_sites
-        self._apply_h0_mode(handle)
-        if h0 is None and self._h0_mode == "reference":
-            h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
-                  self.init_hidden(n, self.num_layers, self.hidden_size))
-        pa = pb = None
-        if h0 is not None:
-            hshape = (2 * self.num_layers, n, self.hidden_size)
-            h0a, h0b = _dev_f32(h0[0], torch.device("cpu"), hshape), _dev_f32(h0[1], torch.device("cpu"), hshape)
-            pa, pb = h0a.data_ptr(), h0b.data_ptr()
-        res = {"prob1": np.empty(n, dtype=np.float32), "mm": np.empty(n, dtype=np.int32),
-               "ml": np.empty(n, dtype=np.uint8)}
-        probs = np.empty((n, self.num_classes), dtype=np.float32) if want_probs else None
-        if n > 0:
-            _lib.check(_lib.load().ccsm_reads_forward_host(handle, pa, pb, None,
-                                                           probs.ctypes.data if want_probs else None,
-                                                           res["prob1"].ctypes.data, res["mm"].ctypes.data,
-                                                           res["ml"].ctypes.data))
-        if want_probs:
-            res["probs"] = probs
-        return res
-
 
 class ModelAttRNN2(ModelAttRNN):
     """Drop-in for the reference ``ModelAttRNN2`` (``model_type`` "attbigru2s2" / "attbilstm2s2", models.py:221-382):
@@ -479,7 +491,7 @@ class _PositionalEmbedding(nn.Module):  # parameter container, reference models.
         self.pos_embed = nn.Embedding(seq_len, d_model)
 
 
-class ModelTransEnc(_NativeModule):
+class ModelTransEnc(_ReadsMixin, _NativeModule):
     """Drop-in for the reference ``ModelTransEnc`` (``model_type="transencoder2s"``, models.py:451-620): integer
     embeddings, SrcEmbed conv stack, learned positions, post-norm transformer encoder, mean pooling, classifier.
     No checkpoint ships for it; fp32 kernels; same 16-tensor ``forward`` (there is no recurrent state, so no h0)."""
@@ -495,6 +507,7 @@ class ModelTransEnc(_NativeModule):
         self.seq_len, self.num_layers, self.num_classes, self.d_model = seq_len, num_layers, num_classes, d_model
         self.nhead, self.dim_ff = nhead, dim_ff
         self.hidden_size = d_model
+        self.rnn_cell = None  # no recurrent state
         self.n_embed = NEMBED_BASE
         self.is_stds, self.is_npass, self.is_sn, self.is_map = is_stds, is_npass, is_sn, is_map
         self.nembed_all = NEMBED_BASE + 2 * 8 + (4 if is_npass else 0)

@@ -98,3 +98,51 @@ def test_pieces_and_rank_shards_give_the_same_modbam(tmp_path, ckpt_file, monkey
         merged.update(_tags_by_name(p))
         sites += c["sites"]
     assert sites == 12691 and merged == ref
+
+
+@pytest.mark.parametrize("mt,extra", [("transencoder2s", ["--layer_trans", "2", "--d_model", "64", "--nhead", "4", "--dim_ff", "128"]),
+                                      ("attbigru2s2", ["--layer_rnn", "2", "--hid_rnn", "32", "--h0", "zeros"]),
+                                      ("attbilstm2s", ["--layer_rnn", "2", "--hid_rnn", "32", "--h0", "zeros", "--norm", "zscore"])])
+def test_call_mods_pipeline_runs_the_other_model_types(tmp_path, mt, extra):
+    """--model_type dispatch through the BAM pipeline (reference call_modifications.py:315-340): seeded random weights
+    (no checkpoint ships for these types); the ML bytes written to the modbam must equal the ones obtained by calling
+    the model's 16-tensor forward on the device-extracted features."""
+    import ctypes
+    from ccsmeth_b200.extract_features import extract_opts, pack_reads
+    torch.manual_seed(11)
+    base = ["-i", DEMO, "-o", str(tmp_path / mt), "--model_type", mt] + (["--norm", "none"] if "--norm" not in extra else []) + extra
+    args = cm.build_parser().parse_args(base + ["-m", "unused"])
+    from ccsmeth_b200.models import ModelAttRNN, ModelAttRNN2, ModelTransEnc
+    if mt == "transencoder2s":
+        ref_model = ModelTransEnc(21, 2, 2, 0, 64, 4, 128)
+    elif mt == "attbigru2s2":
+        ref_model = ModelAttRNN2(21, 2, 2, 0, 32, model_type=mt)
+    else:
+        ref_model = ModelAttRNN(21, 2, 2, 0, 32, model_type=mt)
+    ckpt = str(tmp_path / (mt + ".ckpt"))
+    torch.save(ref_model.state_dict(), ckpt)
+    args.model_file = ckpt
+    counts, path = cm.call_mods(args)
+    assert counts["sites"] == 12691 and counts["reads_written"] == 116
+    recs = list(BamReader(path))
+    # independent route: device features of the first reads -> model.forward -> prob1 -> ML
+    model = cm.load_model(ckpt, args, device=0)
+    model.set_h0_mode("zeros")
+    sub = list(BamReader(DEMO))[:12]
+    batch = pack_reads(sub, args)
+    n = model.extract_reads(batch, extract_opts(args, ["CG"]))
+    site_read, _ = model.reads_sites()
+    f = model.reads_features()
+    order = ("kmer", "kpass", "ipd", None, "pw", None, None, None)
+    a = [f[k] if k else torch.zeros(1) for k in order] + [f[k + "2"] if k else torch.zeros(1) for k in order]
+    kw = {}
+    if mt == "attbigru2s2":
+        kw["h0"] = (torch.zeros(4, n, 32), torch.zeros(4, n, 32))
+    elif mt == "attbilstm2s":
+        z = torch.zeros(4, n, 32)
+        kw["h0"] = ((z, z), (z, z))
+    _, probs = model(*a, **kw)
+    p = probs.cpu().numpy()
+    ml = cm.convert_probs_to_mltag(np.round(p[:, 1] / (p[:, 0] + p[:, 1]), 6))
+    for r in np.unique(site_read):
+        assert np.array_equal(recs[batch.index[r]].get_tag("ML"), ml[site_read == r]), (mt, r)
