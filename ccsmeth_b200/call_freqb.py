@@ -3,7 +3,7 @@
 Keeps the reference's flag surface and output format (ccsmeth/call_mods_freq_bam.py:741-845, `_write_one_line`
 :626-634, file names :639-642) for the default path: symmetric ``--motifs CG``-style sites, count or aggregate mode,
 haplotype split by ``--hap_tag``, ``--refsites_only`` / ``--refsites_all``, ``--base_clip``, ``--discrete``,
-``--only_close``.  Not offered: bed sorting / tabix (``--sort``, ``--gzip`` need bedtools / tabix).
+``--only_close``, ``--sort``, ``--gzip`` (BGZF-compressed; the ``.tbi`` index is left to ``tabix -p bed``).
 
 Where the reference forks region workers that each ``fetch`` their reads through pysam and pile calls up in Python
 dictionaries (:457-540), this streams the sorted BAM once: native BGZF inflate + record index (bamstream.py), native
@@ -342,6 +342,22 @@ def call_freqb(args):
         f.close()
         if n == 0:
             os.remove(p)  # the reference removes empty outputs (:663-666)
+            continue
+        if args.sort or args.gzip:
+            # reference :667-676: bedtools sort (chromosome, then start), then bgzip + tabix.  Here: the same ordering
+            # and BGZF compression through libccsm's thread team; the .tbi index is left to `tabix -p bed`.
+            with open(p) as rf:
+                lines = rf.readlines()
+            lines.sort(key=lambda ln: (ln.split("\t", 2)[0], int(ln.split("\t", 2)[1])))
+            if args.gzip:
+                from .bamio import BgzfWriter
+                wr = BgzfWriter(p + ".gz", threads=max(1, args.threads))
+                wr.write("".join(lines).encode("ascii"))
+                wr.close()
+                os.remove(p)
+            else:
+                with open(p, "w") as wf:
+                    wf.writelines(lines)
     total = parallel.allreduce_counts(n_lines + [0])[:3]  # the run's only collective, like call_mods
     if rank == 0:
         sys.stderr.write("[call_freqb] %d / %d / %d sites (all / hp1 / hp2) in %.1f s, %d rank(s)\n"

@@ -113,3 +113,15 @@ def test_region_shards_over_ranks_cover_the_single_rank_output(tmp_path, ref_out
         lines += _read(paths[0]).splitlines()
     ref = ref_out["count.all.freq.txt"].splitlines()
     assert len(lines) == len(ref) and sorted(lines) == sorted(ref)
+
+
+def test_sort_and_gzip_outputs(tmp_path, ref_out, aggr_ckpt):
+    import gzip
+    _, paths = _run(tmp_path, "sorted", ["--sort", "--contigs", "chrB,chrA"], aggr_ckpt)
+    lines = _read(paths[0]).splitlines()
+    keys = [(ln.split("\t")[0], int(ln.split("\t")[1])) for ln in lines]
+    assert keys == sorted(keys) and sorted(lines) == sorted(ref_out["count.all.freq.txt"].splitlines())
+    _, paths = _run(tmp_path, "gz", ["--gzip"], aggr_ckpt)
+    assert not os.path.exists(paths[0])
+    with gzip.open(paths[0] + ".gz", "rt") as f:  # BGZF is a valid multi-member gzip stream
+        assert sorted(f.read().splitlines()) == sorted(ref_out["count.all.freq.txt"].splitlines())
