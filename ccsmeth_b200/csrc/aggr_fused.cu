@@ -14,6 +14,7 @@
 //
 // Per site: 137,632 FFMA, 924 B of windows + 256 B of h0 read, 4 B written.
 #include <math.h>
+#include <stdlib.h>
 
 #include "ccsm_internal.h"
 
@@ -44,7 +45,14 @@ __host__ __device__ inline AggrPacked aggr_layout(int IN, int C) {
   return p;
 }
 
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// Gate nonlinearities: ex2.approx-based exp and an approximate reciprocal (about 2 ulp each) -- the accurate
+// expf / tanhf / IEEE division cost as many issue slots as the FFMAs of this small model.  Absolute error ~1e-7 per
+// evaluation; the model output stays within 1e-6 of the CPU port (tests/test_parity_gpu.py).
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float a = fminf(fmaxf(x, -15.f), 15.f);
+  return 1.f - __fdividef(2.f, 1.f + __expf(2.f * a));
+}
 
 // S = sites per thread: every weight fetched from shared memory feeds S x 4 FFMA chains.  Measured on B200: the
 // kernel sits at ~28 % of the FP32 pipe; a warp-wide LDS.128 occupies the shared-memory pipe for four passes even
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(AG_THREADS, 2)
             for (int u = 0; u < 4; ++u) {
               const float r = sigmoid_acc(ar[q][u]);
               const float z = sigmoid_acc(az[q][u]);
-              const float nn = tanhf(fmaf(r, ah[q][u], ai[q][u]));
+              const float nn = tanh_acc(fmaf(r, ah[q][u], ai[q][u]));
               const int col = q * AG_THREADS + tid;
               const float hprev = hcol[(j + u) * COLS + col];
               const float hn = fmaf(z, hprev - nn, nn);  // (1 - z) * n + z * h
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(AG_THREADS, 2)
         }
         float et = 0.f;
 #pragma unroll
-        for (int i = 0; i < AG_H; ++i) et = fmaf(VA[i], tanhf(acc[i]), et);
+        for (int i = 0; i < AG_H; ++i) et = fmaf(VA[i], tanh_acc(acc[i]), et);
         // static indexing keeps e / g in registers
 #pragma unroll
         for (int w = 0; w < AG_MAX_L; ++w)
@@ -265,6 +273,302 @@ __global__ void __launch_bounds__(AG_THREADS, 2)
       const int64_t site = base + col;
       if (site < n) out[site] = num / den + sm[lay.fcb];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Register-tiled formulation (default): a CTA owns 128 sites; for each direction and step the gate pre-activations
+// are one small GEMM  [128 sites x 53] . [53 x 96]  whose operands both sit in shared memory -- x_t / h_{t-1} as
+// [k][site] tiles, the weights as [k][unit pair][r0 r1 z0 z1 n0 n1] -- and each thread accumulates 8 sites x 2 units
+// (64 accumulators): 48 FFMA per 4 shared-memory loads instead of 4 per load in the thread-per-site kernel above.
+// The attention tail runs two threads per site (16 attention units each, combined with one shuffle).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TL_SITES = 128;
+constexpr int TL_THREADS = 256;
+
+struct TiledLayout {
+  int wx, wh, bias, wa, ua, va, fcw, fcb, xs, hs, total;
+};
+__host__ __device__ inline TiledLayout tiled_layout(int IN) {
+  TiledLayout p;
+  int o = 0;
+  p.wx = o;   o += 2 * IN * 16 * 6;       // [dir][k][unit pair][r0 r1 z0 z1 n0 n1]
+  p.wh = o;   o += 2 * AG_H * 16 * 6;
+  o = (o + 3) & ~3;
+  p.bias = o; o += 2 * 4 * AG_H;          // [dir][b_r, b_z, b_in, b_hn][unit]
+  p.wa = o;   o += 2 * AG_H * AG_H;       // [k 0..63][unit]
+  p.ua = o;   o += 2 * AG_H * AG_H;
+  p.va = o;   o += AG_H;
+  p.fcw = o;  o += 2 * AG_H;
+  p.fcb = o;  o += 4;
+  p.xs = o;   o += 2 * IN * TL_SITES;     // x_t tiles [2][k][site] (the next step's tile is prefetched)
+  o = (o + 3) & ~3;
+  p.hs = o;   o += 2 * AG_H * TL_SITES;   // h tiles [2][unit][site]
+  p.total = o;
+  return p;
+}
+
+template <int IN>
+__global__ void __launch_bounds__(TL_THREADS, 2)
+    aggr_tiled_kernel(const float* __restrict__ packed, int packed_floats, int64_t n, int L, const float* __restrict__ offsets,
+                      const float* __restrict__ histos, const long long* __restrict__ site_pos, int only_close,
+                      const float* __restrict__ h0, float* scratch, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const TiledLayout lay = tiled_layout(IN);
+  for (int i = threadIdx.x; i < packed_floats; i += TL_THREADS) sm[i] = packed[i];
+  float* xs = sm + lay.xs;
+  float* hs = sm + lay.hs;
+  __syncthreads();
+  constexpr int BINS = IN - 1;
+  const int tid = threadIdx.x;
+  const int sg = tid >> 4, up = tid & 15;      // site group (8 sites), unit pair
+  const int s_lo = sg * 8;
+  float* my_scratch = scratch + (size_t)blockIdx.x * L * 2 * AG_H * TL_SITES;  // [t][unit 0..63][site]
+
+  for (int64_t base = (int64_t)blockIdx.x * TL_SITES; base < n; base += (int64_t)gridDim.x * TL_SITES) {
+#pragma unroll 1
+    for (int dir = 0; dir < 2; ++dir) {
+      const float* WX = sm + lay.wx + dir * IN * 96;
+      const float* WH = sm + lay.wh + dir * AG_H * 96;
+      const float* BS = sm + lay.bias + dir * 4 * AG_H;
+      // h0 tile -> hs[0]
+      for (int idx = tid; idx < TL_SITES * AG_H; idx += TL_THREADS) {
+        const int site = idx >> 5, k = idx & 31;
+        const int64_t gs = base + site < n ? base + site : n - 1;
+        hs[k * TL_SITES + site] = h0 ? h0[((size_t)dir * n + gs) * AG_H + k] : 0.f;
+      }
+      int cur = 0;
+#pragma unroll 1
+      for (int step = 0; step < L; ++step) {
+        // x_t tiles: 20 histogram bins + 1 offset per site (materialised windows, or gathered from per-site rows).
+        // Step 0 loads its own tile; every step then fetches the NEXT step's values into registers before its
+        // GEMM and parks them in the other tile afterwards, so the global-memory latency hides behind the FFMAs.
+        float* xcur = xs + (step & 1) * IN * TL_SITES;
+        float* xnext = xs + ((step + 1) & 1) * IN * TL_SITES;
+        auto fetch = [&](int tt, float4 (&v)[3], float& off) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int idx = tid + i * TL_THREADS;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < TL_SITES * (BINS / 4)) {
+              const int site = idx / (BINS / 4), q = idx - site * (BINS / 4);
+              const int64_t gs = base + site < n ? base + site : n - 1;
+              if (site_pos) {
+                const int64_t j = gs + tt - L / 2;
+                if (j >= 0 && j < n) v[i] = __ldg(reinterpret_cast<const float4*>(histos + (size_t)j * BINS) + q);
+              } else {
+                v[i] = __ldg(reinterpret_cast<const float4*>(histos + ((size_t)gs * L + tt) * BINS) + q);
+              }
+            }
+          }
+          off = 0.f;
+          if (tid < TL_SITES) {
+            const int64_t gs = base + tid < n ? base + tid : n - 1;
+            if (site_pos) {
+              const int64_t j = gs + tt - L / 2;
+              const long long centre = site_pos[gs];
+              const long long pj = j < 0 ? site_pos[0] - 1000 : j >= n ? site_pos[n - 1] + 1000 : site_pos[j];
+              if (only_close) {
+                const long long pjm = j - 1 < 0 ? site_pos[0] - 1000 : j - 1 >= n ? site_pos[n - 1] + 1000 : site_pos[j - 1];
+                off = (pj - pjm == 2) ? 1.f : 0.f;
+              } else {
+                off = (float)llabs(pj - centre);
+              }
+            } else {
+              off = __ldg(offsets + (size_t)gs * L + tt);
+            }
+          }
+        };
+        auto park = [&](float* xt, const float4 (&v)[3], float off) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int idx = tid + i * TL_THREADS;
+            if (idx < TL_SITES * (BINS / 4)) {
+              const int site = idx / (BINS / 4), q = idx - site * (BINS / 4);
+              xt[(q * 4 + 0) * TL_SITES + site] = v[i].x;
+              xt[(q * 4 + 1) * TL_SITES + site] = v[i].y;
+              xt[(q * 4 + 2) * TL_SITES + site] = v[i].z;
+              xt[(q * 4 + 3) * TL_SITES + site] = v[i].w;
+            }
+          }
+          if (tid < TL_SITES) xt[BINS * TL_SITES + tid] = off;
+        };
+        const int t = dir ? L - 1 - step : step;
+        float4 pv[3];
+        float poff;
+        if (step == 0) {
+          fetch(t, pv, poff);
+          park(xcur, pv, poff);
+        }
+        __syncthreads();
+        const bool more = step + 1 < L;
+        if (more) fetch(dir ? t - 1 : t + 1, pv, poff);
+        const float* hc = hs + cur * AG_H * TL_SITES;
+        float* hn_t = hs + (cur ^ 1) * AG_H * TL_SITES;
+        float ar[8][2], az[8][2], ai[8][2], ah[8][2];
+        {
+          const float br0 = BS[0 * AG_H + 2 * up], br1 = BS[0 * AG_H + 2 * up + 1];
+          const float bz0 = BS[1 * AG_H + 2 * up], bz1 = BS[1 * AG_H + 2 * up + 1];
+          const float bi0 = BS[2 * AG_H + 2 * up], bi1 = BS[2 * AG_H + 2 * up + 1];
+          const float bh0 = BS[3 * AG_H + 2 * up], bh1 = BS[3 * AG_H + 2 * up + 1];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            ar[q][0] = br0; ar[q][1] = br1; az[q][0] = bz0; az[q][1] = bz1;
+            ai[q][0] = bi0; ai[q][1] = bi1; ah[q][0] = bh0; ah[q][1] = bh1;
+          }
+        }
+#pragma unroll 3
+        for (int k = 0; k < IN; ++k) {
+          const float4 a0 = *reinterpret_cast<const float4*>(xcur + k * TL_SITES + s_lo);
+          const float4 a1 = *reinterpret_cast<const float4*>(xcur + k * TL_SITES + s_lo + 4);
+          const float* wp = WX + (k * 16 + up) * 6;
+          const float2 wr = *reinterpret_cast<const float2*>(wp), wz = *reinterpret_cast<const float2*>(wp + 2),
+                       wn = *reinterpret_cast<const float2*>(wp + 4);
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            ar[q][0] = fmaf(a[q], wr.x, ar[q][0]); ar[q][1] = fmaf(a[q], wr.y, ar[q][1]);
+            az[q][0] = fmaf(a[q], wz.x, az[q][0]); az[q][1] = fmaf(a[q], wz.y, az[q][1]);
+            ai[q][0] = fmaf(a[q], wn.x, ai[q][0]); ai[q][1] = fmaf(a[q], wn.y, ai[q][1]);
+          }
+        }
+#pragma unroll 4
+        for (int k = 0; k < AG_H; ++k) {
+          const float4 a0 = *reinterpret_cast<const float4*>(hc + k * TL_SITES + s_lo);
+          const float4 a1 = *reinterpret_cast<const float4*>(hc + k * TL_SITES + s_lo + 4);
+          const float* wp = WH + (k * 16 + up) * 6;
+          const float2 wr = *reinterpret_cast<const float2*>(wp), wz = *reinterpret_cast<const float2*>(wp + 2),
+                       wn = *reinterpret_cast<const float2*>(wp + 4);
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            ar[q][0] = fmaf(a[q], wr.x, ar[q][0]); ar[q][1] = fmaf(a[q], wr.y, ar[q][1]);
+            az[q][0] = fmaf(a[q], wz.x, az[q][0]); az[q][1] = fmaf(a[q], wz.y, az[q][1]);
+            ah[q][0] = fmaf(a[q], wn.x, ah[q][0]); ah[q][1] = fmaf(a[q], wn.y, ah[q][1]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int unit = 2 * up + u;
+          const float4 p0 = *reinterpret_cast<const float4*>(hc + unit * TL_SITES + s_lo);
+          const float4 p1 = *reinterpret_cast<const float4*>(hc + unit * TL_SITES + s_lo + 4);
+          const float hp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          float hv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float r = sigmoid_acc(ar[q][u]);
+            const float z = sigmoid_acc(az[q][u]);
+            const float nn = tanh_acc(fmaf(r, ah[q][u], ai[q][u]));
+            hv[q] = fmaf(z, hp[q] - nn, nn);  // (1 - z) * n + z * h
+          }
+          const float4 o0 = make_float4(hv[0], hv[1], hv[2], hv[3]), o1 = make_float4(hv[4], hv[5], hv[6], hv[7]);
+          *reinterpret_cast<float4*>(hn_t + unit * TL_SITES + s_lo) = o0;
+          *reinterpret_cast<float4*>(hn_t + unit * TL_SITES + s_lo + 4) = o1;
+          float* sc = my_scratch + ((size_t)t * 2 * AG_H + dir * AG_H + unit) * TL_SITES + s_lo;
+          *reinterpret_cast<float4*>(sc) = o0;
+          *reinterpret_cast<float4*>(sc + 4) = o1;
+        }
+        if (more) park(xnext, pv, poff);
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+    __syncthreads();  // every thread's scratch writes are visible to the block (global memory, same CTA)
+
+    // ---- attention (utils/attention.py:48-70), register-tiled like the GRU: per step one GEMM
+    // [128 sites x 64] . [64 x 32 attention units]; thread = 4 sites x 4 units; the out_t tile comes back from the
+    // scratch slab into the (now idle) h tiles as [k][site].  e_t and fc1 . out_t land in small shared arrays.
+    {
+      float* tile = hs;                       // [64][128]
+      float* e_s = xs;                        // [L][128]   (x tiles are idle now)
+      float* g_s = xs + AG_MAX_L * TL_SITES;  // [L][128]
+      // mapping: 32 site groups of 4 sites x 8 unit groups of 4 attention units = 16 accumulators per thread, and every
+      // reduction over the attention units stays inside 8 adjacent lanes
+      const int ug = tid & 7;
+      const int sl = (tid >> 3) * 4;
+      const float* WA = sm + lay.wa;
+      const float* UA = sm + lay.ua;
+      const float* VA = sm + lay.va + ug * 4;
+      const float* FW = sm + lay.fcw;
+      auto load_tile = [&](int t_f, int t_r) {  // rows 0..31 from step t_f (forward units), 32..63 from step t_r
+        for (int idx = tid; idx < 2 * AG_H * TL_SITES / 4; idx += TL_THREADS) {
+          const int k = idx / (TL_SITES / 4), c = idx - k * (TL_SITES / 4);
+          const int tt = k < AG_H ? t_f : t_r;
+          reinterpret_cast<float4*>(tile)[idx] =
+              *reinterpret_cast<const float4*>(my_scratch + ((size_t)tt * 2 * AG_H + k) * TL_SITES + c * 4);
+        }
+      };
+      auto gemm = [&](const float* W, float (&acc)[4][4], float (&gp)[4]) {
+#pragma unroll 4
+        for (int k = 0; k < 2 * AG_H; ++k) {
+          const float4 a = *reinterpret_cast<const float4*>(tile + k * TL_SITES + sl);
+          const float4 w = *reinterpret_cast<const float4*>(W + k * AG_H + ug * 4);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[q][0] = fmaf(av[q], w.x, acc[q][0]); acc[q][1] = fmaf(av[q], w.y, acc[q][1]);
+            acc[q][2] = fmaf(av[q], w.z, acc[q][2]); acc[q][3] = fmaf(av[q], w.w, acc[q][3]);
+          }
+          if ((k >> 3) == ug) {  // fc1 . out_t: each of the 8 threads of a site group takes 8 of the 64 inputs
+            const float f = FW[k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gp[q] = fmaf(av[q], f, gp[q]);
+          }
+        }
+      };
+      // query projection: q = [h_n fwd (step L-1) | h_n rev (step 0)]
+      float wq[4][4], dummy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wq[q][u] = 0.f;
+      load_tile(L - 1, 0);
+      __syncthreads();
+      gemm(WA, wq, dummy);
+      __syncthreads();
+#pragma unroll 1
+      for (int t = 0; t < L; ++t) {
+        load_tile(t, t);
+        __syncthreads();
+        float acc[4][4], gp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[q][u] = wq[q][u];
+        gemm(UA, acc, gp);
+        float ep[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ep[q] = VA[0] * tanh_acc(acc[q][0]) + VA[1] * tanh_acc(acc[q][1]) + VA[2] * tanh_acc(acc[q][2]) +
+                  VA[3] * tanh_acc(acc[q][3]);
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            ep[q] += __shfl_xor_sync(0xffffffffu, ep[q], o);
+            gp[q] += __shfl_xor_sync(0xffffffffu, gp[q], o);
+          }
+        }
+        if (ug == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            e_s[t * TL_SITES + sl + q] = ep[q];
+            g_s[t * TL_SITES + sl + q] = gp[q];
+          }
+        }
+        __syncthreads();  // tile is overwritten by the next step; e_s / g_s complete for the softmax below
+      }
+      if (tid < TL_SITES) {
+        float mx = -INFINITY;
+        for (int t = 0; t < L; ++t) mx = fmaxf(mx, e_s[t * TL_SITES + tid]);
+        float den = 0.f, num = 0.f;
+        for (int t = 0; t < L; ++t) {
+          const float p = expf(e_s[t * TL_SITES + tid] - mx);
+          den += p;
+          num = fmaf(p, g_s[t * TL_SITES + tid], num);
+        }
+        if (base + tid < n) out[base + tid] = num / den + sm[lay.fcb];
+      }
+    }
+    __syncthreads();  // the scratch slab and tiles are reused by the next item
   }
 }
 
@@ -324,6 +628,27 @@ int aggr_fused_upload(ccsm_model* m) {
   }
   CCSM_TRY(m->aggr_packed.reserve(p.size() * sizeof(float)));
   CCSM_CUDA(cudaMemcpy(m->aggr_packed.p, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // the register-tiled kernel's layout: GRU weights regrouped per unit pair, the rest copied
+  const TiledLayout tl = tiled_layout(IN);
+  std::vector<float> t((size_t)tl.xs, 0.f);
+  for (int d = 0; d < 2; ++d)
+    for (int upair = 0; upair < 16; ++upair)
+      for (int gate = 0; gate < 3; ++gate)
+        for (int u = 0; u < 2; ++u) {
+          const int j = 2 * upair + u;
+          for (int k = 0; k < IN; ++k)
+            t[tl.wx + ((d * IN + k) * 16 + upair) * 6 + gate * 2 + u] = p[lay.wx + ((d * 3 + gate) * IN + k) * H + j];
+          for (int k = 0; k < H; ++k)
+            t[tl.wh + ((d * H + k) * 16 + upair) * 6 + gate * 2 + u] = p[lay.wh + ((d * 3 + gate) * H + k) * H + j];
+        }
+  std::copy(p.begin() + lay.bias, p.begin() + lay.bias + 2 * 4 * H, t.begin() + tl.bias);
+  std::copy(p.begin() + lay.wa, p.begin() + lay.wa + 2 * H * H, t.begin() + tl.wa);
+  std::copy(p.begin() + lay.ua, p.begin() + lay.ua + 2 * H * H, t.begin() + tl.ua);
+  std::copy(p.begin() + lay.va, p.begin() + lay.va + H, t.begin() + tl.va);
+  std::copy(p.begin() + lay.fcw, p.begin() + lay.fcw + 2 * H, t.begin() + tl.fcw);
+  t[tl.fcb] = p[lay.fcb];
+  CCSM_TRY(m->aggr_packed_tiled.reserve(t.size() * sizeof(float)));
+  CCSM_CUDA(cudaMemcpy(m->aggr_packed_tiled.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
   return CCSM_OK;
 }
 
@@ -345,6 +670,27 @@ int aggr_fused_forward_sites(ccsm_model* m, int64_t n, const long long* site_pos
 static int aggr_launch(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const long long* site_pos,
                        int only_close, const float* h0, float* out, cudaStream_t st) {
   const int IN = m->in_feat, C = m->cfg.num_classes;
+  int sms = 0;
+  CCSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
+  const char* env = getenv("CCSM_AGGR_TILED");
+  if (!(env && atoi(env) == 0)) {
+    // register-tiled kernel (default); CCSM_AGGR_TILED=0 selects the thread-per-site kernel below
+    const TiledLayout tl = tiled_layout(IN);
+    const size_t smem_t = (size_t)tl.total * sizeof(float);
+    static bool attr_t = false;
+    if (!attr_t) {
+      CCSM_CUDA(cudaFuncSetAttribute(aggr_tiled_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      attr_t = true;
+    }
+    const int64_t tiles_t = (n + TL_SITES - 1) / TL_SITES;
+    const int grid_t = (int)(tiles_t < 2LL * sms ? tiles_t : 2LL * sms);
+    CCSM_TRY(m->aggr_scratch.reserve((size_t)grid_t * m->cfg.seq_len * 2 * AG_H * TL_SITES * sizeof(float)));
+    aggr_tiled_kernel<21><<<grid_t, TL_THREADS, smem_t, st>>>(m->aggr_packed_tiled.as<float>(), tl.xs, n, m->cfg.seq_len, offsets,
+                                                              histos, site_pos, only_close, h0, m->aggr_scratch.as<float>(), out);
+    count_launch();
+    CCSM_CUDA(cudaGetLastError());
+    return CCSM_OK;
+  }
   const AggrPacked lay = aggr_layout(IN, C);
   constexpr int COLS = AG_S * AG_THREADS;
   const size_t smem = ((size_t)lay.total + (size_t)AG_H * COLS) * sizeof(float);
@@ -353,8 +699,6 @@ static int aggr_launch(ccsm_model* m, int64_t n, const float* offsets, const flo
     CCSM_CUDA(cudaFuncSetAttribute(aggr_fused_kernel<21, AG_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  int sms = 0;
-  CCSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
   const int64_t tiles = (n + COLS - 1) / COLS;
   const int grid = (int)(tiles < 2LL * sms ? tiles : 2LL * sms);
   CCSM_TRY(m->aggr_scratch.reserve((size_t)grid * m->cfg.seq_len * 2 * AG_H * COLS * sizeof(float)));

@@ -151,6 +151,7 @@ void ccsm_destroy(ccsm_model* m) {
   pu_release(m);
   trans_release(m);
   m->aggr_packed.release();
+  m->aggr_packed_tiled.release();
   m->aggr_scratch.release();
   for (auto& l : m->fp32.layers) {
     l.w_ih.release(); l.b_ih.release(); l.w_hh.release(); l.b_hh.release();

@@ -132,7 +132,7 @@ struct ccsm_model {
   ccsm::TcState* tc = nullptr;
   ccsm::ExState* ex = nullptr;
   ccsm::PuState* pu = nullptr;
-  ccsm::DevBuf aggr_packed, aggr_scratch;  // fused aggregate kernel (aggr_fused.cu)
+  ccsm::DevBuf aggr_packed, aggr_packed_tiled, aggr_scratch;  // fused aggregate kernels (aggr_fused.cu)
   ccsm::Profiler prof;
   int h0_mode = 0;            // CCSM_H0_*
   uint64_t h0_seed = 0;
