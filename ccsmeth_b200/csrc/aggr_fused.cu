@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(AG_THREADS, 2)
 // (64 accumulators): 48 FFMA per 4 shared-memory loads instead of 4 per load in the thread-per-site kernel above.
 // The attention tail runs two threads per site (16 attention units each, combined with one shuffle).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int TL_SITES = 128;
+constexpr int TL_SITES = 128;  // (the index arithmetic below uses >> 7 / & 127)
 constexpr int TL_THREADS = 256;
 
 struct TiledLayout {
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
       const float* BS = sm + lay.bias + dir * 4 * AG_H;
       // h0 tile -> hs[0]
       for (int idx = tid; idx < TL_SITES * AG_H; idx += TL_THREADS) {
-        const int site = idx >> 5, k = idx & 31;
+        const int site = idx & (TL_SITES - 1), k = idx >> 7;  // consecutive lanes -> consecutive sites: no bank conflicts
         const int64_t gs = base + site < n ? base + site : n - 1;
         hs[k * TL_SITES + site] = h0 ? h0[((size_t)dir * n + gs) * AG_H + k] : 0.f;
       }
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
             const int idx = tid + i * TL_THREADS;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < TL_SITES * (BINS / 4)) {
-              const int site = idx / (BINS / 4), q = idx - site * (BINS / 4);
+              const int q = idx >> 7, site = idx & (TL_SITES - 1);  // lanes walk the sites: conflict-free tile stores
               const int64_t gs = base + site < n ? base + site : n - 1;
               if (site_pos) {
                 const int64_t j = gs + tt - L / 2;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2)
           for (int i = 0; i < 3; ++i) {
             const int idx = tid + i * TL_THREADS;
             if (idx < TL_SITES * (BINS / 4)) {
-              const int site = idx / (BINS / 4), q = idx - site * (BINS / 4);
+              const int q = idx >> 7, site = idx & (TL_SITES - 1);
               xt[(q * 4 + 0) * TL_SITES + site] = v[i].x;
               xt[(q * 4 + 1) * TL_SITES + site] = v[i].y;
               xt[(q * 4 + 2) * TL_SITES + site] = v[i].z;
