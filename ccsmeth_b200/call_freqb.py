@@ -256,7 +256,7 @@ def write_one_line(beditem, wf, is_bed):
                             str(cov), str(round(metprob + 0.000001, 4)), "."]) + "\n")
 
 
-def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1):
+def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1, piece_bytes=48 << 20):
     """Streams the sorted BAM and yields (region, bed_all, bed_hp1, bed_hp2) for every reference chunk that has calls.
     With world > 1 the chunks are dealt round-robin to the ranks (chunk index % world == rank): regions are
     independent, windows never cross a chunk boundary, so no data moves between ranks."""
@@ -269,7 +269,7 @@ def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1):
         if ci % world == rank:
             by_contig.setdefault(c[0], []).append(c)
     flt = _lib.BamFilter(0, 0, 0, 0, 0)
-    rd = BamPieceReader(bam_path, flt, threads=max(1, args.threads), align_to=1)
+    rd = BamPieceReader(bam_path, flt, threads=max(1, args.threads), piece_bytes=piece_bytes, align_to=1)
     ref_names = [r[0] for r in rd.references]
     opts = _lib.ModcallOpts(args.mapq, 1 if args.no_supplementary else 0, args.base_clip,
                             args.hap_tag.encode("ascii")[:2], float(args.identity), 0, 0, None, None, None)
@@ -289,25 +289,41 @@ def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1):
         opts.ref_off, opts.sites_fwd, opts.sites_rev = ref_off.ctypes.data, sites_fwd.ctypes.data, sites_rev.ctypes.data
         zero_rule = (len(motifs[0]), args.mod_loc)
     calls = ModCalls()
+
+    def flush(lo, hi):
+        """All reads of references [lo, hi) have been seen (the BAM is coordinate-sorted): call their chunks, then
+        forget their calls -- memory stays bounded by one reference sequence's worth of calls."""
+        rid, pos, ml, hap, strand = calls.arrays()
+        for ref_id in range(lo, hi):
+            name = ref_names[ref_id]
+            if name not in by_contig:
+                continue
+            sel = rid == ref_id
+            if not sel.any():
+                continue
+            cpos, cml, chap, cstrand = pos[sel], ml[sel], hap[sel], strand[sel]
+            for region in by_contig[name]:
+                _, s, e = region
+                pile = region_pileups(cpos, cml, chap, cstrand, s, e, comb, zero_rule)
+                if not pile:
+                    continue
+                beds = call_region(model, args, dnacontigs[name], name, pile, motifs_filter)
+                if beds[0]:
+                    yield (region,) + beds
+        keep = rid >= hi
+        calls.parts = [(rid[keep], pos[keep], ml[keep], hap[keep], strand[keep])] if keep.any() else []
+
+    done = 0
     for piece in rd:
         calls.add_piece(piece, opts)
+        off = int(piece.recs["off"][-1]) + 4
+        last_ref = int(np.frombuffer(piece.buf[off:off + 4].tobytes(), dtype="<i4")[0])
+        upto = len(ref_names) if last_ref < 0 else min(last_ref, len(ref_names))  # unmapped reads (-1) sort last
+        if upto > done:
+            yield from flush(done, upto)
+            done = upto
     rd.close()
-    rid, pos, ml, hap, strand = calls.arrays()
-    for ref_id, name in enumerate(ref_names):
-        if name not in by_contig:
-            continue
-        sel = rid == ref_id
-        if not sel.any():
-            continue
-        cpos, cml, chap, cstrand = pos[sel], ml[sel], hap[sel], strand[sel]
-        for region in by_contig[name]:
-            _, s, e = region
-            pile = region_pileups(cpos, cml, chap, cstrand, s, e, comb, zero_rule)
-            if not pile:
-                continue
-            beds = call_region(model, args, dnacontigs[name], name, pile, motifs_filter)
-            if beds[0]:
-                yield (region,) + beds
+    yield from flush(done, len(ref_names))
 
 
 def call_freqb(args):

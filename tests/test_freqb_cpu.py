@@ -183,6 +183,12 @@ def test_host_chain_with_the_pileup_oracle_reproduces_the_reference_files(ref_ou
     for g, name in enumerate(("all", "hp1", "hp2")):
         assert bufs[g].getvalue() == ref_out["%s.%s.freq.txt" % (tag, name)], (tag, name)
     if tag == "count":
+        # the same through many small pieces: references are flushed as soon as the sorted stream has moved past them
+        b = io.StringIO()
+        for _, *beds in cf.iter_region_results(args, OracleModel(), contigs, BAM, piece_bytes=30000):
+            for item in beds[0]:
+                cf.write_one_line(item, b, False)
+        assert b.getvalue() == ref_out["count.all.freq.txt"]
         # reference chunks dealt round-robin to three ranks: disjoint, and together the one-rank result
         parts = []
         for rank in range(3):
