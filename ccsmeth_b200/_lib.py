@@ -25,15 +25,16 @@ OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED, EKEY = 0, -1, -2, -3, -4, -5, -
 KIND_ATT2S, KIND_AGGR = 0, 1
 PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x3": 3, "fp16": 4}
 FEAT_NPASS, FEAT_STDS, FEAT_SN, FEAT_MAP, CELL_LSTM, MODEL_2S2, MODEL_TRANSENC = 1, 2, 4, 8, 16, 32, 64
+AGGR_LSTM = 0x100
 
 EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_create", "ccsm_destroy",
            "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",
-           "ccsm_forward_att2s_host", "ccsm_forward_att2s_lstm", "ccsm_forward_aggr", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
+           "ccsm_forward_att2s_host", "ccsm_forward_att2s_lstm", "ccsm_forward_aggr", "ccsm_forward_aggr_lstm", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
            "ccsm_debug_umma_pair_gemm", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
            "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound",
            "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records", "ccsm_bam_modcalls", "ccsm_pileup_luts",
-           "ccsm_pileup_begin_host", "ccsm_pileup_finish_host"]
+           "ccsm_pileup_begin_host", "ccsm_pileup_finish_host", "ccsm_pileup_finish_lstm_host"]
 
 
 class CcsmError(RuntimeError):
@@ -156,6 +157,8 @@ def load():
         lib.ccsm_forward_att2s_lstm.argtypes = [vp, i64, ctypes.POINTER(Strand), ctypes.POINTER(Strand), vp, vp, vp, vp, vp, vp, vp]
         lib.ccsm_forward_att2s_lstm.restype = ctypes.c_int
         lib.ccsm_forward_aggr.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        lib.ccsm_forward_aggr_lstm.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
+        lib.ccsm_forward_aggr_lstm.restype = ctypes.c_int
         lib.ccsm_debug_last_rnn_out.argtypes = [vp, vp, i64]
         lib.ccsm_debug_last_rnn_out.restype = i64
         lib.ccsm_debug_tc_layer_out.argtypes = [vp, i32, vp, i64]
@@ -183,7 +186,8 @@ def load():
         lib.ccsm_pileup_luts.argtypes = [ctypes.POINTER(PileupOpts), i32, vp, vp]
         lib.ccsm_pileup_begin_host.argtypes = [vp, ctypes.POINTER(PileupOpts), i64, vp, vp, vp, vp, vp]
         lib.ccsm_pileup_finish_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
-        for fn in ("ccsm_pileup_luts", "ccsm_pileup_begin_host", "ccsm_pileup_finish_host"):
+        lib.ccsm_pileup_finish_lstm_host.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, vp, vp]
+        for fn in ("ccsm_pileup_luts", "ccsm_pileup_begin_host", "ccsm_pileup_finish_host", "ccsm_pileup_finish_lstm_host"):
             getattr(lib, fn).restype = ctypes.c_int
         lib.ccsm_bam_modcalls.argtypes = [vp, vp, i32, ctypes.POINTER(ModcallOpts), vp, vp, vp, vp, vp, i64, ctypes.POINTER(i32)]
         lib.ccsm_bam_modcalls.restype = i64

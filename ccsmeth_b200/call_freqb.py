@@ -25,7 +25,7 @@ import torch
 from . import _lib, parallel
 from .bamstream import BamPieceReader
 from .call_mods import get_motif_seqs
-from .call_mods_freq_bam import AGGR_BATCH, load_aggr_model
+from .call_mods_freq_bam import draw_initial_states, load_aggr_model
 from .models import AggrAttRNN
 from .utils.process_utils import complement_seq
 
@@ -176,17 +176,8 @@ def draw_region_h0(args, n_high):
     torch.manual_seed(args.tseed)
     AggrAttRNN(args.seq_len, args.layer_rnn, args.class_num, 0, args.hid_rnn, binsize=args.bin_size,
                model_type=args.model_type, device="cpu")  # same constructor calls, same generator consumption
-    out = []
-    for nh in n_high:
-        if nh == 0:
-            out.append(None)
-            continue
-        t = torch.empty(2 * args.layer_rnn, nh, args.hid_rnn)
-        for s in range(0, nh, AGGR_BATCH):
-            e = min(nh, s + AGGR_BATCH)
-            t[:, s:e] = torch.randn(2 * args.layer_rnn, e - s, args.hid_rnn)
-        out.append(t)
-    return out
+    return [draw_initial_states(nh, args.layer_rnn, args.hid_rnn, args.model_type == "attbilstm") if nh else None
+            for nh in n_high]
 
 
 def discretize_score(modprob, coverage):

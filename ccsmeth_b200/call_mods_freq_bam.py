@@ -38,19 +38,30 @@ def _cal_modfreq_in_aggregate_mode(refposes, refposes_histos, model, seq_len=11,
         pos_mat = sliding_window_view(pos_mat, seq_len)
     n = len(histos_mat)
     if h0 is None:
-        h0 = torch.empty(2 * model.num_layers, n, model.hidden_size)
-        for s in range(0, n, AGGR_BATCH):  # the reference draws one randn per 1024-slice (models.py:661-671)
-            e = min(n, s + AGGR_BATCH)
-            h0[:, s:e] = torch.randn(2 * model.num_layers, e - s, model.hidden_size)
+        h0 = draw_initial_states(n, model.num_layers, model.hidden_size, model.rnn_cell == "lstm")
     out = model(torch.from_numpy(np.ascontiguousarray(pos_mat, dtype=np.float32)),
                 torch.from_numpy(np.ascontiguousarray(histos_mat, dtype=np.float32)), h0=h0)
     logits = np.round(np.clip(out.cpu().numpy(), 0, 1), 6)
     return [logits[idx][0] for idx in range(n)]
 
 
+def draw_initial_states(n, num_layers, hidden_size, lstm=False):
+    """The initial states the reference's batch loop draws for n sites: per 1024-site slice one ``torch.randn`` for h0
+    and, for the LSTM cell, a second one for c0 (models.py:661-671, call_mods_freq_bam.py:295-301).
+    -> h0 (2*layers, n, hidden), or the pair (h0, c0)."""
+    h0 = torch.empty(2 * num_layers, n, hidden_size)
+    c0 = torch.empty(2 * num_layers, n, hidden_size) if lstm else None
+    for s in range(0, n, AGGR_BATCH):
+        e = min(n, s + AGGR_BATCH)
+        h0[:, s:e] = torch.randn(2 * num_layers, e - s, hidden_size)
+        if lstm:
+            c0[:, s:e] = torch.randn(2 * num_layers, e - s, hidden_size)
+    return (h0, c0) if lstm else h0
+
+
 def load_aggr_model(model_path, args, device=0):
     """Model lifecycle of the reference's per-region loader (call_mods_freq_bam.py:317-342), done once."""
-    if args.model_type not in {"attbigru"}:
+    if args.model_type not in {"attbigru", "attbilstm"}:
         raise ValueError("--model_type not right!")
     model = AggrAttRNN(args.seq_len, args.layer_rnn, args.class_num, 0, args.hid_rnn, binsize=args.bin_size,
                        model_type=args.model_type, device=device)
@@ -88,15 +99,11 @@ def _call_modfreq_of_one_region(refpos2modinfo, args, model, h0=None):
             hap[k] = h if 0 <= h <= 255 else 0
             k += 1
     n_high = model.pileup_begin(refposes, ptr, ml, hap, call_mode=args.call_mode, cov_cf=args.cov_cf,
-                                prob_cf=args.prob_cf, no_amb_cov=args.no_amb_cov, no_hap=args.no_hap)
+                                prob_cf=args.prob_cf, no_amb_cov=args.no_amb_cov, no_hap=args.no_hap,
+                                only_close=getattr(args, "only_close", False))
     if h0 is None and args.call_mode == "aggregate":
-        h0 = []
-        for nh in n_high:
-            t = torch.empty(2 * model.num_layers, nh, model.hidden_size)
-            for s in range(0, nh, AGGR_BATCH):
-                e = min(nh, s + AGGR_BATCH)
-                t[:, s:e] = torch.randn(2 * model.num_layers, e - s, model.hidden_size)
-            h0.append(t if nh else None)
+        h0 = [draw_initial_states(nh, model.num_layers, model.hidden_size, model.rnn_cell == "lstm") if nh else None
+              for nh in n_high]
     cov, cnt, freq = model.pileup_finish(h0 if h0 is not None else (None, None, None))
     out = []
     for i, p in enumerate(refposes):

@@ -579,7 +579,7 @@ static const HostTensor* findw(ccsm_model* m, const std::string& k) {
 }
 
 bool aggr_fused_supported(const ccsm_model* m) {
-  return m->cfg.kind == CCSM_KIND_AGGR && m->cfg.hidden == AG_H && m->cfg.num_layers == 1 && m->cfg.seq_len <= AG_MAX_L &&
+  return m->cfg.kind == CCSM_KIND_AGGR && m->gates == 3 && m->cfg.hidden == AG_H && m->cfg.num_layers == 1 && m->cfg.seq_len <= AG_MAX_L &&
          m->cfg.num_classes == 1 && (m->in_feat == 21);
 }
 

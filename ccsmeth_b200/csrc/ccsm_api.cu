@@ -133,7 +133,14 @@ int ccsm_create(ccsm_model** out, const ccsm_config* cfg) {
     }
   } else {
     m->strands = 1;
-    m->in_feat = cfg->feat_flags + 1;  // bins + offset (reference models.py:639)
+    if (cfg->feat_flags & CCSM_AGGR_LSTM) m->gates = 4;  // AggrAttRNN(model_type="attbilstm") (models.py:640-643)
+    m->cfg.feat_flags = cfg->feat_flags & 255;  // downstream code reads the bin count here
+    if (m->cfg.feat_flags < 1) {
+      set_error("ccsm_create: aggregate model needs a bin count in feat_flags (got %d)", m->cfg.feat_flags);
+      delete m;
+      return CCSM_EINVAL;
+    }
+    m->in_feat = m->cfg.feat_flags + 1;  // bins + offset (reference models.py:639)
     if (is_tc(cfg->precision)) {
       // the aggregate model's K=21/32 contractions are not tensor-core shaped: fp32 FFMA only
       m->cfg.precision = CCSM_PREC_FP32;
@@ -428,29 +435,43 @@ int ccsm_forward_att2s_lstm(ccsm_model* m, int64_t n, const ccsm_strand* fwd, co
   return rc;
 }
 
-int ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
-                      void* stream) {
+static int forward_aggr_impl(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
+                             const float* c0, float* out, void* stream, const char* who) {
   if (!m || m->cfg.kind != CCSM_KIND_AGGR) {
-    set_error("ccsm_forward_aggr: not an aggregate model");
+    set_error("%s: not an aggregate model", who);
     return CCSM_EINVAL;
   }
   if (!m->finalized) {
-    set_error("ccsm_forward_aggr: model not finalized");
+    set_error("%s: model not finalized", who);
     return CCSM_ESTATE;
   }
   if (n < 0 || (n > 0 && (!offsets || !histos || !out))) {
-    set_error("ccsm_forward_aggr: bad argument");
+    set_error("%s: bad argument", who);
     return CCSM_EINVAL;
   }
   if (n == 0) return CCSM_OK;
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
-  // one fused kernel for the shipped configuration (H = 32, 21 inputs, one layer); CCSM_AGGR_UNFUSED=1 keeps the
-  // layer-by-layer fp32 kernels (the path other shapes take) for cross-checks
+  // one fused kernel for the shipped configuration (GRU, H = 32, 21 inputs, one layer); CCSM_AGGR_UNFUSED=1 keeps the
+  // layer-by-layer fp32 kernels (the path other shapes and the LSTM cell take) for cross-checks
   const char* env = getenv("CCSM_AGGR_UNFUSED");
   const bool unfused = env && atoi(env) != 0;
   if (!unfused && aggr_fused_supported(m))
     return aggr_fused_forward(m, n, offsets, histos, h0, out, reinterpret_cast<cudaStream_t>(stream));
-  return fp32_forward_aggr(m, n, offsets, histos, h0, out, reinterpret_cast<cudaStream_t>(stream));
+  return fp32_forward_aggr(m, n, offsets, histos, h0, out, reinterpret_cast<cudaStream_t>(stream), c0);
+}
+
+int ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0, float* out,
+                      void* stream) {
+  return forward_aggr_impl(m, n, offsets, histos, h0, nullptr, out, stream, "ccsm_forward_aggr");
+}
+
+int ccsm_forward_aggr_lstm(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
+                           const float* c0, float* out, void* stream) {
+  if (m && m->gates != 4) {
+    set_error("ccsm_forward_aggr_lstm: not an LSTM aggregate model (CCSM_AGGR_LSTM)");
+    return CCSM_EINVAL;
+  }
+  return forward_aggr_impl(m, n, offsets, histos, h0, c0, out, stream, "ccsm_forward_aggr_lstm");
 }
 
 // Host-buffer entry: H2D staging -> forward -> D2H, pipelined over chunks with two staging buffers.

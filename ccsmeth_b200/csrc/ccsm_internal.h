@@ -154,7 +154,7 @@ int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
                        const float* h0_f, const float* h0_r, float* logits, float* probs, cudaStream_t st,
                        const float* c0_f = nullptr, const float* c0_r = nullptr);
 int fp32_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
-                      float* out, cudaStream_t st);
+                      float* out, cudaStream_t st, const float* c0 = nullptr);
 int trans_upload_weights(ccsm_model* m);
 int trans_forward(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, float* logits, float* probs,
                   cudaStream_t st);

@@ -594,7 +594,7 @@ int fp32_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
 }
 
 int fp32_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
-                      float* out, cudaStream_t st) {
+                      float* out, cudaStream_t st, const float* c0) {
   const int L = m->cfg.seq_len, Bn = m->cfg.feat_flags;
   const int64_t chunk = n < 65536 ? n : 65536;
   CCSM_TRY(reserve_ws(m, chunk));
@@ -604,7 +604,7 @@ int fp32_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const floa
                                                              offsets + s0 * L, histos + s0 * L * Bn,
                                                              m->ws32.x0.as<float>());
     count_launch();
-    CCSM_TRY(run_stack(m, sites, s0, n, h0, nullptr, nullptr, out, st));
+    CCSM_TRY(run_stack(m, sites, s0, n, h0, nullptr, nullptr, out, st, c0, nullptr));
   }
   return CCSM_OK;
 }

@@ -30,7 +30,8 @@ struct PuState {
   DevBuf pos, ptr, ml, hap, lut;
   DevBuf cov, filt, nmod, flag, cidx, blocksum;          // per (group, site)
   DevBuf c_pos, c_histo, c_site, c_out;                  // compact high-coverage lists of the three groups
-  DevBuf r_cov, r_cnt, r_freq, r_kind, h0;
+  DevBuf r_cov, r_cnt, r_freq, r_kind, h0, c0;
+  DevBuf w_off, w_histo;                                 // materialised windows (models outside the fused kernel)
   ccsm_pileup_opts opts{};
   int64_t n = -1;
   int64_t n_high[3] = {0, 0, 0};
@@ -227,11 +228,35 @@ __global__ void __launch_bounds__(256) pileup_finish_kernel(int64_t nc, int64_t 
   r_freq[idx] = (double)p;
 }
 
+// Materialised windows for the models the fused kernel does not cover (other hidden sizes / layer counts, the LSTM
+// cell): offsets (nc, L) and histos (nc, L, bins) exactly as call_mods_freq_bam.py:272-290 pads and slides them --
+// neighbour j = i + t - L/2, zero histogram and a position 1000 bp beyond the region's ends outside it.
+__global__ void pileup_windows_kernel(int64_t nc, int L, int bins, int only_close, const long long* __restrict__ pos,
+                                      const float* __restrict__ histo, float* __restrict__ offsets,
+                                      float* __restrict__ windows) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (site, t)
+  if (idx >= nc * L) return;
+  const int t = (int)(idx % L);
+  const int64_t i = idx / L, j = i + t - L / 2;
+  const long long pj = j < 0 ? pos[0] - 1000 : j >= nc ? pos[nc - 1] + 1000 : pos[j];
+  float off;
+  if (only_close) {
+    const long long pjm = j - 1 < 0 ? pos[0] - 1000 : j - 1 >= nc ? pos[nc - 1] + 1000 : pos[j - 1];
+    off = (pj - pjm == 2) ? 1.f : 0.f;
+  } else {
+    off = (float)llabs(pj - pos[i]);
+  }
+  offsets[idx] = off;
+  float* w = windows + idx * bins;
+  const bool inside = j >= 0 && j < nc;
+  for (int b = 0; b < bins; ++b) w[b] = inside ? histo[j * bins + b] : 0.f;
+}
+
 void pu_release(ccsm_model* m) {
   PuState* s = m->pu;
   if (!s) return;
   for (DevBuf* b : {&s->pos, &s->ptr, &s->ml, &s->hap, &s->lut, &s->cov, &s->filt, &s->nmod, &s->flag, &s->cidx,
-                    &s->blocksum, &s->c_pos, &s->c_histo, &s->c_site, &s->c_out, &s->r_cov, &s->r_cnt, &s->r_freq, &s->r_kind, &s->h0})
+                    &s->blocksum, &s->c_pos, &s->c_histo, &s->c_site, &s->c_out, &s->r_cov, &s->r_cnt, &s->r_freq, &s->r_kind, &s->h0, &s->c0, &s->w_off, &s->w_histo})
     b->release();
   delete s;
   m->pu = nullptr;
@@ -271,8 +296,8 @@ int ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* o, int64_t n, 
     set_error("ccsm_pileup_begin_host: call_mode must be 0 (count) or 1 (aggregate)");
     return CCSM_EINVAL;
   }
-  if (o->call_mode == 1 && (!m->finalized || !aggr_fused_supported(m))) {
-    set_error("ccsm_pileup_begin_host: aggregate mode needs a finalized attbigru model (H = 32, 20 bins, one layer)");
+  if (o->call_mode == 1 && (!m->finalized || m->cfg.num_classes != 1 || m->cfg.feat_flags > 32)) {
+    set_error("ccsm_pileup_begin_host: aggregate mode needs a finalized aggregate model (one output, <= 32 bins)");
     return CCSM_ESTATE;
   }
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
@@ -333,8 +358,10 @@ int ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* o, int64_t n, 
   return CCSM_OK;
 }
 
-int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_hp1, const float* h0_hp2, int32_t* cov,
-                            double* cnt_mod, double* freq, uint8_t* kind) {
+}  // extern "C"
+
+static int pileup_finish_impl(ccsm_model* m, const float* const* h0s, const float* const* c0s, int32_t* cov,
+                              double* cnt_mod, double* freq, uint8_t* kind) {
   if (!m || !m->pu || m->pu->n < 0) {
     set_error("ccsm_pileup_finish_host: no resident pileup (call ccsm_pileup_begin_host first)");
     return CCSM_ESTATE;
@@ -348,8 +375,9 @@ int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_
   }
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
   cudaStream_t st = nullptr;
-  const int bins = s->bins, H = m->cfg.hidden;
-  const float* h0s[3] = {h0_all, h0_hp1, h0_hp2};
+  const int bins = s->bins, H = m->cfg.hidden, L = m->cfg.seq_len;
+  const size_t state_floats = (size_t)2 * m->cfg.num_layers * H;  // per site: (2 * layers, n, hidden)
+  const bool fused = aggr_fused_supported(m);
   for (int g = 0; g < 3 && s->opts.call_mode == 1; ++g) {
     const int64_t nc = s->n_high[g];
     if (nc == 0) continue;
@@ -364,12 +392,29 @@ int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_
     count_launch();
     const float* dh0 = nullptr;
     if (h0s[g]) {
-      CCSM_TRY(s->h0.reserve((size_t)2 * nc * H * 4));
-      CCSM_CUDA(cudaMemcpyAsync(s->h0.p, h0s[g], (size_t)2 * nc * H * 4, cudaMemcpyHostToDevice, st));
+      CCSM_TRY(s->h0.reserve(state_floats * nc * 4));
+      CCSM_CUDA(cudaMemcpyAsync(s->h0.p, h0s[g], state_floats * nc * 4, cudaMemcpyHostToDevice, st));
       dh0 = s->h0.as<float>();
     }
-    CCSM_TRY(aggr_fused_forward_sites(m, nc, s->c_pos.as<long long>(), s->c_histo.as<float>(), s->opts.only_close ? 1 : 0, dh0,
-                                      s->c_out.as<float>(), st));
+    if (fused) {
+      CCSM_TRY(aggr_fused_forward_sites(m, nc, s->c_pos.as<long long>(), s->c_histo.as<float>(),
+                                        s->opts.only_close ? 1 : 0, dh0, s->c_out.as<float>(), st));
+    } else {
+      // other shapes / the LSTM cell: windows are materialised, then the layer-by-layer fp32 kernels run
+      const float* dc0 = nullptr;
+      if (m->gates == 4 && c0s && c0s[g]) {
+        CCSM_TRY(s->c0.reserve(state_floats * nc * 4));
+        CCSM_CUDA(cudaMemcpyAsync(s->c0.p, c0s[g], state_floats * nc * 4, cudaMemcpyHostToDevice, st));
+        dc0 = s->c0.as<float>();
+      }
+      CCSM_TRY(s->w_off.reserve((size_t)nc * L * 4));
+      CCSM_TRY(s->w_histo.reserve((size_t)nc * L * bins * 4));
+      pileup_windows_kernel<<<(unsigned)((nc * L + 255) / 256), 256, 0, st>>>(
+          nc, L, bins, s->opts.only_close ? 1 : 0, s->c_pos.as<long long>(), s->c_histo.as<float>(), s->w_off.as<float>(),
+          s->w_histo.as<float>());
+      count_launch();
+      CCSM_TRY(fp32_forward_aggr(m, nc, s->w_off.as<float>(), s->w_histo.as<float>(), dh0, s->c_out.as<float>(), st, dc0));
+    }
     pileup_finish_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(nc, n, g, s->c_out.as<float>(), s->c_site.as<int>(),
                                                                         s->r_cov.as<int>(), s->r_cnt.as<double>(),
                                                                         s->r_freq.as<double>());
@@ -383,6 +428,27 @@ int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_
   CCSM_CUDA(cudaStreamSynchronize(st));
   CCSM_CUDA(cudaGetLastError());
   return CCSM_OK;
+}
+
+extern "C" {
+
+int ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_hp1, const float* h0_hp2, int32_t* cov,
+                            double* cnt_mod, double* freq, uint8_t* kind) {
+  const float* h0s[3] = {h0_all, h0_hp1, h0_hp2};
+  return pileup_finish_impl(m, h0s, nullptr, cov, cnt_mod, freq, kind);
+}
+
+int ccsm_pileup_finish_lstm_host(ccsm_model* m, const float* const* h0, const float* const* c0, int32_t* cov,
+                                 double* cnt_mod, double* freq, uint8_t* kind) {
+  if (!h0 || !c0) {
+    set_error("ccsm_pileup_finish_lstm_host: h0 / c0 must point at three (possibly NULL) state pointers");
+    return CCSM_EINVAL;
+  }
+  if (m && m->gates != 4) {
+    set_error("ccsm_pileup_finish_lstm_host: not an LSTM aggregate model (CCSM_AGGR_LSTM)");
+    return CCSM_EINVAL;
+  }
+  return pileup_finish_impl(m, h0, c0, cov, cnt_mod, freq, kind);
 }
 
 }  // extern "C"

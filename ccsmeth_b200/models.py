@@ -552,35 +552,43 @@ class ModelTransEnc(_ReadsMixin, _NativeModule):
 
 
 class AggrAttRNN(_NativeModule):
-    """Drop-in for the reference ``AggrAttRNN`` with ``model_type="attbigru"`` (models.py:625-694):
-    regression over 11 neighbouring CpG sites, raw fc1 output (no softmax)."""
+    """Drop-in for the reference ``AggrAttRNN`` (``model_type`` "attbigru" / "attbilstm", models.py:625-694):
+    regression over 11 neighbouring CpG sites, raw fc1 output (no softmax).  The shipped configuration (GRU, hidden 32,
+    20 bins, one layer) runs one fused kernel; other shapes and the LSTM cell run the layer-by-layer fp32 kernels."""
 
     def __init__(self, seq_len=11, num_layers=1, num_classes=1, dropout_rate=0.5, hidden_size=32, binsize=20,
                  model_type="attbigru", device=0, precision=None):
         super().__init__()
-        if model_type != "attbigru":
-            raise ValueError("--model_type not set right! (ccsmeth_b200 implements attbigru)")
+        if model_type not in ("attbigru", "attbilstm"):
+            raise ValueError("--model_type not set right!")
         self.model_type = model_type
         self.device = device
         self.seq_len, self.num_layers, self.num_classes, self.hidden_size = seq_len, num_layers, num_classes, hidden_size
         self.binsize = binsize
         self.feas_ccs = binsize + 1
-        self.rnn_cell = "gru"
-        self.rnn = nn.GRU(self.feas_ccs, hidden_size, num_layers, dropout=0, batch_first=True, bidirectional=True)
+        self.rnn_cell = "lstm" if model_type == "attbilstm" else "gru"
+        rnn = nn.LSTM if self.rnn_cell == "lstm" else nn.GRU
+        self.rnn = rnn(self.feas_ccs, hidden_size, num_layers, dropout=0, batch_first=True, bidirectional=True)
         self._att3 = Attention(hidden_size * 2, hidden_size * 2, hidden_size)
         self.dropout1 = nn.Dropout(p=dropout_rate)
         self.fc1 = nn.Linear(hidden_size * 2, num_classes)
         self.requires_grad_(False)
         self._native_init("fp32")  # K=21/32 contractions are not tensor-core shaped (DESIGN.md)
 
-    def init_hidden(self, batch_size, num_layers, hidden_size):  # reference models.py:661-671
-        return torch.randn(num_layers * 2, batch_size, hidden_size)
+    def init_hidden(self, batch_size, num_layers, hidden_size):  # reference models.py:661-671 (h0, then c0)
+        h0 = torch.randn(num_layers * 2, batch_size, hidden_size)
+        if self.rnn_cell == "lstm":
+            return h0, torch.randn(num_layers * 2, batch_size, hidden_size)
+        return h0
 
     def _config(self, dev):
+        flags = self.binsize | (_lib.AGGR_LSTM if self.rnn_cell == "lstm" else 0)
         return _lib.Config(_lib.KIND_AGGR, self.seq_len, self.num_layers, self.hidden_size, self.num_classes,
-                           0, 0, self.binsize, _lib.PREC["fp32"], dev)
+                           0, 0, flags, _lib.PREC["fp32"], dev)
 
     def forward(self, offsets, histos, h0=None):
+        """h0: the initial state -- a (2*layers, n, hidden) tensor, for the LSTM cell an (h0, c0) pair; None draws it
+        like the reference's init_hidden."""
         handle, dev = self._ensure_handle()
         device = torch.device("cuda", dev)
         L = self.seq_len
@@ -589,12 +597,22 @@ class AggrAttRNN(_NativeModule):
         histos = _dev_f32(histos, device, (n, L, self.binsize))
         if h0 is None:
             h0 = self.init_hidden(n, self.num_layers, self.hidden_size)
+        c0 = None
+        if self.rnn_cell == "lstm":
+            if not isinstance(h0, (tuple, list)) or len(h0) != 2:
+                raise ValueError("attbilstm takes the initial state as an (h0, c0) pair")
+            h0, c0 = h0
+            c0 = _dev_f32(c0, device, (2 * self.num_layers, n, self.hidden_size))
         h0 = _dev_f32(h0, device, (2 * self.num_layers, n, self.hidden_size))
         out = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
         if n > 0:
             stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(_lib.load().ccsm_forward_aggr(handle, n, offsets.data_ptr(), histos.data_ptr(), h0.data_ptr(),
-                                                     out.data_ptr(), ctypes.c_void_p(stream)))
+            if c0 is not None:
+                _lib.check(_lib.load().ccsm_forward_aggr_lstm(handle, n, offsets.data_ptr(), histos.data_ptr(), h0.data_ptr(),
+                                                              c0.data_ptr(), out.data_ptr(), ctypes.c_void_p(stream)))
+            else:
+                _lib.check(_lib.load().ccsm_forward_aggr(handle, n, offsets.data_ptr(), histos.data_ptr(), h0.data_ptr(),
+                                                         out.data_ptr(), ctypes.c_void_p(stream)))
         return out
 
     # ---- call_freqb on the device: one region's pileup -> per-site frequencies (include/ccsm.h ccsm_pileup_*)
@@ -617,7 +635,9 @@ class AggrAttRNN(_NativeModule):
         return tuple(int(v) for v in n_high)
 
     def pileup_finish(self, h0=(None, None, None), with_kind=False):
-        """-> (cov (3, n) int32, cnt_mod (3, n) float64, freq (3, n) float64[, kind (3, n) uint8]), rows = all reads /
+        """h0: per read group (all, hp1, hp2) the initial state for the sites ``pileup_begin`` counted, or None (zeros);
+        for the LSTM cell each entry is an (h0, c0) pair.
+        -> (cov (3, n) int32, cnt_mod (3, n) float64, freq (3, n) float64[, kind (3, n) uint8]), rows = all reads /
         haplotype 1 / 2; cov == -1 marks "no call of this group at this site" (the reference's None); kind: see
         include/ccsm.h (which Python / NumPy value types the reference would hold)."""
         handle, _ = self._ensure_handle()
@@ -625,9 +645,17 @@ class AggrAttRNN(_NativeModule):
         cov = np.full((3, n), -1, dtype=np.int32)
         cnt = np.zeros((3, n), dtype=np.float64)
         freq = np.zeros((3, n), dtype=np.float64)
-        hs = [None if h is None else _dev_f32(h, torch.device("cpu")) for h in h0]
         kind = np.zeros((3, n), dtype=np.uint8)
-        _lib.check(_lib.load().ccsm_pileup_finish_host(handle, *[None if h is None else h.data_ptr() for h in hs],
-                                                       cov.ctypes.data, cnt.ctypes.data, freq.ctypes.data,
-                                                       kind.ctypes.data))
+        cpu = torch.device("cpu")
+        if self.rnn_cell == "lstm":
+            hs = [None if h is None else _dev_f32(h[0], cpu) for h in h0]
+            cs = [None if h is None else _dev_f32(h[1], cpu) for h in h0]
+            ptrs = lambda ts: (ctypes.c_void_p * 3)(*[None if t is None else t.data_ptr() for t in ts])
+            _lib.check(_lib.load().ccsm_pileup_finish_lstm_host(handle, ptrs(hs), ptrs(cs), cov.ctypes.data, cnt.ctypes.data,
+                                                                freq.ctypes.data, kind.ctypes.data))
+        else:
+            hs = [None if h is None else _dev_f32(h, cpu) for h in h0]
+            _lib.check(_lib.load().ccsm_pileup_finish_host(handle, *[None if h is None else h.data_ptr() for h in hs],
+                                                           cov.ctypes.data, cnt.ctypes.data, freq.ctypes.data,
+                                                           kind.ctypes.data))
         return (cov, cnt, freq, kind) if with_kind else (cov, cnt, freq)

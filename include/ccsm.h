@@ -78,6 +78,9 @@ extern "C" {
  * linear1 weight), mean over positions, the two-layer classifier.  state_dict keys as in the reference (BatchNorm
  * running_mean / running_var included; num_batches_tracked is not a float tensor and is not passed).  CCSM_PREC_FP32. */
 #define CCSM_MODEL_TRANSENC 64
+/* CCSM_KIND_AGGR only: AggrAttRNN(model_type="attbilstm") (models.py:640-643), ORed onto the bin count in feat_flags
+ * (bins live in bits 0..7).  Runs on the layer-by-layer fp32 kernels, initial state (h0, c0). */
+#define CCSM_AGGR_LSTM 0x100
 
 typedef struct ccsm_model ccsm_model;
 
@@ -167,6 +170,12 @@ int  ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, c
  * offsets (n, L), histos (n, L, bins), h0 (2*layers, n, hidden) or NULL, out (n, num_classes); device. */
 int  ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos,
                        const float* h0, float* out, void* stream);
+
+/* AggrAttRNN.forward with model_type="attbilstm" (models.py:640-643, 661-671): as ccsm_forward_aggr plus the initial
+ * cell state c0, (2*layers, n, hidden) float32 device or NULL (zeros); the reference draws h0 then c0 with torch.randn.
+ * ccsm_forward_aggr on an LSTM model uses c0 = 0. */
+int  ccsm_forward_aggr_lstm(ccsm_model* m, int64_t n, const float* offsets, const float* histos,
+                            const float* h0, const float* c0, float* out, void* stream);
 
 /* ---- reads in, calls out: feature extraction on the device -----------------------
  * Replaces, for one batch of reads, the per-read host work of
@@ -262,12 +271,18 @@ int  ccsm_pileup_begin_host(ccsm_model* m, const ccsm_pileup_opts* opts, int64_t
                             const int64_t* ptr, const uint8_t* ml, const uint8_t* hap, int64_t* n_high);
 
 /* Step 2 (host buffers): histograms -> fused aggregate model (windows formed in the kernel) -> results.
- * h0_*: host (2, n_high[g], hidden) float32 or NULL (zeros).  Outputs are (3, n_sites) arrays, group-major:
+ * h0_*: host (2*layers, n_high[g], hidden) float32 or NULL (zeros).  The shipped configuration (GRU, hidden 32, 20 bins,
+ * one layer) runs the fused kernel; any other AggrAttRNN shape materialises the windows and runs the fp32 layer kernels.  Outputs are (3, n_sites) arrays, group-major:
  * cov = coverage reported for the site (-1 = the group has no call there: the reference's None), cnt_mod, freq, and
  * (optional) kind = which value types the reference would hold: 0 None, 1 count path with an integer count, 2 count
  * path with np.round(len * freq, 2) (float64), 3 model path (cnt_mod and freq are float32 values). */
 int  ccsm_pileup_finish_host(ccsm_model* m, const float* h0_all, const float* h0_hp1, const float* h0_hp2,
                              int32_t* cov, double* cnt_mod, double* freq, uint8_t* kind);
+
+/* Step 2 for an LSTM aggregate model (CCSM_AGGR_LSTM): h0[g] / c0[g], g = 0 all reads, 1 haplotype 1, 2 haplotype 2,
+ * are host (2*layers, n_high[g], hidden) float32 buffers or NULL (zeros); both arrays hold three pointers. */
+int  ccsm_pileup_finish_lstm_host(ccsm_model* m, const float* const* h0, const float* const* c0,
+                                  int32_t* cov, double* cnt_mod, double* freq, uint8_t* kind);
 
 /* ---- host I/O helpers: BGZF block codec on a thread team (SAM/BAM spec 4.1) --------------------------------
  * The reference reads and writes BAM through pysam/htslib with `threads=` (extract_features.py:60-73,

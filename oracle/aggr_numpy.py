@@ -9,17 +9,21 @@ Pinned against the reference through tests/golden/aggr_*.npz.
 """
 import numpy as np
 
-from .att2s_numpy import bigru_stack, attention
+from .att2s_numpy import bigru_stack, bilstm_stack, attention
 
 
 def forward(sd, offsets, histos, h0, num_layers=1, dtype=np.float64):
     """offsets (n, L), histos (n, L, B), h0 (2*layers, n, H) -> out (n, 1) raw regression (no softmax).
 
-    x = cat(histos, offsets[..., None])   (models.py:675-677)
+    x = cat(histos, offsets[..., None])   (models.py:675-677).  h0 given as an (h0, c0) pair selects the LSTM cell of
+    model_type="attbilstm" (models.py:640-643, 684).
     """
     sd = {k[7:] if k.startswith("module.") else k: np.asarray(v, dtype=dtype) for k, v in sd.items()}
     x = np.concatenate([np.asarray(histos, dtype=dtype), np.asarray(offsets, dtype=dtype)[:, :, None]], axis=2)
-    out, h_n = bigru_stack(x, np.asarray(h0, dtype=dtype), sd, num_layers)
+    if isinstance(h0, (tuple, list)):
+        out, h_n = bilstm_stack(x, np.asarray(h0[0], dtype=dtype), np.asarray(h0[1], dtype=dtype), sd, num_layers)
+    else:
+        out, h_n = bigru_stack(x, np.asarray(h0, dtype=dtype), sd, num_layers)
     q = np.concatenate([h_n[2 * (num_layers - 1)], h_n[2 * (num_layers - 1) + 1]], axis=1)
     ctx, _ = attention(q, out, sd)
     return ctx @ sd["fc1.weight"].T + sd["fc1.bias"]

@@ -40,9 +40,10 @@ def normalized_histo(probs, binsize=20):
 
 
 def call_region(pos, ptr, ml, hap, sd, call_mode="aggregate", cov_cf=4, prob_cf=0.0, no_amb_cov=False, no_hap=False,
-                h0=(None, None, None), seq_len=11, only_close=False):
+                h0=(None, None, None), seq_len=11, only_close=False, num_layers=1):
     """-> (3, n, 3) array of (cov, cnt_mod, freq) per group (all, hp1, hp2), NaN where the reference returns None.
-    h0[g]: (2, n_high_g, 32) initial states of group g's high-coverage sites (zeros if None)."""
+    h0[g]: (2*layers, n_high_g, hidden) initial states of group g's high-coverage sites (zeros if None); an (h0, c0)
+    pair selects the LSTM cell (model_type="attbilstm")."""
     n = len(pos)
     out = np.full((3, n, 3), np.nan)
     for g in range(3):
@@ -62,8 +63,9 @@ def call_region(pos, ptr, ml, hap, sd, call_mode="aggregate", cov_cf=4, prob_cf=
                 out[g, i] = count_mode(probs, prob_cf, no_amb_cov)
         if hi_idx:
             pm, hm = aggr_numpy.build_windows(pos[hi_idx], hi_hist, seq_len, only_close)
-            hh = h0[g] if h0[g] is not None else np.zeros((2, len(hi_idx), 32), dtype=np.float32)
-            raw = aggr_numpy.forward(sd, pm.astype(np.float32), hm.astype(np.float32), hh, dtype=np.float32)
+            hidden = next(np.asarray(w).shape[1] for k, w in sd.items() if k.endswith("rnn.weight_hh_l0"))
+            hh = h0[g] if h0[g] is not None else np.zeros((2 * num_layers, len(hi_idx), hidden), dtype=np.float32)
+            raw = aggr_numpy.forward(sd, pm.astype(np.float32), hm.astype(np.float32), hh, num_layers, dtype=np.float32)
             p = aggr_numpy.postprocess(raw)[:, 0]
             for k, i in enumerate(hi_idx):
                 out[g, i] = (hi_cov[k], round(hi_cov[k] * p[k], 2), p[k])

@@ -105,7 +105,7 @@ def gen_att2s():
     # --- the batch loop: reference _call_mods2s with batch_size 512 over 1100 sites
     ref = refimport.import_reference()
     import ccsmeth.call_modifications as rcm
-    n = 1100
+    n = 1250
     b = synth.make_batch(n, seed=33, with_h0=False)
     code2base = "ACGTN"
     feature_list = []
@@ -296,6 +296,70 @@ def gen_pileup():
         save[tag] = pack(rfb._call_modfreq_of_one_region(info, ns(call_mode="count", **kw)))
     np.savez_compressed(os.path.join(OUT, "pileup_region.npz"), **save)
     print("pileup_region: %d sites, %d calls, aggregate mean freq %.4f" % (n, len(ml), np.nanmean(save["aggr"][0, :, 2])))
+
+
+def gen_aggr_variants():
+    """Section 8f-3 beyond the shipped checkpoint: the reference's region caller with ``--model_type attbilstm`` and
+    with another GRU shape (``--hid_rnn 48 --layer_rnn 2``).  No such checkpoints ship, so seeded random
+    initialisations of the reference's own AggrAttRNN are saved to a temporary checkpoint and loaded by the reference
+    function; every ``init_hidden`` draw (h0, for the LSTM also c0) is recorded."""
+    import argparse
+    import tempfile
+    ref = refimport.import_reference()
+    import ccsmeth.call_mods_freq_bam as rfb
+    import ccsmeth.models as rmodels
+    rng = np.random.default_rng(20261018)
+    n = 1250
+    pos = np.cumsum(rng.integers(2, 120, size=n)).astype(np.int64)
+    cov = rng.integers(1, 31, size=n)
+    ptr = np.concatenate(([0], np.cumsum(cov))).astype(np.int64)
+    ml = np.floor(256 * rng.beta(0.3, 0.3, size=int(ptr[-1]))).clip(0, 255).astype(np.uint8)
+    hap = rng.choice([0, 1, 2], size=int(ptr[-1]), p=[0.4, 0.3, 0.3]).astype(np.uint8)
+    info = {int(pos[i]): [(rfb._cal_mod_prob(int(ml[k])), int(hap[k])) for k in range(ptr[i], ptr[i + 1])] for i in range(n)}
+    save = {"pos": pos, "ptr": ptr, "ml": ml, "hap": hap}
+    drawn = []
+    orig = rmodels.AggrAttRNN.init_hidden
+
+    def recording(self, *a, **k):
+        h = orig(self, *a, **k)
+        drawn.append(tuple(t.detach().clone() for t in h) if isinstance(h, tuple) else (h.detach().clone(),))
+        return h
+
+    rmodels.AggrAttRNN.init_hidden = recording
+    try:
+        for tag, mt, hid, layers, extra in (("lstm", "attbilstm", 32, 1, {}), ("gru48x2", "attbigru", 48, 2, {}),
+                                            ("lstm_close", "attbilstm", 32, 1, {"only_close": True})):
+            torch.manual_seed(97 + hid + layers)
+            m = ref.models.AggrAttRNN(11, layers, 1, 0, hid, binsize=20, model_type=mt, device="cpu")
+            with tempfile.NamedTemporaryFile(suffix=".ckpt") as f:
+                torch.save(m.state_dict(), f.name)
+                a = argparse.Namespace(call_mode="aggregate", cov_cf=4, bin_size=20, prob_cf=0.0, no_amb_cov=False,
+                                       no_hap=False, seq_len=11, layer_rnn=layers, class_num=1, hid_rnn=hid, model_type=mt,
+                                       aggre_model=f.name, only_close=False, discrete=False, tseed=1234)
+                for k, v in extra.items():
+                    setattr(a, k, v)
+                drawn.clear()
+                res = rfb._call_modfreq_of_one_region(info, a)
+            out = np.full((3, n, 3), np.nan)
+            for i, r in enumerate(res):
+                for g in range(3):
+                    if r[1 + g] is not None:
+                        out[g, i] = [float(x) for x in r[1 + g]]
+            save[tag] = out
+            if extra:  # same seed, same constructor, same site counts: the draws repeat those of the plain case
+                assert np.array_equal(torch.cat([d[0] for d in drawn], dim=1).numpy(), save["lstm_h0"])
+                continue
+            save[tag + "_h0"] = torch.cat([d[0] for d in drawn], dim=1).numpy()
+            if mt == "attbilstm":
+                save[tag + "_c0"] = torch.cat([d[1] for d in drawn], dim=1).numpy()
+            save[tag + "_sizes"] = np.array([d[0].shape[1] for d in drawn], dtype=np.int64)
+            if not extra:
+                for k, v in m.state_dict().items():
+                    save[tag + ".sd." + k] = v.detach().numpy()
+            print("aggr_variants %s: mean freq %.4f" % (tag, np.nanmean(out[0, :, 2])))
+    finally:
+        rmodels.AggrAttRNN.init_hidden = orig
+    np.savez_compressed(os.path.join(OUT, "aggr_variants.npz"), **save)
 
 
 def gen_lstm():
@@ -505,10 +569,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pileup":
         gen_pileup()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "aggr_variants":
+        gen_aggr_variants()
+        sys.exit(0)
     save_ckpts()
     gen_att2s()
     gen_aggr()
     gen_pileup()
+    gen_aggr_variants()
     gen_lstm()
     gen_2s2()
     gen_transenc()

@@ -139,6 +139,32 @@ def test_aggr_fused_kernel_vs_oracle_and_layerwise_path(ckpt_aggr, n, monkeypatc
     assert np.abs(fused[:k] - ref).max() <= 1e-5
 
 
+@pytest.mark.parametrize("mt,hid,layers", [("attbilstm", 32, 1), ("attbilstm", 64, 2), ("attbigru", 48, 2)])
+def test_aggr_other_cells_and_shapes_vs_oracle(mt, hid, layers):
+    """AggrAttRNN outside the fused kernel -- the LSTM cell (ccsm_forward_aggr_lstm, initial state (h0, c0)) and other
+    --hid_rnn / --layer_rnn -- on seeded random weights against the numpy oracle (itself pinned to the reference's
+    region caller for these model types, tests/test_pileup_cpu.py)."""
+    from ccsmeth_b200.models import AggrAttRNN
+    torch.manual_seed(11)
+    m = AggrAttRNN(11, layers, 1, 0, hid, binsize=20, model_type=mt, device=0)
+    sd = {k: v.numpy().copy() for k, v in m.state_dict().items()}
+    m = m.cuda(0).eval()
+    rng = np.random.default_rng(7)
+    n = 777
+    histos = rng.random((n, 11, 20)).astype(np.float32)
+    offsets = rng.integers(0, 1500, (n, 11)).astype(np.float32)
+    h0 = rng.standard_normal((2 * layers, n, hid)).astype(np.float32)
+    c0 = rng.standard_normal((2 * layers, n, hid)).astype(np.float32)
+    lstm = mt == "attbilstm"
+    state = (torch.from_numpy(h0), torch.from_numpy(c0)) if lstm else torch.from_numpy(h0)
+    out = m(torch.from_numpy(offsets), torch.from_numpy(histos), h0=state).cpu().numpy()
+    ref = aggr_numpy.forward(sd, offsets, histos, (h0, c0) if lstm else h0, num_layers=layers, dtype=np.float64)
+    assert np.abs(out - ref).max() <= 2e-5
+    if lstm:
+        with pytest.raises(ValueError):
+            m(torch.from_numpy(offsets), torch.from_numpy(histos), h0=torch.from_numpy(h0))
+
+
 def test_set_weight_rejects_wrong_shape(model):
     import ctypes
     from ccsmeth_b200 import _lib

@@ -129,3 +129,57 @@ def test_edge_regions_against_the_oracle(model, ckpt_aggr):
     assert n_high == (2, 0, 0)
     cov_d, _, _ = model.pileup_finish()
     assert list(cov_d[0]) == [5, 6] and (cov_d[1:] == -1).all()
+
+
+@pytest.mark.parametrize("tag,sdtag,mt,hid,layers,kw", [
+    ("lstm", "lstm", "attbilstm", 32, 1, {}),
+    ("gru48x2", "gru48x2", "attbigru", 48, 2, {}),
+    ("lstm_close", "lstm", "attbilstm", 32, 1, {"only_close": True}),
+])
+def test_other_aggregate_models_match_the_reference_region_caller(tag, sdtag, mt, hid, layers, kw):
+    """--model_type attbilstm and --hid_rnn 48 --layer_rnn 2 (outside the fused kernel: materialised windows + the
+    layer-by-layer fp32 kernels) against the reference's region caller on seeded random weights, same (h0, c0)."""
+    v = load_npz("aggr_variants.npz")
+    m = AggrAttRNN(11, layers, 1, 0, hid, binsize=20, model_type=mt, device=0)
+    m.load_state_dict({k[len(sdtag) + 4:]: torch.from_numpy(v[k]) for k in v if k.startswith(sdtag + ".sd.")})
+    m = m.cuda(0).eval()
+    n_high = m.pileup_begin(v["pos"], v["ptr"], v["ml"], v["hap"], call_mode="aggregate", cov_cf=4, **kw)
+    assert sum(n_high) == v[sdtag + "_h0"].shape[1]
+    states, off = [], 0
+    for nh in n_high:
+        h0 = torch.from_numpy(np.ascontiguousarray(v[sdtag + "_h0"][:, off:off + nh]))
+        if mt == "attbilstm":
+            states.append((h0, torch.from_numpy(np.ascontiguousarray(v[sdtag + "_c0"][:, off:off + nh]))))
+        else:
+            states.append(h0)
+        off += nh
+    res = _call_modfreq_of_one_region(_info(v), _args(**kw), m, h0=states)
+    out, ref = _pack(res, len(v["pos"])), v[tag]
+    _same(out[..., 0], ref[..., 0])
+    _same(out[..., 2], ref[..., 2], tol=2e-6)
+    _same(out[..., 1], ref[..., 1], tol=0.0101)
+    # the reference's own draw order reproduced from the seed: h0 (then c0) per 1024-site slice, group after group
+    if not kw:
+        from ccsmeth_b200.call_freqb import draw_region_h0
+        a = argparse.Namespace(tseed=1234, seq_len=11, layer_rnn=layers, class_num=1, hid_rnn=hid, bin_size=20, model_type=mt)
+        drawn = draw_region_h0(a, n_high)
+        first = drawn[0][0] if mt == "attbilstm" else drawn[0]
+        assert np.array_equal(first.numpy(), v[sdtag + "_h0"][:, :n_high[0]])
+
+
+def test_windows_path_agrees_with_the_fused_kernel(g, model, monkeypatch):
+    """The shipped model through the generic path (CCSM_AGGR_UNFUSED is honoured by the windowed forward only, so build
+    the windows on the host and compare with the in-kernel windows of the pileup call)."""
+    from oracle import aggr_numpy
+    n_high = model.pileup_begin(g["pos"], g["ptr"], g["ml"], g["hap"], call_mode="aggregate", no_hap=True)
+    h0 = torch.randn(2, n_high[0], 32, generator=torch.Generator().manual_seed(3))
+    _, _, freq = model.pileup_finish([h0, None, None])
+    cov = np.diff(g["ptr"])
+    hi = np.nonzero(cov >= 4)[0]
+    histos = [pileup_numpy.normalized_histo([pileup_numpy.cal_mod_prob(int(x)) for x in g["ml"][g["ptr"][i]:g["ptr"][i + 1]]])
+              for i in hi]
+    pm, hm = aggr_numpy.build_windows(g["pos"][hi], histos)
+    monkeypatch.setenv("CCSM_AGGR_UNFUSED", "1")
+    raw = model(torch.from_numpy(np.ascontiguousarray(pm, dtype=np.float32)),
+                torch.from_numpy(np.ascontiguousarray(hm, dtype=np.float32)), h0=h0).cpu().numpy()
+    assert np.abs(aggr_numpy.postprocess(raw)[:, 0] - freq[0][hi]).max() <= 2e-6
