@@ -26,6 +26,7 @@ KIND_ATT2S, KIND_AGGR = 0, 1
 PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x3": 3, "fp16": 4}
 FEAT_NPASS, FEAT_STDS, FEAT_SN, FEAT_MAP, CELL_LSTM, MODEL_2S2, MODEL_TRANSENC = 1, 2, 4, 8, 16, 32, 64
 AGGR_LSTM = 0x100
+BGZF_RLE = 0x100
 
 EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_create", "ccsm_destroy",
            "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",

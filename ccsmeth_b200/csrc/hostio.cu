@@ -52,22 +52,28 @@ static int scan_blocks(const uint8_t* src, int64_t n, std::vector<BgzfBlock>& ou
   return 0;
 }
 
-template <class F>
-static void run_team(int threads, int64_t n_items, F&& fn) {
+// A team of `threads` workers (the caller is one of them); each worker pulls item indices from `next` itself, so it
+// can keep per-thread state (a zlib stream) across items.
+template <class W>
+static void run_workers(int threads, int64_t n_items, W&& worker) {
   if (threads < 1) threads = 1;
   if ((int64_t)threads > n_items) threads = (int)(n_items > 0 ? n_items : 1);
   std::atomic<int64_t> next{0};
-  auto body = [&]() {
+  std::vector<std::thread> team;
+  for (int t = 1; t < threads; ++t) team.emplace_back([&]() { worker(next); });
+  worker(next);
+  for (auto& t : team) t.join();
+}
+
+template <class F>
+static void run_team(int threads, int64_t n_items, F&& fn) {
+  run_workers(threads, n_items, [&](std::atomic<int64_t>& next) {
     for (;;) {
       const int64_t i = next.fetch_add(1);
       if (i >= n_items) break;
       fn(i);
     }
-  };
-  std::vector<std::thread> team;
-  for (int t = 1; t < threads; ++t) team.emplace_back(body);
-  body();
-  for (auto& t : team) t.join();
+  });
 }
 
 }  // namespace ccsm
@@ -107,23 +113,29 @@ int64_t ccsm_bgzf_inflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
     return CCSM_EINVAL;
   }
   std::atomic<int> bad{0};
-  run_team(threads, (int64_t)blocks.size(), [&](int64_t i) {
-    const BgzfBlock& b = blocks[i];
-    if (b.isize == 0) return;
+  const int64_t nblk = (int64_t)blocks.size();
+  run_workers(threads, nblk, [&](std::atomic<int64_t>& next) {  // one inflate state per team thread
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-    zs.next_in = const_cast<Bytef*>(src + b.src_off);
-    zs.avail_in = (uInt)b.clen;
-    zs.next_out = dst + b.dst_off;
-    zs.avail_out = (uInt)b.isize;
-    const int rc = inflate(&zs, Z_FINISH);
-    if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= nblk) break;
+      const BgzfBlock& b = blocks[i];
+      if (b.isize == 0) continue;
+      if (inflateReset(&zs) != Z_OK) { bad = 1; break; }
+      zs.next_in = const_cast<Bytef*>(src + b.src_off);
+      zs.avail_in = (uInt)b.clen;
+      zs.next_out = dst + b.dst_off;
+      zs.avail_out = (uInt)b.isize;
+      const int rc = inflate(&zs, Z_FINISH);
+      if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
+      // the CRC32 of the block guards against silent corruption, like htslib
+      const uint8_t* t = src + b.src_off + b.clen;
+      const uint32_t want = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+      if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.dst_off, (uInt)b.isize) != want) bad = 1;
+    }
     inflateEnd(&zs);
-    // the CRC32 of the block guards against silent corruption, like htslib
-    const uint8_t* t = src + b.src_off + b.clen;
-    const uint32_t want = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
-    if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.dst_off, (uInt)b.isize) != want) bad = 1;
   });
   if (bad) {
     set_error("ccsm_bgzf_inflate: corrupt BGZF block (inflate or CRC32 failed)");
@@ -143,37 +155,48 @@ int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
     set_error("ccsm_bgzf_deflate: bad argument (dst_cap must be >= ccsm_bgzf_deflate_bound)");
     return CCSM_EINVAL;
   }
+  const int strategy = (level & CCSM_BGZF_RLE) ? Z_RLE : Z_DEFAULT_STRATEGY;
+  level &= 0xff;
+  if (level > 9) {
+    set_error("ccsm_bgzf_deflate: level %d out of range", level);
+    return CCSM_EINVAL;
+  }
   const int64_t kBlock = 65280, kSlot = 65280 + 1024;
   const int64_t nblk = (src_bytes + kBlock - 1) / kBlock;
   std::vector<int32_t> sizes((size_t)nblk, 0);
-  // each block is compressed into its own slot at the END of dst, then compacted to the front in order
-  std::vector<uint8_t> scratch((size_t)(nblk * kSlot));
+  // block i is compressed into its own slot dst + i * kSlot (the bound reserves one slot per block), then the blocks
+  // are compacted to the front in order; one deflate state per team thread, reset between blocks
   std::atomic<int> bad{0};
-  run_team(threads, nblk, [&](int64_t i) {
-    const uint8_t* in = src + i * kBlock;
-    const int64_t in_n = std::min<int64_t>(kBlock, src_bytes - i * kBlock);
-    uint8_t* out = scratch.data() + i * kSlot;
-    static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-    memcpy(out, hdr, 16);
+  run_workers(threads, nblk, [&](std::atomic<int64_t>& next) {
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
-    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
-    zs.next_in = const_cast<Bytef*>(in);
-    zs.avail_in = (uInt)in_n;
-    zs.next_out = out + 18;
-    zs.avail_out = (uInt)(kSlot - 18 - 8);
-    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) bad = 1;
-    const int64_t clen = (int64_t)zs.total_out;
+    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 9, strategy) != Z_OK) { bad = 1; return; }
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= nblk) break;
+      const uint8_t* in = src + i * kBlock;
+      const int64_t in_n = std::min<int64_t>(kBlock, src_bytes - i * kBlock);
+      uint8_t* out = dst + i * kSlot;
+      static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+      memcpy(out, hdr, 16);
+      if (deflateReset(&zs) != Z_OK) { bad = 1; break; }
+      zs.next_in = const_cast<Bytef*>(in);
+      zs.avail_in = (uInt)in_n;
+      zs.next_out = out + 18;
+      zs.avail_out = (uInt)(kSlot - 18 - 8);
+      if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { bad = 1; break; }
+      const int64_t clen = (int64_t)zs.total_out;
+      const int64_t bsize = clen + 26;  // whole block; header stores bsize - 1
+      if (bsize > 65536) { bad = 1; break; }
+      out[16] = (uint8_t)((bsize - 1) & 0xff);
+      out[17] = (uint8_t)((bsize - 1) >> 8);
+      const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in, (uInt)in_n);
+      uint8_t* t = out + 18 + clen;
+      for (int k = 0; k < 4; ++k) t[k] = (uint8_t)(crc >> (8 * k));
+      for (int k = 0; k < 4; ++k) t[4 + k] = (uint8_t)((uint32_t)in_n >> (8 * k));
+      sizes[(size_t)i] = (int32_t)bsize;
+    }
     deflateEnd(&zs);
-    const int64_t bsize = clen + 26;  // whole block; header stores bsize - 1
-    if (bsize > 65536) { bad = 1; return; }
-    out[16] = (uint8_t)((bsize - 1) & 0xff);
-    out[17] = (uint8_t)((bsize - 1) >> 8);
-    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in, (uInt)in_n);
-    uint8_t* t = out + 18 + clen;
-    for (int k = 0; k < 4; ++k) t[k] = (uint8_t)(crc >> (8 * k));
-    for (int k = 0; k < 4; ++k) t[4 + k] = (uint8_t)((uint32_t)in_n >> (8 * k));
-    sizes[(size_t)i] = (int32_t)bsize;
   });
   if (bad) {
     set_error("ccsm_bgzf_deflate: deflate failed");
@@ -181,7 +204,7 @@ int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
   }
   int64_t o = 0;
   for (int64_t i = 0; i < nblk; ++i) {
-    memcpy(dst + o, scratch.data() + i * kSlot, (size_t)sizes[(size_t)i]);
+    if (o != i * kSlot) memmove(dst + o, dst + i * kSlot, (size_t)sizes[(size_t)i]);
     o += sizes[(size_t)i];
   }
   return o;

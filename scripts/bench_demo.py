@@ -21,14 +21,18 @@ ckpt = os.path.join(out_dir, "model_v3.ckpt")
 torch.save(OrderedDict((k, torch.from_numpy(v)) for k, v in ck.items()), ckpt)
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
 rep = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ["device", "reference"]  # h0 modes of the replicated run
+# optional sweep over (host threads, --device_batch) for the replicated run, e.g. "16:16,8:16,8:32"
+# a third field picks --bam_compress (rle | zlib), e.g. "16:16:zlib"
+sweep = [tuple(kv.split(":")) for kv in sys.argv[4].split(",")] if len(sys.argv) > 4 else []
 demo = os.path.join(ROOT, "tests", "golden", "demo", "hg002.chr20_demo.hifi.bam")
 
 
-def run(inp, extra, reps, out_prefix=None):
+def run(inp, extra, reps, out_prefix=None, threads=None):
     times = []
     for _ in range(reps):
         args = cm.build_parser().parse_args(["-i", inp, "-m", ckpt, "-o", out_prefix or os.path.join(out_dir, "demo_out"),
-                                             "--precision", prec, "--threads", str(os.cpu_count())] + extra)
+                                             "--precision", prec, "--threads", str(threads or os.cpu_count())] + extra)
         t0 = time.perf_counter()
         counts, path = cm.call_mods(args)
         times.append(time.perf_counter() - t0)
@@ -58,7 +62,14 @@ if rep > 0:
             wr.write_raw(bytes(raw))
     wr.close()
     res["big"] = {"workload": "demo reads x%d (%d reads, %.1f MB BAM)" % (rep, rep * len(recs), os.path.getsize(big) / 1e6)}
-    for mode in ("device", "reference"):
+    for mode in modes:
         c, t = run(big, ["--h0", mode], 2, os.path.join(tmp, "out"))
         res["big"]["h0_" + mode] = {"sites": c["sites"], "seconds_runs": t, "sites_per_s": c["sites"] / min(t)}
+    for item in sweep:
+        thr, db, comp = int(item[0]), int(item[1]), (item[2] if len(item) > 2 else "rle")
+        c, t = run(big, ["--h0", "device", "--device_batch", str(db), "--bam_compress", comp], 3, os.path.join(tmp, "out"),
+                   threads=thr)
+        res["big"]["threads%d_device_batch%d_%s" % (thr, db, comp)] = {
+            "seconds_runs": t, "sites_per_s": c["sites"] / min(t), "stages": dict(cm.TIMING),
+            "out_bytes": os.path.getsize(os.path.join(tmp, "out.modbam.bam"))}
 print(json.dumps(res))
