@@ -33,7 +33,7 @@ EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_
            "ccsm_forward_att2s_host", "ccsm_forward_att2s_lstm", "ccsm_forward_aggr", "ccsm_forward_aggr_lstm", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
            "ccsm_debug_umma_pair_gemm", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
-           "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound",
+           "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_inflate_stats", "ccsm_bgzf_deflate_bound",
            "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records", "ccsm_bam_modcalls", "ccsm_pileup_luts",
            "ccsm_pileup_begin_host", "ccsm_pileup_finish_host", "ccsm_pileup_finish_lstm_host"]
 
@@ -180,9 +180,11 @@ def load():
         lib.ccsm_reads_forward_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         lib.ccsm_bgzf_inflated_size.argtypes = [vp, i64, ctypes.POINTER(i64)]
         lib.ccsm_bgzf_inflate.argtypes = [vp, i64, vp, i64, i32, ctypes.POINTER(i64)]
+        lib.ccsm_bgzf_inflate_stats.argtypes = [ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        lib.ccsm_bgzf_inflate_stats.restype = None
         lib.ccsm_bgzf_deflate_bound.argtypes = [i64]
         lib.ccsm_bgzf_deflate.argtypes = [vp, i64, vp, i64, i32, i32]
-        for fn in ("ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_deflate_bound", "ccsm_bgzf_deflate"):
+        for fn in ("ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_inflate_stats", "ccsm_bgzf_deflate_bound", "ccsm_bgzf_deflate"):
             getattr(lib, fn).restype = i64
         lib.ccsm_pileup_luts.argtypes = [ctypes.POINTER(PileupOpts), i32, vp, vp]
         lib.ccsm_pileup_begin_host.argtypes = [vp, ctypes.POINTER(PileupOpts), i64, vp, vp, vp, vp, vp]

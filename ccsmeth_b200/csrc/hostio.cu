@@ -2,6 +2,7 @@
 // through pysam (`pysam.AlignmentFile(..., threads=)`, reference extract_features.py:60-73,
 // call_modifications.py:410-462); the call_mods pipeline needs it at GPU speed, so blocks are inflated /
 // deflated in parallel with zlib.  Pure host code: no CUDA calls.
+#include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
 
@@ -9,9 +10,14 @@
 #include <thread>
 #include <vector>
 
+#include <memory>
+
 #include "ccsm_internal.h"
+#include "inflate_fast.h"
 
 namespace ccsm {
+
+static std::atomic<int64_t> g_inflate_fast{0}, g_inflate_zlib{0};
 
 struct BgzfBlock {
   int64_t src_off;   // start of the deflate payload
@@ -114,34 +120,59 @@ int64_t ccsm_bgzf_inflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
   }
   std::atomic<int> bad{0};
   const int64_t nblk = (int64_t)blocks.size();
-  run_workers(threads, nblk, [&](std::atomic<int64_t>& next) {  // one inflate state per team thread
+  // CCSM_INFLATE=zlib keeps every block on zlib (A/B timing, cross-checks)
+  const char* env = getenv("CCSM_INFLATE");
+  const bool use_fast = !(env && strcmp(env, "zlib") == 0);
+  run_workers(threads, nblk, [&](std::atomic<int64_t>& next) {  // one decoder state per team thread
+    std::unique_ptr<FastInflate> fast(use_fast ? new (std::nothrow) FastInflate() : nullptr);
     z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+    bool zs_ready = false;
+    int64_t n_fast = 0, n_zlib = 0;
     for (;;) {
       const int64_t i = next.fetch_add(1);
       if (i >= nblk) break;
       const BgzfBlock& b = blocks[i];
       if (b.isize == 0) continue;
-      if (inflateReset(&zs) != Z_OK) { bad = 1; break; }
+      // the CRC32 of the block guards against silent corruption, like htslib
+      const uint8_t* t = src + b.src_off + b.clen;
+      const uint32_t want = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+      if (fast && fast->run(src + b.src_off, b.clen, dst + b.dst_off, b.isize) &&
+          (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.dst_off, (uInt)b.isize) == want) {
+        ++n_fast;
+        continue;
+      }
+      // zlib decodes whatever the table decoder rejected (and reports real corruption)
+      if (!zs_ready) {
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; break; }
+        zs_ready = true;
+      } else if (inflateReset(&zs) != Z_OK) {
+        bad = 1;
+        break;
+      }
       zs.next_in = const_cast<Bytef*>(src + b.src_off);
       zs.avail_in = (uInt)b.clen;
       zs.next_out = dst + b.dst_off;
       zs.avail_out = (uInt)b.isize;
       const int rc = inflate(&zs, Z_FINISH);
       if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
-      // the CRC32 of the block guards against silent corruption, like htslib
-      const uint8_t* t = src + b.src_off + b.clen;
-      const uint32_t want = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
       if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.dst_off, (uInt)b.isize) != want) bad = 1;
+      ++n_zlib;
     }
-    inflateEnd(&zs);
+    if (zs_ready) inflateEnd(&zs);
+    g_inflate_fast += n_fast;
+    g_inflate_zlib += n_zlib;
   });
   if (bad) {
     set_error("ccsm_bgzf_inflate: corrupt BGZF block (inflate or CRC32 failed)");
     return CCSM_EINVAL;
   }
   return total;
+}
+
+void ccsm_bgzf_inflate_stats(int64_t* fast_blocks, int64_t* zlib_blocks) {
+  if (fast_blocks) *fast_blocks = g_inflate_fast.load();
+  if (zlib_blocks) *zlib_blocks = g_inflate_zlib.load();
 }
 
 int64_t ccsm_bgzf_deflate_bound(int64_t src_bytes) {

@@ -288,7 +288,10 @@ int  ccsm_pileup_finish_lstm_host(ccsm_model* m, const float* const* h0, const f
  * The reference reads and writes BAM through pysam/htslib with `threads=` (extract_features.py:60-73,
  * call_modifications.py:410-462).  Pure host code; buffers are host memory.
  * ccsm_bgzf_inflated_size: sum of the inflated sizes of the COMPLETE blocks found in src; *consumed = their bytes.
- * ccsm_bgzf_inflate:       inflates those blocks into dst (CRC32 checked); returns bytes written.
+ * ccsm_bgzf_inflate:       inflates those blocks into dst (CRC32 checked); returns bytes written.  Blocks go through
+ *                          the library's table decoder (csrc/inflate_fast.h); zlib decodes any block it rejects or whose
+ *                          CRC32 / size does not match afterwards (CCSM_INFLATE=zlib: zlib for every block).
+ * ccsm_bgzf_inflate_stats: blocks decoded by the table decoder / by zlib so far in this process.
  * ccsm_bgzf_deflate:       cuts src into 65280-byte blocks, deflates them in parallel, writes the concatenated
  *                          BGZF blocks (no EOF marker) into dst (capacity >= ccsm_bgzf_deflate_bound(src_bytes));
  *                          returns bytes written.  `level` = zlib level 0..9, optionally ORed with CCSM_BGZF_RLE:
@@ -300,6 +303,7 @@ int  ccsm_pileup_finish_lstm_host(ccsm_model* m, const float* const* h0, const f
 int64_t ccsm_bgzf_inflated_size(const uint8_t* src, int64_t src_bytes, int64_t* consumed);
 int64_t ccsm_bgzf_inflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, int64_t dst_cap, int32_t threads,
                           int64_t* consumed);
+void    ccsm_bgzf_inflate_stats(int64_t* fast_blocks, int64_t* zlib_blocks);
 int64_t ccsm_bgzf_deflate_bound(int64_t src_bytes);
 int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, int64_t dst_cap, int32_t level,
                           int32_t threads);
