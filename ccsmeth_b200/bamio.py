@@ -114,13 +114,14 @@ def _deflate_block(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
 class BgzfWriter:
     """BGZF writer; ``threads > 1``: blocks are deflated by libccsm's thread team (ccsm_bgzf_deflate).
 
-    strategy "rle" (default): run-length matching + dynamic Huffman (zlib Z_RLE) -- HiFi records are packed bases,
-    qualities and kinetics bytes in which LZ77 finds next to nothing, so this is 3-4x faster than zlib's default
-    strategy for files within 3 % of its size; "zlib": the default strategy at `level` (what htslib does)."""
+    strategy "zlib" (default): zlib's default strategy at `level` (what htslib does; right for text such as bed files);
+    "rle": run-length matching + dynamic Huffman (zlib Z_RLE) -- HiFi records are packed bases, qualities and kinetics
+    bytes in which LZ77 finds next to nothing, so this is 3-4x faster for files within 3 % of the size (BamWriter's
+    default)."""
 
     BLOCK = 65280
 
-    def __init__(self, path, level=6, threads=1, strategy="rle"):
+    def __init__(self, path, level=6, threads=1, strategy="zlib"):
         if strategy not in ("rle", "zlib"):
             raise ValueError("BGZF strategy must be 'rle' or 'zlib'")
         self.f = open(path, "wb")

@@ -358,7 +358,7 @@ def call_freqb(args):
             lines.sort(key=lambda ln: (ln.split("\t", 2)[0], int(ln.split("\t", 2)[1])))
             if args.gzip:
                 from .bamio import BgzfWriter
-                wr = BgzfWriter(p + ".gz", threads=max(1, args.threads))
+                wr = BgzfWriter(p + ".gz", threads=max(1, args.threads), strategy="zlib")  # text: LZ77 pays
                 wr.write("".join(lines).encode("ascii"))
                 wr.close()
                 os.remove(p)
