@@ -362,6 +362,48 @@ def gen_aggr_variants():
     np.savez_compressed(os.path.join(OUT, "aggr_variants.npz"), **save)
 
 
+def gen_cli():
+    """The reference's own argparse definitions of `call_mods` and `call_freqb` (ccsmeth/ccsmeth.py:195-330, 560-650):
+    every flag with its aliases, default, type, choices and action, captured from the parser object the reference's
+    main() builds.  tests/test_cli_cpu.py checks that the ccsmeth_b200 CLIs accept the same command lines."""
+    import argparse
+    import json
+    refimport.import_reference()
+    import ccsmeth.ccsmeth as rmain
+
+    class Captured(Exception):
+        pass
+
+    orig = argparse.ArgumentParser.parse_args
+
+    def capture(self, *a, **k):
+        e = Captured()
+        e.parser = self
+        raise e
+
+    argparse.ArgumentParser.parse_args = capture
+    try:
+        rmain.main()
+    except Captured as e:
+        parser = e.parser
+    finally:
+        argparse.ArgumentParser.parse_args = orig
+    subs = next(a for a in parser._actions if isinstance(a, argparse._SubParsersAction)).choices
+    out = {}
+    for name in ("call_mods", "call_freqb"):
+        flags = []
+        for a in subs[name]._actions:
+            if isinstance(a, argparse._HelpAction):
+                continue
+            flags.append({"flags": list(a.option_strings), "dest": a.dest, "default": a.default,
+                          "type": getattr(a.type, "__name__", None), "choices": list(a.choices) if a.choices else None,
+                          "action": type(a).__name__, "required": bool(a.required)})
+        out[name] = flags
+    with open(os.path.join(OUT, "cli_flags.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("cli_flags: %s" % {k: len(v) for k, v in out.items()})
+
+
 def gen_lstm():
     """Section 8f-4: the reference's ModelAttRNN(model_type="attbilstm2s") -- no checkpoint ships, so a seeded random
     initialisation of a small configuration (hidden 64, 2 layers) is the fixture -- with explicit (h0, c0)."""
@@ -569,6 +611,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pileup":
         gen_pileup()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cli":
+        gen_cli()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "aggr_variants":
         gen_aggr_variants()
         sys.exit(0)
@@ -577,6 +622,7 @@ if __name__ == "__main__":
     gen_aggr()
     gen_pileup()
     gen_aggr_variants()
+    gen_cli()
     gen_lstm()
     gen_2s2()
     gen_transenc()
