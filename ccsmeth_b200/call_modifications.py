@@ -60,16 +60,38 @@ def _batch_feature_list2s(feature_list):
     return (sampleinfo, *cols, labels)
 
 
-def draw_h0_stream(n, batch_size, num_layers, hidden, generator=None):
+def draw_h0_stream(n, batch_size, num_layers, hidden, generator=None, out=None, offset=0):
     """The reference's h0 stream for a hole-batch of n sites processed in ``batch_size`` slices:
-    per slice, strand-1 draw then strand-2 draw.  Returns two (2*layers, n, hidden) float32 tensors."""
-    h0_f = torch.empty(2 * num_layers, n, hidden)
-    h0_r = torch.empty(2 * num_layers, n, hidden)
+    per slice, strand-1 draw then strand-2 draw.  Returns two (2*layers, n, hidden) float32 tensors -- or, with
+    ``out`` = a pair of (2*layers, N, hidden) float32 numpy arrays, writes sites offset..offset+n of them (the
+    caller assembles several hole-batches without further copies).  Each slice is drawn as one contiguous
+    ``torch.randn`` (the reference's call) and placed with a plain memory copy."""
+    if out is None:
+        dst = (np.empty((2 * num_layers, n, hidden), dtype=np.float32),
+               np.empty((2 * num_layers, n, hidden), dtype=np.float32))
+        offset = 0
+    else:
+        dst = out
     for s in range(0, n, batch_size):
         e = min(n, s + batch_size)
-        h0_f[:, s:e] = torch.randn(2 * num_layers, e - s, hidden, generator=generator)
-        h0_r[:, s:e] = torch.randn(2 * num_layers, e - s, hidden, generator=generator)
-    return h0_f, h0_r
+        dst[0][:, offset + s:offset + e] = torch.randn(2 * num_layers, e - s, hidden, generator=generator).numpy()
+        dst[1][:, offset + s:offset + e] = torch.randn(2 * num_layers, e - s, hidden, generator=generator).numpy()
+    if out is None:
+        return torch.from_numpy(dst[0]), torch.from_numpy(dst[1])
+    return out
+
+
+def draw_h0_stream_batches(counts, batch_size, num_layers, hidden, generator=None):
+    """`draw_h0_stream` for consecutive hole-batches of `counts` sites each (the reference's stream restarts its
+    ``batch_size`` slicing at every hole-batch), assembled in place.  -> two (2*layers, sum(counts), hidden) tensors."""
+    total = int(sum(int(c) for c in counts))
+    out = (np.empty((2 * num_layers, total, hidden), dtype=np.float32),
+           np.empty((2 * num_layers, total, hidden), dtype=np.float32))
+    off = 0
+    for c in counts:
+        draw_h0_stream(int(c), batch_size, num_layers, hidden, generator, out=out, offset=off)
+        off += int(c)
+    return torch.from_numpy(out[0]), torch.from_numpy(out[1])
 
 
 def _stack(col, n):

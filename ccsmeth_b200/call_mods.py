@@ -30,7 +30,7 @@ import torch
 from . import VERSION, _lib, parallel
 from .bamio import BamWriter, add_pg_line
 from .bamstream import BamPieceReader, tag_records
-from .call_modifications import draw_h0_stream, load_model
+from .call_modifications import draw_h0_stream_batches, load_model
 from .extract_features import ReadBatch, extract_opts, pack_reads
 from .utils.process_utils import str2bool
 
@@ -100,9 +100,7 @@ def call_reads(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=N
     per_hb = np.bincount(rec_idx // hb, minlength=(len(reads) + hb - 1) // hb)
     n_batches = int(sum((c + args.batch_size - 1) // args.batch_size for c in per_hb))
     if h0 is None and getattr(args, "h0", "reference") == "reference":
-        parts = [draw_h0_stream(int(c), args.batch_size, model.num_layers, model.hidden_size) for c in per_hb if c]
-        h0 = (torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1)) if len(parts) > 1 \
-            else parts[0]
+        h0 = draw_h0_stream_batches(per_hb, args.batch_size, model.num_layers, model.hidden_size)
     t0 = time.perf_counter()
     res = model.reads_forward(h0=h0, want_probs=False)
     _tic("forward", t0)
@@ -180,9 +178,7 @@ def call_piece(model, piece, motifs, args, rank=0, world=1, holeids_e=None, hole
     n_batches = int(((per_hb + args.batch_size - 1) // args.batch_size).sum())
     h0 = None
     if getattr(args, "h0", "reference") == "reference" and getattr(model, "rnn_cell", None) == "gru":
-        parts = [draw_h0_stream(int(c), args.batch_size, model.num_layers, model.hidden_size) for c in per_hb]
-        h0 = (torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1)) if len(parts) > 1 \
-            else parts[0]
+        h0 = draw_h0_stream_batches(per_hb, args.batch_size, model.num_layers, model.hidden_size)
     t0 = time.perf_counter()
     res = model.reads_forward(h0=h0, want_probs=False)
     _tic("forward", t0)

@@ -49,13 +49,16 @@ def draw_initial_states(n, num_layers, hidden_size, lstm=False):
     """The initial states the reference's batch loop draws for n sites: per 1024-site slice one ``torch.randn`` for h0
     and, for the LSTM cell, a second one for c0 (models.py:661-671, call_mods_freq_bam.py:295-301).
     -> h0 (2*layers, n, hidden), or the pair (h0, c0)."""
-    h0 = torch.empty(2 * num_layers, n, hidden_size)
-    c0 = torch.empty(2 * num_layers, n, hidden_size) if lstm else None
+    # each slice is one contiguous torch.randn (the reference's call), placed with a plain memory copy
+    h0 = np.empty((2 * num_layers, n, hidden_size), dtype=np.float32)
+    c0 = np.empty((2 * num_layers, n, hidden_size), dtype=np.float32) if lstm else None
     for s in range(0, n, AGGR_BATCH):
         e = min(n, s + AGGR_BATCH)
-        h0[:, s:e] = torch.randn(2 * num_layers, e - s, hidden_size)
+        h0[:, s:e] = torch.randn(2 * num_layers, e - s, hidden_size).numpy()
         if lstm:
-            c0[:, s:e] = torch.randn(2 * num_layers, e - s, hidden_size)
+            c0[:, s:e] = torch.randn(2 * num_layers, e - s, hidden_size).numpy()
+    h0 = torch.from_numpy(h0)
+    c0 = torch.from_numpy(c0) if lstm else None
     return (h0, c0) if lstm else h0
 
 
