@@ -263,7 +263,7 @@ def call_mods(args):
                          1 if str2bool(args.skip_unmapped) else 0, 1 if str2bool(args.is_sn) else 0)
     # a piece = `device_batch` hole-batches' worth of compressed bytes (about 3 MB per 50 HiFi reads)
     rd = BamPieceReader(args.input, flt, threads=threads,
-                        piece_bytes=max(1, getattr(args, "device_batch", 16)) * args.holes_batch * 65536,
+                        piece_bytes=max(1, getattr(args, "device_batch", 8)) * args.holes_batch * 65536,
                         align_to=args.holes_batch)
     wr = BamWriter(out_modbam, add_pg_line(rd.header_text, VERSION, " ".join(sys.argv)), rd.references, threads=threads,
                    strategy=getattr(args, "bam_compress", "rle"))
@@ -359,7 +359,7 @@ def build_parser():
     p.add_argument("--h0", type=str, default="reference", choices=["reference", "device", "zeros"],
                    help="ccsmeth_b200 only: GRU initial state: the reference's torch.randn stream on the CPU "
                         "(default), N(0,1) drawn on the device (no 12 KB/site transfer), or zeros")
-    p.add_argument("--device_batch", type=int, default=16,
+    p.add_argument("--device_batch", type=int, default=8,
                    help="ccsmeth_b200 only: hole-batches per device call (features are extracted on the GPU for "
                         "this many x --holes_batch reads at once)")
     p.add_argument("--bam_compress", type=str, default="rle", choices=["rle", "zlib"],
