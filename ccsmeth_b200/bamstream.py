@@ -8,6 +8,8 @@ the device's per-site outputs.  Stands in for the pysam reader / writer processe
 (extract_features.py:129-177, call_modifications.py:410-462).
 """
 import ctypes
+import mmap
+import os
 import struct
 
 import numpy as np
@@ -47,10 +49,14 @@ class BamPieceReader:
         self.lib = _lib.load()
         self.f = open(path, "rb")
         self.threads = max(1, threads)
-        self.piece_bytes = piece_bytes
+        self.piece_bytes = max(int(piece_bytes), 1)
         self.align_to = max(1, align_to)
         self.filter = bam_filter
-        self.ctail = b""      # compressed bytes of an incomplete BGZF block
+        # the compressed file is mapped, not read: the thread team inflates straight out of the page cache
+        self.size = os.fstat(self.f.fileno()).st_size
+        self.mm = mmap.mmap(self.f.fileno(), 0, access=mmap.ACCESS_READ) if self.size else None
+        self.src = np.frombuffer(self.mm, dtype=np.uint8) if self.size else np.zeros(0, dtype=np.uint8)
+        self.pos = 0          # next compressed byte
         self.carry = np.zeros(0, dtype=np.uint8)  # inflated bytes not yet consumed
         self.eof = False
         self.n_seen = 0
@@ -59,27 +65,29 @@ class BamPieceReader:
     # -- inflated byte stream
     def _inflate_more(self):
         """Appends the next inflated piece to self.carry; returns False at end of file."""
-        piece = self.f.read(self.piece_bytes)
-        if not piece and not self.ctail:
+        if self.pos >= self.size:
             self.eof = True
             return False
-        src = self.ctail + piece
-        consumed = ctypes.c_int64(0)
-        total = self.lib.ccsm_bgzf_inflated_size(src, len(src), ctypes.byref(consumed))
-        if total < 0:
-            _lib.check(int(total))
-        if consumed.value == 0:
-            if not piece:
+        window = self.piece_bytes
+        while True:
+            n = min(window, self.size - self.pos)
+            base = self.src.ctypes.data + self.pos
+            consumed = ctypes.c_int64(0)
+            total = self.lib.ccsm_bgzf_inflated_size(base, n, ctypes.byref(consumed))
+            if total < 0:
+                _lib.check(int(total))
+            if consumed.value > 0:
+                break
+            if self.pos + n >= self.size:
                 raise ValueError("truncated BGZF block at end of file")
-            self.ctail = src
-            return True
+            window *= 2  # not even one complete block in the window
         buf = np.empty(len(self.carry) + int(total), dtype=np.uint8)
         buf[:len(self.carry)] = self.carry
-        got = self.lib.ccsm_bgzf_inflate(src, len(src), buf[len(self.carry):].ctypes.data, int(total), self.threads,
+        got = self.lib.ccsm_bgzf_inflate(base, consumed.value, buf[len(self.carry):].ctypes.data, int(total), self.threads,
                                          ctypes.byref(consumed))
         if got < 0:
             _lib.check(int(got))
-        self.ctail = src[consumed.value:]
+        self.pos += consumed.value
         self.carry = buf
         return True
 
@@ -153,6 +161,13 @@ class BamPieceReader:
                 return
 
     def close(self):
+        self.src = None  # drop the exported buffer before the mapping goes away
+        if self.mm is not None:
+            try:
+                self.mm.close()
+            except BufferError:  # a caller still holds a view; the mapping is released with it
+                pass
+            self.mm = None
         self.f.close()
 
 
