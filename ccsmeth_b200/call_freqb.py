@@ -211,28 +211,34 @@ def call_region(model, args, contig_seq, ref_name, pileups, motifs_filter):
         if args.call_mode == "aggregate" and getattr(args, "h0", "reference") == "reference":
             h0 = draw_region_h0(args, n_high)
         cov, cnt, freq, kind = model.pileup_finish(h0, with_kind=True)
-        for i, p in enumerate(refpos):
-            p = int(p)
-            if motifs_filter is not None:
+        keep = np.ones(len(refpos), dtype=bool)
+        if motifs_filter is not None:
+            for i, p in enumerate(refpos.tolist()):
                 if ch == "+":
-                    if contig_seq[p + fwd_s:p + fwd_e] not in mset:
-                        continue
-                elif complement_seq(contig_seq[p + rev_s:p + rev_e]) not in mset:
-                    continue
-            for g in range(3):
-                k = kind[g, i]
-                if k == 0:
-                    continue
-                # the value types the reference holds (they decide how str() prints them in the output files)
-                if k == 1:
-                    c, fr = int(cnt[g, i]), float(freq[g, i])
-                elif k == 2:
-                    c, fr = np.float64(cnt[g, i]), float(freq[g, i])
+                    keep[i] = contig_seq[p + fwd_s:p + fwd_e] in mset
                 else:
-                    c, fr = np.float32(cnt[g, i]), np.float32(freq[g, i])
+                    keep[i] = complement_seq(contig_seq[p + rev_s:p + rev_e]) in mset
+        for g in range(3):
+            idx = np.nonzero(keep & (kind[g] != 0))[0]
+            if len(idx) == 0:
+                continue
+            pos_l, cov_l, kind_l = refpos[idx].tolist(), cov[g, idx].tolist(), kind[g, idx].tolist()
+            # the value types the reference holds (they decide how str() prints them in the output files):
+            # kind 1 int count / float freq, kind 2 np.float64 count, kind 3 np.float32 count and freq (model path)
+            cnt_g, freq_g = cnt[g, idx], freq[g, idx]
+            cnt_i, freq_f = cnt_g.astype(np.int64).tolist(), freq_g.tolist()
+            cnt32, freq32 = cnt_g.astype(np.float32), freq_g.astype(np.float32)
+            out = beds[g]
+            for j, k in enumerate(kind_l):
+                if k == 1:
+                    c, fr = cnt_i[j], freq_f[j]
+                elif k == 2:
+                    c, fr = cnt_g[j], freq_f[j]
+                else:
+                    c, fr = cnt32[j], freq32[j]
                     if args.discrete:
-                        c, _, fr = discretize_score(fr, int(cov[g, i]))
-                beds[g].append((ref_name, p, ch, int(cov[g, i]), c, fr))
+                        c, _, fr = discretize_score(fr, cov_l[j])
+                out.append((ref_name, pos_l[j], ch, cov_l[j], c, fr))
     return beds
 
 
@@ -245,6 +251,19 @@ def write_one_line(beditem, wf, is_bed):
     else:
         wf.write("\t".join([ref_name, str(refpos), str(refpos + 1), strand, ".", ".", str(met), str(cov - met),
                             str(cov), str(round(metprob + 0.000001, 4)), "."]) + "\n")
+
+
+def write_lines(beditems, wf, is_bed):
+    """`write_one_line` for a whole list with one write call (same text, line for line; `!s` because an empty format
+    spec prints NumPy float32 scalars with double precision digits, unlike the reference's str())."""
+    if is_bed:
+        wf.write("".join(
+            f"{ref_name}\t{refpos}\t{refpos + 1}\t.\t{cov}\t{strand}\t{refpos}\t{refpos + 1}\t0,0,0\t{cov}\t"
+            f"{int(round(metprob * 100 + 0.001, 0))}\n" for ref_name, refpos, strand, cov, met, metprob in beditems))
+    else:
+        wf.write("".join(
+            f"{ref_name}\t{refpos}\t{refpos + 1}\t{strand}\t.\t.\t{met!s}\t{cov - met!s}\t{cov}\t"
+            f"{round(metprob + 0.000001, 4)!s}\t.\n" for ref_name, refpos, strand, cov, met, metprob in beditems))
 
 
 def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1, piece_bytes=48 << 20):
@@ -342,8 +361,7 @@ def call_freqb(args):
     n_lines = [0, 0, 0]
     for _, *beds in iter_region_results(args, model, dnacontigs, args.input_bam, rank, world):
         for g in range(3):
-            for item in beds[g]:
-                write_one_line(item, files[g], args.bed)
+            write_lines(beds[g], files[g], args.bed)
             n_lines[g] += len(beds[g])
     for f, p, n in zip(files, paths, n_lines):
         f.close()

@@ -198,3 +198,21 @@ def test_host_chain_with_the_pileup_oracle_reproduces_the_reference_files(ref_ou
                     cf.write_one_line(item, b, False)
             parts.append(b.getvalue().splitlines())
         assert all(parts) and sorted(sum(parts, [])) == sorted(ref_out["count.all.freq.txt"].splitlines())
+
+
+def test_write_lines_prints_what_write_one_line_prints():
+    """The list writer must keep the reference's str() formatting of every value type (int, float, np.float64,
+    np.float32 -- the last one prints differently through an empty format spec)."""
+    rng = np.random.default_rng(0)
+    items = [("c", 0, "+", 5, 0, 0.0), ("c", 1, "+", 5, 5, 1.0), ("c", 2, "-", 7, np.float32(0.0), np.float32(1.0))]
+    for i in range(3000):
+        cov, f = int(rng.integers(1, 80)), float(rng.random())
+        items.append(("chr1", 3 * i, "+", cov, int(f * cov), int(f * cov) / cov))
+        items.append(("chr1", 3 * i + 1, "-", cov, np.float64(round(cov * f, 2)), f))
+        items.append(("chrX", 3 * i + 2, "+", cov, np.float32(round(cov * np.float32(f), 2)), np.float32(round(f, 6))))
+    for bed in (False, True):
+        a, b = io.StringIO(), io.StringIO()
+        for it in items:
+            cf.write_one_line(it, a, bed)
+        cf.write_lines(items, b, bed)
+        assert a.getvalue() == b.getvalue()
