@@ -5,8 +5,8 @@
 // run-length strategy (profiles/r01_demo_pipeline_sweep.json).  HiFi records are literal-heavy (packed bases,
 // qualities, kinetics bytes), where zlib's inflate decodes one symbol per loop iteration from a 32-bit bit buffer.
 // This decoder keeps a 64-bit bit buffer refilled with one unaligned load, uses an 11-bit primary table for the
-// literal/length code (8-bit for distances) with second-level tables for longer codes, and decodes up to three
-// literals per refill.  Every BGZF block carries a CRC32 and its inflated size: the caller checks both and falls
+// literal/length code (8-bit for distances) with second-level tables for longer codes, and a literal fast table that
+// yields two literals per lookup when both codes fit the primary index (up to eight literals per refill).  Every BGZF block carries a CRC32 and its inflated size: the caller checks both and falls
 // back to zlib for any block this decoder rejects, so a decoder bug cannot produce silently wrong records.
 #pragma once
 #include <stdint.h>
@@ -42,10 +42,12 @@ class FastInflate {
           }
           lt_ = fixed_lt_;
           dt_ = fixed_dt_;
+          pt_ = fixed_pt_;
         } else if (type == 2) {
           if (!dynamic_header()) return false;
           lt_ = dyn_lt_;
           dt_ = dyn_dt_;
+          pt_ = dyn_pt_;
         } else {
           return false;
         }
@@ -78,6 +80,7 @@ class FastInflate {
     return v;  // little-endian hosts only (x86-64 / aarch64)
   }
   static void store64(uint8_t* p, uint64_t v) { memcpy(p, &v, 8); }
+  static void store16(uint8_t* p, uint16_t v) { memcpy(p, &v, 2); }
 
   void consume(int n) {
     bitbuf_ >>= n;
@@ -197,6 +200,25 @@ class FastInflate {
     *kind = K_LITERAL; *extra = 0; *value = sym;
   }
 
+  // Literal fast table for the hot loop: pt[i] = total code bits | count << 4 | lit1 << 8 | lit2 << 16, where count is
+  // 2 when the LBITS bits i hold two complete literal codes, 1 for one, 0 when the first symbol is not a primary-table
+  // literal (the loop then goes through lt).
+  static void build_pairs(const uint32_t* lt, uint32_t* pt) {
+    for (uint32_t i = 0; i < (1u << LBITS); ++i) {
+      const uint32_t e = lt[i];
+      if (!(e & LIT_FLAG)) {
+        pt[i] = 0;
+        continue;
+      }
+      const uint32_t l1 = e & 15;
+      const uint32_t e2 = lt[i >> l1];  // the bits after the first code, zero-extended
+      if ((e2 & LIT_FLAG) && l1 + (e2 & 15) <= (uint32_t)LBITS)
+        pt[i] = (l1 + (e2 & 15)) | (2u << 4) | ((e >> 16) << 8) | ((e2 >> 16) << 16);
+      else
+        pt[i] = l1 | (1u << 4) | ((e >> 16) << 8);
+    }
+  }
+
   void build_fixed() {
     uint8_t lens[288 + 32];
     for (int i = 0; i < 144; ++i) lens[i] = 8;
@@ -206,6 +228,7 @@ class FastInflate {
     for (int i = 0; i < 32; ++i) lens[288 + i] = 5;
     build_table(lens, 288, LBITS, fixed_lt_, LT_SIZE, describe_litlen);
     build_table(lens + 288, 32, DBITS, fixed_dt_, DT_SIZE, describe_dist);
+    build_pairs(fixed_lt_, fixed_pt_);
     fixed_ready_ = true;
   }
 
@@ -280,12 +303,14 @@ class FastInflate {
     if (lens[256] == 0) return false;  // no end-of-block code
     if (!build_table(lens, hlit, LBITS, dyn_lt_, LT_SIZE, describe_litlen)) return false;
     if (!build_table(lens + hlit, hdist, DBITS, dyn_dt_, DT_SIZE, describe_dist)) return false;
+    build_pairs(dyn_lt_, dyn_pt_);
     return true;
   }
 
   bool huffman_block() {
     const uint32_t* lt = lt_;
     const uint32_t* dt = dt_;
+    const uint32_t* pt = pt_;
     const uint8_t* in_next = in_next_;
     uint8_t* out_next = out_next_;
     uint64_t bitbuf = bitbuf_;
@@ -300,28 +325,34 @@ class FastInflate {
       bitbuf |= load64(in_next) << bitsleft;
       in_next += 7 - ((bitsleft >> 3) & 7);
       bitsleft |= 56;
-      uint32_t e = lt[bitbuf & LMASK];
-      if (e & LIT_FLAG) {
-        // up to four primary-table literals (<= 11 bits each) per refill (>= 56 bits)
-        bitbuf >>= (e & 15); bitsleft -= (int)(e & 15);
-        *out_next++ = (uint8_t)(e >> 16);
-        e = lt[bitbuf & LMASK];
-        if (e & LIT_FLAG) {
-          bitbuf >>= (e & 15); bitsleft -= (int)(e & 15);
-          *out_next++ = (uint8_t)(e >> 16);
-          e = lt[bitbuf & LMASK];
-          if (e & LIT_FLAG) {
-            bitbuf >>= (e & 15); bitsleft -= (int)(e & 15);
-            *out_next++ = (uint8_t)(e >> 16);
-            e = lt[bitbuf & LMASK];
-            if (e & LIT_FLAG) {
-              bitbuf >>= (e & 15); bitsleft -= (int)(e & 15);
-              *out_next++ = (uint8_t)(e >> 16);
+      uint32_t p = pt[bitbuf & LMASK];
+      if (p & 0x30u) {
+        // literal run: up to four lookups (<= LBITS bits each, >= 56 in the buffer), one or two literals per lookup;
+        // two bytes are always stored, the cursor moves by the count
+        store16(out_next, (uint16_t)(p >> 8));
+        out_next += (p >> 4) & 3;
+        bitbuf >>= (p & 15); bitsleft -= (int)(p & 15);
+        p = pt[bitbuf & LMASK];
+        if (p & 0x30u) {
+          store16(out_next, (uint16_t)(p >> 8));
+          out_next += (p >> 4) & 3;
+          bitbuf >>= (p & 15); bitsleft -= (int)(p & 15);
+          p = pt[bitbuf & LMASK];
+          if (p & 0x30u) {
+            store16(out_next, (uint16_t)(p >> 8));
+            out_next += (p >> 4) & 3;
+            bitbuf >>= (p & 15); bitsleft -= (int)(p & 15);
+            p = pt[bitbuf & LMASK];
+            if (p & 0x30u) {
+              store16(out_next, (uint16_t)(p >> 8));
+              out_next += (p >> 4) & 3;
+              bitbuf >>= (p & 15); bitsleft -= (int)(p & 15);
             }
           }
         }
         continue;
       }
+      uint32_t e = lt[bitbuf & LMASK];
       if (e_kind(e) == K_SUB) e = lt[e_value(e) + ((bitbuf >> LBITS) & ((1u << e_extra(e)) - 1))];
       bitbuf >>= e_len(e); bitsleft -= e_len(e);
       const int kind = e_kind(e);
@@ -410,8 +441,10 @@ class FastInflate {
   int bitsleft_ = 0;
   const uint32_t* lt_ = nullptr;
   const uint32_t* dt_ = nullptr;
+  const uint32_t* pt_ = nullptr;
   bool fixed_ready_ = false;
   uint32_t dyn_lt_[LT_SIZE], dyn_dt_[DT_SIZE], fixed_lt_[LT_SIZE], fixed_dt_[DT_SIZE];
+  uint32_t dyn_pt_[1 << LBITS], fixed_pt_[1 << LBITS];
 };
 
 }  // namespace ccsm
