@@ -142,3 +142,15 @@ def test_truncated_file_is_an_error(tmp_path):
     open(cut, "wb").write(raw[:len(raw) // 2])
     with pytest.raises(Exception):
         list(BamPieceReader(cut, _filter(_args()), threads=2, piece_bytes=1 << 20, align_to=1))
+
+
+def test_header_only_and_zero_byte_files(tmp_path):
+    path = str(tmp_path / "empty.bam")
+    BamWriter(path, "@HD\tVN:1.6\n", [("chr1", 1000)]).close()
+    rd = BamPieceReader(path, _filter(_args()), threads=2)
+    assert rd.references == [("chr1", 1000)] and list(rd) == []
+    rd.close()
+    zero = str(tmp_path / "zero.bam")
+    open(zero, "wb").close()
+    with pytest.raises(ValueError):
+        BamPieceReader(zero, _filter(_args()))
