@@ -135,13 +135,15 @@ def motif_site_masks(seq, motifs, mod_loc):
     return masks[0], np.ascontiguousarray(masks[1][::-1])
 
 
-def region_pileups(pos, ml, hap, strand, ref_start, ref_end, comb, zero_rule=None):
+def region_pileups(pos, ml, hap, strand, ref_start, ref_end, comb, zero_rule=None, idx=None):
     """Calls of one contig -> the region's CSR pileups.  Returns a list of (strand_char, refpos, ptr, ml, hap):
     one "+" pileup with the reverse-strand CpG calls folded onto the C of the forward strand (pos - 1) when `comb`
     (call_mods_freq_bam.py:542-551), else a "+" and a "-" pileup.  `strand` bit 1 marks --refsites_all zero calls;
     zero_rule = (motif_len, mod_loc): such a call only counts where its motif occurrence lies inside the region, because
-    the reference searches the motif in the region's slice of the contig (:448-455)."""
-    sel = (pos >= ref_start) & (pos < ref_end)
+    the reference searches the motif in the region's slice of the contig (:448-455).
+    idx: the (ascending) indices of the calls with ref_start <= pos < ref_end when the caller already knows them (a
+    contig's calls are sorted once and every region is a binary search, instead of one scan of the contig per region)."""
+    sel = ((pos >= ref_start) & (pos < ref_end)) if idx is None else idx
     p, m, h, s = pos[sel].astype(np.int64), ml[sel], hap[sel], strand[sel]
     if zero_rule is not None and len(p):
         mlen, mod_loc = zero_rule
@@ -312,9 +314,15 @@ def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1, piec
             if not sel.any():
                 continue
             cpos, cml, chap, cstrand = pos[sel], ml[sel], hap[sel], strand[sel]
+            order = np.argsort(cpos, kind="stable")
+            spos = cpos[order]
             for region in by_contig[name]:
                 _, s, e = region
-                pile = region_pileups(cpos, cml, chap, cstrand, s, e, comb, zero_rule)
+                lo_i, hi_i = np.searchsorted(spos, np.array([s, e], dtype=spos.dtype))  # same dtype: no copy of spos
+                if lo_i == hi_i:
+                    continue
+                idx = np.sort(order[lo_i:hi_i])  # back to read order: what a scan of the contig would select
+                pile = region_pileups(cpos, cml, chap, cstrand, s, e, comb, zero_rule, idx=idx)
                 if not pile:
                     continue
                 beds = call_region(model, args, dnacontigs[name], name, pile, motifs_filter)
