@@ -115,9 +115,9 @@ class BgzfWriter:
     """BGZF writer; ``threads > 1``: blocks are deflated by libccsm's thread team (ccsm_bgzf_deflate).
 
     strategy "zlib" (default): zlib's default strategy at `level` (what htslib does; right for text such as bed files);
-    "rle": run-length matching + dynamic Huffman (zlib Z_RLE) -- HiFi records are packed bases, qualities and kinetics
-    bytes in which LZ77 finds next to nothing, so this is 3-4x faster for files within 3 % of the size (BamWriter's
-    default)."""
+    "rle": run-length matching + dynamic Huffman -- HiFi records are packed bases, qualities and kinetics bytes in which
+    LZ77 finds next to nothing, so files stay within 3 % of the size; the thread team runs the library's own encoder
+    (csrc/deflate_rle.h, 6-8x zlib level 6), the single-threaded Python path zlib's Z_RLE (BamWriter's default)."""
 
     BLOCK = 65280
 

@@ -16,6 +16,7 @@
 #include <memory>
 
 #include "ccsm_internal.h"
+#include "deflate_rle.h"
 #include "inflate_fast.h"
 
 namespace ccsm {
@@ -213,10 +214,15 @@ int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
   // block i is compressed into its own slot dst + i * kSlot (the bound reserves one slot per block), then the blocks
   // are compacted to the front in order; one deflate state per team thread, reset between blocks
   std::atomic<int> bad{0};
+  // CCSM_BGZF_RLE runs the library's own run-length + Huffman encoder (csrc/deflate_rle.h; `level` is ignored);
+  // CCSM_DEFLATE=zlib keeps zlib's Z_RLE for A/B timing and cross-checks
+  const char* env = getenv("CCSM_DEFLATE");
+  const bool own_rle = strategy == Z_RLE && !(env && strcmp(env, "zlib") == 0);
   run_workers(threads, nblk, [&](std::atomic<int64_t>& next) {
+    std::unique_ptr<RleDeflate> rle(own_rle ? new (std::nothrow) RleDeflate() : nullptr);
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
-    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 9, strategy) != Z_OK) { bad = 1; return; }
+    if (!rle && deflateInit2(&zs, level, Z_DEFLATED, -15, 9, strategy) != Z_OK) { bad = 1; return; }
     for (;;) {
       const int64_t i = next.fetch_add(1);
       if (i >= nblk) break;
@@ -225,13 +231,19 @@ int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
       uint8_t* out = dst + i * kSlot;
       static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
       memcpy(out, hdr, 16);
-      if (deflateReset(&zs) != Z_OK) { bad = 1; break; }
-      zs.next_in = const_cast<Bytef*>(in);
-      zs.avail_in = (uInt)in_n;
-      zs.next_out = out + 18;
-      zs.avail_out = (uInt)(kSlot - 18 - 8);
-      if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { bad = 1; break; }
-      const int64_t clen = (int64_t)zs.total_out;
+      int64_t clen;
+      if (rle) {
+        clen = (int64_t)rle->run(in, (int)in_n, out + 18, (size_t)(kSlot - 18 - 8));
+        if (clen <= 0) { bad = 1; break; }
+      } else {
+        if (deflateReset(&zs) != Z_OK) { bad = 1; break; }
+        zs.next_in = const_cast<Bytef*>(in);
+        zs.avail_in = (uInt)in_n;
+        zs.next_out = out + 18;
+        zs.avail_out = (uInt)(kSlot - 18 - 8);
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { bad = 1; break; }
+        clen = (int64_t)zs.total_out;
+      }
       const int64_t bsize = clen + 26;  // whole block; header stores bsize - 1
       if (bsize > 65536) { bad = 1; break; }
       out[16] = (uint8_t)((bsize - 1) & 0xff);
@@ -242,7 +254,7 @@ int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
       for (int k = 0; k < 4; ++k) t[4 + k] = (uint8_t)((uint32_t)in_n >> (8 * k));
       sizes[(size_t)i] = (int32_t)bsize;
     }
-    deflateEnd(&zs);
+    if (!rle) deflateEnd(&zs);
   });
   if (bad) {
     set_error("ccsm_bgzf_deflate: deflate failed");

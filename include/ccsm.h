@@ -295,9 +295,10 @@ int  ccsm_pileup_finish_lstm_host(ccsm_model* m, const float* const* h0, const f
  * ccsm_bgzf_deflate:       cuts src into 65280-byte blocks, deflates them in parallel, writes the concatenated
  *                          BGZF blocks (no EOF marker) into dst (capacity >= ccsm_bgzf_deflate_bound(src_bytes));
  *                          returns bytes written.  `level` = zlib level 0..9, optionally ORed with CCSM_BGZF_RLE:
- *                          run-length matching + dynamic Huffman only (zlib's Z_RLE).  On HiFi records (packed
- *                          bases, qualities, kinetics: high-entropy bytes where LZ77 finds nothing) that is 3-4x
- *                          faster than the default strategy at the same size within 3 %.
+ *                          run-length matching + dynamic Huffman only (the token stream of zlib's Z_RLE, produced by
+ *                          the library's own encoder csrc/deflate_rle.h; `level` is then ignored).  On HiFi records
+ *                          (packed bases, qualities, kinetics: high-entropy bytes where LZ77 finds nothing) that is
+ *                          6-8x faster than zlib's default strategy at the same size within 3 %.
  * Negative return = CCSM_E* code. */
 #define CCSM_BGZF_RLE 0x100
 int64_t ccsm_bgzf_inflated_size(const uint8_t* src, int64_t src_bytes, int64_t* consumed);

@@ -153,3 +153,36 @@ def test_random_corruptions_never_pass_silently():
                 bad[pos] = int(rng.integers(0, 256))
             got, out, _ = _inflate(lib, bytes(bad), threads=2)
             assert got == _lib.EINVAL or out == data, name
+
+
+def test_own_rle_encoder_matches_zlib_rle(monkeypatch):
+    """CCSM_BGZF_RLE runs csrc/deflate_rle.h: any inflater must read its blocks, and its sizes must be those of zlib's
+    Z_RLE strategy (same token stream, same 32 K-token sub-blocks) -- incompressible input is stored, never expanded."""
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    payloads = dict(_payloads())
+    payloads["runs"] = b"".join(bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 600)) for _ in range(400))
+    payloads["empty"] = b""
+    geo = np.minimum(rng.geometric(0.5, size=BLOCK), 60).astype(np.uint8).tobytes()   # deep Huffman trees
+    payloads["geometric"] = geo
+    for name, data in payloads.items():
+        src = np.frombuffer(data, dtype=np.uint8)
+        cap = int(lib.ccsm_bgzf_deflate_bound(len(data)))
+        sizes = {}
+        for impl in ("own", "zlib"):
+            if impl == "zlib":
+                monkeypatch.setenv("CCSM_DEFLATE", "zlib")
+            else:
+                monkeypatch.delenv("CCSM_DEFLATE", raising=False)
+            dst = np.empty(cap, dtype=np.uint8)
+            got = lib.ccsm_bgzf_deflate(src.ctypes.data if len(data) else None, len(data), dst.ctypes.data, cap,
+                                        6 | _lib.BGZF_RLE, 3)
+            assert got >= 0, (name, impl)
+            blob = dst[:got].tobytes()
+            assert _py_inflate(blob) == data, (name, impl)            # Python's zlib reads it
+            if len(data):
+                g2, out, _ = _inflate(lib, blob)
+                assert g2 == len(data) and out == data, (name, impl)   # and so does the table decoder
+            sizes[impl] = got
+        assert sizes["own"] <= sizes["zlib"] * 1.002 + 16, (name, sizes)
+        assert sizes["own"] <= len(data) + 40 * (len(data) // BLOCK + 1), name   # stored fallback: 26 B BGZF frame + 5 B per stored sub-block
