@@ -8,6 +8,9 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <atomic>
 #include <thread>
@@ -22,6 +25,89 @@
 namespace ccsm {
 
 static std::atomic<int64_t> g_inflate_fast{0}, g_inflate_zlib{0};
+
+#if defined(__x86_64__)
+// CRC-32 (gzip polynomial, reflected) by carry-less multiplication: folds 64 bytes per iteration, then reduces
+// (Gopal et al., "Fast CRC computation for generic polynomials using PCLMULQDQ").  len >= 64, multiple of 16.
+__attribute__((target("pclmul,sse4.1")))
+static uint32_t crc32_clmul(const uint8_t* buf, size_t len, uint32_t crc) {
+  static const uint64_t __attribute__((aligned(16))) k1k2[] = {0x0154442bd4ULL, 0x01c6e41596ULL};
+  static const uint64_t __attribute__((aligned(16))) k3k4[] = {0x01751997d0ULL, 0x00ccaa009eULL};
+  static const uint64_t __attribute__((aligned(16))) k5k0[] = {0x0163cd6124ULL, 0x0000000000ULL};
+  static const uint64_t __attribute__((aligned(16))) poly[] = {0x01db710641ULL, 0x01f7011641ULL};
+  __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+  x1 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
+  x2 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+  x3 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
+  x4 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+  x0 = _mm_load_si128((const __m128i*)k1k2);
+  buf += 64; len -= 64;
+  while (len >= 64) {
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00); x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11); x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    y5 = _mm_loadu_si128((const __m128i*)(buf + 0x00)); y6 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+    y7 = _mm_loadu_si128((const __m128i*)(buf + 0x20)); y8 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5); x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7); x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+    buf += 64; len -= 64;
+  }
+  x0 = _mm_load_si128((const __m128i*)k3k4);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (len >= 16) {
+    x2 = _mm_loadu_si128((const __m128i*)buf);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16; len -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_srli_si128(x1, 8);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_loadl_epi64((const __m128i*)k5k0);
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, x3);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_load_si128((const __m128i*)poly);
+  x2 = _mm_and_si128(x1, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+  x2 = _mm_and_si128(x2, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+
+#endif
+
+// gzip CRC-32 of one BGZF block.  x86-64 with PCLMULQDQ: carry-less-multiply folding over the 16-byte-multiple body
+// (5x zlib's table code), zlib for the tail; the folding path is checked against zlib once per process before use.
+static uint32_t block_crc32(const uint8_t* buf, size_t len) {
+#if defined(__x86_64__)
+  static const bool use_clmul = [] {
+    if (!__builtin_cpu_supports("pclmul") || !__builtin_cpu_supports("sse4.1")) return false;
+    uint8_t probe[272];
+    for (int i = 0; i < 272; ++i) probe[i] = (uint8_t)(i * 131 + 7);
+    for (size_t n : {(size_t)64, (size_t)80, (size_t)256, (size_t)272})
+      if (~crc32_clmul(probe, n, ~0u) != (uint32_t)crc32(crc32(0L, Z_NULL, 0), probe, (uInt)n)) return false;
+    return true;
+  }();
+  if (use_clmul && len >= 64) {
+    const size_t body = len & ~(size_t)15;
+    uint32_t c = ~crc32_clmul(buf, body, ~0u);
+    if (len > body) c = (uint32_t)crc32(c, buf + body, (uInt)(len - body));
+    return c;
+  }
+#endif
+  return (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf, (uInt)len);
+}
 
 struct BgzfBlock {
   int64_t src_off;   // start of the deflate payload
@@ -153,7 +239,7 @@ int64_t ccsm_bgzf_inflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
       const uint8_t* t = src + b.src_off + b.clen;
       const uint32_t want = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
       if (fast && fast->run(src + b.src_off, b.clen, dst + b.dst_off, b.isize) &&
-          (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.dst_off, (uInt)b.isize) == want) {
+          block_crc32(dst + b.dst_off, (size_t)b.isize) == want) {
         ++n_fast;
         continue;
       }
@@ -172,7 +258,7 @@ int64_t ccsm_bgzf_inflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
       zs.avail_out = (uInt)b.isize;
       const int rc = inflate(&zs, Z_FINISH);
       if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
-      if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.dst_off, (uInt)b.isize) != want) bad = 1;
+      if (block_crc32(dst + b.dst_off, (size_t)b.isize) != want) bad = 1;
       ++n_zlib;
     }
     if (zs_ready) inflateEnd(&zs);
@@ -248,7 +334,7 @@ int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, i
       if (bsize > 65536) { bad = 1; break; }
       out[16] = (uint8_t)((bsize - 1) & 0xff);
       out[17] = (uint8_t)((bsize - 1) >> 8);
-      const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in, (uInt)in_n);
+      const uint32_t crc = block_crc32(in, (size_t)in_n);
       uint8_t* t = out + 18 + clen;
       for (int k = 0; k < 4; ++k) t[k] = (uint8_t)(crc >> (8 * k));
       for (int k = 0; k < 4; ++k) t[4 + k] = (uint8_t)((uint32_t)in_n >> (8 * k));
