@@ -330,7 +330,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp16": "f16", "fp16x3": "f16x3",
-                                          "fp32": "f32"}[prec],
+                                          "fp16c8": "f16+e4m3", "fp32": "f32"}[prec],
            "data": "synthetic",
            "config": {"workload": "synthetic %dx21xfeat per GPU, attbigru2s forward (v3 checkpoint weights), %s" % (S, prec),
                       "sites_per_gpu_per_step": S, "kmer_len": 21, "precision": prec,

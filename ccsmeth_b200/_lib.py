@@ -23,7 +23,7 @@ LINK_LIBS = ["-lz", "-lpthread"]
 # error codes / enums (mirror include/ccsm.h)
 OK, EINVAL, ESTATE, ECUDA, ENOMEM, EUNSUPPORTED, EKEY = 0, -1, -2, -3, -4, -5, -6
 KIND_ATT2S, KIND_AGGR = 0, 1
-PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x3": 3, "fp16": 4}
+PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x3": 3, "fp16": 4, "fp16c8": 5}
 FEAT_NPASS, FEAT_STDS, FEAT_SN, FEAT_MAP, CELL_LSTM, MODEL_2S2, MODEL_TRANSENC = 1, 2, 4, 8, 16, 32, 64
 AGGR_LSTM = 0x100
 BGZF_RLE = 0x100
@@ -32,7 +32,7 @@ EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_
            "ccsm_set_weight", "ccsm_finalize", "ccsm_set_precision", "ccsm_forward_att2s",
            "ccsm_forward_att2s_host", "ccsm_forward_att2s_lstm", "ccsm_forward_aggr", "ccsm_forward_aggr_lstm", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
-           "ccsm_debug_umma_pair_gemm", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
+           "ccsm_debug_umma_pair_gemm", "ccsm_debug_umma_mixed_gemm", "ccsm_debug_umma_rate", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
            "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_inflate_stats", "ccsm_bgzf_deflate_bound",
            "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records", "ccsm_bam_modcalls", "ccsm_pileup_luts",
            "ccsm_pileup_begin_host", "ccsm_pileup_finish_host", "ccsm_pileup_finish_lstm_host"]
@@ -166,6 +166,10 @@ def load():
         lib.ccsm_debug_tc_layer_out.restype = i64
         lib.ccsm_debug_umma_pair_gemm.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
         lib.ccsm_debug_umma_pair_gemm.restype = ctypes.c_int
+        lib.ccsm_debug_umma_mixed_gemm.argtypes = [i32, i32, i32, vp, vp, vp]
+        lib.ccsm_debug_umma_mixed_gemm.restype = ctypes.c_int
+        lib.ccsm_debug_umma_rate.argtypes = [i32, i32, i32, i32, vp]
+        lib.ccsm_debug_umma_rate.restype = ctypes.c_int
         lib.ccsm_set_h0_mode.argtypes = [vp, i32, ctypes.c_uint64]
         lib.ccsm_set_h0_mode.restype = ctypes.c_int
         lib.ccsm_profile_enable.argtypes = [vp, i32]

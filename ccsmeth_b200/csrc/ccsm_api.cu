@@ -77,7 +77,7 @@ int ccsm_create(ccsm_model** out, const ccsm_config* cfg) {
     set_error("ccsm_create: layers=%d hidden=%d classes=%d unsupported", cfg->num_layers, cfg->hidden, cfg->num_classes);
     return CCSM_EINVAL;
   }
-  if (cfg->precision < CCSM_PREC_FP32 || cfg->precision > CCSM_PREC_FP16) {
+  if (cfg->precision < CCSM_PREC_FP32 || cfg->precision > CCSM_PREC_FP16C8) {
     set_error("ccsm_create: unknown precision %d", cfg->precision);
     return CCSM_EINVAL;
   }
@@ -359,7 +359,7 @@ int ccsm_set_h0_mode(ccsm_model* m, int32_t mode, uint64_t seed) {
 }
 
 int ccsm_set_precision(ccsm_model* m, int32_t precision) {
-  if (!m || precision < CCSM_PREC_FP32 || precision > CCSM_PREC_FP16) {
+  if (!m || precision < CCSM_PREC_FP32 || precision > CCSM_PREC_FP16C8) {
     set_error("ccsm_set_precision: bad argument");
     return CCSM_EINVAL;
   }

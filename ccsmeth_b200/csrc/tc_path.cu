@@ -14,6 +14,15 @@
 //             192 gate rows per unit-chunk j: X part rows = (n_i, r, z), H part rows = (r, z, n_h)
 //   part      = 0 (hi) or 1 (lo): P = 1 single pass; P = 2 -> x ~= hi + lo and three MMA passes
 //               hi*hi + hi*lo + lo*hi (error-compensated split, fp32 accumulate in TMEM).
+//   C8        = "fp16 + e4m3 corrections" (CCSM_PREC_FP16C8, P = 2): the two correction products of the split are
+//               only ~2^-12 of the result, so 4 significant bits are enough for them:
+//                 a . W ~= a_hi . W_hi [fp16 MMA] + e4m3(a) . e4m3(S W_lo) + e4m3(S a_lo) . e4m3(W) [e4m3 MMAs, K = 32 each]
+//               with everything accumulated at scale S = 2^12 (W_hi = fp16(S W), biases x S; the gate math folds 1/S
+//               into its exponent constants).  Two MMA pass-equivalents instead of three, max |dprob| ~3e-5
+//               (scripts/precision_study2.py).  Part 1 of an image then holds, per 32 K elements, two 16-element
+//               e4m3 slabs of the rounded value followed by two of the scaled residual (same bytes as a 16-bit lo part):
+//                 activations [a8 s0 s1][alo8 s0 s1] x 2048 B, weights [Wlo8 s0 s1][W8 s0 s1] x (rows x 16 B).
+//               The K = 11 input of layer 0 keeps the 3-pass fp16 split (weights x S).
 //
 // GRU layer kernel (persistent, one CTA per SM, 384 threads):
 //   warp 0      TMA producer: bulk copies weights + activation K-slabs into a 3-stage ring
@@ -38,10 +47,16 @@ constexpr uint32_t A_SLAB = 2048;     // 128 rows x 16 B
 constexpr uint32_t G_SLAB = 3072;     // 192 gate rows x 16 B
 constexpr uint32_t T_SLAB = 4096;     // 256 attention rows x 16 B
 constexpr uint32_t CHUNK_BYTES = 8 * A_SLAB;  // 64 K elements of a 128-row tile, one part
+constexpr float C8_S = 4096.f;                // accumulator scale of the C8 mode
+constexpr float C8_INV_S = 1.f / 4096.f;
+// C8 part 1 of an activation chunk: byte offset (before + row * 16) of the 8 e4m3 values of 8-unit slab q (0..7):
+// rounded values; the scaled residuals sit 4096 B further on.
+__host__ __device__ constexpr uint32_t c8_off(int q) { return (uint32_t)(q >> 2) * 8192u + (uint32_t)((q >> 1) & 1) * 2048u + (uint32_t)(q & 1) * 8u; }
 
 struct TcState {
   int P = 0;          // parts of the currently packed weights (0 = none)
   bool f16 = false;
+  bool c8 = false;    // fp16 + e4m3 corrections (CCSM_PREC_FP16C8)
   std::vector<DevBuf> wimg;   // per layer
   std::vector<DevBuf> wpair;  // per layer, CTA-pair layout (each CTA's 96-row half contiguous)
   std::vector<size_t> kx_slabs;
@@ -80,6 +95,57 @@ __device__ __forceinline__ float tanh_(float x) {
     return t;
   } else {
     return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f);
+  }
+}
+
+// Accurate forms on accumulators that carry the scale S (C8): sigmoid(x / S), tanh(x / S); ex2.approx + fast division.
+__device__ __forceinline__ float ex2_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_s(float x) { return __fdividef(1.f, 1.f + ex2_(x * (-1.4426950408889634f * C8_INV_S))); }
+__device__ __forceinline__ float tanh_s(float x) {
+  return fmaf(2.f, __fdividef(1.f, 1.f + ex2_(x * (-2.8853900817779268f * C8_INV_S))), -1.f);
+}
+template <bool FAST, bool C8>
+__device__ __forceinline__ float sig_(float x) {
+  if constexpr (C8) return sigmoid_s(x);
+  else return sigmoid_<FAST>(x);
+}
+template <bool FAST, bool C8>
+__device__ __forceinline__ float tnh_(float x) {
+  if constexpr (C8) return tanh_s(x);
+  else return tanh_<FAST>(x);
+}
+
+// C8: 8 fp32 -> fp16 hi (16 bytes), e4m3 of the value (8 bytes), e4m3 of S * (value - hi) (8 bytes)
+__device__ __forceinline__ void split8_c8(const float (&v)[8], uint4& hi, uint2& a8, uint2& l8) {
+  uint32_t h[4];
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack2<true>(v[2 * i], v[2 * i + 1]);
+    const float2 b = unpack2<true>(h[i]);
+    r[2 * i] = (v[2 * i] - b.x) * C8_S;
+    r[2 * i + 1] = (v[2 * i + 1] - b.y) * C8_S;
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  a8 = make_uint2(pack4_e4m3(v[0], v[1], v[2], v[3]), pack4_e4m3(v[4], v[5], v[6], v[7]));
+  l8 = make_uint2(pack4_e4m3(r[0], r[1], r[2], r[3]), pack4_e4m3(r[4], r[5], r[6], r[7]));
+}
+// C8: value = hi + residual / S
+__device__ __forceinline__ void join8_c8(const uint4& hi, const uint2& l8, float (&v)[8]) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+  float r0[4], r1[4];
+  unpack4_e4m3(l8.x, r0);
+  unpack4_e4m3(l8.y, r1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = unpack2<true>(h[i]);
+    const float ra = i < 2 ? r0[2 * i] : r1[2 * i - 4], rb = i < 2 ? r0[2 * i + 1] : r1[2 * i - 3];
+    v[2 * i] = fmaf(ra, C8_INV_S, a.x);
+    v[2 * i + 1] = fmaf(rb, C8_INV_S, a.y);
   }
 }
 
@@ -161,7 +227,7 @@ struct TcStrand {
   const float *kmer, *kpass, *ipd, *pw;
 };
 
-template <int P, bool F16>
+template <int P, bool F16, bool C8 = false>
 __global__ void tc_prep_kernel(int64_t n_tiles, int64_t sites, int64_t site0, int64_t n_total, int L, int NL,
                                int n_vocab, int has_npass, TcStrand s0, TcStrand s1,
                                const float* __restrict__ embed, const float* __restrict__ h0_a,
@@ -225,12 +291,22 @@ __global__ void tc_prep_kernel(int64_t n_tiles, int64_t sites, int64_t site0, in
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = 0.f;
           }
-          uint4 hi, lo;
-          split8<P, F16>(w, hi, lo);
-          uint8_t* base = h0img + ((((int64_t)l * n_tiles + tile) * 2 + d) * 4 + kc) * (size_t)(P * CHUNK_BYTES) +
-                          sl * A_SLAB + r * 16;
-          *reinterpret_cast<uint4*>(base) = hi;
-          if constexpr (P == 2) *reinterpret_cast<uint4*>(base + CHUNK_BYTES) = lo;
+          uint8_t* cbase = h0img + ((((int64_t)l * n_tiles + tile) * 2 + d) * 4 + kc) * (size_t)(P * CHUNK_BYTES);
+          uint8_t* base = cbase + sl * A_SLAB + r * 16;
+          if constexpr (C8) {
+            uint4 hi;
+            uint2 a8, l8;
+            split8_c8(w, hi, a8, l8);
+            *reinterpret_cast<uint4*>(base) = hi;
+            uint8_t* b8 = cbase + CHUNK_BYTES + c8_off(sl) + r * 16;
+            *reinterpret_cast<uint2*>(b8) = a8;
+            *reinterpret_cast<uint2*>(b8 + 4096) = l8;
+          } else {
+            uint4 hi, lo;
+            split8<P, F16>(w, hi, lo);
+            *reinterpret_cast<uint4*>(base) = hi;
+            if constexpr (P == 2) *reinterpret_cast<uint4*>(base + CHUNK_BYTES) = lo;
+          }
         }
     }
 }
@@ -297,9 +373,11 @@ struct GruCfg {
 //           sub-block i+1 is in flight while sub-block i goes through the MUFU / pack / store work (same register
 //           footprint as one 16-unit block).  Aimed at layer 0, whose epilogue (128 KB of TMEM reads per chunk at
 //           64 B/cycle) is longer than its 17 MMAs.
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false, bool PIPE = false>
+//   C8    = fp16 main pass + two e4m3 correction MMAs per 32 K elements (see the file header); P = 2 image sizes.
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false, bool PIPE = false, bool C8 = false>
 __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS, GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
+  static_assert(!C8 || (P == 2 && F16 && PIPE && !HS && KSB == 8), "C8: fp16 images, 32 K elements per stage, pipelined epilogue");
   static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
   static_assert(!MC || NSLOT == 1, "multicast variant: one row tile per CTA");
   static_assert(!(MC && HS), "HS and MC are separate experiments");
@@ -443,6 +521,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc192 = make_idesc(128, 192, F16);
+      constexpr uint32_t idesc192_8 = make_idesc_e4m3(128, 192);
       uint32_t stage = 0, use = 0, chunk = 0;
       uint32_t hcount = 0;  // HS: completions of h_ready consumed so far (one per step: item start, then every step)
       for (int item = item0; item < n_items; item += item_step) {
@@ -460,6 +539,22 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
                 mbar_wait(full0 + 8 * stage, use & 1);
                 tc_fence_after();
                 const uint32_t sb = smem_base + stage * C::STAGE;
+                if (C8 && ns == 4) {
+                  // 32 K elements: two fp16 MMAs (K = 16) on the hi parts, then a8 . Wlo8 and alo8 . W8 (K = 32 each)
+#pragma unroll
+                  for (int sl = 0; sl < NSLOT; ++sl) {
+                    const uint32_t dcol = tmem + (NBUF == 2 ? buf : sl) * 256 + (part == 0 ? 0 : 64);
+                    const uint32_t a0 = sb + P * C::B_PART + (sl * P) * C::A_PART, b0 = sb;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                      umma_f16(dcol, make_smem_desc(a0 + ks * 2 * A_SLAB, A_SLAB, 128),
+                               make_smem_desc(b0 + ks * 2 * G_SLAB, G_SLAB, 128), idesc192, 1u);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                      umma_f8(dcol, make_smem_desc(a0 + C::A_PART + c * 2 * A_SLAB, A_SLAB, 128),
+                              make_smem_desc(b0 + C::B_PART + c * 2 * G_SLAB, G_SLAB, 128), idesc192_8, 1u);
+                  }
+                } else
                 for (int ks = 0; ks < ns / 2; ++ks) {
 #pragma unroll
                   for (int sl = 0; sl < NSLOT; ++sl) {
@@ -547,7 +642,10 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
               hph[q] = *reinterpret_cast<const uint4*>(hp_base + (2 * ub0 + q) * A_SLAB + row * 16);
             else
               hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (2 * ub0 + q) * A_SLAB + row * 16));
-            if constexpr (P == 2)
+            if constexpr (C8) {
+              const uint2 t8 = __ldcg(reinterpret_cast<const uint2*>(hp_base + CHUNK_BYTES + 4096 + c8_off(2 * ub0 + q) + row * 16));
+              hpl[q] = make_uint4(t8.x, t8.y, 0, 0);
+            } else if constexpr (P == 2)
               hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + (2 * ub0 + q) * A_SLAB + row * 16));
             else
               hpl[q] = make_uint4(0, 0, 0, 0);
@@ -559,6 +657,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
           if constexpr (PIPE) {
             constexpr int NSB = 2 * NUB;  // 8-unit sub-blocks of this warp
             uint32_t acc[2][4][8];        // [ping-pong][n_i, r, z, n_h][8 units]
+            uint2 a8_even = make_uint2(0, 0), l8_even = make_uint2(0, 0);  // C8: first half of a 16-element e4m3 row
             const int c00 = ub0 * 16;
 #pragma unroll
             for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + c00, acc[0][g]);
@@ -573,22 +672,38 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
               // re-arm these columns with the biases of the unit-chunk that uses this buffer next
               arm_bias8(trow, col, bz, ((j + NBUF) & 3) * 64 + col);
               float hp[8], hn[8];
-              join8<P, F16>(hph[sb], hpl[sb], hp);
+              if constexpr (C8) join8_c8(hph[sb], make_uint2(hpl[sb].x, hpl[sb].y), hp);
+              else join8<P, F16>(hph[sb], hpl[sb], hp);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float r = sigmoid_<FAST>(__uint_as_float(acc[sb & 1][1][i]));
-                const float z = sigmoid_<FAST>(__uint_as_float(acc[sb & 1][2][i]));
-                const float n = tanh_<FAST>(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
+                const float r = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][1][i]));
+                const float z = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][2][i]));
+                const float n = tnh_<FAST, C8>(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
                 hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
               }
+              const int slab = (col >> 3);  // K-slab of these 8 units inside the 64-unit chunk
+              if constexpr (C8) {
+                uint4 hi;
+                uint2 a8, l8;
+                split8_c8(hn, hi, a8, l8);
+                *reinterpret_cast<uint4*>(out_base + slab * A_SLAB + row * 16) = hi;
+                if ((sb & 1) == 0) {
+                  a8_even = a8;
+                  l8_even = l8;
+                } else {  // both halves of a 16-element e4m3 row: one 16-byte store each
+                  uint8_t* b8 = out_base + CHUNK_BYTES + c8_off(slab - 1) + row * 16;
+                  *reinterpret_cast<uint4*>(b8) = make_uint4(a8_even.x, a8_even.y, a8.x, a8.y);
+                  *reinterpret_cast<uint4*>(b8 + 4096) = make_uint4(l8_even.x, l8_even.y, l8.x, l8.y);
+                }
+              } else {
               uint4 hi, lo;
               split8<P, F16>(hn, hi, lo);
-              const int slab = (col >> 3);  // K-slab of these 8 units inside the 64-unit chunk
               if constexpr (HS) {
                 if (s + 1 < L) *reinterpret_cast<uint4*>(hnext + slab * A_SLAB + row * 16) = hi;
               }
               *reinterpret_cast<uint4*>(out_base + slab * A_SLAB + row * 16) = hi;
               if constexpr (P == 2) *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + slab * A_SLAB + row * 16) = lo;
+              }
             }
           } else {
 #pragma unroll
@@ -938,6 +1053,317 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, PairCf
 }
 
 // ------------------------------------------------------------------------------------------------
+// "Duo" GRU layer kernel: CTA pair (tcgen05.mma.cta_group::2, M = 256) running BOTH directions of its two row tiles
+// as two interleaved recurrences.
+//
+// Why: the layer kernels above are bound by the bytes each SM pulls in through its L2 port (~64 B/clk/SM: bf16,
+// fp16x3 and fp16c8 all land on ~16 cycles per KB of bulk-copy traffic, profiles/r02_*), not by the tensor pipe.
+// In a CTA pair each SM fetches only HALF of every weight slab (96 of the 192 gate rows; the pair's MMA reads the
+// other half from the peer's shared memory), which removes 30 % of the bytes per row tile.  And with the forward
+// and the reverse scan of the same tiles alternating chunk by chunk -- recurrence 0 = forward on TMEM buffer 0,
+// recurrence 1 = reverse on buffer 1 -- one recurrence's MMAs run while the other's gate epilogue drains and while
+// its h_t makes the round trip through L2 at a step boundary (what left layer 0 latency-bound).
+//
+//   warp 0      producer (both CTAs): own A K-slabs + own half of the weight slabs -> 7-stage ring (28 KB stages)
+//   warp 1      rank 0: MMA issuer for the pair; rank 1: relay (local full barrier -> leader's peer_full)
+//   warps 2-5   gate epilogue of recurrence 0 (forward), warps 6-9 of recurrence 1 (reverse); thread = row
+// Work item = one pair of row tiles (CTA c owns tile 2 * pair + c); cluster i takes items i, i + n_clusters, ...
+// Weight image: the CTA-pair layout [dir][j]{X: [half][part][slabs x 1536 B], H: [half][part][32 slabs x 1536 B]}.
+// ------------------------------------------------------------------------------------------------
+constexpr int DUO_THREADS = 320;
+constexpr int DUO_STAGES = 7;
+
+template <int P>
+struct DuoCfg {
+  static constexpr int KS = 8 / P;  // K-slabs (8 elements) per stage and part
+  static constexpr uint32_t B_PART = KS * GH_SLAB;
+  static constexpr uint32_t A_PART = KS * A_SLAB;
+  static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 28672
+  static constexpr uint32_t SMEM = DUO_STAGES * STAGE + 2 * 4 * 256 * 4;
+};
+
+template <int P, bool F16, bool C8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DUO_THREADS, 1) tc_gru_duo_kernel(const GruParams p) {
+  static_assert(!C8 || (P == 2 && F16), "C8: fp16 images");
+  using C = DuoCfg<P>;
+  constexpr int KS = C::KS;
+  constexpr bool FAST = (P == 1);
+  constexpr int S = DUO_STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[3 * S + 6];
+  __shared__ uint32_t tmem_base_s;
+  float* bias_s = reinterpret_cast<float*>(smem + S * C::STAGE);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), peer0 = smem_u32(&bars[2 * S]);
+  // per recurrence r: tmem_full + 8r, tmem_empty + 8r, h_ready + 8r
+  const uint32_t tmem_full = smem_u32(&bars[3 * S]), tmem_empty = smem_u32(&bars[3 * S + 2]),
+                 h_ready = smem_u32(&bars[3 * S + 4]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(peer0 + 8 * i, 1);
+    }
+    for (int r = 0; r < 2; ++r) {
+      mbar_init(tmem_full + 8 * r, 1);
+      mbar_init(tmem_empty + 8 * r, 8);  // one arrival per epilogue warp of the recurrence, both CTAs
+      mbar_init(h_ready + 8 * r, 4);     // the recurrence's four epilogue warps of this CTA
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * 4 * 256; i += DUO_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const int L = p.L;
+  const int n_items = p.n_tiles / 2;  // pairs of row tiles
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const size_t xbytes = (size_t)2 * P * p.kx_slabs * GH_SLAB, hbytes = (size_t)2 * P * 32 * GH_SLAB;
+  const size_t wj_bytes = xbytes + hbytes;
+  // the K = 16 input of layer 0 is a single short stage in the 3-pass layout (also in the C8 mode)
+  const bool x_short = p.kx_slabs < KS;
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA: own A tile, own half of B) =====================
+    if (elect_one()) {
+      uint32_t stage = 0, use = 0, gstep = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int64_t tile = 2 * (int64_t)item + rank;
+        for (int s = 0; s < L; ++s, ++gstep) {
+          for (int j = 0; j < 4; ++j) {
+            for (int d = 0; d < 2; ++d) {  // recurrence d: forward / reverse scan
+              const int t = d ? (L - 1 - s) : s;
+              const int tprev = d ? t + 1 : t - 1;
+              const uint8_t* wj = p.wimg + (size_t)(d * 4 + j) * wj_bytes;
+              for (int part = 0; part < 2; ++part) {
+                const int total = part == 0 ? p.kx_slabs : 32;
+                const uint8_t* wsrc = wj + (part ? xbytes : 0) + (size_t)rank * P * total * GH_SLAB;
+                for (int so = 0; so < total; so += KS) {
+                  const int ns = (total - so) < KS ? (total - so) : KS;
+                  if (part == 1 && so == 0 && j == 0 && gstep > 0) {
+                    mbar_wait(h_ready + 8 * d, (gstep - 1) & 1);  // h_{t_prev} of this recurrence is in the act image
+                    fence_proxy_async_all();
+                  }
+                  mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+                  const uint32_t fb = full0 + 8 * stage;
+                  const uint32_t sb = smem_base + stage * C::STAGE;
+                  mbar_expect_tx(fb, (uint32_t)(P * ns) * (GH_SLAB + A_SLAB));
+                  const uint8_t* asrc;
+                  size_t part_stride;
+                  if (part == 0) {
+                    if (x_short) {
+                      asrc = p.xin + ((tile * L + t) * P) * (2 * (size_t)A_SLAB);
+                      part_stride = 2 * A_SLAB;
+                    } else {
+                      asrc = p.xin + (((tile * L + t) * 8 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                      part_stride = CHUNK_BYTES;
+                    }
+                  } else {
+                    if (s == 0)
+                      asrc = p.h0img + (((tile * 2 + d) * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                    else
+                      asrc = p.out + (((tile * L + tprev) * 8 + d * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES +
+                             (so & 7) * A_SLAB;
+                    part_stride = CHUNK_BYTES;
+                  }
+#pragma unroll
+                  for (int pp = 0; pp < P; ++pp) {
+                    bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * GH_SLAB, ns * GH_SLAB, fb);
+                    bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, asrc + pp * part_stride, ns * A_SLAB, fb);
+                  }
+                  if (++stage == S) {
+                    stage = 0;
+                    ++use;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      if (rank == 1) {
+        // ===================== relay: my operands landed -> tell the leader =====================
+        uint32_t stage = 0, use = 0;
+        const int per_chunk = (p.kx_slabs + KS - 1) / KS + 32 / KS;
+        for (int item = cluster_id; item < n_items; item += n_clusters)
+          for (int c = 0; c < L * 8 * per_chunk; ++c) {
+            mbar_wait(full0 + 8 * stage, use & 1);
+            mbar_arrive_remote(mapa_u32(peer0 + 8 * stage, 0));
+            if (++stage == S) {
+              stage = 0;
+              ++use;
+            }
+          }
+      } else {
+        // ===================== MMA issuer for the pair =====================
+        constexpr uint32_t idesc = make_idesc(256, 192, F16);
+        constexpr uint32_t idesc8 = make_idesc_e4m3(256, 192);
+        uint32_t stage = 0, use = 0, chunk = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+          for (int s = 0; s < L; ++s) {
+            for (int j = 0; j < 4; ++j, ++chunk) {
+              for (int d = 0; d < 2; ++d) {
+                // completion #chunk of tmem_empty[d]: #0 = initial arming, #k = drain + re-arm after chunk k-1
+                mbar_wait(tmem_empty + 8 * d, chunk & 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem + d * 256;
+                for (int part = 0; part < 2; ++part) {
+                  const int total = part == 0 ? p.kx_slabs : 32;
+                  const uint32_t dpart = dcol + (part == 0 ? 0 : 64);  // X -> (n_i, r, z); H -> (r, z, n_h)
+                  for (int so = 0; so < total; so += KS) {
+                    const int ns = (total - so) < KS ? (total - so) : KS;
+                    mbar_wait(full0 + 8 * stage, use & 1);
+                    mbar_wait(peer0 + 8 * stage, use & 1);
+                    tc_fence_after();
+                    const uint32_t sb = smem_base + stage * C::STAGE;
+                    const uint32_t a0 = sb + P * C::B_PART, b0 = sb;
+                    if (C8 && ns == KS) {
+                      // 32 K elements: two fp16 MMAs on the hi parts, then a8 . Wlo8 and alo8 . W8 (K = 32 each)
+#pragma unroll
+                      for (int q = 0; q < 2; ++q) {
+                        umma_f16_pair(dpart, make_smem_desc(a0 + q * 2 * A_SLAB, A_SLAB, 128),
+                                      make_smem_desc(b0 + q * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
+                        umma_f8_pair(dpart, make_smem_desc(a0 + C::A_PART + q * 2 * A_SLAB, A_SLAB, 128),
+                                     make_smem_desc(b0 + C::B_PART + q * 2 * GH_SLAB, GH_SLAB, 128), idesc8, 1u);
+                      }
+                    } else {
+                      for (int ks = 0; ks < ns / 2; ++ks) {
+#pragma unroll
+                        for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
+                          const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                          umma_f16_pair(dpart, make_smem_desc(a0 + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128),
+                                        make_smem_desc(b0 + pb * C::B_PART + ks * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
+                        }
+                      }
+                    }
+                    umma_commit_pair(empty0 + 8 * stage, 0x3);
+                    if (++stage == S) {
+                      stage = 0;
+                      ++use;
+                    }
+                  }
+                }
+                umma_commit_pair(tmem_full + 8 * d, 0x3);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== gate epilogue: warps 2-5 recurrence 0 (forward), warps 6-9 recurrence 1 (reverse) =====
+    const int d = (warp - 2) >> 2;
+    const int quad = warp & 3;  // tcgen05.ld lane rule: a warp touches TMEM lanes [32 * (warp % 4), +32)
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16) + d * 256;
+    const uint32_t remote_empty = mapa_u32(tmem_empty + 8 * d, 0);
+    const float* bz = bias_s + d * 4 * 256;
+#pragma unroll
+    for (int ub = 0; ub < 4; ++ub) arm_bias16(trow, ub, bz, ub * 16);  // unit-chunk 0
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_remote(remote_empty);
+    uint32_t chunk = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int64_t tile = 2 * (int64_t)item + rank;
+      for (int s = 0; s < L; ++s) {
+        const int t = d ? (L - 1 - s) : s;
+        const int tprev = d ? t + 1 : t - 1;
+        for (int j = 0; j < 4; ++j, ++chunk) {
+          const uint8_t* hp_base =
+              (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
+                       : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          // prefetch h_{t_prev} of this row's 64 units (the L2 latency overlaps the chunk's MMAs)
+          uint4 hph[8], hpl[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + q * A_SLAB + row * 16));
+            if constexpr (C8) {
+              const uint2 t8 = __ldcg(reinterpret_cast<const uint2*>(hp_base + CHUNK_BYTES + 4096 + c8_off(q) + row * 16));
+              hpl[q] = make_uint4(t8.x, t8.y, 0, 0);
+            } else if constexpr (P == 2)
+              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + q * A_SLAB + row * 16));
+            else
+              hpl[q] = make_uint4(0, 0, 0, 0);
+          }
+          mbar_wait(tmem_full + 8 * d, chunk & 1);
+          tc_fence_after();
+          uint32_t acc[2][4][8];  // [ping-pong][n_i, r, z, n_h][8 units]
+          uint2 a8_even = make_uint2(0, 0), l8_even = make_uint2(0, 0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64, acc[0][g]);
+#pragma unroll
+          for (int sb = 0; sb < 8; ++sb) {
+            const int col = sb * 8;
+            tmem_ld_wait();  // sub-block sb has landed (issued one iteration ago)
+            if (sb + 1 < 8) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(sb + 1) & 1][g]);
+            }
+            arm_bias8(trow, col, bz, ((j + 1) & 3) * 64 + col);  // biases of this recurrence's next unit-chunk
+            float hp[8], hn[8];
+            if constexpr (C8) join8_c8(hph[sb], make_uint2(hpl[sb].x, hpl[sb].y), hp);
+            else join8<P, F16>(hph[sb], hpl[sb], hp);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float r = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][1][i]));
+              const float z = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][2][i]));
+              const float n = tnh_<FAST, C8>(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
+              hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
+            }
+            if constexpr (C8) {
+              uint4 hi;
+              uint2 a8, l8;
+              split8_c8(hn, hi, a8, l8);
+              *reinterpret_cast<uint4*>(out_base + sb * A_SLAB + row * 16) = hi;
+              if ((sb & 1) == 0) {
+                a8_even = a8;
+                l8_even = l8;
+              } else {
+                uint8_t* b8 = out_base + CHUNK_BYTES + c8_off(sb - 1) + row * 16;
+                *reinterpret_cast<uint4*>(b8) = make_uint4(a8_even.x, a8_even.y, a8.x, a8.y);
+                *reinterpret_cast<uint4*>(b8 + 4096) = make_uint4(l8_even.x, l8_even.y, l8.x, l8.y);
+              }
+            } else {
+              uint4 hi, lo;
+              split8<P, F16>(hn, hi, lo);
+              *reinterpret_cast<uint4*>(out_base + sb * A_SLAB + row * 16) = hi;
+              if constexpr (P == 2) *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + sb * A_SLAB + row * 16) = lo;
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          if (j == 3) fence_proxy_async_all();  // generic-proxy global writes -> visible to the producer's bulk copies
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_remote(remote_empty);
+            if (j == 3) mbar_arrive(h_ready + 8 * d);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention + head kernel (reference utils/attention.py:48-70, models.py:135-150)
 //   Qa = q . Wa^T -> TMEM cols [0,256);  per t: D_t = out_t . Ua^T -> TMEM cols [256,512)
 //   e_t = va . tanh(Qa + D_t) (thread-local: TMEM lane = row), softmax over t, ctx = sum_t w_t out_t,
@@ -969,8 +1395,9 @@ struct AttCfg {
   static constexpr uint32_t SMEM = ATT_STAGES * STAGE + (256 + 2048 + 2 * 128 * 22) * 4;
 };
 
-template <int P, bool F16>
+template <int P, bool F16, bool C8 = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttParams p) {
+  static_assert(!C8 || (P == 2 && F16), "C8: fp16 images");
   using C = AttCfg<P>;
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
@@ -1042,6 +1469,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc256 = make_idesc(128, 256, F16);
+      constexpr uint32_t idesc256_8 = make_idesc_e4m3(128, 256);
       uint32_t stage = 0, use = 0, dcount = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int g = 0; g <= L; ++g) {
@@ -1055,6 +1483,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
             mbar_wait(full0 + 8 * stage, use & 1);
             tc_fence_after();
             const uint32_t sb = smem_base + stage * C::STAGE;
+            if constexpr (C8) {
+              // 32 K elements per stage: two fp16 MMAs on the hi parts, then a8 . Wlo8 and alo8 . W8
+              const uint32_t a0 = sb + P * C::B_PART, b0 = sb;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                umma_f16(dcol, make_smem_desc(a0 + ks * 2 * A_SLAB, A_SLAB, 128),
+                         make_smem_desc(b0 + ks * 2 * T_SLAB, T_SLAB, 128), idesc256, (so == 0 && ks == 0) ? 0u : 1u);
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+                umma_f8(dcol, make_smem_desc(a0 + C::A_PART + c * 2 * A_SLAB, A_SLAB, 128),
+                        make_smem_desc(b0 + C::B_PART + c * 2 * T_SLAB, T_SLAB, 128), idesc256_8, 1u);
+            } else
             for (int ks = 0; ks < KS / 2; ++ks) {
 #pragma unroll
               for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
@@ -1100,7 +1540,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            e = fmaf(va_s[cb * 16 + i], tanh_<FAST>(__uint_as_float(q[i]) + __uint_as_float(dd[i])), e);
+            e = fmaf(va_s[cb * 16 + i], tnh_<FAST, C8>(__uint_as_float(q[i]) + __uint_as_float(dd[i])), e);
         }
         my_e[t] = e;
         tc_fence_before();
@@ -1150,13 +1590,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
               const uint8_t* src = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES +
                                    (sl & 7) * A_SLAB + row * 16;
               hi[k] = __ldcg(reinterpret_cast<const uint4*>(src));
-              if constexpr (P == 2) lo[k] = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
+              if constexpr (C8) {
+                const uint8_t* cb = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES;
+                const uint2 t8 = __ldcg(reinterpret_cast<const uint2*>(cb + CHUNK_BYTES + 4096 + c8_off(sl & 7) + row * 16));
+                lo[k] = make_uint4(t8.x, t8.y, 0, 0);
+              } else if constexpr (P == 2) lo[k] = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
               else lo[k] = make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int k = 0; k < TB; ++k) {
               float v[8];
-              join8<P, F16>(hi[k], lo[k], v);
+              if constexpr (C8) join8_c8(hi[k], make_uint2(lo[k].x, lo[k].y), v);
+              else join8<P, F16>(hi[k], lo[k], v);
               const float w = (t0 + k) < 32 ? wt[(t0 + k) & 31] : 0.f;
 #pragma unroll
               for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
@@ -1196,7 +1641,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
 }
 
 // act image (one layer) -> (rows, L, 512) fp32, for tests
-template <int P, bool F16>
+template <int P, bool F16, bool C8 = false>
 __global__ void tc_unpack_act_kernel(const uint8_t* __restrict__ act, float* __restrict__ out, int64_t rows, int L) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (row, t, slab 0..63)
   if (idx >= rows * L * 64) return;
@@ -1208,9 +1653,14 @@ __global__ void tc_unpack_act_kernel(const uint8_t* __restrict__ act, float* __r
   const uint8_t* src = act + (((tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES + (sl & 7) * A_SLAB + r * 16;
   uint4 hi = *reinterpret_cast<const uint4*>(src);
   uint4 lo = make_uint4(0, 0, 0, 0);
-  if constexpr (P == 2) lo = *reinterpret_cast<const uint4*>(src + CHUNK_BYTES);
   float v[8];
-  join8<P, F16>(hi, lo, v);
+  if constexpr (C8) {
+    const uint8_t* cb = act + (((tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES;
+    join8_c8(hi, *reinterpret_cast<const uint2*>(cb + CHUNK_BYTES + 4096 + c8_off(sl & 7) + r * 16), v);
+  } else {
+    if constexpr (P == 2) lo = *reinterpret_cast<const uint4*>(src + CHUNK_BYTES);
+    join8<P, F16>(hi, lo, v);
+  }
   float* o = out + (R * L + t) * 512 + sl * 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = v[i];
@@ -1249,6 +1699,28 @@ static void pack_image(uint16_t* dst, int rows, int kslabs, int K_src, int P, bo
   }
 }
 
+// C8 weight image: part 0 = fp16(S w) in 8-element K-slabs; part 1 = per 32 K elements two 16-element slabs of
+// e4m3(S w - part 0) followed by two of e4m3(w); a slab = rows x 16 B.  Returns false if S w leaves the fp16 range.
+template <class RowFn>
+static bool pack_image_c8(uint16_t* dst, int rows, int kslabs, int K_src, RowFn row_of) {
+  const size_t part_elems = (size_t)kslabs * rows * 8;
+  uint8_t* p1 = reinterpret_cast<uint8_t*>(dst + part_elems);
+  for (int n = 0; n < rows; ++n) {
+    const float* w = row_of(n);
+    for (int k = 0; k < kslabs * 8; ++k) {
+      const float v = k < K_src ? w[k] : 0.f;
+      const float sv = v * C8_S;
+      if (!(fabsf(sv) < 60000.f)) return false;
+      const uint16_t hi = to_elem(sv, true);
+      dst[(size_t)(k / 8) * rows * 8 + (size_t)n * 8 + (k % 8)] = hi;
+      const size_t off = (size_t)(k / 32) * 4 * rows * 16 + (size_t)((k % 32) / 16) * rows * 16 + (size_t)n * 16 + (k % 16);
+      p1[off] = (uint8_t)__nv_cvt_float_to_fp8(sv - from_elem(hi, true), __NV_SATFINITE, __NV_E4M3);
+      p1[off + (size_t)2 * rows * 16] = (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+    }
+  }
+  return true;
+}
+
 static const HostTensor* findw(ccsm_model* m, const std::string& k) {
   auto it = m->w.find(k);
   return it == m->w.end() ? nullptr : &it->second;
@@ -1265,8 +1737,10 @@ int tc_upload_weights(ccsm_model* m) {
   if (!m->tc) m->tc = new TcState();
   TcState& T = *m->tc;
   const int prec = m->cfg.precision;
-  const int P = (prec == CCSM_PREC_BF16X3 || prec == CCSM_PREC_FP16X3) ? 2 : 1;
-  const bool f16 = (prec == CCSM_PREC_FP16X3 || prec == CCSM_PREC_FP16);
+  const bool c8 = prec == CCSM_PREC_FP16C8;
+  const int P = (prec == CCSM_PREC_BF16X3 || prec == CCSM_PREC_FP16X3 || c8) ? 2 : 1;
+  const bool f16 = (prec == CCSM_PREC_FP16X3 || prec == CCSM_PREC_FP16 || c8);
+  bool c8_ok = true;
   cudaDeviceProp prop;
   CCSM_CUDA(cudaGetDeviceProperties(&prop, m->cfg.device));
   T.sm_count = prop.multiProcessorCount;
@@ -1295,31 +1769,54 @@ int tc_upload_weights(ccsm_model* m) {
         // X part rows: n_i, r, z   (PyTorch gate row order in weight_ih: r [0,H), z [H,2H), n [2H,3H))
         // single-pass modes: r/z rows pre-scaled by 0.5 (exact) for the one-MUFU sigmoid, see sigmoid_<FAST>
         std::vector<float> tmp((size_t)(K > H ? K : H));
-        pack_image(base, 192, kxs, K, P, f16, [&](int n) {
+        auto xrow = [&](int n) {
           const int g = n / 64, u = j * 64 + n % 64;
           const int row = (g == 0 ? 2 * H : (g == 1 ? 0 : H)) + u;
-          const float* w = wih->data.data() + (size_t)row * K;
-          if (P == 2 || g == 0) return w;
+          return wih->data.data() + (size_t)row * K;
+        };
+        auto hrow = [&](int n) {
+          const int g = n / 64, u = j * 64 + n % 64;
+          const int row = (g == 0 ? 0 : (g == 1 ? H : 2 * H)) + u;
+          return whh->data.data() + (size_t)row * H;
+        };
+        if (c8) {
+          // layer 0's K = 11 input keeps the 3-pass fp16 split, at the accumulator scale S
+          if (kxs % 4 != 0)
+            pack_image(base, 192, kxs, K, P, f16, [&](int n) {
+              const float* w = xrow(n);
+              for (int k = 0; k < K; ++k) {
+                tmp[k] = C8_S * w[k];
+                if (!(fabsf(tmp[k]) < 60000.f)) c8_ok = false;
+              }
+              return (const float*)tmp.data();
+            });
+          else
+            c8_ok = pack_image_c8(base, 192, kxs, K, xrow) && c8_ok;
+          c8_ok = pack_image_c8(base + x_elems, 192, 32, H, hrow) && c8_ok;
+        } else {
+        pack_image(base, 192, kxs, K, P, f16, [&](int n) {
+          const float* w = xrow(n);
+          if (P == 2 || n / 64 == 0) return w;
           for (int k = 0; k < K; ++k) tmp[k] = 0.5f * w[k];
           return (const float*)tmp.data();
         });
         // H part rows: r, z, n_h
         pack_image(base + x_elems, 192, 32, H, P, f16, [&](int n) {
-          const int g = n / 64, u = j * 64 + n % 64;
-          const int row = (g == 0 ? 0 : (g == 1 ? H : 2 * H)) + u;
-          const float* w = whh->data.data() + (size_t)row * H;
-          if (P == 2 || g == 2) return w;
+          const float* w = hrow(n);
+          if (P == 2 || n / 64 == 2) return w;
           for (int k = 0; k < H; ++k) tmp[k] = 0.5f * w[k];
           return (const float*)tmp.data();
         });
+        }
       }
       float* b = bias.data() + ((size_t)l * 2 + d) * 4 * H;
       for (int u = 0; u < H; ++u) {
         const float gs = P == 1 ? 0.5f : 1.f;                // matches the r/z row scaling above
-        b[u] = gs * (bih->data[u] + bhh->data[u]);                  // b_r
-        b[H + u] = gs * (bih->data[H + u] + bhh->data[H + u]);      // b_z
-        b[2 * H + u] = bih->data[2 * H + u];                 // b_in
-        b[3 * H + u] = bhh->data[2 * H + u];                 // b_hn (inside r * (.))
+        const float as = c8 ? C8_S : 1.f;                    // C8: accumulators carry the scale S
+        b[u] = as * gs * (bih->data[u] + bhh->data[u]);             // b_r
+        b[H + u] = as * gs * (bih->data[H + u] + bhh->data[H + u]); // b_z
+        b[2 * H + u] = as * bih->data[2 * H + u];            // b_in
+        b[3 * H + u] = as * bhh->data[2 * H + u];            // b_hn (inside r * (.))
       }
     }
     CCSM_TRY(T.wimg[l].reserve(img.size() * 2));
@@ -1350,7 +1847,8 @@ int tc_upload_weights(ccsm_model* m) {
   for (int which = 0; which < 2; ++which) {
     const HostTensor* w = findw(m, which == 0 ? "_att3.Wa.weight" : "_att3.Ua.weight");
     std::vector<uint16_t> img((size_t)P * 64 * 256 * 8);
-    pack_image(img.data(), 256, 64, 2 * H, P, f16, [&](int n) { return w->data.data() + (size_t)n * 2 * H; });
+    if (c8) c8_ok = pack_image_c8(img.data(), 256, 64, 2 * H, [&](int n) { return w->data.data() + (size_t)n * 2 * H; }) && c8_ok;
+    else pack_image(img.data(), 256, 64, 2 * H, P, f16, [&](int n) { return w->data.data() + (size_t)n * 2 * H; });
     DevBuf& dst = which == 0 ? T.wa_img : T.ua_img;
     CCSM_TRY(dst.reserve(img.size() * 2));
     CCSM_CUDA(cudaMemcpy(dst.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
@@ -1365,8 +1863,14 @@ int tc_upload_weights(ccsm_model* m) {
   CCSM_TRY(up(T.fc_w, "fc1.weight"));
   CCSM_TRY(up(T.fc_b, "fc1.bias"));
   CCSM_TRY(up(T.embed, "embed.weight"));
+  if (!c8_ok) {
+    T.P = 0;
+    set_error("precision fp16c8: a weight times 2^12 leaves the fp16 range; use fp16x3 for this checkpoint");
+    return CCSM_EUNSUPPORTED;
+  }
   T.P = P;
   T.f16 = f16;
+  T.c8 = c8;
   return CCSM_OK;
 }
 
@@ -1409,7 +1913,7 @@ static int gru_variant(int layer, int P) {
   static int v[2] = {-2, -2};
   if (v[0] == -2) {
     const char* e = getenv("CCSM_TC_VARIANT");
-    auto dig = [](char c) { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? 10 + (c - 'a') : -1; };
+    auto dig = [](char c) { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'z') ? 10 + (c - 'a') : -1; };
     v[0] = e ? dig(e[0]) : -1;
     v[1] = (e && e[0] && dig(e[1]) >= 0) ? dig(e[1]) : v[0];
   }
@@ -1420,11 +1924,12 @@ static int gru_variant(int layer, int P) {
   return layer > 0 ? 13 : (P == 2 ? 14 : 12);
 }
 
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false, bool HS = false, bool PIPE = false>
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false, bool HS = false, bool PIPE = false,
+          bool C8 = false>
 static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
   using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>;
   static bool attr = false;
-  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC, HS, PIPE>;
+  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC, HS, PIPE, C8>;
   if (!attr) {
     CCSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr = true;
@@ -1457,8 +1962,19 @@ static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStre
 }
 
 // variant -> (NSLOT, NBUF, KSB); 3 and 4 are the CTA-pair kernels
-template <int P, bool F16>
+template <int P, bool F16, bool C8>
 static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
+  if constexpr (C8) {
+    // the C8 mode is built on the pipelined-epilogue kernels only
+    switch (variant) {
+      case 13: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true, true>(gp, tiles, sm_count, st);
+      case 14: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true, true>(gp, tiles, sm_count, st);
+      case 15: return launch_gru<P, F16, 2, 1, 8, 1, false, false, true, true>(gp, tiles, sm_count, st);
+      default:
+        set_error("precision fp16c8 runs GRU kernel variants d, e, f only (got %d)", variant);
+        return CCSM_EINVAL;
+    }
+  } else
   switch (variant) {
     case 0: return launch_gru<P, F16, 1, 1, 4>(gp, tiles, sm_count, st);
     case 1: return launch_gru<P, F16, 2, 1, 8>(gp, tiles, sm_count, st);
@@ -1484,7 +2000,7 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
   }
 }
 
-template <int P, bool F16>
+template <int P, bool F16, bool C8 = false>
 static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_total, const ccsm_strand* fwd,
                         const ccsm_strand* rev, const float* h0_f, const float* h0_r, float* logits, float* probs,
                         cudaStream_t st) {
@@ -1496,22 +2012,24 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
   TcStrand s0{fwd->kmer, fwd->kpass, fwd->ipd_means, fwd->pw_means}, s1{rev->kmer, rev->kpass, rev->ipd_means, rev->pw_means};
   const int64_t rows = tiles * TILE_ROWS;
   int pid = m->prof.begin(PROF_PREP, (double)sites, st);
-  tc_prep_kernel<P, F16><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(
+  tc_prep_kernel<P, F16, C8><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(
       tiles, sites, site0, n_total, L, NL, m->cfg.n_vocab, (m->cfg.feat_flags & CCSM_FEAT_NPASS) ? 1 : 0, s0, s1,
       T.embed.as<float>(), h0_f, h0_r, m->h0_mode == CCSM_H0_DEVICE_RANDOM ? 1 : 0,
       (unsigned long long)m->h0_seed, (unsigned long long)(m->h0_calls * 256), T.x0img.as<uint8_t>(),
       T.h0img.as<uint8_t>());
   m->prof.end(pid, st);
   count_launch();
-  static bool attr_set[2][2] = {{false, false}, {false, false}};
-  if (!attr_set[P - 1][F16]) {
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)PairCfg<P, 2>::SMEM));
-    CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)PairCfg<P, 1>::SMEM));
-    CCSM_CUDA(cudaFuncSetAttribute(tc_att_head_kernel<P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static bool attr_set = false;  // one flag per instantiation of this function template
+  if (!attr_set) {
+    if constexpr (!C8) {
+      CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)PairCfg<P, 2>::SMEM));
+      CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair_kernel<P, F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)PairCfg<P, 1>::SMEM));
+    }
+    CCSM_CUDA(cudaFuncSetAttribute(tc_att_head_kernel<P, F16, C8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)AttCfg<P>::SMEM));
-    attr_set[P - 1][F16] = true;
+    attr_set = true;
   }
   for (int l = 0; l < NL; ++l) {
     GruParams gp;
@@ -1533,17 +2051,32 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
     }
     pid = m->prof.begin(l == 0 ? PROF_GRU_L0 : PROF_GRU_LN, (double)sites, st);
     const int variant = gru_variant(l, P);
-    if (variant == 3 || variant == 4) {
+    if (variant == 16) {
+      // duo kernel: CTA pairs, both directions interleaved; one cluster per TPC
+      gp.wimg = T.wpair[l].as<uint8_t>();
+      static bool duo_attr = false;
+      if (!duo_attr) {
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_duo_kernel<P, F16, C8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)DuoCfg<P>::SMEM));
+        duo_attr = true;
+      }
+      const int64_t items = tiles / 2;
+      const int64_t max_clusters = T.sm_count / 2;
+      const int clusters = (int)(items < max_clusters ? items : max_clusters);
+      tc_gru_duo_kernel<P, F16, C8><<<2 * clusters, DUO_THREADS, DuoCfg<P>::SMEM, st>>>(gp);
+    } else if (!C8 && (variant == 3 || variant == 4)) {
       gp.wimg = T.wpair[l].as<uint8_t>();
       const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
       const int64_t max_clusters = (variant == 3 ? 1 : 2) * (T.sm_count / 2);
       const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;  // even: fixed direction per cluster
-      if (variant == 3)
-        tc_gru_pair_kernel<P, F16, 2><<<2 * clusters, PAIR_THREADS, PairCfg<P, 2>::SMEM, st>>>(gp);
-      else
-        tc_gru_pair_kernel<P, F16, 1><<<2 * clusters, PAIR_THREADS, PairCfg<P, 1>::SMEM, st>>>(gp);
+      if constexpr (!C8) {
+        if (variant == 3)
+          tc_gru_pair_kernel<P, F16, 2><<<2 * clusters, PAIR_THREADS, PairCfg<P, 2>::SMEM, st>>>(gp);
+        else
+          tc_gru_pair_kernel<P, F16, 1><<<2 * clusters, PAIR_THREADS, PairCfg<P, 1>::SMEM, st>>>(gp);
+      }
     } else {
-      CCSM_TRY((launch_gru_variant<P, F16>(variant, gp, tiles, T.sm_count, st)));
+      CCSM_TRY((launch_gru_variant<P, F16, C8>(variant, gp, tiles, T.sm_count, st)));
     }
     m->prof.end(pid, st);
     count_launch();
@@ -1562,7 +2095,7 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
   ap.sites = sites;
   const int grid = (int)(tiles < T.sm_count ? tiles : T.sm_count);
   pid = m->prof.begin(PROF_ATT, (double)sites, st);
-  tc_att_head_kernel<P, F16><<<grid, ATT_THREADS, AttCfg<P>::SMEM, st>>>(ap);
+  tc_att_head_kernel<P, F16, C8><<<grid, ATT_THREADS, AttCfg<P>::SMEM, st>>>(ap);
   m->prof.end(pid, st);
   count_launch();
   CCSM_CUDA(cudaGetLastError());
@@ -1585,7 +2118,8 @@ int tc_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccs
   for (int64_t s0 = 0; s0 < n; s0 += chunk_sites) {
     const int64_t sites = (n - s0) < chunk_sites ? (n - s0) : chunk_sites;
     int rc;
-    if (T.P == 1 && !T.f16) rc = tc_run_chunk<1, false>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
+    if (T.c8) rc = tc_run_chunk<2, true, true>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
+    else if (T.P == 1 && !T.f16) rc = tc_run_chunk<1, false>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
     else if (T.P == 1 && T.f16) rc = tc_run_chunk<1, true>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
     else if (T.P == 2 && !T.f16) rc = tc_run_chunk<2, false>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
     else rc = tc_run_chunk<2, true>(m, sites, s0, n, fwd, rev, h0_f, h0_r, logits, probs, st);
@@ -1609,7 +2143,8 @@ int tc_debug_layer_out(ccsm_model* m, int layer, float* host, int64_t cap, int64
   const unsigned blocks = (unsigned)((total + 255) / 256);
   const uint8_t* act = T.act[layer % 3].as<uint8_t>();
   CCSM_CUDA(cudaDeviceSynchronize());
-  if (T.P == 1 && !T.f16) tc_unpack_act_kernel<1, false><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
+  if (T.c8) tc_unpack_act_kernel<2, true, true><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
+  else if (T.P == 1 && !T.f16) tc_unpack_act_kernel<1, false><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
   else if (T.P == 1 && T.f16) tc_unpack_act_kernel<1, true><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
   else if (T.P == 2 && !T.f16) tc_unpack_act_kernel<2, false><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);
   else tc_unpack_act_kernel<2, true><<<blocks, 256>>>(act, tmp.as<float>(), rows, L);

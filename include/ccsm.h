@@ -56,6 +56,8 @@ extern "C" {
 #define CCSM_PREC_BF16    2    /* tcgen05, single-pass bf16 in / fp32 accumulate (throughput mode) */
 #define CCSM_PREC_FP16X3  3    /* tcgen05, fp16 hi/lo split, 3 passes (parity mode, ~fp32-exact) */
 #define CCSM_PREC_FP16    4    /* tcgen05, single-pass fp16 in / fp32 accumulate */
+#define CCSM_PREC_FP16C8  5    /* tcgen05, fp16 main pass + two e4m3 (kind::f8f6f4) correction passes at half cost:
+                                  2 pass-equivalents, max |dprob| ~3e-5 (parity mode, default) */
 
 /* feature flags (reference models.py:35-47, CLI --is_npass/--is_stds/--is_sn/--is_map) */
 #define CCSM_FEAT_NPASS 1
@@ -395,6 +397,13 @@ int  ccsm_debug_umma_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, 
  * Z(256,32) = [columns 16..31 after zeroing | columns 0..15 untouched].  Host pointers. */
 int  ccsm_debug_umma_pair_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, const float* A,
                                const float* B, float* D, float* Z);
+/* D (128, N) = fp16(A) . fp16(B)^T (kind::f16) + e4m3(A) . e4m3(B)^T (kind::f8f6f4) accumulated in the same TMEM
+ * columns; A (128, K), B (N, K) host fp32, K a multiple of 32.  Pins the 8-bit operand layout and the mixed-kind
+ * accumulation CCSM_PREC_FP16C8 relies on (tests/test_umma_gpu.py). */
+int  ccsm_debug_umma_mixed_gemm(int32_t device, int32_t N, int32_t K, const float* A, const float* B, float* D);
+/* Tensor-pipe rate probe (one CTA, M = 128, N columns, operands fixed in shared memory): cycles for `iters` rounds of
+ * four MMAs.  mode 0 = kind::f16, 1 = kind::f8f6f4 e4m3, 2 = f16 f16 e4m3 e4m3, 3 = alternating, 4 = rounds alternate. */
+int  ccsm_debug_umma_rate(int32_t device, int32_t N, int32_t mode, int32_t iters, int64_t* cycles);
 
 #ifdef __cplusplus
 }

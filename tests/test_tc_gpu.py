@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 # parity modes must meet the north-star tolerance; single-pass modes are reported and only
 # sanity-bounded here
-TOL = {"fp16x3": 1e-4, "bf16x3": 1e-4, "fp16": 5e-3, "bf16": 3e-2}
+TOL = {"fp16c8": 1e-4, "fp16x3": 1e-4, "bf16x3": 1e-4, "fp16": 5e-3, "bf16": 3e-2}
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +39,7 @@ def layer_out(model, layer, n):
     return buf.reshape(tiles * 128, 21, 512)[:2 * n].reshape(n, 2, 21, 512)
 
 
-@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3", "fp16", "bf16"])
+@pytest.mark.parametrize("prec", ["fp16c8", "fp16x3", "bf16x3", "fp16", "bf16"])
 def test_tc_matches_reference_synth(model, golden_synth, prec):
     model.set_precision(prec)
     _, probs = run(model, golden_synth)
@@ -48,7 +48,7 @@ def test_tc_matches_reference_synth(model, golden_synth, prec):
     assert err <= TOL[prec]
 
 
-@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3"])
+@pytest.mark.parametrize("prec", ["fp16c8", "fp16x3", "bf16x3"])
 def test_tc_layers_match_oracle(model, ckpt_att2s, golden_synth, prec):
     model.set_precision(prec)
     n = 64
@@ -62,18 +62,20 @@ def test_tc_layers_match_oracle(model, ckpt_att2s, golden_synth, prec):
             assert err <= 2e-4, (l, s, err)
 
 
+@pytest.mark.parametrize("prec", ["fp16c8", "fp16x3"])
 @pytest.mark.parametrize("case", EDGE_CASES)
-def test_tc_edge_cases(model, golden_edge, case):
-    model.set_precision("fp16x3")
+def test_tc_edge_cases(model, golden_edge, case, prec):
+    model.set_precision(prec)
     _, probs = run(model, golden_edge, case + ".")
     assert probs.shape == golden_edge[case + ".probs"].shape
     assert np.abs(probs - golden_edge[case + ".probs"]).max() <= 1e-4
 
 
-def test_tc_multi_tile_and_chunks(model, golden_synth):
+@pytest.mark.parametrize("prec", ["fp16c8", "fp16x3"])
+def test_tc_multi_tile_and_chunks(model, golden_synth, prec):
     """More sites than one pair of row tiles and than one library chunk (148*8*64 sites): every replica of the
     256 golden sites must reproduce the reference."""
-    model.set_precision("fp16x3")
+    model.set_precision(prec)
     g = golden_synth
     rep = 300  # 76,800 sites > 75,776 per chunk
     big = {k: np.concatenate([g[k]] * rep, axis=1 if k.startswith("h0") else 0) for k in FEATS + ("h0_f", "h0_r")}
@@ -96,7 +98,7 @@ def test_device_h0_same_noise_in_every_mode(model, golden_synth):
     g = golden_synth
     a = [x.cuda() for x in args16(g)]
     outs = {}
-    for prec in ("fp32", "fp16x3", "bf16x3"):
+    for prec in ("fp32", "fp16x3", "bf16x3", "fp16c8"):
         model.set_precision(prec)
         model.set_h0_mode("device", seed=77)
         _, p1 = model(*a)
@@ -104,6 +106,7 @@ def test_device_h0_same_noise_in_every_mode(model, golden_synth):
         outs[prec] = (p1.cpu().numpy(), p2.cpu().numpy())
     assert np.abs(outs["fp32"][0] - outs["fp16x3"][0]).max() <= 1e-4
     assert np.abs(outs["fp32"][0] - outs["bf16x3"][0]).max() <= 1e-4
+    assert np.abs(outs["fp32"][0] - outs["fp16c8"][0]).max() <= 1e-4
     assert np.abs(outs["fp32"][1] - outs["fp16x3"][1]).max() <= 1e-4
     assert np.abs(outs["fp32"][0] - outs["fp32"][1]).max() > 1e-2       # fresh noise on every call
     assert np.abs(outs["fp32"][0] - g["probs"]).max() > 1e-2            # and not the fixture's h0

@@ -52,3 +52,21 @@ def test_umma_pair_gemm_matches_numpy(N, K, f16):
     assert np.abs(D - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
     assert np.all(Z[:, :16] == 0.0)                      # tcgen05.st zeroed columns 16..31
     assert np.abs(Z[:, 16:] - ref[:, :16]).max() < 1e-3 * max(1.0, np.abs(ref).max())  # neighbours untouched
+
+
+@pytest.mark.parametrize("N,K", [(192, 32), (192, 64), (256, 128), (64, 32)])
+def test_umma_mixed_f16_e4m3_accumulate(N, K):
+    """kind::f16 and kind::f8f6f4 (e4m3, K = 32 per MMA, 16-element slabs) accumulating into the same TMEM columns:
+    the layout and the mixing the fp16c8 precision mode is built on."""
+    from ccsmeth_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(N * 31 + K)
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    D = np.zeros((128, N), dtype=np.float32)
+    vp = ctypes.c_void_p
+    _lib.check(lib.ccsm_debug_umma_mixed_gemm(0, N, K, A.ctypes.data_as(vp), B.ctypes.data_as(vp), D.ctypes.data_as(vp)))
+    q16 = lambda x: torch.from_numpy(x).to(torch.float16).double().numpy()
+    q8 = lambda x: torch.from_numpy(x).to(torch.float8_e4m3fn).double().numpy()
+    ref = q16(A) @ q16(B).T + q8(A) @ q8(B).T
+    assert np.abs(D - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
