@@ -1,29 +1,38 @@
 #!/usr/bin/env python
 """Throughput benchmark of the call_mods attbigru2s inference path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16] [--sites S] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16c8] [--sites S]
+                    [--scaling weak|strong --total-sites T] [--impl ours|reference]
 
-A "step" = one pass of the hot path (ModelAttRNN forward: two-strand embedding + 3-layer BiGRU +
-attention + FC/softmax) over one batch of S synthetic CpG sites per GPU (config "synthetic 1M x 21 x
-feat feature tensor, attbigru2s forward, 1xB200, bf16-in/fp32-accum": S = 2^20 per GPU, weak scaling).
+A "step" = one pass of the hot path (ModelAttRNN forward: two-strand embedding + 3-layer BiGRU + attention +
+FC/softmax) over one batch of synthetic CpG sites (BASELINE config 2: 2^20 x 21 x feat per GPU, weak scaling;
+`--scaling strong --total-sites 67108864` is config 4: 64 M sites split over the ranks).
 
-  value      sites/s, whole job, inputs (features + explicit h0) resident in HBM, CUDA-event timed,
-             max over ranks.
-  e2e        the same metric through the host-buffer C-ABI call (ccsm_forward_att2s_host via
-             ModelAttRNN.forward_host): pinned host features + h0 in, probabilities out, copies inside the
-             timed region.
-  roofline   tensor-core bound: 244.23 MFLOP of GEMM work per site / measured bf16 peak.
-  cpu_baseline  the oracle's torch-CPU port (same ATen calls as the reference forward) on the host cores.
+The headline (`value`, `e2e`, `roofline`, `dtype`) is the PARITY precision `fp16c8` -- fp16 tensor-core pass plus two
+e4m3 correction passes, fp32 accumulate, max |dprob| <= 1e-4 against the fp32 CPU forward (checked in this run on
+`parity_sites` sites).  `throughput_mode` repeats the step in single-pass bf16 (BASELINE config 2's "bf16-in /
+fp32-accum"; its max |dprob| is reported, it does not meet 1e-4).
 
-`--impl reference` times that CPU port only (the reference's own CPU implementation of the path cannot
-travel to the GPU box: it is Python importing absent I/O deps; oracle/torch_port.py issues the same ATen
-calls).
+  value         sites/s, whole job, features + explicit h0 resident in HBM, CUDA-event timed, max over ranks
+  e2e           the same metric through the host-buffer C-ABI call (ccsm_forward_att2s_host): pinned host features in,
+                probabilities out, copies inside the timed region, same number of sites as `value`
+  roofline      dominant kernel (GRU layer kernel): algorithmic GEMM FLOPs / its CUDA-event time vs the measured bf16 peak
+  cpu_baseline  the reference's own CPU forward on this box's host cores (oracle/ref_cpu_bench.py in a process with CUDA
+                hidden; kind "reference" = the unmodified reference package staged under oracle/_ref, else the torch port)
+  configs       N = 1 only: BASELINE configs 3 (demo reads x40, BAM in -> modbam out, parity precision) and 5 (aggregate
+                model on synthetic pileup windows), each with its own clock record and CPU baseline
+
+`--impl reference` times the reference's CPU forward alone (rank 0 only under torchrun).
 """
+import os
+import sys
+
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"]:
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""   # before torch: the reference must take its CPU path
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -36,9 +45,13 @@ sys.path.insert(0, ROOT)
 FLOP_PER_SITE = 244233216.0      # SURVEY.md section 8d (MAC x 2, both strands)
 FLOP_GRU_L0 = 2.0 * (709632 + 16515072)      # per site: layer-0 input + recurrent GEMMs, both strands, both dirs
 FLOP_GRU_LN = 2.0 * (33030144 + 16515072)    # per site per layer >= 1
+FLOP_ATT = 2.0 * (5505024 + 262144 + 32256 + 2048)
 ALG_BYTES_PER_SITE = 720.0 + 12288.0  # reference 16-tensor fp32 layout + explicit fp32 h0
 FEATS = ("kmer", "kpass", "ipd", "pw", "kmer2", "kpass2", "ipd2", "pw2")
 METRIC = "CpG sites/sec call_mods attbigru2s seq21"
+DTYPE = {"bf16": "bf16", "bf16x3": "bf16x3", "fp16": "f16", "fp16x3": "f16x3", "fp16c8": "f16+e4m3 (fp32 accumulate)",
+         "fp32": "f32"}
+PASSES = {"bf16": 1.0, "fp16": 1.0, "bf16x3": 3.0, "fp16x3": 3.0, "fp16c8": 2.0, "fp32": 1.0}
 
 
 def load_peaks():
@@ -55,7 +68,7 @@ def load_ckpt():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING a timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -68,12 +81,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -87,7 +101,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -96,60 +110,200 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_throughput(ck, batches, batch_size=512, warmup=1, threads=None):
-    """The oracle's torch-CPU port on the host cores: forward over `batches` x `batch_size` sites
-    (the reference's own per-call batch, call_modifications.py:668), h0 drawn per call like the reference."""
-    from oracle import torch_port
-    from ccsmeth_b200 import synth
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    m = torch_port.load_numpy_state(torch_port.Att2sPort(), ck)
-    b = synth.make_batch(batch_size, seed=synth.SEED, with_h0=False)
-    a = [b[k] for k in FEATS]
-    for _ in range(warmup):
-        m(*a)
-    t0 = time.perf_counter()
-    for _ in range(batches):
-        m(*a)
-    dt = time.perf_counter() - t0
-    return batches * batch_size / dt, dt, threads
+def cpu_baseline(mode, extra=()):
+    """oracle/ref_cpu_bench.py in its own process with CUDA hidden (the reference's use_cuda switch must stay off)."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_cpu_bench.py"), mode] + [str(x) for x in extra]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as e:  # the bench line must still be printed
+        return {"mode": mode, "kind": "failed", "value": None, "error": repr(e)[:200]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ck = load_ckpt()
-    bs, per_step = 512, 4
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_cpu_bench as rcb
     cores = os.cpu_count()
-    cpu_port_throughput(ck, 1, bs, warmup=max(1, args.warmup) - 1 if args.warmup > 1 else 1)
+    torch.set_num_threads(cores)
+    bs, per_step = 512, 4
+    ns = argparse.Namespace(batch_size=bs, batches=per_step, warmup=0)
+    w = argparse.Namespace(batch_size=bs, batches=max(1, args.warmup), warmup=0)
+    rcb.forward(w)
     t0 = time.perf_counter()
-    sites = 0
+    kind = "port"
     for _ in range(args.steps):
-        v, dt, _ = cpu_port_throughput(ck, per_step, bs, warmup=0)
-        sites += per_step * bs
+        kind = rcb.forward(ns)["kind"]
     dt = time.perf_counter() - t0
-    val = sites / dt
+    val = args.steps * per_step * bs / dt
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "sites/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "synthetic (batch,21,feat) attbigru2s forward, bounded sample: %d batches x %d sites "
                                   "per step on host cores" % (per_step, bs), "kmer_len": 21},
-           "cpu_baseline": {"value": val, "unit": "sites/s", "cores": cores, "kind": "port",
-                            "sample": "%d steps x %d batches x %d sites, torch %s CPU, %d threads" %
-                                      (args.steps, per_step, bs, torch.__version__, cores)},
+           "cpu_baseline": {"value": val, "unit": "sites/s", "cores": cores, "kind": kind,
+                            "sample": "%d steps x %d batches x %d sites, %s ModelAttRNN.forward, torch %s CPU, %d threads" %
+                                      (args.steps, per_step, bs, "unmodified reference (oracle/_ref)" if kind == "reference"
+                                       else "torch port of the reference", torch.__version__, cores)},
            "e2e": {"value": val, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
+
+
+def gru_roofline(prof, prec, peaks):
+    """roofline object for the dominant kernel from the library's per-launch CUDA events."""
+    g_ms = prof["gru_l0"][0] + prof["gru_ln"][0]
+    if g_ms <= 0:
+        return None
+    g_flop = prof["gru_l0"][1] * FLOP_GRU_L0 + prof["gru_ln"][1] * FLOP_GRU_LN
+    g_launch = prof["gru_l0"][2] + prof["gru_ln"][2]
+    ach = g_flop / (g_ms * 1e-3) / 1e12
+    tot_ms = sum(v[0] for v in prof.values())
+    traffic, tsrc = None, None
+    tp = os.path.join(ROOT, "profiles", "ncu_gru_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = tj.get(prec)
+        tsrc = "static: per-launch dram bytes of the ncu --set full capture named in profiles/ncu_gru_traffic.json, " \
+               "not measured in this run"
+    per = {}
+    for k, fl in (("gru_l0", FLOP_GRU_L0), ("gru_ln", FLOP_GRU_LN), ("att_head", FLOP_ATT)):
+        if prof[k][0] > 0:
+            tf = prof[k][1] * fl / (prof[k][0] * 1e-3) / 1e12
+            per[k] = {"ms": round(prof[k][0], 3), "launches": prof[k][2], "tflops": tf, "frac": tf / peaks["bf16_tflops"]}
+    return {"bound": "tensor", "kernel": "tc_gru_layer_kernel<%s>" % prec, "achieved": ach,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+            "traffic": traffic, "traffic_source": tsrc, "flop_per_launch": g_flop / g_launch,
+            "ms_per_launch": g_ms / g_launch, "launches": g_launch, "share_of_step": g_ms / tot_ms,
+            "issued_frac": PASSES[prec] * ach / peaks["bf16_tflops"],
+            "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[2]}, "per_kernel": per,
+            "note": "algorithmic GEMM FLOPs (SURVEY.md 8d) of the GRU layer launches / their CUDA-event time, vs %s "
+                    "sustained bf16 cuBLAS peak; issued_frac counts the MMA pass-equivalents the mode issues per "
+                    "algorithmic MAC (fp16c8: 2, x3: 3)" % peaks["source"]}
+
+
+def timed_steps(step, steps, parallel):
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    out = None
+    for _ in range(steps):
+        out = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    return parallel.allreduce_max(ev0.elapsed_time(ev1)), out
+
+
+def demo_config(prec, local, rep=40):
+    """BASELINE config 3 at steady state: the demo reads x rep, BAM in -> device extraction -> forward -> MM/ML ->
+    modbam out through the call_mods pipeline, parity precision, own clock record."""
+    import shutil
+    import tempfile
+    from collections import OrderedDict
+    from ccsmeth_b200 import call_mods as cm
+    from ccsmeth_b200.bamio import BamReader, BamWriter
+    ck = load_ckpt()
+    tmp = tempfile.mkdtemp(prefix="ccsm_bench_demo_")
+    ckpt = os.path.join(tmp, "model_v3.ckpt")
+    torch.save(OrderedDict((k, torch.from_numpy(v)) for k, v in ck.items()), ckpt)
+    demo = os.path.join(ROOT, "tests", "golden", "demo", "hg002.chr20_demo.hifi.bam")
+    big = os.path.join(tmp, "demo_x%d.bam" % rep)
+    rd = BamReader(demo)
+    recs = list(rd)
+    wr = BamWriter(big, rd.header_text, rd.references, threads=os.cpu_count())
+    for k in range(rep):
+        for r in recs:
+            nm = r.raw[32:32 + r.l_read_name - 1] + b"/%d" % k + b"\x00"
+            raw = bytearray(r.raw[:32]) + nm + r.raw[32 + r.l_read_name:]
+            raw[8] = len(nm)
+            wr.write_raw(bytes(raw))
+    wr.close()
+    res = {"workload": "demo/hg002.chr20_demo.hifi.bam reads x%d (%d reads, %.0f MB BAM): call_mods BAM in -> modbam out, "
+                       "1xB200, %s" % (rep, rep * len(recs), os.path.getsize(big) / 1e6, prec), "precision": prec,
+           "host_threads": os.cpu_count()}
+
+    def run(inp, extra, out):
+        a = cm.build_parser().parse_args(["-i", inp, "-m", ckpt, "-o", out, "--precision", prec, "--threads",
+                                          str(os.cpu_count())] + extra)
+        t0 = time.perf_counter()
+        counts, _ = cm.call_mods(a)
+        return counts, time.perf_counter() - t0
+
+    run(demo, ["--h0", "device"], os.path.join(tmp, "warm"))
+    for mode in ("device", "reference"):
+        run(big, ["--h0", mode], os.path.join(tmp, "out"))  # warm-up (workspace growth, page cache)
+        sampler = ClockSampler(local).start()
+        best, counts = None, None
+        for _ in range(2):
+            counts, dt = run(big, ["--h0", mode], os.path.join(tmp, "out"))
+            best = dt if best is None else min(best, dt)
+        res["h0_" + mode] = {"sites": counts["sites"], "seconds": best, "value": counts["sites"] / best, "unit": "sites/s",
+                             "clocks": sampler.stop()}
+    c, dt = run(demo, [], os.path.join(tmp, "demo1"))
+    res["demo_bam_itself"] = {"sites": c["sites"], "seconds": dt, "h0": "reference stream (site-comparable with the reference)"}
+    shutil.rmtree(tmp, ignore_errors=True)
+    return res
+
+
+def aggr_config(local, n=1 << 20):
+    """BASELINE config 5: the aggregate model (attbigru_b11.v2p) on synthetic pileup windows, HBM roofline."""
+    from ccsmeth_b200.models import AggrAttRNN
+    from oracle import torch_port
+    peaks = load_peaks()
+    ck = dict(np.load(os.path.join(ROOT, "tests", "golden", "ckpt_aggr_v2p.npz")))
+    m = AggrAttRNN(11, 1, 1, 0, 32, binsize=20, model_type="attbigru", device=local)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ck.items()})
+    m = m.cuda(local).eval()
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev).manual_seed(20261017)
+    histos = torch.rand((n, 11, 20), generator=g, device=dev)
+    histos = torch.round(histos / histos.norm(dim=2, keepdim=True) * 1e6) / 1e6
+    offsets = torch.randint(0, 1200, (n, 11), generator=g, device=dev).float()
+    h0 = torch.randn((2, n, 32), generator=g, device=dev)
+    for _ in range(3):
+        out = m(offsets, histos, h0=h0)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local).start()
+    K = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = m(offsets, histos, h0=h0)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / K
+    port = torch_port.load_numpy_state(torch_port.AggrPort(), ck)
+    P = 4096
+    with torch.no_grad():
+        ref = port(offsets[:P].cpu(), histos[:P].cpu(), h0[:, :P].cpu().contiguous())
+    d = float((out[:P].cpu() - ref).abs().max())
+    val = n / (ms * 1e-3)
+    gbs = val * 1184.0 / 1e9
+    return {"workload": "call_freqb aggregate attbigru_b11.v2p forward, synthetic (n,11,21) windows, %d sites, 1xB200, fp32" % n,
+            "value": val, "unit": "sites/s", "ms_per_step": ms, "steps": K, "dtype": "f32", "clocks": clocks,
+            "max_abs_diff_vs_cpu_port": d, "parity_sites": P,
+            "roofline": {"bound": "hbm", "kernel": "aggr_tiled_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                         "note": "1,184 algorithmic bytes per site with the windows materialised as the reference does "
+                                 "(SURVEY.md 8d); the kernel is FP32-issue-bound (137.6 kMAC/site on K = 21/32/64 "
+                                 "contractions), not HBM-bound"}}
 
 
 def main():
@@ -158,12 +312,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CCSM_BENCH_PRECISION", "bf16"))
-    ap.add_argument("--sites", type=int, default=1 << 20, help="sites per GPU per step")
-    ap.add_argument("--e2e-sites", type=int, default=1 << 18, help="sites per GPU per e2e step")
+    ap.add_argument("--precision", default=os.environ.get("CCSM_BENCH_PRECISION", "fp16c8"))
+    ap.add_argument("--throughput-precision", default="bf16")
+    ap.add_argument("--sites", type=int, default=1 << 20, help="sites per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-sites", type=int, default=1 << 26, help="--scaling strong: sites per step over all ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-parity-mode", action="store_true", help="skip the extra fp16x3 timing leg")
-    ap.add_argument("--parity-sites", type=int, default=2048)
+    ap.add_argument("--no-throughput-mode", action="store_true", help="skip the extra single-pass bf16 leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 3 / config 5 legs")
+    ap.add_argument("--parity-sites", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,110 +334,99 @@ def main():
     dev = torch.device("cuda", local)
     _lib.load()
     ck = load_ckpt()
+    peaks = load_peaks()
     m = ModelAttRNN(21, 3, 2, 0, 256, is_npass=True, model_type="attbigru2s", device=local)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in ck.items()})
     m = m.cuda(local).eval()
     prec = args.precision
-    try:
-        m.set_precision(prec)
-        m._ensure_handle()
-    except _lib.CcsmError as e:
-        if e.code != _lib.EUNSUPPORTED:
-            raise
-        prec = "fp32"
-        m.set_precision(prec)
-    S = args.sites
-    # inputs resident in HBM: features (n,21) fp32 x8 + explicit h0 (6,n,256) fp32 x2, per-rank seed
-    b = synth.make_batch(S, seed=synth.SEED + rank, device=dev, with_h0=False)
-    g = torch.Generator(device=dev).manual_seed(synth.SEED + 1000 + rank)
-    h0 = []
-    for _ in range(2):
-        h = torch.empty((6, S, 256), device=dev)
-        for l in range(6):
-            h[l].normal_(generator=g)
-        h0.append(h)
+    m.set_precision(prec)
+    m._ensure_handle()
+    strong = args.scaling == "strong"
+    S = args.total_sites // world if strong else args.sites
+    # inputs resident in HBM: features (n,21) fp32 x8, generated in slabs; weak: + explicit h0 (6,n,256) fp32 x2
+    SL = 1 << 22
+    parts = [synth.make_batch(min(SL, S - o), seed=synth.SEED + rank + 7919 * (o // SL), device=dev, with_h0=False)
+             for o in range(0, S, SL)]
+    b = {k: (torch.cat([p[k] for p in parts]) if len(parts) > 1 else parts[0][k]) for k in parts[0]}
+    del parts
     fargs = synth.to_forward_args(b)
+    explicit_h0 = not strong
+    h0 = None
+    if explicit_h0:
+        g = torch.Generator(device=dev).manual_seed(synth.SEED + 1000 + rank)
+        h0 = []
+        for _ in range(2):
+            h = torch.empty((6, S, 256), device=dev)
+            for l in range(6):
+                h[l].normal_(generator=g)
+            h0.append(h)
+    else:
+        m.set_h0_mode("device", seed=synth.SEED + rank)
 
     def step():
-        return m(*fargs, h0=(h0[0], h0[1]))
+        return m(*fargs, h0=(h0[0], h0[1])) if explicit_h0 else m(*fargs)
 
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    parallel.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     m.profile(True)
     m.profile_read()
     l0 = _lib.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        logits, probs = step()
-    ev1.record()
-    torch.cuda.synchronize()
-    parallel.barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms_max, (logits, probs) = timed_steps(step, args.steps, parallel)
     launches = _lib.kernel_launches() - l0
-    ms_max = parallel.allreduce_max(ms)
     clocks = sampler.stop() if rank == 0 else None
     value = world * S * args.steps / (ms_max * 1e-3)
-
-    # per-kernel device times (library-side CUDA events on the launching stream, recorded inside the timed region)
-    prof = m.profile_read()
+    prof = m.profile_read()   # per-kernel device times: library CUDA events on the launching stream, inside the timed region
     m.profile(False)
+    probs_main = probs[:min(args.parity_sites, S)].cpu() if explicit_h0 else None
 
-    # ---- the same step in the <= 1e-4 parity mode (3-pass fp16 split), so that one line carries both numbers
-    parity_leg = None
-    if prec in ("bf16", "fp16") and not args.no_parity_mode:
-        m.set_precision("fp16x3")
+    # ---- single-pass bf16 (BASELINE config 2's "bf16-in/fp32-accum") on the same step
+    tp_leg, tprobs_c = None, None
+    if not args.no_throughput_mode and prec != args.throughput_precision:
+        tprec = args.throughput_precision
+        m.set_precision(tprec)
         for _ in range(2):
             step()
-        torch.cuda.synchronize()
-        parallel.barrier()
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record()
-        for _ in range(max(2, args.steps // 2)):
-            _, probs_x3 = step()
-        pe1.record()
-        torch.cuda.synchronize()
-        pms = parallel.allreduce_max(pe0.elapsed_time(pe1))
-        parity_leg = {"precision": "fp16x3", "value": world * S * max(2, args.steps // 2) / (pms * 1e-3), "unit": "sites/s",
-                      "steps": max(2, args.steps // 2)}
+        tsampler = ClockSampler(local)
+        if rank == 0:
+            tsampler.start()
+        m.profile(True)
+        m.profile_read()
+        tsteps = max(2, args.steps)
+        tms, (_, tprobs) = timed_steps(step, tsteps, parallel)
+        tprof = m.profile_read()
+        m.profile(False)
+        tp_leg = {"precision": tprec, "dtype": DTYPE[tprec], "value": world * S * tsteps / (tms * 1e-3), "unit": "sites/s",
+                  "steps": tsteps, "ms_per_step": tms / tsteps, "clocks": tsampler.stop() if rank == 0 else None,
+                  "roofline": gru_roofline(tprof, tprec, peaks)}
+        tprobs_c = tprobs[:min(args.parity_sites, S)].cpu() if explicit_h0 else None
         m.set_precision(prec)
 
-    # ---- e2e: host buffers through the C-ABI host entry (ccsm_forward_att2s_host).
-    # Like the reference's forward, the model draws h0 itself (models.py:77-87,125-130) -- here on the device
-    # (Philox, CCSM_H0_DEVICE_RANDOM) -- so the caller hands over only the 8 feature tensors and reads back probs.
-    E = min(args.e2e_sites, S)
-    hb = synth.make_batch(E, seed=synth.SEED + 77 + rank, with_h0=False)
-    hfeats = {k: hb[k].pin_memory() for k in FEATS}
+    # ---- e2e: host buffers through the C-ABI host entry (ccsm_forward_att2s_host), same number of sites as `value`.
+    # Like the reference's forward, the model draws h0 itself (models.py:77-87,125-130) -- here on the device -- so the
+    # caller hands over only the 8 feature tensors and reads back logits + probs.
+    E = min(S, 1 << 22)
+    hfeats = {k: b[k][:E].cpu().pin_memory() for k in FEATS}
     m.set_h0_mode("device", seed=synth.SEED + rank)
-    for _ in range(max(1, args.warmup - 1)):
+    for _ in range(max(1, min(2, args.warmup - 1))):
         m.forward_host(hfeats)
+    esteps = max(2, min(args.steps, 8))
     parallel.barrier()
+    esampler = ClockSampler(local)
+    if rank == 0:
+        esampler.start()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(esteps):
         _, p_host = m.forward_host(hfeats)
-    e2e_s = time.perf_counter() - t0
-    e2e_s = parallel.allreduce_max(e2e_s)
-    e2e_val = world * E * args.steps / e2e_s
+    e2e_s = parallel.allreduce_max(time.perf_counter() - t0)
+    eclocks = esampler.stop() if rank == 0 else None
+    e2e_val = world * E * esteps / e2e_s
     h2d = E * (8 * 21 * 4)
     d2h = E * 2 * 2 * 4
-    # same call with an explicit host-resident h0 (parity-style use): +12,288 B/site over PCIe
-    m.set_h0_mode("reference")
-    E2 = min(E, 1 << 17)
-    hh0 = (torch.randn(6, E2, 256).pin_memory(), torch.randn(6, E2, 256).pin_memory())
-    hf2 = {k: v[:E2] for k, v in hfeats.items()}
-    m.forward_host(hf2, h0=hh0)
-    parallel.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        m.forward_host(hf2, h0=hh0)
-    e2e2_s = parallel.allreduce_max(time.perf_counter() - t0)
-    e2e_host_h0 = world * E2 * args.steps / e2e2_s
+    if explicit_h0:
+        m.set_h0_mode("reference")
 
     # ---- end-of-run count all-reduce (the path's only collective: SURVEY.md section 8e)
     counts = parallel.allreduce_counts([S * args.steps, -(-S // 512) * args.steps, 0, 0])
@@ -290,66 +436,68 @@ def main():
         return
 
     # ---- parity of the timed configuration on a slice, vs the CPU oracle port with the same h0
-    from oracle import torch_port
+    dprob = None
     P = min(args.parity_sites, S)
-    port = torch_port.load_numpy_state(torch_port.Att2sPort(), ck)
-    torch.set_num_threads(os.cpu_count())
-    with torch.no_grad():
-        _, ref = port(*[b[k][:P].cpu() for k in FEATS], h0[0][:, :P].cpu().contiguous(), h0[1][:, :P].cpu().contiguous())
-    dprob = float((probs[:P].cpu() - ref).abs().max())
-    if parity_leg is not None:
-        parity_leg["max_abs_dprob_vs_cpu_port"] = float((probs_x3[:P].cpu() - ref).abs().max())
-        parity_leg["roofline_issued_frac"] = 3.0 * parity_leg["value"] / world * FLOP_PER_SITE / 1e12 / load_peaks()["bf16_tflops"]
+    if explicit_h0:
+        from oracle import torch_port
+        port = torch_port.load_numpy_state(torch_port.Att2sPort(), ck)
+        torch.set_num_threads(os.cpu_count())
+        with torch.no_grad():
+            _, ref = port(*[b[k][:P].cpu() for k in FEATS], h0[0][:, :P].cpu().contiguous(), h0[1][:, :P].cpu().contiguous())
+        dprob = float((probs_main - ref).abs().max())
+        if tprobs_c is not None:
+            tp_leg["max_abs_dprob_vs_cpu_port"] = float((tprobs_c - ref).abs().max())
+            tp_leg["parity_sites"] = P
 
-    peaks = load_peaks()
     tflops = value / world * FLOP_PER_SITE / 1e12
-    roof = {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": tflops / peaks["bf16_tflops"], "traffic": None, "kernel": "whole forward (all kernels)",
-            "note": "per GPU vs %s sustained bf16 peak; 244.23 MFLOP/site" % peaks["source"]}
-    g_ms = prof["gru_l0"][0] + prof["gru_ln"][0]
-    if g_ms > 0:
-        # dominant kernel = tc_gru_layer_kernel (3 launches per chunk: layer 0 with K_in=16, layers 1-2 with K_in=512)
-        g_flop = prof["gru_l0"][1] * FLOP_GRU_L0 + prof["gru_ln"][1] * FLOP_GRU_LN
-        g_launch = prof["gru_l0"][2] + prof["gru_ln"][2]
-        ach = g_flop / (g_ms * 1e-3) / 1e12
-        tot_ms = sum(v[0] for v in prof.values())
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_gru_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(prec)
-        roof = {"bound": "tensor", "kernel": "tc_gru_layer_kernel<%s>" % prec, "achieved": ach,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                "traffic": traffic, "flop_per_launch": g_flop / g_launch, "ms_per_launch": g_ms / g_launch,
-                "launches": g_launch, "share_of_step": g_ms / tot_ms,
-                "issued_frac": (3.0 if prec.endswith("x3") else 1.0) * ach / peaks["bf16_tflops"],
-                "whole_forward_tflops": tflops, "whole_forward_frac": tflops / peaks["bf16_tflops"],
-                "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[2]},
-                "note": "algorithmic GEMM FLOPs (SURVEY.md 8d) of the GRU layer launches / their CUDA-event time, "
-                        "vs %s sustained bf16 cuBLAS peak; x3 modes issue 3 MMAs per algorithmic MAC (issued_frac)"
-                        % peaks["source"]}
+    roof = gru_roofline(prof, prec, peaks) or {
+        "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": tflops / peaks["bf16_tflops"], "traffic": None, "kernel": "whole forward (all kernels)"}
+    roof["whole_forward_tflops"] = tflops
+    roof["whole_forward_frac"] = tflops / peaks["bf16_tflops"]
     out = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp16": "f16", "fp16x3": "f16x3",
-                                          "fp16c8": "f16+e4m3", "fp32": "f32"}[prec],
-           "data": "synthetic",
-           "config": {"workload": "synthetic %dx21xfeat per GPU, attbigru2s forward (v3 checkpoint weights), %s" % (S, prec),
+           "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+           "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE[prec], "data": "synthetic",
+           "config": {"workload": "synthetic %dx21xfeat per GPU%s, attbigru2s forward (v3 checkpoint weights), %s" %
+                                  (S, " (%d total, strong scaling)" % (S * world) if strong else "", prec),
                       "sites_per_gpu_per_step": S, "kmer_len": 21, "precision": prec,
-                      "l2": "inputs (%.1f GB/step) larger than L2" % (S * ALG_BYTES_PER_SITE / 1e9),
+                      "h0": "explicit fp32 (6,n,256) x2 resident in HBM" if explicit_h0 else
+                            "drawn inside the feature-packing kernel (Philox), like the reference's forward draws it internally",
+                      "l2": "inputs (%.1f GB/step) larger than L2" % (S * (ALG_BYTES_PER_SITE if explicit_h0 else 720.0) / 1e9),
                       "parallelism": "dp%d (reads sharded per rank, no data-path collective)" % world},
-           "max_abs_dprob_vs_cpu_port": dprob, "parity_sites": P, "parity_mode": parity_leg,
+           "max_abs_dprob_vs_cpu_port": dprob, "parity_sites": P if explicit_h0 else 0, "parity_tolerance": 1e-4,
+           "throughput_mode": tp_leg,
            "e2e": {"value": e2e_val, "unit": "sites/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "sites_per_step": E, "timer": "host wall clock around ccsm_forward_att2s_host, max over ranks",
-                   "h0": "drawn on device by the library (the reference's forward also draws h0 internally)",
-                   "with_explicit_host_h0": {"value": e2e_host_h0, "sites_per_step": E2,
-                                             "h2d_bytes_per_step": E2 * (8 * 21 * 4 + 2 * 6 * 256 * 4)}},
+                   "sites_per_step": E, "steps": esteps, "precision": prec, "clocks": eclocks,
+                   "timer": "host wall clock around ccsm_forward_att2s_host (pinned host features in, host logits + probs "
+                            "out), max over ranks",
+                   "h0": "drawn on device by the library (the reference's forward also draws h0 internally)"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-           "allreduce_counts": {"sites": counts[0], "model_batches": counts[1]}}
+           "allreduce_counts": {"sites": counts[0], "model_batches": counts[1], "reads": counts[2], "reads_with_mm": counts[3]}}
+    if world == 1 and not args.no_configs and not strong:
+        cfgs = {}
+        del h0, b, fargs, hfeats
+        torch.cuda.empty_cache()
+        try:
+            cfgs["demo_e2e"] = demo_config(prec, local)
+        except Exception as e:
+            cfgs["demo_e2e"] = {"error": repr(e)[:300]}
+        try:
+            cfgs["aggr"] = aggr_config(local)
+        except Exception as e:
+            cfgs["aggr"] = {"error": repr(e)[:300]}
+        if not args.no_cpu_baseline:
+            cb = cpu_baseline("demo", ["--repeats", 1])
+            if "error" not in cfgs["demo_e2e"]:
+                cfgs["demo_e2e"]["cpu_baseline"] = cb
+            cb = cpu_baseline("aggr", ["--batches", 200])
+            if "error" not in cfgs["aggr"]:
+                cfgs["aggr"]["cpu_baseline"] = cb
+        out["configs"] = cfgs
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count()
-        v, dt, th = cpu_port_throughput(ck, 64, 512, warmup=2)
-        out["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": th, "kind": "port",
-                               "sample": "64 batches x 512 sites (%.1f s), torch %s CPU ATen path of the reference forward"
-                                         % (dt, torch.__version__)}
+        cb = cpu_baseline("forward", ["--batches", 48, "--warmup", 2])
+        out["cpu_baseline"] = {"value": cb.get("value"), "unit": "sites/s", "cores": cb.get("cores"), "kind": cb.get("kind"),
+                               "sample": cb.get("sample"), "seconds": cb.get("seconds")}
     print(json.dumps(out))
     parallel.finalize()
 

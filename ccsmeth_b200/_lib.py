@@ -81,6 +81,19 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def source_hash():
+    """sha256 over every source the library is built from (names + contents, sorted): ties a loaded .so to its sources
+    (the hash is printed by __graft_entry__.build() and recorded in profiles/sass_summary.md)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+        sorted(glob.glob(os.path.join(INCLUDE, "*.h")))
+    for p in deps:
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True

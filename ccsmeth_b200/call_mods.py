@@ -365,8 +365,8 @@ def build_parser():
     p.add_argument("--bam_compress", type=str, default="rle", choices=["rle", "zlib"],
                    help="ccsmeth_b200 only: BGZF block compression of the output modbam: 'rle' = run-length + Huffman "
                         "(zlib Z_RLE; 3-4x faster on HiFi records, size within 3 %%), 'zlib' = default strategy, level 6")
-    p.add_argument("--precision", type=str, default=None, choices=["fp32", "fp16x3", "bf16x3", "fp16", "bf16"],
-                   help="ccsmeth_b200 only: arithmetic mode (default fp16x3, <= 1e-4 vs the fp32 reference)")
+    p.add_argument("--precision", type=str, default=None, choices=["fp32", "fp16c8", "fp16x3", "bf16x3", "fp16", "bf16"],
+                   help="ccsmeth_b200 only: arithmetic mode (default fp16c8, <= 1e-4 vs the fp32 reference)")
     return p
 
 

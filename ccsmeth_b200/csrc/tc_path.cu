@@ -1970,8 +1970,9 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
       case 13: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true, true>(gp, tiles, sm_count, st);
       case 14: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true, true>(gp, tiles, sm_count, st);
       case 15: return launch_gru<P, F16, 2, 1, 8, 1, false, false, true, true>(gp, tiles, sm_count, st);
+      case 17: return launch_gru<P, F16, 1, 1, 8, 1, false, false, true, true>(gp, tiles, sm_count, st);  // two CTAs per SM
       default:
-        set_error("precision fp16c8 runs GRU kernel variants d, e, f only (got %d)", variant);
+        set_error("precision fp16c8 runs GRU kernel variants d, e, f, g, h only (got %d)", variant);
         return CCSM_EINVAL;
     }
   } else
@@ -1994,6 +1995,7 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
     case 13: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 2 + pipelined epilogue
     case 14: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true>(gp, tiles, sm_count, st);  // 6 + pipelined epilogue
     case 15: return launch_gru<P, F16, 2, 1, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 1 + pipelined epilogue
+    case 17: return launch_gru<P, F16, 1, 1, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 5 + pipelined epilogue
     default:
       set_error("unknown GRU kernel variant %d", variant);
       return CCSM_EINVAL;

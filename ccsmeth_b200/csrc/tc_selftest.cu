@@ -307,6 +307,58 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int mode, int 
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+
+// Same probe for a CTA pair (tcgen05.mma.cta_group::2, M = 256, each CTA holds N/2 rows of B): mode 0 = kind::f16.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pair_kernel(int N, int mode, int iters,
+                                                                                        long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[1];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  const uint32_t bar_done = smem_u32(&bars[0]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 256);
+    tmem_relinquish2();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0 && rank == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(256, N, true), idesc8 = make_idesc_e4m3(256, N);
+      const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 16384;
+      const uint32_t a_lbo = 2048, b_lbo = (uint32_t)(N / 2) * 16u, sbo = 128;
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool f8 = mode == 1 || (mode == 3 && (q & 1));
+          const uint64_t ad = make_smem_desc(sA + q * 2 * a_lbo, a_lbo, sbo), bd = make_smem_desc(sB + q * 2 * b_lbo, b_lbo, sbo);
+          if (f8) umma_f8_pair(tmem, ad, bd, idesc8, 1u);
+          else umma_f16_pair(tmem, ad, bd, idesc, 1u);
+        }
+      }
+      umma_commit_pair(bar_done, 0x3);
+      mbar_wait(bar_done, 0);
+      *cycles = clock64() - t0;
+    }
+    __syncwarp();
+  } else if (warp == 0) {
+    mbar_wait(bar_done, 0);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem, 256);
+}
+
 // rows x K floats -> e4m3 image: K/16 slabs of (rows x 16 B)
 static void pack_rows_e4m3(const float* src, int rows, int K, std::vector<uint8_t>& img) {
   img.assign((size_t)rows * K, 0);
@@ -451,7 +503,7 @@ extern "C" int ccsm_debug_umma_gemm(int32_t device, int32_t N, int32_t K, int32_
 }
 
 extern "C" int ccsm_debug_umma_rate(int32_t device, int32_t N, int32_t mode, int32_t iters, int64_t* cycles) {
-  if (N < 16 || N > 256 || N % 16 || mode < 0 || mode > 4 || iters < 1 || !cycles) {
+  if (N < 16 || N > 256 || N % 32 || mode < 0 || (mode > 4 && mode < 16) || mode > 19 || iters < 1 || !cycles) {
     set_error("ccsm_debug_umma_rate: bad argument");
     return CCSM_EINVAL;
   }
@@ -460,6 +512,10 @@ extern "C" int ccsm_debug_umma_rate(int32_t device, int32_t N, int32_t mode, int
   CCSM_TRY(dc.reserve(8));
   const int smem = 65536;
   CCSM_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (mode >= 16) {  // bit 4: CTA-pair probe (modes 0, 1, 3)
+    CCSM_CUDA(cudaFuncSetAttribute(umma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_rate_pair_kernel<<<2, 128, smem>>>(N, mode & 15, iters, dc.as<long long>());
+  } else
   umma_rate_kernel<<<1, 128, smem>>>(N, mode, iters, dc.as<long long>());
   count_launch();
   cudaError_t e = cudaDeviceSynchronize();

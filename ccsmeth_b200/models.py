@@ -22,7 +22,7 @@ import torch.nn as nn
 from . import _lib
 from .utils.process_utils import N_VOCAB, NEMBED_BASE
 
-DEFAULT_PRECISION = os.environ.get("CCSMETH_B200_PRECISION", "fp16x3")
+DEFAULT_PRECISION = os.environ.get("CCSMETH_B200_PRECISION", "fp16c8")
 
 
 class Attention(nn.Module):

@@ -1,4 +1,6 @@
-"""Import the UNMODIFIED reference (read-only /root/reference) -- build-container tool only.
+"""Import the UNMODIFIED reference -- from the read-only /root/reference in the build container, or from the
+byte-identical staged copy under oracle/_ref (oracle/stage_ref.py; git-ignored, travels to the GPU box) -- test and
+measurement infrastructure only.
 
 The reference's hot-path modules import ``pysam`` (and transitively
 ``statsmodels``, ``tabix``, ``pybedtools``) at module top
@@ -6,9 +8,9 @@ The reference's hot-path modules import ``pysam`` (and transitively
 touched by the model forward.  Registering empty stub modules makes
 ``ccsmeth.models`` / ``ccsmeth.call_modifications`` importable unmodified.
 
-/root/reference does not exist on the GPU box: nothing that runs there may call this
-(tests guard on ``available()``).  Used by scripts/gen_golden.py to generate the
-committed fixtures under tests/golden/.
+/root/reference does not exist on the GPU box: there only the staged package is importable (checkpoints and the demo
+BAM come from tests/golden/).  Used by scripts/gen_golden.py to generate the committed fixtures under tests/golden/
+and by oracle/ref_cpu_bench.py (the CPU baseline arm of bench.py).
 """
 import os
 import sys
@@ -19,23 +21,36 @@ V3_CKPT = os.path.join(REFERENCE_ROOT, "models", "model_ccsmeth_5mCpG_call_mods_
 AGGR_CKPT = os.path.join(REFERENCE_ROOT, "models", "model_ccsmeth_5mCpG_aggregate_attbigru_b11.v2p.ckpt")
 DEMO_BAM = os.path.join(REFERENCE_ROOT, "demo", "hg002.chr20_demo.hifi.bam")
 
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
 _STUBS = ["pysam", "statsmodels", "statsmodels.robust", "tabix", "pybedtools"]
 
 
 def available():
+    """The full reference tree (checkpoints, demo data) is present: build container only."""
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "ccsmeth"))
+
+
+def package_root():
+    """Directory holding an importable, unmodified ``ccsmeth`` package, or None."""
+    if available():
+        return REFERENCE_ROOT
+    if os.path.isfile(os.path.join(STAGED_ROOT, "ccsmeth", "models.py")):
+        return STAGED_ROOT
+    return None
 
 
 def import_reference():
     """Returns the reference's ``ccsmeth`` package (models, call_modifications importable)."""
-    if not available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    root = package_root()
+    if root is None:
+        raise RuntimeError("reference package neither at %s nor staged under %s" % (REFERENCE_ROOT, STAGED_ROOT))
     for m in _STUBS:
         if m not in sys.modules:
             sys.modules[m] = types.ModuleType(m)
     sys.modules["statsmodels"].robust = sys.modules["statsmodels.robust"]
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import ccsmeth  # noqa: F401  (the reference package, not ours: ours is ccsmeth_b200)
     import ccsmeth.models  # noqa: F401
     return ccsmeth
