@@ -126,7 +126,10 @@ def _call_mods2s(features_batch, model, batch_size, device=0, h0=None):
         if model.is_map:
             feats["maps" + sfx] = _stack(mp, n)
     if h0 is None:
-        h0 = draw_h0_stream(n, batch_size, model.num_layers, model.hidden_size)
+        if model._stream_h0():
+            model.set_h0_batching([n], batch_size)   # the library draws the reference's stream on the device
+        elif model._host_h0():
+            h0 = draw_h0_stream(n, batch_size, model.num_layers, model.hidden_size)
     _, probs = model.forward_host(feats, h0=h0)
     p = probs.numpy()
     prob_1_norm = np.round(p[:, 1] / (p[:, 0] + p[:, 1]), 6)  # float32, like round(np.float32, 6) (:223)

@@ -75,6 +75,20 @@ def convert_probs_to_mltag(probs):
     return np.where(p < 1, np.floor(p * np.float32(256)), 255).astype(np.uint8)
 
 
+def _announce_or_draw_h0(model, args, per_hb, h0):
+    """The reference's h0 stream restarts its ``--batch_size`` slicing at every hole-batch: "reference" announces the
+    hole-batch site counts to the library, which draws the stream on the device; "reference_host" draws it with
+    torch.randn here (12 KB/site over PCIe); explicit h0 and the other modes pass through."""
+    mode = getattr(args, "h0", "reference")
+    if h0 is not None or getattr(model, "rnn_cell", None) != "gru":
+        return h0
+    if mode == "reference_host":
+        return draw_h0_stream_batches(per_hb, args.batch_size, model.num_layers, model.hidden_size)
+    if mode == "reference":
+        model.set_h0_batching(per_hb, args.batch_size)
+    return None
+
+
 def call_reads(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=None, holes_batch=None):
     """A run of consecutive hole-batches (list of BamRecord) -> (per-read list of (locs, prob_1_norm, mm, ml) or None,
     n_sites, n_model_batches).  Equivalent of process_one_holebatch + _batch_feature_list2s + _call_mods2s + the
@@ -99,8 +113,7 @@ def call_reads(model, reads, motifs, args, holeids_e=None, holeids_ne=None, h0=N
     rec_idx = np.asarray(batch.index, dtype=np.int64)[site_read]       # site -> position in `reads`
     per_hb = np.bincount(rec_idx // hb, minlength=(len(reads) + hb - 1) // hb)
     n_batches = int(sum((c + args.batch_size - 1) // args.batch_size for c in per_hb))
-    if h0 is None and getattr(args, "h0", "reference") == "reference":
-        h0 = draw_h0_stream_batches(per_hb, args.batch_size, model.num_layers, model.hidden_size)
+    h0 = _announce_or_draw_h0(model, args, per_hb, h0)
     t0 = time.perf_counter()
     res = model.reads_forward(h0=h0, want_probs=False)
     _tic("forward", t0)
@@ -176,9 +189,7 @@ def call_piece(model, piece, motifs, args, rank=0, world=1, holeids_e=None, hole
     site_hb = (gidx[use] // hb)[site_read]
     per_hb = np.diff(np.concatenate(([0], np.nonzero(np.diff(site_hb))[0] + 1, [n])))
     n_batches = int(((per_hb + args.batch_size - 1) // args.batch_size).sum())
-    h0 = None
-    if getattr(args, "h0", "reference") == "reference" and getattr(model, "rnn_cell", None) == "gru":
-        h0 = draw_h0_stream_batches(per_hb, args.batch_size, model.num_layers, model.hidden_size)
+    h0 = _announce_or_draw_h0(model, args, per_hb, None)
     t0 = time.perf_counter()
     res = model.reads_forward(h0=h0, want_probs=False)
     _tic("forward", t0)
@@ -233,7 +244,7 @@ def call_mods(args):
         raise ValueError("--input_file does not exist!")
     if not (args.input.endswith(".bam")):
         raise ValueError("ccsmeth_b200 call_mods takes BAM input (features.tsv input is out of scope)")
-    if args.model_type in ("attbilstm2s", "attbilstm2s2") and getattr(args, "h0", "reference") == "reference":
+    if args.model_type in ("attbilstm2s", "attbilstm2s2") and getattr(args, "h0", "reference") in ("reference", "reference_host"):
         raise ValueError("--model_type %s: the BAM pipeline takes the LSTM initial state from the library; "
                          "pass --h0 device or --h0 zeros" % args.model_type)
     if args.model_type in ("attbigru2s2", "attbilstm2s2", "transencoder2s") and args.norm != "none":
@@ -356,9 +367,10 @@ def build_parser():
     p.add_argument("--threads_call", type=int, default=3)
     p.add_argument("--tseed", type=int, default=1234)
     p.add_argument("--use_compile", type=str, default="no")
-    p.add_argument("--h0", type=str, default="reference", choices=["reference", "device", "zeros"],
-                   help="ccsmeth_b200 only: GRU initial state: the reference's torch.randn stream on the CPU "
-                        "(default), N(0,1) drawn on the device (no 12 KB/site transfer), or zeros")
+    p.add_argument("--h0", type=str, default="reference", choices=["reference", "reference_host", "device", "zeros"],
+                   help="ccsmeth_b200 only: GRU initial state: the reference's torch.randn stream reproduced on the "
+                        "device bit for bit (default), the same stream drawn by torch on the host (12 KB/site over "
+                        "PCIe), N(0,1) from the device's own generator, or zeros")
     p.add_argument("--device_batch", type=int, default=8,
                    help="ccsmeth_b200 only: hole-batches per device call (features are extracted on the GPU for "
                         "this many x --holes_batch reads at once)")

@@ -156,6 +156,7 @@ void ccsm_destroy(ccsm_model* m) {
   tc_release(m);
   ex_release(m);
   pu_release(m);
+  mt_destroy(m);
   trans_release(m);
   m->aggr_packed.release();
   m->aggr_packed_tiled.release();
@@ -174,6 +175,7 @@ void ccsm_destroy(ccsm_model* m) {
     m->stage_out[i].release();
     if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
     if (m->events[i]) cudaEventDestroy(m->events[i]);
+    if (m->done[i]) cudaEventDestroy(m->done[i]);
   }
   delete m;
 }
@@ -348,14 +350,49 @@ int ccsm_finalize(ccsm_model* m) {
 }
 
 int ccsm_set_h0_mode(ccsm_model* m, int32_t mode, uint64_t seed) {
-  if (!m || (mode != CCSM_H0_ZEROS && mode != CCSM_H0_DEVICE_RANDOM)) {
+  if (!m || (mode != CCSM_H0_ZEROS && mode != CCSM_H0_DEVICE_RANDOM && mode != CCSM_H0_TORCH_STREAM)) {
     set_error("ccsm_set_h0_mode: bad argument");
     return CCSM_EINVAL;
+  }
+  if (mode == CCSM_H0_TORCH_STREAM) {
+    if (m->cfg.kind != CCSM_KIND_ATT2S || m->gates != 3 || m->is_trans) {
+      set_error("ccsm_set_h0_mode: the torch.randn stream is implemented for the GRU att2s models");
+      return CCSM_EUNSUPPORTED;
+    }
+    CCSM_CUDA(cudaSetDevice(m->cfg.device));
+    CCSM_TRY(mt_seed(m, seed));
   }
   m->h0_mode = mode;
   m->h0_seed = seed;
   m->h0_calls = 0;
   return CCSM_OK;
+}
+
+int ccsm_set_h0_batching(ccsm_model* m, const int64_t* holebatch_sites, int64_t n_holebatches, int32_t batch_size) {
+  if (!m || (n_holebatches > 0 && !holebatch_sites) || n_holebatches < 0) {
+    set_error("ccsm_set_h0_batching: bad argument");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  return mt_set_batching(m, holebatch_sites, n_holebatches, batch_size);
+}
+
+int ccsm_h0_stream_set_state(ccsm_model* m, const uint32_t* words624, int32_t pos) {
+  if (!m || !words624) {
+    set_error("ccsm_h0_stream_set_state: bad argument");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  return mt_set_state(m, words624, pos);
+}
+
+int ccsm_h0_stream_get_state(ccsm_model* m, uint32_t* words624, int32_t* pos) {
+  if (!m || !words624 || !pos) {
+    set_error("ccsm_h0_stream_get_state: bad argument");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  return mt_get_state(m, words624, pos);
 }
 
 int ccsm_set_precision(ccsm_model* m, int32_t precision) {
@@ -372,6 +409,79 @@ int ccsm_set_precision(ccsm_model* m, int32_t precision) {
   }
   return CCSM_OK;
 }
+
+}  // extern "C"
+
+namespace ccsm {
+
+void seg_chunks(const std::vector<int64_t>& segs, int64_t max_sites, std::vector<SegChunk>& out) {
+  out.clear();
+  int64_t site = 0;
+  for (int k = 0; k < (int)segs.size();) {
+    SegChunk c{k, 0, site, 0};
+    while (k < (int)segs.size() && (c.nseg == 0 || c.sites + segs[k] <= max_sites)) {
+      c.sites += segs[k];
+      ++c.nseg;
+      ++k;
+    }
+    site += c.sites;
+    out.push_back(c);
+  }
+}
+
+static ccsm_strand strand_at(const ccsm_strand* s, int64_t off, int L) {
+  ccsm_strand r = *s;
+  auto adv = [&](const float* p, int64_t per) { return p ? p + off * per : nullptr; };
+  r.kmer = adv(s->kmer, L);
+  r.kpass = adv(s->kpass, L);
+  r.ipd_means = adv(s->ipd_means, L);
+  r.ipd_stds = adv(s->ipd_stds, L);
+  r.pw_means = adv(s->pw_means, L);
+  r.pw_stds = adv(s->pw_stds, L);
+  r.sns = adv(s->sns, 4);
+  r.maps = adv(s->maps, L);
+  return r;
+}
+
+int forward_att2s_dev(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, const float* h0_fwd,
+                      const float* h0_rev, float* logits, float* probs, cudaStream_t st, const int64_t* segs, int nseg) {
+  if (m->is_trans) return trans_forward(m, n, fwd, rev, logits, probs, st);  // no recurrent state: h0 is ignored
+  auto inner = [&](int64_t cn, const ccsm_strand* f, const ccsm_strand* r, const float* ha, const float* hb, float* lg,
+                   float* pr) {
+    const int rc = is_tc(m->cfg.precision) ? tc_forward_att2s(m, cn, f, r, ha, hb, lg, pr, st)
+                                           : fp32_forward_att2s(m, cn, f, r, ha, hb, lg, pr, st);
+    m->h0_calls += 1;
+    return rc;
+  };
+  if (m->h0_mode != CCSM_H0_TORCH_STREAM || h0_fwd || h0_rev || m->gates != 3)
+    return inner(n, fwd, rev, h0_fwd, h0_rev, logits, probs);
+  // the reference's torch.randn stream, drawn on the device: windows of whole model calls
+  std::vector<int64_t> own;
+  if (!segs) {
+    CCSM_TRY(mt_take_segments(m, n, own));
+    segs = own.data();
+    nseg = (int)own.size();
+  }
+  std::vector<int64_t> sv(segs, segs + nseg);
+  std::vector<SegChunk> chunks;
+  seg_chunks(sv, 75776, chunks);
+  const int L = m->cfg.seq_len, C = m->cfg.num_classes;
+  for (const SegChunk& c : chunks) {
+    const float *ha = nullptr, *hb = nullptr;
+    int buf = 0;
+    CCSM_TRY(mt_fill(m, segs + c.seg0, c.nseg, st, &ha, &hb, &buf));
+    const ccsm_strand f = strand_at(fwd, c.site0, L), r = strand_at(rev, c.site0, L);
+    const int rc = inner(c.sites, &f, &r, ha, hb, logits ? logits + c.site0 * C : nullptr,
+                         probs ? probs + c.site0 * C : nullptr);
+    CCSM_TRY(mt_release(m, buf, st));
+    CCSM_TRY(rc);
+  }
+  return CCSM_OK;
+}
+
+}  // namespace ccsm
+
+extern "C" {
 
 static int check_strand(const ccsm_model* m, const ccsm_strand* s, const char* which) {
   const int f = m->cfg.feat_flags;
@@ -402,12 +512,7 @@ int ccsm_forward_att2s(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const c
   CCSM_TRY(check_strand(m, fwd, "forward"));
   CCSM_TRY(check_strand(m, rev, "reverse"));
   CCSM_CUDA(cudaSetDevice(m->cfg.device));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (m->is_trans) return trans_forward(m, n, fwd, rev, logits, probs, st);  // no recurrent state: h0 is ignored
-  const int rc = is_tc(m->cfg.precision) ? tc_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st)
-                                         : fp32_forward_att2s(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, st);
-  m->h0_calls += 1;
-  return rc;
+  return forward_att2s_dev(m, n, fwd, rev, h0_fwd, h0_rev, logits, probs, reinterpret_cast<cudaStream_t>(stream), nullptr, 0);
 }
 
 int ccsm_forward_att2s_lstm(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, const float* h0_fwd,
@@ -499,28 +604,45 @@ int ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, co
     if (!m->events[i]) CCSM_CUDA(cudaEventCreateWithFlags(&m->events[i], cudaEventDisableTiming));
   }
   const int L = m->cfg.seq_len, H = m->cfg.hidden, NL = m->cfg.num_layers, C = m->cfg.num_classes;
-  // one tensor-core library chunk (8 row-tile items per SM) per staging buffer
+  // one tensor-core library chunk (8 row-tile items per SM) per staging buffer; in the torch-stream h0 mode the chunks
+  // are cut at the reference's model-call boundaries so that every chunk draws whole randn calls
   const int64_t kHostChunk = 75776;
-  const int64_t chunk = n < kHostChunk ? n : kHostChunk;
+  const bool torch_h0 = m->h0_mode == CCSM_H0_TORCH_STREAM && !h0_fwd && !h0_rev && m->gates == 3 && !m->is_trans;
+  std::vector<int64_t> segs;
+  std::vector<SegChunk> chunks;
+  if (torch_h0) {
+    CCSM_TRY(mt_take_segments(m, n, segs));
+    seg_chunks(segs, kHostChunk, chunks);
+  } else {
+    for (int64_t s0 = 0; s0 < n; s0 += kHostChunk) chunks.push_back(SegChunk{0, 0, s0, (n - s0) < kHostChunk ? (n - s0) : kHostChunk});
+  }
+  int64_t chunk = 0;
+  for (const SegChunk& c : chunks) chunk = c.sites > chunk ? c.sites : chunk;
   // staging layout per buffer (floats): 2 strands x [kmer,kpass,ipd,ipd_sd,pw,pw_sd,maps](L each) + sns(4) + h0 x2
   const int64_t per_strand = (int64_t)7 * L + 4;
   const int64_t h0_floats = (int64_t)2 * NL * H;
-  const size_t in_bytes = (size_t)chunk * (2 * per_strand + 2 * h0_floats) * sizeof(float);
+  const size_t in_bytes = (size_t)chunk * (2 * per_strand + ((h0_fwd || h0_rev) ? 2 * h0_floats : 0)) * sizeof(float);
   const size_t out_bytes = (size_t)chunk * 2 * C * sizeof(float);
-  cudaEvent_t done[2];
   for (int i = 0; i < 2; ++i) {
     CCSM_TRY(m->stage_in[i].reserve(in_bytes));
     CCSM_TRY(m->stage_out[i].reserve(out_bytes));
-    CCSM_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    if (!m->done[i]) CCSM_CUDA(cudaEventCreateWithFlags(&m->done[i], cudaEventDisableTiming));
   }
   cudaStream_t s_in = m->streams[0], s_cmp = m->streams[1];
   int rc = CCSM_OK;
+  cudaError_t ce = cudaSuccess;  // first failing runtime call of the pipelined loop
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && ce == cudaSuccess) ce = e;
+    return e == cudaSuccess;
+  };
   int64_t ci = 0;
-  for (int64_t s0 = 0; s0 < n && rc == CCSM_OK; s0 += chunk, ++ci) {
+  for (const SegChunk& ck : chunks) {
+    if (rc != CCSM_OK || ce != cudaSuccess) break;
     const int b = (int)(ci & 1);
-    const int64_t cn = (n - s0) < chunk ? (n - s0) : chunk;
+    const int64_t s0 = ck.site0, cn = ck.sites;
     float* base = m->stage_in[b].as<float>();
-    if (ci >= 2) cudaStreamWaitEvent(s_in, done[b], 0);  // buffer b is free once chunk ci-2 finished
+    if (ci >= 2) ok(cudaStreamWaitEvent(s_in, m->done[b], 0));  // buffer b is free once chunk ci-2 finished
+    ++ci;
     ccsm_strand dev[2];
     const ccsm_strand* src[2] = {fwd, rev};
     float* cur = base;
@@ -528,7 +650,7 @@ int ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, co
       if (!hp) return nullptr;
       float* d = cur;
       cur += cn * per;
-      cudaMemcpyAsync(d, hp + s0 * per, (size_t)cn * per * sizeof(float), cudaMemcpyHostToDevice, s_in);
+      ok(cudaMemcpyAsync(d, hp + s0 * per, (size_t)cn * per * sizeof(float), cudaMemcpyHostToDevice, s_in));
       return d;
     };
     for (int s = 0; s < 2; ++s) {
@@ -548,26 +670,27 @@ int ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, co
       float* d = cur;
       cur += cn * h0_floats;
       // (2*layers, n, H) -> (2*layers, cn, H): one strided copy
-      cudaMemcpy2DAsync(d, (size_t)cn * H * sizeof(float), h0s[s] + s0 * H, (size_t)n * H * sizeof(float),
-                        (size_t)cn * H * sizeof(float), 2 * NL, cudaMemcpyHostToDevice, s_in);
+      ok(cudaMemcpy2DAsync(d, (size_t)cn * H * sizeof(float), h0s[s] + s0 * H, (size_t)n * H * sizeof(float),
+                           (size_t)cn * H * sizeof(float), 2 * NL, cudaMemcpyHostToDevice, s_in));
       dh0[s] = d;
     }
-    cudaEventRecord(m->events[b], s_in);
-    cudaStreamWaitEvent(s_cmp, m->events[b], 0);
+    ok(cudaEventRecord(m->events[b], s_in));
+    ok(cudaStreamWaitEvent(s_cmp, m->events[b], 0));
+    if (ce != cudaSuccess) break;
     float* dl = m->stage_out[b].as<float>();
     float* dp = dl + cn * C;
-    rc = ccsm_forward_att2s(m, cn, &dev[0], &dev[1], dh0[0], dh0[1], dl, dp, s_cmp);
+    rc = forward_att2s_dev(m, cn, &dev[0], &dev[1], dh0[0], dh0[1], dl, dp, s_cmp, torch_h0 ? segs.data() + ck.seg0 : nullptr,
+                           torch_h0 ? ck.nseg : 0);
     if (rc != CCSM_OK) break;
-    if (logits) cudaMemcpyAsync(logits + s0 * C, dl, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, s_cmp);
-    if (probs) cudaMemcpyAsync(probs + s0 * C, dp, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, s_cmp);
-    cudaEventRecord(done[b], s_cmp);
+    if (logits) ok(cudaMemcpyAsync(logits + s0 * C, dl, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, s_cmp));
+    if (probs) ok(cudaMemcpyAsync(probs + s0 * C, dp, (size_t)cn * C * sizeof(float), cudaMemcpyDeviceToHost, s_cmp));
+    ok(cudaEventRecord(m->done[b], s_cmp));
   }
   cudaError_t e1 = cudaStreamSynchronize(s_in);
   cudaError_t e2 = cudaStreamSynchronize(s_cmp);
-  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
   if (rc != CCSM_OK) return rc;
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    set_error("ccsm_forward_att2s_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  if (ce != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("ccsm_forward_att2s_host: %s", cudaGetErrorString(ce != cudaSuccess ? ce : (e1 != cudaSuccess ? e1 : e2)));
     return CCSM_ECUDA;
   }
   return CCSM_OK;

@@ -87,6 +87,7 @@ struct Fp32Workspace {
 struct TcState;  // tensor-core (tcgen05) path state, defined in tc_path.cu
 struct PuState;  // resident region pileup (pileup.cu)
 struct ExState;  // device feature extraction state (resident read batch), defined in extract.cu
+struct MtStream; // device reproduction of the reference's torch.randn h0 stream (mtstream.cu)
 
 // Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).
 enum ProfClass { PROF_PREP = 0, PROF_GRU_L0 = 1, PROF_GRU_LN = 2, PROF_ATT = 3, PROF_EX_SCAN = 4, PROF_EX_GATHER = 5,
@@ -132,6 +133,7 @@ struct ccsm_model {
   ccsm::TcState* tc = nullptr;
   ccsm::ExState* ex = nullptr;
   ccsm::PuState* pu = nullptr;
+  ccsm::MtStream* mts = nullptr;
   ccsm::DevBuf aggr_packed, aggr_packed_tiled, aggr_scratch;  // fused aggregate kernels (aggr_fused.cu)
   ccsm::Profiler prof;
   int h0_mode = 0;            // CCSM_H0_*
@@ -140,6 +142,7 @@ struct ccsm_model {
   // host-entry staging
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaEvent_t events[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
   ccsm::DevBuf stage_in[2], stage_out[2];
   // debug: where the last layer-stack output of the most recent fp32 chunk lives
   const float* dbg_rnn_out = nullptr;
@@ -175,6 +178,23 @@ int aggr_fused_forward(ccsm_model* m, int64_t n, const float* offsets, const flo
 int aggr_fused_forward_sites(ccsm_model* m, int64_t n, const long long* site_pos, const float* site_histo, int only_close,
                              const float* h0, float* out, cudaStream_t st);
 void pu_release(ccsm_model* m);
+
+// ---- the reference's h0 stream on the device (mtstream.cu)
+int mt_seed(ccsm_model* m, uint64_t seed);
+int mt_set_state(ccsm_model* m, const uint32_t* words, int32_t pos);
+int mt_get_state(ccsm_model* m, uint32_t* words, int32_t* pos);
+int mt_set_batching(ccsm_model* m, const int64_t* counts, int64_t n_counts, int32_t batch_size);
+int mt_take_segments(ccsm_model* m, int64_t n, std::vector<int64_t>& segs);
+int mt_fill(ccsm_model* m, const int64_t* segs, int nseg, cudaStream_t user, const float** h0a, const float** h0b, int* buf);
+int mt_release(ccsm_model* m, int buf, cudaStream_t user);
+void mt_destroy(ccsm_model* m);
+// att2s forward on device buffers; segs (nseg model-call site counts summing to n) only matters in CCSM_H0_TORCH_STREAM
+// mode with no explicit h0: nullptr = take the announced hole-batches (ccsm_set_h0_batching) or one hole-batch of n
+int forward_att2s_dev(ccsm_model* m, int64_t n, const ccsm_strand* fwd, const ccsm_strand* rev, const float* h0_fwd,
+                      const float* h0_rev, float* logits, float* probs, cudaStream_t st, const int64_t* segs, int nseg);
+// cuts consecutive model calls into groups of at most max_sites sites: (first segment, segment count, first site, sites)
+struct SegChunk { int seg0, nseg; int64_t site0, sites; };
+void seg_chunks(const std::vector<int64_t>& segs, int64_t max_sites, std::vector<SegChunk>& out);
 
 // ---- device feature extraction (extract.cu)
 void ex_release(ccsm_model* m);

@@ -650,7 +650,18 @@ int ccsm_reads_forward_host(ccsm_model* m, const float* h0_fwd, const float* h0_
   const int L = m->cfg.seq_len, H = m->cfg.hidden, NL = m->cfg.num_layers, C = m->cfg.num_classes;
   const bool has_np = m->cfg.feat_flags & CCSM_FEAT_NPASS, has_sn = m->cfg.feat_flags & CCSM_FEAT_SN;
   const int64_t kChunk = 75776;  // one tensor-core library chunk
-  const int64_t chunk = n < kChunk ? n : kChunk;
+  // torch-stream h0 mode: chunks are cut at the reference's model-call boundaries (whole randn calls per chunk)
+  const bool torch_h0 = m->h0_mode == CCSM_H0_TORCH_STREAM && !(h0_fwd && h0_rev) && m->gates == 3 && !m->is_trans;
+  std::vector<int64_t> segs;
+  std::vector<SegChunk> chunks;
+  if (torch_h0) {
+    CCSM_TRY(mt_take_segments(m, n, segs));
+    seg_chunks(segs, kChunk, chunks);
+  } else {
+    for (int64_t s0 = 0; s0 < n; s0 += kChunk) chunks.push_back(SegChunk{0, 0, s0, (n - s0) < kChunk ? (n - s0) : kChunk});
+  }
+  int64_t chunk = 0;
+  for (const SegChunk& c : chunks) chunk = c.sites > chunk ? c.sites : chunk;
   const int64_t per_strand = (int64_t)4 * L + 4;
   const int64_t h0_floats = (int64_t)2 * NL * H;
   const bool has_h0 = h0_fwd && h0_rev;
@@ -665,10 +676,12 @@ int ccsm_reads_forward_host(ccsm_model* m, const float* h0_fwd, const float* h0_
   CCSM_TRY(ex->tags.reserve(2 * tag_bytes));
   cudaStream_t st = ex->st, sc = ex->st_copy;
   int rc = CCSM_OK;
-  int64_t ci = 0;
-  for (int64_t s0 = 0; s0 < n && rc == CCSM_OK; s0 += chunk, ++ci) {
+  int64_t ci = -1;
+  for (const SegChunk& ck : chunks) {
+    if (rc != CCSM_OK) break;
+    ++ci;
     const int b = (int)(ci & 1);
-    const int64_t cn = (n - s0) < chunk ? (n - s0) : chunk;
+    const int64_t s0 = ck.site0, cn = ck.sites;
     float* fb = reinterpret_cast<float*>(ex->feat.as<char>() + b * feat_bytes);
     ccsm_strand dev[2];
     float* cur = fb;
@@ -698,7 +711,8 @@ int ccsm_reads_forward_host(ccsm_model* m, const float* h0_fwd, const float* h0_
     if (rc != CCSM_OK) break;
     float* dl = reinterpret_cast<float*>(ex->out.as<char>() + b * out_bytes);
     float* dp = dl + cn * C;
-    rc = ccsm_forward_att2s(m, cn, &dev[0], &dev[1], dh0[0], dh0[1], dl, dp, st);
+    rc = forward_att2s_dev(m, cn, &dev[0], &dev[1], dh0[0], dh0[1], dl, dp, st, torch_h0 ? segs.data() + ck.seg0 : nullptr,
+                           torch_h0 ? ck.nseg : 0);
     if (rc != CCSM_OK) break;
     char* tb = ex->tags.as<char>() + b * tag_bytes;
     float* d_p1 = reinterpret_cast<float*>(tb);

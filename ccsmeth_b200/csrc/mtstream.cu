@@ -1,0 +1,399 @@
+// Device reproduction of the reference's GRU initial-state stream.
+//
+// Replaces: reference ccsmeth/models.py:77-87 (ModelAttRNN.init_hidden = torch.randn(2*layers, n, hidden) on the CPU
+// default generator, one draw per strand per model call) seeded by call_modifications.py:479-481 (torch.manual_seed).
+//
+// What ATen does for that draw (aten/src/ATen/native/cpu/DistributionTemplates.h; the kernel every AVX2-capable x86
+// host dispatches to -- the AVX512 slot of this stub is empty, so AVX512 hosts run it too):
+//   * engine at::mt19937 = MT19937 seeded like init_genrand from the low 32 seed bits, one 32-bit output per element;
+//   * uniform u = (x & (2^24 - 1)) * 2^-24;
+//   * normal_fill_AVX2 on groups of 16 consecutive elements: for j < 8, u1 = 1 - u[j], u2 = u[j + 8],
+//       radius = sqrt(-2 * log256_ps(u1)), theta = float(2 pi) * u2, out[j] = radius * cos, out[j + 8] = radius * sin
+//     with the single-precision Cephes polynomials of avx_mathfun.h, whose multiply-adds the compiler contracted into
+//     FMAs (pattern pinned bit-for-bit against torch.randn by tests/test_h0_stream_gpu.py).
+// Here: mt_generate_kernel produces the tempered 32-bit outputs (one CTA: the twist is a sequential recurrence over
+// 624-word blocks, 227-wide inside a block), mt_normal_kernel turns them into the (2*layers, n, hidden) fp32 tensors the
+// forward takes as explicit h0 -- same values, same order, nothing crosses PCIe.  All float arithmetic below is written
+// with round-to-nearest intrinsics so that nvcc neither contracts nor reassociates it.
+#include <stdint.h>
+
+#include <vector>
+
+#include "ccsm_internal.h"
+
+namespace ccsm {
+
+constexpr int MT_N = 624, MT_M = 397;
+
+__device__ __forceinline__ uint32_t mt_tw(uint32_t u, uint32_t v) {
+  const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+  return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+// state[0..623] = generator words, state[624] = position of the next output inside the block (624 = twist first).
+// Writes the next n tempered outputs to out and leaves the generator where the reference's would be.
+__global__ void __launch_bounds__(256, 1) mt_generate_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ out,
+                                                             long long n) {
+  __shared__ uint32_t s[2][MT_N];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < MT_N; i += 256) s[0][i] = state[i];
+  int pos = (int)state[MT_N];
+  int cur = 0;
+  __syncthreads();
+  long long o = 0;
+  while (o < n) {
+    if (pos == MT_N) {
+      const uint32_t* a = s[cur];
+      uint32_t* b = s[cur ^ 1];
+      // new[i] = old[i + 397] ^ tw(old[i], old[i + 1]) for i < 227; later words use freshly generated ones
+      if (tid < MT_N - MT_M) b[tid] = a[tid + MT_M] ^ mt_tw(a[tid], a[tid + 1]);
+      __syncthreads();
+      if (tid < MT_N - MT_M) b[tid + 227] = b[tid] ^ mt_tw(a[tid + 227], a[tid + 228]);
+      __syncthreads();
+      if (tid < MT_N - 1 - 454) b[tid + 454] = b[tid + 227] ^ mt_tw(a[tid + 454], a[tid + 455]);
+      __syncthreads();
+      if (tid == 0) b[MT_N - 1] = b[MT_M - 1] ^ mt_tw(a[MT_N - 1], b[0]);
+      __syncthreads();
+      cur ^= 1;
+      pos = 0;
+    }
+    const long long left = n - o;
+    const int k = left < (long long)(MT_N - pos) ? (int)left : MT_N - pos;
+    for (int i = tid; i < k; i += 256) out[o + i] = mt_temper(s[cur][pos + i]);
+    pos += k;
+    o += k;
+  }
+  __syncthreads();
+  for (int i = tid; i < MT_N; i += 256) state[i] = s[cur][i];
+  if (tid == 0) state[MT_N] = (uint32_t)pos;
+}
+
+// ---- avx_mathfun.h log256_ps / sincos256_ps, one lane, with the FMA contractions of the shipped ATen binary
+__device__ __forceinline__ float avx_log(float x) {
+  x = fmaxf(x, 1.17549435e-38f);
+  int e_i = (int)(__float_as_uint(x) >> 23) - 0x7f;
+  x = __uint_as_float((__float_as_uint(x) & ~0x7f800000u) | 0x3f000000u);
+  float e = __fadd_rn((float)e_i, 1.0f);
+  const bool lt = x < 0.707106781186547524f;
+  const float tmp = lt ? x : 0.0f;
+  x = __fsub_rn(x, 1.0f);
+  e = __fsub_rn(e, lt ? 1.0f : 0.0f);
+  x = __fadd_rn(x, tmp);
+  const float z = __fmul_rn(x, x);
+  float y = 7.0376836292E-2f;
+  y = __fmaf_rn(y, x, -1.1514610310E-1f);
+  y = __fmaf_rn(y, x, 1.1676998740E-1f);
+  y = __fmaf_rn(y, x, -1.2420140846E-1f);
+  y = __fmaf_rn(y, x, 1.4249322787E-1f);
+  y = __fmaf_rn(y, x, -1.6668057665E-1f);
+  y = __fmaf_rn(y, x, 2.0000714765E-1f);
+  y = __fmaf_rn(y, x, -2.4999993993E-1f);
+  y = __fmaf_rn(y, x, 3.3333331174E-1f);
+  y = __fmul_rn(y, x);
+  y = __fmaf_rn(y, z, __fmul_rn(e, -2.12194440e-4f));   // (y * z) fused with the add; e * q1 rounded on its own
+  y = __fmaf_rn(-z, 0.5f, y);
+  x = __fadd_rn(x, y);
+  return __fmaf_rn(e, 0.693359375f, x);
+}
+__device__ __forceinline__ void avx_sincos(float x, float& s, float& c) {
+  uint32_t sign_sin = __float_as_uint(x) & 0x80000000u;
+  x = fabsf(x);
+  float y = __fmul_rn(x, 1.27323954473516f);
+  int j = __float2int_rz(y);
+  j = (j + 1) & ~1;
+  y = (float)j;
+  const uint32_t swap_sin = ((uint32_t)(j & 4)) << 29;
+  const bool poly = (j & 2) == 0;
+  x = __fmaf_rn(y, -0.78515625f, x);
+  x = __fmaf_rn(y, -2.4187564849853515625e-4f, x);
+  x = __fmaf_rn(y, -3.77489497744594108e-8f, x);
+  const uint32_t sign_cos = ((uint32_t)(~(j - 2) & 4)) << 29;
+  sign_sin ^= swap_sin;
+  const float z = __fmul_rn(x, x);
+  float yc = 2.443315711809948E-005f;
+  yc = __fmaf_rn(yc, z, -1.388731625493765E-003f);
+  yc = __fmaf_rn(yc, z, 4.166664568298827E-002f);
+  yc = __fmul_rn(yc, z);
+  yc = __fmaf_rn(yc, z, -__fmul_rn(z, 0.5f));
+  yc = __fadd_rn(yc, 1.0f);
+  float ys = -1.9515295891E-4f;
+  ys = __fmaf_rn(ys, z, 8.3321608736E-3f);
+  ys = __fmaf_rn(ys, z, -1.6666654611E-1f);
+  ys = __fmul_rn(ys, z);
+  ys = __fmaf_rn(ys, x, x);
+  s = __uint_as_float(__float_as_uint(poly ? ys : yc) ^ sign_sin);
+  c = __uint_as_float(__float_as_uint(poly ? yc : ys) ^ sign_cos);
+}
+// one Box-Muller pair of normal_fill_16: raw outputs a (-> u1) and b (-> u2)
+__device__ __forceinline__ void normal_pair(uint32_t a, uint32_t b, float& n_cos, float& n_sin) {
+  const float u1 = __fsub_rn(1.0f, __fmul_rn((float)(a & 0xffffffu), 5.9604644775390625e-8f));  // exact
+  const float u2 = __fmul_rn((float)(b & 0xffffffu), 5.9604644775390625e-8f);
+  const float radius = __fsqrt_rn(__fmul_rn(-2.0f, avx_log(u1)));
+  float s, c;
+  avx_sincos(__fmul_rn(6.283185307179586f, u2), s, c);
+  n_cos = __fmul_rn(radius, c);
+  n_sin = __fmul_rn(radius, s);
+}
+
+// Plain stream: out[16 g + j] / out[16 g + 8 + j] for every group g of 16 words (debug / tests).
+__global__ void mt_normal_flat_kernel(const uint32_t* __restrict__ words, float* __restrict__ out, long long groups) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one pair per thread
+  if (t >= groups * 8) return;
+  const long long g = t >> 3;
+  const int j = (int)(t & 7);
+  float nc, ns;
+  normal_pair(words[g * 16 + j], words[g * 16 + 8 + j], nc, ns);
+  out[g * 16 + j] = nc;
+  out[g * 16 + 8 + j] = ns;
+}
+
+// The reference's layout: model call k (a "segment" of n_k <= batch sites starting at site s_k) draws
+// randn(LD, n_k, H) for strand 1, then for strand 2; word base w_k = sum_{k' < k} 2 LD n_k' H.
+// seg_site[k] = s_k (seg_site[nseg] = n), seg_word[k] = w_k.  h0a / h0b: (LD, n, H) fp32.
+__global__ void mt_normal_h0_kernel(const uint32_t* __restrict__ words, const long long* __restrict__ seg_site,
+                                    const long long* __restrict__ seg_word, int nseg, long long n, int LD, int H,
+                                    float* __restrict__ h0a, float* __restrict__ h0b) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one pair per thread
+  const long long total_pairs = n * 2 * LD * H / 2;
+  if (t >= total_pairs) return;
+  const long long g = t >> 3;
+  const int j = (int)(t & 7);
+  const long long w = g * 16;  // stream position of the group's first word
+  int lo = 0, hi = nseg - 1;   // last segment whose word base is <= w
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg_word[mid] <= w) lo = mid;
+    else hi = mid - 1;
+  }
+  const long long s0 = seg_site[lo], nk = seg_site[lo + 1] - s0;
+  long long rel = w - seg_word[lo];
+  const long long per_strand = (long long)LD * nk * H;
+  const int strand = rel >= per_strand;
+  rel -= strand * per_strand;
+  const long long ld = rel / (nk * H);
+  rel -= ld * nk * H;
+  const long long site = s0 + rel / H;
+  const int unit = (int)(rel % H);
+  float nc, ns;
+  normal_pair(words[w + j], words[w + 8 + j], nc, ns);
+  float* dst = (strand ? h0b : h0a) + (ld * n + site) * H + unit;
+  dst[j] = nc;
+  dst[8 + j] = ns;
+}
+
+struct MtStream {
+  DevBuf state;   // 624 words + position
+  bool seeded = false;
+  uint64_t seed = 0;
+  int batch = 512;                 // the reference's --batch_size: sites per model call
+  std::vector<int64_t> pending;    // hole-batch site counts announced for the next forward call
+  DevBuf words[2], h0[2], segtab[2];
+  int next_buf = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+};
+
+static int mt_ensure(ccsm_model* m) {
+  if (!m->mts) m->mts = new MtStream();
+  MtStream& S = *m->mts;
+  if (!S.st) {
+    CCSM_CUDA(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CCSM_CUDA(cudaEventCreateWithFlags(&S.ready[i], cudaEventDisableTiming));
+      CCSM_CUDA(cudaEventCreateWithFlags(&S.freed[i], cudaEventDisableTiming));
+    }
+  }
+  return CCSM_OK;
+}
+
+int mt_seed(ccsm_model* m, uint64_t seed) {
+  CCSM_TRY(mt_ensure(m));
+  MtStream& S = *m->mts;
+  uint32_t st[MT_N + 1];
+  st[0] = (uint32_t)(seed & 0xffffffffu);
+  for (int j = 1; j < MT_N; ++j) st[j] = 1812433253u * (st[j - 1] ^ (st[j - 1] >> 30)) + (uint32_t)j;
+  st[MT_N] = MT_N;  // the first output twists
+  CCSM_TRY(S.state.reserve(sizeof(st)));
+  CCSM_CUDA(cudaStreamSynchronize(S.st));
+  CCSM_CUDA(cudaMemcpy(S.state.p, st, sizeof(st), cudaMemcpyHostToDevice));
+  S.seeded = true;
+  S.seed = seed;
+  S.pending.clear();
+  return CCSM_OK;
+}
+
+int mt_set_state(ccsm_model* m, const uint32_t* words, int32_t pos) {
+  CCSM_TRY(mt_ensure(m));
+  MtStream& S = *m->mts;
+  if (pos < 0 || pos > MT_N) {
+    set_error("h0 stream: position %d outside [0, 624]", pos);
+    return CCSM_EINVAL;
+  }
+  uint32_t st[MT_N + 1];
+  for (int i = 0; i < MT_N; ++i) st[i] = words[i];
+  st[MT_N] = (uint32_t)pos;
+  CCSM_TRY(S.state.reserve(sizeof(st)));
+  CCSM_CUDA(cudaStreamSynchronize(S.st));
+  CCSM_CUDA(cudaMemcpy(S.state.p, st, sizeof(st), cudaMemcpyHostToDevice));
+  S.seeded = true;
+  return CCSM_OK;
+}
+
+int mt_get_state(ccsm_model* m, uint32_t* words, int32_t* pos) {
+  CCSM_TRY(mt_ensure(m));
+  MtStream& S = *m->mts;
+  if (!S.seeded) CCSM_TRY(mt_seed(m, m->h0_seed));
+  uint32_t st[MT_N + 1];
+  CCSM_CUDA(cudaStreamSynchronize(S.st));
+  CCSM_CUDA(cudaMemcpy(st, S.state.p, sizeof(st), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < MT_N; ++i) words[i] = st[i];
+  *pos = (int32_t)st[MT_N];
+  return CCSM_OK;
+}
+
+int mt_set_batching(ccsm_model* m, const int64_t* counts, int64_t n_counts, int32_t batch_size) {
+  CCSM_TRY(mt_ensure(m));
+  MtStream& S = *m->mts;
+  if (batch_size <= 0) {
+    set_error("h0 stream: batch_size must be positive");
+    return CCSM_EINVAL;
+  }
+  S.batch = batch_size;
+  S.pending.assign(counts, counts + n_counts);
+  return CCSM_OK;
+}
+
+// The model calls ("segments") the reference would make for the next n sites: every announced hole-batch is cut
+// into slices of <= batch sites (reference call_modifications.py:177-181); without an announcement the n sites are one
+// hole-batch.  Consumes the announcement.
+int mt_take_segments(ccsm_model* m, int64_t n, std::vector<int64_t>& segs) {
+  CCSM_TRY(mt_ensure(m));
+  MtStream& S = *m->mts;
+  if (!S.seeded) CCSM_TRY(mt_seed(m, m->h0_seed));
+  std::vector<int64_t> hb;
+  hb.swap(S.pending);
+  if (hb.empty()) hb.push_back(n);
+  int64_t tot = 0;
+  segs.clear();
+  for (int64_t c : hb) {
+    if (c < 0) {
+      set_error("h0 stream: negative hole-batch count");
+      return CCSM_EINVAL;
+    }
+    tot += c;
+    for (int64_t s = 0; s < c; s += S.batch) segs.push_back((c - s) < S.batch ? (c - s) : S.batch);
+  }
+  if (tot != n) {
+    set_error("h0 stream: the announced hole-batches hold %lld sites, the call has %lld", (long long)tot, (long long)n);
+    return CCSM_EINVAL;
+  }
+  return CCSM_OK;
+}
+
+// Draws the h0 of `nseg` consecutive model calls (site counts segs[]) on the generator's own stream into one of two
+// buffers; `user` (the stream the forward runs on) is made to wait for it.  *h0a / *h0b: (LD, n, H) device tensors,
+// valid until the second-next call; the caller records `freed` via mt_release after launching the consumer.
+int mt_fill(ccsm_model* m, const int64_t* segs, int nseg, cudaStream_t user, const float** h0a, const float** h0b, int* buf) {
+  MtStream& S = *m->mts;
+  const int LD = 2 * m->cfg.num_layers, H = m->cfg.hidden;
+  if (H % 16 != 0) {
+    set_error("h0 stream: hidden size must be a multiple of 16");
+    return CCSM_EUNSUPPORTED;
+  }
+  std::vector<long long> tab(2 * (size_t)(nseg + 1));
+  long long n = 0, w = 0;
+  for (int k = 0; k < nseg; ++k) {
+    tab[k] = n;
+    tab[nseg + 1 + k] = w;
+    n += segs[k];
+    w += 2LL * LD * segs[k] * H;
+  }
+  tab[nseg] = n;
+  tab[2 * nseg + 1] = w;
+  const int b = S.next_buf;
+  S.next_buf ^= 1;
+  if (S.used[b]) CCSM_CUDA(cudaStreamWaitEvent(S.st, S.freed[b], 0));  // the forward that read this buffer is done
+  CCSM_TRY(S.words[b].reserve((size_t)w * 4));
+  CCSM_TRY(S.h0[b].reserve((size_t)w * 4));
+  CCSM_TRY(S.segtab[b].reserve(tab.size() * 8));
+  // pageable source: the call returns once the table sits in the driver's staging memory, so `tab` may die afterwards
+  CCSM_CUDA(cudaMemcpyAsync(S.segtab[b].p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, S.st));
+  mt_generate_kernel<<<1, 256, 0, S.st>>>(S.state.as<uint32_t>(), S.words[b].as<uint32_t>(), w);
+  float* a = S.h0[b].as<float>();
+  float* bb = a + (size_t)LD * n * H;
+  const long long pairs = w / 2;
+  mt_normal_h0_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, S.st>>>(
+      S.words[b].as<uint32_t>(), S.segtab[b].as<long long>(), S.segtab[b].as<long long>() + nseg + 1, nseg, n, LD, H, a, bb);
+  count_launch(2);
+  CCSM_CUDA(cudaGetLastError());
+  CCSM_CUDA(cudaEventRecord(S.ready[b], S.st));
+  CCSM_CUDA(cudaStreamWaitEvent(user, S.ready[b], 0));
+  S.used[b] = true;
+  *h0a = a;
+  *h0b = bb;
+  *buf = b;
+  return CCSM_OK;
+}
+
+int mt_release(ccsm_model* m, int buf, cudaStream_t user) {
+  CCSM_CUDA(cudaEventRecord(m->mts->freed[buf], user));
+  return CCSM_OK;
+}
+
+void mt_destroy(ccsm_model* m) {
+  if (!m->mts) return;
+  MtStream& S = *m->mts;
+  S.state.release();
+  for (int i = 0; i < 2; ++i) {
+    S.words[i].release();
+    S.h0[i].release();
+    S.segtab[i].release();
+    if (S.ready[i]) cudaEventDestroy(S.ready[i]);
+    if (S.freed[i]) cudaEventDestroy(S.freed[i]);
+  }
+  if (S.st) cudaStreamDestroy(S.st);
+  delete m->mts;
+  m->mts = nullptr;
+}
+
+}  // namespace ccsm
+
+using namespace ccsm;
+
+// torch.manual_seed(seed); torch.randn(skip); torch.randn(n) -> out (host, n floats; skip and n multiples of 16).
+extern "C" int ccsm_debug_torch_randn(int32_t device, uint64_t seed, int64_t skip, int64_t n, float* out) {
+  if (!out || n <= 0 || n % 16 || skip < 0 || skip % 16) {
+    set_error("ccsm_debug_torch_randn: n and skip must be multiples of 16");
+    return CCSM_EINVAL;
+  }
+  CCSM_CUDA(cudaSetDevice(device));
+  uint32_t st[MT_N + 1];
+  st[0] = (uint32_t)(seed & 0xffffffffu);
+  for (int j = 1; j < MT_N; ++j) st[j] = 1812433253u * (st[j - 1] ^ (st[j - 1] >> 30)) + (uint32_t)j;
+  st[MT_N] = MT_N;
+  DevBuf ds, dw, df;
+  CCSM_TRY(ds.reserve(sizeof(st)));
+  CCSM_TRY(dw.reserve((size_t)(skip > n ? skip : n) * 4));
+  CCSM_TRY(df.reserve((size_t)n * 4));
+  CCSM_CUDA(cudaMemcpy(ds.p, st, sizeof(st), cudaMemcpyHostToDevice));
+  if (skip) mt_generate_kernel<<<1, 256>>>(ds.as<uint32_t>(), dw.as<uint32_t>(), skip);
+  mt_generate_kernel<<<1, 256>>>(ds.as<uint32_t>(), dw.as<uint32_t>(), n);
+  mt_normal_flat_kernel<<<(unsigned)((n / 2 + 255) / 256), 256>>>(dw.as<uint32_t>(), df.as<float>(), n / 16);
+  count_launch(3);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, df.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  ds.release(); dw.release(); df.release();
+  if (e != cudaSuccess) {
+    set_error("ccsm_debug_torch_randn: %s", cudaGetErrorString(e));
+    return CCSM_ECUDA;
+  }
+  return CCSM_OK;
+}

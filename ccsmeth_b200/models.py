@@ -81,23 +81,69 @@ class _NativeModule(nn.Module):
 
     def set_h0_mode(self, mode, seed=1234):
         """How ``forward(..., h0=None)`` obtains the GRU initial state:
-        "reference" (default) -- torch.randn on the CPU default generator, exactly the reference's stream
-                                 (models.py:77-87), copied to the device (12 KB/site);
+        "reference" (default) -- the reference's stream (models.py:77-87: torch.randn on the process-wide CPU
+                                 generator, per model call, strand 1 then strand 2), drawn ON THE DEVICE bit for bit
+                                 (include/ccsm.h CCSM_H0_TORCH_STREAM): the call borrows torch's generator state, the
+                                 library draws from it, and the advanced state is handed back to torch -- so
+                                 ``torch.manual_seed(s); model(...)`` behaves like the reference and nothing crosses
+                                 PCIe.  GRU models; LSTM models fall back to "reference_host";
+        "reference_host"      -- the same stream drawn by torch.randn on the host and copied over (12 KB/site);
         "device"              -- N(0,1) drawn inside the feature-packing kernel (Philox, include/ccsm.h
-                                 CCSM_H0_DEVICE_RANDOM): same distribution, nothing materialised or transferred;
+                                 CCSM_H0_DEVICE_RANDOM): same distribution, not the reference's stream;
         "zeros"               -- zero state."""
-        if mode not in ("reference", "device", "zeros"):
-            raise ValueError("h0 mode must be reference, device or zeros")
+        if mode not in ("reference", "reference_host", "device", "zeros"):
+            raise ValueError("h0 mode must be reference, reference_host, device or zeros")
         self._h0_mode = mode
         self._h0_seed = int(seed)
         self._h0_mode_dirty = True
         return self
 
+    def _stream_h0(self):
+        """True when a call with h0=None draws the reference's stream inside the library."""
+        return self._h0_mode == "reference" and getattr(self, "rnn_cell", None) == "gru"
+
+    def _host_h0(self):
+        """True when a call with h0=None draws the reference's stream with torch.randn on the host."""
+        return self._h0_mode == "reference_host" or (self._h0_mode == "reference" and not self._stream_h0())
+
     def _apply_h0_mode(self, handle):
         if getattr(self, "_h0_mode_dirty", False):
-            mode = 1 if self._h0_mode == "device" else 0
+            mode = 1 if self._h0_mode == "device" else (2 if self._stream_h0() else 0)
             _lib.check(_lib.load().ccsm_set_h0_mode(handle, mode, ctypes.c_uint64(self._h0_seed)))
             self._h0_mode_dirty = False
+
+    def set_h0_batching(self, holebatch_sites, batch_size=512):
+        """"reference" mode: the next call's sites are these consecutive hole-batches, each cut into model calls of at
+        most ``batch_size`` sites like the reference's batch loop (call_modifications.py:177-181).  One-shot."""
+        self._h0_batching = (np.ascontiguousarray(holebatch_sites, dtype=np.int64), int(batch_size))
+
+    def _borrow_torch_rng(self, handle, n):
+        """Hands torch's CPU generator (MT19937 state + position) to the library's stream and announces the batching."""
+        lib = _lib.load()
+        st = torch.get_rng_state().numpy()
+        left = int.from_bytes(st[8:12].tobytes(), "little", signed=True)
+        nxt = int.from_bytes(st[16:24].tobytes(), "little")
+        words = np.ascontiguousarray(st[24:24 + 4992].view(np.uint64).astype(np.uint32))
+        pos = 624 if left == 1 else nxt
+        _lib.check(lib.ccsm_h0_stream_set_state(handle, words.ctypes.data, pos))
+        counts, bs = getattr(self, "_h0_batching", None) or (np.array([n], dtype=np.int64), 512)
+        self._h0_batching = None
+        if int(counts.sum()) != n:
+            raise ValueError("set_h0_batching announced %d sites, the call has %d" % (int(counts.sum()), n))
+        _lib.check(lib.ccsm_set_h0_batching(handle, counts.ctypes.data, len(counts), bs))
+        return st
+
+    def _return_torch_rng(self, handle, st):
+        """Reads the advanced generator back and installs it as torch's CPU generator state."""
+        words = np.empty(624, dtype=np.uint32)
+        pos = ctypes.c_int32(0)
+        _lib.check(_lib.load().ccsm_h0_stream_get_state(handle, words.ctypes.data, ctypes.byref(pos)))
+        st = st.copy()
+        st[24:24 + 4992] = words.astype(np.uint64).view(np.uint8)
+        p = pos.value
+        st[8:12] = np.frombuffer(int(1 if p == 624 else 625 - p).to_bytes(4, "little", signed=True), dtype=np.uint8)
+        st[16:24] = np.frombuffer(int(p).to_bytes(8, "little"), dtype=np.uint8)
+        torch.set_rng_state(torch.from_numpy(st))
 
     def _device_index(self):
         p = next(self.parameters())
@@ -123,7 +169,7 @@ class _NativeModule(nn.Module):
             h = ctypes.c_void_p()
             _lib.check(lib.ccsm_create(ctypes.byref(h), ctypes.byref(cfg)))
             self._handle, self._handle_key, self._dirty = h, key, True
-            self._h0_mode_dirty = self._h0_mode != "reference"
+            self._h0_mode_dirty = True
         if self._dirty:
             _lib.check(lib.ccsm_set_precision(self._handle, _lib.PREC[self._precision]))
             for k, v in self.state_dict().items():
@@ -221,12 +267,13 @@ class _ReadsMixin:
         if cell is None:
             h0 = None  # no recurrent state (transformer encoder)
         elif cell == "lstm":
-            if h0 is not None or self._h0_mode == "reference":
+            if h0 is not None or self._h0_mode in ("reference", "reference_host"):
                 raise ValueError("LSTM models in the reads pipeline take their initial state from the library: use "
                                  "h0 mode 'device' or 'zeros' (the cell state is zero)")
-        elif h0 is None and self._h0_mode == "reference":
+        elif h0 is None and self._host_h0():
             h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
                   self.init_hidden(n, self.num_layers, self.hidden_size))
+        borrowed = self._borrow_torch_rng(handle, n) if (h0 is None and cell == "gru" and self._stream_h0() and n > 0) else None
         pa = pb = None
         if h0 is not None:
             hshape = (2 * self.num_layers, n, self.hidden_size)
@@ -240,6 +287,8 @@ class _ReadsMixin:
                                                            probs.ctypes.data if want_probs else None,
                                                            res["prob1"].ctypes.data, res["mm"].ctypes.data,
                                                            res["ml"].ctypes.data))
+        if borrowed is not None:
+            self._return_torch_rng(handle, borrowed)
         if want_probs:
             res["probs"] = probs
         return res
@@ -323,7 +372,7 @@ class ModelAttRNN(_ReadsMixin, _NativeModule):
         device = torch.device("cuda", dev)
         n = int(torch.as_tensor(kmer).reshape(-1, self.seq_len).shape[0])
         self._apply_h0_mode(handle)
-        if h0 is None and self._h0_mode == "reference":
+        if h0 is None and self._host_h0():
             h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
                   self.init_hidden(n, self.num_layers, self.hidden_size))
         keep = []
@@ -351,9 +400,12 @@ class ModelAttRNN(_ReadsMixin, _NativeModule):
             pa = pb = None  # library draws (device mode) or uses zeros
         if n > 0:
             stream = torch.cuda.current_stream(device).cuda_stream
+            borrowed = self._borrow_torch_rng(handle, n) if (h0 is None and self._stream_h0()) else None
             _lib.check(_lib.load().ccsm_forward_att2s(handle, n, ctypes.byref(fwd), ctypes.byref(rev),
                                                       pa, pb, logits.data_ptr(),
                                                       probs.data_ptr(), ctypes.c_void_p(stream)))
+            if borrowed is not None:
+                self._return_torch_rng(handle, borrowed)
         return logits, probs
 
     def profile(self, on=True):
@@ -394,7 +446,7 @@ class ModelAttRNN(_ReadsMixin, _NativeModule):
                     setattr(s, name, t.data_ptr())
             strands.append(s)
         self._apply_h0_mode(handle)
-        if h0 is None and self._h0_mode == "reference":
+        if h0 is None and self._host_h0():
             h0 = (self.init_hidden(n, self.num_layers, self.hidden_size),
                   self.init_hidden(n, self.num_layers, self.hidden_size))
         hshape = (2 * self.num_layers, n, self.hidden_size)
@@ -406,8 +458,11 @@ class ModelAttRNN(_ReadsMixin, _NativeModule):
         logits = torch.empty((n, self.num_classes), dtype=torch.float32)
         probs = torch.empty((n, self.num_classes), dtype=torch.float32)
         if n > 0:
+            borrowed = self._borrow_torch_rng(handle, n) if (h0 is None and self._stream_h0()) else None
             _lib.check(_lib.load().ccsm_forward_att2s_host(handle, n, ctypes.byref(strands[0]), ctypes.byref(strands[1]),
                                                            pa, pb, logits.data_ptr(), probs.data_ptr()))
+            if borrowed is not None:
+                self._return_torch_rng(handle, borrowed)
         return logits, probs
 
 

@@ -139,10 +139,30 @@ int  ccsm_finalize(ccsm_model* m);
  *     kernel -- the reference draws torch.randn inside forward (models.py:77-87,125-130); this is the same
  *     distribution without materialising or transferring 12 KB/site of noise.  Value u of (site, strand, layer,
  *     direction) is output u of Philox subsequence ((site*2+strand)*2*layers + 2*layer+direction) at offset
- *     256*call, so every forward call sees fresh noise and all arithmetic modes see the same noise. */
+ *     256*call, so every forward call sees fresh noise and all arithmetic modes see the same noise.
+ *   CCSM_H0_TORCH_STREAM:    the reference's own stream, reproduced on the device bit for bit: what
+ *     torch.manual_seed(seed) followed by the reference's per-model-call torch.randn(2*layers, n_call, hidden) draws
+ *     (strand 1, then strand 2; models.py:77-87, seeded at call_modifications.py:479-481) yields on an AVX2-capable x86
+ *     host -- MT19937 outputs, 24-bit uniforms and ATen's 16-wide Box-Muller with its single-precision log / sincos
+ *     polynomials (csrc/mtstream.cu).  The generator state lives on the device and advances from call to call like the
+ *     reference's process-wide generator.  How a call's n sites split into the reference's model calls is announced with
+ *     ccsm_set_h0_batching; GRU att2s models only. */
 #define CCSM_H0_ZEROS 0
 #define CCSM_H0_DEVICE_RANDOM 1
+#define CCSM_H0_TORCH_STREAM 2
 int  ccsm_set_h0_mode(ccsm_model* m, int32_t mode, uint64_t seed);
+
+/* CCSM_H0_TORCH_STREAM: the NEXT forward call covers n_holebatches consecutive hole-batches of holebatch_sites[i] sites,
+ * each of which the reference cuts into model calls of at most batch_size sites (call_modifications.py:177-181, --batch_size).
+ * One-shot (consumed by the next call; without it a call is one hole-batch); batch_size stays in force. */
+int  ccsm_set_h0_batching(ccsm_model* m, const int64_t* holebatch_sites, int64_t n_holebatches, int32_t batch_size);
+
+/* CCSM_H0_TORCH_STREAM: hand over / read back the MT19937 state (624 words + position of the next output inside the
+ * block, 624 = regenerate first) -- the host mirror (ccsmeth_b200/models.py) uses it to draw from, and advance, torch's
+ * own CPU generator, so that forward(h0=None) consumes the process-wide stream exactly like the reference's forward.
+ * The getter waits for the generator's stream only. */
+int  ccsm_h0_stream_set_state(ccsm_model* m, const uint32_t* words624, int32_t pos);
+int  ccsm_h0_stream_get_state(ccsm_model* m, uint32_t* words624, int32_t* pos);
 
 /* Change the arithmetic mode of a finalized model (re-packs weights if needed). */
 int  ccsm_set_precision(ccsm_model* m, int32_t precision);
@@ -404,6 +424,9 @@ int  ccsm_debug_umma_mixed_gemm(int32_t device, int32_t N, int32_t K, const floa
 /* Tensor-pipe rate probe (one CTA, M = 128, N columns, operands fixed in shared memory): cycles for `iters` rounds of
  * four MMAs.  mode 0 = kind::f16, 1 = kind::f8f6f4 e4m3, 2 = f16 f16 e4m3 e4m3, 3 = alternating, 4 = rounds alternate. */
 int  ccsm_debug_umma_rate(int32_t device, int32_t N, int32_t mode, int32_t iters, int64_t* cycles);
+/* torch.manual_seed(seed); torch.randn(skip); torch.randn(n) reproduced on the device -> out (host, n floats; skip and
+ * n multiples of 16).  tests/test_h0_stream_gpu.py compares it with torch bit for bit. */
+int  ccsm_debug_torch_randn(int32_t device, uint64_t seed, int64_t skip, int64_t n, float* out);
 
 #ifdef __cplusplus
 }
