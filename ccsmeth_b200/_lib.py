@@ -33,7 +33,7 @@ EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_
            "ccsm_forward_att2s_host", "ccsm_forward_att2s_lstm", "ccsm_forward_aggr", "ccsm_forward_aggr_lstm", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
            "ccsm_debug_umma_pair_gemm", "ccsm_debug_umma_mixed_gemm", "ccsm_debug_umma_rate", "ccsm_debug_torch_randn", "ccsm_set_h0_batching",
-           "ccsm_h0_stream_set_state", "ccsm_h0_stream_get_state", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
+           "ccsm_h0_stream_set_state", "ccsm_h0_stream_get_state", "ccsm_bam_scan_records", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
            "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_inflate_stats", "ccsm_bgzf_deflate_bound",
            "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records", "ccsm_bam_modcalls", "ccsm_pileup_luts",
            "ccsm_pileup_begin_host", "ccsm_pileup_finish_host", "ccsm_pileup_finish_lstm_host"]
@@ -75,7 +75,11 @@ class ModcallOpts(ctypes.Structure):
 
 
 class BamFilter(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("mode_align", "mapq", "no_supplementary", "skip_unmapped", "want_sn")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("mode_align", "mapq", "no_supplementary", "skip_unmapped", "want_sn", "pad_")] + \
+               [("identity", ctypes.c_double)]
+
+    def __init__(self, mode_align=0, mapq=0, no_supplementary=0, skip_unmapped=0, want_sn=0, identity=0.0):
+        super().__init__(mode_align, mapq, no_supplementary, skip_unmapped, want_sn, 0, float(identity))
 
 
 def sources():
@@ -192,6 +196,8 @@ def load():
         lib.ccsm_h0_stream_set_state.restype = ctypes.c_int
         lib.ccsm_h0_stream_get_state.argtypes = [vp, vp, vp]
         lib.ccsm_h0_stream_get_state.restype = ctypes.c_int
+        lib.ccsm_bam_scan_records.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.ccsm_bam_scan_records.restype = ctypes.c_int64
         lib.ccsm_set_h0_mode.argtypes = [vp, i32, ctypes.c_uint64]
         lib.ccsm_set_h0_mode.restype = ctypes.c_int
         lib.ccsm_profile_enable.argtypes = [vp, i32]

@@ -332,7 +332,22 @@ def iter_region_results(args, model, dnacontigs, bam_path, rank=0, world=1, piec
         calls.parts = [(rid[keep], pos[keep], ml[keep], hap[keep], strand[keep])] if keep.any() else []
 
     done = 0
+    last_key = -1
     for piece in rd:
+        # the streaming flush below relies on coordinate order; the reference fails loudly on other input (it fetches
+        # regions through the index), so an unsorted modbam must not silently lose calls here
+        offs = piece.recs["off"].astype(np.int64)
+        rp = np.frombuffer(piece.buf, dtype=np.uint8)
+        rid_pos = np.stack([rp[offs + 4 + k].astype(np.int64) << (8 * (k % 4)) for k in range(8)], axis=0)
+        r_id = rid_pos[:4].sum(0).astype(np.uint32).astype(np.int32).astype(np.int64)
+        r_id = np.where(r_id < 0, np.int64(1) << 30, r_id)               # unplaced (-1) sorts last
+        r_pos = (rid_pos[4:].sum(0).astype(np.uint32).astype(np.int32) + 1).astype(np.int64)
+        keys = (r_id << 32) | r_pos
+        if len(keys) and (int(keys[0]) < last_key or np.any(keys[1:] < keys[:-1])):
+            raise ValueError("%s is not coordinate-sorted: sort it first (samtools sort, or call_mods without --no_sort)"
+                             % args.input_bam)
+        if len(keys):
+            last_key = int(keys[-1])
         calls.add_piece(piece, opts)
         off = int(piece.recs["off"][-1]) + 4
         last_ref = int(np.frombuffer(piece.buf[off:off + 4].tobytes(), dtype="<i4")[0])

@@ -12,8 +12,9 @@ The reference wires reader / extractors / model workers / writer with multiproce
 native record indexing, bamstream.py), the GPU calls (feature extraction + forward + MM/ML values on the device,
 csrc/extract.cu) and a writer thread (native re-tagging + BGZF deflate on the thread team), takes the hole-batches
 with ``batch_idx % world == rank`` and writes its own BAM shard.  No per-read Python objects on this path;
-``call_reads`` / ``tag_read`` are the record-level equivalents kept for callers that hold BamRecords.  Sorting/indexing
-(call_modifications.py:592-607) needs samtools and is left to the caller: the output is always unsorted.
+``call_reads`` / ``tag_read`` are the record-level equivalents kept for callers that hold BamRecords.  Unless
+``--no_sort`` is given the output is coordinate-sorted and indexed (.bai) like the reference's (call_modifications.py:592-607
+runs samtools sort / index through pysam; here bamsort.py), with the rank shards merged into one file by rank 0.
 
     python -m ccsmeth_b200.call_mods -i in.hifi.bam -m model.ckpt -o out_prefix [--mode denovo] ...
 """
@@ -271,7 +272,8 @@ def call_mods(args):
 
     threads = max(1, args.threads)
     flt = _lib.BamFilter(1 if args.mode == "align" else 0, args.mapq, 1 if args.no_supplementary else 0,
-                         1 if str2bool(args.skip_unmapped) else 0, 1 if str2bool(args.is_sn) else 0)
+                         1 if str2bool(args.skip_unmapped) else 0, 1 if str2bool(args.is_sn) else 0,
+                         identity=args.identity if args.mode == "align" else 0.0)
     # a piece = `device_batch` hole-batches' worth of compressed bytes (about 3 MB per 50 HiFi reads)
     rd = BamPieceReader(args.input, flt, threads=threads,
                         piece_bytes=max(1, getattr(args, "device_batch", 8)) * args.holes_batch * 65536,
@@ -309,6 +311,11 @@ def call_mods(args):
     wr.close()
     rd.close()
     total = parallel.allreduce_counts(counts)
+    if not args.no_sort:
+        # reference call_modifications.py:592-607: samtools sort + index of the modbam unless --no_sort
+        t_sort = time.perf_counter()
+        out_modbam = _sort_and_index(args, out_modbam, rank, world, threads)
+        _tic("sort_index", t_sort)
     if rank == 0:
         dt = time.time() - t0
         sys.stderr.write("[call_mods] %d sites in %d model batches(%d), wrote %d reads, in which %d were added mm "
@@ -317,6 +324,27 @@ def call_mods(args):
             sys.stderr.write("[call_mods] stage seconds (threads overlap): %s\n" %
                              ", ".join("%s %.3f" % kv for kv in sorted(TIMING.items())))
     return dict(zip(("sites", "model_batches", "reads_written", "reads_with_mm"), total)), out_modbam
+
+
+def _sort_and_index(args, out_modbam, rank, world, threads):
+    """Coordinate sort + .bai of the output (ccsmeth_b200/bamsort.py).  One rank: in place -- and when the records are
+    already in coordinate order (a sorted input keeps its order; an unaligned input has only unplaced reads) only the
+    index is written.  Several ranks (one node): rank 0 merges the sorted shards into <output>.modbam.bam."""
+    from . import bamsort
+    final = args.output + ".modbam.bam"
+    comp = getattr(args, "bam_compress", "rle")
+    if world == 1:
+        if bamsort.index_sorted(out_modbam, threads=threads) < 0:
+            bamsort.sort_and_index(out_modbam, out_modbam, threads=threads, bam_compress=comp)
+        return out_modbam
+    parallel.barrier()
+    if rank == 0:
+        shards = [args.output + ".rank%d.modbam.bam" % r for r in range(world)]
+        bamsort.sort_and_index(shards, final, threads=threads, bam_compress=comp)
+        for p in shards:
+            os.remove(p)
+    parallel.barrier()
+    return final
 
 
 def _get_holes(path):

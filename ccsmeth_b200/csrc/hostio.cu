@@ -127,10 +127,11 @@ static int scan_blocks(const uint8_t* src, int64_t n, std::vector<BgzfBlock>& ou
     for (int i = 0; i + 4 <= xlen;) {
       const uint8_t* e = src + p + 12 + i;
       const int slen = e[2] | (e[3] << 8);
+      if (i + 4 + slen > xlen) return -1;  // a subfield must lie inside the extra field
       if (e[0] == 66 && e[1] == 67 && slen == 2) bsize = (e[4] | (e[5] << 8)) + 1;
       i += 4 + slen;
     }
-    if (bsize < 0) return -1;
+    if (bsize < 12 + xlen + 8) return -1;  // header + extra field + CRC32 + ISIZE at the very least
     if (p + bsize > n) break;
     BgzfBlock b;
     b.src_off = p + 12 + xlen;
@@ -453,6 +454,18 @@ int ccsm_bam_index(const uint8_t* buf, int64_t n_bytes, const ccsm_bam_filter* f
       if (rec.flag & (0x4 | 0x100 | 0x400)) use = false;
       if (f->no_supplementary && (rec.flag & 0x800)) use = false;
       if (rec.mapq < f->mapq) use = false;
+      if (use && f->identity > 0.0) {
+        // compute_pct_identity (process_utils.py:174-186), applied at extract_features.py:283-286
+        const uint8_t* cig = r + 32 + l_name;
+        double nalign = 0, nmatch = 0;
+        for (int c = 0; c < rec.n_cigar; ++c) {
+          const uint32_t v = (uint32_t)rd_i32(cig + 4 * c);
+          const int op = v & 15;
+          if (op != 4 && op != 5 && op <= 9) nalign += v >> 4;
+          if (op == 0 || op == 7) nmatch += v >> 4;
+        }
+        if ((nalign > 0 ? nmatch / nalign : 0.0) < f->identity) use = false;
+      }
     }
     // aux scan: kinetics arrays (B:C of l_seq entries), pass counts, sn
     const uint8_t* a = r + aux_off;
@@ -478,8 +491,9 @@ int ccsm_bam_index(const uint8_t* buf, int64_t n_bytes, const ccsm_bam_filter* f
           if (rd_i32(a + 4) == rec.l_seq) koff[k] = (a + 8) - buf;
           else bad_kin = true;  // incomplete kinetics: the reference skips the read (extract_features.py:321-326)
         } else {
-          set_error("ccsm_bam_index: tag %c%c is not a B:C (uint8) array; ccsmeth_b200 reads CodecV1 kinetics", t0, t1);
-          return CCSM_EUNSUPPORTED;
+          // not CodecV1 bytes (e.g. raw-frame B:S arrays): this read cannot be called here; like a read with
+          // incomplete kinetics it is passed through to the output untouched instead of failing the whole run
+          bad_kin = true;
         }
       } else if (t0 == 'f' && t1 == 'n') {
         has_fn = aux_int(a, &fn);
@@ -649,7 +663,21 @@ int64_t ccsm_bam_modcalls(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t 
       const char t0 = (char)a[0], t1 = (char)a[1];
       if (t0 == 'M' && t1 == 'M' && a[2] == 'Z') mm = (const char*)a + 3;
       else if (t0 == 'M' && t1 == 'L' && a[2] == 'B' && (a[3] == 'C' || a[3] == 'c')) { mlp = a + 8; ml_n = (uint32_t)rd_i32(a + 4); }
-      else if (t0 == o->hap_tag[0] && t1 == o->hap_tag[1]) { int32_t v; if (aux_int(a, &v)) hp = v; }
+      else if (t0 == o->hap_tag[0] && t1 == o->hap_tag[1]) {
+        int32_t v;
+        if (aux_int(a, &v)) hp = v;
+        else if (a[2] == 'A' && a[3] >= '0' && a[3] <= '9') hp = a[3] - '0';  // the reference does int(get_tag(..))
+        else if (a[2] == 'Z') {
+          const char* z = (const char*)a + 3;
+          int32_t acc = 0;
+          bool dig = *z != 0;
+          for (; *z; ++z) {
+            if (*z < '0' || *z > '9' || acc > 100000000) { dig = false; break; }
+            acc = acc * 10 + (*z - '0');
+          }
+          if (dig) hp = acc;
+        }
+      }
       else if (t0 == 'N' && t1 == 'M') { int32_t v; if (aux_int(a, &v)) nm = v; }
       a += sz;
     }
@@ -780,6 +808,57 @@ int64_t ccsm_bam_modcalls(const uint8_t* buf, const ccsm_bam_rec* recs, int32_t 
   }
   *n_reads_used = used;
   return n_out;  // > cap: the caller retries with a larger buffer
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// Replaces the record walk of `samtools sort` / `samtools index` (reference call_modifications.py:592-607 runs both
+// through pysam): per complete alignment record of an inflated BAM stream the coordinate key
+// (uint32(refID) << 32 | (pos + 1) << 1 | reverse-strand), its byte range, and the fields the BAI needs.
+int64_t ccsm_bam_scan_records(const uint8_t* buf, int64_t n_bytes, int64_t max_recs, uint64_t* key, int64_t* off,
+                              int32_t* len, int32_t* ref_id, int32_t* pos, int32_t* end, int32_t* flag,
+                              int64_t* consumed) {
+  if (!buf || n_bytes < 0 || max_recs < 0 || !key || !off || !len || !ref_id || !pos || !end || !flag || !consumed) {
+    ccsm::set_error("ccsm_bam_scan_records: bad argument");
+    return CCSM_EINVAL;
+  }
+  int64_t p = 0, n = 0;
+  while (p + 4 <= n_bytes && n < max_recs) {
+    const int64_t bs = rd_i32(buf + p);
+    if (bs < 32) {
+      ccsm::set_error("ccsm_bam_scan_records: record at byte %lld has block_size %lld", (long long)p, (long long)bs);
+      return CCSM_EINVAL;
+    }
+    if (p + 4 + bs > n_bytes) break;
+    const uint8_t* r = buf + p + 4;
+    const int32_t tid = rd_i32(r), ps = rd_i32(r + 4);
+    const int l_name = r[8];
+    const uint32_t n_cig = rd_u16(r + 12), fl = rd_u16(r + 14);
+    if (32 + (int64_t)l_name + 4 * (int64_t)n_cig > bs) {
+      ccsm::set_error("ccsm_bam_scan_records: record at byte %lld overruns its block_size", (long long)p);
+      return CCSM_EINVAL;
+    }
+    int64_t rl = 0;
+    const uint8_t* cg = r + 32 + l_name;
+    for (uint32_t i = 0; i < n_cig; ++i) {
+      const uint32_t v = (uint32_t)rd_i32(cg + 4 * i), op = v & 15;
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += v >> 4;
+    }
+    if ((fl & 4) || rl == 0) rl = 1;
+    key[n] = ((uint64_t)(uint32_t)tid << 32) | ((uint64_t)(uint32_t)(ps + 1) << 1) | ((fl & 16) ? 1u : 0u);
+    off[n] = p;
+    len[n] = (int32_t)(bs + 4);
+    ref_id[n] = tid;
+    pos[n] = ps;
+    end[n] = (int32_t)(ps + rl);
+    flag[n] = (int32_t)fl;
+    ++n;
+    p += 4 + bs;
+  }
+  *consumed = p;
+  return n;
 }
 
 }  // extern "C"

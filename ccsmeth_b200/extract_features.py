@@ -57,7 +57,21 @@ def read_passes_filters(rec, args, holeids_e=None, holeids_ne=None):
             return False
         if rec.mapq < args.mapq:
             return False
+        if getattr(args, "identity", 0.0) > 0.0 and cigar_identity(rec) < args.identity:
+            return False
     return True
+
+
+def cigar_identity(rec):
+    """compute_pct_identity of the reference (process_utils.py:174-186) on a bamio.BamRecord: matches (M, =) over every
+    aligned operation except clips; 0 for a CIGAR-less record."""
+    nalign = nmatch = 0
+    for op, ln in rec.cigartuples or ():
+        if op not in (4, 5) and op <= 9:
+            nalign += ln
+        if op in (0, 7):
+            nmatch += ln
+    return nmatch / float(nalign) if nalign else 0.0
 
 
 def pack_reads(records, args, holeids_e=None, holeids_ne=None):

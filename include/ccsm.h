@@ -331,6 +331,17 @@ int64_t ccsm_bgzf_deflate_bound(int64_t src_bytes);
 int64_t ccsm_bgzf_deflate(const uint8_t* src, int64_t src_bytes, uint8_t* dst, int64_t dst_cap, int32_t level,
                           int32_t threads);
 
+/* Replaces the record walk of `samtools sort` / `samtools index`, which the reference runs on its output through pysam
+ * (call_modifications.py:592-607).  Walks the complete alignment records of an inflated BAM stream positioned at a
+ * record boundary; per record: the coordinate sort key samtools uses, (uint32) refID << 32 | (pos + 1) << 1 | reverse
+ * strand (refID -1 sorts last), the byte offset and length of the record including its 4-byte block_size, refID, pos,
+ * end = pos + reference length of the CIGAR (pos + 1 for unmapped / CIGAR-less records) and the flag.  Returns the number
+ * of records (at most max_recs); *consumed = bytes of the complete records walked.  Host code (ccsmeth_b200/bamsort.py
+ * builds the sorted BAM and its .bai from it). */
+int64_t ccsm_bam_scan_records(const uint8_t* buf, int64_t n_bytes, int64_t max_recs, uint64_t* key, int64_t* off,
+                              int32_t* len, int32_t* ref_id, int32_t* pos, int32_t* end, int32_t* flag,
+                              int64_t* consumed);
+
 /* ---- host I/O helpers: BAM record indexing and re-tagging (SAM/BAM spec 4.2) -------------------------------
  * ccsm_bam_index walks the complete alignment records in an inflated BAM byte stream `buf` (positioned at a
  * record boundary) and fills, per record, a ccsm_bam_rec, and per read that takes part in calling, a ccsm_read
@@ -356,6 +367,9 @@ typedef struct ccsm_bam_filter {
   int32_t no_supplementary;  /* --no_supplementary */
   int32_t skip_unmapped;     /* --skip_unmapped yes: only sites inside the aligned part of the query */
   int32_t want_sn;           /* --is_sn yes: copy the sn tag */
+  int32_t pad_;
+  double  identity;          /* --identity (--mode align): drop reads whose CIGAR identity, matches (M, =) over all
+                                aligned operations but clips (process_utils.py:174-186), is below it */
 } ccsm_bam_filter;
 
 int     ccsm_bam_index(const uint8_t* buf, int64_t n_bytes, const ccsm_bam_filter* f, ccsm_bam_rec* recs,

@@ -33,9 +33,9 @@ p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
 t2 = time.time()
 assert p.returncode == 0, p.stderr[-2000:]
 one = tags(os.path.join(tmp, "one.modbam.bam"))
-many = {}
-for r in range(N):
-    many.update(tags(os.path.join(tmp, "many.rank%d.modbam.bam" % r)))
+# without --no_sort rank 0 merges the rank shards into one coordinate-sorted, indexed modbam (bamsort.py)
+many = tags(os.path.join(tmp, "many.modbam.bam"))
+assert os.path.exists(os.path.join(tmp, "many.modbam.bam.bai")) and not os.path.exists(os.path.join(tmp, "many.rank0.modbam.bam"))
 log = [l for l in p.stderr.splitlines() if l.startswith("[call_mods]")]
 res = {"ranks": N, "reads": len(one), "call_mods_shards_equal_single": many == one, "single_s": t1 - t0, "multi_s": t2 - t1,
        "rank0_log": log[-1] if log else ""}

@@ -25,7 +25,8 @@ def _args(**kw):
 
 def _filter(args):
     return _lib.BamFilter(1 if args.mode == "align" else 0, args.mapq, 1 if args.no_supplementary else 0,
-                          1 if args.skip_unmapped == "yes" else 0, 0)
+                          1 if args.skip_unmapped == "yes" else 0, 0,
+                          identity=getattr(args, "identity", 0.0) if args.mode == "align" else 0.0)
 
 
 def _check_pieces(path, args, piece_bytes, align_to):
@@ -125,15 +126,19 @@ def test_index_applies_align_mode_filters_and_softclip_windows(tmp_path):
     recs.append(random_read(rng, "unmapped", 300, flag=4)[0])
     recs.append(random_read(rng, "lowq", 300, flag=0, cigar=((0, 300),), mapq=0)[0])
     recs.append(random_read(rng, "dup", 300, flag=1024, cigar=((0, 300),), mapq=60)[0])
+    # CIGAR identity (--identity, reference extract_features.py:283-286): 250 / 300 and 290 / 300
+    recs.append(random_read(rng, "lowid", 300, flag=0, cigar=((0, 200), (1, 50), (0, 50)), mapq=60)[0])
+    recs.append(random_read(rng, "highid", 300, flag=0, cigar=((7, 290), (8, 10)), mapq=60)[0])
     path = str(tmp_path / "syn.bam")
     wr = BamWriter(path, "@HD\tVN:1.6\n@SQ\tSN:chr1\tLN:100000\n", [("chr1", 100000)])
     for r in recs:
         wr.write_raw(r.raw)
     wr.close()
-    for kw in ({"mode": "align"}, {"mode": "align", "skip_unmapped": "no"}, {"mode": "denovo"}):
+    for kw in ({"mode": "align"}, {"mode": "align", "skip_unmapped": "no"}, {"mode": "denovo"},
+               {"mode": "align", "identity": 0.9}, {"mode": "denovo", "identity": 0.9}):
         pieces, _ = _check_pieces(path, _args(**kw), 1 << 20, 5)
         kept = sum(len(p.descs) for p in pieces)
-        assert kept == (9 if kw["mode"] == "align" else 12)
+        assert kept == ((10 if kw.get("identity") else 11) if kw["mode"] == "align" else 14)
 
 
 def test_truncated_file_is_an_error(tmp_path):

@@ -216,3 +216,35 @@ def test_write_lines_prints_what_write_one_line_prints():
             cf.write_one_line(it, a, bed)
         cf.write_lines(items, b, bed)
         assert a.getvalue() == b.getvalue()
+
+
+def test_unsorted_modbam_is_refused_and_sorting_it_restores_the_result(tmp_path, ref_out):
+    import struct
+    """The streaming region caller needs coordinate order (the reference fetches through the index and fails loudly on
+    other input): an unsorted modbam raises, and after ccsmeth_b200.bamsort the golden output comes back."""
+    from ccsmeth_b200 import bamsort
+    from ccsmeth_b200.bamio import BamReader, BamWriter
+    rd = BamReader(BAM)
+    recs = [r.raw for r in rd]
+    rng = np.random.default_rng(1)
+    shuffled = str(tmp_path / "shuffled.bam")
+    w = BamWriter(shuffled, rd.header_text.replace("SO:coordinate", "SO:unsorted"), rd.references)
+    for i in rng.permutation(len(recs)):
+        w.write_raw(recs[i])
+    w.close()
+    args = _args()
+    contigs = cf.read_fasta(FA)
+
+    class NoModel:
+        def pileup_begin(self, *a, **k):
+            raise AssertionError("unsorted input must be refused before any region is called")
+
+    with pytest.raises(ValueError, match="not coordinate-sorted"):
+        for _ in cf.iter_region_results(args, NoModel(), contigs, shuffled, piece_bytes=30000):
+            pass
+    fixed = str(tmp_path / "fixed.bam")
+    assert bamsort.sort_and_index(shuffled, fixed, threads=2) == len(recs)
+    got = [r.raw for r in BamReader(fixed)]
+    key = lambda raw: ((struct.unpack_from("<i", raw, 0)[0] & 0xFFFFFFFF) << 32) | ((struct.unpack_from("<i", raw, 4)[0] + 1) << 1) | \
+        (1 if struct.unpack_from("<H", raw, 14)[0] & 16 else 0)
+    assert [key(r) for r in got] == sorted(key(r) for r in recs) and sorted(got) == sorted(recs)
