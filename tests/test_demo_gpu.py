@@ -22,7 +22,7 @@ def ckpt_file(tmp_path_factory, ckpt_att2s):
     return p
 
 
-@pytest.mark.parametrize("prec,max_ml_flips", [("fp16x3", 12), ("fp32", 12), ("bf16x3", 20)])
+@pytest.mark.parametrize("prec,max_ml_flips", [("fp16c8", 12), ("fp16x3", 12), ("fp32", 12), ("bf16x3", 20)])
 def test_call_mods_demo_matches_reference_chain(tmp_path, ckpt_file, prec, max_ml_flips):
     g = load_npz("demo_callmods.npz")
     out = str(tmp_path / ("demo_" + prec))
