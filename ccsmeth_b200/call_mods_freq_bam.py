@@ -1,16 +1,16 @@
 """Aggregate-mode frequency model, host side (the reference's ccsmeth/call_mods_freq_bam.py, hot part only).
 
-Mirrors ``_cal_modfreq_in_aggregate_mode`` (reference call_mods_freq_bam.py:265-305): zero-pad 5 sites each
-side, sliding windows of 11 neighbouring CpG sites -> (n, 11, 20) histograms and (n, 11) |position offsets|,
-model forward, ``np.round(np.clip(out, 0, 1), 6)``.  The reference runs the model in batches of 1024 on the
-CPU and rebuilds + reloads it for every region (:308-342); here the model is resident on the GPU, the whole
-region goes through in one call, and the h0 stream is still drawn per 1024-slice in the reference's order.
+Stands in for ``_cal_modfreq_in_aggregate_mode`` (reference call_mods_freq_bam.py:265-305): every site sees the
+histograms of its 11-site neighbourhood (zero rows beyond the region's ends) and the distances to them, the model
+runs, the output is clipped to [0, 1] and rounded to 6 places.  The reference builds the (n, 11, 20) windows on the
+host, runs the model in batches of 1024 on the CPU and rebuilds + reloads it for every region (:308-342); here the
+model is resident on the GPU, the kernel gathers the neighbourhoods from the per-site rows, the whole region goes
+through in one call, and the h0 stream is still drawn per 1024-slice in the reference's order.
 """
 from collections import OrderedDict
 
 import numpy as np
 import torch
-from numpy.lib.stride_tricks import sliding_window_view
 
 from .models import AggrAttRNN
 
@@ -18,31 +18,44 @@ AGGR_BATCH = 1024  # reference call_mods_freq_bam.py:295
 
 
 def _cal_modfreq_in_aggregate_mode(refposes, refposes_histos, model, seq_len=11, only_close=False, h0=None):
-    if len(refposes) == 0:
+    """Same arguments and result as the reference's function (call_mods_freq_bam.py:265-305).  The shipped model
+    configuration hands the per-site rows to the device, where the kernel gathers each site's neighbourhood
+    (``AggrAttRNN.forward_sites``); other configurations get their windows from ``site_windows`` below."""
+    n = len(refposes)
+    if n == 0:
         return None
-    pad_len = seq_len // 2
-    histos_mat = np.pad(np.stack(refposes_histos), pad_width=((pad_len, pad_len), (0, 0)),
-                        mode='constant', constant_values=0)
-    histos_mat = np.swapaxes(sliding_window_view(histos_mat, seq_len, axis=0), 1, 2)
-    if not only_close:
-        pos_mat = np.pad(refposes, pad_width=(pad_len, pad_len), mode='constant',
-                         constant_values=(refposes[0] - 1000, refposes[-1] + 1000))
-        pos_mat = sliding_window_view(pos_mat, seq_len)
-        pos_mat_center = np.repeat(refposes, seq_len).reshape((-1, seq_len))
-        pos_mat = np.absolute(np.subtract(pos_mat, pos_mat_center))
-    else:
-        pos_mat = np.pad(refposes, pad_width=(pad_len + 1, pad_len), mode='constant',
-                         constant_values=(refposes[0] - 1000, refposes[-1] + 1000))
-        pos_mat = np.diff(pos_mat)
-        pos_mat = (pos_mat == 2).astype(int)
-        pos_mat = sliding_window_view(pos_mat, seq_len)
-    n = len(histos_mat)
+    pos = np.asarray(refposes, dtype=np.int64)
+    rows = np.asarray(refposes_histos, dtype=np.float32).reshape(n, -1)
     if h0 is None:
         h0 = draw_initial_states(n, model.num_layers, model.hidden_size, model.rnn_cell == "lstm")
-    out = model(torch.from_numpy(np.ascontiguousarray(pos_mat, dtype=np.float32)),
-                torch.from_numpy(np.ascontiguousarray(histos_mat, dtype=np.float32)), h0=h0)
-    logits = np.round(np.clip(out.cpu().numpy(), 0, 1), 6)
-    return [logits[idx][0] for idx in range(n)]
+    if model.fused() and seq_len == model.seq_len:
+        out = model.forward_sites(pos, rows, h0=h0, only_close=only_close)
+    else:
+        offsets, windows = site_windows(pos, rows, seq_len, only_close)
+        out = model(torch.from_numpy(offsets), torch.from_numpy(windows), h0=h0)
+    freq = np.round(np.clip(out.cpu().numpy(), 0, 1), 6)
+    return [freq[i][0] for i in range(n)]
+
+
+def site_windows(pos, rows, seq_len=11, only_close=False):
+    """Neighbourhood tensors of a region's sites, by index gather: window slot k of site i is site i + k - seq_len // 2.
+    Slots outside the region hold a zero histogram and sit 1000 bp before the first / after the last site
+    (reference call_mods_freq_bam.py:272-283).  Returns (offsets (n, seq_len) float32, windows (n, seq_len, bins) float32):
+    offsets = distance to the centre site, or with ``only_close`` 1.0 where a slot's site lies exactly 2 bp after the
+    previous slot's site (:285-290)."""
+    n, half = len(pos), seq_len // 2
+    nb = np.arange(n)[:, None] + np.arange(-half, half + 1)[None, :]       # (n, seq_len) site index of every slot
+    inside = (nb >= 0) & (nb < n)
+    at = np.clip(nb, 0, n - 1)
+    windows = np.where(inside[:, :, None], rows[at], np.float32(0))
+    slot_pos = np.where(nb < 0, pos[0] - 1000, np.where(nb >= n, pos[-1] + 1000, pos[at]))
+    if only_close:
+        before = nb - 1                                                     # the slot one step to the left
+        prev_pos = np.where(before < 0, pos[0] - 1000, np.where(before >= n, pos[-1] + 1000, pos[np.clip(before, 0, n - 1)]))
+        offsets = (slot_pos - prev_pos == 2)
+    else:
+        offsets = np.abs(slot_pos - pos[:, None])
+    return np.ascontiguousarray(offsets, dtype=np.float32), np.ascontiguousarray(windows, dtype=np.float32)
 
 
 def draw_initial_states(n, num_layers, hidden_size, lstm=False):

@@ -570,6 +570,30 @@ int ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const floa
   return forward_aggr_impl(m, n, offsets, histos, h0, nullptr, out, stream, "ccsm_forward_aggr");
 }
 
+int ccsm_forward_aggr_sites(ccsm_model* m, int64_t n, const int64_t* site_pos, const float* site_histo,
+                            int32_t only_close, const float* h0, float* out, void* stream) {
+  if (!m || m->cfg.kind != CCSM_KIND_AGGR) {
+    set_error("ccsm_forward_aggr_sites: not an aggregate model");
+    return CCSM_EINVAL;
+  }
+  if (!m->finalized) {
+    set_error("ccsm_forward_aggr_sites: model not finalized");
+    return CCSM_ESTATE;
+  }
+  if (n < 0 || (n > 0 && (!site_pos || !site_histo || !out))) {
+    set_error("ccsm_forward_aggr_sites: bad argument");
+    return CCSM_EINVAL;
+  }
+  if (n == 0) return CCSM_OK;
+  if (!aggr_fused_supported(m)) {
+    set_error("ccsm_forward_aggr_sites: in-kernel windows need the fused configuration (GRU, hidden 32, one layer)");
+    return CCSM_EUNSUPPORTED;
+  }
+  CCSM_CUDA(cudaSetDevice(m->cfg.device));
+  return aggr_fused_forward_sites(m, n, reinterpret_cast<const long long*>(site_pos), site_histo, only_close ? 1 : 0, h0,
+                                  out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ccsm_forward_aggr_lstm(ccsm_model* m, int64_t n, const float* offsets, const float* histos, const float* h0,
                            const float* c0, float* out, void* stream) {
   if (m && m->gates != 4) {

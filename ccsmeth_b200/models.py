@@ -670,6 +670,30 @@ class AggrAttRNN(_NativeModule):
                                                          out.data_ptr(), ctypes.c_void_p(stream)))
         return out
 
+    def fused(self):
+        """True for the configuration the one-launch kernel implements (include/ccsm.h ccsm_forward_aggr_sites)."""
+        return self.rnn_cell == "gru" and self.hidden_size == 32 and self.num_layers == 1 and self.binsize == 20 \
+            and self.num_classes == 1 and self.seq_len <= 32
+
+    def forward_sites(self, positions, site_histos, h0=None, only_close=False):
+        """The forward from per-site rows (include/ccsm.h ccsm_forward_aggr_sites): positions (n,) and histograms
+        (n, bins) of the region's sites in order; the kernel forms every site's window of ``seq_len`` neighbours itself
+        (what reference call_mods_freq_bam.py:265-293 materialises on the host)."""
+        handle, dev = self._ensure_handle()
+        device = torch.device("cuda", dev)
+        pos = torch.as_tensor(np.ascontiguousarray(positions, dtype=np.int64)).to(device)
+        n = int(pos.shape[0])
+        histos = _dev_f32(site_histos, device, (n, self.binsize))
+        if h0 is None:
+            h0 = self.init_hidden(n, self.num_layers, self.hidden_size)
+        h0 = _dev_f32(h0, device, (2 * self.num_layers, n, self.hidden_size))
+        out = torch.empty((n, self.num_classes), dtype=torch.float32, device=device)
+        if n > 0:
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(_lib.load().ccsm_forward_aggr_sites(handle, n, pos.data_ptr(), histos.data_ptr(), 1 if only_close else 0,
+                                                           h0.data_ptr(), out.data_ptr(), ctypes.c_void_p(stream)))
+        return out
+
     # ---- call_freqb on the device: one region's pileup -> per-site frequencies (include/ccsm.h ccsm_pileup_*)
     def pileup_begin(self, refpos, ptr, ml, hap=None, call_mode="aggregate", cov_cf=4, prob_cf=0.0, no_amb_cov=False,
                      no_hap=False, only_close=False):

@@ -193,6 +193,15 @@ int  ccsm_forward_att2s_host(ccsm_model* m, int64_t n, const ccsm_strand* fwd, c
 int  ccsm_forward_aggr(ccsm_model* m, int64_t n, const float* offsets, const float* histos,
                        const float* h0, float* out, void* stream);
 
+/* The same forward from per-SITE rows: the kernel gathers each site's window of L neighbouring sites itself -- zero
+ * histogram rows and positions pos[0] - 1000 / pos[n-1] + 1000 beyond the ends, offsets |pos_j - pos_centre|, or with
+ * only_close the 0/1 "next CpG is 2 bp away" flags (reference call_mods_freq_bam.py:265-293) -- so the (n, L, bins + 1)
+ * windows the reference materialises on the host never exist.  site_pos (n) int64, site_histo (n, bins) float32, h0
+ * (2*layers, n, hidden) or NULL, out (n, num_classes); device.  Fused-kernel configurations only (GRU, hidden 32, one
+ * layer, 20 bins); CCSM_EUNSUPPORTED otherwise. */
+int  ccsm_forward_aggr_sites(ccsm_model* m, int64_t n, const int64_t* site_pos, const float* site_histo,
+                             int32_t only_close, const float* h0, float* out, void* stream);
+
 /* AggrAttRNN.forward with model_type="attbilstm" (models.py:640-643, 661-671): as ccsm_forward_aggr plus the initial
  * cell state c0, (2*layers, n, hidden) float32 device or NULL (zeros); the reference draws h0 then c0 with torch.randn.
  * ccsm_forward_aggr on an LSTM model uses c0 = 0. */

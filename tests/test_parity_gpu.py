@@ -249,3 +249,23 @@ def test_transencoder_matches_reference():
     sub = {k: v[:5] for k, v in g.items() if not k.startswith("sd.") and k not in ("logits", "probs")}
     _, p5 = m(*args16(sub))
     assert np.abs(p5.cpu().numpy() - g["probs"][:5]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("only_close", [False, True])
+def test_aggr_in_kernel_windows_equal_materialised_windows(ckpt_aggr, golden_aggr, only_close):
+    """ccsm_forward_aggr_sites (the kernel gathers each site's neighbourhood) == ccsm_forward_aggr on the windows
+    call_mods_freq_bam.site_windows builds, including the reference's only_close flags."""
+    from ccsmeth_b200.models import AggrAttRNN
+    from ccsmeth_b200.call_mods_freq_bam import site_windows
+    m = AggrAttRNN(11, 1, 1, 0, 32, binsize=20, model_type="attbigru", device=0)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ckpt_aggr.items()})
+    m = m.cuda(0).eval()
+    rng = np.random.default_rng(3)
+    n = 3000
+    pos = (np.cumsum(rng.integers(1, 3, size=n)) * 2).astype(np.int64)
+    rows = rng.random((n, 20)).astype(np.float32)
+    h0 = torch.randn(2, n, 32)
+    off, win = site_windows(pos, rows, 11, only_close)
+    a = m(torch.from_numpy(off), torch.from_numpy(win), h0=h0).cpu().numpy()
+    b = m.forward_sites(pos, rows, h0=h0, only_close=only_close).cpu().numpy()
+    assert np.abs(a - b).max() <= 1e-6
