@@ -766,6 +766,361 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp16c8 GRU layer kernel with ON-CHIP operand conversion ("CV").
+//
+// The layer kernels are bound by the bytes each SM pulls in through its L2 port (~64 B/clk/SM: profiles/r02_bound.md), and
+// half of the fp16c8 correction operands are redundant on the wire: e4m3(a) and e4m3(W) are just roundings of the fp16
+// hi parts that are loaded anyway.  This kernel loads, per 32 K elements, only hi (fp16) and the scaled residuals
+// (alo8, Wlo8) -- 30 KB per stage instead of 40 KB -- and four converter warps produce a8 = e4m3(hi_a) and
+// W8 = e4m3(hi_W / S) in shared memory, right where the e4m3 MMAs expect them.  The fp16 MMAs of a stage issue as soon as
+// it lands; its two e4m3 MMAs issue one stage later, when the conversion is done, so the converters are off the
+// critical path.  Work item, TMEM plan, bias arming and the pipelined epilogue are those of tc_gru_layer_kernel with
+// (NSLOT 1, NBUF 2): one row tile per CTA, one direction per CTA, two accumulator buffers.
+//   warp 0 producer | warp 1 MMA issuer | 4 * EPIW epilogue warps | 4 converter warps
+// ------------------------------------------------------------------------------------------------
+template <int EPIW>
+struct CvCfg {
+  static constexpr int KS = 4;                          // 8-element K-slabs per stage = 32 K elements
+  static constexpr uint32_t B_PART = KS * G_SLAB;       // 12288: fp16 hi | [Wlo8 6144][W8 6144]
+  static constexpr uint32_t A_PART = KS * A_SLAB;       // 8192:  fp16 hi | [a8 4096][alo8 4096]
+  static constexpr uint32_t STAGE = 2 * (B_PART + A_PART);  // 40960
+  static constexpr int STAGES = 5;
+  static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
+  static constexpr int EPI_WARP0 = 2;
+  static constexpr int CV_WARP0 = 2 + 4 * EPIW;
+  static constexpr int THREADS = 32 * (CV_WARP0 + 4);
+};
+
+// 16 fp16 (two 16-byte slab rows) -> 16 e4m3 (one 16-byte row), optionally scaled by 2^-12 first (exact in fp16)
+template <bool SCALE>
+__device__ __forceinline__ uint4 cvt16_e4m3(const uint4& a, const uint4& b) {
+  const uint32_t in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t r[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      __half2 v = *reinterpret_cast<const __half2*>(&in[2 * i + h]);
+      if constexpr (SCALE) v = __hmul2(v, __float2half2_rn(C8_INV_S));
+      r[h] = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<__half2_raw*>(&v), __NV_SATFINITE, __NV_E4M3);
+    }
+    out[i] = r[0] | (r[1] << 16);
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+template <int EPIW>
+__global__ void __launch_bounds__(CvCfg<EPIW>::THREADS, 1) tc_gru_cv_kernel(const GruParams p) {
+  using C = CvCfg<EPIW>;
+  constexpr int S = C::STAGES, KS = C::KS, P = 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[3 * S + 5];
+  __shared__ uint32_t tmem_base_s;
+  float* bias_s = reinterpret_cast<float*>(smem + S * C::STAGE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), conv0 = smem_u32(&bars[2 * S]);
+  const uint32_t tmem_full = smem_u32(&bars[3 * S]), tmem_empty = smem_u32(&bars[3 * S + 2]),
+                 h_ready = smem_u32(&bars[3 * S + 4]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(conv0 + 8 * i, 4);  // one arrival per converter warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, EPIW * 128);
+    }
+    mbar_init(h_ready, EPIW * 128);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * 4 * 256; i += C::THREADS) bias_s[i] = p.bias[i];
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const int L = p.L;
+  const int n_items = p.n_tiles * 2;   // (row tile, direction); the grid is even, so a CTA keeps one direction
+  const int item0 = (int)blockIdx.x, item_step = (int)gridDim.x;
+  const size_t xbytes = (size_t)P * p.kx_slabs * G_SLAB, hbytes = (size_t)P * 32 * G_SLAB;
+  const size_t wj_bytes = xbytes + hbytes;
+  const bool x_short = p.kx_slabs < KS;  // layer 0: one 16-K stage in the 3-pass fp16 layout, nothing to convert
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t stage = 0, use = 0, gstep = 0;
+      for (int item = item0; item < n_items; item += item_step) {
+        const int64_t tile = item >> 1;
+        const int d = item & 1;
+        for (int s = 0; s < L; ++s, ++gstep) {
+          const int t = d ? (L - 1 - s) : s;
+          const int tprev = d ? t + 1 : t - 1;
+          for (int j = 0; j < 4; ++j) {
+            const uint8_t* wj = p.wimg + (size_t)(d * 4 + j) * wj_bytes;
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? p.kx_slabs : 32;
+              const uint8_t* wsrc = wj + (part ? xbytes : 0);
+              for (int so = 0; so < total; so += KS) {
+                const int ns = (total - so) < KS ? (total - so) : KS;
+                if (part == 1 && so == 0 && j == 0 && gstep > 0) {
+                  mbar_wait(h_ready, (gstep - 1) & 1);  // h_{t_prev} is in the act image
+                  fence_proxy_async_all();
+                }
+                mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+                const uint32_t fb = full0 + 8 * stage;
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                const uint8_t* asrc;
+                size_t part_stride;
+                if (part == 0) {
+                  if (x_short) {
+                    asrc = p.xin + ((tile * L + t) * P) * (2 * (size_t)A_SLAB);
+                    part_stride = 2 * A_SLAB;
+                  } else {
+                    asrc = p.xin + (((tile * L + t) * 8 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                    part_stride = CHUNK_BYTES;
+                  }
+                } else {
+                  if (s == 0)
+                    asrc = p.h0img + (((tile * 2 + d) * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                  else
+                    asrc = p.out + (((tile * L + tprev) * 8 + d * 4 + (so >> 3)) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+                  part_stride = CHUNK_BYTES;
+                }
+                if (ns == KS) {
+                  // hi parts whole; of the e4m3 parts only the scaled residuals: Wlo8 = first half of the weight group,
+                  // alo8 = second half of the activation group.  e4m3(W) / e4m3(a) are produced on chip.
+                  mbar_expect_tx(fb, C::B_PART + C::B_PART / 2 + C::A_PART + C::A_PART / 2);
+                  bulk_g2s(sb, wsrc + (size_t)so * G_SLAB, C::B_PART, fb);
+                  bulk_g2s(sb + C::B_PART, wsrc + ((size_t)total + so) * G_SLAB, C::B_PART / 2, fb);
+                  bulk_g2s(sb + 2 * C::B_PART, asrc, C::A_PART, fb);
+                  bulk_g2s(sb + 2 * C::B_PART + C::A_PART + C::A_PART / 2, asrc + part_stride + C::A_PART / 2, C::A_PART / 2, fb);
+                } else {
+                  mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + A_SLAB));
+#pragma unroll
+                  for (int pp = 0; pp < P; ++pp) {
+                    bulk_g2s(sb + pp * C::B_PART, wsrc + ((size_t)pp * total + so) * G_SLAB, ns * G_SLAB, fb);
+                    bulk_g2s(sb + 2 * C::B_PART + pp * C::A_PART, asrc + pp * part_stride, ns * A_SLAB, fb);
+                  }
+                }
+                if (++stage == S) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, 192, true);
+      constexpr uint32_t idesc8 = make_idesc_e4m3(128, 192);
+      uint32_t stage = 0, use = 0, chunk = 0;
+      // the stage whose e4m3 MMAs are still owed (issued once its conversion is done, one stage later)
+      bool owe = false;
+      uint32_t owe_stage = 0, owe_use = 0, owe_dcol = 0;
+      auto settle = [&]() {
+        if (!owe) return;
+        mbar_wait(conv0 + 8 * owe_stage, owe_use & 1);
+        tc_fence_after();
+        const uint32_t sb = smem_base + owe_stage * C::STAGE;
+        const uint32_t a1 = sb + 2 * C::B_PART + C::A_PART, b1 = sb + C::B_PART;
+        // a8 . Wlo8, then alo8 . W8 (K = 32 each)
+        umma_f8(owe_dcol, make_smem_desc(a1, A_SLAB, 128), make_smem_desc(b1, G_SLAB, 128), idesc8, 1u);
+        umma_f8(owe_dcol, make_smem_desc(a1 + 2 * A_SLAB, A_SLAB, 128), make_smem_desc(b1 + 2 * G_SLAB, G_SLAB, 128), idesc8, 1u);
+        umma_commit(empty0 + 8 * owe_stage);
+        owe = false;
+      };
+      for (int item = item0; item < n_items; item += item_step) {
+        for (int s = 0; s < L; ++s) {
+          for (int j = 0; j < 4; ++j, ++chunk) {
+            const uint32_t buf = chunk & 1, bphase = (chunk >> 1) & 1;
+            mbar_wait(tmem_empty + 8 * buf, bphase);
+            tc_fence_after();
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? p.kx_slabs : 32;
+              const uint32_t dcol = tmem + buf * 256 + (part == 0 ? 0 : 64);  // X -> (n_i, r, z); H -> (r, z, n_h)
+              for (int so = 0; so < total; so += KS) {
+                const int ns = (total - so) < KS ? (total - so) : KS;
+                mbar_wait(full0 + 8 * stage, use & 1);
+                tc_fence_after();
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                const uint32_t a0 = sb + 2 * C::B_PART, b0 = sb;
+                if (ns == KS) {
+#pragma unroll
+                  for (int q = 0; q < 2; ++q)
+                    umma_f16(dcol, make_smem_desc(a0 + q * 2 * A_SLAB, A_SLAB, 128),
+                             make_smem_desc(b0 + q * 2 * G_SLAB, G_SLAB, 128), idesc, 1u);
+                  settle();
+                  owe = true;
+                  owe_stage = stage;
+                  owe_use = use;
+                  owe_dcol = dcol;
+                } else {
+                  settle();
+                  for (int ks = 0; ks < ns / 2; ++ks) {
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                      const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                      umma_f16(dcol, make_smem_desc(a0 + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128),
+                               make_smem_desc(b0 + pb * C::B_PART + ks * 2 * G_SLAB, G_SLAB, 128), idesc, 1u);
+                    }
+                  }
+                  umma_commit(empty0 + 8 * stage);
+                }
+                if (++stage == S) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+            settle();
+            umma_commit(tmem_full + 8 * buf);  // accumulators of this unit-chunk complete
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= C::CV_WARP0) {
+    // ===================== converters: a8 = e4m3(a_hi), W8 = e4m3(W_hi / S) of every full stage =====================
+    const int ct = (warp - C::CV_WARP0) * 32 + lane;  // 0..127
+    uint32_t stage = 0, use = 0;
+    const int per_chunk_x = (p.kx_slabs + KS - 1) / KS;
+    for (int item = item0; item < n_items; item += item_step)
+      for (int c = 0; c < L * 4; ++c)
+        for (int st = 0; st < per_chunk_x + 8; ++st) {
+          const bool full_stage = !(x_short && st < per_chunk_x);
+          if (full_stage) mbar_wait(full0 + 8 * stage, use & 1);
+          if (full_stage && p.l2_hint != 7) {  // l2_hint == 7: timing experiment without the conversion (wrong results)
+            uint8_t* sb = smem + stage * C::STAGE;
+            // activations: 128 rows x 2 groups of 16 K elements
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int task = ct + q * 128, row = task & 127, k16 = task >> 7;
+              const uint8_t* src = sb + 2 * C::B_PART + (2 * k16) * A_SLAB + row * 16;
+              *reinterpret_cast<uint4*>(sb + 2 * C::B_PART + C::A_PART + k16 * A_SLAB + row * 16) =
+                  cvt16_e4m3<false>(*reinterpret_cast<const uint4*>(src), *reinterpret_cast<const uint4*>(src + A_SLAB));
+            }
+            // weights: 192 rows x 2 groups
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const int task = ct + q * 128, row = task % 192, k16 = task / 192;
+              const uint8_t* src = sb + (2 * k16) * G_SLAB + row * 16;
+              *reinterpret_cast<uint4*>(sb + C::B_PART + (2 + k16) * G_SLAB + row * 16) =
+                  cvt16_e4m3<true>(*reinterpret_cast<const uint4*>(src), *reinterpret_cast<const uint4*>(src + G_SLAB));
+            }
+            fence_proxy_async_smem();  // generic-proxy shared-memory writes -> visible to the MMA's operand reads
+          }
+          // every use of a stage completes one phase of its conv barrier (short stages too: the parity follows `use`)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(conv0 + 8 * stage);
+          if (++stage == S) {
+            stage = 0;
+            ++use;
+          }
+        }
+  } else {
+    // ===================== gate epilogue (pipelined, one thread per row and half-chunk) =====================
+    const int quad = warp & 3;  // tcgen05.ld lane rule: a warp touches TMEM lanes [32 * (warp % 4), +32)
+    const int ub0 = EPIW == 2 ? 2 * ((warp - C::EPI_WARP0) >> 2) : 0;  // first 16-unit block of this warp
+    constexpr int NUB = 4 / EPIW, NSB = 2 * NUB;
+    const int row = quad * 32 + lane;
+    const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t chunk = 0;
+    const float* bz = bias_s + (item0 & 1) * 4 * 256;
+    for (int b = 0; b < 2; ++b) {  // arm the first two unit-chunks (j = b)
+#pragma unroll
+      for (int k = 0; k < NUB; ++k) arm_bias16(trow0 + b * 256, ub0 + k, bz, b * 64 + (ub0 + k) * 16);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(tmem_empty + 8 * b);
+    }
+    for (int item = item0; item < n_items; item += item_step) {
+      const int64_t tile = item >> 1;
+      const int d = item & 1;
+      for (int s = 0; s < L; ++s) {
+        const int t = d ? (L - 1 - s) : s;
+        const int tprev = d ? t + 1 : t - 1;
+        for (int j = 0; j < 4; ++j, ++chunk) {
+          const uint8_t* hp_base = (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
+                                            : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint4 hph[NSB];
+          uint2 hpl[NSB];
+#pragma unroll
+          for (int q = 0; q < NSB; ++q) {
+            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (2 * ub0 + q) * A_SLAB + row * 16));
+            hpl[q] = __ldcg(reinterpret_cast<const uint2*>(hp_base + CHUNK_BYTES + 4096 + c8_off(2 * ub0 + q) + row * 16));
+          }
+          const uint32_t buf = chunk & 1, bphase = (chunk >> 1) & 1;
+          const uint32_t trow = trow0 + buf * 256;
+          mbar_wait(tmem_full + 8 * buf, bphase);
+          tc_fence_after();
+          uint32_t acc[2][4][8];
+          uint2 a8_even = make_uint2(0, 0), l8_even = make_uint2(0, 0);
+          const int c00 = ub0 * 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + c00, acc[0][g]);
+#pragma unroll
+          for (int sb = 0; sb < NSB; ++sb) {
+            const int col = c00 + sb * 8;
+            tmem_ld_wait();
+            if (sb + 1 < NSB) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(sb + 1) & 1][g]);
+            }
+            arm_bias8(trow, col, bz, ((j + 2) & 3) * 64 + col);
+            float hp[8], hn[8];
+            join8_c8(hph[sb], hpl[sb], hp);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float r = sigmoid_s(__uint_as_float(acc[sb & 1][1][i]));
+              const float z = sigmoid_s(__uint_as_float(acc[sb & 1][2][i]));
+              const float n = tanh_s(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
+              hn[i] = fmaf(z, hp[i] - n, n);
+            }
+            uint4 hi;
+            uint2 a8, l8;
+            split8_c8(hn, hi, a8, l8);
+            const int slab = col >> 3;
+            *reinterpret_cast<uint4*>(out_base + slab * A_SLAB + row * 16) = hi;
+            if ((sb & 1) == 0) {
+              a8_even = a8;
+              l8_even = l8;
+            } else {
+              // e4m3(h) is still stored for the kernels that load it (attention, the non-converting variants)
+              uint8_t* b8 = out_base + CHUNK_BYTES + c8_off(slab - 1) + row * 16;
+              *reinterpret_cast<uint4*>(b8) = make_uint4(a8_even.x, a8_even.y, a8.x, a8.y);
+              *reinterpret_cast<uint4*>(b8 + 4096) = make_uint4(l8_even.x, l8_even.y, l8.x, l8.y);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(tmem_empty + 8 * buf);
+          if (j == 3) {
+            fence_proxy_async_all();
+            mbar_arrive(h_ready);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-pair GRU layer kernel (tcgen05.mma.cta_group::2): a cluster of two CTAs (one TPC) runs M = 256:
 // CTA c owns row tile 2*pair + c (its 128 rows of A in its own shared memory, its 128 TMEM lanes) and
 // HALF of every weight tile (96 of the 192 gate rows), so each weight byte is fetched from L2 and read
@@ -1996,6 +2351,8 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
     case 14: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true>(gp, tiles, sm_count, st);  // 6 + pipelined epilogue
     case 15: return launch_gru<P, F16, 2, 1, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 1 + pipelined epilogue
     case 17: return launch_gru<P, F16, 1, 1, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 5 + pipelined epilogue
+    case 18: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // (fp16c8-only kernel: d here)
+    case 19: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true>(gp, tiles, sm_count, st);  // (fp16c8-only kernel: e here)
     default:
       set_error("unknown GRU kernel variant %d", variant);
       return CCSM_EINVAL;
@@ -2047,13 +2404,25 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
       static int hint = -1;
       if (hint < 0) {
         const char* e = getenv("CCSM_TC_L2HINT");
-        hint = (e && atoi(e) != 0) ? 1 : 0;
+        hint = e ? atoi(e) : 0;
       }
       gp.l2_hint = hint;
     }
     pid = m->prof.begin(l == 0 ? PROF_GRU_L0 : PROF_GRU_LN, (double)sites, st);
     const int variant = gru_variant(l, P);
-    if (variant == 16) {
+    if (C8 && (variant == 18 || variant == 19)) {
+      // fp16c8 with on-chip operand conversion (30 KB instead of 40 KB through the SM's L2 port per stage)
+      static bool cv_attr = false;
+      if (!cv_attr) {
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_cv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<1>::SMEM));
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_cv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CvCfg<2>::SMEM));
+        cv_attr = true;
+      }
+      const int64_t items = tiles * 2;
+      const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;
+      if (variant == 18) tc_gru_cv_kernel<1><<<grid, CvCfg<1>::THREADS, CvCfg<1>::SMEM, st>>>(gp);
+      else tc_gru_cv_kernel<2><<<grid, CvCfg<2>::THREADS, CvCfg<2>::SMEM, st>>>(gp);
+    } else if (variant == 16) {
       // duo kernel: CTA pairs, both directions interleaved; one cluster per TPC
       gp.wimg = T.wpair[l].as<uint8_t>();
       static bool duo_attr = false;
