@@ -374,16 +374,30 @@ struct GruCfg {
 //           footprint as one 16-unit block).  Aimed at layer 0, whose epilogue (128 KB of TMEM reads per chunk at
 //           64 B/cycle) is longer than its 17 MMAs.
 //   C8    = fp16 main pass + two e4m3 correction MMAs per 32 K elements (see the file header); P = 2 image sizes.
+//   Multi-warp producer (NSLOT == 1, no MC / HS): a stage's 2 P bulk copies are issued by 2 P threads in 2 P different warps
+//   (warp 0 = weights part 0 + expect_tx; 2 P - 1 extra warps at the end of the block = weights part 1, activation parts).
+//   ncu showed the single producer thread -- ~90 dependent address / uniform-datapath instructions per stage, ~660 cycles
+//   -- as what every precision mode was waiting for (the MMA thread spun on the `full` barriers while the ring's `empty`
+//   barriers were always already free); with one copy per thread and running pointers a stage costs each of them ~25
+//   instructions.
+template <int P, int NSLOT, bool MC, bool HS>
+struct GruProd {
+  static constexpr bool MP = NSLOT == 1 && !MC && !HS;
+  static constexpr int EXTRA_WARPS = MP ? 2 * P - 1 : 0;
+};
 template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false, bool PIPE = false, bool C8 = false>
-__global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS, GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::CTAS_PER_SM)
+__global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS + 32 * GruProd<P, NSLOT, MC, HS>::EXTRA_WARPS,
+                                  GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
   static_assert(!C8 || (P == 2 && F16 && PIPE && !HS && KSB == 8), "C8: fp16 images, 32 K elements per stage, pipelined epilogue");
   static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
   static_assert(!MC || NSLOT == 1, "multicast variant: one row tile per CTA");
   static_assert(!(MC && HS), "HS and MC are separate experiments");
   using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>;
+  using PR = GruProd<P, NSLOT, MC, HS>;
   constexpr int GRU_STAGES = C::STAGES;
-  constexpr int GRU_THREADS = C::THREADS;
+  constexpr int GRU_THREADS = C::THREADS + 32 * PR::EXTRA_WARPS;
+  constexpr int CORE_WARPS = C::THREADS / 32;  // producer role r > 0 runs in warp CORE_WARPS + r - 1
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -433,7 +447,69 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
   const size_t xbytes = (size_t)P * p.kx_slabs * G_SLAB, hbytes = (size_t)P * 32 * G_SLAB;
   const size_t wj_bytes = xbytes + hbytes;
 
-  if (warp == 0) {
+  if (PR::MP && (warp == 0 || warp >= CORE_WARPS)) {
+    // ===================== TMA producers: one bulk copy per stage and thread =====================
+    if (elect_one()) {
+      const int role = warp == 0 ? 0 : warp - CORE_WARPS + 1;  // [0, P): weight part; [P, 2 P): activation part
+      const bool is_b = role < P;
+      const int pp = is_b ? role : role - P;
+      const bool x_short = p.kx_slabs == 2;  // layer 0: one K = 16 stage, x0 image
+      uint32_t stage = 0, use = 0, gstep = 0;
+      for (int item = item0; item < n_items; item += item_step) {
+        const int64_t tile = item >> 1;
+        const int d = item & 1;
+        for (int s = 0; s < L; ++s, ++gstep) {
+          const int t = d ? (L - 1 - s) : s;
+          const int tprev = d ? t + 1 : t - 1;
+          // this thread's part of the step's activation operands
+          const uint8_t* xa = x_short ? p.xin + ((tile * L + t) * P + pp) * (2 * (size_t)A_SLAB)
+                                      : p.xin + (((tile * L + t) * 8) * P + pp) * (size_t)CHUNK_BYTES;
+          const uint8_t* ha = (s == 0 ? p.h0img + (((tile * 2 + d) * 4) * P + pp) * (size_t)CHUNK_BYTES
+                                      : p.out + (((tile * L + tprev) * 8 + d * 4) * P + pp) * (size_t)CHUNK_BYTES);
+          for (int j = 0; j < 4; ++j) {
+            const uint8_t* wj = p.wimg + (size_t)(d * 4 + j) * wj_bytes;
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? p.kx_slabs : 32;
+              // running source pointer of this thread's copy, and its bump per stage
+              const uint8_t* src;
+              size_t bump;
+              if (is_b) {
+                src = wj + (part ? xbytes : 0) + (size_t)pp * total * G_SLAB;
+                bump = (size_t)KS * G_SLAB;
+              } else {
+                src = part ? ha : xa;
+                bump = 0;  // activations: (so >> 3) chunks of P * CHUNK_BYTES, then slabs inside the chunk
+              }
+              for (int so = 0; so < total; so += KS) {
+                const int ns = (total - so) < KS ? (total - so) : KS;
+                if (!is_b && part == 1 && so == 0 && j == 0 && gstep > 0) {
+                  mbar_wait(h_ready, (gstep - 1) & 1);  // h_{t_prev} is in the act image
+                  fence_proxy_async_all();
+                }
+                mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+                const uint32_t fb = full0 + 8 * stage;
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                if (role == 0) mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + A_SLAB));
+                if (is_b) {
+                  bulk_g2s(sb + pp * C::B_PART, src, ns * G_SLAB, fb);
+                  src += bump;
+                } else {
+                  const uint8_t* a = (x_short && part == 0) ? src
+                                                            : src + (size_t)(so >> 3) * (P * CHUNK_BYTES) + (so & 7) * A_SLAB;
+                  bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb);
+                }
+                if (++stage == GRU_STAGES) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t stage = 0, use = 0;  // use = how many times the ring wrapped
@@ -2297,7 +2373,7 @@ static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStre
     const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * clusters));
-    cfg.blockDim = dim3(C::THREADS);
+    cfg.blockDim = dim3(C::THREADS + 32 * GruProd<P, NSLOT, MC, HS>::EXTRA_WARPS);
     cfg.dynamicSmemBytes = C::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -2312,7 +2388,7 @@ static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStre
   }
   const int64_t items = (tiles / NSLOT) * 2;  // groups of NSLOT row tiles x 2 directions
   const int grid = (int)(items < slots ? items : slots) & ~1;  // even: fixed direction per CTA
-  kern<<<grid, C::THREADS, C::SMEM, st>>>(gp);
+  kern<<<grid, C::THREADS + 32 * GruProd<P, NSLOT, MC, HS>::EXTRA_WARPS, C::SMEM, st>>>(gp);
   return CCSM_OK;
 }
 
