@@ -1076,8 +1076,8 @@ __global__ void __launch_bounds__(CvCfg<EPIW>::THREADS, 1) tc_gru_cv_kernel(cons
       for (int c = 0; c < L * 4; ++c)
         for (int st = 0; st < per_chunk_x + 8; ++st) {
           const bool full_stage = !(x_short && st < per_chunk_x);
-          if (full_stage) mbar_wait(full0 + 8 * stage, use & 1);
-          if (full_stage && p.l2_hint != 7) {  // l2_hint == 7: timing experiment without the conversion (wrong results)
+          if (full_stage) {
+            mbar_wait(full0 + 8 * stage, use & 1);
             uint8_t* sb = smem + stage * C::STAGE;
             // activations: 128 rows x 2 groups of 16 K elements
 #pragma unroll

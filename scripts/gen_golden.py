@@ -46,6 +46,26 @@ def run_ref(model, b, h0_f, h0_r):
     return logits.detach().numpy(), probs.detach().numpy()
 
 
+def gen_att2s_16k(n=16384, seed=synth.SEED + 16):
+    """A larger parity sample (SURVEY.md 8d asks for a 16k-site slice): the unmodified reference forward over
+    synth.make_batch(16384, seed) -- features and the explicit h0 are regenerated from the seed by the test (torch's CPU
+    generator is deterministic), so only the reference's outputs are stored (probs float32 + logits float16-safe range
+    as float32: 256 KB)."""
+    torch.set_num_threads(os.cpu_count())
+    m = refimport.load_ref_att2s()
+    b = synth.make_batch(n, seed=seed)
+    probs = np.empty((n, 2), np.float32)
+    logits = np.empty((n, 2), np.float32)
+    for s in range(0, n, 2048):   # the reference's forward has no chunking of its own; 2048-site calls bound the memory
+        sl = {k: (v[:, s:s + 2048] if k.startswith("h0") else v[s:s + 2048]) for k, v in b.items()}
+        lg, pr = run_ref(m, sl, sl["h0_f"].contiguous(), sl["h0_r"].contiguous())
+        logits[s:s + 2048], probs[s:s + 2048] = lg, pr
+    # a checksum of the regenerated inputs guards against a generator change going unnoticed
+    chk = float(sum(float(v.double().sum()) for v in b.values()))
+    np.savez_compressed(os.path.join(OUT, "att2s_synth16k.npz"), probs=probs, logits=logits, n=n, seed=seed, input_checksum=chk)
+    print("att2s_synth16k: prob1 mean %.4f, input checksum %.6f" % (probs[:, 1].mean(), chk))
+
+
 def gen_att2s():
     torch.set_num_threads(8)
     m = refimport.load_ref_att2s()
@@ -593,6 +613,9 @@ def gen_freqb():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "att2s_16k":
+        gen_att2s_16k()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "transenc":
         gen_transenc()
         sys.exit(0)

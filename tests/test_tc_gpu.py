@@ -119,3 +119,22 @@ def test_device_h0_same_noise_in_every_mode(model, golden_synth):
     _, pe = model(*a, h0=(z, z))
     assert np.abs(pz.cpu().numpy() - pe.cpu().numpy()).max() == 0.0
     model.set_h0_mode("reference")
+
+
+@pytest.mark.parametrize("prec", ["fp16c8", "fp16x3", "bf16x3", "fp32"])
+def test_parity_on_16k_reference_sites(model, prec):
+    """16,384 synthetic sites (regenerated from the seed) against the unmodified reference's outputs
+    (tests/golden/att2s_synth16k.npz, scripts/gen_golden.py att2s_16k): every parity mode within 1e-4 on every site."""
+    from ccsmeth_b200 import synth
+    from tests.conftest import load_npz
+    g = load_npz("att2s_synth16k.npz")
+    n = int(g["n"])
+    b = synth.make_batch(n, seed=int(g["seed"]))
+    chk = float(sum(float(v.double().sum()) for v in b.values()))
+    assert abs(chk - float(g["input_checksum"])) < 1e-6 * abs(chk), "the input generator changed: regenerate the fixture"
+    model.set_precision(prec)
+    _, probs = model(*[a.cuda() for a in synth.to_forward_args(b)], h0=(b["h0_f"], b["h0_r"]))
+    d = np.abs(probs.cpu().numpy() - g["probs"])
+    print("%s on %d sites: max|dprob| %.3e mean %.3e" % (prec, n, d.max(), d.mean()))
+    assert d.max() <= 1e-4
+    model.set_precision("fp16x3")
