@@ -11,11 +11,13 @@
 //       radius = sqrt(-2 * log256_ps(u1)), theta = float(2 pi) * u2, out[j] = radius * cos, out[j + 8] = radius * sin
 //     with the single-precision Cephes polynomials of avx_mathfun.h, whose multiply-adds the compiler contracted into
 //     FMAs (pattern pinned bit-for-bit against torch.randn by tests/test_h0_stream_gpu.py).
-// Here: mt_generate_kernel produces the tempered 32-bit outputs (one CTA: the twist is a sequential recurrence over
+// Here: mt_generate_kernel produces the 32-bit generator words (one CTA: the twist is a sequential recurrence over
 // 624-word blocks, 227-wide inside a block), mt_normal_kernel turns them into the (2*layers, n, hidden) fp32 tensors the
 // forward takes as explicit h0 -- same values, same order, nothing crosses PCIe.  All float arithmetic below is written
 // with round-to-nearest intrinsics so that nvcc neither contracts nor reassociates it.
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -37,42 +39,96 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-// state[0..623] = generator words, state[624] = position of the next output inside the block (624 = twist first).
-// Writes the next n tempered outputs to out and leaves the generator where the reference's would be.
-__global__ void __launch_bounds__(256, 1) mt_generate_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ out,
-                                                             long long n) {
-  __shared__ uint32_t s[2][MT_N];
+// state[0..623] = generator words (a twisted block), state[624] = position of the next output inside it (624 = the
+// block is used up).  Writes the next n tempered outputs to out and leaves the generator exactly where ATen's would be.
+//
+// The twist is the linear recurrence x[k] = x[k - 227] ^ T(k), T(k) = tw(x[k - 624], x[k - 623]), over the output
+// sequence: only 227 consecutive words are independent of each other.  Substituting the recurrence into itself twice,
+//     x[k] = x[k - 681] ^ T(k) ^ T(k - 227) ^ T(k - 454),
+// every operand lies at least 623 words back, so 623 consecutive words are independent: one block-wide barrier per 623
+// words (one word per thread, three tw() instead of one) instead of one per 227.  The first 454 words after the state
+// block are produced with the plain recurrence (two steps) to build the 1078 words of history the long form reads.
+constexpr int MT_LAG = MT_N - MT_M;  // 227
+constexpr int MT_WIDE = MT_N - 1;    // 623 words per step
+constexpr int MT_HIST = MT_N + 2 * MT_LAG;  // 1078 words of history a wide step reads
+constexpr int MT_BUF = 8192;         // linear window: slides back to the start every 11 steps, so addresses need no masking
+constexpr int MT_THREADS = 640;
+
+// Writes the UNTEMPERED words x[k]; the consumers temper on load (they run on every SM, this kernel on one).
+__global__ void __launch_bounds__(MT_THREADS, 1) mt_generate_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ out,
+                                                                    long long n) {
+  __shared__ uint32_t x[MT_BUF];
   const int tid = threadIdx.x;
-  for (int i = tid; i < MT_N; i += 256) s[0][i] = state[i];
-  int pos = (int)state[MT_N];
-  int cur = 0;
+  for (int i = tid; i < MT_N; i += MT_THREADS) x[i] = state[i];
+  const int pos = (int)state[MT_N];
   __syncthreads();
-  long long o = 0;
-  while (o < n) {
-    if (pos == MT_N) {
-      const uint32_t* a = s[cur];
-      uint32_t* b = s[cur ^ 1];
-      // new[i] = old[i + 397] ^ tw(old[i], old[i + 1]) for i < 227; later words use freshly generated ones
-      if (tid < MT_N - MT_M) b[tid] = a[tid + MT_M] ^ mt_tw(a[tid], a[tid + 1]);
+  if (n <= 0) return;
+  // outputs still owed by the current block
+  const long long head = (long long)(MT_N - pos) < n ? (MT_N - pos) : n;
+  for (int i = tid; i < head; i += MT_THREADS) out[i] = x[pos + i];
+  // stream index (from the start of the current block) one past the last output, and the block that holds that output
+  const long long p_end = pos + n;
+  const long long blk = (p_end - 1) / MT_N;          // >= 0
+  const long long k_stop = (blk + 1) * MT_N;         // generate x[624 .. k_stop)
+  long long kbase = 0;  // stream index of x[0]
+  if (blk > 0) {
+    // two plain steps: x[624 .. 1078)
+    for (int m = 0; m < 2; ++m) {
+      const int k = MT_N + m * MT_LAG + tid;
+      if (tid < MT_LAG) {
+        const uint32_t v = x[k - MT_LAG] ^ mt_tw(x[k - MT_N], x[k - MT_N + 1]);
+        x[k] = v;
+        const long long o = (long long)k - pos;
+        if (o < n) out[o] = v;
+      }
       __syncthreads();
-      if (tid < MT_N - MT_M) b[tid + 227] = b[tid] ^ mt_tw(a[tid + 227], a[tid + 228]);
-      __syncthreads();
-      if (tid < MT_N - 1 - 454) b[tid + 454] = b[tid + 227] ^ mt_tw(a[tid + 454], a[tid + 455]);
-      __syncthreads();
-      if (tid == 0) b[MT_N - 1] = b[MT_M - 1] ^ mt_tw(a[MT_N - 1], b[0]);
-      __syncthreads();
-      cur ^= 1;
-      pos = 0;
     }
-    const long long left = n - o;
-    const int k = left < (long long)(MT_N - pos) ? (int)left : MT_N - pos;
-    for (int i = tid; i < k; i += 256) out[o + i] = mt_temper(s[cur][pos + i]);
-    pos += k;
-    o += k;
+    // wide steps: stream words k0 + tid, k0 = 1078 + 623 q, at x[w + tid]
+    const long long k_first = MT_HIST;
+    const long long n_wide = k_stop > k_first ? (k_stop - k_first + MT_WIDE - 1) / MT_WIDE : 0;
+    const long long o_first = k_first - pos;
+    long long n_full = (n - o_first) / MT_WIDE;  // steps whose 623 words are all outputs: no bounds check inside
+    n_full = n_full < 0 ? 0 : (n_full > n_wide ? n_wide : n_full);
+    uint32_t* op = out + (o_first + tid);
+    const bool act = tid < MT_WIDE;
+    int w = MT_HIST;  // x[] index of the step's first word
+    auto wide = [&](const uint32_t* c) {  // c = &x[index of this thread's word]
+      return c[-3 * MT_LAG] ^ mt_tw(c[-MT_N], c[-MT_N + 1]) ^ mt_tw(c[-MT_N - MT_LAG], c[-MT_N - MT_LAG + 1]) ^
+             mt_tw(c[-MT_N - 2 * MT_LAG], c[-MT_N - 2 * MT_LAG + 1]);
+    };
+    for (long long q = 0; q < n_wide; ++q) {
+      if (w + MT_WIDE > MT_BUF) {
+        // slide the last 1078 words back to the start of the window
+        uint32_t keep[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) keep[i] = (tid + i * MT_THREADS < MT_HIST) ? x[w - MT_HIST + tid + i * MT_THREADS] : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (tid + i * MT_THREADS < MT_HIST) x[tid + i * MT_THREADS] = keep[i];
+        __syncthreads();
+        kbase += w - MT_HIST;
+        w = MT_HIST;
+      }
+      if (act) {
+        uint32_t* c = x + w + tid;
+        const uint32_t v = wide(c);
+        *c = v;
+        if (q < n_full || o_first + q * MT_WIDE + tid < n) *op = v;
+      }
+      w += MT_WIDE;
+      op += MT_WIDE;
+      __syncthreads();
+    }
   }
-  __syncthreads();
-  for (int i = tid; i < MT_N; i += 256) state[i] = s[cur][i];
-  if (tid == 0) state[MT_N] = (uint32_t)pos;
+  // the block holding the last output becomes the state; its position = how far into it the stream has advanced
+  const long long b0 = blk * MT_N;
+  for (int i = tid; i < MT_N; i += MT_THREADS) state[i] = x[(int)(b0 - kbase) + i];
+  if (tid == 0) state[MT_N] = (uint32_t)(p_end - b0);
+}
+
+static void mt_launch_generate(uint32_t* state, uint32_t* out, long long n, cudaStream_t st) {
+  mt_generate_kernel<<<1, MT_THREADS, 0, st>>>(state, out, n);
 }
 
 // ---- avx_mathfun.h log256_ps / sincos256_ps, one lane, with the FMA contractions of the shipped ATen binary
@@ -138,8 +194,9 @@ __device__ __forceinline__ void normal_pair(uint32_t a, uint32_t b, float& n_cos
   const float radius = __fsqrt_rn(__fmul_rn(-2.0f, avx_log(u1)));
   float s, c;
   avx_sincos(__fmul_rn(6.283185307179586f, u2), s, c);
-  n_cos = __fmul_rn(radius, c);
-  n_sin = __fmul_rn(radius, s);
+  // ATen finishes with fmadd(n, std = 1, mean = +0): exact, except that it turns a -0 (u1 == 1) into +0
+  n_cos = __fmaf_rn(__fmul_rn(radius, c), 1.0f, 0.0f);
+  n_sin = __fmaf_rn(__fmul_rn(radius, s), 1.0f, 0.0f);
 }
 
 // Plain stream: out[16 g + j] / out[16 g + 8 + j] for every group g of 16 words (debug / tests).
@@ -149,7 +206,7 @@ __global__ void mt_normal_flat_kernel(const uint32_t* __restrict__ words, float*
   const long long g = t >> 3;
   const int j = (int)(t & 7);
   float nc, ns;
-  normal_pair(words[g * 16 + j], words[g * 16 + 8 + j], nc, ns);
+  normal_pair(mt_temper(words[g * 16 + j]), mt_temper(words[g * 16 + 8 + j]), nc, ns);
   out[g * 16 + j] = nc;
   out[g * 16 + 8 + j] = ns;
 }
@@ -182,7 +239,7 @@ __global__ void mt_normal_h0_kernel(const uint32_t* __restrict__ words, const lo
   const long long site = s0 + rel / H;
   const int unit = (int)(rel % H);
   float nc, ns;
-  normal_pair(words[w + j], words[w + 8 + j], nc, ns);
+  normal_pair(mt_temper(words[w + j]), mt_temper(words[w + 8 + j]), nc, ns);
   float* dst = (strand ? h0b : h0a) + (ld * n + site) * H + unit;
   dst[j] = nc;
   dst[8 + j] = ns;
@@ -326,7 +383,7 @@ int mt_fill(ccsm_model* m, const int64_t* segs, int nseg, cudaStream_t user, con
   CCSM_TRY(S.segtab[b].reserve(tab.size() * 8));
   // pageable source: the call returns once the table sits in the driver's staging memory, so `tab` may die afterwards
   CCSM_CUDA(cudaMemcpyAsync(S.segtab[b].p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, S.st));
-  mt_generate_kernel<<<1, 256, 0, S.st>>>(S.state.as<uint32_t>(), S.words[b].as<uint32_t>(), w);
+  mt_launch_generate(S.state.as<uint32_t>(), S.words[b].as<uint32_t>(), w, S.st);
   float* a = S.h0[b].as<float>();
   float* bb = a + (size_t)LD * n * H;
   const long long pairs = w / 2;
@@ -384,11 +441,23 @@ extern "C" int ccsm_debug_torch_randn(int32_t device, uint64_t seed, int64_t ski
   CCSM_TRY(dw.reserve((size_t)(skip > n ? skip : n) * 4));
   CCSM_TRY(df.reserve((size_t)n * 4));
   CCSM_CUDA(cudaMemcpy(ds.p, st, sizeof(st), cudaMemcpyHostToDevice));
-  if (skip) mt_generate_kernel<<<1, 256>>>(ds.as<uint32_t>(), dw.as<uint32_t>(), skip);
-  mt_generate_kernel<<<1, 256>>>(ds.as<uint32_t>(), dw.as<uint32_t>(), n);
+  if (skip) mt_launch_generate(ds.as<uint32_t>(), dw.as<uint32_t>(), skip, nullptr);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  mt_launch_generate(ds.as<uint32_t>(), dw.as<uint32_t>(), n, nullptr);
+  cudaEventRecord(e1);
   mt_normal_flat_kernel<<<(unsigned)((n / 2 + 255) / 256), 256>>>(dw.as<uint32_t>(), df.as<float>(), n / 16);
   count_launch(3);
   cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && getenv("CCSM_MT_TIMING")) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[mt] %lld words in %.3f ms = %.2f G words/s\n", (long long)n, ms, n / (ms * 1e6));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   if (e == cudaSuccess) e = cudaMemcpy(out, df.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
   ds.release(); dw.release(); df.release();
   if (e != cudaSuccess) {
