@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
       const bool is_b = role < P;
       const int pp = is_b ? role : role - P;
       const bool x_short = p.kx_slabs == 2;  // layer 0: one K = 16 stage, x0 image
+      const uint64_t pol_last = make_policy_evict_last(), pol_first = make_policy_evict_first();
       uint32_t stage = 0, use = 0, gstep = 0;
       for (int item = item0; item < n_items; item += item_step) {
         const int64_t tile = item >> 1;
@@ -491,12 +492,18 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
                 const uint32_t sb = smem_base + stage * C::STAGE;
                 if (role == 0) mbar_expect_tx(fb, (uint32_t)(P * ns) * (G_SLAB + A_SLAB));
                 if (is_b) {
-                  bulk_g2s(sb + pp * C::B_PART, src, ns * G_SLAB, fb);
+                  // L2 policy experiments (CCSM_TC_L2HINT): 1, 2 = weights evict_last
+                  if (p.l2_hint == 1 || p.l2_hint == 2) bulk_g2s_hint(sb + pp * C::B_PART, src, ns * G_SLAB, fb, pol_last);
+                  else bulk_g2s(sb + pp * C::B_PART, src, ns * G_SLAB, fb);
                   src += bump;
                 } else {
                   const uint8_t* a = (x_short && part == 0) ? src
                                                             : src + (size_t)(so >> 3) * (P * CHUNK_BYTES) + (so & 7) * A_SLAB;
-                  bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb);
+                  // 1 = activations evict_last too; 3 = the last (fourth) read of x_t and every read of h_{t-1} evict_first
+                  if (p.l2_hint == 1) bulk_g2s_hint(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb, pol_last);
+                  else if (p.l2_hint == 3 && (j == 3 || part == 1))
+                    bulk_g2s_hint(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb, pol_first);
+                  else bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb);
                 }
                 if (++stage == GRU_STAGES) {
                   stage = 0;
