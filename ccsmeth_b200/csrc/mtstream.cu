@@ -19,9 +19,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <vector>
 
 #include "ccsm_internal.h"
+#include "mtjump.h"
 
 namespace ccsm {
 
@@ -54,14 +56,12 @@ constexpr int MT_HIST = MT_N + 2 * MT_LAG;  // 1078 words of history a wide step
 constexpr int MT_BUF = 8192;         // linear window: slides back to the start every 11 steps, so addresses need no masking
 constexpr int MT_THREADS = 640;
 
-// Writes the UNTEMPERED words x[k]; the consumers temper on load (they run on every SM, this kernel on one).
-__global__ void __launch_bounds__(MT_THREADS, 1) mt_generate_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ out,
-                                                                    long long n) {
-  __shared__ uint32_t x[MT_BUF];
+// Emits n UNTEMPERED words (the consumers temper on load: they run on every SM, the generator on one) starting at
+// position `pos` of the 624-word window in x[0..624), x = a shared-memory buffer of MT_BUF words.  A window whose first
+// word only carries its top bit -- a state vector, as a jump produces it -- is emitted with pos = 1.  If state_out is
+// given, the block holding the last output and the position inside it are stored there (ATen's representation).
+__device__ void mt_emit(uint32_t* x, int pos, long long n, uint32_t* __restrict__ out, uint32_t* __restrict__ state_out) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < MT_N; i += MT_THREADS) x[i] = state[i];
-  const int pos = (int)state[MT_N];
-  __syncthreads();
   if (n <= 0) return;
   // outputs still owed by the current block
   const long long head = (long long)(MT_N - pos) < n ? (MT_N - pos) : n;
@@ -121,14 +121,190 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mt_generate_kernel(uint32_t* __
       __syncthreads();
     }
   }
-  // the block holding the last output becomes the state; its position = how far into it the stream has advanced
-  const long long b0 = blk * MT_N;
-  for (int i = tid; i < MT_N; i += MT_THREADS) state[i] = x[(int)(b0 - kbase) + i];
-  if (tid == 0) state[MT_N] = (uint32_t)(p_end - b0);
+  if (state_out) {
+    // the block holding the last output becomes the state; its position = how far into it the stream has advanced
+    const long long b0 = blk * MT_N;
+    for (int i = tid; i < MT_N; i += MT_THREADS) state_out[i] = x[(int)(b0 - kbase) + i];
+    if (tid == 0) state_out[MT_N] = (uint32_t)(p_end - b0);
+  }
 }
 
-static void mt_launch_generate(uint32_t* state, uint32_t* out, long long n, cudaStream_t st) {
-  mt_generate_kernel<<<1, MT_THREADS, 0, st>>>(state, out, n);
+// state[0..623] = generator words (a twisted block), state[624] = position of the next output inside it (624 = the block
+// is used up).  Writes the next n generator words to out and leaves the generator exactly where ATen's would be.
+__global__ void __launch_bounds__(MT_THREADS, 1) mt_generate_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ out,
+                                                                    long long n) {
+  __shared__ uint32_t x[MT_BUF];
+  for (int i = threadIdx.x; i < MT_N; i += MT_THREADS) x[i] = state[i];
+  const int pos = (int)state[MT_N];
+  __syncthreads();
+  mt_emit(x, pos, n, out, state);
+}
+
+// ---- sub-streams by jump-ahead: the stream of one call cut into pieces of MT_J words, one CTA each.
+// The state J words ahead is a fixed GF(2)-linear function of the state: with g(x) = x^J mod phi(x) (phi = the
+// characteristic polynomial of the one-word transition, degree 19937; host code in mtjump.h), the state vector at word
+// b + J is the XOR, over the set bits i of g, of the state vectors at words b + i.  CTA c applies the polynomials of
+// J, 2 J, 4 J, ... selected by the bits of c: each jump lays out the next 19,937 + 623 words after its window in shared
+// memory and XORs about ten thousand shifted views of them.  A state vector is (top bit of x[b], x[b + 1 .. b + 623]),
+// so CTA c jumps from the word BEFORE the call's first output and emits from position 1 of the resulting window.
+constexpr int MT_JLOG = 21;
+constexpr long long MT_J = 1LL << MT_JLOG;   // words per sub-stream
+constexpr int MT_JMAXBITS = 7;               // up to 128 sub-streams per launch
+constexpr int MT_DEG = 19937;
+constexpr int MT_JLIST = 12288;              // capacity of a polynomial's set-bit list (about 10,000 of 19,937 bits are set)
+constexpr int MT_SEQ = 2 * MT_N + MT_DEG + MT_WIDE + 32;  // words a jump lays out: window offset < 624, + 19,937 + window
+
+__global__ void __launch_bounds__(MT_THREADS, 1) mt_generate_multi_kernel(const uint32_t* __restrict__ state,
+                                                                          uint32_t* __restrict__ out, long long n,
+                                                                          const uint16_t* __restrict__ jlist,
+                                                                          const int* __restrict__ jcount) {
+  extern __shared__ uint32_t sm[];  // MT_SEQ words (>= MT_BUF)
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x;
+  for (int i = tid; i < MT_N; i += MT_THREADS) sm[i] = state[i];
+  int pos = (int)state[MT_N];
+  __syncthreads();
+  if (c > 0) {
+    int b = pos - 1;  // the window (state vector) starts at sm[b]
+    for (int k = 0; k < MT_JMAXBITS; ++k) {
+      if (!((c >> k) & 1)) continue;
+      // lay out sm[624 + ..] up to b + 624 + 19,937: every word from index 624 on follows from the 624 before it
+      const int stop = b + MT_N + MT_DEG;
+      for (int k0 = MT_N; k0 < stop; k0 += MT_LAG) {   // plain 227-wide steps (20 k words: a few tens of microseconds)
+        const int kk = k0 + tid;
+        if (tid < MT_LAG && kk < stop) sm[kk] = sm[kk - MT_LAG] ^ mt_tw(sm[kk - MT_N], sm[kk - MT_N + 1]);
+        __syncthreads();
+      }
+      uint32_t acc = 0;
+      if (tid < MT_N) {
+        const uint16_t* lst = jlist + (size_t)k * MT_JLIST;
+        const int cnt = jcount[k];
+        const uint32_t* base = sm + b + tid;
+        for (int i = 0; i < cnt; ++i) acc ^= base[lst[i]];
+      }
+      __syncthreads();
+      if (tid < MT_N) sm[tid] = acc;   // the jumped state vector; only the top bit of its first word is meaningful
+      __syncthreads();
+      b = 0;
+    }
+    pos = 1;
+    if (b != 0) {  // (c > 0 always jumps at least once, so b == 0 here; kept for clarity)
+      return;
+    }
+  }
+  const long long first = (long long)c * MT_J;
+  const long long len = (n - first) < MT_J ? (n - first) : MT_J;
+  mt_emit(sm, pos, len, out + first, nullptr);
+}
+
+// After the sub-streams: the generator state ATen would hold, from the last 624 words written (n >= 624).
+__global__ void __launch_bounds__(256, 1) mt_finalize_kernel(uint32_t* __restrict__ state, const uint32_t* __restrict__ out,
+                                                             long long n) {
+  __shared__ uint32_t x[2 * MT_N];
+  const int tid = threadIdx.x;
+  const long long e = (long long)state[MT_N] + n - 1;   // index of the last output, counted from the old block's start
+  const long long blk = e / MT_N;
+  const int have = (int)(e - blk * MT_N) + 1;           // words of block `blk` that were output: its first `have` words
+  // x[0..624) = the 624 words ending at the last output (index e - 623 .. e)
+  for (int i = tid; i < MT_N; i += 256) x[i] = out[n - MT_N + i];
+  __syncthreads();
+  // the rest of the block: words e + 1 .. (blk + 1) * 624 - 1 at x[624 ..]
+  const int more = MT_N - have;
+  for (int k0 = 0; k0 < more; k0 += MT_LAG) {
+    const int kk = MT_N + k0 + tid;
+    if (tid < MT_LAG && k0 + tid < more) x[kk] = x[kk - MT_LAG] ^ mt_tw(x[kk - MT_N], x[kk - MT_N + 1]);
+    __syncthreads();
+  }
+  // block word i sits at x[624 - have + i]
+  for (int i = tid; i < MT_N; i += 256) state[i] = x[MT_N - have + i];
+  if (tid == 0) state[MT_N] = (uint32_t)have;
+}
+
+// Jump polynomials x^(2^k J) mod phi, k < MT_JMAXBITS, as lists of set-bit indices; computed once per process
+// (Berlekamp-Massey + a few polynomial squarings, ~0.1 s) and uploaded once per device.
+struct MtJumpTables {
+  std::vector<uint16_t> lists;  // [MT_JMAXBITS][MT_JLIST]
+  std::vector<int> counts;
+  bool ok = false;
+};
+static const MtJumpTables& mt_jump_tables() {
+  static MtJumpTables T;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    mtjump::Field F = mtjump::make_field();
+    int deg = -1;
+    for (int i = (int)F.phi.size() * 64 - 1; i >= 0 && deg < 0; --i)
+      if (mtjump::get(F.phi, i)) deg = i;
+    if (deg != MT_DEG) return;  // never expected; the callers fall back to the one-CTA generator
+    T.lists.assign((size_t)MT_JMAXBITS * MT_JLIST, 0);
+    T.counts.assign(MT_JMAXBITS, 0);
+    mtjump::Poly g = F.xpow((uint64_t)MT_J);
+    for (int k = 0; k < MT_JMAXBITS; ++k) {
+      int c = 0;
+      for (int i = 0; i < MT_DEG; ++i)
+        if (mtjump::get(g, i)) {
+          if (c >= MT_JLIST) return;
+          T.lists[(size_t)k * MT_JLIST + c++] = (uint16_t)i;
+        }
+      T.counts[k] = c;
+      if (k + 1 < MT_JMAXBITS) g = F.mulmod(g, g);
+    }
+    T.ok = true;
+  });
+  return T;
+}
+struct MtJumpDev {
+  DevBuf lists, counts;
+  bool ready = false, failed = false;
+};
+static MtJumpDev* mt_jump_dev() {
+  static MtJumpDev dev[64];
+  static std::mutex mu;
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  MtJumpDev& D = dev[d];
+  if (D.failed) return nullptr;
+  if (!D.ready) {
+    const MtJumpTables& T = mt_jump_tables();
+    if (!T.ok || D.lists.reserve(T.lists.size() * 2) != CCSM_OK || D.counts.reserve(T.counts.size() * 4) != CCSM_OK ||
+        cudaMemcpy(D.lists.p, T.lists.data(), T.lists.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(D.counts.p, T.counts.data(), T.counts.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaFuncSetAttribute(mt_generate_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SEQ * 4) != cudaSuccess) {
+      D.failed = true;
+      return nullptr;
+    }
+    D.ready = true;
+  }
+  return &D;
+}
+
+// Advances the generator by n words into out.  Short draws run on one CTA; from two sub-streams' worth on, the draw is
+// cut into sub-streams of MT_J words generated in parallel (up to 128 per launch), followed by the state update.
+// pos_may_be_zero: the state was just set by the caller with position 0 (a state vector needs the word before the first
+// output, which such a block does not hold): one-CTA path.
+static void mt_launch_generate(uint32_t* state, uint32_t* out, long long n, cudaStream_t st, bool pos_may_be_zero = false) {
+  static int force_serial = -1;
+  if (force_serial < 0) {
+    const char* e = getenv("CCSM_MT_SERIAL");
+    force_serial = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  MtJumpDev* J = (n >= 2 * MT_J && !pos_may_be_zero && !force_serial) ? mt_jump_dev() : nullptr;
+  if (!J) {
+    mt_generate_kernel<<<1, MT_THREADS, 0, st>>>(state, out, n);
+    return;
+  }
+  const long long per_launch = MT_J << MT_JMAXBITS;
+  for (long long o = 0; o < n; o += per_launch) {
+    const long long m = (n - o) < per_launch ? (n - o) : per_launch;
+    if (m < MT_N) {  // (cannot happen for the sizes that reach this path; the state update needs 624 written words)
+      mt_generate_kernel<<<1, MT_THREADS, 0, st>>>(state, out + o, m);
+      continue;
+    }
+    const int ctas = (int)((m + MT_J - 1) / MT_J);
+    mt_generate_multi_kernel<<<ctas, MT_THREADS, MT_SEQ * 4, st>>>(state, out + o, m, J->lists.as<uint16_t>(), J->counts.as<int>());
+    mt_finalize_kernel<<<1, 256, 0, st>>>(state, out + o, m);
+  }
 }
 
 // ---- avx_mathfun.h log256_ps / sincos256_ps, one lane, with the FMA contractions of the shipped ATen binary
@@ -248,6 +424,7 @@ __global__ void mt_normal_h0_kernel(const uint32_t* __restrict__ words, const lo
 struct MtStream {
   DevBuf state;   // 624 words + position
   bool seeded = false;
+  bool pos_zero = false;   // the state was set with position 0 and nothing has been drawn since
   uint64_t seed = 0;
   int batch = 512;                 // the reference's --batch_size: sites per model call
   std::vector<int64_t> pending;    // hole-batch site counts announced for the next forward call
@@ -282,6 +459,7 @@ int mt_seed(ccsm_model* m, uint64_t seed) {
   CCSM_CUDA(cudaStreamSynchronize(S.st));
   CCSM_CUDA(cudaMemcpy(S.state.p, st, sizeof(st), cudaMemcpyHostToDevice));
   S.seeded = true;
+  S.pos_zero = false;
   S.seed = seed;
   S.pending.clear();
   return CCSM_OK;
@@ -301,6 +479,7 @@ int mt_set_state(ccsm_model* m, const uint32_t* words, int32_t pos) {
   CCSM_CUDA(cudaStreamSynchronize(S.st));
   CCSM_CUDA(cudaMemcpy(S.state.p, st, sizeof(st), cudaMemcpyHostToDevice));
   S.seeded = true;
+  S.pos_zero = pos == 0;
   return CCSM_OK;
 }
 
@@ -383,7 +562,8 @@ int mt_fill(ccsm_model* m, const int64_t* segs, int nseg, cudaStream_t user, con
   CCSM_TRY(S.segtab[b].reserve(tab.size() * 8));
   // pageable source: the call returns once the table sits in the driver's staging memory, so `tab` may die afterwards
   CCSM_CUDA(cudaMemcpyAsync(S.segtab[b].p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, S.st));
-  mt_launch_generate(S.state.as<uint32_t>(), S.words[b].as<uint32_t>(), w, S.st);
+  mt_launch_generate(S.state.as<uint32_t>(), S.words[b].as<uint32_t>(), w, S.st, S.pos_zero);
+  if (w > 0) S.pos_zero = false;
   float* a = S.h0[b].as<float>();
   float* bb = a + (size_t)LD * n * H;
   const long long pairs = w / 2;

@@ -8,7 +8,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("seed,skip,n", [(1234, 0, 1 << 20), (0, 160, 4096), (20261017, 624 * 16, 6 * 37 * 256)])
+@pytest.mark.parametrize("seed,skip,n", [(1234, 0, 1 << 20), (0, 160, 4096), (20261017, 624 * 16, 6 * 37 * 256),
+                                         # long draws are cut into 2^21-word sub-streams by polynomial jump-ahead
+                                         (7, 160, 1 << 26), (3, 624 * 16 * 3 + 16, (1 << 22) + 16 * 37),
+                                         (11, 0, (1 << 22) + (1 << 21))])
 def test_device_randn_is_bit_identical_to_torch(seed, skip, n):
     """MT19937 outputs -> 24-bit uniforms -> ATen's 16-wide Box-Muller with its log / sincos polynomials: every float
     equals torch.randn's on this host, bit for bit."""
