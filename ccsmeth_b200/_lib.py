@@ -33,7 +33,7 @@ EXPORTS = ["ccsm_abi_version", "ccsm_last_error", "ccsm_kernel_launches", "ccsm_
            "ccsm_forward_att2s_host", "ccsm_forward_att2s_lstm", "ccsm_forward_aggr", "ccsm_forward_aggr_lstm", "ccsm_debug_last_rnn_out", "ccsm_debug_umma_gemm",
            "ccsm_debug_tc_layer_out", "ccsm_profile_enable", "ccsm_profile_read", "ccsm_set_h0_mode",
            "ccsm_debug_umma_pair_gemm", "ccsm_debug_umma_mixed_gemm", "ccsm_debug_umma_rate", "ccsm_debug_torch_randn", "ccsm_set_h0_batching",
-           "ccsm_h0_stream_set_state", "ccsm_h0_stream_get_state", "ccsm_bam_scan_records", "ccsm_forward_aggr_sites", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
+           "ccsm_h0_stream_set_state", "ccsm_h0_stream_get_state", "ccsm_bam_scan_records", "ccsm_forward_aggr_sites", "ccsm_debug_mt_jump_check", "ccsm_reads_extract_host", "ccsm_reads_sites", "ccsm_reads_features",
            "ccsm_reads_forward_host", "ccsm_bgzf_inflated_size", "ccsm_bgzf_inflate", "ccsm_bgzf_inflate_stats", "ccsm_bgzf_deflate_bound",
            "ccsm_bgzf_deflate", "ccsm_bam_index", "ccsm_bam_tag_records", "ccsm_bam_modcalls", "ccsm_pileup_luts",
            "ccsm_pileup_begin_host", "ccsm_pileup_finish_host", "ccsm_pileup_finish_lstm_host"]
@@ -200,6 +200,8 @@ def load():
         lib.ccsm_bam_scan_records.restype = ctypes.c_int64
         lib.ccsm_forward_aggr_sites.argtypes = [vp, i64, vp, vp, i32, vp, vp, vp]
         lib.ccsm_forward_aggr_sites.restype = ctypes.c_int
+        lib.ccsm_debug_mt_jump_check.argtypes = [ctypes.c_uint32, i32]
+        lib.ccsm_debug_mt_jump_check.restype = ctypes.c_int
         lib.ccsm_set_h0_mode.argtypes = [vp, i32, ctypes.c_uint64]
         lib.ccsm_set_h0_mode.restype = ctypes.c_int
         lib.ccsm_profile_enable.argtypes = [vp, i32]

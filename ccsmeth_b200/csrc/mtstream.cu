@@ -646,3 +646,32 @@ extern "C" int ccsm_debug_torch_randn(int32_t device, uint64_t seed, int64_t ski
   }
   return CCSM_OK;
 }
+
+// Host-only self-check of the jump polynomials: the state vector J_k = 2^k J words ahead of word b, computed as the XOR
+// of the state vectors i words ahead over the set bits i of x^(J_k) mod phi, against plain generation.  Returns the number
+// of mismatching words (0 = pass), or a negative error code.  No GPU needed.
+extern "C" int ccsm_debug_mt_jump_check(uint32_t seed, int32_t k) {
+  if (k < 0 || k >= MT_JMAXBITS) {
+    set_error("ccsm_debug_mt_jump_check: k outside [0, %d)", MT_JMAXBITS);
+    return CCSM_EINVAL;
+  }
+  const MtJumpTables& T = mt_jump_tables();
+  if (!T.ok) {
+    set_error("ccsm_debug_mt_jump_check: the characteristic polynomial did not come out with degree 19937");
+    return CCSM_ESTATE;
+  }
+  const long long J = MT_J << k;
+  mtjump::MT g(seed);
+  std::vector<uint32_t> x((size_t)J + MT_DEG + 2 * MT_N);
+  for (auto& v : x) v = g.next();
+  const int b = 17;
+  int bad = 0;
+  const uint16_t* lst = T.lists.data() + (size_t)k * MT_JLIST;
+  for (int j = 0; j < MT_N; ++j) {
+    uint32_t acc = 0;
+    for (int i = 0; i < T.counts[k]; ++i) acc ^= x[(size_t)b + lst[i] + j];
+    const uint32_t want = x[(size_t)b + J + j];
+    if (j == 0 ? ((acc ^ want) & 0x80000000u) != 0 : acc != want) ++bad;
+  }
+  return bad;
+}

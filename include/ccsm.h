@@ -450,6 +450,10 @@ int  ccsm_debug_umma_rate(int32_t device, int32_t N, int32_t mode, int32_t iters
 /* torch.manual_seed(seed); torch.randn(skip); torch.randn(n) reproduced on the device -> out (host, n floats; skip and
  * n multiples of 16).  tests/test_h0_stream_gpu.py compares it with torch bit for bit. */
 int  ccsm_debug_torch_randn(int32_t device, uint64_t seed, int64_t skip, int64_t n, float* out);
+/* Host-only self-check of the MT19937 jump-ahead polynomials the sub-stream generator uses (csrc/mtjump.h): the state
+ * 2^k * 2^21 words ahead obtained through x^(2^k 2^21) mod phi against plain generation from `seed`.  Returns the number of
+ * mismatching state words (0 = pass) or a negative CCSM_E* code.  No GPU needed. */
+int  ccsm_debug_mt_jump_check(uint32_t seed, int32_t k);
 
 #ifdef __cplusplus
 }
