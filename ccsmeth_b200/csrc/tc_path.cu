@@ -108,6 +108,17 @@ __device__ __forceinline__ float sigmoid_s(float x) { return __fdividef(1.f, 1.f
 __device__ __forceinline__ float tanh_s(float x) {
   return fmaf(2.f, __fdividef(1.f, 1.f + ex2_(x * (-2.8853900817779268f * C8_INV_S))), -1.f);
 }
+// C8: both gate sigmoids of a unit with ONE reciprocal: r = (1 + eb) / ((1 + ea)(1 + eb)), z = (1 + ea) / (...): 3 MUFU
+// instead of 4 (the gate epilogue of layer 0 sits on the MUFU pipe).  Pre-activations are clamped at -40 so that the
+// product stays finite (sigmoid(-40) = 4e-18).
+__device__ __forceinline__ void sigmoid2_s(float a, float b, float& r, float& z) {
+  const float lo = -40.f * C8_S;
+  const float pa = 1.f + ex2_(fmaxf(a, lo) * (-1.4426950408889634f * C8_INV_S));
+  const float pb = 1.f + ex2_(fmaxf(b, lo) * (-1.4426950408889634f * C8_INV_S));
+  const float inv = __fdividef(1.f, pa * pb);
+  r = inv * pb;
+  z = inv * pa;
+}
 template <bool FAST, bool C8>
 __device__ __forceinline__ float sig_(float x) {
   if constexpr (C8) return sigmoid_s(x);
@@ -385,7 +396,15 @@ struct GruProd {
   static constexpr bool MP = NSLOT == 1 && !MC && !HS;
   static constexpr int EXTRA_WARPS = MP ? 2 * P - 1 : 0;
 };
-template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false, bool PIPE = false, bool C8 = false>
+// IL: chunk order of one step of an interleaved item: F0 F1 R0 R1 F2 F3 R2 R3 (F = forward recurrence, R = reverse; digit
+// = 64-unit block j).  After a recurrence's last chunk of a step (j = 3) the other one issues two chunks of MMAs before
+// its next step starts -- that is the time the gate epilogue of j = 3 plus the h_t round trip (act image -> fence -> bulk
+// copy) needs, which in layer 0 (K_in = 16: no input-projection MMAs to fill it) was a bubble of a third of every step.
+__host__ __device__ constexpr int il_d(int jj) { return (jj >> 1) & 1; }
+__host__ __device__ constexpr int il_j(int jj) { return (jj >> 2) * 2 + (jj & 1); }
+
+template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW, bool MC, bool HS = false, bool PIPE = false, bool C8 = false,
+          bool IL = false>
 __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS + 32 * GruProd<P, NSLOT, MC, HS>::EXTRA_WARPS,
                                   GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::CTAS_PER_SM)
     tc_gru_layer_kernel(const GruParams p) {
@@ -393,6 +412,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
   static_assert(NSLOT * NBUF <= 2, "TMEM holds 512 columns");
   static_assert(!MC || NSLOT == 1, "multicast variant: one row tile per CTA");
   static_assert(!(MC && HS), "HS and MC are separate experiments");
+  static_assert(!IL || (NSLOT == 1 && NBUF == 2 && !MC && !HS && PIPE), "IL: one row tile per CTA, TMEM double-buffered");
   using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>;
   using PR = GruProd<P, NSLOT, MC, HS>;
   constexpr int GRU_STAGES = C::STAGES;
@@ -401,7 +421,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * GRU_STAGES + 5];
+  __shared__ __align__(8) uint64_t bars[2 * GRU_STAGES + 6];
   __shared__ uint32_t tmem_base_s;
   float* bias_s = reinterpret_cast<float*>(smem + GRU_STAGES * C::STAGE);
   // HS: two h_t buffers [kc 0..3][8 slabs x 2048 B] right after the biases (1024-byte aligned: STAGE and 8 KB are)
@@ -423,6 +443,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
       mbar_init(tmem_empty + 8 * i, NSLOT * EPIW * 128);
     }
     mbar_init(h_ready, NSLOT * EPIW * 128);
+    mbar_init(h_ready + 8, NSLOT * EPIW * 128);  // IL: the reverse recurrence's steps
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * 4 * 256; i += GRU_THREADS) bias_s[i] = p.bias[i];
@@ -440,7 +461,9 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
   // work items = (group of row tiles, direction).  Plain: one item per CTA at a time, NSLOT tiles each.
   // MC: one item per CLUSTER at a time = two neighbouring row tiles, one per CTA (rank), same direction.
   const uint32_t crank = MC ? cluster_ctarank() : 0;
-  const int n_items = MC ? (p.n_tiles / 2) * 2 : (p.n_tiles / NSLOT) * 2;
+  // IL: one item = one row tile, BOTH directions, as two recurrences interleaved chunk by chunk (see IL_D / IL_J).
+  const int n_items = IL ? p.n_tiles : MC ? (p.n_tiles / 2) * 2 : (p.n_tiles / NSLOT) * 2;
+  constexpr int NCH = IL ? 8 : 4;  // unit-chunks per step of an item
   const int item0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int TILES_PER_ITEM = MC ? 2 : NSLOT;
@@ -457,17 +480,18 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
       const uint64_t pol_last = make_policy_evict_last(), pol_first = make_policy_evict_first();
       uint32_t stage = 0, use = 0, gstep = 0;
       for (int item = item0; item < n_items; item += item_step) {
-        const int64_t tile = item >> 1;
-        const int d = item & 1;
+        const int64_t tile = IL ? item : item >> 1;
         for (int s = 0; s < L; ++s, ++gstep) {
-          const int t = d ? (L - 1 - s) : s;
-          const int tprev = d ? t + 1 : t - 1;
-          // this thread's part of the step's activation operands
-          const uint8_t* xa = x_short ? p.xin + ((tile * L + t) * P + pp) * (2 * (size_t)A_SLAB)
-                                      : p.xin + (((tile * L + t) * 8) * P + pp) * (size_t)CHUNK_BYTES;
-          const uint8_t* ha = (s == 0 ? p.h0img + (((tile * 2 + d) * 4) * P + pp) * (size_t)CHUNK_BYTES
-                                      : p.out + (((tile * L + tprev) * 8 + d * 4) * P + pp) * (size_t)CHUNK_BYTES);
-          for (int j = 0; j < 4; ++j) {
+          for (int jj = 0; jj < NCH; ++jj) {
+            const int d = IL ? il_d(jj) : (item & 1);
+            const int j = IL ? il_j(jj) : jj;
+            const int t = d ? (L - 1 - s) : s;
+            const int tprev = d ? t + 1 : t - 1;
+            // this thread's part of the step's activation operands
+            const uint8_t* xa = x_short ? p.xin + ((tile * L + t) * P + pp) * (2 * (size_t)A_SLAB)
+                                        : p.xin + (((tile * L + t) * 8) * P + pp) * (size_t)CHUNK_BYTES;
+            const uint8_t* ha = (s == 0 ? p.h0img + (((tile * 2 + d) * 4) * P + pp) * (size_t)CHUNK_BYTES
+                                        : p.out + (((tile * L + tprev) * 8 + d * 4) * P + pp) * (size_t)CHUNK_BYTES);
             const uint8_t* wj = p.wimg + (size_t)(d * 4 + j) * wj_bytes;
             for (int part = 0; part < 2; ++part) {
               const int total = part == 0 ? p.kx_slabs : 32;
@@ -484,7 +508,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
               for (int so = 0; so < total; so += KS) {
                 const int ns = (total - so) < KS ? (total - so) : KS;
                 if (!is_b && part == 1 && so == 0 && j == 0 && gstep > 0) {
-                  mbar_wait(h_ready, (gstep - 1) & 1);  // h_{t_prev} is in the act image
+                  mbar_wait(h_ready + (IL ? 8 * d : 0), (gstep - 1) & 1);  // h_{t_prev} is in the act image
                   fence_proxy_async_all();
                 }
                 mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
@@ -609,7 +633,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
       uint32_t hcount = 0;  // HS: completions of h_ready consumed so far (one per step: item start, then every step)
       for (int item = item0; item < n_items; item += item_step) {
         for (int s = 0; s < L; ++s, ++hcount) {
-          for (int j = 0; j < 4; ++j, ++chunk) {
+          for (int j = 0; j < NCH; ++j, ++chunk) {
             const uint32_t buf = chunk % NBUF, bphase = (chunk / NBUF) & 1;
             // completion #u of tmem_empty[buf]: #0 = initial bias arming, #k = drain + re-arm after use k-1
             mbar_wait(tmem_empty + 8 * buf, bphase);
@@ -674,27 +698,29 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
   } else if (warp >= C::EPI_WARP0) {
     // ===================== gate epilogue =====================
     // tcgen05.ld lane rule: a warp may only touch TMEM lanes [32 * (warp % 4), +32)
-    const int slot = EPIW == 2 ? 0 : (warp - C::EPI_WARP0) >> 2, quad = warp & 3;
-    const int ub0 = EPIW == 2 ? 2 * ((warp - C::EPI_WARP0) >> 2) : 0;  // first 16-unit block of this warp
-    constexpr int NUB = 4 / EPIW;                                       // blocks per warp
+    constexpr int NUB = 4 / EPIW;                                       // 16-unit blocks per warp
+    const int slot = EPIW >= 2 ? 0 : (warp - C::EPI_WARP0) >> 2, quad = warp & 3;
+    const int ub0 = EPIW >= 2 ? NUB * ((warp - C::EPI_WARP0) >> 2) : 0;  // first 16-unit block of this warp
     const int row = quad * 32 + lane;
     const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
     uint32_t chunk = 0;
     // gridDim.x is even (host), so every item of this CTA has the same direction: the biases to arm are fixed
-    const float* bz = bias_s + (item0 & 1) * 4 * 256;
+    // (IL: the direction changes from chunk to chunk; the first two chunks are the forward recurrence's.)
+    const float* bz0 = bias_s + (IL ? 0 : (item0 & 1)) * 4 * 256;
     for (int b = 0; b < NBUF; ++b) {  // arm the first NBUF unit-chunks (j = b)
 #pragma unroll
       for (int k = 0; k < NUB; ++k)
-        arm_bias16(trow0 + (NBUF == 2 ? b * 256 : 0), ub0 + k, bz, b * 64 + (ub0 + k) * 16);
+        arm_bias16(trow0 + (NBUF == 2 ? b * 256 : 0), ub0 + k, bz0, b * 64 + (ub0 + k) * 16);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(tmem_empty + 8 * b);
     }
     uint32_t hcnt = 0;  // HS: steps started so far (selects the h buffer: read (hcnt & 1), write the other one)
     for (int item = item0; item < n_items; item += item_step) {
-      const int pair = item >> 1, d = item & 1;
-      const int64_t tile = TILES_PER_ITEM * (int64_t)pair + crank + slot;
+      const int pair = item >> 1, d_item = item & 1;
+      const int64_t tile = IL ? (int64_t)item : TILES_PER_ITEM * (int64_t)pair + crank + slot;
       if constexpr (HS) {
+        const int d = d_item;
         // h0 of this row -> the buffer step 0 reads.  Safe to overwrite: every MMA that read this buffer (step L-2 of
         // the previous item) retired before the tmem_full of the previous item's last step, which this thread passed.
         const uint8_t* src = p.h0img + ((tile * 2 + d) * 4) * (size_t)CHUNK_BYTES + row * 16;
@@ -708,9 +734,14 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
         mbar_arrive(h_ready);
       }
       for (int s = 0; s < L; ++s, ++hcnt) {
-        const int t = d ? (L - 1 - s) : s;
-        const int tprev = d ? t + 1 : t - 1;
-        for (int j = 0; j < 4; ++j, ++chunk) {
+        for (int jj = 0; jj < NCH; ++jj, ++chunk) {
+          const int d = IL ? il_d(jj) : d_item;
+          const int j = IL ? il_j(jj) : jj;
+          const int t = d ? (L - 1 - s) : s;
+          const int tprev = d ? t + 1 : t - 1;
+          // biases of the unit-chunk that uses this accumulator buffer next (IL: two chunks further on in the interleaved order)
+          const float* bz = IL ? bias_s + il_d((jj + 2) & 7) * 4 * 256 : bz0;
+          const int jnext = IL ? il_j((jj + 2) & 7) : ((j + NBUF) & 3);
           const uint8_t* hp_base =
               HS ? hbuf_g + (hcnt & 1) * C::HBUF + j * (size_t)CHUNK_BYTES
                  : ((s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
@@ -753,14 +784,19 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
                 for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(sb + 1) & 1][g]);
               }
               // re-arm these columns with the biases of the unit-chunk that uses this buffer next
-              arm_bias8(trow, col, bz, ((j + NBUF) & 3) * 64 + col);
+              arm_bias8(trow, col, bz, jnext * 64 + col);
               float hp[8], hn[8];
               if constexpr (C8) join8_c8(hph[sb], make_uint2(hpl[sb].x, hpl[sb].y), hp);
               else join8<P, F16>(hph[sb], hpl[sb], hp);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float r = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][1][i]));
-                const float z = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][2][i]));
+                float r, z;
+                if constexpr (C8) {
+                  sigmoid2_s(__uint_as_float(acc[sb & 1][1][i]), __uint_as_float(acc[sb & 1][2][i]), r, z);
+                } else {
+                  r = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][1][i]));
+                  z = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][2][i]));
+                }
                 const float n = tnh_<FAST, C8>(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
                 hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
               }
@@ -799,7 +835,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
             tmem_ld16(trow + 192 + ub * 16, anh);
             tmem_ld_wait();
             // re-arm these columns with the biases of the unit-chunk that uses this buffer next
-            arm_bias16(trow, ub, bz, ((j + NBUF) & 3) * 64 + ub * 16);
+            arm_bias16(trow, ub, bz, jnext * 64 + ub * 16);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float hp[8], hn[8];
@@ -835,7 +871,7 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
               }
             } else {
               fence_proxy_async_all();  // generic-proxy global writes -> visible to the producer's bulk copies
-              mbar_arrive(h_ready);
+              mbar_arrive(h_ready + (IL ? 8 * d : 0));
             }
           }
         }
@@ -1806,6 +1842,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DUO_THREADS, 1) tc_g
 //   Qa = q . Wa^T -> TMEM cols [0,256);  per t: D_t = out_t . Ua^T -> TMEM cols [256,512)
 //   e_t = va . tanh(Qa + D_t) (thread-local: TMEM lane = row), softmax over t, ctx = sum_t w_t out_t,
 //   partial logits = fc1[:, strand*512 : +512] . ctx, two strands combined with a warp shuffle.
+//   ONE pass over the layer's act image: fc1 . ctx = sum_t w_t (fc1 . out_t), and fc1 . out_t is taken by the head warps
+//   from the A-operand stages of D_t while they sit in shared memory (each stage is released by the MMA commit AND the
+//   four head warps); the softmax over t runs online (running max, rescaled sums), one step behind the scores.
 // ------------------------------------------------------------------------------------------------
 struct AttParams {
   const uint8_t* act;   // last layer's act image
@@ -1822,7 +1861,7 @@ struct AttParams {
 };
 
 constexpr int ATT_STAGES = 4;
-constexpr int ATT_THREADS = 384;  // warp 0 producer, 1 MMA, 4-7 score warps, 8-11 context/head warps
+constexpr int ATT_THREADS = 384;  // warps 0, 2, 3 producers, 1 MMA, 4-7 score warps, 8-11 head warps (fc1 . out_t, online softmax)
 
 template <int P>
 struct AttCfg {
@@ -1830,7 +1869,7 @@ struct AttCfg {
   static constexpr uint32_t B_PART = KS * T_SLAB;
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 49152
-  static constexpr uint32_t SMEM = ATT_STAGES * STAGE + (256 + 2048 + 2 * 128 * 22) * 4;
+  static constexpr uint32_t SMEM = ATT_STAGES * STAGE + (256 + 2048 + 2 * 128) * 4;
 };
 
 template <int P, bool F16, bool C8 = false>
@@ -1840,27 +1879,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * ATT_STAGES + 6];
+  __shared__ __align__(8) uint64_t bars[2 * ATT_STAGES + 4];
   __shared__ uint32_t tmem_base_s;
   float* va_s = reinterpret_cast<float*>(smem + ATT_STAGES * C::STAGE);
   float* fc_s = va_s + 256;
-  float* e_s = fc_s + 2048;  // [2][128][22]: softmax weights of a tile, double-buffered between the warp groups
+  float* e_s = fc_s + 2048;  // [2][128]: score e_t of each row, slot = (running step count) & 1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[ATT_STAGES]);
   const uint32_t d_full = smem_u32(&bars[2 * ATT_STAGES]), d_empty = smem_u32(&bars[2 * ATT_STAGES + 1]);
-  const uint32_t w_full = smem_u32(&bars[2 * ATT_STAGES + 2]), w_empty = smem_u32(&bars[2 * ATT_STAGES + 4]);
+  const uint32_t e_full = smem_u32(&bars[2 * ATT_STAGES + 2]);  // [2]: score warps -> head warps, alternating per step
   if (threadIdx.x == 0) {
     for (int i = 0; i < ATT_STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1 + 4);  // MMA commit + one arrival per head warp
     }
     mbar_init(d_full, 1);
     mbar_init(d_empty, 128);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(w_full + 8 * i, 128);   // score warps -> context warps: weights of a tile are in e_s[i]
-      mbar_init(w_empty + 8 * i, 128);  // context warps -> score warps: e_s[i] may be overwritten
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(e_full + 8 * i, 128);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 256; i += ATT_THREADS) va_s[i] = p.va[i];
@@ -1876,24 +1912,30 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
   const uint32_t smem_base = smem_u32(smem);
   const int L = p.L;
 
-  if (warp == 0) {
-    if (elect_one()) {
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ===================== TMA producers: warp 0 = weights part 0 (+ expect_tx), warp 2 = weights part 1, warp 3 = activations
+    // (one thread each, running source pointers: a single producer thread needed longer per stage than the stage's MMAs)
+    const int role = warp == 0 ? 0 : warp - 1;
+    if ((role != 1 || P == 2) && elect_one()) {
       uint32_t stage = 0, use = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int g = 0; g <= L; ++g) {  // g == 0: Qa; g >= 1: D_{t = g-1}
-          const uint8_t* wimg = g == 0 ? p.wa_img : p.ua_img;
+          const uint8_t* wsrc = (g == 0 ? p.wa_img : p.ua_img) + (role == 1 ? (size_t)64 * T_SLAB : 0);
           for (int so = 0; so < 64; so += KS) {
-            const int c = so >> 3;
-            const int t = g == 0 ? (c < 4 ? L - 1 : 0) : g - 1;  // q = [h_n fwd (t = L-1) | h_n rev (t = 0)]
             mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
             const uint32_t fb = full0 + 8 * stage;
             const uint32_t sb = smem_base + stage * C::STAGE;
-            mbar_expect_tx(fb, (uint32_t)(P * KS) * (T_SLAB + A_SLAB));
-            const uint8_t* asrc = p.act + ((((int64_t)tile * L + t) * 8 + c) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
+            if (role == 0) mbar_expect_tx(fb, (uint32_t)(P * KS) * (T_SLAB + A_SLAB));
+            if (role < 2) {
+              bulk_g2s(sb + role * C::B_PART, wsrc, KS * T_SLAB, fb);
+              wsrc += (size_t)KS * T_SLAB;
+            } else {
+              const int c = so >> 3;
+              const int t = g == 0 ? (c < 4 ? L - 1 : 0) : g - 1;  // q = [h_n fwd (t = L-1) | h_n rev (t = 0)]
+              const uint8_t* asrc = p.act + ((((int64_t)tile * L + t) * 8 + c) * P) * (size_t)CHUNK_BYTES + (so & 7) * A_SLAB;
 #pragma unroll
-            for (int pp = 0; pp < P; ++pp) {
-              bulk_g2s(sb + pp * C::B_PART, wimg + ((size_t)pp * 64 + so) * T_SLAB, KS * T_SLAB, fb);
-              bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, asrc + (size_t)pp * CHUNK_BYTES, KS * A_SLAB, fb);
+              for (int pp = 0; pp < P; ++pp)
+                bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, asrc + (size_t)pp * CHUNK_BYTES, KS * A_SLAB, fb);
             }
             if (++stage == ATT_STAGES) {
               stage = 0;
@@ -1957,121 +1999,136 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) tc_att_head_kernel(const AttPa
     }
     __syncwarp();
   } else if (warp >= 4 && warp < 8) {
-    // ===================== score warps: e_t = va . tanh(Qa + D_t), softmax over t =====================
+    // ===================== score warps: e_t = va . tanh(Qa + D_t) =====================
     const int quad = warp - 4;
     const int row = quad * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t dcount = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t wb = it & 1;
-      float* my_e = e_s + (wb * 128 + row) * 22;
-      mbar_wait(w_empty + 8 * wb, ((it >> 1) & 1) ^ 1);  // context warps are done with this buffer
+    uint32_t dcount = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       for (int t = 0; t < L; ++t, ++dcount) {
         mbar_wait(d_full, dcount & 1);
         tc_fence_after();
-        float e = 0.f;
-#pragma unroll 1
+        // 16-column blocks, the tcgen05.ld of block cb + 1 in flight while block cb goes through the MUFU pipe
+        float e0 = 0.f, e1 = 0.f;
+        uint32_t q[2][16], dd[2][16];
+        tmem_ld16(trow, q[0]);
+        tmem_ld16(trow + 256, dd[0]);
+#pragma unroll
         for (int cb = 0; cb < 16; ++cb) {
-          uint32_t q[16], dd[16];
-          tmem_ld16(trow + cb * 16, q);
-          tmem_ld16(trow + 256 + cb * 16, dd);
           tmem_ld_wait();
+          if (cb + 1 < 16) {
+            tmem_ld16(trow + (cb + 1) * 16, q[(cb + 1) & 1]);
+            tmem_ld16(trow + 256 + (cb + 1) * 16, dd[(cb + 1) & 1]);
+          }
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            e = fmaf(va_s[cb * 16 + i], tnh_<FAST, C8>(__uint_as_float(q[i]) + __uint_as_float(dd[i])), e);
-        }
-        my_e[t] = e;
-        tc_fence_before();
-        mbar_arrive(d_empty);
-      }
-      // softmax over t (thread-local), normalised weights handed to the context warps
-      float mx = -INFINITY;
-      for (int t = 0; t < L; ++t) mx = fmaxf(mx, my_e[t]);
-      float sum = 0.f;
-      for (int t = 0; t < L; ++t) {
-        float w = __expf(my_e[t] - mx);
-        my_e[t] = w;
-        sum += w;
-      }
-      const float inv = 1.f / sum;
-      for (int t = 0; t < L; ++t) my_e[t] *= inv;
-      mbar_arrive(w_full + 8 * wb);
-    }
-  } else if (warp >= 8) {
-    // ===================== context + head warps (overlap the next tile's MMAs and scores) =====================
-    const int row = (warp - 8) * 32 + lane;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t wb = it & 1;
-      const float* my_e = e_s + (wb * 128 + row) * 22;
-      mbar_wait(w_full + 8 * wb, (it >> 1) & 1);
-      float wt[32];
-#pragma unroll
-      for (int t = 0; t < 32; ++t) wt[t] = t < L ? my_e[t] : 0.f;
-      mbar_arrive(w_empty + 8 * wb);  // weights are in registers
-      // context + fc1 partial (this row's strand half of fc1)
-      const int strand = row & 1;
-      float lg0 = 0.f, lg1 = 0.f;
-#pragma unroll 1
-      for (int sl = 0; sl < 64; ++sl) {  // 64 slabs of 8 columns = 512 context features
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        constexpr int TB = (P == 1) ? 21 : 11;  // 16-byte loads in flight per thread and part
-#pragma unroll
-        for (int t0 = 0; t0 < 32; t0 += TB) {  // seq_len <= 32 (ccsm_create)
-          if (t0 < L) {
-            uint4 hi[TB], lo[TB];
-#pragma unroll
-            for (int k = 0; k < TB; ++k) {
-              const int t = (t0 + k) < L ? (t0 + k) : (L - 1);
-              const uint8_t* src = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES +
-                                   (sl & 7) * A_SLAB + row * 16;
-              hi[k] = __ldcg(reinterpret_cast<const uint4*>(src));
-              if constexpr (C8) {
-                const uint8_t* cb = p.act + ((((int64_t)tile * L + t) * 8 + (sl >> 3)) * P) * (size_t)CHUNK_BYTES;
-                const uint2 t8 = __ldcg(reinterpret_cast<const uint2*>(cb + CHUNK_BYTES + 4096 + c8_off(sl & 7) + row * 16));
-                lo[k] = make_uint4(t8.x, t8.y, 0, 0);
-              } else if constexpr (P == 2) lo[k] = __ldcg(reinterpret_cast<const uint4*>(src + CHUNK_BYTES));
-              else lo[k] = make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int k = 0; k < TB; ++k) {
-              float v[8];
-              if constexpr (C8) join8_c8(hi[k], make_uint2(lo[k].x, lo[k].y), v);
-              else join8<P, F16>(hi[k], lo[k], v);
-              const float w = (t0 + k) < 32 ? wt[(t0 + k) & 31] : 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
-            }
+          for (int i = 0; i < 16; i += 2) {
+            e0 = fmaf(va_s[cb * 16 + i], tnh_<FAST, C8>(__uint_as_float(q[cb & 1][i]) + __uint_as_float(dd[cb & 1][i])), e0);
+            e1 = fmaf(va_s[cb * 16 + i + 1],
+                      tnh_<FAST, C8>(__uint_as_float(q[cb & 1][i + 1]) + __uint_as_float(dd[cb & 1][i + 1])), e1);
           }
         }
-        const float* f0 = fc_s + strand * 512 + sl * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          lg0 = fmaf(acc[i], f0[i], lg0);
-          lg1 = fmaf(acc[i], f0[1024 + i], lg1);
-        }
+        const float e = e0 + e1;
+        tc_fence_before();
+        mbar_arrive(d_empty);
+        // Slot dcount & 1 is free: the head warps read e of step dcount - 2 before they release the first stage of step
+        // dcount, and D of step dcount needs all of its 16 stages.
+        e_s[(dcount & 1) * 128 + row] = e;
+        mbar_arrive(e_full + 8 * (dcount & 1));
       }
-      lg0 += __shfl_xor_sync(0xffffffffu, lg0, 1);  // strand 1 + strand 2 of the same site (adjacent rows)
-      lg1 += __shfl_xor_sync(0xffffffffu, lg1, 1);
-      const int64_t site = ((int64_t)tile * TILE_ROWS + row) >> 1;
-      if (strand == 0 && site < p.sites) {
-        lg0 += p.fc_b[0];
-        lg1 += p.fc_b[1];
-        const float m2 = fmaxf(lg0, lg1);
-        const float e0 = __expf(lg0 - m2), e1 = __expf(lg1 - m2);
-        const float is = 1.f / (e0 + e1);
-        if (p.logits) {
-          p.logits[site * 2] = lg0;
-          p.logits[site * 2 + 1] = lg1;
+    }
+  } else if (warp >= 8) {
+    // ===================== head warps: g_t = fc1[:, strand half] . out_t from the operand stages, online softmax =====================
+    const int row = (warp - 8) * 32 + lane;
+    const int strand = row & 1;
+    const float* f0 = fc_s + strand * 512;
+    const uint32_t arow = (uint32_t)row * 16;
+    uint32_t stage = 0, use = 0, ecount = 0;
+    float mx = -INFINITY, sum = 0.f, a0 = 0.f, a1 = 0.f;  // running max, sum of weights, weighted g
+    float g0 = 0.f, g1 = 0.f;                              // g of the step whose score is still on its way
+    bool pending = false, pend_last = false;
+    int pend_tile = 0;
+    auto settle = [&]() {
+      // the score of the pending step: it was finished while this warp went through the 16 stages that followed
+      mbar_wait(e_full + 8 * (ecount & 1), (ecount >> 1) & 1);
+      const float e = e_s[(ecount & 1) * 128 + row];
+      ++ecount;
+      const float m2 = fmaxf(mx, e);
+      const float c = __expf(mx - m2), w = __expf(e - m2);
+      sum = fmaf(sum, c, w);
+      a0 = fmaf(a0, c, w * g0);
+      a1 = fmaf(a1, c, w * g1);
+      mx = m2;
+      if (pend_last) {
+        const float inv = 1.f / sum;
+        float lg0 = a0 * inv, lg1 = a1 * inv;
+        lg0 += __shfl_xor_sync(0xffffffffu, lg0, 1);  // strand 1 + strand 2 of the same site (adjacent rows)
+        lg1 += __shfl_xor_sync(0xffffffffu, lg1, 1);
+        const int64_t site = ((int64_t)pend_tile * TILE_ROWS + row) >> 1;
+        if (strand == 0 && site < p.sites) {
+          lg0 += p.fc_b[0];
+          lg1 += p.fc_b[1];
+          const float m3 = fmaxf(lg0, lg1);
+          const float e0 = __expf(lg0 - m3), e1 = __expf(lg1 - m3);
+          const float is = 1.f / (e0 + e1);
+          if (p.logits) {
+            p.logits[site * 2] = lg0;
+            p.logits[site * 2 + 1] = lg1;
+          }
+          if (p.probs) {
+            p.probs[site * 2] = e0 * is;
+            p.probs[site * 2 + 1] = e1 * is;
+          }
         }
-        if (p.probs) {
-          p.probs[site * 2] = e0 * is;
-          p.probs[site * 2 + 1] = e1 * is;
+        mx = -INFINITY;
+        sum = a0 = a1 = 0.f;
+      }
+      pending = false;
+    };
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int g = 0; g <= L; ++g) {
+        float n0 = 0.f, n1 = 0.f;
+        for (int so = 0; so < 64; so += KS) {
+          mbar_wait(full0 + 8 * stage, use & 1);
+          if (g >= 1) {
+            const uint8_t* ap = smem + stage * C::STAGE + P * C::B_PART + arow;
+#pragma unroll
+            for (int q = 0; q < KS; ++q) {
+              const uint4 hi = *reinterpret_cast<const uint4*>(ap + q * A_SLAB);
+              float v[8];
+              if constexpr (C8) {
+                const uint2 l8 = *reinterpret_cast<const uint2*>(ap + C::A_PART + 4096 + (q >> 1) * 2048 + (q & 1) * 8);
+                join8_c8(hi, l8, v);
+              } else if constexpr (P == 2) {
+                join8<P, F16>(hi, *reinterpret_cast<const uint4*>(ap + C::A_PART + q * A_SLAB), v);
+              } else {
+                join8<P, F16>(hi, make_uint4(0, 0, 0, 0), v);
+              }
+              const float* f = f0 + (so + q) * 8;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                n0 = fmaf(v[i], f[i], n0);
+                n1 = fmaf(v[i], f[1024 + i], n1);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+          if (++stage == ATT_STAGES) {
+            stage = 0;
+            ++use;
+          }
+        }
+        if (pending) settle();
+        if (g >= 1) {
+          g0 = n0;
+          g1 = n1;
+          pending = true;
+          pend_last = g == L;
+          pend_tile = tile;
         }
       }
     }
+    if (pending) settle();
   }
   tc_fence_before();
   __syncthreads();
@@ -2358,16 +2415,16 @@ static int gru_variant(int layer, int P) {
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
   // Defaults = the pipelined-epilogue forms (profiles/r01_variants.md): layers >= 1 -> d (variant 2 + PIPE); layer 0 ->
-  // c (two CTAs per SM + PIPE) in the single-pass modes, e (8 epilogue warps + PIPE) in the x3 modes.
-  return layer > 0 ? 13 : (P == 2 ? 14 : 12);
+  // l (8 epilogue warps + PIPE, both directions of a row tile interleaved in one CTA: profiles/r02_bound.md section 7).
+  return layer > 0 ? 13 : 21;
 }
 
 template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false, bool HS = false, bool PIPE = false,
-          bool C8 = false>
+          bool C8 = false, bool IL = false>
 static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStream_t st) {
   using C = GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>;
   static bool attr = false;
-  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC, HS, PIPE, C8>;
+  auto kern = tc_gru_layer_kernel<P, F16, NSLOT, NBUF, KSB, EPIW, MC, HS, PIPE, C8, IL>;
   if (!attr) {
     CCSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr = true;
@@ -2393,6 +2450,11 @@ static int launch_gru(const GruParams& gp, int64_t tiles, int sm_count, cudaStre
     CCSM_CUDA(cudaLaunchKernelEx(&cfg, kern, gp));
     return CCSM_OK;
   }
+  if constexpr (IL) {
+    const int grid = (int)(tiles < slots ? tiles : slots);  // one item = one row tile, both directions
+    kern<<<grid, C::THREADS + 32 * GruProd<P, NSLOT, MC, HS>::EXTRA_WARPS, C::SMEM, st>>>(gp);
+    return CCSM_OK;
+  }
   const int64_t items = (tiles / NSLOT) * 2;  // groups of NSLOT row tiles x 2 directions
   const int grid = (int)(items < slots ? items : slots) & ~1;  // even: fixed direction per CTA
   kern<<<grid, C::THREADS + 32 * GruProd<P, NSLOT, MC, HS>::EXTRA_WARPS, C::SMEM, st>>>(gp);
@@ -2409,8 +2471,11 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
       case 14: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true, true>(gp, tiles, sm_count, st);
       case 15: return launch_gru<P, F16, 2, 1, 8, 1, false, false, true, true>(gp, tiles, sm_count, st);
       case 17: return launch_gru<P, F16, 1, 1, 8, 1, false, false, true, true>(gp, tiles, sm_count, st);  // two CTAs per SM
+      case 20: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true, true, true>(gp, tiles, sm_count, st);  // d, interleaved
+      case 21: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true, true, true>(gp, tiles, sm_count, st);  // e, interleaved
+      case 22: return launch_gru<P, F16, 1, 2, 8, 4, false, false, true, true, true>(gp, tiles, sm_count, st);  // 16 epilogue warps
       default:
-        set_error("precision fp16c8 runs GRU kernel variants d, e, f, g, h only (got %d)", variant);
+        set_error("precision fp16c8 runs GRU kernel variants d, e, f, g, h, i, j, k, l only (got %d)", variant);
         return CCSM_EINVAL;
     }
   } else
@@ -2436,6 +2501,9 @@ static int launch_gru_variant(int variant, const GruParams& gp, int64_t tiles, i
     case 17: return launch_gru<P, F16, 1, 1, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // 5 + pipelined epilogue
     case 18: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true>(gp, tiles, sm_count, st);  // (fp16c8-only kernel: d here)
     case 19: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true>(gp, tiles, sm_count, st);  // (fp16c8-only kernel: e here)
+    case 20: return launch_gru<P, F16, 1, 2, 8, 1, false, false, true, false, true>(gp, tiles, sm_count, st);  // d, both directions interleaved
+    case 21: return launch_gru<P, F16, 1, 2, 8, 2, false, false, true, false, true>(gp, tiles, sm_count, st);  // e, both directions interleaved
+    case 22: return launch_gru<P, F16, 1, 2, 8, 4, false, false, true, false, true>(gp, tiles, sm_count, st);  // 16 epilogue warps
     default:
       set_error("unknown GRU kernel variant %d", variant);
       return CCSM_EINVAL;
