@@ -523,9 +523,10 @@ __global__ void __launch_bounds__(GruCfg<P, NSLOT, NBUF, KSB, EPIW, HS>::THREADS
                 } else {
                   const uint8_t* a = (x_short && part == 0) ? src
                                                             : src + (size_t)(so >> 3) * (P * CHUNK_BYTES) + (so & 7) * A_SLAB;
-                  // 1 = activations evict_last too; 3 = the last (fourth) read of x_t and every read of h_{t-1} evict_first
+                  // 1 = activations evict_last too; 3 = the last (fourth) read of x_t and every read of h_{t-1} evict_first;
+                  // 4 = the last read of x_t and of h_{t-1} evict_first
                   if (p.l2_hint == 1) bulk_g2s_hint(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb, pol_last);
-                  else if (p.l2_hint == 3 && (j == 3 || part == 1))
+                  else if ((p.l2_hint == 3 && (j == 3 || part == 1)) || (p.l2_hint == 4 && j == 3))
                     bulk_g2s_hint(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb, pol_first);
                   else bulk_g2s(sb + P * C::B_PART + pp * C::A_PART, a, ns * A_SLAB, fb);
                 }
@@ -2555,9 +2556,11 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
       static int hint = -1;
       if (hint < 0) {
         const char* e = getenv("CCSM_TC_L2HINT");
-        hint = e ? atoi(e) : 0;
+        hint = e ? atoi(e) : -2;
       }
-      gp.l2_hint = hint;
+      // default: hi/lo images mark the last read of x_t and of h_{t-1} evict_first (22 -> 16 GB of DRAM reads per fp16c8
+      // layer launch, profiles/r02_bound.md section 8); the single-pass images already sit at the 2x-image floor
+      gp.l2_hint = hint == -2 ? (P == 2 ? 4 : 0) : hint;
     }
     pid = m->prof.begin(l == 0 ? PROF_GRU_L0 : PROF_GRU_LN, (double)sites, st);
     const int variant = gru_variant(l, P);
