@@ -68,6 +68,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// 2-D tensor-map load issued by either CTA of a pair into ITS OWN shared memory, completing on the LEADER CTA's mbarrier
+// (bar_leader = mapa of the barrier's address to cluster rank 0).  c0 = inner coordinate (8-byte elements), c1 = slab index.
+__device__ __forceinline__ void tma2d_pair(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar_leader), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // same with an L2 eviction-priority hint (policy from make_policy_evict_last / _first)
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
   asm volatile(

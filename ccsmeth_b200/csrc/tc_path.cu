@@ -38,6 +38,7 @@
 
 #include "ccsm_internal.h"
 #include "tc_common.cuh"
+#include "tmap.h"
 
 namespace ccsm {
 using namespace tc;
@@ -1839,6 +1840,302 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DUO_THREADS, 1) tc_g
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair GRU layer kernel, second form ("pair2", variant n): tcgen05.mma.cta_group::2 (M = 256: CTA c owns row tile
+// 2 * pair + c, its 128 rows of A in its own shared memory, and HALF of every weight slab -- 96 of the 192 gate rows),
+// so every weight byte crosses L2 -> SM once per 256 rows: 688 KB instead of 983 KB per row tile and unit-chunk in fp16c8.
+// Against round 1's pair kernel: operands arrive by 2-D tensor-map loads (cp.async.bulk.tensor ... .cta_group::2) that
+// complete on the LEADER CTA's `full` barrier from both CTAs -- no relay warp, no relay hop on the critical path (plain
+// bulk copies can only signal a barrier of the destination CTA: tc_selftest.cu, flag 2 vs flag 4) --, one load per
+// producer thread in 2 P warps per CTA, the software-pipelined gate epilogue, and the fp16c8 operand forms.
+//   warp 0 + 2 P - 1 warps at the end   producers (weights part pp / activations part pp of this CTA)
+//   warp 1                              rank 0: MMA issuer for the pair (rank 1: idle)
+//   warps 2-5                           gate epilogue of this CTA's row tile
+// Work item = (pair of row tiles, direction); the cluster count is even, so a cluster keeps one direction.
+// Layers >= 1 only (K_in = 512: every stage is full).  Weight image: the CTA-pair layout of tc_gru_pair_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int P>
+struct Pair2Cfg {
+  static constexpr int KS = 8 / P;
+  static constexpr int STAGES = 7;
+  static constexpr uint32_t B_PART = KS * GH_SLAB;
+  static constexpr uint32_t A_PART = KS * A_SLAB;
+  static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 28672
+  static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
+  static constexpr int CORE_WARPS = 6;
+  static constexpr int THREADS = 32 * (CORE_WARPS + 2 * P - 1);
+};
+
+template <int P, bool F16, bool C8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS, 1)
+    tc_gru_pair2_kernel(const GruParams p, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                        const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_h0) {
+  static_assert(!C8 || (P == 2 && F16), "C8: fp16 images");
+  using C = Pair2Cfg<P>;
+  constexpr int KS = C::KS;
+  constexpr bool FAST = (P == 1);
+  constexpr int S = C::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * S + 5];
+  __shared__ uint32_t tmem_base_s;
+  float* bias_s = reinterpret_cast<float*>(smem + S * C::STAGE);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]);
+  const uint32_t tmem_full = smem_u32(&bars[2 * S]), tmem_empty = smem_u32(&bars[2 * S + 2]),
+                 h_ready = smem_u32(&bars[2 * S + 4]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1);   // used in the leader: its expect_tx arrival + the bytes of both CTAs
+      mbar_init(empty0 + 8 * i, 1);  // multicast commit of the stage's MMAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, 8);  // one arrival per epilogue warp of both CTAs (leader's barrier)
+    }
+    mbar_init(h_ready, 4);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * 4 * 256; i += C::THREADS) bias_s[i] = p.bias[i];
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const int L = p.L;
+  const int n_items = (p.n_tiles / 2) * 2;  // pairs of row tiles x 2 directions
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // weight image in 1536-byte slabs: [dir][j]{X: [half][part][64], H: [half][part][32]}
+  constexpr int XS = 2 * P * 64, HSL = 2 * P * 32, WJ = XS + HSL;
+
+  if (warp == 0 || warp >= C::CORE_WARPS) {
+    // ===================== producers: one tensor-map load per stage and thread =====================
+    if (elect_one()) {
+      const int role = warp == 0 ? 0 : warp - C::CORE_WARPS + 1;  // [0, P): weight part; [P, 2 P): activation part
+      const bool is_b = role < P;
+      const int pp = is_b ? role : role - P;
+      const uint32_t leader_full0 = mapa_u32(full0, 0);
+      if (lane == 0 || true) {
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_o);
+        tma_prefetch_desc(&tm_h0);
+      }
+      uint32_t stage = 0, use = 0, gstep = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int pair = item >> 1, d = item & 1;
+        const int64_t tile = 2 * (int64_t)pair + rank;
+        for (int s = 0; s < L; ++s, ++gstep) {
+          const int t = d ? (L - 1 - s) : s;
+          const int tprev = d ? t + 1 : t - 1;
+          // first slab (2048-byte units) of this thread's part of x_t / h_{t-1}; + (so >> 3) * P * 8 + (so & 7) per stage
+          const int xs0 = (int)((((tile * L + t) * 8) * P + pp) * 8);
+          const int hs0 = s == 0 ? (int)((((tile * 2 + d) * 4) * P + pp) * 8) : (int)((((tile * L + tprev) * 8 + d * 4) * P + pp) * 8);
+          for (int j = 0; j < 4; ++j) {
+            const int wj = (d * 4 + j) * WJ;
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? 64 : 32;
+              const int ws0 = wj + (part ? XS : 0) + (int)rank * P * total + pp * total;
+              for (int so = 0; so < total; so += KS) {
+                if (!is_b && part == 1 && so == 0 && j == 0 && gstep > 0) {
+                  mbar_wait(h_ready, (gstep - 1) & 1);  // h_{t_prev} of this CTA's rows is in the act image
+                  fence_proxy_async_all();
+                }
+                mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                if (role == 0 && rank == 0) mbar_expect_tx(full0 + 8 * stage, 2u * (uint32_t)(P * KS) * (GH_SLAB + A_SLAB));
+                const uint32_t fb = leader_full0 + 8 * stage;
+                if (is_b) {
+                  tma2d_pair(sb + pp * C::B_PART, &tm_w, 0, ws0 + so, fb);
+                } else {
+                  const int sl = (so >> 3) * (P * 8) + (so & 7);
+                  if (part == 0) tma2d_pair(sb + P * C::B_PART + pp * C::A_PART, &tm_x, 0, xs0 + sl, fb);
+                  else if (s == 0) tma2d_pair(sb + P * C::B_PART + pp * C::A_PART, &tm_h0, 0, hs0 + sl, fb);
+                  else tma2d_pair(sb + P * C::B_PART + pp * C::A_PART, &tm_o, 0, hs0 + sl, fb);
+                }
+                if (++stage == S) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ===================== MMA issuer for the pair =====================
+      constexpr uint32_t idesc = make_idesc(256, 192, F16);
+      constexpr uint32_t idesc8 = make_idesc_e4m3(256, 192);
+      uint32_t stage = 0, use = 0, chunk = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        for (int s = 0; s < L; ++s) {
+          for (int j = 0; j < 4; ++j, ++chunk) {
+            const uint32_t buf = chunk & 1, u = chunk >> 1;
+            mbar_wait(tmem_empty + 8 * buf, u & 1);  // completion #u: #0 = initial arming, #k = drain of use k-1
+            tc_fence_after();
+            const uint32_t dcol = tmem + buf * 256;
+            for (int part = 0; part < 2; ++part) {
+              const int total = part == 0 ? 64 : 32;
+              const uint32_t dpart = dcol + (part == 0 ? 0 : 64);  // X -> (n_i, r, z); H -> (r, z, n_h)
+              for (int so = 0; so < total; so += KS) {
+                mbar_wait(full0 + 8 * stage, use & 1);
+                tc_fence_after();
+                const uint32_t sb = smem_base + stage * C::STAGE;
+                const uint32_t a0 = sb + P * C::B_PART, b0 = sb;
+                if constexpr (C8) {
+#pragma unroll
+                  for (int q = 0; q < 2; ++q)
+                    umma_f16_pair(dpart, make_smem_desc(a0 + q * 2 * A_SLAB, A_SLAB, 128),
+                                  make_smem_desc(b0 + q * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
+#pragma unroll
+                  for (int q = 0; q < 2; ++q)
+                    umma_f8_pair(dpart, make_smem_desc(a0 + C::A_PART + q * 2 * A_SLAB, A_SLAB, 128),
+                                 make_smem_desc(b0 + C::B_PART + q * 2 * GH_SLAB, GH_SLAB, 128), idesc8, 1u);
+                } else {
+#pragma unroll
+                  for (int ks = 0; ks < KS / 2; ++ks) {
+#pragma unroll
+                    for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
+                      const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                      umma_f16_pair(dpart, make_smem_desc(a0 + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128),
+                                    make_smem_desc(b0 + pb * C::B_PART + ks * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
+                    }
+                  }
+                }
+                umma_commit_pair(empty0 + 8 * stage, 0x3);
+                if (++stage == S) {
+                  stage = 0;
+                  ++use;
+                }
+              }
+            }
+            umma_commit_pair(tmem_full + 8 * buf, 0x3);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== gate epilogue (warps 2-5) of this CTA's row tile =====================
+    const int quad = warp & 3;  // tcgen05.ld lane rule: a warp touches TMEM lanes [32 * (warp % 4), +32)
+    const int row = quad * 32 + lane;
+    const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t remote_empty = mapa_u32(tmem_empty, 0);
+    const float* bz = bias_s + (cluster_id & 1) * 4 * 256;  // every item of this cluster has the same direction
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + b * 256, ub, bz, b * 64 + ub * 16);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive_remote(remote_empty);
+      mbar_arrive_remote(remote_empty + 8);
+    }
+    uint32_t chunk = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int pair = item >> 1, d = item & 1;
+      const int64_t tile = 2 * (int64_t)pair + rank;
+      for (int s = 0; s < L; ++s) {
+        const int t = d ? (L - 1 - s) : s;
+        const int tprev = d ? t + 1 : t - 1;
+        for (int j = 0; j < 4; ++j, ++chunk) {
+          const uint8_t* hp_base =
+              (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
+                       : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
+          // prefetch h_{t_prev} of this row's 64 units (the L2 latency overlaps the chunk's MMAs)
+          uint4 hph[8], hpl[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + q * A_SLAB + row * 16));
+            if constexpr (C8) {
+              const uint2 t8 = __ldcg(reinterpret_cast<const uint2*>(hp_base + CHUNK_BYTES + 4096 + c8_off(q) + row * 16));
+              hpl[q] = make_uint4(t8.x, t8.y, 0, 0);
+            } else if constexpr (P == 2)
+              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + q * A_SLAB + row * 16));
+            else
+              hpl[q] = make_uint4(0, 0, 0, 0);
+          }
+          const uint32_t buf = chunk & 1, u = chunk >> 1;
+          const uint32_t trow = trow0 + buf * 256;
+          mbar_wait(tmem_full + 8 * buf, u & 1);
+          tc_fence_after();
+          uint32_t acc[2][4][8];  // [ping-pong][n_i, r, z, n_h][8 units]
+          uint2 a8_even = make_uint2(0, 0), l8_even = make_uint2(0, 0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64, acc[0][g]);
+#pragma unroll
+          for (int sb = 0; sb < 8; ++sb) {
+            const int col = sb * 8;
+            tmem_ld_wait();  // sub-block sb has landed (issued one iteration ago)
+            if (sb + 1 < 8) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(sb + 1) & 1][g]);
+            }
+            arm_bias8(trow, col, bz, ((j + 2) & 3) * 64 + col);  // biases of the unit-chunk that uses this buffer next
+            float hp[8], hn[8];
+            if constexpr (C8) join8_c8(hph[sb], make_uint2(hpl[sb].x, hpl[sb].y), hp);
+            else join8<P, F16>(hph[sb], hpl[sb], hp);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float r, z;
+              if constexpr (C8) {
+                sigmoid2_s(__uint_as_float(acc[sb & 1][1][i]), __uint_as_float(acc[sb & 1][2][i]), r, z);
+              } else {
+                r = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][1][i]));
+                z = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][2][i]));
+              }
+              const float n = tnh_<FAST, C8>(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
+              hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
+            }
+            if constexpr (C8) {
+              uint4 hi;
+              uint2 a8, l8;
+              split8_c8(hn, hi, a8, l8);
+              *reinterpret_cast<uint4*>(out_base + sb * A_SLAB + row * 16) = hi;
+              if ((sb & 1) == 0) {
+                a8_even = a8;
+                l8_even = l8;
+              } else {
+                uint8_t* b8 = out_base + CHUNK_BYTES + c8_off(sb - 1) + row * 16;
+                *reinterpret_cast<uint4*>(b8) = make_uint4(a8_even.x, a8_even.y, a8.x, a8.y);
+                *reinterpret_cast<uint4*>(b8 + 4096) = make_uint4(l8_even.x, l8_even.y, l8.x, l8.y);
+              }
+            } else {
+              uint4 hi, lo;
+              split8<P, F16>(hn, hi, lo);
+              *reinterpret_cast<uint4*>(out_base + sb * A_SLAB + row * 16) = hi;
+              if constexpr (P == 2) *reinterpret_cast<uint4*>(out_base + CHUNK_BYTES + sb * A_SLAB + row * 16) = lo;
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          if (j == 3) fence_proxy_async_all();  // generic-proxy global writes -> visible to the producers' tensor-map loads
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_remote(remote_empty + 8 * buf);
+            if (j == 3) mbar_arrive(h_ready);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention + head kernel (reference utils/attention.py:48-70, models.py:135-150)
 //   Qa = q . Wa^T -> TMEM cols [0,256);  per t: D_t = out_t . Ua^T -> TMEM cols [256,512)
 //   e_t = va . tanh(Qa + D_t) (thread-local: TMEM lane = row), softmax over t, ctx = sum_t w_t out_t,
@@ -2576,6 +2873,28 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
       const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;
       if (variant == 18) tc_gru_cv_kernel<1><<<grid, CvCfg<1>::THREADS, CvCfg<1>::SMEM, st>>>(gp);
       else tc_gru_cv_kernel<2><<<grid, CvCfg<2>::THREADS, CvCfg<2>::SMEM, st>>>(gp);
+    } else if (variant == 23 && l > 0) {
+      // pair2 kernel: CTA pairs, tensor-map loads completing on the leader's barrier
+      gp.wimg = T.wpair[l].as<uint8_t>();
+      static bool p2_attr = false;
+      if (!p2_attr) {
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Pair2Cfg<P>::SMEM));
+        p2_attr = true;
+      }
+      const uint64_t act_slabs = (uint64_t)tiles * L * 8 * P * 8, h0_slabs = (uint64_t)tiles * 2 * 4 * P * 8;
+      CUtensorMap tm_w, tm_x, tm_o, tm_h0;
+      if (make_slab_tmap(&tm_w, gp.wimg, GH_SLAB, (uint64_t)8 * (2 * P * 64 + 2 * P * 32), Pair2Cfg<P>::KS) ||
+          make_slab_tmap(&tm_x, gp.xin, A_SLAB, act_slabs, Pair2Cfg<P>::KS) ||
+          make_slab_tmap(&tm_o, gp.out, A_SLAB, act_slabs, Pair2Cfg<P>::KS) ||
+          make_slab_tmap(&tm_h0, gp.h0img, A_SLAB, h0_slabs, Pair2Cfg<P>::KS)) {
+        set_error("cuTensorMapEncodeTiled failed (pair2 GRU kernel)");
+        return CCSM_ECUDA;
+      }
+      const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
+      const int64_t max_clusters = T.sm_count / 2;
+      const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;  // even: fixed direction per cluster
+      tc_gru_pair2_kernel<P, F16, C8><<<2 * clusters, Pair2Cfg<P>::THREADS, Pair2Cfg<P>::SMEM, st>>>(gp, tm_w, tm_x, tm_o, tm_h0);
     } else if (variant == 16) {
       // duo kernel: CTA pairs, both directions interleaved; one cluster per TPC
       gp.wimg = T.wpair[l].as<uint8_t>();

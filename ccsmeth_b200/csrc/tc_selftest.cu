@@ -3,7 +3,10 @@
 #include <vector>
 
 #include "ccsm_internal.h"
+#include <string.h>
+
 #include "tc_common.cuh"
+#include "tmap.h"
 
 namespace ccsm {
 using namespace tc;
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint8_t* __
 template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     umma_pair_selftest_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img,
-                              float* __restrict__ D, float* __restrict__ Z, int N, int K, int direct_signal) {
+                              float* __restrict__ D, float* __restrict__ Z, int N, int K, int direct_signal,
+                              const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[3];  // full (local), peer_full (used in CTA 0), done
   __shared__ uint32_t tmem_base_s;
@@ -105,7 +109,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
   const uint32_t tmem = tmem_base_s;
   if (warp == 0) {
     if (elect_one()) {
-      if (direct_signal) {
+      if (direct_signal == 2) {
+        // tensor-map loads of both CTAs complete on the LEADER's mbarrier (cp.async.bulk.tensor ... .cta_group::2)
+        if (rank == 0) mbar_expect_tx(bar_full, 2 * (a_bytes + b_bytes));
+        const uint32_t bar = mapa_u32(bar_full, 0);
+        tma2d_pair(smem_u32(sA), &ta, 0, (int)rank * (K / 8), bar);
+        tma2d_pair(smem_u32(sB), &tb, 0, (int)rank * (K / 8), bar);
+        if (rank == 0) mbar_wait(bar_full, 0);
+      } else if (direct_signal) {
         // experiment: the peer's bulk copies complete_tx directly on the LEADER's mbarrier (no relay hop)
         if (rank == 0) mbar_expect_tx(bar_full, 2 * (a_bytes + b_bytes));
         const uint32_t bar = rank == 0 ? bar_full : mapa_u32(bar_full, 0);
@@ -415,8 +426,9 @@ extern "C" int ccsm_debug_umma_mixed_gemm(int32_t device, int32_t N, int32_t K, 
 
 extern "C" int ccsm_debug_umma_pair_gemm(int32_t device, int32_t N, int32_t K, int32_t is_f16, const float* A,
                                          const float* B, float* D, float* Z) {
-  // is_f16 bit 1 selects the "peer signals the leader's mbarrier directly" experiment
-  const int direct_signal = (is_f16 >> 1) & 1;
+  // is_f16 bit 1 selects the "peer signals the leader's mbarrier directly" experiment with plain bulk copies (fails: a bulk
+  // copy can only complete on a barrier of the destination CTA), bit 2 the same with cta_group::2 tensor-map loads
+  const int direct_signal = (is_f16 & 4) ? 2 : (is_f16 >> 1) & 1;
   is_f16 &= 1;
   if (N < 32 || N > 256 || N % 32 || K < 16 || K % 16 || !A || !B || !D || !Z) {
     set_error("ccsm_debug_umma_pair_gemm: bad shape N=%d K=%d", N, K);
@@ -443,12 +455,22 @@ extern "C" int ccsm_debug_umma_pair_gemm(int32_t device, int32_t N, int32_t K, i
   CCSM_TRY(dz.reserve((size_t)256 * 32 * 4));
   CCSM_CUDA(cudaMemcpy(da.p, ai.data(), ai.size() * 2, cudaMemcpyHostToDevice));
   CCSM_CUDA(cudaMemcpy(db.p, bi.data(), bi.size() * 2, cudaMemcpyHostToDevice));
+  CUtensorMap ta, tb;
+  memset(&ta, 0, sizeof(ta));
+  memset(&tb, 0, sizeof(tb));
+  if (direct_signal == 2) {
+    if (K / 8 > 256 || make_slab_tmap(&ta, da.p, 2048, (uint64_t)2 * (K / 8), (uint32_t)(K / 8)) ||
+        make_slab_tmap(&tb, db.p, (uint32_t)NH * 16u, (uint64_t)2 * (K / 8), (uint32_t)(K / 8))) {
+      set_error("ccsm_debug_umma_pair_gemm: cuTensorMapEncodeTiled failed");
+      return CCSM_ECUDA;
+    }
+  }
   if (is_f16) {
     CCSM_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_pair_selftest_kernel<true><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K, direct_signal);
+    umma_pair_selftest_kernel<true><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K, direct_signal, ta, tb);
   } else {
     CCSM_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_pair_selftest_kernel<false><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K, direct_signal);
+    umma_pair_selftest_kernel<false><<<2, 128, smem>>>(da.as<uint8_t>(), db.as<uint8_t>(), dd.as<float>(), dz.as<float>(), N, K, direct_signal, ta, tb);
   }
   count_launch();
   cudaError_t e = cudaDeviceSynchronize();
