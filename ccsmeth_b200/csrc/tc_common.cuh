@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma2d_pair(uint32_t dst, const void* tmap, int c
       "l"(tmap), "r"(bar_leader), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma2d_pair_hint(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar_leader, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(tmap), "r"(bar_leader), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

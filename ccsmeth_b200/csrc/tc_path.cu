@@ -1853,7 +1853,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DUO_THREADS, 1) tc_g
 // Work item = (pair of row tiles, direction); the cluster count is even, so a cluster keeps one direction.
 // Layers >= 1 only (K_in = 512: every stage is full).  Weight image: the CTA-pair layout of tc_gru_pair_kernel.
 // ------------------------------------------------------------------------------------------------
-template <int P>
+template <int P, bool DUO>
 struct Pair2Cfg {
   static constexpr int KS = 8 / P;
   static constexpr int STAGES = 7;
@@ -1861,21 +1861,28 @@ struct Pair2Cfg {
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 28672
   static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
-  static constexpr int CORE_WARPS = 6;
+  static constexpr int EPI_WARPS = DUO ? 8 : 4;
+  static constexpr int CORE_WARPS = 2 + EPI_WARPS;
   static constexpr int THREADS = 32 * (CORE_WARPS + 2 * P - 1);
 };
 
-template <int P, bool F16, bool C8>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS, 1)
+// DUO = false: work item = (pair of row tiles, direction), the two TMEM buffers alternate chunk by chunk (layers >= 1).
+// DUO = true:  work item = pair of row tiles, BOTH directions as two recurrences that alternate chunk by chunk (F0 R0 F1 R1
+//              ...), recurrence d on TMEM buffer d with its own four epilogue warps -- layer 0, where nothing else hides the
+//              h_t round trip at a step boundary; its K = 16 input part is one short stage (two slabs, 3-pass form).
+template <int P, bool F16, bool C8, bool DUO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::THREADS, 1)
     tc_gru_pair2_kernel(const GruParams p, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
-                        const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_h0) {
+                        const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_h0,
+                        const __grid_constant__ CUtensorMap tm_wx, const __grid_constant__ CUtensorMap tm_xs) {
   static_assert(!C8 || (P == 2 && F16), "C8: fp16 images");
-  using C = Pair2Cfg<P>;
+  using C = Pair2Cfg<P, DUO>;
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   constexpr int S = C::STAGES;
+  constexpr int ND = DUO ? 2 : 1;  // recurrences per item
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * S + 5];
+  __shared__ __align__(8) uint64_t bars[2 * S + 6];
   __shared__ uint32_t tmem_base_s;
   float* bias_s = reinterpret_cast<float*>(smem + S * C::STAGE);
 
@@ -1891,9 +1898,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, 8);  // one arrival per epilogue warp of both CTAs (leader's barrier)
+      mbar_init(tmem_empty + 8 * i, 8);  // one arrival per epilogue warp (of the buffer's recurrence) of both CTAs
+      mbar_init(h_ready + 8 * i, 4);     // DUO: one per recurrence
     }
-    mbar_init(h_ready, 4);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * 4 * 256; i += C::THREADS) bias_s[i] = p.bias[i];
@@ -1907,10 +1914,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS
   const uint32_t tmem = tmem_base_s;
   const uint32_t smem_base = smem_u32(smem);
   const int L = p.L;
-  const int n_items = (p.n_tiles / 2) * 2;  // pairs of row tiles x 2 directions
+  const int n_items = DUO ? p.n_tiles / 2 : (p.n_tiles / 2) * 2;  // pairs of row tiles (x 2 directions)
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  // weight image in 1536-byte slabs: [dir][j]{X: [half][part][64], H: [half][part][32]}
-  constexpr int XS = 2 * P * 64, HSL = 2 * P * 32, WJ = XS + HSL;
+  // weight image in 1536-byte slabs: [dir][j]{X: [half][part][kx], H: [half][part][32]}
+  const int kx = p.kx_slabs;
+  const bool x_short = kx < KS;  // layer 0: K = 16, one stage of two slabs
+  const int XS = 2 * P * kx, WJ = XS + 2 * P * 32;
 
   if (warp == 0 || warp >= C::CORE_WARPS) {
     // ===================== producers: one tensor-map load per stage and thread =====================
@@ -1919,47 +1928,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS
       const bool is_b = role < P;
       const int pp = is_b ? role : role - P;
       const uint32_t leader_full0 = mapa_u32(full0, 0);
-      if (lane == 0 || true) {
-        tma_prefetch_desc(&tm_w);
-        tma_prefetch_desc(&tm_x);
+      const uint64_t pol_first = make_policy_evict_first();
+      tma_prefetch_desc(is_b ? (const void*)&tm_w : (const void*)&tm_x);
+      tma_prefetch_desc(is_b ? (const void*)&tm_wx : (const void*)&tm_xs);
+      if (!is_b) {
         tma_prefetch_desc(&tm_o);
         tma_prefetch_desc(&tm_h0);
       }
       uint32_t stage = 0, use = 0, gstep = 0;
       for (int item = cluster_id; item < n_items; item += n_clusters) {
-        const int pair = item >> 1, d = item & 1;
-        const int64_t tile = 2 * (int64_t)pair + rank;
+        const int64_t tile = 2 * (int64_t)(DUO ? item : item >> 1) + rank;
         for (int s = 0; s < L; ++s, ++gstep) {
-          const int t = d ? (L - 1 - s) : s;
-          const int tprev = d ? t + 1 : t - 1;
-          // first slab (2048-byte units) of this thread's part of x_t / h_{t-1}; + (so >> 3) * P * 8 + (so & 7) per stage
-          const int xs0 = (int)((((tile * L + t) * 8) * P + pp) * 8);
-          const int hs0 = s == 0 ? (int)((((tile * 2 + d) * 4) * P + pp) * 8) : (int)((((tile * L + tprev) * 8 + d * 4) * P + pp) * 8);
           for (int j = 0; j < 4; ++j) {
-            const int wj = (d * 4 + j) * WJ;
-            for (int part = 0; part < 2; ++part) {
-              const int total = part == 0 ? 64 : 32;
-              const int ws0 = wj + (part ? XS : 0) + (int)rank * P * total + pp * total;
-              for (int so = 0; so < total; so += KS) {
-                if (!is_b && part == 1 && so == 0 && j == 0 && gstep > 0) {
-                  mbar_wait(h_ready, (gstep - 1) & 1);  // h_{t_prev} of this CTA's rows is in the act image
-                  fence_proxy_async_all();
-                }
-                mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
-                const uint32_t sb = smem_base + stage * C::STAGE;
-                if (role == 0 && rank == 0) mbar_expect_tx(full0 + 8 * stage, 2u * (uint32_t)(P * KS) * (GH_SLAB + A_SLAB));
-                const uint32_t fb = leader_full0 + 8 * stage;
-                if (is_b) {
-                  tma2d_pair(sb + pp * C::B_PART, &tm_w, 0, ws0 + so, fb);
-                } else {
-                  const int sl = (so >> 3) * (P * 8) + (so & 7);
-                  if (part == 0) tma2d_pair(sb + P * C::B_PART + pp * C::A_PART, &tm_x, 0, xs0 + sl, fb);
-                  else if (s == 0) tma2d_pair(sb + P * C::B_PART + pp * C::A_PART, &tm_h0, 0, hs0 + sl, fb);
-                  else tma2d_pair(sb + P * C::B_PART + pp * C::A_PART, &tm_o, 0, hs0 + sl, fb);
-                }
-                if (++stage == S) {
-                  stage = 0;
-                  ++use;
+            for (int dd = 0; dd < ND; ++dd) {
+              const int d = DUO ? dd : (item & 1);
+              const int t = d ? (L - 1 - s) : s;
+              const int tprev = d ? t + 1 : t - 1;
+              // first slab (2048-byte units) of this thread's part of x_t / h_{t-1}
+              const int xs0 = x_short ? (int)(((tile * L + t) * P + pp) * 2) : (int)((((tile * L + t) * 8) * P + pp) * 8);
+              const int hs0 = s == 0 ? (int)((((tile * 2 + d) * 4) * P + pp) * 8)
+                                     : (int)((((tile * L + tprev) * 8 + d * 4) * P + pp) * 8);
+              const int wj = (d * 4 + j) * WJ;
+              for (int part = 0; part < 2; ++part) {
+                const int total = part == 0 ? kx : 32;
+                const int ws0 = wj + (part ? XS : 0) + (int)rank * P * total + pp * total;
+                for (int so = 0; so < total; so += KS) {
+                  const int ns = (total - so) < KS ? (total - so) : KS;
+                  if (!is_b && part == 1 && so == 0 && j == 0 && gstep > 0) {
+                    mbar_wait(h_ready + 8 * dd, (gstep - 1) & 1);  // h_{t_prev} of this CTA's rows is in the act image
+                    fence_proxy_async_all();
+                  }
+                  mbar_wait(empty0 + 8 * stage, (use & 1) ^ 1);
+                  const uint32_t sb = smem_base + stage * C::STAGE;
+                  if (role == 0 && rank == 0) mbar_expect_tx(full0 + 8 * stage, 2u * (uint32_t)(P * ns) * (GH_SLAB + A_SLAB));
+                  const uint32_t fb = leader_full0 + 8 * stage;
+                  if (is_b) {
+                    tma2d_pair(sb + pp * C::B_PART, (part == 0 && x_short) ? &tm_wx : &tm_w, 0, ws0 + so, fb);
+                  } else {
+                    const uint32_t dst = sb + P * C::B_PART + pp * C::A_PART;
+                    if (part == 0 && x_short) {
+                      tma2d_pair(dst, &tm_xs, 0, xs0, fb);
+                    } else {
+                      const int sl = (so >> 3) * (P * 8) + (so & 7);
+                      const void* tm = part == 0 ? &tm_x : (s == 0 ? &tm_h0 : &tm_o);
+                      const int c1 = (part == 0 ? xs0 : hs0) + sl;
+                      // the step's last read of x_t / h_{t-1} leaves L2 first (CCSM_TC_L2HINT 4, see tc_gru_layer_kernel)
+                      if (p.l2_hint == 4 && j == 3) tma2d_pair_hint(dst, tm, 0, c1, fb, pol_first);
+                      else tma2d_pair(dst, tm, 0, c1, fb);
+                    }
+                  }
+                  if (++stage == S) {
+                    stage = 0;
+                    ++use;
+                  }
                 }
               }
             }
@@ -1973,78 +1994,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS
       // ===================== MMA issuer for the pair =====================
       constexpr uint32_t idesc = make_idesc(256, 192, F16);
       constexpr uint32_t idesc8 = make_idesc_e4m3(256, 192);
-      uint32_t stage = 0, use = 0, chunk = 0;
+      uint32_t stage = 0, use = 0, chunk = 0;  // chunk: per TMEM buffer pair (non-DUO: every chunk; DUO: per recurrence)
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         for (int s = 0; s < L; ++s) {
-          for (int j = 0; j < 4; ++j, ++chunk) {
-            const uint32_t buf = chunk & 1, u = chunk >> 1;
-            mbar_wait(tmem_empty + 8 * buf, u & 1);  // completion #u: #0 = initial arming, #k = drain of use k-1
-            tc_fence_after();
-            const uint32_t dcol = tmem + buf * 256;
-            for (int part = 0; part < 2; ++part) {
-              const int total = part == 0 ? 64 : 32;
-              const uint32_t dpart = dcol + (part == 0 ? 0 : 64);  // X -> (n_i, r, z); H -> (r, z, n_h)
-              for (int so = 0; so < total; so += KS) {
-                mbar_wait(full0 + 8 * stage, use & 1);
-                tc_fence_after();
-                const uint32_t sb = smem_base + stage * C::STAGE;
-                const uint32_t a0 = sb + P * C::B_PART, b0 = sb;
-                if constexpr (C8) {
+          for (int j = 0; j < 4; ++j) {
+            for (int dd = 0; dd < ND; ++dd) {
+              const uint32_t buf = DUO ? (uint32_t)dd : (chunk & 1), u = DUO ? chunk : (chunk >> 1);
+              mbar_wait(tmem_empty + 8 * buf, u & 1);  // completion #u: #0 = initial arming, #k = drain of use k-1
+              tc_fence_after();
+              const uint32_t dcol = tmem + buf * 256;
+              for (int part = 0; part < 2; ++part) {
+                const int total = part == 0 ? kx : 32;
+                const uint32_t dpart = dcol + (part == 0 ? 0 : 64);  // X -> (n_i, r, z); H -> (r, z, n_h)
+                for (int so = 0; so < total; so += KS) {
+                  const int ns = (total - so) < KS ? (total - so) : KS;
+                  mbar_wait(full0 + 8 * stage, use & 1);
+                  tc_fence_after();
+                  const uint32_t sb = smem_base + stage * C::STAGE;
+                  const uint32_t a0 = sb + P * C::B_PART, b0 = sb;
+                  if (C8 && ns == KS) {
 #pragma unroll
-                  for (int q = 0; q < 2; ++q)
-                    umma_f16_pair(dpart, make_smem_desc(a0 + q * 2 * A_SLAB, A_SLAB, 128),
-                                  make_smem_desc(b0 + q * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
+                    for (int q = 0; q < 2; ++q)
+                      umma_f16_pair(dpart, make_smem_desc(a0 + q * 2 * A_SLAB, A_SLAB, 128),
+                                    make_smem_desc(b0 + q * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
 #pragma unroll
-                  for (int q = 0; q < 2; ++q)
-                    umma_f8_pair(dpart, make_smem_desc(a0 + C::A_PART + q * 2 * A_SLAB, A_SLAB, 128),
-                                 make_smem_desc(b0 + C::B_PART + q * 2 * GH_SLAB, GH_SLAB, 128), idesc8, 1u);
-                } else {
+                    for (int q = 0; q < 2; ++q)
+                      umma_f8_pair(dpart, make_smem_desc(a0 + C::A_PART + q * 2 * A_SLAB, A_SLAB, 128),
+                                   make_smem_desc(b0 + C::B_PART + q * 2 * GH_SLAB, GH_SLAB, 128), idesc8, 1u);
+                  } else {
+                    for (int ks = 0; ks < ns / 2; ++ks) {
 #pragma unroll
-                  for (int ks = 0; ks < KS / 2; ++ks) {
-#pragma unroll
-                    for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
-                      const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
-                      umma_f16_pair(dpart, make_smem_desc(a0 + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128),
-                                    make_smem_desc(b0 + pb * C::B_PART + ks * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
+                      for (int pass = 0; pass < (P == 2 ? 3 : 1); ++pass) {
+                        const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                        umma_f16_pair(dpart, make_smem_desc(a0 + pa * C::A_PART + ks * 2 * A_SLAB, A_SLAB, 128),
+                                      make_smem_desc(b0 + pb * C::B_PART + ks * 2 * GH_SLAB, GH_SLAB, 128), idesc, 1u);
+                      }
                     }
                   }
-                }
-                umma_commit_pair(empty0 + 8 * stage, 0x3);
-                if (++stage == S) {
-                  stage = 0;
-                  ++use;
+                  umma_commit_pair(empty0 + 8 * stage, 0x3);
+                  if (++stage == S) {
+                    stage = 0;
+                    ++use;
+                  }
                 }
               }
+              umma_commit_pair(tmem_full + 8 * buf, 0x3);
+              if (!DUO) ++chunk;
             }
-            umma_commit_pair(tmem_full + 8 * buf, 0x3);
+            if (DUO) ++chunk;
           }
         }
       }
     }
     __syncwarp();
   } else {
-    // ===================== gate epilogue (warps 2-5) of this CTA's row tile =====================
+    // ===================== gate epilogue of this CTA's row tile (DUO: warps 2-5 forward, 6-9 reverse recurrence) =====
+    const int rec = DUO ? (warp - 2) >> 2 : 0;
     const int quad = warp & 3;  // tcgen05.ld lane rule: a warp touches TMEM lanes [32 * (warp % 4), +32)
     const int row = quad * 32 + lane;
     const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t remote_empty = mapa_u32(tmem_empty, 0);
-    const float* bz = bias_s + (cluster_id & 1) * 4 * 256;  // every item of this cluster has the same direction
+    // non-DUO: every item of this cluster has the same direction (even cluster count)
+    const int d = DUO ? rec : (cluster_id & 1);
+    const float* bz = bias_s + d * 4 * 256;
+    if constexpr (DUO) {
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
+      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + rec * 256, ub, bz, ub * 16);  // unit-chunk 0
+    } else {
 #pragma unroll
-      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + b * 256, ub, bz, b * 64 + ub * 16);
+      for (int b = 0; b < 2; ++b) {
+#pragma unroll
+        for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + b * 256, ub, bz, b * 64 + ub * 16);
+      }
     }
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive_remote(remote_empty);
-      mbar_arrive_remote(remote_empty + 8);
+      if (DUO) {
+        mbar_arrive_remote(remote_empty + 8 * rec);
+      } else {
+        mbar_arrive_remote(remote_empty);
+        mbar_arrive_remote(remote_empty + 8);
+      }
     }
     uint32_t chunk = 0;
     for (int item = cluster_id; item < n_items; item += n_clusters) {
-      const int pair = item >> 1, d = item & 1;
-      const int64_t tile = 2 * (int64_t)pair + rank;
+      const int64_t tile = 2 * (int64_t)(DUO ? item : item >> 1) + rank;
       for (int s = 0; s < L; ++s) {
         const int t = d ? (L - 1 - s) : s;
         const int tprev = d ? t + 1 : t - 1;
@@ -2066,7 +2102,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS
             else
               hpl[q] = make_uint4(0, 0, 0, 0);
           }
-          const uint32_t buf = chunk & 1, u = chunk >> 1;
+          const uint32_t buf = DUO ? (uint32_t)rec : (chunk & 1), u = DUO ? chunk : (chunk >> 1);
+          const int jnext = DUO ? ((j + 1) & 3) : ((j + 2) & 3);  // the unit-chunk that uses this buffer next
           const uint32_t trow = trow0 + buf * 256;
           mbar_wait(tmem_full + 8 * buf, u & 1);
           tc_fence_after();
@@ -2082,7 +2119,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS
 #pragma unroll
               for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(sb + 1) & 1][g]);
             }
-            arm_bias8(trow, col, bz, ((j + 2) & 3) * 64 + col);  // biases of the unit-chunk that uses this buffer next
+            arm_bias8(trow, col, bz, jnext * 64 + col);
             float hp[8], hn[8];
             if constexpr (C8) join8_c8(hph[sb], make_uint2(hpl[sb].x, hpl[sb].y), hp);
             else join8<P, F16>(hph[sb], hpl[sb], hp);
@@ -2124,7 +2161,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P>::THREADS
           __syncwarp();
           if (lane == 0) {
             mbar_arrive_remote(remote_empty + 8 * buf);
-            if (j == 3) mbar_arrive(h_ready);
+            if (j == 3) mbar_arrive(h_ready + 8 * rec);
           }
         }
       }
@@ -2712,9 +2749,9 @@ static int gru_variant(int layer, int P) {
   }
   const int forced = v[layer == 0 ? 0 : 1];
   if (forced >= 0) return forced;
-  // Defaults = the pipelined-epilogue forms (profiles/r01_variants.md): layers >= 1 -> d (variant 2 + PIPE); layer 0 ->
+  // Defaults: layers >= 1 -> n (CTA-pair kernel with tensor-map loads, profiles/r02_bound.md section 9); layer 0 ->
   // l (8 epilogue warps + PIPE, both directions of a row tile interleaved in one CTA: profiles/r02_bound.md section 7).
-  return layer > 0 ? 13 : 21;
+  return layer > 0 ? 23 : 21;
 }
 
 template <int P, bool F16, int NSLOT, int NBUF, int KSB, int EPIW = 1, bool MC = false, bool HS = false, bool PIPE = false,
@@ -2873,28 +2910,48 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
       const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;
       if (variant == 18) tc_gru_cv_kernel<1><<<grid, CvCfg<1>::THREADS, CvCfg<1>::SMEM, st>>>(gp);
       else tc_gru_cv_kernel<2><<<grid, CvCfg<2>::THREADS, CvCfg<2>::SMEM, st>>>(gp);
-    } else if (variant == 23 && l > 0) {
-      // pair2 kernel: CTA pairs, tensor-map loads completing on the leader's barrier
+    } else if ((variant == 23 && l > 0) || variant == 24) {
+      // pair2 kernel: CTA pairs, tensor-map loads completing on the leader's barrier (24 = both directions interleaved)
       gp.wimg = T.wpair[l].as<uint8_t>();
+      const bool duo = variant == 24;
+      constexpr int KSP = Pair2Cfg<P, false>::KS;
+      const int kx = (int)T.kx_slabs[l];
+      if (!duo && kx < KSP) {
+        set_error("GRU kernel variant n needs K_in >= %d (layers >= 1)", KSP * 8);
+        return CCSM_EINVAL;
+      }
       static bool p2_attr = false;
       if (!p2_attr) {
-        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Pair2Cfg<P>::SMEM));
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Pair2Cfg<P, false>::SMEM));
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Pair2Cfg<P, true>::SMEM));
         p2_attr = true;
       }
+      const bool x_short = kx < KSP;
+      const uint64_t x_slabs = x_short ? (uint64_t)tiles * L * P * 2 : (uint64_t)tiles * L * 8 * P * 8;
       const uint64_t act_slabs = (uint64_t)tiles * L * 8 * P * 8, h0_slabs = (uint64_t)tiles * 2 * 4 * P * 8;
-      CUtensorMap tm_w, tm_x, tm_o, tm_h0;
-      if (make_slab_tmap(&tm_w, gp.wimg, GH_SLAB, (uint64_t)8 * (2 * P * 64 + 2 * P * 32), Pair2Cfg<P>::KS) ||
-          make_slab_tmap(&tm_x, gp.xin, A_SLAB, act_slabs, Pair2Cfg<P>::KS) ||
-          make_slab_tmap(&tm_o, gp.out, A_SLAB, act_slabs, Pair2Cfg<P>::KS) ||
-          make_slab_tmap(&tm_h0, gp.h0img, A_SLAB, h0_slabs, Pair2Cfg<P>::KS)) {
+      const uint64_t w_slabs = (uint64_t)8 * (2 * P * kx + 2 * P * 32);
+      const uint32_t xbox = x_short ? (uint32_t)kx : (uint32_t)KSP;
+      CUtensorMap tm_w, tm_x, tm_o, tm_h0, tm_wx, tm_xs;
+      if (make_slab_tmap(&tm_w, gp.wimg, GH_SLAB, w_slabs, KSP) || make_slab_tmap(&tm_wx, gp.wimg, GH_SLAB, w_slabs, xbox) ||
+          make_slab_tmap(&tm_x, gp.xin, A_SLAB, x_slabs, xbox) || make_slab_tmap(&tm_xs, gp.xin, A_SLAB, x_slabs, xbox) ||
+          make_slab_tmap(&tm_o, gp.out, A_SLAB, act_slabs, KSP) || make_slab_tmap(&tm_h0, gp.h0img, A_SLAB, h0_slabs, KSP)) {
         set_error("cuTensorMapEncodeTiled failed (pair2 GRU kernel)");
         return CCSM_ECUDA;
       }
-      const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
       const int64_t max_clusters = T.sm_count / 2;
-      const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;  // even: fixed direction per cluster
-      tc_gru_pair2_kernel<P, F16, C8><<<2 * clusters, Pair2Cfg<P>::THREADS, Pair2Cfg<P>::SMEM, st>>>(gp, tm_w, tm_x, tm_o, tm_h0);
+      if (duo) {
+        const int64_t items = tiles / 2;
+        const int clusters = (int)(items < max_clusters ? items : max_clusters);
+        tc_gru_pair2_kernel<P, F16, C8, true><<<2 * clusters, Pair2Cfg<P, true>::THREADS, Pair2Cfg<P, true>::SMEM, st>>>(
+            gp, tm_w, tm_x, tm_o, tm_h0, tm_wx, tm_xs);
+      } else {
+        const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
+        const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;  // even: fixed direction per cluster
+        tc_gru_pair2_kernel<P, F16, C8, false><<<2 * clusters, Pair2Cfg<P, false>::THREADS, Pair2Cfg<P, false>::SMEM, st>>>(
+            gp, tm_w, tm_x, tm_o, tm_h0, tm_wx, tm_xs);
+      }
     } else if (variant == 16) {
       // duo kernel: CTA pairs, both directions interleaved; one cluster per TPC
       gp.wimg = T.wpair[l].as<uint8_t>();
