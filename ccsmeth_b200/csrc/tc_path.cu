@@ -1853,7 +1853,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DUO_THREADS, 1) tc_g
 // Work item = (pair of row tiles, direction); the cluster count is even, so a cluster keeps one direction.
 // Layers >= 1 only (K_in = 512: every stage is full).  Weight image: the CTA-pair layout of tc_gru_pair_kernel.
 // ------------------------------------------------------------------------------------------------
-template <int P, bool DUO>
+template <int P, int MODE>
 struct Pair2Cfg {
   static constexpr int KS = 8 / P;
   static constexpr int STAGES = 7;
@@ -1861,26 +1861,30 @@ struct Pair2Cfg {
   static constexpr uint32_t A_PART = KS * A_SLAB;
   static constexpr uint32_t STAGE = P * (B_PART + A_PART);  // 28672
   static constexpr uint32_t SMEM = STAGES * STAGE + 2 * 4 * 256 * 4;
-  static constexpr int EPI_WARPS = DUO ? 8 : 4;
+  static constexpr int EPI_WARPS = MODE ? 8 : 4;
   static constexpr int CORE_WARPS = 2 + EPI_WARPS;
   static constexpr int THREADS = 32 * (CORE_WARPS + 2 * P - 1);
 };
 
-// DUO = false: work item = (pair of row tiles, direction), the two TMEM buffers alternate chunk by chunk (layers >= 1).
-// DUO = true:  work item = pair of row tiles, BOTH directions as two recurrences that alternate chunk by chunk (F0 R0 F1 R1
-//              ...), recurrence d on TMEM buffer d with its own four epilogue warps -- layer 0, where nothing else hides the
-//              h_t round trip at a step boundary; its K = 16 input part is one short stage (two slabs, 3-pass form).
-template <int P, bool F16, bool C8, bool DUO>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::THREADS, 1)
+// MODE 0: work item = (pair of row tiles, direction), the two TMEM buffers alternate chunk by chunk (layers >= 1).
+// MODE 1: work item = pair of row tiles, BOTH directions as two recurrences that alternate chunk by chunk (F0 R0 F1 R1
+//         ...), recurrence d on TMEM buffer d with its own four epilogue warps.
+// MODE 2: both directions in the order of tc_gru_layer_kernel's IL form (F0 F1 R0 R1 F2 F3 R2 R3), the two TMEM buffers
+//         alternating chunk by chunk, eight epilogue warps that each take half of a chunk's units.
+// Modes 1 / 2 are meant for layer 0, where nothing else hides the h_t round trip at a step boundary; its K = 16 input part is
+// one short stage (two slabs, 3-pass form).
+template <int P, bool F16, bool C8, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, MODE>::THREADS, 1)
     tc_gru_pair2_kernel(const GruParams p, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                         const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_h0,
                         const __grid_constant__ CUtensorMap tm_wx, const __grid_constant__ CUtensorMap tm_xs) {
   static_assert(!C8 || (P == 2 && F16), "C8: fp16 images");
-  using C = Pair2Cfg<P, DUO>;
+  using C = Pair2Cfg<P, MODE>;
+  constexpr bool DUO = MODE != 0;  // both directions in one item
+  constexpr int NCH = DUO ? 8 : 4;  // unit-chunks per step of an item
   constexpr int KS = C::KS;
   constexpr bool FAST = (P == 1);
   constexpr int S = C::STAGES;
-  constexpr int ND = DUO ? 2 : 1;  // recurrences per item
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 * S + 6];
   __shared__ uint32_t tmem_base_s;
@@ -1898,8 +1902,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::TH
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, 8);  // one arrival per epilogue warp (of the buffer's recurrence) of both CTAs
-      mbar_init(h_ready + 8 * i, 4);     // DUO: one per recurrence
+      mbar_init(tmem_empty + 8 * i, MODE == 2 ? 16 : 8);  // one arrival per epilogue warp working on the buffer, both CTAs
+      mbar_init(h_ready + 8 * i, MODE == 2 ? 8 : 4);      // DUO: one per recurrence
     }
     fence_barrier_init();
   }
@@ -1939,8 +1943,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::TH
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int64_t tile = 2 * (int64_t)(DUO ? item : item >> 1) + rank;
         for (int s = 0; s < L; ++s, ++gstep) {
-          for (int j = 0; j < 4; ++j) {
-            for (int dd = 0; dd < ND; ++dd) {
+          for (int c = 0; c < NCH; ++c) {
+            {
+              const int dd = MODE == 0 ? 0 : MODE == 1 ? (c & 1) : il_d(c);
+              const int j = MODE == 0 ? c : MODE == 1 ? (c >> 1) : il_j(c);
               const int d = DUO ? dd : (item & 1);
               const int t = d ? (L - 1 - s) : s;
               const int tprev = d ? t + 1 : t - 1;
@@ -1997,9 +2003,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::TH
       uint32_t stage = 0, use = 0, chunk = 0;  // chunk: per TMEM buffer pair (non-DUO: every chunk; DUO: per recurrence)
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         for (int s = 0; s < L; ++s) {
-          for (int j = 0; j < 4; ++j) {
-            for (int dd = 0; dd < ND; ++dd) {
-              const uint32_t buf = DUO ? (uint32_t)dd : (chunk & 1), u = DUO ? chunk : (chunk >> 1);
+          for (int c = 0; c < NCH; ++c) {
+            {
+              // MODE 1: buffer = recurrence, chunk counts (s, j) pairs; otherwise the buffers alternate chunk by chunk
+              const uint32_t buf = MODE == 1 ? (uint32_t)(c & 1) : (chunk & 1), u = MODE == 1 ? chunk : (chunk >> 1);
               mbar_wait(tmem_empty + 8 * buf, u & 1);  // completion #u: #0 = initial arming, #k = drain of use k-1
               tc_fence_after();
               const uint32_t dcol = tmem + buf * 256;
@@ -2039,39 +2046,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::TH
                 }
               }
               umma_commit_pair(tmem_full + 8 * buf, 0x3);
-              if (!DUO) ++chunk;
+              if (MODE != 1 || (c & 1)) ++chunk;
             }
-            if (DUO) ++chunk;
           }
         }
       }
     }
     __syncwarp();
   } else {
-    // ===================== gate epilogue of this CTA's row tile (DUO: warps 2-5 forward, 6-9 reverse recurrence) =====
-    const int rec = DUO ? (warp - 2) >> 2 : 0;
+    // ===================== gate epilogue of this CTA's row tile =====================
+    // MODE 0: warps 2-5, every chunk.  MODE 1: warps 2-5 the forward, 6-9 the reverse recurrence.  MODE 2: warps 2-9, every
+    // chunk, warps 2-5 the first 32 units of a chunk and 6-9 the last 32.
+    const int grp = (warp - 2) >> 2;
+    const int rec = MODE == 1 ? grp : 0;
+    constexpr int NSB = MODE == 2 ? 4 : 8;           // 8-unit sub-blocks per thread and chunk
+    const int sb0 = MODE == 2 ? grp * 4 : 0;
     const int quad = warp & 3;  // tcgen05.ld lane rule: a warp touches TMEM lanes [32 * (warp % 4), +32)
     const int row = quad * 32 + lane;
     const uint32_t trow0 = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t remote_empty = mapa_u32(tmem_empty, 0);
-    // non-DUO: every item of this cluster has the same direction (even cluster count)
-    const int d = DUO ? rec : (cluster_id & 1);
-    const float* bz = bias_s + d * 4 * 256;
-    if constexpr (DUO) {
+    // MODE 0: every item of this cluster has the same direction (even cluster count)
+    const int d_fixed = MODE == 1 ? rec : (MODE == 0 ? (cluster_id & 1) : 0);
+    if constexpr (MODE == 1) {
 #pragma unroll
-      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + rec * 256, ub, bz, ub * 16);  // unit-chunk 0
+      for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + rec * 256, ub, bias_s + d_fixed * 1024, ub * 16);  // unit-chunk 0
     } else {
+      // buffers 0 / 1 <- unit-chunks 0 / 1 of the (first) direction
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
 #pragma unroll
-        for (int ub = 0; ub < 4; ++ub) arm_bias16(trow0 + b * 256, ub, bz, b * 64 + ub * 16);
+        for (int q = 0; q < NSB; ++q) arm_bias8(trow0 + b * 256, (sb0 + q) * 8, bias_s + d_fixed * 1024, b * 64 + (sb0 + q) * 8);
       }
     }
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      if (DUO) {
+      if (MODE == 1) {
         mbar_arrive_remote(remote_empty + 8 * rec);
       } else {
         mbar_arrive_remote(remote_empty);
@@ -2082,57 +2093,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::TH
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int64_t tile = 2 * (int64_t)(DUO ? item : item >> 1) + rank;
       for (int s = 0; s < L; ++s) {
-        const int t = d ? (L - 1 - s) : s;
-        const int tprev = d ? t + 1 : t - 1;
-        for (int j = 0; j < 4; ++j, ++chunk) {
+        for (int c = 0; c < (MODE == 2 ? 8 : 4); ++c, ++chunk) {
+          const int d = MODE == 2 ? il_d(c) : d_fixed;
+          const int j = MODE == 2 ? il_j(c) : c;
+          const int t = d ? (L - 1 - s) : s;
+          const int tprev = d ? t + 1 : t - 1;
+          // the unit-chunk that uses this accumulator buffer next, and its direction's biases
+          const int cn = (c + 2) & 7;
+          const int jnext = MODE == 0 ? ((j + 2) & 3) : MODE == 1 ? ((j + 1) & 3) : il_j(cn);
+          const float* bz = bias_s + (MODE == 2 ? il_d(cn) : d_fixed) * 1024;
           const uint8_t* hp_base =
               (s == 0) ? p.h0img + (((tile * 2 + d) * 4 + j) * P) * (size_t)CHUNK_BYTES
                        : p.out + (((tile * L + tprev) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
           uint8_t* out_base = p.out + (((tile * L + t) * 8 + d * 4 + j) * P) * (size_t)CHUNK_BYTES;
-          // prefetch h_{t_prev} of this row's 64 units (the L2 latency overlaps the chunk's MMAs)
-          uint4 hph[8], hpl[8];
+          // prefetch h_{t_prev} of this row's units (the L2 latency overlaps the chunk's MMAs)
+          uint4 hph[NSB], hpl[NSB];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + q * A_SLAB + row * 16));
+          for (int q = 0; q < NSB; ++q) {
+            hph[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + (sb0 + q) * A_SLAB + row * 16));
             if constexpr (C8) {
-              const uint2 t8 = __ldcg(reinterpret_cast<const uint2*>(hp_base + CHUNK_BYTES + 4096 + c8_off(q) + row * 16));
+              const uint2 t8 = __ldcg(reinterpret_cast<const uint2*>(hp_base + CHUNK_BYTES + 4096 + c8_off(sb0 + q) + row * 16));
               hpl[q] = make_uint4(t8.x, t8.y, 0, 0);
             } else if constexpr (P == 2)
-              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + q * A_SLAB + row * 16));
+              hpl[q] = __ldcg(reinterpret_cast<const uint4*>(hp_base + CHUNK_BYTES + (sb0 + q) * A_SLAB + row * 16));
             else
               hpl[q] = make_uint4(0, 0, 0, 0);
           }
-          const uint32_t buf = DUO ? (uint32_t)rec : (chunk & 1), u = DUO ? chunk : (chunk >> 1);
-          const int jnext = DUO ? ((j + 1) & 3) : ((j + 2) & 3);  // the unit-chunk that uses this buffer next
+          const uint32_t buf = MODE == 1 ? (uint32_t)rec : (chunk & 1), u = MODE == 1 ? chunk : (chunk >> 1);
           const uint32_t trow = trow0 + buf * 256;
           mbar_wait(tmem_full + 8 * buf, u & 1);
           tc_fence_after();
           uint32_t acc[2][4][8];  // [ping-pong][n_i, r, z, n_h][8 units]
           uint2 a8_even = make_uint2(0, 0), l8_even = make_uint2(0, 0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64, acc[0][g]);
+          for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + sb0 * 8, acc[0][g]);
 #pragma unroll
-          for (int sb = 0; sb < 8; ++sb) {
+          for (int q = 0; q < NSB; ++q) {
+            const int sb = sb0 + q;
             const int col = sb * 8;
-            tmem_ld_wait();  // sub-block sb has landed (issued one iteration ago)
-            if (sb + 1 < 8) {
+            tmem_ld_wait();  // sub-block q has landed (issued one iteration ago)
+            if (q + 1 < NSB) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(sb + 1) & 1][g]);
+              for (int g = 0; g < 4; ++g) tmem_ld8(trow + g * 64 + col + 8, acc[(q + 1) & 1][g]);
             }
             arm_bias8(trow, col, bz, jnext * 64 + col);
             float hp[8], hn[8];
-            if constexpr (C8) join8_c8(hph[sb], make_uint2(hpl[sb].x, hpl[sb].y), hp);
-            else join8<P, F16>(hph[sb], hpl[sb], hp);
+            if constexpr (C8) join8_c8(hph[q], make_uint2(hpl[q].x, hpl[q].y), hp);
+            else join8<P, F16>(hph[q], hpl[q], hp);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               float r, z;
               if constexpr (C8) {
-                sigmoid2_s(__uint_as_float(acc[sb & 1][1][i]), __uint_as_float(acc[sb & 1][2][i]), r, z);
+                sigmoid2_s(__uint_as_float(acc[q & 1][1][i]), __uint_as_float(acc[q & 1][2][i]), r, z);
               } else {
-                r = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][1][i]));
-                z = sig_<FAST, C8>(__uint_as_float(acc[sb & 1][2][i]));
+                r = sig_<FAST, C8>(__uint_as_float(acc[q & 1][1][i]));
+                z = sig_<FAST, C8>(__uint_as_float(acc[q & 1][2][i]));
               }
-              const float n = tnh_<FAST, C8>(fmaf(r, __uint_as_float(acc[sb & 1][3][i]), __uint_as_float(acc[sb & 1][0][i])));
+              const float n = tnh_<FAST, C8>(fmaf(r, __uint_as_float(acc[q & 1][3][i]), __uint_as_float(acc[q & 1][0][i])));
               hn[i] = fmaf(z, hp[i] - n, n);  // (1 - z) * n + z * h
             }
             if constexpr (C8) {
@@ -2140,7 +2157,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::TH
               uint2 a8, l8;
               split8_c8(hn, hi, a8, l8);
               *reinterpret_cast<uint4*>(out_base + sb * A_SLAB + row * 16) = hi;
-              if ((sb & 1) == 0) {
+              if ((q & 1) == 0) {
                 a8_even = a8;
                 l8_even = l8;
               } else {
@@ -2161,7 +2178,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2Cfg<P, DUO>::TH
           __syncwarp();
           if (lane == 0) {
             mbar_arrive_remote(remote_empty + 8 * buf);
-            if (j == 3) mbar_arrive(h_ready + 8 * rec);
+            if (j == 3) mbar_arrive(h_ready + 8 * (MODE == 0 ? 0 : d));
           }
         }
       }
@@ -2910,22 +2927,20 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
       const int grid = (int)(items < T.sm_count ? items : T.sm_count) & ~1;
       if (variant == 18) tc_gru_cv_kernel<1><<<grid, CvCfg<1>::THREADS, CvCfg<1>::SMEM, st>>>(gp);
       else tc_gru_cv_kernel<2><<<grid, CvCfg<2>::THREADS, CvCfg<2>::SMEM, st>>>(gp);
-    } else if ((variant == 23 && l > 0) || variant == 24) {
+    } else if (variant == 23 || variant == 24 || variant == 25) {
       // pair2 kernel: CTA pairs, tensor-map loads completing on the leader's barrier (24 = both directions interleaved)
       gp.wimg = T.wpair[l].as<uint8_t>();
-      const bool duo = variant == 24;
-      constexpr int KSP = Pair2Cfg<P, false>::KS;
+      const bool duo = variant != 23;
+      constexpr int KSP = Pair2Cfg<P, 0>::KS;
       const int kx = (int)T.kx_slabs[l];
-      if (!duo && kx < KSP) {
-        set_error("GRU kernel variant n needs K_in >= %d (layers >= 1)", KSP * 8);
-        return CCSM_EINVAL;
-      }
       static bool p2_attr = false;
       if (!p2_attr) {
-        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Pair2Cfg<P, false>::SMEM));
-        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Pair2Cfg<P, true>::SMEM));
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Pair2Cfg<P, 0>::SMEM));
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Pair2Cfg<P, 1>::SMEM));
+        CCSM_CUDA(cudaFuncSetAttribute(tc_gru_pair2_kernel<P, F16, C8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Pair2Cfg<P, 2>::SMEM));
         p2_attr = true;
       }
       const bool x_short = kx < KSP;
@@ -2944,12 +2959,16 @@ static int tc_run_chunk(ccsm_model* m, int64_t sites, int64_t site0, int64_t n_t
       if (duo) {
         const int64_t items = tiles / 2;
         const int clusters = (int)(items < max_clusters ? items : max_clusters);
-        tc_gru_pair2_kernel<P, F16, C8, true><<<2 * clusters, Pair2Cfg<P, true>::THREADS, Pair2Cfg<P, true>::SMEM, st>>>(
-            gp, tm_w, tm_x, tm_o, tm_h0, tm_wx, tm_xs);
+        if (variant == 24)
+          tc_gru_pair2_kernel<P, F16, C8, 1><<<2 * clusters, Pair2Cfg<P, 1>::THREADS, Pair2Cfg<P, 1>::SMEM, st>>>(
+              gp, tm_w, tm_x, tm_o, tm_h0, tm_wx, tm_xs);
+        else
+          tc_gru_pair2_kernel<P, F16, C8, 2><<<2 * clusters, Pair2Cfg<P, 2>::THREADS, Pair2Cfg<P, 2>::SMEM, st>>>(
+              gp, tm_w, tm_x, tm_o, tm_h0, tm_wx, tm_xs);
       } else {
         const int64_t items = tiles;  // (tiles / 2) pairs x 2 directions
         const int clusters = (int)(items < max_clusters ? items : max_clusters) & ~1;  // even: fixed direction per cluster
-        tc_gru_pair2_kernel<P, F16, C8, false><<<2 * clusters, Pair2Cfg<P, false>::THREADS, Pair2Cfg<P, false>::SMEM, st>>>(
+        tc_gru_pair2_kernel<P, F16, C8, 0><<<2 * clusters, Pair2Cfg<P, 0>::THREADS, Pair2Cfg<P, 0>::SMEM, st>>>(
             gp, tm_w, tm_x, tm_o, tm_h0, tm_wx, tm_xs);
       }
     } else if (variant == 16) {

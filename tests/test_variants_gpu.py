@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (layer 0, layers >= 1): d / e = one direction per CTA (4 / 8 epilogue warps), k / l / m = both directions of a row tile
 # interleaved (4 / 8 / 16 epilogue warps), h = two CTAs per SM, f = two row tiles per CTA, g = CTA pair (cta_group::2),
 # i / j = fp16c8 with on-chip operand conversion, 3 = round 1's CTA-pair kernel (not in fp16c8), n = CTA pair with tensor-map
-# loads (layers >= 1; the default there), o = the same with both directions interleaved (any layer)
-VARIANTS = ["dd", "ee", "kk", "ll", "md", "hf", "gd", "ij", "c3", "ln", "oo", "on"]
+# loads (the default for layers >= 1), o / p = the same with both directions interleaved (per-recurrence buffers / IL order)
+VARIANTS = ["dd", "ee", "kk", "ll", "md", "hf", "gd", "ij", "c3", "ln", "oo", "pn", "nn"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
