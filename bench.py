@@ -184,7 +184,7 @@ def gru_roofline(prof, prec, peaks):
         if prof[k][0] > 0:
             tf = prof[k][1] * fl / (prof[k][0] * 1e-3) / 1e12
             per[k] = {"ms": round(prof[k][0], 3), "launches": prof[k][2], "tflops": tf, "frac": tf / peaks["bf16_tflops"]}
-    return {"bound": "tensor", "kernel": "tc_gru_layer_kernel<%s>" % prec, "achieved": ach,
+    return {"bound": "tensor", "kernel": "GRU layer launches <%s>: tc_gru_layer_kernel (layer 0) + tc_gru_pair2_kernel (layers 1-2)" % prec, "achieved": ach,
             "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
             "traffic": traffic, "traffic_source": tsrc, "flop_per_launch": g_flop / g_launch,
             "ms_per_launch": g_ms / g_launch, "launches": g_launch, "share_of_step": g_ms / tot_ms,
