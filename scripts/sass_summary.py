@@ -60,8 +60,8 @@ def main():
                 % (hashlib.sha256(open(so, "rb").read()).hexdigest(), _lib.source_hash()))
         f.write("* `cuobjdump -sass`, %d kernels; totals: %s\n\n" % (len(kernels), ", ".join("%s %d" % (k, tot[k]) for k in MNEMONICS)))
         f.write("tcgen05.mma -> `UTCHMMA` (kind::f16) / `UTCQMMA` (kind::f8f6f4, the e4m3 correction passes of fp16c8); "
-                "tcgen05.ld / st -> `LDTM` / `STTM`; cp.async.bulk -> `UBLKCP` (1-D bulk copies of pre-tiled images: no tensor "
-                "maps, hence no `UTMALDG`); tcgen05.commit -> `UTCBAR`; mbarrier -> `SYNCS`.  `HMMA` (legacy mma.sync) must be 0.\n\n")
+                "tcgen05.ld / st -> `LDTM` / `STTM`; cp.async.bulk -> `UBLKCP` (1-D bulk copies of pre-tiled images); "
+                "cp.async.bulk.tensor -> `UTMALDG` (the CTA-pair kernel's tensor-map loads, .cta_group::2); tcgen05.commit -> `UTCBAR`; mbarrier -> `SYNCS`.  `HMMA` (legacy mma.sync) must be 0.\n\n")
         f.write("| kernel | instr | " + " | ".join(MNEMONICS) + " |\n|---|---:|" + "---:|" * len(MNEMONICS) + "\n")
         for k, c in sorted(kernels.items(), key=lambda kv: -(kv[1]["UTCHMMA"] + kv[1]["UTCQMMA"]) * 100000 - kv[1]["_instr"]):
             nm = names[k].replace("ccsm::", "")
