@@ -3,7 +3,8 @@
 //
 // Reference behaviour restated here (all under /root/reference/ccsmeth/):
 //   extract_features.py:261-406   extract_features_from_double_strand_read (site selection and windows)
-//   extract_features.py:181-199   _normalize_signals (np.mean / population np.std / np.around(6), float64)
+//   extract_features.py:181-199   _normalize_signals (np.mean / population np.std / np.around(6), float64; "mad" = np.median
+//                                 and statsmodels 0.14 robust.scale.mad, restated from its published formula)
 //   utils/process_utils.py:426-449 CodecV1 code -> frames
 //   utils/process_utils.py:122-137 get_refloc_of_methysite_in_motif
 //   call_modifications.py:73-123  _batch_feature_list2s (base codes, npass broadcast over the window)
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) read_scan_kernel(ExParams P, SigStat* __r
   const ccsm_read r = P.reads[r_idx];
   __shared__ long long s_sum[8], s_sq[8];
   __shared__ int s_min[8], s_max[8], s_cnt[8];
+  __shared__ int s_hist[256];  // --norm mad: occurrences of every kinetics code in the read (the codes are bytes)
   __shared__ __align__(16) uint8_t s_codes[SEQ_TILE + SEQ_HALO + 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int sig = 0; sig < 4; ++sig) {
@@ -137,7 +139,12 @@ __global__ void __launch_bounds__(256) read_scan_kernel(ExParams P, SigStat* __r
     const int64_t off = sig == 0 ? r.fi_off : sig == 1 ? r.ri_off : sig == 2 ? r.fp_off : r.rp_off;
     long long S = 0, Q = 0;
     int mn = 1 << 30, mx = -1;
-    if (P.norm != CCSM_NORM_NONE) {
+    if (P.norm == CCSM_NORM_MAD) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+      __syncthreads();
+      const uint8_t* a = P.blob + off;
+      for (int i = threadIdx.x; i < r.len; i += blockDim.x) atomicAdd(&s_hist[a[i]], 1);
+    } else if (P.norm != CCSM_NORM_NONE) {
       // 16-byte loads over the aligned span covering [off, off + len); only the two end chunks are masked
       // (the blob allocation is 16-byte aligned and padded by 16 bytes)
       const uint8_t* a = P.blob + off;
@@ -183,6 +190,41 @@ __global__ void __launch_bounds__(256) read_scan_kernel(ExParams P, SigStat* __r
       } else if (P.norm == CCSM_NORM_MINMAX) {
         st.shift = (double)mnt;
         st.scale = (double)(mxt - mnt);
+      } else if (P.norm == CCSM_NORM_MAD && r.len > 0) {
+        // np.median and statsmodels.robust.scale.mad (0.14: median(|a - median(a)| / c), c = Gaussian.ppf(3/4), float64)
+        // from the 256-bin histogram: the code -> value map is increasing, so code order is value order
+        const int k1 = (r.len - 1) >> 1, k2 = r.len >> 1;  // the middle element(s), 0-based
+        int v1 = -1, v2 = -1, c2 = 0, cum = 0;
+        for (int c = 0; c < 256 && v2 < 0; ++c) {
+          const int cnt = s_hist[c];
+          if (!cnt) continue;
+          const int v = P.decode ? code_to_frames(c) : c;
+          if (v1 < 0 && cum + cnt > k1) v1 = v;
+          if (cum + cnt > k2) { v2 = v; c2 = c; }
+          cum += cnt;
+        }
+        const double med = v1 == v2 ? (double)v1 : __ddiv_rn((double)(v1 + v2), 2.0);
+        // |value - med| is V-shaped over the codes: merge the two sorted arms (downwards from the median, upwards above it)
+        int li = c2, ri = c2 + 1;
+        while (li >= 0 && (double)(P.decode ? code_to_frames(li) : li) > med) --li;  // even n: c2 is the upper middle
+        ri = li + 1;
+        double d1 = -1.0, d2 = -1.0;
+        cum = 0;
+        while ((li >= 0 || ri < 256) && d2 < 0.0) {
+          const double dl = li >= 0 ? med - (double)(P.decode ? code_to_frames(li) : li) : 1e300;
+          const double dr = ri < 256 ? (double)(P.decode ? code_to_frames(ri) : ri) - med : 1e300;
+          double d;
+          int cnt;
+          if (dl <= dr) { d = dl; cnt = s_hist[li]; --li; } else { d = dr; cnt = s_hist[ri]; ++ri; }
+          if (!cnt) continue;
+          if (d1 < 0.0 && cum + cnt > k1) d1 = d;
+          if (cum + cnt > k2) d2 = d;
+          cum += cnt;
+        }
+        const double c = 0.6744897501960817;
+        const double x1 = __ddiv_rn(d1, c), x2 = __ddiv_rn(d2, c);
+        st.shift = med;
+        st.scale = d1 == d2 ? x1 : __ddiv_rn(__dadd_rn(x1, x2), 2.0);
       } else {
         st.shift = 0.0;
         st.scale = 1.0;
@@ -527,7 +569,7 @@ int ccsm_reads_extract_host(ccsm_model* m, const ccsm_extract_opts* o, const uin
     return CCSM_EINVAL;
   }
   if (o->n_motifs < 1 || o->n_motifs > 8 || o->motif_len < 1 || o->motif_len > 8 || o->mod_loc < 0 ||
-      o->mod_loc >= o->motif_len || o->norm < CCSM_NORM_ZSCORE || o->norm > CCSM_NORM_NONE) {
+      o->mod_loc >= o->motif_len || o->norm < CCSM_NORM_ZSCORE || o->norm > CCSM_NORM_MAD) {
     set_error("ccsm_reads_extract_host: unsupported options (motifs=%d x %d, mod_loc=%d, norm=%d)", o->n_motifs,
               o->motif_len, o->mod_loc, o->norm);
     return CCSM_EINVAL;

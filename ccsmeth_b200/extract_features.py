@@ -18,7 +18,7 @@ READ_DTYPE = np.dtype([("seq_off", "<i8"), ("fi_off", "<i8"), ("ri_off", "<i8"),
                        ("win_hi", "<i4"), ("sn", "<f4", (4,))], align=True)
 assert READ_DTYPE.itemsize == 80
 READ_REVERSE, READ_SEQ_4BIT = 1, 2
-NORM = {"zscore": 0, "min-mean": 1, "min-max": 2, "none": 3}
+NORM = {"zscore": 0, "min-mean": 1, "min-max": 2, "none": 3, "mad": 4}
 
 
 class ReadBatch:
@@ -125,7 +125,7 @@ def pack_reads(records, args, holeids_e=None, holeids_ne=None):
 def extract_opts(args, motifs):
     """CLI args + expanded motif list -> the fields of `ccsm_extract_opts` (dict)."""
     if args.norm not in NORM:
-        raise ValueError("--norm %s is not supported by ccsmeth_b200 (statsmodels 'mad' is unavailable)" % args.norm)
+        raise ValueError("--norm %s is not one of %s" % (args.norm, sorted(NORM)))
     mlen = len(motifs[0])
     if any(len(m) != mlen for m in motifs):
         raise ValueError("all --motifs must have the same length")

@@ -235,10 +235,13 @@ typedef struct ccsm_read {
   float   sn[4];              /* tag sn (used iff CCSM_FEAT_SN) */
 } ccsm_read;
 
-#define CCSM_NORM_ZSCORE  0    /* --norm, extract_features.py:181-199 ("mad" needs statsmodels: not offered) */
+#define CCSM_NORM_ZSCORE  0    /* --norm, extract_features.py:181-199 */
 #define CCSM_NORM_MINMEAN 1
 #define CCSM_NORM_MINMAX  2
 #define CCSM_NORM_NONE    3
+#define CCSM_NORM_MAD     4    /* shift = np.median, scale = statsmodels.robust.scale.mad (statsmodels 0.14.0, environment.yml:13:
+                                * median(|a - median(a)| / Gaussian.ppf(3/4)); the package is absent from this image, its
+                                * published formula is restated) */
 
 typedef struct ccsm_extract_opts {
   int32_t mod_loc;            /* --mod_loc */

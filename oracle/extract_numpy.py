@@ -6,7 +6,7 @@ extractor run on the demo BAM (tests/golden/demo_callmods.npz, scripts/gen_golde
 
 Mirrors ``extract_features_from_double_strand_read`` (reference ccsmeth/extract_features.py:261-406) for the
 call_mods defaults (``--mode denovo|align`` site selection without ``--is_map``, ``--motifs CG``-style symmetric
-motifs, ``--norm zscore|none|min-max|min-mean``, CodecV1 decode unless ``--no_decode``): per read, decode the
+motifs, ``--norm zscore|none|min-max|min-mean|mad``, CodecV1 decode unless ``--no_decode``): per read, decode the
 ``fi/ri/fp/rp`` kinetics (process_utils.py:426-449), normalise each over the whole read
 (extract_features.py:181-199), scan the motif, and cut 21-base windows on the forward read and on its reverse
 complement (kinetics of the reverse strand are NOT flipped, :316,319).
@@ -44,6 +44,20 @@ class ReadFeatures:
         return len(self.locs)
 
 
+MAD_C = 0.6744897501960817  # scipy.stats.norm.ppf(3 / 4)
+
+
+def statsmodels_mad(a, c=MAD_C):
+    """statsmodels.robust.scale.mad of a 1-D array (statsmodels 0.14.0, the reference's environment.yml:13; the package
+    is not in this image, so its published formula is restated): float64, ``median(|a - median(a)| / c)`` -- the division
+    comes before the median."""
+    a = np.asarray(a, dtype=np.double)
+    if not a.size:
+        return np.nan
+    center = np.apply_over_axes(np.median, a, 0)
+    return np.median(np.abs(a - center) / c, axis=0)
+
+
 def _normalize_signals(signals, method="zscore"):
     """reference extract_features.py:181-199 (np.mean / population np.std / np.around 6)."""
     if method == "none":
@@ -54,8 +68,10 @@ def _normalize_signals(signals, method="zscore"):
         sshift, sscale = np.min(signals), np.max(signals) - np.min(signals)
     elif method == "min-mean":
         sshift, sscale = np.min(signals), np.mean(signals)
+    elif method == "mad":
+        sshift, sscale = np.median(signals), float(statsmodels_mad(signals))
     else:
-        raise ValueError("--norm %s is not supported by ccsmeth_b200 (statsmodels 'mad' is unavailable)" % method)
+        raise ValueError("--norm %s" % method)
     if sscale == 0.0:
         return np.zeros(len(signals), dtype=np.float64)
     return np.around((signals - sshift) / sscale, decimals=6)

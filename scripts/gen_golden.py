@@ -611,8 +611,36 @@ def gen_freqb():
     np.savez_compressed(os.path.join(d, "reference_outputs.npz"), **texts)
 
 
+def gen_norm_mad():
+    """`--norm mad` through the reference's own _normalize_signals (extract_features.py:181-199).  statsmodels is not in this
+    image: `robust.scale.mad` is provided by oracle.extract_numpy.statsmodels_mad, the restated formula of statsmodels 0.14.0
+    (the reference's environment.yml:13) -- so this fixture pins the reference's code AROUND the call (np.median as the
+    shift, float(), the zero-scale branch, np.around(6)), not statsmodels itself."""
+    import types
+    refimport.import_reference()
+    import ccsmeth.extract_features as ref_ef
+    from oracle.extract_numpy import statsmodels_mad
+    scale = types.ModuleType("statsmodels.robust.scale")
+    scale.mad = statsmodels_mad
+    ref_ef.robust.scale = scale
+    rng = np.random.default_rng(41)
+    out = {}
+    cases = [rng.integers(0, 953, 301), rng.integers(0, 953, 300), rng.integers(0, 60, 4096), np.full(50, 17),
+             np.array([3, 3, 3, 9, 9, 9]), np.array([5]), np.array([1, 2]), rng.integers(0, 4, 1001),
+             np.concatenate([np.full(400, 20), rng.integers(0, 953, 399)])]
+    for i, sig in enumerate(cases):
+        sig = np.asarray(sig, dtype=np.int64)
+        out["sig%d" % i] = sig
+        out["out%d" % i] = np.asarray(ref_ef._normalize_signals(sig, "mad"), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "norm_mad.npz"), **out)
+    print("norm_mad", {k: v.shape for k, v in out.items() if k.startswith("out")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "norm_mad":
+        gen_norm_mad()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "att2s_16k":
         gen_att2s_16k()
         sys.exit(0)

@@ -113,7 +113,7 @@ def test_demo_chunked_feature_ranges(model, reads):
         model.reads_features(n - 5, 10)
 
 
-@pytest.mark.parametrize("norm", ["zscore", "min-mean", "min-max", "none"])
+@pytest.mark.parametrize("norm", ["zscore", "min-mean", "min-max", "none", "mad"])
 @pytest.mark.parametrize("no_decode", [False, True])
 def test_synthetic_reads_every_norm(model, norm, no_decode):
     rng = np.random.default_rng(7)

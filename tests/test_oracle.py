@@ -132,3 +132,21 @@ def test_transenc_numpy_oracle_matches_reference():
                                                  num_layers=2, nhead=4)
     assert np.abs(probs - g["probs"]).max() <= 1e-6
     assert np.abs(logits - g["logits"]).max() <= 1e-5
+
+
+def test_norm_mad_oracle_matches_the_reference_normaliser():
+    """`--norm mad` (reference extract_features.py:181-199 with statsmodels 0.14's robust.scale.mad restated: the package is
+    not in this image).  Fixture: scripts/gen_golden.py norm_mad -- the reference's _normalize_signals around that formula."""
+    from oracle.extract_numpy import _normalize_signals, statsmodels_mad, MAD_C
+    from tests.conftest import load_npz
+    g = load_npz("norm_mad.npz")
+    n = 0
+    while "sig%d" % n in g:
+        out = np.asarray(_normalize_signals(g["sig%d" % n], "mad"), dtype=np.float64)
+        assert np.array_equal(out, g["out%d" % n]), n
+        n += 1
+    assert n == 9
+    # known answers: MAD of 1..9 is 2 (median 5, deviations 0 1 1 2 2 3 3 4 4), scaled by 1 / norm.ppf(3/4)
+    assert statsmodels_mad(np.arange(1, 10)) == 2.0 / MAD_C
+    assert abs(MAD_C - 0.6744897501960817) == 0.0
+    assert np.isnan(statsmodels_mad(np.array([])))
