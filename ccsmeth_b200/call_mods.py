@@ -251,7 +251,9 @@ def call_mods(args):
     if args.model_type in ("attbigru2s2", "attbilstm2s2", "transencoder2s") and args.norm != "none":
         raise ValueError("--model_type %s embeds the kinetics as integers: run it with --norm none" % args.model_type)
     if str2bool(args.is_map) or str2bool(args.is_stds):
-        raise ValueError("--is_map/--is_stds features are not extracted by ccsmeth_b200 (SURVEY.md section 8f)")
+        raise ValueError("--is_map / --is_stds features are not extracted by ccsmeth_b200 (the reference's extractor itself "
+                         "writes '.' for the std columns, extract_features.py:353-364; --is_map needs the reference FASTA walk "
+                         "of extract_features.py:202-258)")
     rank, world, local = parallel.init_from_env()
     TIMING.clear()
     out_dir = os.path.dirname(os.path.abspath(args.output))
