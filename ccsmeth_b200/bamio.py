@@ -413,9 +413,11 @@ class BamWriter:
         self.bg = BgzfWriter(path, level, threads, strategy)
         text = header_text.encode("utf-8")
         self.bg.write(b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(references)))
+        self.header_bytes = 12 + len(text)  # inflated size of everything before the first record
         for name, l_ref in references:
             nm = name.encode("ascii") + b"\x00"
             self.bg.write(struct.pack("<i", len(nm)) + nm + struct.pack("<i", l_ref))
+            self.header_bytes += 8 + len(nm)
 
     def write_raw(self, raw):
         self.bg.write(struct.pack("<i", len(raw)) + raw)

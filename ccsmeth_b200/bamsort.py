@@ -315,14 +315,76 @@ def _block_table(path):
     return np.array(coff, dtype=np.int64), np.array(isz, dtype=np.int64)
 
 
+def _write_bai_for(path, n_refs, c):
+    """.bai of a written BAM from its records' (ref, pos, end, flag, inflated start, inflated end): virtual offsets come
+    from the file's BGZF block table."""
+    coff, isz = _block_table(path)
+    ustart_of_block = np.concatenate(([0], np.cumsum(isz)))
+    data_blk = np.nonzero(isz > 0)[0]           # empty blocks (EOF markers) hold no positions
+    dstart = ustart_of_block[data_blk]
+    eof_coff = int(coff[-1]) if len(coff) and isz[-1] == 0 else int(os.path.getsize(path))
+
+    def voff(u):
+        u = np.asarray(u, dtype=np.int64)
+        j = np.searchsorted(dstart, u, side="right") - 1
+        j = np.clip(j, 0, max(len(data_blk) - 1, 0))
+        inside = u - dstart[j]
+        at_end = inside >= isz[data_blk[j]]          # the end of the last record: the EOF block
+        return np.where(at_end, np.uint64(eof_coff) << np.uint64(16),
+                        (coff[data_blk[j]].astype(np.uint64) << np.uint64(16)) | inside.astype(np.uint64))
+
+    write_bai(path + ".bai", n_refs, c["ref"], c["pos"], c["end"], c["flag"], voff(c["ustart"]), voff(c["uend"]))
+    return len(c["ref"])
+
+
+class StreamIndexer:
+    """index_sorted without reading the file back: the writer feeds the record bytes it is about to write (whole records,
+    in file order), and after the file is closed `finish` writes the .bai -- or reports that the records were not in
+    coordinate order, in which case the caller sorts (call_mods: the output of a sorted or unaligned input is already in
+    order, and re-inflating what was just deflated was a third of the demo run)."""
+
+    def __init__(self, header_bytes):
+        self.lib = _lib.load()
+        self.u = int(header_bytes)   # inflated offset of the next record
+        self.metas = []
+        self.last_key = -1
+        self.in_order = True
+
+    def feed(self, data):
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        if not len(data):
+            return
+        if self.in_order:
+            a, used = _scan(self.lib, data)
+            if used != len(data):
+                raise ValueError("StreamIndexer.feed: the chunk does not end on a record boundary")
+            k = a["key"]
+            if len(k):
+                if int(k[0]) < self.last_key or np.any(k[1:] < k[:-1]):
+                    self.in_order = False
+                    self.metas = []
+                else:
+                    self.last_key = int(k[-1])
+                    a["ustart"] = self.u + a["off"]
+                    a["uend"] = a["ustart"] + a["len"]
+                    self.metas.append({f: a[f] for f in ("ref", "pos", "end", "flag", "ustart", "uend")})
+        self.u += len(data)
+
+    def finish(self, path, n_refs):
+        """Record count, or -1 (nothing written) when the records were not sorted."""
+        if not self.in_order:
+            return -1
+        c = {k: (np.concatenate([m[k] for m in self.metas]) if self.metas else np.zeros(0, np.int64))
+             for k in ("ref", "pos", "end", "flag", "ustart", "uend")}
+        return _write_bai_for(path, n_refs, c)
+
+
 def index_sorted(path, threads=4):
     """Writes path + ".bai" for a BAM whose records are already in coordinate order (no rewrite).  Returns the record
     count, or -1 -- and writes nothing -- if the records turn out not to be sorted."""
     lib = _lib.load()
     st = _Inflated(path, threads)
     _text, refs, carry = _read_header(st)
-    coff, isz = _block_table(path)
-    ustart_of_block = np.concatenate(([0], np.cumsum(isz)))
     metas = []
     buf = carry
     last_key = -1
@@ -345,22 +407,7 @@ def index_sorted(path, threads=4):
     st.close()
     c = {k: (np.concatenate([m[k] for m in metas]) if metas else np.zeros(0, np.int64))
          for k in ("ref", "pos", "end", "flag", "ustart", "uend")}
-
-    data_blk = np.nonzero(isz > 0)[0]           # empty blocks (EOF markers) hold no positions
-    dstart = ustart_of_block[data_blk]
-    eof_coff = int(coff[-1]) if len(coff) and isz[-1] == 0 else int(os.path.getsize(path))
-
-    def voff(u):
-        u = np.asarray(u, dtype=np.int64)
-        j = np.searchsorted(dstart, u, side="right") - 1
-        j = np.clip(j, 0, max(len(data_blk) - 1, 0))
-        inside = u - dstart[j]
-        at_end = inside >= isz[data_blk[j]]          # the end of the last record: the EOF block
-        return np.where(at_end, np.uint64(eof_coff) << np.uint64(16),
-                        (coff[data_blk[j]].astype(np.uint64) << np.uint64(16)) | inside.astype(np.uint64))
-
-    write_bai(path + ".bai", len(refs), c["ref"], c["pos"], c["end"], c["flag"], voff(c["ustart"]), voff(c["uend"]))
-    return len(c["ref"])
+    return _write_bai_for(path, len(refs), c)
 
 
 class _Run:

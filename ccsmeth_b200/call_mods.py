@@ -210,9 +210,10 @@ def _reader_thread(rd, q):
         q.put(("error", e))
 
 
-def _writer_thread(wr, q, keep_pulse, mod_base_is_c, counts, err):
+def _writer_thread(wr, q, keep_pulse, mod_base_is_c, counts, err, indexer=None):
     """Re-tags and writes the records of finished pieces (reference _worker_write_modbam,
-    call_modifications.py:410-462)."""
+    call_modifications.py:410-462).  `indexer` (bamsort.StreamIndexer) sees the same bytes, so that an output whose
+    records are already in coordinate order gets its .bai without being read back."""
     try:
         while True:
             msg = q.get()
@@ -224,6 +225,8 @@ def _writer_thread(wr, q, keep_pulse, mod_base_is_c, counts, err):
                 mm = ml = None
             data, with_mm = tag_records(piece, recs, keep_pulse, site_begin, mm, ml)
             wr.bg.write(data)
+            if indexer is not None:
+                indexer.feed(data)
             counts[2] += len(recs)
             counts[3] += with_mm
             _tic("tag+write", t0)
@@ -287,7 +290,11 @@ def call_mods(args):
     th.start()
     counts = [0, 0, 0, 0]
     wq, werr = queue.Queue(maxsize=2), []
-    wth = threading.Thread(target=_writer_thread, args=(wr, wq, args.keep_pulse, mod_base_is_c, counts, werr),
+    indexer = None
+    if not args.no_sort and world == 1:
+        from . import bamsort
+        indexer = bamsort.StreamIndexer(wr.header_bytes)
+    wth = threading.Thread(target=_writer_thread, args=(wr, wq, args.keep_pulse, mod_base_is_c, counts, werr, indexer),
                            daemon=True)
     wth.start()
     try:
@@ -316,7 +323,7 @@ def call_mods(args):
     if not args.no_sort:
         # reference call_modifications.py:592-607: samtools sort + index of the modbam unless --no_sort
         t_sort = time.perf_counter()
-        out_modbam = _sort_and_index(args, out_modbam, rank, world, threads)
+        out_modbam = _sort_and_index(args, out_modbam, rank, world, threads, indexer, len(rd.references))
         _tic("sort_index", t_sort)
     if rank == 0:
         dt = time.time() - t0
@@ -328,15 +335,17 @@ def call_mods(args):
     return dict(zip(("sites", "model_batches", "reads_written", "reads_with_mm"), total)), out_modbam
 
 
-def _sort_and_index(args, out_modbam, rank, world, threads):
+def _sort_and_index(args, out_modbam, rank, world, threads, indexer=None, n_refs=0):
     """Coordinate sort + .bai of the output (ccsmeth_b200/bamsort.py).  One rank: in place -- and when the records are
     already in coordinate order (a sorted input keeps its order; an unaligned input has only unplaced reads) only the
-    index is written.  Several ranks (one node): rank 0 merges the sorted shards into <output>.modbam.bam."""
+    index is written, from what the writer thread's StreamIndexer collected (no second pass over the file).  Several
+    ranks (one node): rank 0 merges the sorted shards into <output>.modbam.bam."""
     from . import bamsort
     final = args.output + ".modbam.bam"
     comp = getattr(args, "bam_compress", "rle")
     if world == 1:
-        if bamsort.index_sorted(out_modbam, threads=threads) < 0:
+        done = indexer.finish(out_modbam, n_refs) if indexer is not None else bamsort.index_sorted(out_modbam, threads=threads)
+        if done < 0:
             bamsort.sort_and_index(out_modbam, out_modbam, threads=threads, bam_compress=comp)
         return out_modbam
     parallel.barrier()

@@ -240,3 +240,44 @@ def test_index_only_for_an_already_sorted_bam(tmp_path):
                         if t == tid and p < end and p + rl > beg:
                             found.append(raw)
             assert sorted(found) == brute
+
+
+def test_stream_indexer_matches_index_sorted(tmp_path):
+    """The index built from the bytes the writer emits (no read-back) == the index built by re-reading the file, for
+    every way of cutting the record stream into writes; an out-of-order stream is reported, not indexed."""
+    rng = np.random.default_rng(5)
+    src = str(tmp_path / "in.bam")
+    refs, recs = _make_unsorted(src, rng, n=700)
+    out = str(tmp_path / "sorted.bam")
+    bamsort.sort_and_index(src, out, threads=2)
+    rd = BamReader(out)
+    raws = [struct.pack("<i", len(r.raw)) + r.raw for r in rd]
+    for cut in (1, 13, 250, 10 ** 9):
+        path = str(tmp_path / ("w%d.bam" % min(cut, 9999)))
+        w = BamWriter(path, rd.header_text, rd.references, threads=2)
+        ix = bamsort.StreamIndexer(w.header_bytes)
+        for i in range(0, len(raws), cut):
+            chunk = np.frombuffer(b"".join(raws[i:i + cut]), dtype=np.uint8)
+            w.bg.write(chunk)
+            ix.feed(chunk)
+        w.close()
+        assert ix.finish(path, len(rd.references)) == len(raws)
+        streamed = open(path + ".bai", "rb").read()
+        os.remove(path + ".bai")
+        assert bamsort.index_sorted(path, threads=2) == len(raws)
+        assert open(path + ".bai", "rb").read() == streamed
+    # the unsorted input: reported as such, nothing written
+    rd2 = BamReader(src)
+    w = BamWriter(str(tmp_path / "u.bam"), rd2.header_text, rd2.references, threads=1)
+    ix = bamsort.StreamIndexer(w.header_bytes)
+    for r in rd2:
+        b = np.frombuffer(struct.pack("<i", len(r.raw)) + r.raw, dtype=np.uint8)
+        w.bg.write(b)
+        ix.feed(b)
+    w.close()
+    assert ix.finish(str(tmp_path / "u.bam"), len(rd2.references)) == -1
+    assert not os.path.exists(str(tmp_path / "u.bam") + ".bai")
+    # a write that stops inside a record cannot be indexed
+    ix = bamsort.StreamIndexer(100)
+    with pytest.raises(ValueError):
+        ix.feed(np.frombuffer(raws[0][:-3], dtype=np.uint8))

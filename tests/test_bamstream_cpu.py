@@ -159,3 +159,38 @@ def test_header_only_and_zero_byte_files(tmp_path):
     open(zero, "wb").close()
     with pytest.raises(ValueError):
         BamPieceReader(zero, _filter(_args()))
+
+
+def test_writer_thread_indexes_while_it_writes(tmp_path):
+    """call_mods' writer thread + StreamIndexer + _sort_and_index on the demo pieces (no GPU: the site lists come from the
+    golden): the .bai written without reading the output back == the one index_sorted builds from the file."""
+    import queue
+    import threading
+    from ccsmeth_b200 import bamsort
+    g = load_npz("demo_callmods.npz")
+    rd = BamPieceReader(DEMO, _filter(_args()), threads=2, piece_bytes=1 << 20, align_to=50)
+    out = str(tmp_path / "o.modbam.bam")
+    wr = BamWriter(out, rd.header_text, rd.references, threads=2)
+    ix = bamsort.StreamIndexer(wr.header_bytes)
+    q, counts, err = queue.Queue(), [0, 0, 0, 0], []
+    th = threading.Thread(target=cm._writer_thread, args=(wr, q, False, True, counts, err, ix))
+    th.start()
+    off = k = 0
+    for p in rd:
+        c = g["n_sites_per_read"][k:k + len(p.recs)]
+        sb = np.concatenate(([0], np.cumsum(c))).astype(np.int64)
+        ns = int(sb[-1])
+        q.put((p, p.recs, sb, g["mm"][off:off + ns].astype(np.int32), g["ml"][off:off + ns]))
+        off += ns
+        k += len(p.recs)
+    q.put(None)
+    th.join()
+    assert not err and counts[2] == k
+    wr.close()
+    a = _args(output=str(tmp_path / "o"), no_sort=False)
+    assert cm._sort_and_index(a, out, 0, 1, 2, ix, len(rd.references)) == out
+    streamed = open(out + ".bai", "rb").read()
+    os.remove(out + ".bai")
+    assert bamsort.index_sorted(out, threads=2) == k
+    assert open(out + ".bai", "rb").read() == streamed
+    assert [r.query_name for r in BamReader(out)] == list(g["names"])
