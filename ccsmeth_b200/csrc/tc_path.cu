@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05 / TMEM / TMA bulk-copy) implementation of the attbigru2s forward for sm_100a.
+// Tensor-core (tcgen05 / TMEM / TMA) implementation of the attbigru2s forward for sm_100a.
 //
 // Replaces: reference ccsmeth/models.py:89-150 (ModelAttRNN.forward) + utils/attention.py:48-70.
 //
@@ -24,12 +24,19 @@
 //                 activations [a8 s0 s1][alo8 s0 s1] x 2048 B, weights [Wlo8 s0 s1][W8 s0 s1] x (rows x 16 B).
 //               The K = 11 input of layer 0 keeps the 3-pass fp16 split (weights x S).
 //
-// GRU layer kernel (persistent, one CTA per SM, 384 threads):
-//   warp 0      TMA producer: bulk copies weights + activation K-slabs into a 3-stage ring
-//   warp 1      MMA issuer (one elected thread): D[tmem] += A[smem] . B[smem]^T, N = 192 per instruction
-//   warps 4-11  gate epilogue: tcgen05.ld accumulators -> sigmoid/tanh/blend -> h_t written to the act image
-//   Two row tiles ("slots") share every weight stage; TMEM holds [n_i | r | z | n_h] x 64 units per slot.
-//   h_t goes back to the next step's A operand through the (L2-resident) act image.
+// Kernels in this file (what runs by default: gru_variant()):
+//   tc_prep_kernel        features -> x0 image, h0 -> h0 images
+//   tc_gru_layer_kernel   one launch per GRU layer, persistent; warp roles = TMA producers (one bulk copy per thread and
+//                         stage) | MMA issuer (one elected thread, N = 192 per instruction) | gate epilogue warps
+//                         (tcgen05.ld accumulators -> sigmoid / tanh / blend -> h_t into the act image, which is also how
+//                         h_t reaches the next step's A operand).  Template forms: row tiles per CTA, TMEM buffers,
+//                         epilogue warps, pipelined epilogue, both directions interleaved (IL: the default for layer 0).
+//   tc_gru_pair2_kernel   the same layer on CTA pairs: tcgen05.mma.cta_group::2 (M = 256), each CTA holds half of every
+//                         weight slab, operands by tensor-map loads that complete on the leader's barrier (default for
+//                         layers >= 1)
+//   tc_gru_pair_kernel / tc_gru_duo_kernel / tc_gru_cv_kernel   earlier CTA-pair forms (relay warp) and the on-chip
+//                         operand-conversion form: measured experiments, selectable with CCSM_TC_VARIANT
+//   tc_att_head_kernel    attention scores, online softmax, fc1, softmax: one pass over the last layer's act image
 #include <curand_kernel.h>
 #include <stdio.h>
 #include <stdlib.h>
