@@ -14,6 +14,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libccsm.so")
+HASH_PATH = LIB_PATH + ".srchash"   # sources the library was built from (git-ignored like the library, travels with it)
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -112,6 +113,9 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu into ccsmeth_b200/libccsm.so for sm_100a (cross-compiles without a GPU).
     One nvcc -c per source file (in parallel, objects cached under csrc/build/), then one link."""
     if not force and not _stale():
+        if not os.path.exists(HASH_PATH):  # a library from before the record existed, newer than every source
+            with open(HASH_PATH, "w") as f:
+                f.write(source_hash() + "\n")
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -140,9 +144,19 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as f:  # which sources this binary was built from (checked by load())
+        f.write(source_hash() + "\n")
     if verbose:
         print("".join(e for _, e in done))
     return LIB_PATH
+
+
+def built_from():
+    """Source hash recorded next to the library when it was built, or None (a library from before the record existed)."""
+    try:
+        return open(HASH_PATH).read().strip() or None
+    except OSError:
+        return None
 
 
 _lib = None
@@ -160,6 +174,14 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("%s is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(nvcc, sm_100a). ccsmeth_b200 has no CPU fallback." % LIB_PATH)
+        rec = built_from()
+        if rec is not None and rec != source_hash():
+            # the binary rode along from an older tree (it is git-ignored, mtimes do not survive a copy): never run it
+            try:
+                build(force=True)
+            except Exception as e:
+                raise RuntimeError("%s was built from other sources (recorded %s..., tree %s...) and rebuilding failed: %s"
+                                   % (LIB_PATH, rec[:16], source_hash()[:16], e))
         lib = ctypes.CDLL(LIB_PATH)
         vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
         lib.ccsm_abi_version.restype = ctypes.c_int

@@ -73,3 +73,21 @@ def test_state_dict_contract(ckpt_att2s, ckpt_aggr):
     assert lstm.state_dict()["rnn.weight_ih_l0"].shape == (256, 11) and lstm.get_precision() == "fp32"
     h, c = lstm.init_hidden(5, 2, 64)
     assert h.shape == c.shape == (4, 5, 64)
+
+
+def test_library_is_tied_to_its_sources(tmp_path, monkeypatch):
+    """build() records the hash of the sources next to the library; load() refuses to run a binary that was built from
+    other sources (it rebuilds; if that fails the error names both hashes)."""
+    from ccsmeth_b200 import _lib as L
+    assert L.built_from() == L.source_hash()
+    # a stale record + no working compiler -> a loud error, not a silently stale binary
+    stale = str(tmp_path / "libccsm.so.srchash")
+    open(stale, "w").write("0" * 64 + "\n")
+    monkeypatch.setattr(L, "HASH_PATH", stale)
+    monkeypatch.setattr(L, "_lib", None)
+
+    def no_build(force=False, verbose=False):
+        raise RuntimeError("nvcc unavailable (test)")
+    monkeypatch.setattr(L, "build", no_build)
+    with pytest.raises(RuntimeError, match="built from other sources"):
+        L.load()
